@@ -1,0 +1,144 @@
+"""Deterministic synthetic checkpoints (no real ``model.pt`` / ``model3.pt`` is available offline).
+
+Every tensor is drawn from a CPU generator seeded by ``crc32(key) ^ seed`` so that the
+reference (in the build container), the oracle and the CUDA engine (on the GPU box) all
+load bit-identical weights without shipping a 1 GB file.  BatchNorm running statistics use
+per-layer scalars measured once with the oracle (tools/calibrate_bn.py ->
+data/bn_calibration_<size>.json) plus seeded per-channel jitter: random-init eval-mode
+activations are otherwise badly scaled and no box would survive the
+post-processing thresholds of process_ocr_base.py:524-529.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import zlib
+from typing import Dict, Optional
+
+import torch
+
+from . import arch
+
+_DATA = os.path.join(os.path.dirname(__file__), "data")
+
+
+def _gen(key: str, seed: int) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed((zlib.crc32(key.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+    return g
+
+
+def bn_running_stats(key_prefix: str, c: int, m: float, v: float, seed: int):
+    """Per-channel running_mean / running_var from per-layer scalars (m, v) + seeded jitter."""
+    g = _gen(key_prefix + ".stats", seed)
+    mean = m + 0.1 * math.sqrt(max(v, 1e-12)) * torch.randn(c, generator=g)
+    var = v * (0.75 + 0.5 * torch.rand(c, generator=g))
+    return mean.float(), var.float().clamp_min(1e-8)
+
+
+def _draw(spec: arch.ParamSpec, seed: int) -> torch.Tensor:
+    g = _gen(spec.key, seed)
+    k, shape = spec.kind, spec.shape
+    if k in ("conv", "dwconv", "linear"):
+        gain = 3.3 if spec.key.endswith("top_conv.0.weight") else 1.0   # un-normalised head outputs: std ~1.5
+        return torch.randn(shape, generator=g) * (gain / math.sqrt(max(spec.fan_in, 1)))
+    if k == "bn_w":
+        return 0.8 + 0.4 * torch.rand(shape, generator=g)
+    if k == "bn_b":
+        return 0.2 * torch.randn(shape, generator=g)
+    if k == "bn_mean":
+        return torch.zeros(shape)
+    if k == "bn_var":
+        return torch.ones(shape)
+    if k == "bn_count":
+        return torch.tensor(1, dtype=torch.long)
+    if k == "bias":
+        return 0.1 * torch.randn(shape, generator=g)
+    if k == "embed":
+        return torch.randn(shape, generator=g)
+    if k == "ln_w":
+        return 0.9 + 0.2 * torch.rand(shape, generator=g)
+    if k == "ln_b":
+        return 0.05 * torch.randn(shape, generator=g)
+    if k == "posenc":
+        # sinusoid init (models/transformer.py:27-42) + small seeded perturbation (the table is learnable)
+        max_len, d = shape
+        pos = torch.arange(0, max_len).float().unsqueeze(1)
+        _2i = torch.arange(0, d, step=2).float()
+        enc = torch.zeros(max_len, d)
+        enc[:, 0::2] = torch.sin(pos / (10000 ** (_2i / d)))
+        enc[:, 1::2] = torch.cos(pos / (10000 ** (_2i / d)))
+        return enc + 0.02 * torch.randn(shape, generator=g)
+    raise ValueError(k)
+
+
+def load_bn_calibration(model_size: str = "xl") -> Optional[Dict[str, list]]:
+    path = os.path.join(_DATA, f"bn_calibration_{model_size}.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
+
+
+def detector_state_dict(seed: int = 0, model_size: str = "xl", calibration="auto") -> Dict[str, torch.Tensor]:
+    """Synthetic ``TextDetectorModel.state_dict()`` (fp32, CPU)."""
+    if calibration == "auto":
+        calibration = load_bn_calibration(model_size)
+    sd: Dict[str, torch.Tensor] = {}
+    for spec in arch.text_detector_specs(model_size):
+        sd[spec.key] = _draw(spec, seed)
+    # head output biases chosen so that the post-processing path is exercised:
+    # a few hundred peaks per tile above cut_off=0.4, decoded w/h of a few tens of pixels.
+    sd["detector.keyheatmap.top_conv.0.bias"] = torch.tensor([-2.5])
+    sd["detector.sizes.top_conv.0.bias"] = torch.tensor([-0.47, -0.30])
+    if calibration:
+        for prefix, (m, v) in calibration.items():
+            c = sd[prefix + ".running_mean"].numel()
+            mean, var = bn_running_stats(prefix, c, float(m), float(v), seed)
+            sd[prefix + ".running_mean"] = mean
+            sd[prefix + ".running_var"] = var
+    return sd
+
+
+def transformer_state_dict(seed: int = 0, **dims) -> Dict[str, torch.Tensor]:
+    """Synthetic ``Transformer.state_dict()`` for ``ModelDimensions(**dims)`` (fp32, CPU)."""
+    sd: Dict[str, torch.Tensor] = {}
+    for spec in arch.transformer_specs(**dims):
+        sd[spec.key] = _draw(spec, seed)
+    return sd
+
+
+def detector_input(batch: int, seed: int = 0, kind: str = "rand") -> torch.Tensor:
+    """Seeded ``[B,3,768,768]`` fp32 image batch in [0,1] (models/detector.py:218 input domain)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    if kind == "rand":
+        return torch.rand(batch, 3, arch.HEIGHT, arch.WIDTH, generator=g)
+    if kind == "text":
+        # white page with dark glyph-like rectangles (SURVEY.md 8d config 2/5 "text-like" variant)
+        x = torch.ones(batch, 3, arch.HEIGHT, arch.WIDTH)
+        for b in range(batch):
+            n = 120
+            cx = torch.randint(16, arch.WIDTH - 16, (n,), generator=g)
+            cy = torch.randint(16, arch.HEIGHT - 16, (n,), generator=g)
+            w = torch.randint(3, 14, (n,), generator=g)
+            h = torch.randint(3, 14, (n,), generator=g)
+            v = 0.3 * torch.rand(n, generator=g)
+            for i in range(n):
+                x[b, :, cy[i] - h[i]:cy[i] + h[i], cx[i] - w[i]:cx[i] + w[i]] = v[i]
+        return x + 0.02 * torch.rand(x.shape, generator=g) - 0.02
+    raise ValueError(kind)
+
+
+def transformer_inputs(batch: int, enc_len: int, dec_len: int, seed: int = 0):
+    """Seeded encoder features / decoder codes."""
+    g = torch.Generator().manual_seed(2000 + seed)
+    enc = 5.0 * torch.randn(batch, enc_len, arch.ENCODER_DIM, generator=g)
+    lens = torch.randint(max(2, enc_len // 5), enc_len + 1, (batch,), generator=g)
+    for b in range(batch):
+        enc[b, int(lens[b]):] = 0
+    dec = torch.randint(0, 0x3FFFF, (batch, dec_len), generator=g)
+    msk = torch.rand(batch, dec_len, generator=g) < 0.5
+    dec[msk] = arch.DECODER_MSK
+    dec[:, 0] = arch.DECODER_SOT
+    return enc, dec, lens

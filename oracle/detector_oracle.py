@@ -1,0 +1,207 @@
+"""ORACLE — test infrastructure only (never imported by the product path).
+
+CPU fp32 restatement of the reference detector hot path as plain functional torch ops over
+a ``state_dict`` (no nn.Module, no torchvision):
+
+  * ``detection_forward``   <- models/detector.py:217-230 (CenterNetDetection.forward),
+                               :139-146 (BackboneModel.forward), :192-201 (Leafmap.forward),
+                               torchvision models/efficientnet.py:105-231 (MBConv / FusedMBConv),
+                               ops/misc.py:225-261 (SqueezeExcitation)
+  * ``detector_forward``    <- models/detector.py:289-296 (CenterNetDetector.forward)
+  * ``simple_decoder``      <- models/detector.py:232-254
+  * ``text_detector_forward`` / ``get_fmask`` <- models/detector.py:262-281
+  * ``decode_tile``         <- process_ocr_base.py:498-538 (per-tile peak sort + box decode)
+
+Pinned against the unmodified reference by tests/golden/*.npz (made by
+oracle/make_golden.py, which imports /root/reference in the build container).  The
+reference owns no golden vectors of its own -> the pin is
+"reference-run-here", not "reference-owned".
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from findtextcenternet_b200 import arch
+
+
+def _bn(sd, p, x, eps, calib=None, seed=0):
+    if calib is not None:
+        # sequential eval-mode calibration: measure this layer's input, write its running stats
+        from findtextcenternet_b200.synthetic import bn_running_stats
+        m = float(x.mean())
+        v = float(x.var())
+        calib[p] = [m, v]
+        mean, var = bn_running_stats(p, x.shape[1], m, v, seed)
+        sd[p + ".running_mean"], sd[p + ".running_var"] = mean, var
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"],
+                        sd[p + ".weight"], sd[p + ".bias"], False, 0.0, eps)
+
+
+def _conv_bn_act(sd, p, x, stride=1, groups=1, act=True, calib=None, seed=0):
+    w = sd[p + ".0.weight"]
+    x = F.conv2d(x, w, None, stride, (w.shape[-1] - 1) // 2, 1, groups)
+    x = _bn(sd, p + ".1", x, arch.BACKBONE_BN_EPS, calib, seed)
+    return F.silu(x) if act else x
+
+
+def backbone_forward(sd, x, prefix="detector.backbone.features", model_size="xl", calib=None, seed=0):
+    """-> [x1, x2, x3, x4] taps (after features[2], [3], [5], last)."""
+    stem, stages, last = arch.backbone_cfg(model_size)
+    taps = []
+    x = _conv_bn_act(sd, f"{prefix}.0", x, stride=2, calib=calib, seed=seed)
+    for si, st in enumerate(stages, start=1):
+        for li in range(st.layers):
+            cin = st.cin if li == 0 else st.cout
+            stride = st.stride if li == 0 else 1
+            exp = cin * st.expand
+            p = f"{prefix}.{si}.{li}.block"
+            res = stride == 1 and cin == st.cout
+            if st.fused:
+                if exp != cin:
+                    y = _conv_bn_act(sd, p + ".0", x, stride, calib=calib, seed=seed)
+                    y = _conv_bn_act(sd, p + ".1", y, act=False, calib=calib, seed=seed)
+                else:
+                    y = _conv_bn_act(sd, p + ".0", x, stride, calib=calib, seed=seed)
+            else:
+                y = _conv_bn_act(sd, p + ".0", x, calib=calib, seed=seed)
+                y = _conv_bn_act(sd, p + ".1", y, stride, groups=exp, calib=calib, seed=seed)
+                s = y.mean((2, 3), keepdim=True)
+                s = F.silu(F.conv2d(s, sd[p + ".2.fc1.weight"], sd[p + ".2.fc1.bias"]))
+                s = torch.sigmoid(F.conv2d(s, sd[p + ".2.fc2.weight"], sd[p + ".2.fc2.bias"]))
+                y = y * s
+                y = _conv_bn_act(sd, p + ".3", y, act=False, calib=calib, seed=seed)
+            x = y + x if res else y       # eval mode: StochasticDepth is the identity
+        if si in arch.TAP_FEATURE_IDX:
+            taps.append(x)
+    x = _conv_bn_act(sd, f"{prefix}.{len(stages) + 1}", x, calib=calib, seed=seed)
+    taps.append(x)
+    return taps
+
+
+def leafmap_forward(sd, p, taps, calib=None, seed=0):
+    y = None
+    n = len(taps)
+    for i in range(n):
+        x = taps[n - 1 - i]
+        x = _bn(sd, f"{p}.in_bn.{n - 1 - i}", x, arch.HEAD_BN_EPS, calib, seed)
+        if y is not None:
+            x = torch.cat([y, x], dim=1)
+        y = F.conv2d(x, sd[f"{p}.upsamplers.{i}.0.weight"], None, 1, 1)
+        y = _bn(sd, f"{p}.upsamplers.{i}.1", y, arch.HEAD_BN_EPS, calib, seed)
+        y = F.gelu(y)
+        if i < n - 1:
+            y = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True)
+    return F.conv2d(y, sd[p + ".top_conv.0.weight"], sd[p + ".top_conv.0.bias"], 1, 1)
+
+
+def detection_forward(sd, x, prefix="detector", model_size="xl", calib=None, seed=0):
+    """x [B,3,768,768] in [0,1] -> (heatmap [B,9,192,192], feature [B,100,192,192])."""
+    x = x * 2 - 1
+    taps = backbone_forward(sd, x, prefix + ".backbone.features", model_size, calib, seed)
+    outs = [leafmap_forward(sd, f"{prefix}.{name}", taps, calib, seed) for name, _ in arch.HEADS]
+    return torch.cat(outs[:-1], dim=1), outs[-1]
+
+
+def peak_pick(heatmap):
+    """heatmap [B,9,H,W] -> [B,10,H,W] with channel 1 = key if 3x3 local max else -inf."""
+    keymap = heatmap[:, 0:1]
+    lp = F.pad(keymap, (1, 1, 1, 1), value=float("-inf"))
+    lp = F.max_pool2d(lp, kernel_size=3, stride=1)
+    det = torch.where(keymap < lp, torch.tensor(float("-inf"), dtype=keymap.dtype), keymap)
+    return torch.cat([keymap, det, heatmap[:, 1:]], dim=1)
+
+
+def detector_forward(sd, x, prefix="detector", model_size="xl"):
+    with torch.no_grad():
+        heat, feat = detection_forward(sd, x, prefix, model_size)
+        return peak_pick(heat), feat
+
+
+def simple_decoder(sd, x, prefix="decoder", calib=None, seed=0):
+    outs = []
+    for i in range(len(arch.MODULO_LIST)):
+        p = f"{prefix}.blocks.{i}"
+        y = F.linear(x, sd[p + ".0.weight"])
+        y = F.gelu(_bn1d(sd, p + ".1", y, calib, seed))
+        y = F.linear(y, sd[p + ".3.weight"])
+        y = F.gelu(_bn1d(sd, p + ".4", y, calib, seed))
+        outs.append(F.linear(y, sd[p + ".6.weight"], sd[p + ".6.bias"]))
+    return outs
+
+
+def _bn1d(sd, p, x, calib=None, seed=0):
+    if calib is not None:
+        from findtextcenternet_b200.synthetic import bn_running_stats
+        m, v = float(x.mean()), float(x.var())
+        calib[p] = [m, v]
+        sd[p + ".running_mean"], sd[p + ".running_var"] = bn_running_stats(p, x.shape[1], m, v, seed)
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        False, 0.0, arch.HEAD_BN_EPS)
+
+
+def get_fmask(labelmap0: torch.Tensor) -> torch.Tensor:
+    """labelmap [B,C,H,W] -> bool [B*H*W], top 1024*B of channel 0 (models/detector.py:270-281)."""
+    b = labelmap0.shape[0]
+    flat = labelmap0[:, 0].flatten()
+    idx = torch.argsort(flat, descending=True)
+    mask = torch.zeros_like(idx, dtype=torch.bool)
+    mask[idx[:1024 * b]] = True
+    return mask
+
+
+def text_detector_forward(sd, x, fmask, model_size="xl", calib=None, seed=0):
+    heat, feat = detection_forward(sd, x, "detector", model_size, calib, seed)
+    f = feat.permute(0, 2, 3, 1).flatten(0, -2)
+    return heat, simple_decoder(sd, f[fmask], "decoder", calib, seed)
+
+
+# ----------------------------------------------------------------------------------------------
+# host-side per-tile decode (numpy), process_ocr_base.py:498-538
+
+def np_sigmoid(x):
+    return (np.tanh(x / 2) + 1) / 2      # util_func.py:14
+
+
+def tile_mask(x_i, y_i, img_w, img_h, step_ratio=0.6):
+    """Centre-crop validity mask of one 192x192 tile (process_ocr_base.py:498-503)."""
+    x_s, y_s = arch.WIDTH // arch.SCALE, arch.HEIGHT // arch.SCALE
+    mask = np.zeros([y_s, x_s], dtype=bool)
+    x_min = int(x_s * (1 - step_ratio) / 2) if x_i > 0 else 0
+    x_max = int(x_s * (1 - (1 - step_ratio) / 2)) + 1 if x_i + arch.WIDTH < img_w else x_s
+    y_min = int(y_s * (1 - step_ratio) / 2) if y_i > 0 else 0
+    y_max = int(y_s * (1 - (1 - step_ratio) / 2)) + 1 if y_i + arch.HEIGHT < img_h else y_s
+    mask[y_min:y_max, x_min:x_max] = True
+    return mask
+
+
+def decode_tile(heatmap10: np.ndarray, features: np.ndarray, x_i=0, y_i=0, img_w=arch.WIDTH, img_h=arch.HEIGHT,
+                cut_off=0.4, step_ratio=0.6):
+    """One tile's peaks -> (locations [n,9] float64, glyphfeatures [n,100] float32), in descending-score
+    order with ties broken by flat index (the reference uses an unstable argsort; compare as sets)."""
+    mask = tile_mask(x_i, y_i, img_w, img_h, step_ratio)
+    code_p = [np_sigmoid(heatmap10[6 + k]) for k in range(4)]
+    peak = np_sigmoid(heatmap10[1]) * mask
+    order = np.lexsort((np.arange(peak.size), -peak.ravel()))
+    locs, feats = [], []
+    for idx in order:
+        y, x = divmod(int(idx), peak.shape[1])
+        if peak[y, x] < cut_off:
+            break
+        w = np.exp(heatmap10[2, y, x] - 3) * 1024
+        h = np.exp(heatmap10[3, y, x] - 3) * 1024
+        if w <= 0 or h <= 0:
+            continue
+        if w > img_w or h > img_h:
+            continue
+        ix = x * arch.SCALE + x_i
+        iy = y * arch.SCALE + y_i
+        locs.append(np.array([peak[y, x], ix, iy, w, h, *[c[y, x] for c in code_p]]))
+        feats.append(features[:, y, x])
+    if not locs:
+        return np.zeros([0, 9]), np.zeros([0, arch.FEATURE_DIM], dtype=np.float32)
+    return np.array(locs), np.array(feats)

@@ -1,0 +1,182 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference)
+on the synthetic checkpoints.  Runs only in the build container (the GPU box has no
+/root/reference); the outputs are committed.  Usage:  python oracle/make_golden.py [detector|transformer|all]
+"""
+import io
+import os
+import sys
+import contextlib
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from findtextcenternet_b200 import arch, synthetic  # noqa: E402
+
+
+def load_test1_tile():
+    """img/test1.png -> the single padded 768x768 tile exactly as call_OCR builds it
+    (process_ocr_base.py:58-76).  Returns uint8 [768,768,3]."""
+    from PIL import Image
+    im0 = np.asarray(Image.open(os.path.join(REF, "img", "test1.png")).convert("RGB"))
+    stepx = stepy = int(768 * 0.6)
+    padx = max(0, (768 - im0.shape[1]) % stepx, 768 - im0.shape[1])
+    pady = max(0, (768 - im0.shape[0]) % stepy, 768 - im0.shape[0])
+    im0 = np.pad(im0, [[0, pady], [0, padx], [0, 0]], "constant", constant_values=255)
+    assert im0.shape == (768, 768, 3), im0.shape
+    return im0
+
+
+def golden_detector():
+    from models.detector import TextDetectorModel, CenterNetDetector
+    from process_ocr_base import OCR_Processer
+
+    sd = synthetic.detector_state_dict(0)
+    model = TextDetectorModel(pre_weights=False)
+    ref_keys = [(k, list(v.shape)) for k, v in model.state_dict().items()]
+    missing = model.load_state_dict(sd, strict=True)
+    print("load_state_dict:", missing)
+    det = CenterNetDetector(model.detector).eval()
+
+    tile = load_test1_tile()
+    np.savez_compressed(os.path.join(GOLD, "test1_tile.npz"), tile=tile)
+    inputs = {
+        "rand0": synthetic.detector_input(1, 0, "rand"),
+        "test1": torch.from_numpy(tile.astype(np.float32)[None] / 255.).permute(0, 3, 1, 2).float(),
+    }
+    out = {}
+    with torch.no_grad():
+        for name, x in inputs.items():
+            h10, feat = det(x)
+            h10, feat = h10.numpy(), feat.numpy()
+            pk = np.isfinite(h10[0, 1])
+            out[name + "_heatmap10"] = h10[0]
+            out[name + "_feat_s8"] = feat[0, :, ::8, ::8].copy()
+            ys, xs = np.nonzero(pk & (h10[0, 1] > -1.0))
+            out[name + "_feat_at_peaks_yx"] = np.stack([ys, xs], 1).astype(np.int32)
+            out[name + "_feat_at_peaks"] = feat[0][:, ys, xs].T.copy()
+            out[name + "_feat_sum"] = np.array([feat.astype(np.float64).sum(), np.abs(feat).astype(np.float64).sum()])
+            print(name, "peaks finite", int(pk.sum()), "kept", len(ys))
+
+    # reference run_detector on the single-tile test1 page and on the rand0 "page"
+    class RefProc(OCR_Processer):
+        def call_detector(self, image_input):
+            images = torch.from_numpy(image_input / 255.).permute(0, 3, 1, 2).float()
+            with torch.no_grad():
+                h, f = det(images)
+            return h.numpy(), f.numpy()
+
+        def call_transformer(self, encoder_input):
+            raise NotImplementedError
+
+    proc = RefProc()
+    for name, x in inputs.items():
+        im = (x[0].permute(1, 2, 0).numpy() * 255.).astype(np.float32)
+        ds0 = [{"input": im[None], "offsetx": 0, "offsety": 0}]
+        with contextlib.redirect_stdout(io.StringIO()):
+            loc, gf, lines, seps = proc.run_detector(ds0, im)
+        out[name + "_locations"] = loc
+        out[name + "_glyphfeatures"] = gf
+        out[name + "_lines_s4"] = lines[::4, ::4].copy()
+        out[name + "_seps_s4"] = seps[::4, ::4].copy()
+        print(name, "run_detector boxes", loc.shape)
+
+    # train-path pieces: get_fmask + SimpleDecoder (TextDetectorModel.forward), eval mode
+    model.eval()
+    g = torch.Generator().manual_seed(7)
+    label = torch.rand(1, 5, 192, 192, generator=g)
+    fmask = model.get_fmask(label, None)
+    with torch.no_grad():
+        heat, dec = model(inputs["rand0"], fmask)
+    out["rand0_fmask_idx"] = torch.nonzero(fmask)[:, 0].numpy().astype(np.int32)
+    for i, d in enumerate(dec):
+        out[f"rand0_decoder{i}_s16"] = d.numpy()[::16].copy()
+    np.savez_compressed(os.path.join(GOLD, "detector_xl_seed0.npz"), **out)
+    import json
+    with open(os.path.join(GOLD, "detector_state_keys.json"), "w") as f:
+        json.dump(ref_keys, f)
+    print("detector goldens written")
+
+
+TRANSFORMER_CFGS = {
+    # name: (dims, batch, predictor max_decoderlen)
+    "tiny": (dict(embed_dim=64, head_num=4, enc_block_num=2, dec_block_num=2, max_enc_seq_len=24, max_dec_seq_len=24), 3),
+    "cfg4": (dict(embed_dim=512, head_num=16, enc_block_num=16, dec_block_num=16, max_enc_seq_len=100, max_dec_seq_len=100), 2),
+    "default": (dict(), 1),
+}
+
+
+def golden_transformer():
+    import models.transformer as T
+    import json
+    out = {}
+    keys = {}
+    for name, (dims, batch) in TRANSFORMER_CFGS.items():
+        cfg = T.ModelDimensions(**dims)
+        model = T.Transformer(**cfg.__dict__).eval()
+        keys[name] = [(k, list(v.shape)) for k, v in model.state_dict().items()]
+        sd = synthetic.transformer_state_dict(0, **cfg.__dict__)
+        model.load_state_dict(sd, strict=True)
+        le, ld = cfg.max_enc_seq_len, cfg.max_dec_seq_len
+        enc, dec, lens = synthetic.transformer_inputs(batch, le, ld, seed=0)
+        with torch.no_grad():
+            logits = model(enc, dec)
+        for i, lg in enumerate(logits):
+            lg = lg.numpy()
+            out[f"{name}_logits{i}_s"] = lg[:, ::max(1, ld // 8)].copy()      # 8-ish positions, all classes
+            out[f"{name}_argmax{i}"] = lg.argmax(-1).astype(np.int32)
+            out[f"{name}_lse{i}"] = torch.logsumexp(torch.from_numpy(lg), -1).numpy()
+        # predictor (hard-codes const.max_decoderlen at models/transformer.py:278 -> patch the module global)
+        old = T.max_decoderlen
+        T.max_decoderlen = ld
+        pred = T.TransformerPredictor(model.encoder, model.decoder).eval()
+        buf = io.StringIO()
+        with torch.no_grad(), contextlib.redirect_stdout(buf):
+            ids = pred(enc)
+        T.max_decoderlen = old
+        out[f"{name}_pred_ids"] = ids.numpy()
+        out[f"{name}_pred_log"] = np.array(buf.getvalue())
+        print(name, "logits ok; predictor:", buf.getvalue().strip() or "(8 passes)", ids[0, :8].tolist())
+        if name == "tiny":
+            # early-exit variants: bias the three output heads towards the residues of U+3042 so that the
+            # candidate probability is ~1 ("early stop") or ~0.95 ("no remask stop"), models/transformer.py:326,356
+            for vname, boost in (("peaked", 20.0), ("medium", 10.5)):
+                sd2 = dict(sd)
+                for i, m in enumerate(arch.MODULO_LIST):
+                    bias = sd[f"decoder.out_layers.{i}.bias"].clone()
+                    bias[0x3042 % m] += boost
+                    sd2[f"decoder.out_layers.{i}.bias"] = bias
+                model.load_state_dict(sd2, strict=True)
+                T.max_decoderlen = ld
+                buf = io.StringIO()
+                with torch.no_grad(), contextlib.redirect_stdout(buf):
+                    ids = T.TransformerPredictor(model.encoder, model.decoder).eval()(enc)
+                T.max_decoderlen = old
+                out[f"tiny_{vname}_pred_ids"] = ids.numpy()
+                out[f"tiny_{vname}_pred_log"] = np.array(buf.getvalue())
+                print("  variant", vname, buf.getvalue().strip(), ids[0, :4].tolist())
+    # CRT golden: calc_predid on a seeded batch
+    from util_func import calc_predid
+    g = torch.Generator().manual_seed(5)
+    b = [torch.randint(0, m, (4096,), generator=g) for m in arch.MODULO_LIST]
+    out["crt_in"] = torch.stack(b).numpy()
+    out["crt_out"] = calc_predid(*b).numpy()
+    np.savez_compressed(os.path.join(GOLD, "transformer_seed0.npz"), **out)
+    with open(os.path.join(GOLD, "transformer_state_keys.json"), "w") as f:
+        json.dump(keys, f)
+    print("transformer goldens written")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    if what in ("detector", "all"):
+        golden_detector()
+    if what in ("transformer", "all"):
+        golden_transformer()

@@ -1,0 +1,122 @@
+"""CPU: the oracle restatement vs golden vectors produced by the unmodified reference
+(oracle/make_golden.py).  This is the pin that lets the GPU parity tests trust the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_l2
+from findtextcenternet_b200 import arch, synthetic
+from oracle import detector_oracle as DO
+from oracle import transformer_oracle as TO
+
+
+def test_detector_state_keys_match_reference():
+    with open(os.path.join(GOLDEN, "detector_state_keys.json")) as f:
+        ref = [(k, tuple(s)) for k, s in json.load(f)]
+    ours = [(s.key, tuple(s.shape)) for s in arch.text_detector_specs("xl")]
+    assert len(ref) == 2444
+    assert ours == ref
+
+
+def test_transformer_state_keys_match_reference():
+    from oracle.make_golden import TRANSFORMER_CFGS
+    with open(os.path.join(GOLDEN, "transformer_state_keys.json")) as f:
+        ref = json.load(f)
+    for name, (dims, _) in TRANSFORMER_CFGS.items():
+        ours = [(s.key, list(s.shape)) for s in arch.transformer_specs(**dims)]
+        assert ours == [(k, s) for k, s in ref[name]], name
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", ["rand0", "test1"])
+def test_detector_oracle_matches_reference(name, golden_detector, test1_tile, detector_sd):
+    g = golden_detector
+    if name == "rand0":
+        x = synthetic.detector_input(1, 0, "rand")
+    else:
+        x = torch.from_numpy(test1_tile.astype(np.float32)[None] / 255.).permute(0, 3, 1, 2).float()
+    h10, feat = DO.detector_forward(detector_sd, x)
+    h10, feat = h10.numpy()[0], feat.numpy()[0]
+    ref = g[name + "_heatmap10"]
+    # peak channel: identical -inf pattern (exact index parity), values to fp32 round-off
+    assert np.array_equal(np.isfinite(h10[1]), np.isfinite(ref[1]))
+    fin = np.isfinite(ref[1])
+    assert rel_l2(h10[1][fin], ref[1][fin]) < 1e-5
+    other = [0] + list(range(2, 10))
+    assert rel_l2(h10[other], ref[other]) < 1e-5
+    assert rel_l2(feat[:, ::8, ::8], g[name + "_feat_s8"]) < 1e-5
+    yx = g[name + "_feat_at_peaks_yx"]
+    assert rel_l2(feat[:, yx[:, 0], yx[:, 1]].T, g[name + "_feat_at_peaks"]) < 1e-5
+    # per-tile decode (pre-NMS) must contain every box the reference's run_detector kept
+    loc, gf = DO.decode_tile(h10, feat)
+    ref_loc = g[name + "_locations"]
+    keys = {(int(l[1]), int(l[2])): i for i, l in enumerate(loc)}
+    for r, rf in zip(ref_loc, g[name + "_glyphfeatures"]):
+        i = keys[(int(r[1]), int(r[2]))]
+        np.testing.assert_allclose(loc[i][:5], r[:5], rtol=1e-4)
+        np.testing.assert_allclose(gf[i], rf, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.slow
+def test_simple_decoder_and_fmask_match_reference(golden_detector, detector_sd):
+    g = golden_detector
+    gen = torch.Generator().manual_seed(7)
+    label = torch.rand(1, 5, 192, 192, generator=gen)
+    fmask = DO.get_fmask(label)
+    assert np.array_equal(torch.nonzero(fmask)[:, 0].numpy(), g["rand0_fmask_idx"])
+    with torch.no_grad():
+        _, dec = DO.text_detector_forward(detector_sd, synthetic.detector_input(1, 0, "rand"), fmask)
+    for i, d in enumerate(dec):
+        assert rel_l2(d.numpy()[::16], g[f"rand0_decoder{i}_s16"]) < 1e-5
+
+
+def test_crt_matches_reference(golden_transformer):
+    g = golden_transformer
+    b = g["crt_in"]
+    assert np.array_equal(TO.calc_predid_np(b[0], b[1], b[2]), g["crt_out"])
+    # exhaustive identity on a range of code points
+    x = np.arange(0, 0x40000, 7, dtype=np.int64)
+    assert np.array_equal(TO.calc_predid_np(x % 1091, x % 1093, x % 1097), x)
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg4", "default"])
+def test_transformer_oracle_matches_reference(name, golden_transformer):
+    if name == "default":
+        pytest.importorskip("torch")
+    from oracle.make_golden import TRANSFORMER_CFGS
+    g = golden_transformer
+    dims, batch = TRANSFORMER_CFGS[name]
+    full = dict(enc_input_dim=arch.ENCODER_DIM, embed_dim=768, head_num=12, enc_block_num=10, dec_block_num=10,
+                max_enc_seq_len=400, max_dec_seq_len=400)
+    full.update(dims)
+    sd = synthetic.transformer_state_dict(0, **dims)
+    enc, dec, _ = synthetic.transformer_inputs(batch, full["max_enc_seq_len"], full["max_dec_seq_len"], 0)
+    logits = TO.transformer_forward(sd, full["head_num"], enc, dec)
+    ld = full["max_dec_seq_len"]
+    for i, lg in enumerate(logits):
+        lg = lg.numpy()
+        assert rel_l2(lg[:, ::max(1, ld // 8)], g[f"{name}_logits{i}_s"]) < 2e-5
+        assert rel_l2(torch.logsumexp(torch.from_numpy(lg), -1).numpy(), g[f"{name}_lse{i}"]) < 2e-5
+    if name != "default":
+        ids = TO.predictor_forward(sd, full["head_num"], enc, max_decoderlen=ld)
+        assert np.array_equal(ids.numpy(), g[f"{name}_pred_ids"])
+
+
+@pytest.mark.parametrize("variant,boost", [("peaked", 20.0), ("medium", 10.5)])
+def test_predictor_early_exit_variants(variant, boost, golden_transformer):
+    from oracle.make_golden import TRANSFORMER_CFGS
+    dims, batch = TRANSFORMER_CFGS["tiny"]
+    sd = synthetic.transformer_state_dict(0, **dims)
+    for i, m in enumerate(arch.MODULO_LIST):
+        b = sd[f"decoder.out_layers.{i}.bias"].clone()
+        b[0x3042 % m] += boost
+        sd[f"decoder.out_layers.{i}.bias"] = b
+    enc, _, _ = synthetic.transformer_inputs(batch, 24, 24, 0)
+    trace = []
+    ids = TO.predictor_forward(sd, dims["head_num"], enc, max_decoderlen=24, trace=trace)
+    assert np.array_equal(ids.numpy(), golden_transformer[f"tiny_{variant}_pred_ids"])
+    if variant == "peaked":
+        assert len(trace) == 1   # "[0 early stop]"
