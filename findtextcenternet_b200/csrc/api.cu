@@ -1,0 +1,134 @@
+// C-ABI plumbing (error text, launch counter, version) and the single-op entry points of include/ftc_b200.h.
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/ftc_b200.h"
+#include "conv_gemm.cuh"
+#include "detector_ops.cuh"
+
+namespace ftc {
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+std::vector<uint32_t> make_ktab(int CA, int CB, int ksize, int* Kout) {
+  int taps = ksize * ksize;
+  int kreal = taps * (CA + CB);
+  int K = (kreal + KBLOCK - 1) / KBLOCK * KBLOCK;
+  std::vector<uint32_t> t(K / KCHUNK, 0u);
+  for (int kc = 0; kc < kreal / KCHUNK; ++kc) {
+    int k = kc * KCHUNK;
+    if (k < taps * CA) {
+      int tap = k / CA, c = k % CA;
+      t[kc] = kt_make(false, tap / ksize, tap % ksize, c);
+    } else {
+      int k2 = k - taps * CA;
+      int tap = k2 / CB, c = k2 % CB;
+      t[kc] = kt_make(true, tap / ksize, tap % ksize, c);
+    }
+  }
+  *Kout = K;
+  return t;
+}
+
+}  // namespace ftc
+
+using namespace ftc;
+
+extern "C" {
+
+int ftc_version(void) { return 100; }
+const char* ftc_last_error(void) { return g_err.c_str(); }
+int64_t ftc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ftc_peak_decode(const float* heat9, const float* feat, int batch, int h, int w, int feat_ch, const int* tile_meta,
+                    float cut_off, float page_w, float page_h, int max_peaks, int* count, float* loc, float* gfeat,
+                    void* scratch, void* stream) {
+  FTC_REQUIRE(heat9 && feat && tile_meta && count && loc && gfeat && scratch && batch > 0, "bad argument");
+  return peak_decode(heat9, feat, batch, h, w, feat_ch, tile_meta, cut_off, page_w, page_h, max_peaks, count, loc, gfeat,
+                     scratch, (cudaStream_t)stream);
+}
+
+int ftc_peak_pick(const float* heat9, float* heat10, int batch, int h, int w, void* stream) {
+  FTC_REQUIRE(heat9 && heat10 && batch > 0, "bad argument");
+  return peak_pick(heat9, heat10, batch, h, w, (cudaStream_t)stream);
+}
+
+size_t ftc_op_conv2d_wpack_bytes(int cin, int cout, int ksize) {
+  int K = 0;
+  std::vector<uint32_t> kt = make_ktab(cin, 0, ksize, &K);
+  int npad = (cout + 15) / 16 * 16;
+  return align_up((size_t)npad * K * 4, 256) + align_up(kt.size() * 4, 256) + 256;
+}
+
+int ftc_op_conv2d(const void* x, int dtype, int batch, int h, int w, int cin, const float* w_oihw, int cout, int ksize,
+                  int stride, const float* scale, const float* bias, int act, const void* residual,
+                  const float* a_scale, void* out, void* wpack, size_t wpack_bytes, int backend, void* stream) {
+  FTC_REQUIRE(x && w_oihw && out && wpack, "null argument");
+  FTC_REQUIRE(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
+  FTC_REQUIRE(cin % 8 == 0, "cin must be a multiple of 8");
+  FTC_REQUIRE(wpack_bytes >= ftc_op_conv2d_wpack_bytes(cin, cout, ksize), "wpack too small");
+  FTC_REQUIRE(a_scale == nullptr || ksize == 1, "a_scale only for 1x1");
+  cudaStream_t s = (cudaStream_t)stream;
+  int K = 0;
+  std::vector<uint32_t> kt = make_ktab(cin, 0, ksize, &K);
+  const size_t es = dtype == DT_BF16 ? 2 : 4;
+  const int npad = (cout + 15) / 16 * 16;
+  char* wp = (char*)wpack;
+  uint32_t* ktab_d = (uint32_t*)(wp + align_up((size_t)npad * K * 4, 256));
+  FTC_CHECK_CUDA(cudaMemsetAsync(wp, 0, (size_t)npad * K * es, s));
+  FTC_CHECK_CUDA(cudaMemcpyAsync(ktab_d, kt.data(), kt.size() * 4, cudaMemcpyHostToDevice, s));
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = batch; p.H = h; p.W = w; p.stride = stride; p.pad = (ksize - 1) / 2;
+  p.Ho = (h - 1) / stride + 1; p.Wo = (w - 1) / stride + 1;
+  p.M = batch * p.Ho * p.Wo; p.N = cout; p.G = 1; p.K = K;
+  p.srcA = x; p.a_pix_stride = cin; p.ktab = ktab_d;
+  p.a_scale = a_scale; p.a_scale_stride = cin;
+  p.w = wp; p.scale = scale; p.bias_tab = bias; p.ncase = 1; p.act = act;
+  p.res1 = residual; p.res1_stride = cout;
+  p.out = out; p.out_layout = OUT_NHWC; p.out_stride = cout;
+  p.out_ch_base[0] = 0; p.n_valid[0] = cout;
+  p.dtype = dtype;
+  int rc;
+  if (backend == FTC_GEMM_TCGEN05) {
+    FTC_REQUIRE(dtype == DT_BF16, "tcgen05 backend needs bf16");
+    ConvTcPlan plan;
+    rc = conv_gemm_tc_plan(p, &plan);
+    if (rc) return rc;
+    rc = pack_conv_weight_tc(wp, w_oihw, cout, cin, ksize, ksize, 0, cin, 0, K, 0, plan.BN, nullptr, s);
+    if (rc) return rc;
+    p.tc = plan;
+    rc = conv_gemm_tc(p, s);
+  } else {
+    rc = pack_conv_weight(wp, dtype, w_oihw, cout, cin, ksize, ksize, 0, cin, 0, K, 0, nullptr, s);
+    if (rc) return rc;
+    rc = conv_gemm_simt(p, s);
+  }
+  if (rc) return rc;
+  FTC_CHECK_CUDA(cudaStreamSynchronize(s));   // ktab upload source is a host temporary
+  return 0;
+}
+
+int ftc_op_dwconv3x3(const void* x, void* out, int dtype, int batch, int h, int w, int c, int stride,
+                     const float* w9c, const float* scale, const float* bias, float* se_sum, void* stream) {
+  FTC_REQUIRE(x && out && w9c && scale && bias, "null argument");
+  return dwconv3x3(x, out, dtype, batch, h, w, c, stride, w9c, scale, bias, se_sum, (cudaStream_t)stream);
+}
+
+int ftc_op_se_fc(float* sum, float* scale_out, int batch, int c, int s, float inv_hw, const float* w1, const float* b1,
+                 const float* w2t, const float* b2, void* stream) {
+  FTC_REQUIRE(sum && scale_out && w1 && b1 && w2t && b2, "null argument");
+  return se_fc(sum, scale_out, batch, c, s, inv_hw, w1, b1, w2t, b2, (cudaStream_t)stream);
+}
+
+int ftc_op_upsample2x(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream) {
+  FTC_REQUIRE(x && out, "null argument");
+  return upsample2x(x, out, dtype, batch, h, w, c, (cudaStream_t)stream);
+}
+
+}  // extern "C"

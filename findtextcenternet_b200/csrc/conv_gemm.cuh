@@ -1,0 +1,86 @@
+// Implicit-GEMM convolution / linear op shared by every dense layer of the hot path.
+//
+//   out[m, g*N + n] = act( (sum_k A[m,k] * W[g][n][k]) * scale[g*N+n] + bias_tab[case(m)][g*N+n]
+//                          + res1[m, n] + res2[m, n] )
+//
+// m enumerates output pixels (b, oy, ox) of an NHWC tensor; k enumerates (source, ky, kx, c):
+// first the taps of source A (shared by all groups), then the taps of source B (per-group channel
+// slice) -- this is the Leafmap "cat([y, bn(x)])" conv (models/detector.py:199) without materialising
+// the concat.  A per-op chunk table (one int per 8 channels of k) carries (valid, src, ky, kx, c).
+// 1x1 convs / nn.Linear are the H=M, W=1 special case.
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace ftc {
+
+constexpr int KCHUNK = 8;          // channels per k-chunk (16 B of bf16)
+constexpr int KBLOCK = 64;         // k per pipeline stage (one 128 B swizzle row of bf16)
+constexpr int MAX_GROUPS = 9;
+
+// chunk table entry
+constexpr uint32_t KT_VALID = 1u << 31;
+constexpr uint32_t KT_SRCB = 1u << 30;
+__host__ __device__ inline uint32_t kt_make(bool srcb, int ky, int kx, int c) {
+  return KT_VALID | (srcb ? KT_SRCB : 0u) | (uint32_t(ky) << 18) | (uint32_t(kx) << 16) | uint32_t(c);
+}
+__host__ __device__ inline int kt_ky(uint32_t e) { return (e >> 18) & 3; }
+__host__ __device__ inline int kt_kx(uint32_t e) { return (e >> 16) & 3; }
+__host__ __device__ inline int kt_c(uint32_t e) { return e & 0xFFFF; }
+
+// tile plan of the tcgen05 path (conv_gemm_tc.cu); also fixes the packed-weight layout
+struct ConvTcPlan {
+  int BN;       // N tile (multiple of 16, <= 256) = UMMA N
+  int NT;       // N tiles per group; packed weight rows per group = NT*BN
+  int NKB;      // K / KBLOCK
+  int stages;   // smem pipeline depth
+};
+
+struct ConvGemmParams {
+  // geometry
+  int B, H, W;          // input spatial (both sources)
+  int Ho, Wo;           // output spatial
+  int stride, pad;
+  int M;                // B*Ho*Wo
+  int N;                // output channels per group
+  int G;                // groups (source A shared, source B sliced by g*srcB_group_stride)
+  int K;                // padded k (multiple of KBLOCK)
+  // sources (element type = dtype)
+  const void* srcA; int a_pix_stride; int a_ch_off;
+  const void* srcB; int b_pix_stride; int b_ch_off; int b_group_stride;
+  const uint32_t* ktab; // K / KCHUNK entries
+  const float* a_scale; // optional [B, a_scale_stride] multiplier on source A channels (SE), 1x1 only
+  int a_scale_stride;
+  // weights [G*N][K] (k-major), element type = dtype
+  const void* w;
+  // epilogue
+  const float* scale;     // [G*N] or null (=1)
+  const float* bias_tab;  // [ncase][G*N] or null (=0); ncase 1 or 9 (3x3 border cases)
+  int ncase;
+  int act;
+  const void* res1; int res1_stride; int res1_row_mod;   // row index = res_row_mod ? m % res_row_mod : m
+  const void* res2; int res2_stride;
+  // output
+  void* out; int out_layout; int out_stride;   // NHWC: elements per pixel;  NCHW: total channels
+  int out_ch_base[MAX_GROUPS];                 // first output channel of group g
+  int n_valid[MAX_GROUPS];                     // channels of group g actually stored (<= N)
+  int dtype;                                   // DT_F32 / DT_BF16 (sources, weights, NHWC output, residuals)
+  ConvTcPlan tc;                               // tcgen05 path only
+};
+
+// SIMT (CUDA-core, fp32 accumulate) implementation: any dtype, the parity path.
+int conv_gemm_simt(const ConvGemmParams& p, cudaStream_t stream);
+// tcgen05/TMEM implementation: bf16 only, the product path.  p.tc must come from conv_gemm_tc_plan and the
+// weights must have been packed with pack_conv_weight_tc for the same plan.
+int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan);
+int conv_gemm_tc(const ConvGemmParams& p, cudaStream_t stream);
+// tcgen05 weight image: per (padded row tile, k-block) one [BN rows][64 k] bf16 block in the 128B-swizzled
+// K-major shared-memory layout, so that a stage's B operand is ONE contiguous cp.async.bulk.
+//   row R = o_off + o (o_off in padded-row space: group g starts at g*NT*BN), k = k_off + (ky*kw+kx)*C + c
+int pack_conv_weight_tc(void* dst, const float* src, int O, int Itot, int kh, int kw, int c_off, int C, int k_off,
+                        int Kpad, int o_off, int BN, const float* cscale, cudaStream_t s);
+size_t conv_tc_weight_bytes(const ConvTcPlan& plan, int G);
+
+std::vector<uint32_t> make_ktab(int CA, int CB, int ksize, int* Kout);
+
+}  // namespace ftc

@@ -1,0 +1,514 @@
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulate in tensor memory).
+//
+// One persistent CTA per SM, 9 warps, three roles connected by mbarrier pipelines:
+//   warps 0-3  A producers : gather the im2col rows of a 128-pixel tile straight from the NHWC activation
+//                            tensor(s) with 16-byte cp.async into the 128B-swizzled K-major smem layout that
+//                            tcgen05.mma reads (zero fill for padding / ragged tails; the Leafmap "concat" is just
+//                            a second source pointer in the k-chunk table).  Thread 0 also issues the stage's
+//                            weight block as ONE cp.async.bulk (TMA bulk copy): weights are pre-packed in
+//                            exactly the smem image (pack_conv_weight_tc).
+//   warp  4    MMA issuer  : one thread, 4 x tcgen05.mma (M=128, N=BN, K=16) per 64-wide k-block, accumulating
+//                            in one of two TMEM accumulators; tcgen05.commit releases smem stages / publishes
+//                            the accumulator.
+//   warps 5-8  epilogue    : tcgen05.ld the accumulator (32 lanes per warp), folded-BN scale + (border-aware)
+//                            bias + residual(s) + SiLU / erf-GELU / SwiGLU, store NHWC bf16 or NCHW fp32.
+// The epilogue of tile i overlaps the main loop of tile i+1 (double-buffered TMEM).
+#include "conv_gemm.cuh"
+
+namespace ftc {
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 288;
+constexpr int TC_LAG = 2;                 // cp.async groups kept in flight per producer thread
+constexpr uint32_t A_STAGE_BYTES = TC_BM * 128;
+constexpr int TC_MAX_STAGES = 6;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a broken pipeline traps (launch failure) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzle shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+struct TileCoord { int m0, g, nt; };
+__device__ __forceinline__ TileCoord decode_tile(int tile, int NT, int G) {
+  int per_m = NT * G;
+  int mt = tile / per_m;
+  int rest = tile - mt * per_m;
+  TileCoord t;
+  t.m0 = mt * TC_BM;
+  t.g = rest / NT;
+  t.nt = rest - t.g * NT;
+  return t;
+}
+
+
+// one row x 16 accumulator columns: scale / bias / residuals / activation / store
+__device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const uint32_t (&raw16)[16], int g, int n0, int m,
+                                               int b, int oy, int ox, int hw, int64_t r1row, int nvalid, int chb,
+                                               const float* __restrict__ scale_row, const float* __restrict__ bias_row,
+                                               const bf16* __restrict__ res1, const bf16* __restrict__ res2) {
+  float v[16];
+  const bool full16 = n0 + 16 <= p.N;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x = __uint_as_float(raw16[i]);
+    int n = n0 + i;
+    if (full16 || n < p.N) {
+      if (scale_row) x *= __ldg(scale_row + n);
+      if (bias_row) x += __ldg(bias_row + n);
+    }
+    v[i] = x;
+  }
+  if (res1) {
+    const bf16* rp = res1 + r1row * p.res1_stride + (int64_t)g * p.N + n0;
+    if (full16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+      float a[8], c[8];
+      load8(rp, a); load8(rp + 8, c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] += a[i]; v[8 + i] += c[i]; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (n0 + i < p.N) v[i] += __bfloat162float(rp[i]);
+    }
+  }
+  if (res2) {
+    const bf16* rp = res2 + (int64_t)m * p.res2_stride + (int64_t)g * p.N + n0;
+    if (full16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+      float a[8], c[8];
+      load8(rp, a); load8(rp + 8, c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] += a[i]; v[8 + i] += c[i]; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (n0 + i < p.N) v[i] += __bfloat162float(rp[i]);
+    }
+  }
+  if (p.act == ACT_SWIGLU) {
+    // interleaved (x1, xg) column pairs -> x1 * silu(xg), 8 outputs per 16 columns
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = v[2 * i] * silu_f(v[2 * i + 1]);
+    bf16* op = reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.out_stride + chb + (n0 >> 1);
+    if (n0 + 16 <= nvalid && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+      store8(op, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (n0 + 2 * i + 1 < nvalid) op[i] = __float2bfloat16_rn(o[i]);
+    }
+    return;
+  }
+  if (p.act == ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
+  } else if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (p.out_layout == OUT_NCHW_F32) {
+    float* op = reinterpret_cast<float*>(p.out) + (((int64_t)b * p.out_stride + chb + n0) * p.Ho + oy) * p.Wo + ox;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) if (n0 + i < nvalid) op[(int64_t)i * hw] = v[i];
+  } else {
+    bf16* op = reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.out_stride + chb + n0;
+    if (n0 + 16 <= nvalid && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+      float lo[8], hi[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+      store8(op, lo); store8(op + 8, hi);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (n0 + i < nvalid) op[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+}
+
+template <bool SE>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p,
+                                                                      const int num_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024 B alignment
+  uint8_t* smem = smem_raw + (sbase - raw);
+  const int S = p.tc.stages, BN = p.tc.BN, NKB = p.tc.NKB, NT = p.tc.NT;
+  const uint32_t b_bytes = (uint32_t)BN * 128u;
+  const uint32_t stage_bytes = A_STAGE_BYTES + b_bytes;
+  const uint32_t bar0 = sbase + (uint32_t)S * stage_bytes;   // 8 B each: full[S], empty[S], tfull[2], tempty[2]
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + (size_t)S * stage_bytes + 8 * (2 * S + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 4 + 1); mbar_init(empty_bar(s), 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const int G = p.G;
+  const int hw = p.Ho * p.Wo;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ A producers (+ B bulk copy)
+    const int t = threadIdx.x;
+    const int j = t & 7;             // 16-byte chunk of the 128-byte k-block row this thread fills
+    const int rbase = t >> 3;        // rows rbase + 16*i, i = 0..7
+    const uint32_t row_off = (uint32_t)(rbase >> 3) * 1024u + (uint32_t)(rbase & 7) * 128u + (uint32_t)((j ^ (rbase & 7)) << 4);
+    const bf16* srcA = reinterpret_cast<const bf16*>(p.srcA);
+    const bf16* srcB = reinterpret_cast<const bf16*>(p.srcB);
+    const bf16* wgt = reinterpret_cast<const bf16*>(p.w);
+    int stage = 0;
+    uint32_t phase = 0;
+    int arr_stage = 0;               // next stage whose A fill this thread still has to publish
+    uint32_t pending = 0;            // committed-but-unpublished cp.async groups
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(tile, NT, G);
+      int pixoff[8];
+      uint32_t yx[8];
+      int img[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int m = tc.m0 + rbase + 16 * i;
+        if (m < p.M) {
+          int b = m / hw;
+          int r = m - b * hw;
+          int oy = r / p.Wo, ox = r - oy * p.Wo;
+          int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+          pixoff[i] = (b * p.H + iy0) * p.W + ix0;
+          yx[i] = ((uint32_t)(iy0 + 1) << 16) | (uint32_t)(ix0 + 1);
+          img[i] = b;
+        } else {
+          pixoff[i] = 0; yx[i] = 0xFFFFFFFFu; img[i] = 0;
+        }
+      }
+      const bf16* wtile = wgt + (size_t)(tc.g * NT + tc.nt) * NKB * ((size_t)BN * 64);
+      for (int kb = 0; kb < NKB; ++kb) {
+        const uint32_t e = __ldg(p.ktab + kb * 8 + j);
+        const bool srcb = (e & KT_SRCB) != 0;
+        const int c = kt_c(e), ky = kt_ky(e), kx = kt_kx(e);
+        const bf16* base = srcb ? (srcB + p.b_ch_off + tc.g * p.b_group_stride + c) : (srcA + p.a_ch_off + c);
+        const int pstride = srcb ? p.b_pix_stride : p.a_pix_stride;
+        const int dpix = ky * p.W + kx;
+        const bool evalid = (e & KT_VALID) != 0;
+        uint4 regs[SE ? 8 : 1];
+        if (SE) {
+          // register-staged path (SE-scaled A operand): issue the loads before blocking on the stage
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint32_t y = (yx[i] >> 16) + ky, x = (yx[i] & 0xFFFFu) + kx;
+            bool ok = evalid && y >= 1u && y <= (uint32_t)p.H && x >= 1u && x <= (uint32_t)p.W;
+            regs[SE ? i : 0] = ok ? __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(pixoff[i] + dpix) * pstride))
+                                  : make_uint4(0, 0, 0, 0);
+          }
+        }
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t a_dst = sbase + (uint32_t)stage * stage_bytes;
+        if (t == 0) {
+          mbar_arrive_expect_tx(full_bar(stage), b_bytes);
+          bulk_copy_g2s(a_dst + A_STAGE_BYTES, wtile + (size_t)kb * BN * 64, b_bytes, full_bar(stage));
+        }
+        if (SE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float v[8];
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&regs[SE ? i : 0]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { float2 f = __bfloat1622float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+            if (evalid) {
+              const float4* sp = reinterpret_cast<const float4*>(p.a_scale + (int64_t)img[i] * p.a_scale_stride + c);
+              float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+              v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
+              v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+            }
+            uint4 u;
+            __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_dst + row_off + (uint32_t)i * 2048u), "r"(u.x),
+                         "r"(u.y), "r"(u.z), "r"(u.w)
+                         : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar(stage));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint32_t y = (yx[i] >> 16) + ky, x = (yx[i] & 0xFFFFu) + kx;
+            bool ok = evalid && y >= 1u && y <= (uint32_t)p.H && x >= 1u && x <= (uint32_t)p.W;
+            const bf16* src = ok ? base + (int64_t)(pixoff[i] + dpix) * pstride : base;
+            cp_async16(a_dst + row_off + (uint32_t)i * 2048u, src, ok ? 16u : 0u);
+          }
+          cp_async_commit();
+          ++pending;
+          if (pending > (uint32_t)TC_LAG) {
+            cp_async_wait<TC_LAG>();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(arr_stage));
+            arr_stage = (arr_stage + 1 == S) ? 0 : arr_stage + 1;
+            --pending;
+          }
+        }
+        stage = (stage + 1 == S) ? 0 : stage + 1;
+        phase ^= (stage == 0) ? 1u : 0u;
+      }
+    }
+    if (!SE) {
+      // drain: publish the last (<= TC_LAG) stages
+      cp_async_wait<0>();
+      fence_proxy_async();
+      __syncwarp();
+      while (pending > 0) {
+        if (lane == 0) mbar_arrive(full_bar(arr_stage));
+        arr_stage = (arr_stage + 1 == S) ? 0 : arr_stage + 1;
+        --pending;
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t titer = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+        const uint32_t acc = titer & 1u;
+        mbar_wait(tempty_bar(acc), ((titer >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
+        for (int kb = 0; kb < NKB; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = sbase + (uint32_t)stage * stage_bytes;
+          const uint64_t adesc = umma_desc_sw128(a_addr);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row: +2 in 16-byte units
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          stage = (stage + 1 == S) ? 0 : stage + 1;
+          phase ^= (stage == 0) ? 1u : 0u;
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const bf16* res1 = reinterpret_cast<const bf16*>(p.res1);
+    const bf16* res2 = reinterpret_cast<const bf16*>(p.res2);
+    uint32_t titer = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+      const TileCoord tc = decode_tile(tile, NT, G);
+      const uint32_t acc = titer & 1u;
+      mbar_wait(tfull_bar(acc), (titer >> 1) & 1u);
+      tc_fence_after();
+      const int m = tc.m0 + row;
+      const bool mvalid = m < p.M;
+      int b = 0, oy = 0, ox = 0;
+      if (mvalid) { b = m / hw; int r = m - b * hw; oy = r / p.Wo; ox = r - oy * p.Wo; }
+      int cs = 0;
+      if (p.ncase == 9) cs = (oy == 0 ? 0 : (oy == p.Ho - 1 ? 2 : 1)) * 3 + (ox == 0 ? 0 : (ox == p.Wo - 1 ? 2 : 1));
+      const float* bias_row = p.bias_tab ? p.bias_tab + (int64_t)cs * G * p.N + (int64_t)tc.g * p.N : nullptr;
+      const float* scale_row = p.scale ? p.scale + (int64_t)tc.g * p.N : nullptr;
+      const int64_t r1row = p.res1_row_mod ? (m % p.res1_row_mod) : m;
+      const int nvalid = min(p.N, p.n_valid[tc.g]);
+      const int chb = p.out_ch_base[tc.g];
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        const int n0 = tc.nt * BN + c0;
+        if (n0 >= p.N) break;                       // warp-uniform
+        uint32_t raw16[16];
+        __syncwarp();                               // tcgen05.ld is warp-collective: reconverge first
+        tmem_ld16(t_addr + (uint32_t)c0, raw16);
+        tmem_ld_wait();
+        if (mvalid) epilogue_store(p, raw16, tc.g, n0, m, b, oy, ox, hw, r1row, nvalid, chb, scale_row, bias_row, res1, res2);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+__global__ void pack_conv_weight_tc_kernel(bf16* __restrict__ dst, const float* __restrict__ src, int O, int Itot, int kh,
+                                           int kw, int c_off, int C, int k_off, int NKB, int o_off, int BN,
+                                           const float* __restrict__ cscale) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t per_o = (int64_t)kh * kw * C;
+  if (idx >= (int64_t)O * per_o) return;
+  int o = idx / per_o;
+  int r = idx - (int64_t)o * per_o;
+  int t = r / C, c = r - t * C;
+  int ky = t / kw, kx = t - ky * kw;
+  float v = src[(((int64_t)o * Itot + c_off + c) * kh + ky) * kw + kx];
+  if (cscale) v *= cscale[c];
+  int R = o_off + o;
+  int tile = R / BN, rr = R - tile * BN;
+  int k = k_off + r;
+  int kb = k >> 6, kk = k & 63;
+  int chunk = kk >> 3, within = kk & 7;
+  int64_t off = ((int64_t)tile * NKB + kb) * ((int64_t)BN * 64) + (rr >> 3) * 512 + (rr & 7) * 64 + ((chunk ^ (rr & 7)) << 3) + within;
+  dst[off] = __float2bfloat16_rn(v);
+}
+
+int g_num_sms = 0;
+bool g_attr_set[2] = {false, false};
+
+}  // namespace
+
+int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan) {
+  FTC_REQUIRE(p.K % KBLOCK == 0 && p.K > 0, "K must be a positive multiple of 64");
+  FTC_REQUIRE(p.N >= 1, "N");
+  int best_bn = 0, best_nt = 0;
+  long best_pad = -1;
+  int nt_min = (p.N + 255) / 256;
+  for (int nt = nt_min; nt <= nt_min + 3; ++nt) {
+    int bn = ((p.N + nt - 1) / nt + 15) / 16 * 16;
+    if (bn > 256) continue;
+    long pad = (long)bn * nt;
+    if (best_pad < 0 || pad < best_pad) { best_pad = pad; best_bn = bn; best_nt = nt; }
+  }
+  FTC_REQUIRE(best_bn > 0, "no N tiling");
+  plan->BN = best_bn;
+  plan->NT = best_nt;
+  plan->NKB = p.K / KBLOCK;
+  int stage_bytes = (int)A_STAGE_BYTES + best_bn * 128;
+  int s = (200 * 1024) / stage_bytes;
+  plan->stages = s > TC_MAX_STAGES ? TC_MAX_STAGES : (s < 3 ? 3 : s);
+  return 0;
+}
+
+size_t conv_tc_weight_bytes(const ConvTcPlan& plan, int G) {
+  return (size_t)G * plan.NT * plan.NKB * plan.BN * 128;
+}
+
+int pack_conv_weight_tc(void* dst, const float* src, int O, int Itot, int kh, int kw, int c_off, int C, int k_off, int Kpad,
+                        int o_off, int BN, const float* cscale, cudaStream_t s) {
+  int64_t total = (int64_t)O * kh * kw * C;
+  int grid = (int)((total + 255) / 256);
+  pack_conv_weight_tc_kernel<<<grid, 256, 0, s>>>((bf16*)dst, src, O, Itot, kh, kw, c_off, C, k_off, Kpad / KBLOCK, o_off, BN,
+                                                  cscale);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int conv_gemm_tc(const ConvGemmParams& p, cudaStream_t stream) {
+  FTC_REQUIRE(p.dtype == DT_BF16, "tcgen05 path is bf16 only");
+  FTC_REQUIRE(p.G >= 1 && p.G <= MAX_GROUPS, "groups out of range");
+  FTC_REQUIRE(p.tc.BN >= 16 && p.tc.BN <= 256 && p.tc.BN % 16 == 0, "bad tc plan");
+  FTC_REQUIRE(p.tc.NKB * KBLOCK == p.K, "tc plan does not match K");
+  FTC_REQUIRE(p.H < 65000 && p.W < 65000, "spatial size");
+  FTC_REQUIRE(p.act != ACT_SWIGLU || p.out_layout == OUT_NHWC, "swiglu needs NHWC out");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    FTC_CHECK_CUDA(cudaGetDevice(&dev));
+    FTC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const bool se = p.a_scale != nullptr;
+  if (!g_attr_set[se ? 1 : 0]) {
+    if (se) FTC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else FTC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    g_attr_set[se ? 1 : 0] = true;
+  }
+  const int m_tiles = ceil_div(p.M, TC_BM);
+  const int num_tiles = m_tiles * p.tc.NT * p.G;
+  size_t smem = (size_t)p.tc.stages * (A_STAGE_BYTES + (size_t)p.tc.BN * 128) + 1024 + 256;
+  if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: the CTA owns all 512 TMEM columns
+  FTC_REQUIRE(smem <= 227 * 1024, "smem budget");
+  int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
+  if (se) conv_gemm_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p, num_tiles);
+  else conv_gemm_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p, num_tiles);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+}  // namespace ftc

@@ -1,0 +1,491 @@
+// Bandwidth-bound detector kernels + device-side weight packing.  See detector_ops.cuh for the
+// reference lines each op follows.  All activations are NHWC; fp32 (parity mode) or bf16 (product mode).
+#include "detector_ops.cuh"
+#include <math.h>
+
+namespace ftc {
+
+// ------------------------------------------------------------------------------------------------
+// stem
+template <typename T, int COUT>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ img, T* __restrict__ out, int B,
+                                                        int H, int W, const float* __restrict__ w,
+                                                        const float* __restrict__ scale, const float* __restrict__ bias) {
+  __shared__ float sw[27 * COUT];
+  __shared__ float ss[COUT], sb[COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) { ss[i] = scale[i]; sb[i] = bias[i]; }
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= (int64_t)B * Ho * Wo) return;
+  int b = m / (Ho * Wo);
+  int r = m - (int64_t)b * Ho * Wo;
+  int oy = r / Wo, ox = r - oy * Wo;
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[(((int64_t)b * 3 + c) * H + iy) * W + ix] * 2.f - 1.f;
+        const float* wk = &sw[((c * 3 + ky) * 3 + kx) * COUT];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wk[o], acc[o]);
+      }
+  T* op = out + m * COUT;
+#pragma unroll
+  for (int o0 = 0; o0 < COUT; o0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = acc[o0 + j] * ss[o0 + j] + sb[o0 + j];
+      v[j] = sizeof(T) == 4 ? silu_precise(t) : silu_f(t);
+    }
+    store8(op + o0, v);
+  }
+}
+
+int stem_conv(const float* img, void* out, int dtype, int B, int H, int W, int Cout, const float* w,
+              const float* scale, const float* bias, cudaStream_t s) {
+  FTC_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem needs even H, W");
+  int64_t M = (int64_t)B * (H / 2) * (W / 2);
+  int grid = (int)((M + 127) / 128);
+#define LAUNCH(TT, CC) stem_conv_kernel<TT, CC><<<grid, 128, 0, s>>>(img, (TT*)out, B, H, W, w, scale, bias)
+  if (Cout == 32) { if (dtype == DT_F32) LAUNCH(float, 32); else LAUNCH(bf16, 32); }
+  else if (Cout == 24) { if (dtype == DT_F32) LAUNCH(float, 24); else LAUNCH(bf16, 24); }
+  else FTC_REQUIRE(false, "stem Cout must be 24 or 32");
+#undef LAUNCH
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3 + BN + SiLU + SE partial sums.  block (32 chunk lanes, 8 pixel lanes), 64 pixels per block.
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W,
+                                                        int C, int stride, int Ho, int Wo,
+                                                        const float* __restrict__ w, const float* __restrict__ scale,
+                                                        const float* __restrict__ bias, float* __restrict__ se_sum) {
+  __shared__ float red[8][32][8];
+  const int cx = threadIdx.x, py = threadIdx.y;
+  const int b = blockIdx.z;
+  const int c0 = (blockIdx.y * 32 + cx) * 8;
+  const bool active = c0 < C;
+  float wk[9][8], sc[8], bi[8], ssum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ssum[j] = 0.f; sc[j] = 0.f; bi[j] = 0.f; }
+  if (active) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wk[t][j] = w[t * C + c0 + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; bi[j] = bias[c0 + j]; }
+  }
+  const int npix = Ho * Wo;
+  if (active) {
+    for (int it = 0; it < 8; ++it) {
+      int pidx = blockIdx.x * 64 + it * 8 + py;
+      if (pidx >= npix) break;
+      int oy = pidx / Wo, ox = pidx - oy * Wo;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        int iy = oy * stride - 1 + ky;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          int ix = ox * stride - 1 + kx;
+          if (ix < 0 || ix >= W) continue;
+          float v[8];
+          load8(in + (((int64_t)b * H + iy) * W + ix) * C + c0, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wk[ky * 3 + kx][j], acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = acc[j] * sc[j] + bi[j];
+        acc[j] = sizeof(T) == 4 ? silu_precise(t) : silu_f(t);
+        ssum[j] += acc[j];
+      }
+      store8(out + ((int64_t)b * npix + pidx) * C + c0, acc);
+    }
+  }
+  if (se_sum == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[py][cx][j] = ssum[j];
+  __syncthreads();
+  if (py == 0 && active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += red[q][cx][j];
+      atomicAdd(&se_sum[(int64_t)b * C + c0 + j], t);
+    }
+  }
+}
+
+int dwconv3x3(const void* in, void* out, int dtype, int B, int H, int W, int C, int stride, const float* w,
+              const float* scale, const float* bias, float* se_sum, cudaStream_t s) {
+  FTC_REQUIRE(C % 8 == 0, "depthwise channels must be a multiple of 8");
+  int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;   // k=3, pad=1
+  dim3 grid(ceil_div(Ho * Wo, 64), ceil_div(C / 8, 32), B), block(32, 8);
+  if (dtype == DT_F32)
+    dwconv3x3_kernel<float><<<grid, block, 0, s>>>((const float*)in, (float*)out, H, W, C, stride, Ho, Wo, w, scale, bias, se_sum);
+  else
+    dwconv3x3_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)in, (bf16*)out, H, W, C, stride, Ho, Wo, w, scale, bias, se_sum);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SE excitation, one block per image
+__global__ void __launch_bounds__(256) se_fc_kernel(float* __restrict__ sum, float* __restrict__ scale_out, int C, int S,
+                                                    float inv_hw, const float* __restrict__ w1,
+                                                    const float* __restrict__ b1, const float* __restrict__ w2t,
+                                                    const float* __restrict__ b2) {
+  extern __shared__ float sm[];
+  float* mean = sm;        // [C]
+  float* hid = sm + C;     // [S]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < C; c += blockDim.x) {
+    mean[c] = sum[(int64_t)b * C + c] * inv_hw;
+    sum[(int64_t)b * C + c] = 0.f;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  for (int sidx = warp; sidx < S; sidx += nw) {
+    float t = 0.f;
+    const float* wr = w1 + (int64_t)sidx * C;
+    for (int c = lane; c < C; c += 32) t = fmaf(wr[c], mean[c], t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) hid[sidx] = silu_precise(t + b1[sidx]);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    float t = b2[c];
+    for (int k = 0; k < S; ++k) t = fmaf(w2t[(int64_t)k * C + c], hid[k], t);
+    scale_out[(int64_t)b * C + c] = sigmoid_precise(t);
+  }
+}
+
+int se_fc(float* sum, float* scale_out, int B, int C, int S, float inv_hw, const float* w1, const float* b1,
+          const float* w2t, const float* b2, cudaStream_t s) {
+  size_t smem = (size_t)(C + S) * sizeof(float);
+  FTC_REQUIRE(smem <= 48 * 1024, "SE too wide for static smem budget");
+  se_fc_kernel<<<B, 256, smem, s>>>(sum, scale_out, C, S, inv_hw, w1, b1, w2t, b2);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear x2 align_corners=True
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H,
+                                                         int W, int C, float sy, float sx) {
+  const int Ho = 2 * H, Wo = 2 * W, CH = C / 8;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)B * Ho * Wo * CH;
+  if (idx >= total) return;
+  int ch = idx % CH;
+  int64_t pix = idx / CH;
+  int ox = pix % Wo;
+  int64_t t = pix / Wo;
+  int oy = t % Ho;
+  int b = t / Ho;
+  float fy = sy * oy, fx = sx * ox;
+  int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+  int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  float ly = fminf(fmaxf(fy - y0, 0.f), 1.f), lx = fminf(fmaxf(fx - x0, 0.f), 1.f);
+  float hy = 1.f - ly, hx = 1.f - lx;
+  const T* base = in + (int64_t)b * H * W * C + ch * 8;
+  float a[8], bb[8], c[8], d[8], o[8];
+  load8(base + ((int64_t)y0 * W + x0) * C, a);
+  load8(base + ((int64_t)y0 * W + x1) * C, bb);
+  load8(base + ((int64_t)y1 * W + x0) * C, c);
+  load8(base + ((int64_t)y1 * W + x1) * C, d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = hy * (hx * a[j] + lx * bb[j]) + ly * (hx * c[j] + lx * d[j]);
+  store8(out + pix * C + ch * 8, o);
+}
+
+int upsample2x(const void* in, void* out, int dtype, int B, int H, int W, int C, cudaStream_t s) {
+  FTC_REQUIRE(C % 8 == 0, "upsample channels must be a multiple of 8");
+  int64_t total = (int64_t)B * 4 * H * W * (C / 8);
+  int grid = (int)((total + 255) / 256);
+  float sy = (float)(H - 1) / (float)(2 * H - 1), sx = (float)(W - 1) / (float)(2 * W - 1);
+  if (dtype == DT_F32)
+    upsample2x_kernel<float><<<grid, 256, 0, s>>>((const float*)in, (float*)out, B, H, W, C, sy, sx);
+  else
+    upsample2x_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, (bf16*)out, B, H, W, C, sy, sx);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// peak pick
+__device__ __forceinline__ float local_max3x3(const float* __restrict__ key, int H, int W, int y, int x) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      int yy = y + dy, xx = x + dx;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) mx = fmaxf(mx, key[yy * W + xx]);
+    }
+  return mx;
+}
+
+__global__ void __launch_bounds__(256) peak_pick_kernel(const float* __restrict__ heat9, float* __restrict__ heat10,
+                                                        int B, int H, int W) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int hw = H * W;
+  if (idx >= (int64_t)B * hw) return;
+  int b = idx / hw, r = idx - (int64_t)b * hw;
+  int y = r / W, x = r - y * W;
+  const float* h9 = heat9 + (int64_t)b * 9 * hw;
+  float* h10 = heat10 + (int64_t)b * 10 * hw;
+  float k = h9[r];
+  float mx = local_max3x3(h9, H, W, y, x);
+  h10[r] = k;
+  h10[hw + r] = (k < mx) ? -INFINITY : k;      // torch.where(keymap < local_peak, -inf, keymap)
+#pragma unroll
+  for (int c = 1; c < 9; ++c) h10[(c + 1) * hw + r] = h9[c * hw + r];
+}
+
+int peak_pick(const float* heat9, float* heat10, int B, int H, int W, cudaStream_t s) {
+  int64_t total = (int64_t)B * H * W;
+  peak_pick_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(heat9, heat10, B, H, W);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// peak compaction + box decode
+__device__ __forceinline__ float np_sigmoid(float x) { return (tanhf(x * 0.5f) + 1.0f) * 0.5f; }   // util_func.py:14
+
+__global__ void __launch_bounds__(256) peak_collect_kernel(const float* __restrict__ heat9, int H, int W,
+                                                           const int* __restrict__ tile_meta, float cut_off,
+                                                           float page_w, float page_h, int max_peaks,
+                                                           int* __restrict__ count, unsigned long long* __restrict__ cand) {
+  const int b = blockIdx.y;
+  const int hw = H * W;
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= hw) return;
+  int y = r / W, x = r - y * W;
+  const int* tm = tile_meta + b * 6;
+  if (x < tm[2] || x >= tm[3] || y < tm[4] || y >= tm[5]) return;          // centre-crop mask
+  const float* h9 = heat9 + (int64_t)b * 9 * hw;
+  float k = h9[r];
+  if (k < local_max3x3(h9, H, W, y, x)) return;                             // not a 3x3 local maximum
+  float p = np_sigmoid(k);
+  if (!(p >= cut_off)) return;
+  float w = expf(h9[hw + r] - 3.f) * 1024.f;
+  float h = expf(h9[2 * hw + r] - 3.f) * 1024.f;
+  if (w <= 0.f || h <= 0.f) return;
+  if (w > page_w || h > page_h) return;
+  int slot = atomicAdd(&count[b], 1);
+  if (slot < max_peaks)
+    cand[(int64_t)b * max_peaks + slot] =
+        ((unsigned long long)__float_as_uint(p) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(1024) peak_emit_kernel(const float* __restrict__ heat9, const float* __restrict__ feat,
+                                                         int H, int W, int FC, const int* __restrict__ tile_meta,
+                                                         int max_peaks, int* __restrict__ count,
+                                                         const unsigned long long* __restrict__ cand,
+                                                         float* __restrict__ loc, float* __restrict__ gfeat) {
+  __shared__ unsigned long long keys[NMAX];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int hw = H * W;
+  int n = min(count[b], max_peaks);
+  for (int i = tid; i < NMAX; i += blockDim.x) keys[i] = (i < n) ? cand[(int64_t)b * max_peaks + i] : 0ull;
+  __syncthreads();
+  // bitonic sort, descending
+  for (int k = 2; k <= NMAX; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < NMAX; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = keys[i], c = keys[ixj];
+          bool desc = (i & k) == 0;
+          if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  const float* h9 = heat9 + (int64_t)b * 9 * hw;
+  const int* tm = tile_meta + b * 6;
+  for (int i = tid; i < n; i += blockDim.x) {
+    unsigned long long kk = keys[i];
+    int r = (int)(0xFFFFFFFFu - (unsigned)(kk & 0xFFFFFFFFull));
+    int y = r / W, x = r - y * W;
+    float* l = loc + ((int64_t)b * max_peaks + i) * 9;
+    l[0] = __uint_as_float((unsigned)(kk >> 32));
+    l[1] = (float)(x * 4 + tm[0]);
+    l[2] = (float)(y * 4 + tm[1]);
+    l[3] = expf(h9[hw + r] - 3.f) * 1024.f;
+    l[4] = expf(h9[2 * hw + r] - 3.f) * 1024.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) l[5 + c] = np_sigmoid(h9[(5 + c) * hw + r]);
+  }
+  // feature gather: warp per peak
+  const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < n; i += nw) {
+    int r = (int)(0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFull));
+    for (int c = lane; c < FC; c += 32)
+      gfeat[((int64_t)b * max_peaks + i) * FC + c] = feat[((int64_t)b * FC + c) * hw + r];
+  }
+  if (tid == 0) count[b] = n;
+}
+
+int peak_decode(const float* heat9, const float* feat, int B, int H, int W, int FC, const int* tile_meta, float cut_off,
+                float page_w, float page_h, int max_peaks, int* count, float* loc, float* gfeat, void* scratch,
+                cudaStream_t s) {
+  FTC_REQUIRE(max_peaks == 1024 || max_peaks == 2048 || max_peaks == 4096, "max_peaks must be 1024/2048/4096");
+  FTC_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * B, s));
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(scratch);   // [B][max_peaks]
+  dim3 grid(ceil_div(H * W, 256), B);
+  peak_collect_kernel<<<grid, 256, 0, s>>>(heat9, H, W, tile_meta, cut_off, page_w, page_h, max_peaks, count, cand);
+  FTC_POST_LAUNCH();
+  if (max_peaks == 1024)
+    peak_emit_kernel<1024><<<B, 1024, 0, s>>>(heat9, feat, H, W, FC, tile_meta, max_peaks, count, cand, loc, gfeat);
+  else if (max_peaks == 2048)
+    peak_emit_kernel<2048><<<B, 1024, 0, s>>>(heat9, feat, H, W, FC, tile_meta, max_peaks, count, cand, loc, gfeat);
+  else
+    peak_emit_kernel<4096><<<B, 1024, 0, s>>>(heat9, feat, H, W, FC, tile_meta, max_peaks, count, cand, loc, gfeat);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing
+template <typename T>
+__global__ void pack_conv_weight_kernel(T* __restrict__ dst, const float* __restrict__ src, int O, int Itot, int kh,
+                                        int kw, int c_off, int C, int k_off, int Kpad, int o_off,
+                                        const float* __restrict__ cscale) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t per_o = (int64_t)kh * kw * C;
+  if (idx >= (int64_t)O * per_o) return;
+  int o = idx / per_o;
+  int r = idx - (int64_t)o * per_o;
+  int t = r / C, c = r - t * C;
+  int ky = t / kw, kx = t - ky * kw;
+  float v = src[(((int64_t)o * Itot + c_off + c) * kh + ky) * kw + kx];
+  if (cscale) v *= cscale[c];
+  dst[(int64_t)(o_off + o) * Kpad + k_off + r] = from_f<T>(v);
+}
+
+int pack_conv_weight(void* dst, int dtype, const float* src, int O, int Itot, int kh, int kw, int c_off, int C, int k_off,
+                     int Kpad, int o_off, const float* cscale, cudaStream_t s) {
+  int64_t total = (int64_t)O * kh * kw * C;
+  int grid = (int)((total + 255) / 256);
+  if (dtype == DT_F32)
+    pack_conv_weight_kernel<float><<<grid, 256, 0, s>>>((float*)dst, src, O, Itot, kh, kw, c_off, C, k_off, Kpad, o_off, cscale);
+  else
+    pack_conv_weight_kernel<bf16><<<grid, 256, 0, s>>>((bf16*)dst, src, O, Itot, kh, kw, c_off, C, k_off, Kpad, o_off, cscale);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+__global__ void bn_fold_kernel(float* scale, float* bias, const float* gamma, const float* beta, const float* mean,
+                               const float* var, float eps, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sc = gamma[c] / sqrtf(var[c] + eps);
+  scale[c] = sc;
+  bias[c] = beta[c] - mean[c] * sc;
+}
+
+int bn_fold(float* scale, float* bias, const float* gamma, const float* beta, const float* mean, const float* var,
+            float eps, int C, cudaStream_t s) {
+  bn_fold_kernel<<<ceil_div(C, 256), 256, 0, s>>>(scale, bias, gamma, beta, mean, var, eps, C);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+// one block per output channel n: T[tap] = sum_c w[n][c_off+c][tap] * shift[c]; then the 9 border cases
+__global__ void __launch_bounds__(256) leaf_bias_table_kernel(float* __restrict__ tab, int ld, const float* __restrict__ w,
+                                                              int Itot, int c_off, int C, const float* __restrict__ shift,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ bias) {
+  __shared__ float red[9][256];
+  __shared__ float T[9];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  for (int c = tid; c < C; c += blockDim.x) {
+    const float* wp = w + ((int64_t)n * Itot + c_off + c) * 9;
+    float sh = shift[c];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = fmaf(wp[t], sh, acc[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) red[t][tid] = acc[t];
+  __syncthreads();
+  if (tid < 9) {
+    float s = 0.f;
+    for (int i = 0; i < 256; ++i) s += red[tid][i];
+    T[tid] = s;
+  }
+  __syncthreads();
+  if (tid < 9) {
+    int rc = tid / 3, cc = tid % 3;   // 0: first row/col, 1: interior, 2: last row/col
+    float s = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      if ((rc == 0 && ky == 0) || (rc == 2 && ky == 2)) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        if ((cc == 0 && kx == 0) || (cc == 2 && kx == 2)) continue;
+        s += T[ky * 3 + kx];
+      }
+    }
+    tab[(int64_t)tid * ld + n] = bias[n] + scale[n] * s;
+  }
+}
+
+int leaf_bias_table(float* tab, int ld, const float* w, int O, int Itot, int c_off, int C, const float* shift,
+                    const float* scale, const float* bias, cudaStream_t s) {
+  leaf_bias_table_kernel<<<O, 256, 0, s>>>(tab, ld, w, Itot, c_off, C, shift, scale, bias);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+__global__ void fill_f32_kernel(float* p, float v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int fill_f32(float* p, float v, int64_t n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  fill_f32_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(p, v, n);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+// dst[c][r] = src[r][c]  (src is [R][C])
+__global__ void transpose_f32_kernel(float* dst, const float* src, int R, int C) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)R * C) return;
+  int r = i / C, c = i - (int64_t)r * C;
+  dst[(int64_t)c * R + r] = src[i];
+}
+int transpose_f32(float* dst, const float* src, int R, int C, cudaStream_t s) {
+  int64_t n = (int64_t)R * C;
+  transpose_f32_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(dst, src, R, C);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+}  // namespace ftc

@@ -1,0 +1,50 @@
+// Bandwidth-bound detector kernels (stem, depthwise+SE, upsample, peak-pick/decode) and weight packing.
+#pragma once
+#include "common.cuh"
+
+namespace ftc {
+
+// stem: NCHW fp32 image in [0,1] -> (x*2-1) -> conv3x3 s2 p1 -> BN -> SiLU -> NHWC (dtype)
+// models/detector.py:218 + torchvision efficientnet.py:271-276
+int stem_conv(const float* img, void* out, int dtype, int B, int H, int W, int Cout,
+              const float* w /*[27][Cout]*/, const float* scale, const float* bias, cudaStream_t s);
+
+// depthwise 3x3 (stride 1/2, pad 1) + BN + SiLU on NHWC, and per-(b,c) sums of the output for SE
+// (torchvision efficientnet.py:137-149; ops/misc.py:251 avgpool)
+int dwconv3x3(const void* in, void* out, int dtype, int B, int H, int W, int C, int stride,
+              const float* w /*[9][C]*/, const float* scale, const float* bias, float* se_sum /*[B,C]*/,
+              cudaStream_t s);
+
+// SE excitation: scale[b,c] = sigmoid(fc2(silu(fc1(sum/HW)))) ; zeroes `sum` afterwards (ops/misc.py:251-261)
+int se_fc(float* sum, float* scale_out, int B, int C, int S, float inv_hw, const float* w1 /*[S][C]*/,
+          const float* b1, const float* w2 /*[C][S]*/, const float* b2, cudaStream_t s);
+
+// bilinear x2, align_corners=True, NHWC (nn.UpsamplingBilinear2d, models/detector.py:170)
+int upsample2x(const void* in, void* out, int dtype, int B, int H, int W, int C, cudaStream_t s);
+
+// CenterNetDetector.forward tail (models/detector.py:289-296): heat9 NCHW fp32 -> heat10 NCHW fp32
+int peak_pick(const float* heat9, float* heat10, int B, int H, int W, cudaStream_t s);
+
+// per-tile peak compaction + box decode (process_ocr_base.py:498-538), sorted by descending score.
+//   tile_meta[b] = {x_i, y_i, x_min, x_max, y_min, y_max} (page offset and centre-crop mask bounds)
+//   loc [B][max_peaks][9] fp32: p, cx, cy, w, h, c1, c2, c4, c8 ; feat [B][max_peaks][100] fp32
+int peak_decode(const float* heat9, const float* feat, int B, int H, int W, int FC, const int* tile_meta,
+                float cut_off, float page_w, float page_h, int max_peaks, int* count, float* loc,
+                float* gfeat, void* scratch /* 8*B*max_peaks bytes */, cudaStream_t s);
+
+// ---- weight packing (device side; sources are fp32 torch-layout tensors) ----
+// dst[o*Kpad + k_off + (ky*kw+kx)*C + c] = src[((o*Itot + c_off + c)*kh + ky)*kw + kx] * (cscale ? cscale[c] : 1)
+int pack_conv_weight(void* dst, int dtype, const float* src, int O, int Itot, int kh, int kw, int c_off, int C,
+                     int k_off, int Kpad, int o_off, const float* cscale, cudaStream_t s);
+// scale = gamma * rsqrt(var + eps), bias = beta - mean * scale   (both written at [off, off+C))
+int bn_fold(float* scale, float* bias, const float* gamma, const float* beta, const float* mean, const float* var,
+            float eps, int C, cudaStream_t s);
+// Leafmap border-aware bias table (see DESIGN.md "in_bn before zero padding"):
+//   tab[case][n] = bias[n] + scale[n] * sum_{taps valid in case} sum_c w[n][c_off+c][ky][kx] * shift[c]
+int leaf_bias_table(float* tab /*[9][ld], pre-offset to this group's first column*/, int ld, const float* w, int O,
+                    int Itot, int c_off, int C, const float* shift, const float* scale, const float* bias, cudaStream_t s);
+int fill_f32(float* p, float v, int64_t n, cudaStream_t s);
+// dst[c][r] = src[r][c] for src [R][C]: depthwise [C][9]->[9][C], stem [Cout][27]->[27][Cout], SE fc2 [C][S]->[S][C]
+int transpose_f32(float* dst, const float* src, int R, int C, cudaStream_t s);
+
+}  // namespace ftc

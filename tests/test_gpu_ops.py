@@ -1,0 +1,165 @@
+"""GPU: single-op C-ABI entry points vs plain PyTorch fp32 references of the same op.
+Tolerances: fp32 SIMT path 1e-4 rel-L2 (accumulation order only); bf16 paths 1e-2 rel-L2 (operands are rounded to
+bf16 on both sides, the reference accumulates in fp32, the output is rounded to bf16 once)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from findtextcenternet_b200 import _lib, _ops
+    return _lib, _ops
+
+
+def _act(y, act):
+    if act == 1:
+        return F.silu(y)
+    if act == 2:
+        return F.gelu(y)
+    return y
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, stride, act, residual
+    (2, 24, 24, 64, 96, 3, 1, 1, False),
+    (1, 17, 13, 32, 32, 3, 1, 1, True),       # ragged M (221 rows), Cin=32 (4 chunks per tap)
+    (2, 32, 32, 32, 128, 3, 2, 1, False),     # stride 2
+    (1, 24, 24, 96, 384, 3, 1, 1, False),     # Cin=96: k-blocks straddle taps; N=384 -> 2 x 192 tiles
+    (2, 24, 24, 256, 64, 1, 1, 0, True),      # 1x1 project + residual
+    (1, 12, 12, 640, 1280, 1, 1, 1, False),   # N=1280 -> 5 x 256
+    (1, 48, 48, 192, 16, 3, 1, 0, False),     # tiny N
+    (3, 10, 10, 8, 24, 3, 1, 2, False),       # K=72 -> padded k-block, GELU
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("mode", ["simt_f32", "simt_bf16", "tc_bf16"])
+def test_conv2d(case, mode):
+    _lib, ops = _ops()
+    b, h, w, cin, cout, k, stride, act, use_res = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = torch.randn(b, h, w, cin, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)
+    scale = 0.5 + torch.rand(cout, generator=g)
+    bias = 0.3 * torch.randn(cout, generator=g)
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    res = torch.randn(b, ho, wo, cout, generator=g) if use_res else None
+    dt = torch.float32 if mode == "simt_f32" else torch.bfloat16
+    xq, wq = x.to(dt).float(), (wt.to(dt).float() if dt == torch.bfloat16 else wt)
+    resq = None if res is None else res.to(dt).float()
+    ref = F.conv2d(xq.permute(0, 3, 1, 2), wq, None, stride, (k - 1) // 2)
+    ref = ref * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    if resq is not None:
+        ref = ref + resq.permute(0, 3, 1, 2)
+    ref = _act(ref, act).permute(0, 2, 3, 1)
+    backend = _lib.GEMM_TCGEN05 if mode == "tc_bf16" else _lib.GEMM_SIMT
+    out = ops.conv2d(x.to(dt).cuda(), wt, stride, scale, bias, act, None if res is None else res.to(dt).cuda(),
+                     None, backend)
+    torch.cuda.synchronize()
+    tol = 1e-4 if mode == "simt_f32" else 1e-2
+    assert out.shape == ref.shape
+    assert rel_l2(out.float().cpu().numpy(), ref.numpy()) < tol
+
+
+@pytest.mark.parametrize("mode", ["simt_f32", "tc_bf16"])
+def test_conv2d_se_scaled_operand(mode):
+    """1x1 project conv with the SE excitation applied to the A operand (torchvision efficientnet.py MBConv:
+    block[2] scale then block[3] conv)."""
+    _lib, ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    b, h, w, cin, cout = 3, 12, 12, 384, 96
+    dt = torch.float32 if mode == "simt_f32" else torch.bfloat16
+    x = torch.randn(b, h, w, cin, generator=g)
+    wt = torch.randn(cout, cin, 1, 1, generator=g) / np.sqrt(cin)
+    a_scale = torch.rand(b, cin, generator=g)
+    xs = x.to(dt).float() * a_scale.view(b, 1, 1, cin)
+    if dt == torch.bfloat16:
+        xs = xs.to(dt).float()
+        wq = wt.to(dt).float()
+    else:
+        wq = wt
+    ref = F.conv2d(xs.permute(0, 3, 1, 2), wq).permute(0, 2, 3, 1)
+    backend = _lib.GEMM_TCGEN05 if mode == "tc_bf16" else _lib.GEMM_SIMT
+    out = ops.conv2d(x.to(dt).cuda(), wt, 1, None, None, 0, None, a_scale.cuda(), backend)
+    assert rel_l2(out.float().cpu().numpy(), ref.numpy()) < (1e-4 if mode == "simt_f32" else 1e-2)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("stride", [1, 2])
+def test_dwconv_se(dt, stride):
+    _lib, ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    b, h, w, c = 2, 24, 24, 384
+    x = torch.randn(b, h, w, c, generator=g).to(dt)
+    wt = torch.randn(c, 1, 3, 3, generator=g) / 3
+    scale = 0.5 + torch.rand(c, generator=g)
+    bias = 0.2 * torch.randn(c, generator=g)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, stride, 1, 1, c)
+    ref = F.silu(ref * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    se = torch.zeros(b, c, device="cuda")
+    out = ops.dwconv3x3(x.cuda(), wt.view(c, 9).t().contiguous().cuda(), scale.cuda(), bias.cuda(), stride, se)
+    tol = 1e-5 if dt == torch.float32 else 1e-2
+    assert rel_l2(out.float().cpu().numpy(), ref.permute(0, 2, 3, 1).numpy()) < tol
+    assert rel_l2(se.cpu().numpy(), ref.sum((2, 3)).numpy()) < (1e-4 if dt == torch.float32 else 2e-2)
+    # SE excitation (ops/misc.py:251-261)
+    s = 96
+    w1 = torch.randn(s, c, generator=g) / np.sqrt(c); b1 = 0.1 * torch.randn(s, generator=g)
+    w2 = torch.randn(c, s, generator=g) / np.sqrt(s); b2 = 0.1 * torch.randn(c, generator=g)
+    mean = ref.mean((2, 3))
+    ref_scale = torch.sigmoid(F.linear(F.silu(F.linear(mean, w1, b1)), w2, b2))
+    ho = ref.shape[2]
+    got = ops.se_fc(se, 1.0 / (ho * ho), w1.cuda(), b1.cuda(), w2.t().contiguous().cuda(), b2.cuda())
+    assert rel_l2(got.cpu().numpy(), ref_scale.numpy()) < (1e-4 if dt == torch.float32 else 1e-2)
+    assert float(se.abs().max()) == 0.0   # the kernel re-arms the accumulator
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_upsample2x_align_corners(dt):
+    _lib, ops = _ops()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 24, 24, 192, generator=g).to(dt)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
+    out = ops.upsample2x(x.cuda())
+    assert rel_l2(out.float().cpu().numpy(), ref.permute(0, 2, 3, 1).numpy()) < (1e-5 if dt == torch.float32 else 5e-3)
+
+
+def test_peak_pick_and_decode_match_oracle(golden_detector):
+    """Bit-exact peak index set; decoded boxes vs the numpy oracle of process_ocr_base.py:498-538."""
+    from findtextcenternet_b200 import _ops as ops
+    from findtextcenternet_b200.engine import peak_decode
+    from oracle import detector_oracle as DO
+    h10 = golden_detector["rand0_heatmap10"]
+    heat9 = torch.from_numpy(np.concatenate([h10[0:1], h10[2:]], 0)[None].copy()).cuda()
+    got10 = ops.peak_pick(heat9).cpu().numpy()[0]
+    assert np.array_equal(got10, h10)          # includes the -inf pattern
+    # plateau ties and borders: quantised random map
+    g = torch.Generator().manual_seed(9)
+    q = torch.round(torch.randn(2, 9, 64, 48, generator=g) * 2) / 2
+    got = ops.peak_pick(q.cuda()).cpu()
+    ref = DO.peak_pick(q)
+    assert torch.equal(got, ref)
+    # decode: synthetic feature map so the gather is checked too
+    feat = torch.randn(1, 100, 192, 192, generator=g)
+    for (x_i, y_i, pw, ph) in [(0, 0, 768, 768), (460, 920, 2148, 2148)]:
+        mask = DO.tile_mask(x_i, y_i, pw, ph)
+        ys, xs = np.nonzero(mask)
+        meta = torch.tensor([[x_i, y_i, xs.min(), xs.max() + 1, ys.min(), ys.max() + 1]], dtype=torch.int32).cuda()
+        count, loc, gf = peak_decode(heat9, feat.cuda(), meta, pw, ph, 0.4, 4096)
+        n = int(count[0])
+        ref_loc, ref_gf = DO.decode_tile(h10, feat[0].numpy(), x_i, y_i, pw, ph)
+        assert n == len(ref_loc) and n > 10
+        loc = loc[0, :n].cpu().numpy(); gf = gf[0, :n].cpu().numpy()
+        # identical peak SET (the reference's argsort is unstable, so order among equal scores is unspecified);
+        # device order must be non-increasing in score
+        assert np.all(np.diff(loc[:, 0]) <= 0)
+        key = lambda l: (int(l[1]), int(l[2]))
+        ref_by = {key(l): i for i, l in enumerate(ref_loc)}
+        assert sorted(ref_by) == sorted(key(l) for l in loc)
+        perm = np.array([ref_by[key(l)] for l in loc])
+        np.testing.assert_allclose(loc, ref_loc[perm], rtol=2e-5, atol=1e-6)
+        assert np.array_equal(gf, ref_gf[perm])
