@@ -53,6 +53,7 @@ SYMBOLS = {
     "ftc_detector_workspace_bytes": (_sz, [_vp, _i]),
     "ftc_detector_pack_weights": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(_i64), _vp, _sz, _vp]),
     "ftc_detector_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ftc_detector_tap": (_i, [_vp, _i, _i, _vp, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ftc_peak_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "ftc_peak_pick": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ftc_op_conv2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),

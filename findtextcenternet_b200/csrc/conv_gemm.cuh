@@ -1,7 +1,9 @@
 // Implicit-GEMM convolution / linear op shared by every dense layer of the hot path.
 //
-//   out[m, g*N + n] = act( (sum_k A[m,k] * W[g][n][k]) * scale[g*N+n] + bias_tab[case(m)][g*N+n]
-//                          + res1[m, n] + res2[m, n] )
+//   out[m, g*N + n] = act( (sum_k A[m,k] * W[g][n][k]) * scale[g*N+n] + bias_tab[case(m)][g*N+n] )
+//                     + res1[m, n] + res2[m, n]
+// (FusedMBConv with expand 1 adds its input AFTER the SiLU, torchvision efficientnet.py:224-230; every other
+//  residual user has act = none.  SwiGLU: residuals are added to the (x1, xg) pair columns before gating -- unused.)
 //
 // m enumerates output pixels (b, oy, ox) of an NHWC tensor; k enumerates (source, ky, kx, c):
 // first the taps of source A (shared by all groups), then the taps of source B (per-group channel

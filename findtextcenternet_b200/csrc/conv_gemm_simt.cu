@@ -117,12 +117,12 @@ __global__ void __launch_bounds__(NT) conv_gemm_simt_kernel(const ConvGemmParams
         int gn = g * p.N + n;
         if (p.scale) v *= p.scale[gn];
         if (p.bias_tab) v += p.bias_tab[(int64_t)cs * p.G * p.N + gn];
+        if (p.act != ACT_SWIGLU) v = apply_act<true>(v, p.act);   // residuals are added after the activation
         if (res1) {
           int64_t rr = p.res1_row_mod ? (m % p.res1_row_mod) : m;
           v += to_f(res1[rr * p.res1_stride + gn]);
         }
         if (res2) v += to_f(res2[(int64_t)m * p.res2_stride + gn]);
-        if (p.act != ACT_SWIGLU) v = apply_act<true>(v, p.act);
       }
       vals[j] = v;
     }

@@ -127,6 +127,13 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
     }
     v[i] = x;
   }
+  if (p.act == ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
+  } else if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+  }
   if (res1) {
     const bf16* rp = res1 + r1row * p.res1_stride + (int64_t)g * p.N + n0;
     if (full16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
@@ -164,13 +171,6 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
       for (int i = 0; i < 8; ++i) if (n0 + 2 * i + 1 < nvalid) op[i] = __float2bfloat16_rn(o[i]);
     }
     return;
-  }
-  if (p.act == ACT_SILU) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
-  } else if (p.act == ACT_GELU) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
   }
   if (p.out_layout == OUT_NCHW_F32) {
     float* op = reinterpret_cast<float*>(p.out) + (((int64_t)b * p.out_stride + chb + n0) * p.Ho + oy) * p.Wo + ox;

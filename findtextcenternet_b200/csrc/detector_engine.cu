@@ -77,6 +77,7 @@ struct ftc_detector {
   std::vector<std::function<int(const Lookup&, char*, cudaStream_t)>> pack_tasks;
   char* packed = nullptr;              // bound at pack time
   int Hq = 0, Wq = 0;                  // output resolution (H/4)
+  int tapC[4] = {0, 0, 0, 0}, tapH[4] = {0, 0, 0, 0}, tapW[4] = {0, 0, 0, 0};
 
   size_t walloc(size_t bytes) { size_t o = weight_bytes; weight_bytes = align_up(weight_bytes + bytes, 256); return o; }
   void need(int buf, size_t elems) { if (buf >= 0 && buf < BUF_COUNT && elems > buf_elems[buf]) buf_elems[buf] = elems; }
@@ -244,6 +245,7 @@ int ftc_detector::build() {
   const int tap_W[4] = {c.width / 4, c.width / 8, c.width / 16, c.width / 32};
   for (int i = 0; i < 4; ++i) FTC_REQUIRE(tap_H[i] == c.height / (4 << i), "unexpected tap resolution");
   Hq = c.height / 4; Wq = c.width / 4;
+  for (int i = 0; i < 4; ++i) { tapC[i] = tap_C[i]; tapH[i] = tap_H[i]; tapW[i] = tap_W[i]; }
 
   // ---- nine Leafmap heads, batched: N = n_heads * 192 per level ----
   const int NH = c.n_heads, CD = 192, NT = NH * CD;
@@ -443,6 +445,18 @@ size_t ftc_detector_workspace_bytes(const ftc_detector* d, int batch) {
   for (int i = 0; i < BUF_COUNT; ++i) off += align_up(d->buf_elems[i] * batch * d->esize, 256);
   off += 2 * align_up(d->se_c_max * batch * 4, 256);
   return off + 256;
+}
+
+int ftc_detector_tap(const ftc_detector* d, int tap, int batch, void* workspace, void** ptr, int* channels, int* h, int* w) {
+  FTC_REQUIRE(d && workspace && ptr && tap >= 0 && tap < 4, "bad argument");
+  const int ids[4] = {BUF_T1, BUF_T2, BUF_T3, BUF_T4};
+  size_t off = 0;
+  for (int i = 0; i < ids[tap]; ++i) off += align_up(d->buf_elems[i] * batch * d->esize, 256);
+  *ptr = (char*)workspace + off;
+  if (channels) *channels = d->tapC[tap];
+  if (h) *h = d->tapH[tap];
+  if (w) *w = d->tapW[tap];
+  return 0;
 }
 
 int ftc_detector_pack_weights(ftc_detector* d, int n, const char* const* names, const void* const* ptrs,

@@ -104,6 +104,19 @@ class DetectorEngine:
         return heat9, feat, heat10
 
 
+def read_tap(eng: DetectorEngine, tap: int, batch: int) -> torch.Tensor:
+    """Copy of backbone tap x{tap+1} [B,H,W,C] (engine dtype) after the last forward of ``batch`` images (tests)."""
+    ptr, c, h, w = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+    _lib.check(eng.lib.ftc_detector_tap(eng.handle, tap, batch, eng.workspace.data_ptr(), C.byref(ptr), C.byref(c),
+                                        C.byref(h), C.byref(w)), "ftc_detector_tap")
+    es = 4 if eng.precision == "fp32" else 2
+    off = ptr.value - eng.workspace.data_ptr()
+    n = batch * h.value * w.value * c.value
+    raw = eng.workspace[off:off + n * es]
+    dt = torch.float32 if es == 4 else torch.bfloat16
+    return raw.view(dt).view(batch, h.value, w.value, c.value).clone()
+
+
 def peak_decode(heat9: torch.Tensor, feat: torch.Tensor, tile_meta: torch.Tensor, page_w: float, page_h: float,
                 cut_off: float = 0.4, max_peaks: int = 4096):
     """Per-tile peak compaction + box decode on the device (process_ocr_base.py:498-538).

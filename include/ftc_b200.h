@@ -63,6 +63,10 @@ int ftc_detector_pack_weights(ftc_detector* d, int n, const char* const* names, 
 int ftc_detector_forward(ftc_detector* d, const float* images, int batch, float* heat9, float* feat, float* heat10,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* introspection (tests): device pointer of backbone tap `tap` (0..3 = x1..x4, NHWC, engine dtype) inside `workspace`
+ * after a forward of `batch` images; *channels / *hw receive its shape. */
+int ftc_detector_tap(const ftc_detector* d, int tap, int batch, void* workspace, void** ptr, int* channels, int* h, int* w);
+
 /* ---- per-tile peak compaction + box decode (process_ocr_base.py:498-538) ----
  * tile_meta: int32 [B][6] = {offset_x, offset_y, mask_xmin, mask_xmax, mask_ymin, mask_ymax} (device)
  * count: int32 [B]; loc: fp32 [B][max_peaks][9]; gfeat: fp32 [B][max_peaks][F]; scratch: 8*B*max_peaks bytes */

@@ -54,9 +54,10 @@ def test_conv2d(case, mode):
     resq = None if res is None else res.to(dt).float()
     ref = F.conv2d(xq.permute(0, 3, 1, 2), wq, None, stride, (k - 1) // 2)
     ref = ref * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    ref = _act(ref, act)                      # residual joins after the activation (FusedMBConv semantics)
     if resq is not None:
         ref = ref + resq.permute(0, 3, 1, 2)
-    ref = _act(ref, act).permute(0, 2, 3, 1)
+    ref = ref.permute(0, 2, 3, 1)
     backend = _lib.GEMM_TCGEN05 if mode == "tc_bf16" else _lib.GEMM_SIMT
     out = ops.conv2d(x.to(dt).cuda(), wt, stride, scale, bias, act, None if res is None else res.to(dt).cuda(),
                      None, backend)
