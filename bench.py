@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Benchmark of the detector hot path (BASELINE.json metric: 768x768 images/sec, detector forward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): CenterNetDetector forward (EfficientNetV2-XL + 9 Leafmap heads + 3x3 peak
+channel), synthetic uniform-[0,1) 768x768x3 images, batch 32 per GPU, bf16 operands / fp32 accumulate on tcgen05,
+seeded synthetic weights (BN-calibrated; findtextcenternet_b200/synthetic.py).  A "step" is one forward over one batch.
+
+`value`   : images/s with the batch already resident in HBM (CUDA events, max over ranks, L2 flushed between steps).
+`e2e`     : images/s through OCR_b200_Processer.detect_tiles: pinned HOST float32 NHWC 0..255 tiles -> H2D -> detector
+            -> on-device peak compaction/box decode -> D2H of (count, locations, glyphfeatures), all inside the timed region.
+`roofline`: tensor-pipe bound.  achieved = algorithmic FLOPs of the dominant kernel family (the tcgen05 implicit-GEMM
+            convolution, every dense conv launch of one forward) / the summed CUDA-event durations of those launches,
+            measured live by ftc_detector_forward_timed; peak = MEASURED_PEAKS.json bf16_tflops_sustained.
+`cpu_baseline`: the oracle port (oracle/detector_oracle.py, fp32 torch CPU ops restating the reference) on the host cores.
+--impl reference: the same CPU port timed as the reference arm (the reference is Python+torchvision and cannot travel
+            to the GPU box; oracle/ restates it and is pinned to it by tests/golden).
+Multi-GPU: pure data parallelism, no collective on the data path: each rank runs its own batch ("weak").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_IMAGE = 865.0e9     # SURVEY.md 8d / BASELINE.md section 2 (2*MAC over all convs, reference probe)
+METRIC = "detector_fwd_images_per_sec_768x768"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_burst": p.get("bf16_tflops", 1590.0), "bf16_sustained": p.get("bf16_tflops_sustained", 1400.0),
+                "hbm": p.get("hbm_gbs", 6650.0), "src": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_images_per_sec(n_images: int, repeats: int, warmup: int = 0):
+    """Oracle port (fp32 CPU) timed on the host cores: returns (img/s, threads, seconds per repeat list)."""
+    import torch
+    from findtextcenternet_b200 import synthetic
+    from oracle import detector_oracle as DO
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = synthetic.detector_state_dict(0)
+    x = synthetic.detector_input(n_images, 0, "rand")
+    times = []
+    for i in range(warmup + repeats):
+        t0 = time.perf_counter()
+        DO.detector_forward(sd, x)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return n_images * len(times) / sum(times), threads, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_img = 2 if threads >= 16 else 1
+    ips, threads, times = cpu_port_images_per_sec(n_img, args.steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CenterNetDetector forward, EfficientNetV2-XL + 9 Leafmap heads, 768x768x3, fp32 CPU",
+                   "images_per_step": n_img},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_img} image(s) per step x {args.steps} steps of the bench workload, oracle port on host cores"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from findtextcenternet_b200 import _lib, synthetic
+    from findtextcenternet_b200.process_ocr_b200 import OCR_b200_Processer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    B = args.batch
+    proc = OCR_b200_Processer(precision=args.precision, device=dev, detector_state_dict=synthetic.detector_state_dict(0))
+    det = proc.detector
+    det.detector.weights_frozen = True
+    g = torch.Generator().manual_seed(1000 + rank)
+    x_dev = torch.rand(B, 3, 768, 768, generator=g).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step():
+        return det(x_dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        # ---- timed region: K steps, device events, L2 flushed between steps (flush excluded from the sum) ----
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        l0 = _lib.launch_count()
+        barrier()
+        t_wall0 = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            step()
+            b.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = _lib.launch_count() - l0
+        clocks = sampler.stop()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        value = world * B * args.steps / (ms_total / 1e3)
+
+        # ---- e2e: pinned host NHWC 0..255 tiles -> H2D -> detector -> device peak decode -> D2H ----
+        tiles = (torch.rand(B, 768, 768, 3, generator=g) * 255.0).pin_memory()
+        offsets = [(0, 0)] * B
+        for _ in range(2):
+            proc.detect_tiles(tiles, offsets, 768, 768)
+        barrier()
+        e2e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            count, loc, gf = proc.detect_tiles(tiles, offsets, 768, 768)
+        barrier()
+        e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e_value = world * B * e2e_steps / float(e2e_t.item())
+        h2d = tiles.numel() * 4 + B * 6 * 4
+        d2h = count.numel() * 4 + loc.numel() * 4 + gf.numel() * 4
+
+        # ---- per-op CUDA-event profile of one forward -> roofline of the tcgen05 conv kernel family ----
+        roofline = cpu = None
+        if rank == 0:
+            eng = det.detector.engine(dev)
+            eng.forward_timed(x_dev)
+            ops = eng.forward_timed(x_dev)
+            peaks = load_peaks()
+            gemm_ms = sum(m for k, m, f in ops if k in (1, 2))
+            gemm_fl = sum(f for k, m, f in ops if k in (1, 2))
+            n_gemm = sum(1 for k, m, f in ops if k in (1, 2))
+            all_ms = sum(m for k, m, f in ops)
+            achieved = gemm_fl / (gemm_ms / 1e3) / 1e12
+            by_kind = {}
+            for k, m, f in ops:
+                d = by_kind.setdefault(k, [0.0, 0.0, 0])
+                d[0] += m; d[1] += f; d[2] += 1
+            names = {0: "stem", 1: "conv3x3_tc", 2: "conv1x1_tc", 3: "depthwise_se", 4: "se_fc", 5: "upsample"}
+            roofline = {
+                "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                "kernel": "conv_gemm_tc_kernel (tcgen05 implicit-GEMM conv), %d launches per forward" % n_gemm,
+                "flop_per_launch_avg": gemm_fl / max(n_gemm, 1), "ms_per_launch_avg": gemm_ms / max(n_gemm, 1),
+                "share_of_step": gemm_ms / all_ms, "peak_source": peaks["src"] + " bf16_tflops_sustained",
+                "whole_forward_tflops": FLOP_PER_IMAGE * (value / world) / 1e12,
+                "whole_forward_frac": FLOP_PER_IMAGE * (value / world) / 1e12 / peaks["bf16_sustained"],
+                "per_kind_ms": {names[k]: {"ms": round(v[0], 3), "tflops": (v[1] / (v[0] / 1e3) / 1e12 if v[0] > 0 else 0.0),
+                                           "launches": v[2]} for k, v in sorted(by_kind.items())},
+            }
+            if not args.no_cpu_baseline:
+                ips, threads, times = cpu_port_images_per_sec(1, 3, 1)
+                cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                       "sample": "1 image per pass x 3 passes (+1 warm-up) of the same forward, fp32 oracle port on the host cores"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision.startswith("bf16") else "f32", "data": "synthetic",
+        "config": {"workload": "CenterNetDetector forward (BASELINE.json configs[1]): EfficientNetV2-XL + 9 Leafmap heads, "
+                               "768x768x3 -> 192x192x(10+100)", "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"dp{world} (independent batches, no collective)", "precision": args.precision,
+                   "l2": "256 MiB flush buffer written between timed steps", "wall_s_timed_region": t_wall},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "OCR_b200_Processer.detect_tiles(pinned float32 NHWC 0..255 tiles)", "steps": e2e_steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16_simt", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,7 @@ PREC_F32, PREC_BF16 = 0, 1
 GEMM_SIMT, GEMM_TCGEN05 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_SWIGLU = 0, 1, 2, 3
 DT_F32, DT_BF16 = 0, 1
+INPUT_NCHW_UNIT, INPUT_NHWC_255 = 0, 1
 
 
 class StageCfg(C.Structure):
@@ -41,6 +42,11 @@ class DetectorConfig(C.Structure):
     ]
 
 
+class TransformerConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("enc_input_dim", "embed_dim", "head_num", "enc_blocks", "dec_blocks", "max_enc_len",
+                                       "max_dec_len", "precision", "gemm_backend")]
+
+
 # every symbol include/ftc_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 SYMBOLS = {
@@ -53,13 +59,27 @@ SYMBOLS = {
     "ftc_detector_workspace_bytes": (_sz, [_vp, _i]),
     "ftc_detector_pack_weights": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(_i64), _vp, _sz, _vp]),
     "ftc_detector_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ftc_detector_set_input_format": (_i, [_vp, _i]),
+    "ftc_detector_num_ops": (_i, [_vp]),
+    "ftc_detector_forward_timed": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _i, C.POINTER(C.c_float),
+                                        C.POINTER(C.c_double), C.POINTER(_i)]),
     "ftc_detector_tap": (_i, [_vp, _i, _i, _vp, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "ftc_transformer_create": (_i, [C.POINTER(TransformerConfig), C.POINTER(_vp)]),
+    "ftc_transformer_destroy": (None, [_vp]),
+    "ftc_transformer_weight_bytes": (_sz, [_vp]),
+    "ftc_transformer_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "ftc_transformer_pack_weights": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(_i64), _vp, _sz, _vp]),
+    "ftc_transformer_logit_stride": (_i, []),
+    "ftc_transformer_head_stride": (_i, []),
+    "ftc_transformer_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "ftc_transformer_predict": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, C.POINTER(_i), C.POINTER(_i), _vp, _sz, _vp]),
+    "ftc_mask_predict_step": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "ftc_peak_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "ftc_peak_pick": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ftc_op_conv2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "ftc_op_conv2d_wpack_bytes": (_sz, [_i, _i, _i]),
     "ftc_op_dwconv3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "ftc_op_se_fc": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "ftc_op_se_fc": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "ftc_op_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 

@@ -63,8 +63,9 @@ def se_fc(se_sum: torch.Tensor, inv_hw: float, w1, b1, w2t, b2) -> torch.Tensor:
     b, c = se_sum.shape
     s = w1.shape[0]
     out = torch.empty(b, c, dtype=torch.float32, device=se_sum.device)
+    hid = torch.empty(b, s, dtype=torch.float32, device=se_sum.device)
     with torch.cuda.device(se_sum.device):
-        _lib.check(lib.ftc_op_se_fc(se_sum.data_ptr(), out.data_ptr(), b, c, s, inv_hw, w1.data_ptr(), b1.data_ptr(),
+        _lib.check(lib.ftc_op_se_fc(se_sum.data_ptr(), out.data_ptr(), hid.data_ptr(), b, c, s, inv_hw, w1.data_ptr(), b1.data_ptr(),
                                     w2t.data_ptr(), b2.data_ptr(), _s(se_sum)), "ftc_op_se_fc")
     return out
 

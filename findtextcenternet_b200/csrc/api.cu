@@ -6,6 +6,7 @@
 #include "../../include/ftc_b200.h"
 #include "conv_gemm.cuh"
 #include "detector_ops.cuh"
+#include "transformer_ops.cuh"
 
 namespace ftc {
 
@@ -120,10 +121,16 @@ int ftc_op_dwconv3x3(const void* x, void* out, int dtype, int batch, int h, int 
   return dwconv3x3(x, out, dtype, batch, h, w, c, stride, w9c, scale, bias, se_sum, (cudaStream_t)stream);
 }
 
-int ftc_op_se_fc(float* sum, float* scale_out, int batch, int c, int s, float inv_hw, const float* w1, const float* b1,
-                 const float* w2t, const float* b2, void* stream) {
-  FTC_REQUIRE(sum && scale_out && w1 && b1 && w2t && b2, "null argument");
-  return se_fc(sum, scale_out, batch, c, s, inv_hw, w1, b1, w2t, b2, (cudaStream_t)stream);
+int ftc_op_se_fc(float* sum, float* scale_out, float* hid, int batch, int c, int s, float inv_hw, const float* w1,
+                 const float* b1, const float* w2t, const float* b2, void* stream) {
+  FTC_REQUIRE(sum && scale_out && hid && w1 && b1 && w2t && b2, "null argument");
+  return se_fc(sum, scale_out, hid, batch, c, s, inv_hw, w1, b1, w2t, b2, (cudaStream_t)stream);
+}
+
+int ftc_mask_predict_step(const float* logits, int ld, int head_ld, const int64_t* dec_in, int64_t* ids, float* prob,
+                          int64_t* next_in, int* flags, int rows, void* stream) {
+  FTC_REQUIRE(logits && dec_in && ids && prob && next_in && flags && rows > 0, "bad argument");
+  return mask_predict_step(logits, ld, head_ld, dec_in, ids, prob, next_in, flags, rows, (cudaStream_t)stream);
 }
 
 int ftc_op_upsample2x(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream) {

@@ -12,7 +12,7 @@ typedef __nv_bfloat16 bf16;
 
 enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_SWIGLU = 3 };
 enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
-enum OutLayout : int { OUT_NHWC = 0, OUT_NCHW_F32 = 1 };
+enum OutLayout : int { OUT_NHWC = 0, OUT_NCHW_F32 = 1, OUT_NHWC_F32 = 2 };   // NHWC = row-major [M, out_stride]
 
 // error plumbing: C-ABI entry points return negative codes, message kept per thread
 void set_error(const std::string& msg);

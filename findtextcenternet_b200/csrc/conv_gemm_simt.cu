@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(NT) conv_gemm_simt_kernel(const ConvGemmParams
       int ch = p.out_ch_base[g] + n;
       if (p.out_layout == OUT_NCHW_F32) {
         reinterpret_cast<float*>(p.out)[(((int64_t)b * p.out_stride + ch) * p.Ho + oy) * p.Wo + ox] = vals[j];
+      } else if (p.out_layout == OUT_NHWC_F32) {
+        reinterpret_cast<float*>(p.out)[(int64_t)m * p.out_stride + ch] = vals[j];
       } else {
         reinterpret_cast<T*>(p.out)[(int64_t)m * p.out_stride + ch] = from_f<T>(vals[j]);
       }

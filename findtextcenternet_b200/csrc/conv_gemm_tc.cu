@@ -20,7 +20,7 @@ namespace ftc {
 namespace {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 288;
+constexpr int TC_THREADS = 416;         // 4 producer + 1 MMA + 8 epilogue warps
 constexpr int TC_LAG = 2;                 // cp.async groups kept in flight per producer thread
 constexpr uint32_t A_STAGE_BYTES = TC_BM * 128;
 constexpr int TC_MAX_STAGES = 6;
@@ -110,26 +110,34 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int NT, int G) {
 }
 
 
-// one row x 16 accumulator columns: scale / bias / residuals / activation / store
+// SiLU with ONE SFU op per element: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx.f32, rel. error ~2^-11:
+// below bf16 output rounding).  The exp+rcp form costs two MUFU ops and made N=256 SiLU epilogues SFU-bound.
+__device__ __forceinline__ float silu_tanh(float x) {
+  float h = 0.5f * x, t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+// one row x 16 accumulator columns: scale / bias / activation / residuals / store.
+// sscale / sbias point at this tile's staged per-column vectors in shared memory (column c0 of the tile).
 __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const uint32_t (&raw16)[16], int g, int n0, int m,
                                                int b, int oy, int ox, int hw, int64_t r1row, int nvalid, int chb,
-                                               const float* __restrict__ scale_row, const float* __restrict__ bias_row,
+                                               const float* __restrict__ sscale, const float* __restrict__ sbias,
                                                const bf16* __restrict__ res1, const bf16* __restrict__ res2) {
   float v[16];
   const bool full16 = n0 + 16 <= p.N;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float x = __uint_as_float(raw16[i]);
-    int n = n0 + i;
-    if (full16 || n < p.N) {
-      if (scale_row) x *= __ldg(scale_row + n);
-      if (bias_row) x += __ldg(bias_row + n);
-    }
-    v[i] = x;
+  for (int i = 0; i < 16; i += 4) {
+    const float4 sc = *reinterpret_cast<const float4*>(sscale + i);
+    const float4 bi = *reinterpret_cast<const float4*>(sbias + i);
+    v[i + 0] = fmaf(__uint_as_float(raw16[i + 0]), sc.x, bi.x);
+    v[i + 1] = fmaf(__uint_as_float(raw16[i + 1]), sc.y, bi.y);
+    v[i + 2] = fmaf(__uint_as_float(raw16[i + 2]), sc.z, bi.z);
+    v[i + 3] = fmaf(__uint_as_float(raw16[i + 3]), sc.w, bi.w);
   }
   if (p.act == ACT_SILU) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = silu_f(v[i]);
+    for (int i = 0; i < 16; ++i) v[i] = silu_tanh(v[i]);
   } else if (p.act == ACT_GELU) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
@@ -176,6 +184,15 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
     float* op = reinterpret_cast<float*>(p.out) + (((int64_t)b * p.out_stride + chb + n0) * p.Ho + oy) * p.Wo + ox;
 #pragma unroll
     for (int i = 0; i < 16; ++i) if (n0 + i < nvalid) op[(int64_t)i * hw] = v[i];
+  } else if (p.out_layout == OUT_NHWC_F32) {
+    float* op = reinterpret_cast<float*>(p.out) + (int64_t)m * p.out_stride + chb + n0;
+    if (n0 + 16 <= nvalid && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (n0 + i < nvalid) op[i] = v[i];
+    }
   } else {
     bf16* op = reinterpret_cast<bf16*>(p.out) + (int64_t)m * p.out_stride + chb + n0;
     if (n0 + 16 <= nvalid && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
@@ -189,6 +206,10 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
     }
   }
 }
+
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int STAGED_FLOATS = 10 * 256;   // per-tile scale[BN] + bias[ncase<=9][BN]
 
 template <bool SE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p,
@@ -205,13 +226,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
   auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + (size_t)S * stage_bytes + 8 * (2 * S + 4));
+  uint8_t* after_bars = smem + (size_t)S * stage_bytes + 8 * (2 * S + 4);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(after_bars);
+  float* staged = reinterpret_cast<float*>(after_bars + 16);      // [STAGED_FLOATS], 16 B aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 4 + 1); mbar_init(empty_bar(s), 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -237,13 +260,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
     const bf16* wgt = reinterpret_cast<const bf16*>(p.w);
     int stage = 0;
     uint32_t phase = 0;
-    int arr_stage = 0;               // next stage whose A fill this thread still has to publish
+    int arr_stage = 0;               // oldest stage whose A fill this thread still has to publish
+    int arr_kb = 0;                  // its k-block index inside the current tile (SE scaling needs the channel)
     uint32_t pending = 0;            // committed-but-unpublished cp.async groups
+    int img[8];
+
+    // publish the oldest pending stage: its cp.async group has completed (caller waited); SE: scale in place first
+    auto publish = [&]() {
+      if (SE) {
+        const uint32_t e = __ldg(p.ktab + arr_kb * 8 + j);
+        if (e & KT_VALID) {
+          const int c = kt_c(e);
+          const uint32_t a_dst = sbase + (uint32_t)arr_stage * stage_bytes + row_off;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint4 u;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                         : "r"(a_dst + (uint32_t)i * 2048u) : "memory");
+            const float4* sp = reinterpret_cast<const float4*>(p.a_scale + (int64_t)img[i] * p.a_scale_stride + c);
+            const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            float2 f;
+            f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * s0.x, f.y * s0.y);
+            f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * s0.z, f.y * s0.w);
+            f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * s1.x, f.y * s1.y);
+            f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * s1.z, f.y * s1.w);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_dst + (uint32_t)i * 2048u), "r"(u.x), "r"(u.y),
+                         "r"(u.z), "r"(u.w) : "memory");
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(arr_stage));
+      arr_stage = (arr_stage + 1 == S) ? 0 : arr_stage + 1;
+      ++arr_kb;
+      --pending;
+    };
+
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, NT, G);
       int pixoff[8];
       uint32_t yx[8];
-      int img[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         int m = tc.m0 + rbase + 16 * i;
@@ -260,6 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
         }
       }
       const bf16* wtile = wgt + (size_t)(tc.g * NT + tc.nt) * NKB * ((size_t)BN * 64);
+      if (SE) arr_kb = 0;            // SE drains at tile end, so pending == 0 here
       for (int kb = 0; kb < NKB; ++kb) {
         const uint32_t e = __ldg(p.ktab + kb * 8 + j);
         const bool srcb = (e & KT_SRCB) != 0;
@@ -268,81 +327,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
         const int pstride = srcb ? p.b_pix_stride : p.a_pix_stride;
         const int dpix = ky * p.W + kx;
         const bool evalid = (e & KT_VALID) != 0;
-        uint4 regs[SE ? 8 : 1];
-        if (SE) {
-          // register-staged path (SE-scaled A operand): issue the loads before blocking on the stage
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint32_t y = (yx[i] >> 16) + ky, x = (yx[i] & 0xFFFFu) + kx;
-            bool ok = evalid && y >= 1u && y <= (uint32_t)p.H && x >= 1u && x <= (uint32_t)p.W;
-            regs[SE ? i : 0] = ok ? __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(pixoff[i] + dpix) * pstride))
-                                  : make_uint4(0, 0, 0, 0);
-          }
-        }
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t a_dst = sbase + (uint32_t)stage * stage_bytes;
         if (t == 0) {
           mbar_arrive_expect_tx(full_bar(stage), b_bytes);
           bulk_copy_g2s(a_dst + A_STAGE_BYTES, wtile + (size_t)kb * BN * 64, b_bytes, full_bar(stage));
         }
-        if (SE) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float v[8];
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&regs[SE ? i : 0]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { float2 f = __bfloat1622float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
-            if (evalid) {
-              const float4* sp = reinterpret_cast<const float4*>(p.a_scale + (int64_t)img[i] * p.a_scale_stride + c);
-              float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
-              v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
-              v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
-            }
-            uint4 u;
-            __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) o[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_dst + row_off + (uint32_t)i * 2048u), "r"(u.x),
-                         "r"(u.y), "r"(u.z), "r"(u.w)
-                         : "memory");
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_bar(stage));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint32_t y = (yx[i] >> 16) + ky, x = (yx[i] & 0xFFFFu) + kx;
-            bool ok = evalid && y >= 1u && y <= (uint32_t)p.H && x >= 1u && x <= (uint32_t)p.W;
-            const bf16* src = ok ? base + (int64_t)(pixoff[i] + dpix) * pstride : base;
-            cp_async16(a_dst + row_off + (uint32_t)i * 2048u, src, ok ? 16u : 0u);
-          }
-          cp_async_commit();
-          ++pending;
-          if (pending > (uint32_t)TC_LAG) {
-            cp_async_wait<TC_LAG>();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(arr_stage));
-            arr_stage = (arr_stage + 1 == S) ? 0 : arr_stage + 1;
-            --pending;
-          }
+        for (int i = 0; i < 8; ++i) {
+          uint32_t y = (yx[i] >> 16) + ky, x = (yx[i] & 0xFFFFu) + kx;
+          bool ok = evalid && y >= 1u && y <= (uint32_t)p.H && x >= 1u && x <= (uint32_t)p.W;
+          const bf16* src = ok ? base + (int64_t)(pixoff[i] + dpix) * pstride : base;
+          cp_async16(a_dst + row_off + (uint32_t)i * 2048u, src, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        ++pending;
+        if (pending > (uint32_t)TC_LAG) {
+          cp_async_wait<TC_LAG>();
+          publish();
         }
         stage = (stage + 1 == S) ? 0 : stage + 1;
         phase ^= (stage == 0) ? 1u : 0u;
       }
-    }
-    if (!SE) {
-      // drain: publish the last (<= TC_LAG) stages
-      cp_async_wait<0>();
-      fence_proxy_async();
-      __syncwarp();
-      while (pending > 0) {
-        if (lane == 0) mbar_arrive(full_bar(arr_stage));
-        arr_stage = (arr_stage + 1 == S) ? 0 : arr_stage + 1;
-        --pending;
+      if (SE) {      // the scale rows (img[]) belong to this tile: publish everything before moving on
+        cp_async_wait<0>();
+        while (pending > 0) publish();
       }
     }
+    cp_async_wait<0>();
+    while (pending > 0) publish();
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
@@ -373,15 +386,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue (8 warps: 4 lane quarters x 2 column halves)
+    const int ew = warp - 5;                   // 0..7
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                  // which 16-column chunks (even / odd)
+    const int etid = threadIdx.x - 5 * 32;     // 0..255
     const int row = q * 32 + lane;
     const bf16* res1 = reinterpret_cast<const bf16*>(p.res1);
     const bf16* res2 = reinterpret_cast<const bf16*>(p.res2);
+    float* sscale = staged;                    // [BN]
+    float* sbias = staged + 256;               // [ncase][BN]
     uint32_t titer = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
       const TileCoord tc = decode_tile(tile, NT, G);
       const uint32_t acc = titer & 1u;
+      // stage this tile's per-column scale / bias (the previous tile's readers are past this barrier)
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      {
+        const int ncol0 = tc.nt * BN;
+        for (int c = etid; c < BN; c += EPI_THREADS) {
+          const int n = ncol0 + c;
+          sscale[c] = (p.scale && n < p.N) ? __ldg(p.scale + (int64_t)tc.g * p.N + n) : 1.f;
+        }
+        for (int c = etid; c < p.ncase * BN; c += EPI_THREADS) {
+          const int cs_ = c / BN, cc = c - cs_ * BN;
+          const int n = ncol0 + cc;
+          sbias[c] = (p.bias_tab && n < p.N) ? __ldg(p.bias_tab + ((int64_t)cs_ * G + tc.g) * p.N + n) : 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       mbar_wait(tfull_bar(acc), (titer >> 1) & 1u);
       tc_fence_after();
       const int m = tc.m0 + row;
@@ -390,20 +423,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
       if (mvalid) { b = m / hw; int r = m - b * hw; oy = r / p.Wo; ox = r - oy * p.Wo; }
       int cs = 0;
       if (p.ncase == 9) cs = (oy == 0 ? 0 : (oy == p.Ho - 1 ? 2 : 1)) * 3 + (ox == 0 ? 0 : (ox == p.Wo - 1 ? 2 : 1));
-      const float* bias_row = p.bias_tab ? p.bias_tab + (int64_t)cs * G * p.N + (int64_t)tc.g * p.N : nullptr;
-      const float* scale_row = p.scale ? p.scale + (int64_t)tc.g * p.N : nullptr;
       const int64_t r1row = p.res1_row_mod ? (m % p.res1_row_mod) : m;
       const int nvalid = min(p.N, p.n_valid[tc.g]);
       const int chb = p.out_ch_base[tc.g];
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = half * 16; c0 < BN; c0 += 32) {
         const int n0 = tc.nt * BN + c0;
         if (n0 >= p.N) break;                       // warp-uniform
         uint32_t raw16[16];
         __syncwarp();                               // tcgen05.ld is warp-collective: reconverge first
         tmem_ld16(t_addr + (uint32_t)c0, raw16);
         tmem_ld_wait();
-        if (mvalid) epilogue_store(p, raw16, tc.g, n0, m, b, oy, ox, hw, r1row, nvalid, chb, scale_row, bias_row, res1, res2);
+        if (mvalid)
+          epilogue_store(p, raw16, tc.g, n0, m, b, oy, ox, hw, r1row, nvalid, chb, sscale + c0, sbias + cs * BN + c0, res1, res2);
       }
       tc_fence_before();
       __syncwarp();
@@ -462,7 +494,7 @@ int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan) {
   plan->NT = best_nt;
   plan->NKB = p.K / KBLOCK;
   int stage_bytes = (int)A_STAGE_BYTES + best_bn * 128;
-  int s = (200 * 1024) / stage_bytes;
+  int s = (208 * 1024) / stage_bytes;
   plan->stages = s > TC_MAX_STAGES ? TC_MAX_STAGES : (s < 3 ? 3 : s);
   return 0;
 }
@@ -501,7 +533,7 @@ int conv_gemm_tc(const ConvGemmParams& p, cudaStream_t stream) {
   }
   const int m_tiles = ceil_div(p.M, TC_BM);
   const int num_tiles = m_tiles * p.tc.NT * p.G;
-  size_t smem = (size_t)p.tc.stages * (A_STAGE_BYTES + (size_t)p.tc.BN * 128) + 1024 + 256;
+  size_t smem = (size_t)p.tc.stages * (A_STAGE_BYTES + (size_t)p.tc.BN * 128) + 1024 + 256 + STAGED_FLOATS * 4;
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: the CTA owns all 512 TMEM columns
   FTC_REQUIRE(smem <= 227 * 1024, "smem budget");
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;

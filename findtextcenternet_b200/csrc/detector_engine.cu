@@ -76,6 +76,7 @@ struct ftc_detector {
   size_t scratch_off = 0;              // packing scratch (floats) inside the packed buffer
   std::vector<std::function<int(const Lookup&, char*, cudaStream_t)>> pack_tasks;
   char* packed = nullptr;              // bound at pack time
+  int input_format = 0;                // FTC_INPUT_*
   int Hq = 0, Wq = 0;                  // output resolution (H/4)
   int tapC[4] = {0, 0, 0, 0}, tapH[4] = {0, 0, 0, 0}, tapW[4] = {0, 0, 0, 0};
 
@@ -356,8 +357,26 @@ int ftc_detector::build() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// flops (2*MAC) of one op for `B` images
+static double op_flops(const Op& op, int B) {
+  switch (op.type) {
+    case Op::STEM: return 2.0 * B * (op.H / 2) * (op.W / 2) * 27.0 * op.C;
+    case Op::DW: { int Ho = (op.H - 1) / op.stride + 1, Wo = (op.W - 1) / op.stride + 1; return 2.0 * B * Ho * Wo * 9.0 * op.C; }
+    case Op::SE: return 4.0 * B * (double)op.C * op.S;
+    case Op::UP: return 0.0;
+    case Op::GEMM: {
+      const GemmOp& g = op.g;
+      double kreal = (double)g.ksize * g.ksize * (g.CA + g.CB);
+      double n = 0;
+      for (int i = 0; i < g.G; ++i) n += g.n_valid[i];
+      return 2.0 * B * g.Ho * g.Wo * kreal * n;
+    }
+  }
+  return 0.0;
+}
+
 static int detector_forward_impl(ftc_detector* d, const float* images, int B, float* heat9, float* feat, float* heat10,
-                                 void* workspace, size_t ws_bytes, cudaStream_t s) {
+                                 void* workspace, size_t ws_bytes, cudaStream_t s, cudaEvent_t* ev = nullptr) {
   FTC_REQUIRE(d->packed != nullptr, "ftc_detector_pack_weights must be called before forward");
   FTC_REQUIRE(ws_bytes >= ftc_detector_workspace_bytes(d, B), "workspace too small");
   char* ws = (char*)workspace;
@@ -366,6 +385,7 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
   for (int i = 0; i < BUF_COUNT; ++i) { bufp[i] = ws + off; off += align_up(d->buf_elems[i] * B * d->esize, 256); }
   float* se_sum = (float*)(ws + off); off += align_up(d->se_c_max * B * 4, 256);
   float* se_scale = (float*)(ws + off); off += align_up(d->se_c_max * B * 4, 256);
+  float* se_hid = (float*)(ws + off); off += align_up((size_t)256 * B * 4, 256);
   FTC_CHECK_CUDA(cudaMemsetAsync(se_sum, 0, d->se_c_max * B * 4, s));
   auto bp = [&](int id) -> void* {
     if (id == BUF_NONE) return nullptr;
@@ -374,11 +394,14 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
     return bufp[id];
   };
   char* P = d->packed;
+  int op_index = 0;
   for (const Op& op : d->ops) {
     int rc = 0;
+    if (ev) FTC_CHECK_CUDA(cudaEventRecord(ev[op_index], s));
+    ++op_index;
     switch (op.type) {
       case Op::STEM:
-        rc = stem_conv(images, bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, (const float*)(P + op.w_off),
+        rc = stem_conv(images, d->input_format, bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, (const float*)(P + op.w_off),
                        (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), s);
         break;
       case Op::DW:
@@ -386,7 +409,7 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
                        (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), se_sum, s);
         break;
       case Op::SE:
-        rc = se_fc(se_sum, se_scale, B, op.C, op.S, 1.0f / (float)(op.H * op.W), (const float*)(P + op.w_off),
+        rc = se_fc(se_sum, se_scale, se_hid, B, op.C, op.S, 1.0f / (float)(op.H * op.W), (const float*)(P + op.w_off),
                    (const float*)(P + op.b1_off), (const float*)(P + op.w2_off), (const float*)(P + op.b2_off), s);
         break;
       case Op::UP:
@@ -419,6 +442,7 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
     }
     if (rc) return rc;
   }
+  if (ev) FTC_CHECK_CUDA(cudaEventRecord(ev[op_index], s));
   if (heat10) return peak_pick(heat9, heat10, B, d->Hq, d->Wq, s);
   return 0;
 }
@@ -443,8 +467,41 @@ size_t ftc_detector_workspace_bytes(const ftc_detector* d, int batch) {
   if (!d) return 0;
   size_t off = 0;
   for (int i = 0; i < BUF_COUNT; ++i) off += align_up(d->buf_elems[i] * batch * d->esize, 256);
-  off += 2 * align_up(d->se_c_max * batch * 4, 256);
+  off += 2 * align_up(d->se_c_max * batch * 4, 256) + align_up((size_t)256 * batch * 4, 256);
   return off + 256;
+}
+
+int ftc_detector_set_input_format(ftc_detector* d, int fmt) {
+  FTC_REQUIRE(d && (fmt == FTC_INPUT_NCHW_UNIT || fmt == FTC_INPUT_NHWC_255), "bad input format");
+  d->input_format = fmt;
+  return 0;
+}
+
+int ftc_detector_num_ops(const ftc_detector* d) { return d ? (int)d->ops.size() : 0; }
+
+int ftc_detector_forward_timed(ftc_detector* d, const float* images, int batch, float* heat9, float* feat, void* workspace,
+                               size_t workspace_bytes, void* stream, int max_ops, float* op_ms, double* op_flop,
+                               int* op_kind) {
+  FTC_REQUIRE(d && images && heat9 && feat && workspace && op_ms && op_flop && op_kind, "bad argument");
+  const int n = (int)d->ops.size();
+  FTC_REQUIRE(max_ops >= n, "op arrays too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) FTC_CHECK_CUDA(cudaEventCreate(&e));
+  int rc = detector_forward_impl(d, images, batch, heat9, feat, nullptr, workspace, workspace_bytes, s, ev.data());
+  if (rc == 0) {
+    FTC_CHECK_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) {
+      FTC_CHECK_CUDA(cudaEventElapsedTime(&op_ms[i], ev[i], ev[i + 1]));
+      op_flop[i] = op_flops(d->ops[i], batch);
+      const Op& op = d->ops[i];
+      // kind: 0 stem, 1 dense 3x3 conv, 2 1x1 conv, 3 depthwise, 4 SE, 5 upsample
+      op_kind[i] = op.type == Op::STEM ? 0 : op.type == Op::GEMM ? (op.g.ksize == 3 ? 1 : 2) : op.type == Op::DW ? 3
+                   : op.type == Op::SE ? 4 : 5;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
 int ftc_detector_tap(const ftc_detector* d, int tap, int batch, void* workspace, void** ptr, int* channels, int* h, int* w) {

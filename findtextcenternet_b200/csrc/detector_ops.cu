@@ -7,7 +7,7 @@ namespace ftc {
 
 // ------------------------------------------------------------------------------------------------
 // stem
-template <typename T, int COUT>
+template <typename T, int COUT, bool NHWC255>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ img, T* __restrict__ out, int B,
                                                         int H, int W, const float* __restrict__ w,
                                                         const float* __restrict__ scale, const float* __restrict__ bias) {
@@ -33,7 +33,12 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
       for (int kx = 0; kx < 3; ++kx) {
         int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
         float v = 0.f;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[(((int64_t)b * 3 + c) * H + iy) * W + ix] * 2.f - 1.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          if (NHWC255)   // backend-ABI tile: fp32 NHWC 0..255 (process_ocr_torch.py:44 divides by 255 first)
+            v = (img[(((int64_t)b * H + iy) * W + ix) * 3 + c] / 255.f) * 2.f - 1.f;
+          else
+            v = img[(((int64_t)b * 3 + c) * H + iy) * W + ix] * 2.f - 1.f;
+        }
         const float* wk = &sw[((c * 3 + ky) * 3 + kx) * COUT];
 #pragma unroll
         for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wk[o], acc[o]);
@@ -51,12 +56,16 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
   }
 }
 
-int stem_conv(const float* img, void* out, int dtype, int B, int H, int W, int Cout, const float* w,
+int stem_conv(const float* img, int nhwc255, void* out, int dtype, int B, int H, int W, int Cout, const float* w,
               const float* scale, const float* bias, cudaStream_t s) {
   FTC_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem needs even H, W");
   int64_t M = (int64_t)B * (H / 2) * (W / 2);
   int grid = (int)((M + 127) / 128);
-#define LAUNCH(TT, CC) stem_conv_kernel<TT, CC><<<grid, 128, 0, s>>>(img, (TT*)out, B, H, W, w, scale, bias)
+#define LAUNCH(TT, CC)                                                                            \
+  do {                                                                                            \
+    if (nhwc255) stem_conv_kernel<TT, CC, true><<<grid, 128, 0, s>>>(img, (TT*)out, B, H, W, w, scale, bias); \
+    else stem_conv_kernel<TT, CC, false><<<grid, 128, 0, s>>>(img, (TT*)out, B, H, W, w, scale, bias);        \
+  } while (0)
   if (Cout == 32) { if (dtype == DT_F32) LAUNCH(float, 32); else LAUNCH(bf16, 32); }
   else if (Cout == 24) { if (dtype == DT_F32) LAUNCH(float, 24); else LAUNCH(bf16, 24); }
   else FTC_REQUIRE(false, "stem Cout must be 24 or 32");
@@ -66,125 +75,163 @@ int stem_conv(const float* img, void* out, int dtype, int B, int H, int W, int C
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 3x3 + BN + SiLU + SE partial sums.  block (32 chunk lanes, 8 pixel lanes), 64 pixels per block.
+// depthwise 3x3 + BN + SiLU + SE partial sums.
+// One CTA = a TH x TW output tile x 64 channels.  The (TH-1)*s+3 x (TW-1)*s+3 input halo tile is staged ONCE in shared
+// memory with full-line (128 B per pixel) coalesced loads, so HBM/L2 sees each input ~1.4x instead of 9x; the 9 taps
+// are 16-byte shared-memory reads.  tid = pixel_lane * 8 + chunk (8 channels per thread).
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W,
-                                                        int C, int stride, int Ho, int Wo,
+                                                        int C, int stride, int Ho, int Wo, int TH, int TW, int tiles_x,
                                                         const float* __restrict__ w, const float* __restrict__ scale,
                                                         const float* __restrict__ bias, float* __restrict__ se_sum) {
-  __shared__ float red[8][32][8];
-  const int cx = threadIdx.x, py = threadIdx.y;
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  T* tile = reinterpret_cast<T*>(dw_smem);                       // [IH][IW][64]
+  const int IH = (TH - 1) * stride + 3, IW = (TW - 1) * stride + 3;
+  float* red = reinterpret_cast<float*>(dw_smem + (((size_t)IH * IW * 64 * sizeof(T)) + 15) / 16 * 16);   // [32][64]
+  const int tid = threadIdx.x, chunk = tid & 7, plane = tid >> 3;
   const int b = blockIdx.z;
-  const int c0 = (blockIdx.y * 32 + cx) * 8;
-  const bool active = c0 < C;
+  const int c0 = blockIdx.y * 64 + chunk * 8;
+  const bool cvalid = c0 < C;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int oy0 = ty * TH, ox0 = tx * TW;
+  const int iy0 = oy0 * stride - 1, ix0 = ox0 * stride - 1;
+  // ---- stage the halo tile (zeros outside the image) ----
+  for (int p = plane; p < IH * IW; p += 32) {
+    int py = p / IW, px = p - py * IW;
+    int iy = iy0 + py, ix = ix0 + px;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    float4 f0 = make_float4(0, 0, 0, 0), f1 = f0;
+    const bool ok = cvalid && iy >= 0 && iy < H && ix >= 0 && ix < W;
+    if (sizeof(T) == 2) {
+      if (ok) v = *reinterpret_cast<const uint4*>(in + (((int64_t)b * H + iy) * W + ix) * C + c0);
+      *reinterpret_cast<uint4*>(tile + (size_t)p * 64 + chunk * 8) = v;
+    } else {
+      if (ok) {
+        const float4* src = reinterpret_cast<const float4*>(in + (((int64_t)b * H + iy) * W + ix) * C + c0);
+        f0 = src[0]; f1 = src[1];
+      }
+      float4* dst = reinterpret_cast<float4*>(tile + (size_t)p * 64 + chunk * 8);
+      dst[0] = f0; dst[1] = f1;
+    }
+  }
   float wk[9][8], sc[8], bi[8], ssum[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { ssum[j] = 0.f; sc[j] = 0.f; bi[j] = 0.f; }
-  if (active) {
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) wk[t][j] = w[t * C + c0 + j];
+    for (int j = 0; j < 8; ++j) wk[t][j] = cvalid ? w[t * C + c0 + j] : 0.f;
+  if (cvalid) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; bi[j] = bias[c0 + j]; }
   }
-  const int npix = Ho * Wo;
-  if (active) {
-    for (int it = 0; it < 8; ++it) {
-      int pidx = blockIdx.x * 64 + it * 8 + py;
-      if (pidx >= npix) break;
-      int oy = pidx / Wo, ox = pidx - oy * Wo;
-      float acc[8];
+  __syncthreads();
+  const int npix = TH * TW;
+  for (int p = plane; p < npix; p += 32) {
+    const int py = p / TW, px = p - py * TW;
+    const int oy = oy0 + py, ox = ox0 + px;
+    if (oy >= Ho || ox >= Wo || !cvalid) continue;
+    float acc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        int iy = oy * stride - 1 + ky;
-        if (iy < 0 || iy >= H) continue;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          int ix = ox * stride - 1 + kx;
-          if (ix < 0 || ix >= W) continue;
-          float v[8];
-          load8(in + (((int64_t)b * H + iy) * W + ix) * C + c0, v);
+      for (int kx = 0; kx < 3; ++kx) {
+        float v[8];
+        load8(tile + ((size_t)(py * stride + ky) * IW + (px * stride + kx)) * 64 + chunk * 8, v);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wk[ky * 3 + kx][j], acc[j]);
-        }
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wk[ky * 3 + kx][j], acc[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = acc[j] * sc[j] + bi[j];
-        acc[j] = sizeof(T) == 4 ? silu_precise(t) : silu_f(t);
-        ssum[j] += acc[j];
-      }
-      store8(out + ((int64_t)b * npix + pidx) * C + c0, acc);
+    for (int j = 0; j < 8; ++j) {
+      float t = acc[j] * sc[j] + bi[j];
+      acc[j] = sizeof(T) == 4 ? silu_precise(t) : silu_f(t);
+      ssum[j] += acc[j];
     }
+    store8(out + (((int64_t)b * Ho + oy) * Wo + ox) * C + c0, acc);
   }
   if (se_sum == nullptr) return;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) red[py][cx][j] = ssum[j];
+  for (int j = 0; j < 8; ++j) red[plane * 64 + chunk * 8 + j] = ssum[j];
   __syncthreads();
-  if (py == 0 && active) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) t += red[q][cx][j];
-      atomicAdd(&se_sum[(int64_t)b * C + c0 + j], t);
-    }
+  if (tid < 64) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) t += red[q * 64 + tid];
+    const int c = blockIdx.y * 64 + tid;
+    if (c < C) atomicAdd(&se_sum[(int64_t)b * C + c], t);
   }
 }
 
 int dwconv3x3(const void* in, void* out, int dtype, int B, int H, int W, int C, int stride, const float* w,
               const float* scale, const float* bias, float* se_sum, cudaStream_t s) {
   FTC_REQUIRE(C % 8 == 0, "depthwise channels must be a multiple of 8");
+  FTC_REQUIRE(stride == 1 || stride == 2, "depthwise stride must be 1 or 2");
   int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;   // k=3, pad=1
-  dim3 grid(ceil_div(Ho * Wo, 64), ceil_div(C / 8, 32), B), block(32, 8);
-  if (dtype == DT_F32)
-    dwconv3x3_kernel<float><<<grid, block, 0, s>>>((const float*)in, (float*)out, H, W, C, stride, Ho, Wo, w, scale, bias, se_sum);
-  else
-    dwconv3x3_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)in, (bf16*)out, H, W, C, stride, Ho, Wo, w, scale, bias, se_sum);
+  const int TH = 8, TW = (Wo % 16 == 0) ? 16 : 8;
+  const int tiles_x = ceil_div(Wo, TW), tiles_y = ceil_div(Ho, TH);
+  const int IH = (TH - 1) * stride + 3, IW = (TW - 1) * stride + 3;
+  const size_t es = dtype == DT_F32 ? 4 : 2;
+  size_t smem = align_up((size_t)IH * IW * 64 * es, 16) + 32 * 64 * sizeof(float);
+  dim3 grid(tiles_x * tiles_y, ceil_div(C, 64), B);
+  static bool attr_done[2] = {false, false};
+  if (dtype == DT_F32) {
+    if (!attr_done[0]) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_done[0] = true; }
+    dwconv3x3_kernel<float><<<grid, 256, smem, s>>>((const float*)in, (float*)out, H, W, C, stride, Ho, Wo, TH, TW, tiles_x, w, scale, bias, se_sum);
+  } else {
+    if (!attr_done[1]) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_done[1] = true; }
+    dwconv3x3_kernel<bf16><<<grid, 256, smem, s>>>((const bf16*)in, (bf16*)out, H, W, C, stride, Ho, Wo, TH, TW, tiles_x, w, scale, bias, se_sum);
+  }
   FTC_POST_LAUNCH();
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// SE excitation, one block per image
-__global__ void __launch_bounds__(256) se_fc_kernel(float* __restrict__ sum, float* __restrict__ scale_out, int C, int S,
-                                                    float inv_hw, const float* __restrict__ w1,
-                                                    const float* __restrict__ b1, const float* __restrict__ w2t,
-                                                    const float* __restrict__ b2) {
-  extern __shared__ float sm[];
-  float* mean = sm;        // [C]
-  float* hid = sm + C;     // [S]
-  const int b = blockIdx.x, tid = threadIdx.x;
-  for (int c = tid; c < C; c += blockDim.x) {
-    mean[c] = sum[(int64_t)b * C + c] * inv_hw;
-    sum[(int64_t)b * C + c] = 0.f;
+// SE excitation in two small grid-filling kernels (one block per image was latency-bound: 0.22 ms per layer):
+//   fc1: one warp per (image, squeeze unit)   hid[b,s] = silu(b1[s] + w1[s,:] . mean[b,:])
+//   fc2: one thread per (image, channel)      scale[b,c] = sigmoid(b2[c] + w2t[:,c] . hid[b,:]); re-arms sum[b,c] = 0
+__global__ void __launch_bounds__(256) se_fc1_kernel(const float* __restrict__ sum, float* __restrict__ hid, int C, int S,
+                                                     float inv_hw, const float* __restrict__ w1,
+                                                     const float* __restrict__ b1) {
+  const int b = blockIdx.y;
+  const int sidx = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (sidx >= S) return;
+  const float* wr = w1 + (int64_t)sidx * C;
+  const float* sp = sum + (int64_t)b * C;
+  float t = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 w = *reinterpret_cast<const float4*>(wr + c);
+    float4 m = *reinterpret_cast<const float4*>(sp + c);
+    t = fmaf(w.x, m.x * inv_hw, t); t = fmaf(w.y, m.y * inv_hw, t);
+    t = fmaf(w.z, m.z * inv_hw, t); t = fmaf(w.w, m.w * inv_hw, t);
   }
-  __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  for (int sidx = warp; sidx < S; sidx += nw) {
-    float t = 0.f;
-    const float* wr = w1 + (int64_t)sidx * C;
-    for (int c = lane; c < C; c += 32) t = fmaf(wr[c], mean[c], t);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) hid[sidx] = silu_precise(t + b1[sidx]);
-  }
-  __syncthreads();
-  for (int c = tid; c < C; c += blockDim.x) {
-    float t = b2[c];
-    for (int k = 0; k < S; ++k) t = fmaf(w2t[(int64_t)k * C + c], hid[k], t);
-    scale_out[(int64_t)b * C + c] = sigmoid_precise(t);
-  }
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) hid[(int64_t)b * S + sidx] = silu_precise(t + b1[sidx]);
 }
 
-int se_fc(float* sum, float* scale_out, int B, int C, int S, float inv_hw, const float* w1, const float* b1,
+__global__ void __launch_bounds__(256) se_fc2_kernel(float* __restrict__ sum, const float* __restrict__ hid,
+                                                     float* __restrict__ scale_out, int C, int S,
+                                                     const float* __restrict__ w2t, const float* __restrict__ b2) {
+  __shared__ float sh[256];
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < S; k += blockDim.x) sh[k] = hid[(int64_t)b * S + k];
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = b2[c];
+  for (int k = 0; k < S; ++k) t = fmaf(w2t[(int64_t)k * C + c], sh[k], t);
+  scale_out[(int64_t)b * C + c] = sigmoid_precise(t);
+  sum[(int64_t)b * C + c] = 0.f;
+}
+
+int se_fc(float* sum, float* scale_out, float* hid, int B, int C, int S, float inv_hw, const float* w1, const float* b1,
           const float* w2t, const float* b2, cudaStream_t s) {
-  size_t smem = (size_t)(C + S) * sizeof(float);
-  FTC_REQUIRE(smem <= 48 * 1024, "SE too wide for static smem budget");
-  se_fc_kernel<<<B, 256, smem, s>>>(sum, scale_out, C, S, inv_hw, w1, b1, w2t, b2);
+  FTC_REQUIRE(S <= 256 && C % 4 == 0, "SE: squeeze <= 256 and channels % 4 == 0");
+  se_fc1_kernel<<<dim3(ceil_div(S, 8), B), 256, 0, s>>>(sum, hid, C, S, inv_hw, w1, b1);
+  FTC_POST_LAUNCH();
+  se_fc2_kernel<<<dim3(ceil_div(C, 256), B), 256, 0, s>>>(sum, hid, scale_out, C, S, w2t, b2);
   FTC_POST_LAUNCH();
   return 0;
 }

@@ -6,7 +6,8 @@ namespace ftc {
 
 // stem: NCHW fp32 image in [0,1] -> (x*2-1) -> conv3x3 s2 p1 -> BN -> SiLU -> NHWC (dtype)
 // models/detector.py:218 + torchvision efficientnet.py:271-276
-int stem_conv(const float* img, void* out, int dtype, int B, int H, int W, int Cout,
+//   nhwc255 = 1: img is the backend-ABI tile layout [B,H,W,3] fp32 in 0..255 (process_ocr_base.py:49-51)
+int stem_conv(const float* img, int nhwc255, void* out, int dtype, int B, int H, int W, int Cout,
               const float* w /*[27][Cout]*/, const float* scale, const float* bias, cudaStream_t s);
 
 // depthwise 3x3 (stride 1/2, pad 1) + BN + SiLU on NHWC, and per-(b,c) sums of the output for SE
@@ -16,8 +17,9 @@ int dwconv3x3(const void* in, void* out, int dtype, int B, int H, int W, int C, 
               cudaStream_t s);
 
 // SE excitation: scale[b,c] = sigmoid(fc2(silu(fc1(sum/HW)))) ; zeroes `sum` afterwards (ops/misc.py:251-261)
-int se_fc(float* sum, float* scale_out, int B, int C, int S, float inv_hw, const float* w1 /*[S][C]*/,
-          const float* b1, const float* w2 /*[C][S]*/, const float* b2, cudaStream_t s);
+//   hid: scratch [B, S] fp32
+int se_fc(float* sum, float* scale_out, float* hid, int B, int C, int S, float inv_hw, const float* w1 /*[S][C]*/,
+          const float* b1, const float* w2t /*[S][C]*/, const float* b2, cudaStream_t s);
 
 // bilinear x2, align_corners=True, NHWC (nn.UpsamplingBilinear2d, models/detector.py:170)
 int upsample2x(const void* in, void* out, int dtype, int B, int H, int W, int C, cudaStream_t s);

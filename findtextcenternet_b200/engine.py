@@ -83,25 +83,53 @@ class DetectorEngine:
             self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self.workspace
 
-    def forward(self, images: torch.Tensor, want_heat10: bool) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    def _check_input(self, images: torch.Tensor, nhwc255: bool):
         if self.packed is None:
             raise RuntimeError("weights not packed")
         if images.device != self.device:
             raise RuntimeError(f"input on {images.device}, engine on {self.device}")
-        if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != self.height or images.shape[3] != self.width:
-            raise ValueError(f"expected [B,3,{self.height},{self.width}], got {tuple(images.shape)}")
-        x = images.to(torch.float32).contiguous()
-        b = x.shape[0]
+        want = (self.height, self.width, 3) if nhwc255 else (3, self.height, self.width)
+        if images.dim() != 4 or tuple(images.shape[1:]) != want:
+            raise ValueError(f"expected [B,{want[0]},{want[1]},{want[2]}], got {tuple(images.shape)}")
+        fmt = _lib.INPUT_NHWC_255 if nhwc255 else _lib.INPUT_NCHW_UNIT
+        _lib.check(self.lib.ftc_detector_set_input_format(self.handle, fmt), "ftc_detector_set_input_format")
+        return images.to(torch.float32).contiguous()
+
+    def _outputs(self, b: int, want_heat10: bool):
         hq, wq = self.height // arch.SCALE, self.width // arch.SCALE
         heat9 = torch.empty(b, 9, hq, wq, dtype=torch.float32, device=self.device)
         feat = torch.empty(b, arch.FEATURE_DIM, hq, wq, dtype=torch.float32, device=self.device)
         heat10 = torch.empty(b, 10, hq, wq, dtype=torch.float32, device=self.device) if want_heat10 else None
+        return heat9, feat, heat10
+
+    def forward(self, images: torch.Tensor, want_heat10: bool, nhwc255: bool = False
+                ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+        """images: [B,3,H,W] fp32 in [0,1], or (nhwc255) the backend-ABI tile layout [B,H,W,3] fp32 in 0..255."""
+        x = self._check_input(images, nhwc255)
+        b = x.shape[0]
+        heat9, feat, heat10 = self._outputs(b, want_heat10)
         ws = self._workspace(b)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ftc_detector_forward(self.handle, x.data_ptr(), b, heat9.data_ptr(), feat.data_ptr(),
                                                      heat10.data_ptr() if want_heat10 else None, ws.data_ptr(), ws.numel(),
                                                      _stream_ptr(self.device)), "ftc_detector_forward")
         return heat9, feat, heat10
+
+    def forward_timed(self, images: torch.Tensor):
+        """One forward with CUDA events around every op: list of (kind, ms, flops).  Measurement only."""
+        x = self._check_input(images, False)
+        b = x.shape[0]
+        heat9, feat, _ = self._outputs(b, False)
+        ws = self._workspace(b)
+        n = int(self.lib.ftc_detector_num_ops(self.handle))
+        ms = (C.c_float * n)()
+        fl = (C.c_double * n)()
+        kind = (C.c_int * n)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ftc_detector_forward_timed(self.handle, x.data_ptr(), b, heat9.data_ptr(), feat.data_ptr(),
+                                                           ws.data_ptr(), ws.numel(), _stream_ptr(self.device), n, ms, fl,
+                                                           kind), "ftc_detector_forward_timed")
+        return [(int(kind[i]), float(ms[i]), float(fl[i])) for i in range(n)]
 
 
 def read_tap(eng: DetectorEngine, tap: int, batch: int) -> torch.Tensor:
@@ -142,3 +170,95 @@ def peak_decode(heat9: torch.Tensor, feat: torch.Tensor, tile_meta: torch.Tensor
                                        float(page_w), float(page_h), max_peaks, count.data_ptr(), loc.data_ptr(),
                                        gfeat.data_ptr(), scratch.data_ptr(), _stream_ptr(dev)), "ftc_peak_decode")
     return count, loc, gfeat
+
+
+class TransformerEngine:
+    """One ``ftc_transformer`` plan + packed weights (models/transformer.py Encoder + Decoder)."""
+
+    def __init__(self, dims: dict, precision: str, device: torch.device):
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        if device.type != "cuda":
+            raise RuntimeError("findtextcenternet_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.dims, self.precision, self.device = dict(dims), precision, device
+        prec, backend = _PRECISIONS[precision]
+        self.cfg = _lib.TransformerConfig(dims["enc_input_dim"], dims["embed_dim"], dims["head_num"], dims["enc_block_num"],
+                                          dims["dec_block_num"], dims["max_enc_seq_len"], dims["max_dec_seq_len"], prec, backend)
+        handle = C.c_void_p()
+        _lib.check(self.lib.ftc_transformer_create(C.byref(self.cfg), C.byref(handle)), "ftc_transformer_create")
+        self.handle = handle
+        self.packed: Optional[torch.Tensor] = None
+        self.workspace: Optional[torch.Tensor] = None
+        self.logit_stride = int(self.lib.ftc_transformer_logit_stride())
+        self.head_stride = int(self.lib.ftc_transformer_head_stride())
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.ftc_transformer_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def pack(self, tensors: Dict[str, torch.Tensor]) -> None:
+        names, ptrs, numels, keep = [], [], [], []
+        for k, v in tensors.items():
+            t = v.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            names.append(k.encode())
+            ptrs.append(t.data_ptr())
+            numels.append(t.numel())
+        n = len(names)
+        nbytes = int(self.lib.ftc_transformer_weight_bytes(self.handle))
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ftc_transformer_pack_weights(self.handle, n, (C.c_char_p * n)(*names), (C.c_void_p * n)(*ptrs),
+                                                             (C.c_int64 * n)(*numels), packed.data_ptr(), nbytes,
+                                                             _stream_ptr(self.device)), "ftc_transformer_pack_weights")
+        self.packed = packed
+        del keep
+
+    def _workspace(self, b: int, le: int, ld: int) -> torch.Tensor:
+        need = int(self.lib.ftc_transformer_workspace_bytes(self.handle, b, le, ld))
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = None
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self.workspace
+
+    def _check(self, enc_input: torch.Tensor):
+        if self.packed is None:
+            raise RuntimeError("weights not packed")
+        if enc_input.device != self.device:
+            raise RuntimeError(f"input on {enc_input.device}, engine on {self.device}")
+        if enc_input.dim() != 3 or enc_input.shape[2] != self.dims["enc_input_dim"]:
+            raise ValueError(f"expected [B,L,{self.dims['enc_input_dim']}], got {tuple(enc_input.shape)}")
+        return enc_input.to(torch.float32).contiguous()
+
+    def forward(self, enc_input: torch.Tensor, dec_input: torch.Tensor):
+        """-> list of 3 fp32 logits views [B, Ld, m_i] into one [B*Ld, 3*head_stride] buffer."""
+        x = self._check(enc_input)
+        tok = dec_input.to(device=self.device, dtype=torch.int64).contiguous()
+        b, le, _ = x.shape
+        ld = tok.shape[1]
+        logits = torch.empty(b * ld, self.logit_stride, dtype=torch.float32, device=self.device)
+        ws = self._workspace(b, le, ld)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ftc_transformer_forward(self.handle, x.data_ptr(), tok.data_ptr(), b, le, ld, logits.data_ptr(),
+                                                        ws.data_ptr(), ws.numel(), _stream_ptr(self.device)),
+                       "ftc_transformer_forward")
+        lg = logits.view(b, ld, self.logit_stride)
+        return [lg[:, :, g * self.head_stride: g * self.head_stride + m] for g, m in enumerate(arch.MODULO_LIST)]
+
+    def predict(self, enc_input: torch.Tensor, dec_len: int, max_passes: int = 8):
+        """-> (ids int64 [B, dec_len], passes_run, stop_reason)"""
+        x = self._check(enc_input)
+        b, le, _ = x.shape
+        ids = torch.empty(b, dec_len, dtype=torch.int64, device=self.device)
+        ws = self._workspace(b, le, dec_len)
+        passes, reason = C.c_int(0), C.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ftc_transformer_predict(self.handle, x.data_ptr(), b, le, dec_len, ids.data_ptr(), max_passes,
+                                                        C.byref(passes), C.byref(reason), ws.data_ptr(), ws.numel(),
+                                                        _stream_ptr(self.device)), "ftc_transformer_predict")
+        return ids, passes.value, reason.value

@@ -58,6 +58,7 @@ class CenterNetDetection(nn.Module):
         for name, od in arch.HEADS:
             setattr(self, name, Leafmap(out_dim=od, model_size=model_size))
         self.precision = default_precision()
+        self.weights_frozen = False      # True: skip the per-call "did a parameter change?" scan (serving loops)
         self._engine: Optional[DetectorEngine] = None
         self._engine_key = None
 
@@ -73,6 +74,9 @@ class CenterNetDetection(nn.Module):
         return (str(device), self.precision, ptr, hash(vers))
 
     def engine(self, device: torch.device) -> DetectorEngine:
+        if (self.weights_frozen and self._engine is not None and self._engine_key is not None
+                and self._engine.precision == self.precision and self._engine.device == device):
+            return self._engine
         key = self._weights_key(device)
         if self._engine is None or self._engine.precision != self.precision or self._engine.device != device:
             self._engine = DetectorEngine(self.model_size, self.precision, device)

@@ -1,0 +1,111 @@
+"""``OCR_b200_Processer``: the B200 backend for the reference's OCR pipeline.
+
+Mirrors /root/reference/process_ocr_torch.py:6-54 (``OCR_torch_Processer``) behind the backend ABI of
+process_ocr_base.py:39-55: ``call_detector(np.float32[1,768,768,3] 0..255) -> (heatmap[1,10,192,192],
+features[1,100,192,192])`` and ``call_transformer(np.float32[1,max_encoderlen,106]) -> np.int64[max_decoderlen]``.
+When ``process_ocr_base`` is importable (running from a reference checkout) this class derives from its
+``OCR_Processer`` so ``call_OCR`` / ``run_detector`` are inherited unchanged; otherwise a minimal stand-in base with
+the same constructor is used.
+
+Beyond the reference ABI it adds the batched entry point the hardware wants: ``detect_tiles`` runs all tiles of a
+page (or many pages) in one launch sequence and returns only the decoded peaks (KBs) instead of 16 MB of maps/tile.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import arch
+from .engine import peak_decode
+
+try:  # running inside a reference checkout
+    from process_ocr_base import OCR_Processer as _Base  # type: ignore
+except Exception:  # pragma: no cover - exercised on the GPU box
+    class _Base:  # process_ocr_base.py:39-47
+        def __init__(self, step_ratio=0.6, cut_off=0.4):
+            self.step_ratio = step_ratio
+            self.stepx = int(arch.WIDTH * self.step_ratio)
+            self.stepy = int(arch.HEIGHT * self.step_ratio)
+            self.cut_off = cut_off
+
+
+def tile_meta(x_i: int, y_i: int, img_w: int, img_h: int, step_ratio: float = 0.6) -> List[int]:
+    """(offset_x, offset_y, mask x_min, x_max, y_min, y_max) of one tile: the centre-crop validity window of
+    process_ocr_base.py:498-503 as half-open bounds in 192x192 map coordinates."""
+    x_s, y_s = arch.WIDTH // arch.SCALE, arch.HEIGHT // arch.SCALE
+    x_min = int(x_s * (1 - step_ratio) / 2) if x_i > 0 else 0
+    x_max = int(x_s * (1 - (1 - step_ratio) / 2)) + 1 if x_i + arch.WIDTH < img_w else x_s
+    y_min = int(y_s * (1 - step_ratio) / 2) if y_i > 0 else 0
+    y_max = int(y_s * (1 - (1 - step_ratio) / 2)) + 1 if y_i + arch.HEIGHT < img_h else y_s
+    return [x_i, y_i, x_min, x_max, y_min, y_max]
+
+
+class OCR_b200_Processer(_Base):
+    def __init__(self, model_size="xl", precision: Optional[str] = None, device: Optional[torch.device] = None,
+                 detector_state_dict=None, transformer_state_dict=None, transformer_config=None):
+        super().__init__()
+        from .models.detector import TextDetectorModel, CenterNetDetector
+        if not torch.cuda.is_available():
+            raise RuntimeError("OCR_b200_Processer needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        model = TextDetectorModel(model_size=model_size)
+        if detector_state_dict is not None:
+            model.load_state_dict(detector_state_dict)
+        elif os.path.exists("model.pt"):   # process_ocr_torch.py:13-15
+            data = torch.load("model.pt", map_location="cpu", weights_only=True)
+            model.load_state_dict(data["model_state_dict"])
+        if precision is not None:
+            model.detector.set_precision(precision)
+        detector = CenterNetDetector(model.detector)
+        detector.to(device=self.device)
+        detector.eval()
+        self.detector = detector
+        self.transformer = None
+        self._transformer_args = (transformer_state_dict, transformer_config)
+
+    # ---- reference backend ABI ---------------------------------------------------------------------
+    def call_detector(self, image_input):
+        x = torch.from_numpy(np.ascontiguousarray(image_input, dtype=np.float32)).to(self.device, non_blocking=True)
+        eng = self.detector.detector.engine(self.device)
+        with torch.no_grad():
+            _, feat, heat10 = eng.forward(x, True, nhwc255=True)
+        return heat10.cpu().numpy(), feat.cpu().numpy()
+
+    def _load_transformer(self):
+        from .models.transformer import ModelDimensions, Transformer, TransformerPredictor
+        sd, cfg = self._transformer_args
+        if sd is None and os.path.exists("model3.pt"):   # process_ocr_torch.py:30-34
+            data = torch.load("model3.pt", map_location="cpu", weights_only=True)
+            cfg, sd = data["config"], data["model_state_dict"]
+        config = ModelDimensions(**(cfg or {}))
+        model = Transformer(**config.__dict__)
+        if sd is not None:
+            model.load_state_dict(sd)
+        pred = TransformerPredictor(model.encoder, model.decoder)
+        pred.to(self.device)
+        pred.eval()
+        self.transformer = pred
+
+    def call_transformer(self, encoder_input):
+        if self.transformer is None:
+            self._load_transformer()
+        x = torch.from_numpy(np.ascontiguousarray(encoder_input, dtype=np.float32)).to(self.device)
+        return self.transformer(x).squeeze(0).cpu().numpy()
+
+    # ---- batched device-side path --------------------------------------------------------------------
+    def detect_tiles(self, tiles: torch.Tensor, offsets: Sequence[Tuple[int, int]], page_w: int, page_h: int,
+                     max_peaks: int = 1024):
+        """tiles: float32 [B,768,768,3] in 0..255 (host, ideally pinned, or device).  Runs detector + per-tile peak
+        compaction/box decode (process_ocr_base.py:487-538) on the device and returns host arrays
+        (count int32 [B], locations float32 [B,max_peaks,9], glyphfeatures float32 [B,max_peaks,100])."""
+        x = tiles.to(self.device, non_blocking=True)
+        eng = self.detector.detector.engine(self.device)
+        meta = torch.tensor([tile_meta(ox, oy, page_w, page_h, self.step_ratio) for ox, oy in offsets], dtype=torch.int32)
+        meta = meta.to(self.device, non_blocking=True)
+        with torch.no_grad():
+            heat9, feat, _ = eng.forward(x, False, nhwc255=True)
+            count, loc, gfeat = peak_decode(heat9, feat, meta, page_w, page_h, self.cut_off, max_peaks)
+        return count.cpu(), loc.cpu(), gfeat.cpu()

@@ -22,6 +22,10 @@ extern "C" {
 
 enum { FTC_PREC_F32 = 0, FTC_PREC_BF16 = 1 };
 enum { FTC_GEMM_SIMT = 0, FTC_GEMM_TCGEN05 = 1 };
+/* layout/range of the `images` argument of ftc_detector_forward:
+ *   NCHW_UNIT: [B,3,H,W] fp32 in [0,1]   (models/detector.py:217 CenterNetDetection.forward input)
+ *   NHWC_255 : [B,H,W,3] fp32 in 0..255  (process_ocr_base.py:49-51 call_detector input; /255 as process_ocr_torch.py:44) */
+enum { FTC_INPUT_NCHW_UNIT = 0, FTC_INPUT_NHWC_255 = 1 };
 
 typedef struct ftc_stage_cfg {
   int fused;   /* 1 = FusedMBConv, 0 = MBConv (torchvision efficientnet.py:105-231) */
@@ -63,6 +67,13 @@ int ftc_detector_pack_weights(ftc_detector* d, int n, const char* const* names, 
 int ftc_detector_forward(ftc_detector* d, const float* images, int batch, float* heat9, float* feat, float* heat10,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+int ftc_detector_set_input_format(ftc_detector* d, int fmt);
+/* measurement: same forward with a CUDA-event pair around every op of the plan (synchronises the stream).
+ * op_ms / op_flop (2*MAC for `batch` images) / op_kind (0 stem, 1 dense 3x3, 2 1x1, 3 depthwise, 4 SE, 5 upsample) */
+int ftc_detector_num_ops(const ftc_detector* d);
+int ftc_detector_forward_timed(ftc_detector* d, const float* images, int batch, float* heat9, float* feat, void* workspace,
+                               size_t workspace_bytes, void* stream, int max_ops, float* op_ms, double* op_flop,
+                               int* op_kind);
 /* introspection (tests): device pointer of backbone tap `tap` (0..3 = x1..x4, NHWC, engine dtype) inside `workspace`
  * after a forward of `batch` images; *channels / *hw receive its shape. */
 int ftc_detector_tap(const ftc_detector* d, int tap, int batch, void* workspace, void** ptr, int* channels, int* h, int* w);
@@ -75,6 +86,41 @@ int ftc_peak_decode(const float* heat9, const float* feat, int batch, int h, int
                     void* scratch, void* stream);
 int ftc_peak_pick(const float* heat9, float* heat10, int batch, int h, int w, void* stream);
 
+/* ---- Transformer: Encoder / Decoder / TransformerPredictor (models/transformer.py) ---- */
+/* replaces: models/transformer.py:255-264 ModelDimensions */
+typedef struct ftc_transformer_config {
+  int enc_input_dim;   /* 106 */
+  int embed_dim, head_num, enc_blocks, dec_blocks, max_enc_len, max_dec_len;
+  int precision;       /* FTC_PREC_* */
+  int gemm_backend;    /* FTC_GEMM_* */
+} ftc_transformer_config;
+typedef struct ftc_transformer ftc_transformer;
+
+int ftc_transformer_create(const ftc_transformer_config* cfg, ftc_transformer** out);
+void ftc_transformer_destroy(ftc_transformer* t);
+size_t ftc_transformer_weight_bytes(const ftc_transformer* t);
+size_t ftc_transformer_workspace_bytes(const ftc_transformer* t, int batch, int enc_len, int dec_len);
+/* names = reference Transformer.state_dict() keys ("encoder.blocks.0.mha.q_proj.weight", ...), fp32 device tensors */
+int ftc_transformer_pack_weights(ftc_transformer* t, int n, const char* const* names, const void* const* ptrs,
+                                 const int64_t* numels, void* packed, size_t packed_bytes, void* stream);
+/* logits rows are [3 * head_stride] fp32: head g (modulus 1091/1093/1097) at columns [g*head_stride, g*head_stride+m_g) */
+int ftc_transformer_logit_stride(void);
+int ftc_transformer_head_stride(void);
+/* Transformer.forward (models/transformer.py:248-253): enc_input fp32 [B,Le,enc_input_dim], dec_input int64 [B,Ld]
+ * -> logits fp32 [B*Ld, logit_stride].  Rows of enc_input that are all zero are masked keys. */
+int ftc_transformer_forward(ftc_transformer* t, const float* enc_input, const int64_t* dec_input, int batch, int enc_len,
+                            int dec_len, float* logits, void* workspace, size_t workspace_bytes, void* stream);
+/* TransformerPredictor.forward (models/transformer.py:274-360): encoder once, then <= max_passes (reference: 8)
+ * mask-predict decoder passes with the reference's two data-dependent exits.  out_ids int64 [B,Ld] (device).
+ * This call synchronises the stream once per pass (the reference does it twice per pass).
+ * stop_reason: 0 = ran all passes, 1 = "early stop" (:326), 2 = "no remask stop" (:356). */
+int ftc_transformer_predict(ftc_transformer* t, const float* enc_input, int batch, int enc_len, int dec_len, int64_t* out_ids,
+                            int max_passes, int* passes_run, int* stop_reason, void* workspace, size_t workspace_bytes,
+                            void* stream);
+/* one mask-predict decision per position on fp32 logits (models/transformer.py:311-324 + util_func.py:92-126) */
+int ftc_mask_predict_step(const float* logits, int ld, int head_ld, const int64_t* dec_in, int64_t* ids, float* prob,
+                          int64_t* next_in, int* flags, int rows, void* stream);
+
 /* ---- single ops (unit-test / building-block entry points) ---- */
 /* dense conv (k in {1,3}) or linear as implicit GEMM on NHWC activations.
  * x: [B,H,W,Cin] (dtype), w_oihw: fp32 [Cout,Cin,k,k] (packed on the fly into `wpack`),
@@ -85,8 +131,9 @@ int ftc_op_conv2d(const void* x, int dtype, int batch, int h, int w, int cin, co
 size_t ftc_op_conv2d_wpack_bytes(int cin, int cout, int ksize);
 int ftc_op_dwconv3x3(const void* x, void* out, int dtype, int batch, int h, int w, int c, int stride,
                      const float* w9c, const float* scale, const float* bias, float* se_sum, void* stream);
-int ftc_op_se_fc(float* sum, float* scale_out, int batch, int c, int s, float inv_hw, const float* w1, const float* b1,
-                 const float* w2t, const float* b2, void* stream);
+/* hid: fp32 scratch [batch, s]; `sum` is zeroed (re-armed) on return */
+int ftc_op_se_fc(float* sum, float* scale_out, float* hid, int batch, int c, int s, float inv_hw, const float* w1,
+                 const float* b1, const float* w2t, const float* b2, void* stream);
 int ftc_op_upsample2x(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream);
 
 #ifdef __cplusplus

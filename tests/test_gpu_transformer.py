@@ -1,0 +1,168 @@
+"""GPU parity of the Transformer engine (nn.Module mirror -> C-ABI) against golden vectors produced by the unmodified
+reference on CPU fp32 (tests/golden/transformer_seed0.npz) and against the oracle on fresh seeded inputs.
+
+fp32 path: logits within 1e-3 relative, argmax and predicted code points equal.  bf16 tcgen05 path: logits within 5e-2
+relative (bf16 storage between 32-48 GEMM/LN stages), argmax agreement >= 97 %."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+FULL = dict(enc_input_dim=106, embed_dim=768, head_num=12, enc_block_num=10, dec_block_num=10, max_enc_seq_len=400,
+            max_dec_seq_len=400)
+
+
+def _cfg(name):
+    from oracle.make_golden import TRANSFORMER_CFGS
+    dims, batch = TRANSFORMER_CFGS[name]
+    full = dict(FULL)
+    full.update(dims)
+    return dims, full, batch
+
+
+def _model(name, precision):
+    from findtextcenternet_b200 import synthetic
+    from findtextcenternet_b200.models.transformer import ModelDimensions, Transformer
+    dims, full, batch = _cfg(name)
+    m = Transformer(**ModelDimensions(**dims).__dict__)
+    m.load_state_dict(synthetic.transformer_state_dict(0, **dims), strict=True)
+    m = m.cuda().eval()
+    m.set_precision(precision)
+    enc, dec, _ = synthetic.transformer_inputs(batch, full["max_enc_seq_len"], full["max_dec_seq_len"], 0)
+    return m, full, enc, dec
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg4", "default"])
+def test_transformer_fp32_logits_match_reference(name, golden_transformer):
+    g = golden_transformer
+    m, full, enc, dec = _model(name, "fp32")
+    with torch.no_grad():
+        logits = m(enc.cuda(), dec.cuda())
+    ld = full["max_dec_seq_len"]
+    for i, lg in enumerate(logits):
+        assert lg.shape[-1] == (1091, 1093, 1097)[i]
+        lg = lg.cpu().numpy()
+        assert rel_l2(lg[:, ::max(1, ld // 8)], g[f"{name}_logits{i}_s"]) < 1e-3
+        assert rel_l2(torch.logsumexp(torch.from_numpy(lg), -1).numpy(), g[f"{name}_lse{i}"]) < 1e-3
+        assert (lg.argmax(-1) == g[f"{name}_argmax{i}"]).mean() > 0.999
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg4"])
+def test_predictor_fp32_codepoints_match_reference(name, golden_transformer):
+    import findtextcenternet_b200.models.transformer as T
+    m, full, enc, dec = _model(name, "fp32")
+    old = T.max_decoderlen
+    T.max_decoderlen = full["max_dec_seq_len"]
+    try:
+        pred = T.TransformerPredictor(m.encoder, m.decoder).cuda().eval().set_precision("fp32")
+        buf = io.StringIO()
+        with torch.no_grad(), contextlib.redirect_stdout(buf):
+            ids = pred(enc.cuda())
+    finally:
+        T.max_decoderlen = old
+    assert ids.dtype == torch.int64
+    assert np.array_equal(ids.cpu().numpy(), golden_transformer[f"{name}_pred_ids"])
+    assert buf.getvalue() == str(golden_transformer[f"{name}_pred_log"])
+
+
+@pytest.mark.parametrize("variant,boost", [("peaked", 20.0), ("medium", 10.5)])
+def test_predictor_early_exits(variant, boost, golden_transformer):
+    """models/transformer.py:326 ("early stop") and :356 ("no remask stop")."""
+    import findtextcenternet_b200.models.transformer as T
+    from findtextcenternet_b200 import arch, synthetic
+    dims, full, batch = _cfg("tiny")
+    sd = synthetic.transformer_state_dict(0, **dims)
+    for i, mod in enumerate(arch.MODULO_LIST):
+        b = sd[f"decoder.out_layers.{i}.bias"].clone()
+        b[0x3042 % mod] += boost
+        sd[f"decoder.out_layers.{i}.bias"] = b
+    m = T.Transformer(**T.ModelDimensions(**dims).__dict__)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    enc, _, _ = synthetic.transformer_inputs(batch, 24, 24, 0)
+    old = T.max_decoderlen
+    T.max_decoderlen = 24
+    try:
+        pred = T.TransformerPredictor(m.encoder, m.decoder).cuda().eval().set_precision("fp32")
+        buf = io.StringIO()
+        with torch.no_grad(), contextlib.redirect_stdout(buf):
+            ids = pred(enc.cuda())
+    finally:
+        T.max_decoderlen = old
+    assert np.array_equal(ids.cpu().numpy(), golden_transformer[f"tiny_{variant}_pred_ids"])
+    assert buf.getvalue() == str(golden_transformer[f"tiny_{variant}_pred_log"])
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg4"])
+@pytest.mark.parametrize("precision", ["bf16_simt", "bf16"])
+def test_transformer_bf16_close(name, precision, golden_transformer):
+    g = golden_transformer
+    m, full, enc, dec = _model(name, precision)
+    with torch.no_grad():
+        logits = m(enc.cuda(), dec.cuda())
+    ld = full["max_dec_seq_len"]
+    for i, lg in enumerate(logits):
+        lg = lg.cpu().numpy()
+        assert rel_l2(lg[:, ::max(1, ld // 8)], g[f"{name}_logits{i}_s"]) < 5e-2
+        assert (lg.argmax(-1) == g[f"{name}_argmax{i}"]).mean() > 0.97
+
+
+def test_transformer_ragged_batch_matches_oracle():
+    """Fresh seed, odd batch, enc/dec lengths below the table size, fully padded tail rows (key mask)."""
+    from findtextcenternet_b200 import synthetic
+    from findtextcenternet_b200.models.transformer import ModelDimensions, Transformer
+    from oracle import transformer_oracle as TO
+    dims = dict(embed_dim=128, head_num=4, enc_block_num=2, dec_block_num=3, max_enc_seq_len=40, max_dec_seq_len=48)
+    sd = synthetic.transformer_state_dict(5, **dims)
+    m = Transformer(**ModelDimensions(**dims).__dict__)
+    m.load_state_dict(sd)
+    m = m.cuda().eval().set_precision("fp32")
+    enc, dec, _ = synthetic.transformer_inputs(5, 33, 37, seed=11)
+    ref = TO.transformer_forward(sd, 4, enc, dec)
+    with torch.no_grad():
+        got = m(enc.cuda(), dec.cuda())
+    for r, o in zip(ref, got):
+        assert rel_l2(o.cpu().numpy(), r.numpy()) < 1e-3
+
+
+def test_mask_predict_step_matches_oracle():
+    """Bit-exact code points (CRT over 1091/1093/1097 in int64) and flags on random logits with forced edge cases."""
+    import ctypes as C
+    from findtextcenternet_b200 import _lib
+    from oracle import transformer_oracle as TO
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    B, L = 6, 50
+    hs = int(lib.ftc_transformer_head_stride())
+    outs = [4.0 * torch.randn(B, L, m, generator=g) for m in (1091, 1093, 1097)]
+    for b in range(3):   # confident positions: residues of a valid code point
+        for l in range(0, L, 3):
+            cp = 0x3042 + 7 * l + b
+            for o, m in zip(outs, (1091, 1093, 1097)):
+                o[b, l, cp % m] += 25.0
+    ref_ids, ref_p = TO.mask_predict_step(outs)
+    dec_in = torch.full((B, L), 3, dtype=torch.int64)
+    dec_in[:, ::5] = 0x3042
+    logits = torch.zeros(B * L, 3 * hs)
+    for i, o in enumerate(outs):
+        logits[:, i * hs:i * hs + o.shape[-1]] = o.reshape(B * L, -1)
+    logits = logits.cuda()
+    ids = torch.empty(B * L, dtype=torch.int64, device="cuda")
+    prob = torch.empty(B * L, dtype=torch.float32, device="cuda")
+    nxt = torch.empty(B * L, dtype=torch.int64, device="cuda")
+    flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+    _lib.check(lib.ftc_mask_predict_step(logits.data_ptr(), 3 * hs, hs, dec_in.cuda().data_ptr(), ids.data_ptr(), prob.data_ptr(),
+                                         nxt.data_ptr(), flags.data_ptr(), B * L, torch.cuda.current_stream().cuda_stream))
+    ids, prob, nxt = ids.cpu().view(B, L), prob.cpu().view(B, L), nxt.cpu().view(B, L)
+    assert torch.equal(ids, ref_ids)
+    np.testing.assert_allclose(prob.numpy(), ref_p.numpy(), rtol=1e-4, atol=1e-7)
+    remask = (ref_p < 0.9) | (ref_ids > 0x3FFFF)
+    assert torch.equal(nxt, torch.where(remask, torch.tensor(3), ref_ids))
+    notconf = bool(((dec_in == 3) & (ref_ids > 0) & ~(ref_p > 0.99)).any())
+    assert flags.cpu().tolist() == [int(notconf), int(bool(remask.any()))]
