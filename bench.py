@@ -226,7 +226,7 @@ def run_ours(args):
             for k, m, f in ops:
                 d = by_kind.setdefault(k, [0.0, 0.0, 0])
                 d[0] += m; d[1] += f; d[2] += 1
-            names = {0: "stem", 1: "conv3x3_tc", 2: "conv1x1_tc", 3: "depthwise_se", 4: "se_fc", 5: "upsample"}
+            names = {0: "stem", 1: "conv3x3_tc", 2: "conv1x1_tc", 3: "depthwise_se", 4: "se_fc", 5: "upsample", 6: "head_top_small"}
             roofline = {
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "traffic": None,

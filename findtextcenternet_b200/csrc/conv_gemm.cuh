@@ -36,6 +36,8 @@ struct ConvTcPlan {
   int NT;       // N tiles per group; packed weight rows per group = NT*BN
   int NKB;      // K / KBLOCK
   int stages;   // smem pipeline depth
+  int flags;    // experiment bits (env FTC_TC_FLAGS; results are garbage when >= 4): 1 try_wait suspend hint, 2 epilogue
+                // poll backoff, 4 skip B copies, 8 skip A gathers, 16 skip MMAs, 32 skip epilogue math/stores
 };
 
 struct ConvGemmParams {

@@ -48,13 +48,14 @@ struct GemmOp {
   bool has_scale = true;
   size_t w_off = 0, scale_off = 0, bias_off = 0, ktab_off = 0;
   std::vector<uint32_t> ktab;
-  ConvTcPlan tc{0, 0, 0, 0};
+  ConvTcPlan tc{0, 0, 0, 0, 0};
 };
 
 struct Op {
-  enum Type { STEM, GEMM, DW, SE, UP } type;
+  enum Type { STEM, GEMM, DW, SE, UP, TOPS } type;
   GemmOp g;                          // GEMM
-  // STEM / DW / SE / UP
+  // STEM / DW / SE / UP / TOPS
+  int n_heads = 0, head0 = 0, od[8] = {0}, pix_stride = 0, out_ch = 0;
   int bufIn = BUF_NONE, bufOut = BUF_NONE, C = 0, H = 0, W = 0, stride = 1, S = 0;
   size_t w_off = 0, scale_off = 0, bias_off = 0, w2_off = 0, b1_off = 0, b2_off = 0;
 };
@@ -349,8 +350,32 @@ int ftc_detector::build() {
     ops.push_back(std::move(op));
   };
   int heat_ch = 0;
-  for (int h = 0; h < NH - 1; ++h) { heat_ch += c.head_out[h]; FTC_REQUIRE(c.head_out[h] <= 16, "small head out_dim <= 16"); }
-  add_top(0, NH - 1, 16, BUF_EXT_HEAT9, heat_ch);
+  for (int h = 0; h < NH - 1; ++h) { heat_ch += c.head_out[h]; FTC_REQUIRE(c.head_out[h] <= 2, "small head out_dim <= 2"); }
+  {
+    // the eight small heads: dedicated bandwidth kernel (head_top_conv), fp32 tap-major weights
+    Op op; op.type = Op::TOPS; op.bufIn = ybuf; op.H = Hq; op.W = Wq; op.n_heads = NH - 1; op.head0 = 0; op.pix_stride = NT;
+    op.out_ch = heat_ch;
+    for (int h = 0; h < NH - 1; ++h) op.od[h] = c.head_out[h];
+    op.w_off = walloc((size_t)heat_ch * 9 * CD * 4);
+    op.bias_off = walloc((size_t)heat_ch * 4);
+    const Op oc = op;
+    int row = 0;
+    for (int h = 0; h < NH - 1; ++h) {
+      const std::string hp = std::string(c.head_names[h]);
+      const int od = c.head_out[h], r0 = row;
+      pack_tasks.push_back([=](const Lookup& L, char* base, cudaStream_t s) -> int {
+        const float* w = L.get(hp + ".top_conv.0.weight", (int64_t)od * CD * 9);
+        const float* b = L.get(hp + ".top_conv.0.bias", od);
+        if (!w || !b) return -1;
+        int rc = pack_conv_weight(base + oc.w_off, DT_F32, w, od, CD, 3, 3, 0, CD, 0, 9 * CD, r0, nullptr, s);
+        if (rc) return rc;
+        FTC_CHECK_CUDA(cudaMemcpyAsync((float*)(base + oc.bias_off) + r0, b, od * 4, cudaMemcpyDeviceToDevice, s));
+        return 0;
+      });
+      row += od;
+    }
+    ops.push_back(op);
+  }
   int fpad = (c.head_out[NH - 1] + 15) / 16 * 16;
   add_top(NH - 1, 1, fpad, BUF_EXT_FEAT, c.head_out[NH - 1]);
   return 0;
@@ -364,6 +389,7 @@ static double op_flops(const Op& op, int B) {
     case Op::DW: { int Ho = (op.H - 1) / op.stride + 1, Wo = (op.W - 1) / op.stride + 1; return 2.0 * B * Ho * Wo * 9.0 * op.C; }
     case Op::SE: return 4.0 * B * (double)op.C * op.S;
     case Op::UP: return 0.0;
+    case Op::TOPS: return 2.0 * B * op.H * op.W * 9.0 * 192.0 * op.out_ch;
     case Op::GEMM: {
       const GemmOp& g = op.g;
       double kreal = (double)g.ksize * g.ksize * (g.CA + g.CB);
@@ -411,6 +437,10 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
       case Op::SE:
         rc = se_fc(se_sum, se_scale, se_hid, B, op.C, op.S, 1.0f / (float)(op.H * op.W), (const float*)(P + op.w_off),
                    (const float*)(P + op.b1_off), (const float*)(P + op.w2_off), (const float*)(P + op.b2_off), s);
+        break;
+      case Op::TOPS:
+        rc = head_top_conv(bp(op.bufIn), d->dtype, op.pix_stride, op.head0, op.n_heads, op.od, (const float*)(P + op.w_off),
+                           (const float*)(P + op.bias_off), heat9, op.out_ch, B, op.H, op.W, s);
         break;
       case Op::UP:
         rc = upsample2x(bp(op.bufIn), bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, s);
@@ -497,7 +527,7 @@ int ftc_detector_forward_timed(ftc_detector* d, const float* images, int batch, 
       const Op& op = d->ops[i];
       // kind: 0 stem, 1 dense 3x3 conv, 2 1x1 conv, 3 depthwise, 4 SE, 5 upsample
       op_kind[i] = op.type == Op::STEM ? 0 : op.type == Op::GEMM ? (op.g.ksize == 3 ? 1 : 2) : op.type == Op::DW ? 3
-                   : op.type == Op::SE ? 4 : 5;
+                   : op.type == Op::SE ? 4 : op.type == Op::UP ? 5 : 6;
     }
   }
   for (auto& e : ev) cudaEventDestroy(e);

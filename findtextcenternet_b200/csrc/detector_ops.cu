@@ -76,90 +76,132 @@ int stem_conv(const float* img, int nhwc255, void* out, int dtype, int B, int H,
 
 // ------------------------------------------------------------------------------------------------
 // depthwise 3x3 + BN + SiLU + SE partial sums.
-// One CTA = a TH x TW output tile x 64 channels.  The (TH-1)*s+3 x (TW-1)*s+3 input halo tile is staged ONCE in shared
-// memory with full-line (128 B per pixel) coalesced loads, so HBM/L2 sees each input ~1.4x instead of 9x; the 9 taps
-// are 16-byte shared-memory reads.  tid = pixel_lane * 8 + chunk (8 channels per thread).
-template <typename T>
+// One CTA = a TH x TW output tile x 64 channels.  The halo tile is staged ONCE in shared memory with full-line
+// (128 B per pixel) cp.async loads, so HBM/L2 sees each input ~1.2x instead of 9x.  Each thread owns one output column
+// and 4 channels and walks down the tile with a 3-row register window: per output element 9 FMA + 3 conversions +
+// 0.75 shared loads (the first version spent ~65 instructions per element, this one ~20: the op is instruction-bound
+// on the CUDA cores, not HBM-bound, until that count is small).
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float silu_tanh_f(float x) {   // 1 SFU op: x*sigmoid(x) = h + h*tanh(h), h = x/2
+  float h = 0.5f * x, t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+template <typename T, int STRIDE>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W,
-                                                        int C, int stride, int Ho, int Wo, int TH, int TW, int tiles_x,
+                                                        int C, int Ho, int Wo, int TH, int TW, int tiles_x,
                                                         const float* __restrict__ w, const float* __restrict__ scale,
                                                         const float* __restrict__ bias, float* __restrict__ se_sum) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
   T* tile = reinterpret_cast<T*>(dw_smem);                       // [IH][IW][64]
-  const int IH = (TH - 1) * stride + 3, IW = (TW - 1) * stride + 3;
-  float* red = reinterpret_cast<float*>(dw_smem + (((size_t)IH * IW * 64 * sizeof(T)) + 15) / 16 * 16);   // [32][64]
-  const int tid = threadIdx.x, chunk = tid & 7, plane = tid >> 3;
+  const int IH = (TH - 1) * STRIDE + 3, IW = (TW - 1) * STRIDE + 3;
+  float* red = reinterpret_cast<float*>(dw_smem + (((size_t)IH * IW * 64 * sizeof(T)) + 15) / 16 * 16);   // [TW][64]
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int b = blockIdx.z;
-  const int c0 = blockIdx.y * 64 + chunk * 8;
-  const bool cvalid = c0 < C;
+  const int cb = blockIdx.y * 64;
   const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
   const int oy0 = ty * TH, ox0 = tx * TW;
-  const int iy0 = oy0 * stride - 1, ix0 = ox0 * stride - 1;
-  // ---- stage the halo tile (zeros outside the image) ----
-  for (int p = plane; p < IH * IW; p += 32) {
-    int py = p / IW, px = p - py * IW;
-    int iy = iy0 + py, ix = ix0 + px;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    float4 f0 = make_float4(0, 0, 0, 0), f1 = f0;
-    const bool ok = cvalid && iy >= 0 && iy < H && ix >= 0 && ix < W;
-    if (sizeof(T) == 2) {
-      if (ok) v = *reinterpret_cast<const uint4*>(in + (((int64_t)b * H + iy) * W + ix) * C + c0);
-      *reinterpret_cast<uint4*>(tile + (size_t)p * 64 + chunk * 8) = v;
-    } else {
-      if (ok) {
-        const float4* src = reinterpret_cast<const float4*>(in + (((int64_t)b * H + iy) * W + ix) * C + c0);
-        f0 = src[0]; f1 = src[1];
-      }
-      float4* dst = reinterpret_cast<float4*>(tile + (size_t)p * 64 + chunk * 8);
-      dst[0] = f0; dst[1] = f1;
+  const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
+  // ---- stage the halo tile (zeros outside the image): 16-byte cp.async per piece, all in flight at once ----
+  {
+    constexpr int PPP = (int)(64 * sizeof(T) / 16);   // 16-byte pieces per pixel: 8 (bf16) or 16 (fp32)
+    constexpr int EPP = (int)(16 / sizeof(T));        // elements per piece
+    for (int i = tid; i < IH * IW * PPP; i += nthr) {
+      const int pix = i / PPP, piece = i - pix * PPP;
+      const int py = pix / IW, px = pix - py * IW;
+      const int iy = iy0 + py, ix = ix0 + px;
+      const int c = cb + piece * EPP;
+      const bool ok = c < C && iy >= 0 && iy < H && ix >= 0 && ix < W;
+      const T* src = ok ? in + (((int64_t)b * H + iy) * W + ix) * C + c : in;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + (size_t)pix * 64 + piece * EPP);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const int quad = tid & 15, col = tid >> 4;          // 4 channels, one output column
+  const int c0 = cb + quad * 4;
+  const bool cvalid = c0 < C;
+  float wk[9][4], sc[4], bi[4], ssum[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { ssum[j] = 0.f; sc[j] = 0.f; bi[j] = 0.f; }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    if (cvalid) load4(w + t * C + c0, wk[t]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wk[t][j] = 0.f;
     }
   }
-  float wk[9][8], sc[8], bi[8], ssum[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { ssum[j] = 0.f; sc[j] = 0.f; bi[j] = 0.f; }
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wk[t][j] = cvalid ? w[t * C + c0 + j] : 0.f;
-  if (cvalid) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; bi[j] = bias[c0 + j]; }
-  }
+  if (cvalid) { load4(scale + c0, sc); load4(bias + c0, bi); }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const int npix = TH * TW;
-  for (int p = plane; p < npix; p += 32) {
-    const int py = p / TW, px = p - py * TW;
-    const int oy = oy0 + py, ox = ox0 + px;
-    if (oy >= Ho || ox >= Wo || !cvalid) continue;
-    float acc[8];
+  const int ox = ox0 + col;
+  if (cvalid && ox < Wo) {
+    const T* tcol = tile + (size_t)(col * STRIDE) * 64 + quad * 4;   // window column 0 of this thread, tile row 0
+    float r[3][3][4];                                                // [window row][window col][channel]
+    auto load_row = [&](int slot, int trow) {
+      const T* rp = tcol + (size_t)trow * IW * 64;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int kx = 0; kx < 3; ++kx) load4(rp + kx * 64, r[slot][kx]);
+    };
+    if (STRIDE == 1) { load_row(0, 0); load_row(1, 1); }
+    for (int py = 0; py < TH; ++py) {
+      const int oy = oy0 + py;
+      if (oy >= Ho) break;
+      if (STRIDE == 1) load_row(2, py + 2);
+      else { if (py == 0) load_row(0, 0); load_row(1, 2 * py + 1); load_row(2, 2 * py + 2); }
+      float acc[4];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+      for (int j = 0; j < 4; ++j) acc[j] = 0.f;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        float v[8];
-        load8(tile + ((size_t)(py * stride + ky) * IW + (px * stride + kx)) * 64 + chunk * 8, v);
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wk[ky * 3 + kx][j], acc[j]);
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(r[ky][kx][j], wk[ky * 3 + kx][j], acc[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float t = fmaf(acc[j], sc[j], bi[j]);
+        acc[j] = sizeof(T) == 4 ? silu_precise(t) : silu_tanh_f(t);
+        ssum[j] += acc[j];
       }
+      store4(out + (((int64_t)b * Ho + oy) * Wo + ox) * C + c0, acc);
+      // slide the window down
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = acc[j] * sc[j] + bi[j];
-      acc[j] = sizeof(T) == 4 ? silu_precise(t) : silu_f(t);
-      ssum[j] += acc[j];
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (STRIDE == 1) { r[0][kx][j] = r[1][kx][j]; r[1][kx][j] = r[2][kx][j]; }
+          else r[0][kx][j] = r[2][kx][j];
+        }
     }
-    store8(out + (((int64_t)b * Ho + oy) * Wo + ox) * C + c0, acc);
   }
   if (se_sum == nullptr) return;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) red[plane * 64 + chunk * 8 + j] = ssum[j];
+  for (int j = 0; j < 4; ++j) red[col * 64 + quad * 4 + j] = ssum[j];
   __syncthreads();
   if (tid < 64) {
     float t = 0.f;
-#pragma unroll 8
-    for (int q = 0; q < 32; ++q) t += red[q * 64 + tid];
-    const int c = blockIdx.y * 64 + tid;
+    for (int q = 0; q < TW; ++q) t += red[q * 64 + tid];
+    const int c = cb + tid;
     if (c < C) atomicAdd(&se_sum[(int64_t)b * C + c], t);
   }
 }
@@ -169,20 +211,30 @@ int dwconv3x3(const void* in, void* out, int dtype, int B, int H, int W, int C, 
   FTC_REQUIRE(C % 8 == 0, "depthwise channels must be a multiple of 8");
   FTC_REQUIRE(stride == 1 || stride == 2, "depthwise stride must be 1 or 2");
   int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;   // k=3, pad=1
-  const int TH = 8, TW = (Wo % 16 == 0) ? 16 : 8;
-  const int tiles_x = ceil_div(Wo, TW), tiles_y = ceil_div(Ho, TH);
-  const int IH = (TH - 1) * stride + 3, IW = (TW - 1) * stride + 3;
+  // one thread per (output column, channel quad): TW columns x 16 quads = block size; tall tiles amortise the window
+  int TW = (Wo % 16 == 0) ? 16 : 8;
+  int TH = (Ho % 24 == 0) ? 24 : ((Ho % 16 == 0) ? 16 : 8);
   const size_t es = dtype == DT_F32 ? 4 : 2;
-  size_t smem = align_up((size_t)IH * IW * 64 * es, 16) + 32 * 64 * sizeof(float);
-  dim3 grid(tiles_x * tiles_y, ceil_div(C, 64), B);
-  static bool attr_done[2] = {false, false};
-  if (dtype == DT_F32) {
-    if (!attr_done[0]) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_done[0] = true; }
-    dwconv3x3_kernel<float><<<grid, 256, smem, s>>>((const float*)in, (float*)out, H, W, C, stride, Ho, Wo, TH, TW, tiles_x, w, scale, bias, se_sum);
-  } else {
-    if (!attr_done[1]) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_done[1] = true; }
-    dwconv3x3_kernel<bf16><<<grid, 256, smem, s>>>((const bf16*)in, (bf16*)out, H, W, C, stride, Ho, Wo, TH, TW, tiles_x, w, scale, bias, se_sum);
+  int IH, IW;
+  size_t smem;
+  for (;;) {
+    IH = (TH - 1) * stride + 3; IW = (TW - 1) * stride + 3;
+    smem = align_up((size_t)IH * IW * 64 * es, 16) + (size_t)TW * 64 * sizeof(float);
+    if (smem <= 72 * 1024 || TH <= 4) break;                   // keep >= 3 CTAs per SM
+    TH /= 2;
   }
+  const int tiles_x = ceil_div(Wo, TW), tiles_y = ceil_div(Ho, TH);
+  dim3 grid(tiles_x * tiles_y, ceil_div(C, 64), B);
+  const int threads = TW * 16;
+#define DW_LAUNCH(TT, SS)                                                                                             \
+  do {                                                                                                                \
+    static bool done = false;                                                                                         \
+    if (!done) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_kernel<TT, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); done = true; } \
+    dwconv3x3_kernel<TT, SS><<<grid, threads, smem, s>>>((const TT*)in, (TT*)out, H, W, C, Ho, Wo, TH, TW, tiles_x, w, scale, bias, se_sum); \
+  } while (0)
+  if (dtype == DT_F32) { if (stride == 1) DW_LAUNCH(float, 1); else DW_LAUNCH(float, 2); }
+  else { if (stride == 1) DW_LAUNCH(bf16, 1); else DW_LAUNCH(bf16, 2); }
+#undef DW_LAUNCH
   FTC_POST_LAUNCH();
   return 0;
 }
@@ -276,6 +328,120 @@ int upsample2x(const void* in, void* out, int dtype, int B, int H, int W, int C,
     upsample2x_kernel<float><<<grid, 256, 0, s>>>((const float*)in, (float*)out, B, H, W, C, sy, sx);
   else
     upsample2x_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, (bf16*)out, B, H, W, C, sy, sx);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Leafmap top_conv of the eight 1-/2-channel heads (models/detector.py:188-190, 3x3, 192 -> 1|2, +bias).
+// As a GEMM this is N <= 2 per head with a private K = 1728 operand per head: pure operand bandwidth (it ran at
+// 5 TFLOP/s on the tensor path).  Here each CTA stages one head's 192-channel halo tile in shared memory once and
+// every lane owns a fixed set of (tap, 8-channel chunk) pairs whose weights live in registers.
+struct HeadTopParams {
+  const void* y; int pix_stride;          // NHWC source, channels of head h at [h*192, h*192+192)
+  const float* w;                         // [rows][9*192] fp32, row = output channel (tap-major k)
+  const float* bias;                      // [rows]
+  float* out; int out_ch;                 // NCHW fp32 [B, out_ch, H, W]
+  int H, W, tiles_x, n_heads;
+  int row_base[8];                        // first output row (= channel) of head h
+  int od[8];                              // 1 or 2
+  int head0;                              // first head index in the source buffer
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) head_top_conv_kernel(const HeadTopParams p) {
+  extern __shared__ __align__(16) unsigned char ht_smem[];
+  constexpr int CD = 192, CH = CD / 8, TH = 8, TW = 16, IH = TH + 2, IW = TW + 2;
+  T* tile = reinterpret_cast<T*>(ht_smem);                                    // [IH*IW][192]
+  float* outs = reinterpret_cast<float*>(ht_smem + (size_t)IH * IW * CD * sizeof(T));   // [2][128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+  const int oy0 = ty * TH, ox0 = tx * TW;
+  const T* src = reinterpret_cast<const T*>(p.y) + (size_t)(p.head0 + h) * CD;
+  constexpr int PIECES = (int)(8 * sizeof(T) / 16);
+  for (int i = tid; i < IH * IW * CH; i += 256) {
+    const int pix = i / CH, ch = i - pix * CH;
+    const int py = pix / IW, px = pix - py * IW;
+    const int iy = oy0 - 1 + py, ix = ox0 - 1 + px;
+    const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+    const T* g = ok ? src + (((int64_t)b * p.H + iy) * p.W + ix) * p.pix_stride + ch * 8 : src;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + (size_t)pix * CD + ch * 8);
+#pragma unroll
+    for (int q = 0; q < PIECES; ++q)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16u * q),
+                   "l"(reinterpret_cast<const char*>(g) + 16 * q), "r"(ok ? 16u : 0u) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int od = p.od[h];
+  for (int o = 0; o < od; ++o) {
+    // lane owns pairs q = lane + 32*it of the 9*24 = 216 (tap, chunk) pairs
+    float wr[7][8];
+    int toff[7];
+    const float* wrow = p.w + (size_t)(p.row_base[h] + o) * (9 * CD);
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+      const int q = lane + 32 * it;
+      const bool ok = q < 9 * CH;
+      const int tap = ok ? q / CH : 0, ch = ok ? q - tap * CH : 0;
+      toff[it] = ((tap / 3) * IW + (tap % 3)) * CD + ch * 8;
+      if (ok) load8(wrow + tap * CD + ch * 8, wr[it]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wr[it][j] = 0.f;
+      }
+    }
+    for (int pi = 0; pi < 16; ++pi) {
+      const int pix = warp * 16 + pi;                 // 8 warps x 16 = 128 tile pixels
+      const int py = pix / TW, px = pix - py * TW;
+      const T* base = tile + (size_t)(py * IW + px) * CD;
+      float acc = 0.f;
+#pragma unroll
+      for (int it = 0; it < 7; ++it) {
+        float v[8];
+        load8(base + toff[it], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(v[j], wr[it][j], acc);
+      }
+#pragma unroll
+      for (int s2 = 16; s2 > 0; s2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s2);
+      if (lane == 0) outs[o * 128 + pix] = acc + p.bias[p.row_base[h] + o];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < od * 128; i += 256) {
+    const int o = i >> 7, pix = i & 127;
+    const int oy = oy0 + pix / TW, ox = ox0 + pix % TW;
+    if (oy < p.H && ox < p.W)
+      p.out[(((int64_t)b * p.out_ch + p.row_base[h] + o) * p.H + oy) * p.W + ox] = outs[i];
+  }
+}
+
+int head_top_conv(const void* y, int dtype, int pix_stride, int head0, int n_heads, const int* od, const float* w,
+                  const float* bias, float* out, int out_ch, int B, int H, int W, cudaStream_t s) {
+  FTC_REQUIRE(n_heads >= 1 && n_heads <= 8, "head_top_conv handles up to 8 heads");
+  HeadTopParams p;
+  p.y = y; p.pix_stride = pix_stride; p.w = w; p.bias = bias; p.out = out; p.out_ch = out_ch; p.H = H; p.W = W;
+  p.tiles_x = ceil_div(W, 16); p.n_heads = n_heads; p.head0 = head0;
+  int row = 0;
+  for (int i = 0; i < 8; ++i) {
+    p.row_base[i] = row; p.od[i] = i < n_heads ? od[i] : 0;
+    FTC_REQUIRE(p.od[i] <= 2, "head_top_conv: out_dim <= 2");
+    row += p.od[i];
+  }
+  dim3 grid(p.tiles_x * ceil_div(H, 8), n_heads, B);
+  const size_t es = dtype == DT_F32 ? 4 : 2;
+  size_t smem = (size_t)10 * 18 * 192 * es + 2 * 128 * sizeof(float);
+  static bool attr_done[2] = {false, false};
+  if (dtype == DT_F32) {
+    if (!attr_done[0]) { FTC_CHECK_CUDA(cudaFuncSetAttribute(head_top_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[0] = true; }
+    head_top_conv_kernel<float><<<grid, 256, smem, s>>>(p);
+  } else {
+    if (!attr_done[1]) { FTC_CHECK_CUDA(cudaFuncSetAttribute(head_top_conv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[1] = true; }
+    head_top_conv_kernel<bf16><<<grid, 256, smem, s>>>(p);
+  }
   FTC_POST_LAUNCH();
   return 0;
 }

@@ -24,6 +24,12 @@ int se_fc(float* sum, float* scale_out, float* hid, int B, int C, int S, float i
 // bilinear x2, align_corners=True, NHWC (nn.UpsamplingBilinear2d, models/detector.py:170)
 int upsample2x(const void* in, void* out, int dtype, int B, int H, int W, int C, cudaStream_t s);
 
+// Leafmap.top_conv (models/detector.py:188-190) of the small heads (out_dim 1 or 2): 3x3, 192 -> od, +bias.
+//   y: NHWC (dtype) with head (head0+i)'s 192 channels at [(head0+i)*192, ...); w: fp32 [sum(od)][9*192] tap-major;
+//   out: NCHW fp32 [B, out_ch, H, W], head i writes channels [sum(od[:i]), +od[i])
+int head_top_conv(const void* y, int dtype, int pix_stride, int head0, int n_heads, const int* od, const float* w,
+                  const float* bias, float* out, int out_ch, int B, int H, int W, cudaStream_t s);
+
 // CenterNetDetector.forward tail (models/detector.py:289-296): heat9 NCHW fp32 -> heat10 NCHW fp32
 int peak_pick(const float* heat9, float* heat10, int B, int H, int W, cudaStream_t s);
 

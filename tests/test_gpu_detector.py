@@ -116,3 +116,23 @@ def test_state_dict_roundtrip_and_fail_loudly(detector_sd):
     assert list(m.state_dict().keys()) == list(detector_sd.keys())
     with pytest.raises(RuntimeError):
         m.eval().detector(torch.zeros(1, 3, 768, 768))      # CPU tensor: no fallback
+
+
+def test_text_detector_model_forward_with_fmask(model, golden_detector):
+    """TextDetectorModel.forward(x, fmask) = heatmap + SimpleDecoder on the fmask-selected pixels
+    (models/detector.py:262-281), fp32, vs the reference golden (every 16th selected row)."""
+    from findtextcenternet_b200 import synthetic
+    m, _ = model
+    m.detector.set_precision("fp32")
+    m.decoder.precision = "fp32"
+    g = golden_detector
+    gen = torch.Generator().manual_seed(7)
+    label = torch.rand(1, 5, 192, 192, generator=gen)
+    fmask = m.get_fmask(label.cuda(), None)
+    assert np.array_equal(torch.nonzero(fmask)[:, 0].cpu().numpy(), g["rand0_fmask_idx"])
+    with torch.no_grad():
+        heat, dec = m(synthetic.detector_input(1, 0, "rand").cuda(), fmask)
+    assert heat.shape == (1, 9, 192, 192)
+    for i, d in enumerate(dec):
+        assert d.shape == (1024, (1091, 1093, 1097)[i])
+        assert rel_l2(d.cpu().numpy()[::16], g[f"rand0_decoder{i}_s16"]) < 1e-3

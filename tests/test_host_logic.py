@@ -1,0 +1,140 @@
+"""CPU: host-side logic, C-ABI surface, world_size-2 gloo sharding."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    from findtextcenternet_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    with open(os.path.join(ROOT, "include", "ftc_b200.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"\b(ftc_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ftc_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert lib.ftc_version() >= 100
+    # struct layout agreement between ctypes and the header (no GPU needed: create/destroy are host-only)
+    cfg = _lib.make_detector_config("xl", _lib.PREC_BF16, _lib.GEMM_TCGEN05)
+    h = C.c_void_p()
+    _lib.check(lib.ftc_detector_create(C.byref(cfg), C.byref(h)))
+    wb = lib.ftc_detector_weight_bytes(h)
+    assert 4.0e8 < wb < 9.0e8, wb            # ~242 M conv weights in bf16 + tables
+    assert lib.ftc_detector_workspace_bytes(h, 32) > lib.ftc_detector_workspace_bytes(h, 1) > 0
+    assert lib.ftc_detector_num_ops(h) > 280
+    lib.ftc_detector_destroy(h)
+    tcfg = _lib.TransformerConfig(106, 512, 16, 16, 16, 100, 100, _lib.PREC_BF16, _lib.GEMM_TCGEN05)
+    _lib.check(lib.ftc_transformer_create(C.byref(tcfg), C.byref(h)))
+    assert lib.ftc_transformer_weight_bytes(h) > 2.0e8
+    assert lib.ftc_transformer_workspace_bytes(h, 256, 100, 100) > 0
+    lib.ftc_transformer_destroy(h)
+    # bad configs fail loudly with a message
+    bad = _lib.TransformerConfig(106, 500, 16, 1, 1, 100, 100, 0, 0)
+    assert lib.ftc_transformer_create(C.byref(bad), C.byref(h)) != 0
+    assert b"embed_dim" in lib.ftc_last_error()
+
+
+def test_product_path_has_no_cpu_fallback():
+    from findtextcenternet_b200.models.detector import TextDetectorModel
+    from findtextcenternet_b200.models.transformer import ModelDimensions, Transformer
+    m = TextDetectorModel(pre_weights=False).eval()
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            m.detector(torch.zeros(1, 3, 768, 768))
+    t = Transformer(**ModelDimensions(embed_dim=64, head_num=4, enc_block_num=1, dec_block_num=1).__dict__).eval()
+    with pytest.raises(RuntimeError):
+        t(torch.zeros(1, 8, 106), torch.zeros(1, 8, dtype=torch.long))
+    with pytest.raises(NotImplementedError):
+        m.train().detector(torch.zeros(1, 3, 768, 768))
+    # nothing under the package imports the oracle
+    pkg = os.path.join(ROOT, "findtextcenternet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_tile_meta_matches_oracle_mask():
+    from findtextcenternet_b200.process_ocr_b200 import tile_meta
+    from oracle import detector_oracle as DO
+    for (x_i, y_i, w, h) in [(0, 0, 768, 768), (0, 0, 2148, 2148), (460, 0, 2148, 2148), (1380, 920, 2148, 2148), (460, 460, 1228, 1688)]:
+        ox, oy, x0, x1, y0, y1 = tile_meta(x_i, y_i, w, h)
+        mask = np.zeros((192, 192), bool)
+        mask[y0:y1, x0:x1] = True
+        assert (ox, oy) == (x_i, y_i)
+        assert np.array_equal(mask, DO.tile_mask(x_i, y_i, w, h))
+
+
+def test_shard_range_partitions():
+    from findtextcenternet_b200.shard import shard_range
+    for n in (0, 1, 7, 16, 33):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["FTC_ROOT"])
+from findtextcenternet_b200.shard import shard_range, gather_ragged, allreduce_gradients
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# inference sharding: 16 tiles -> ranks, ragged per-rank results gathered everywhere
+a, b = shard_range(16, rank, world)
+local = torch.arange(a, b, dtype=torch.float32).repeat_interleave(rank + 1).unsqueeze(1)   # rank-dependent row count
+parts = gather_ragged(local)
+assert len(parts) == world
+for r, p in enumerate(parts):
+    ra, rb = shard_range(16, r, world)
+    assert torch.equal(p[:, 0], torch.arange(ra, rb, dtype=torch.float32).repeat_interleave(r + 1)), (r, p)
+# training: bucketed gradient averaging equals the mean of per-rank gradients
+torch.manual_seed(0)
+model = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Linear(53, 11))
+g = torch.Generator().manual_seed(100 + rank)
+for p in model.parameters():
+    p.grad = torch.randn(p.shape, generator=g)
+expect = []
+for p in model.parameters():
+    acc = torch.zeros_like(p)
+    for r in range(world):
+        gr = torch.Generator().manual_seed(100 + r)
+        # regenerate rank r's gradients in registration order
+    expect.append(None)
+grads_all = []
+for r in range(world):
+    gr = torch.Generator().manual_seed(100 + r)
+    grads_all.append([torch.randn(p.shape, generator=gr) for p in model.parameters()])
+calls = allreduce_gradients(model.parameters(), bucket_bytes=4096)
+assert calls >= 2
+for i, p in enumerate(model.parameters()):
+    mean = sum(grads_all[r][i] for r in range(world)) / world
+    assert torch.allclose(p.grad, mean, atol=1e-6), i
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_world2_sharding_and_gradient_allreduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, FTC_ROOT=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + os.getpid() % 300), str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") >= 2   # the two ranks interleave their prints

@@ -1,0 +1,48 @@
+"""Transformer config #4 (BASELINE.json configs[3]): enc100/dec100, d=512, 16 heads, 16+16 layers, batch 256, bf16 tcgen05.
+Prints one JSON line: sequences/s for Transformer.forward and for the <=8-pass TransformerPredictor loop."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from findtextcenternet_b200 import synthetic, _lib
+import findtextcenternet_b200.models.transformer as T
+
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
+prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+dims = dict(cfg4=dict(embed_dim=512, head_num=16, enc_block_num=16, dec_block_num=16, max_enc_seq_len=100, max_dec_seq_len=100),
+            default=dict())[name]
+B = 256 if name == "cfg4" else 64
+cfg = T.ModelDimensions(**dims)
+m = T.Transformer(**cfg.__dict__)
+m.load_state_dict(synthetic.transformer_state_dict(0, **dims))
+m = m.cuda().eval().set_precision(prec)
+m.weights_frozen = True
+enc, dec, _ = synthetic.transformer_inputs(B, cfg.max_enc_seq_len, cfg.max_dec_seq_len, 0)
+enc, dec = enc.cuda(), dec.cuda()
+flop = {"cfg4": 21.47e9, "default": 130.0e9}[name]
+with torch.no_grad():
+    for _ in range(3):
+        m(enc, dec)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 10
+    a.record()
+    for _ in range(steps):
+        m(enc, dec)
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    launches = (_lib.launch_count() - l0) // steps
+    T.max_decoderlen = cfg.max_dec_seq_len
+    pred = T.TransformerPredictor(m.encoder, m.decoder).cuda().eval().set_precision(prec)
+    pred.verbose = False; pred.weights_frozen = True
+    pred(enc); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ids = pred(enc); torch.cuda.synchronize()
+    pred_s = time.perf_counter() - t0
+peak = 1390.7
+if os.path.exists("MEASURED_PEAKS.json"):
+    peak = json.load(open("MEASURED_PEAKS.json")).get("bf16_tflops_sustained", peak)
+print(json.dumps({"metric": "transformer_fwd_sequences_per_sec", "config": name, "precision": prec, "batch": B,
+                  "value": B / (ms / 1e3), "ms_per_batch": ms, "tflops": flop * B / (ms / 1e3) / 1e12,
+                  "frac_of_bf16_sustained": flop * B / (ms / 1e3) / 1e12 / peak, "launches_per_forward": launches,
+                  "predictor_passes": pred.last_passes, "predictor_seq_per_s": B / pred_s, "predictor_s": pred_s}))

@@ -11,7 +11,7 @@ x = torch.rand(B, 3, 768, 768, device="cuda")
 eng = m.detector.engine(x.device)
 for _ in range(2): eng.forward_timed(x)
 ops = eng.forward_timed(x)
-names = {0: "stem", 1: "conv3x3", 2: "conv1x1", 3: "dw+se", 4: "se_fc", 5: "upsample"}
+names = {0: "stem", 1: "conv3x3", 2: "conv1x1", 3: "dw+se", 4: "se_fc", 5: "upsample", 6: "top_small"}
 tot = sum(o[1] for o in ops)
 print(f"batch {B}: {tot:.2f} ms total, {len(ops)} ops")
 for i, (k, ms, fl) in enumerate(ops):
