@@ -74,12 +74,15 @@ SYMBOLS = {
     "ftc_transformer_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "ftc_transformer_predict": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, C.POINTER(_i), C.POINTER(_i), _vp, _sz, _vp]),
     "ftc_mask_predict_step": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "ftc_adamw_sf_chunk_elems": (_i, []),
+    "ftc_adamw_sf_step": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _vp]),
     "ftc_peak_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "ftc_peak_pick": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ftc_op_conv2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "ftc_op_conv2d_wpack_bytes": (_sz, [_i, _i, _i]),
     "ftc_op_dwconv3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "ftc_op_se_fc": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "ftc_debug_set_trace": (_i, [_vp]),
     "ftc_op_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 

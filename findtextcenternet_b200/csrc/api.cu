@@ -133,6 +133,11 @@ int ftc_mask_predict_step(const float* logits, int ld, int head_ld, const int64_
   return mask_predict_step(logits, ld, head_ld, dec_in, ids, prob, next_in, flags, rows, (cudaStream_t)stream);
 }
 
+int ftc_debug_set_trace(void* dev_u64_4096) {
+  conv_gemm_tc_set_trace((unsigned long long*)dev_u64_4096);
+  return 0;
+}
+
 int ftc_op_upsample2x(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream) {
   FTC_REQUIRE(x && out, "null argument");
   return upsample2x(x, out, dtype, batch, h, w, c, (cudaStream_t)stream);

@@ -36,6 +36,7 @@ struct ConvTcPlan {
   int NT;       // N tiles per group; packed weight rows per group = NT*BN
   int NKB;      // K / KBLOCK
   int stages;   // smem pipeline depth
+  int MT;       // 128-row sub-tiles per CTA tile (1 or 2)
   int flags;    // experiment bits (env FTC_TC_FLAGS; results are garbage when >= 4): 1 try_wait suspend hint, 2 epilogue
                 // poll backoff, 4 skip B copies, 8 skip A gathers, 16 skip MMAs, 32 skip epilogue math/stores
 };
@@ -70,6 +71,7 @@ struct ConvGemmParams {
   int n_valid[MAX_GROUPS];                     // channels of group g actually stored (<= N)
   int dtype;                                   // DT_F32 / DT_BF16 (sources, weights, NHWC output, residuals)
   ConvTcPlan tc;                               // tcgen05 path only
+  unsigned long long* trace;                   // optional clock64 trace of CTA 0 (ftc_debug_set_trace), else null
 };
 
 // SIMT (CUDA-core, fp32 accumulate) implementation: any dtype, the parity path.
@@ -84,6 +86,7 @@ int conv_gemm_tc(const ConvGemmParams& p, cudaStream_t stream);
 int pack_conv_weight_tc(void* dst, const float* src, int O, int Itot, int kh, int kw, int c_off, int C, int k_off,
                         int Kpad, int o_off, int BN, const float* cscale, cudaStream_t s);
 size_t conv_tc_weight_bytes(const ConvTcPlan& plan, int G);
+void conv_gemm_tc_set_trace(unsigned long long* dev_ptr);   // 4 x 1024 u64: MMA wait start/end, producer wait start/end
 
 std::vector<uint32_t> make_ktab(int CA, int CB, int ksize, int* Kout);
 

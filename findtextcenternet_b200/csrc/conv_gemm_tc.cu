@@ -22,7 +22,7 @@ namespace {
 constexpr int TC_BM = 128;
 // warp roles: 0-7 epilogue, 8 MMA issuer, 9-16 producers (producers get the HIGHEST warp ids: the SM's issue arbiter
 // favours high warp ids, and the producers' address-generation chain is the critical path of the pipeline)
-constexpr int PROD_WARPS = 8, PROD_THREADS = PROD_WARPS * 32, ROWS_PER_THREAD = TC_BM * 8 / PROD_THREADS;   // 4
+constexpr int PROD_WARPS = 8;
 constexpr int MMA_WARP = 8, PROD_WARP0 = 9;
 constexpr int TC_THREADS = (8 + 1 + PROD_WARPS) * 32;   // 544
 constexpr int TC_MAX_KTAB = 1536;         // k-chunk table entries staged in shared memory (K <= 12288)
@@ -85,15 +85,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {   // wait until at most n groups are pending
-  switch (n) {
-    case 0: cp_async_wait<0>(); break;
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    default: cp_async_wait<4>(); break;
-  }
-}
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   // the barrier receives this thread's arrival when all of its earlier cp.async copies have landed (non-blocking)
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -134,12 +125,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 }
 
 struct TileCoord { int m0, g, nt; };
-__device__ __forceinline__ TileCoord decode_tile(int tile, int NT, int G) {
+__device__ __forceinline__ TileCoord decode_tile(int tile, int NT, int G, int rows_per_tile) {
   int per_m = NT * G;
   int mt = tile / per_m;
   int rest = tile - mt * per_m;
   TileCoord t;
-  t.m0 = mt * TC_BM;
+  t.m0 = mt * rows_per_tile;
   t.g = rest / NT;
   t.nt = rest - t.g * NT;
   return t;
@@ -247,7 +238,10 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int STAGED_FLOATS = 10 * 256;   // per-tile scale[BN] + bias[ncase<=9][BN]
 
-template <bool SE>
+// MT = number of 128-row sub-tiles per CTA tile (1: 128 x BN with double-buffered TMEM accumulators so the epilogue
+// overlaps the next main loop; 2: 256 x BN, two accumulators sharing every B stage -> 30 % fewer smem bytes per MMA
+// cycle, used when K is long enough that the exposed epilogue is small)
+template <bool SE, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ ConvGemmParams p,
                                                                       const int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -256,7 +250,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
   uint8_t* smem = smem_raw + (sbase - raw);
   const int S = p.tc.stages, BN = p.tc.BN, NKB = p.tc.NKB, NT = p.tc.NT;
   const uint32_t b_bytes = (uint32_t)BN * 128u;
-  const uint32_t stage_bytes = A_STAGE_BYTES + b_bytes;
+  constexpr uint32_t A_BYTES = (uint32_t)MT * A_STAGE_BYTES;
+  const uint32_t stage_bytes = A_BYTES + b_bytes;
   const uint32_t bar0 = sbase + (uint32_t)S * stage_bytes;   // 8 B each: full[S], empty[S], tfull[2], tempty[2]
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
@@ -271,8 +266,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == MMA_WARP) {
     if (lane == 0) {
-      const bool async_arrive = !SE && !(p.tc.flags & 256);   // producers arrive through cp.async.mbarrier.arrive.noinc
-      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), (async_arrive ? PROD_THREADS : PROD_WARPS) + 1); mbar_init(empty_bar(s), 1); }
+      // full: the B expect_tx arrive + either 256 async per-thread arrivals or (SE) one arrival per producer warp
+      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1 + (SE ? PROD_WARPS : PROD_WARPS * 32)); mbar_init(empty_bar(s), 1); }
       for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -292,49 +287,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
 
   if (warp >= PROD_WARP0) {
     // ------------------------------------------------------------------ A producers (+ B bulk copy)
+    // All 8 producer warps cooperate on every k-block: thread t owns chunk j = t & 7 of rows (t >> 3) + 32*i.
+    // Plain convs publish through cp.async.mbarrier.arrive.noinc (the barrier receives the thread's arrival when its
+    // copies land), so producers only ever block on the stage-empty barrier.  SE convs keep `lag` k-blocks in flight,
+    // then scale the landed operand in place and publish.
+    constexpr int ROWS = 4 * MT;                   // rows per thread
     const int t = threadIdx.x - PROD_WARP0 * 32;   // 0..255
-    const int j = t & 7;             // 16-byte chunk of the 128-byte k-block row this thread fills
-    const int rbase = t >> 3;        // rows rbase + 32*i, i = 0..3
+    const int j = t & 7;
+    const int rbase = t >> 3;                      // 0..31
     const uint32_t row_off = (uint32_t)(rbase >> 3) * 1024u + (uint32_t)(rbase & 7) * 128u + (uint32_t)((j ^ (rbase & 7)) << 4);
-    constexpr uint32_t ROW_STEP = 32u * 128u;      // 32 rows further down the tile = 4 swizzle groups
+    auto dst_off = [&](int i) { return (uint32_t)(i >> 2) * A_STAGE_BYTES + row_off + (uint32_t)(i & 3) * 4096u; };
     const bf16* srcA = reinterpret_cast<const bf16*>(p.srcA);
     const bf16* srcB = reinterpret_cast<const bf16*>(p.srcB);
     const bf16* wgt = reinterpret_cast<const bf16*>(p.w);
     const bf16* any_src = srcA ? srcA : srcB;      // dereferenceable address for zero-byte (fill-only) copies
     int stage = 0;
     uint32_t phase = 0;
-    int arr_stage = 0;               // oldest stage whose A fill this thread still has to publish
-    int arr_kb = 0;                  // its k-block index inside the current tile (SE scaling needs the channel)
-    uint32_t pending = 0;            // committed-but-unpublished cp.async groups
-    int img[ROWS_PER_THREAD];
-    int lag = S - 2 > 4 ? 4 : S - 2;   // one stage being consumed + one of slack; the rest in flight
-    if ((p.tc.flags >> 6) & 3) lag = (p.tc.flags >> 6) & 3;
-    if (lag > S - 2) lag = S - 2;
-    const bool async_arrive = !SE && !(p.tc.flags & 256);
+    int arr_stage = 0;               // SE: oldest stage whose A fill this thread still has to publish
+    int arr_kb = 0;                  //     its k-block index inside the current tile (the scale needs the channel)
+    uint32_t pending = 0;            //     committed-but-unpublished cp.async groups
+    int img[ROWS];
+    int trace_n = 0;
+    const int lag = S - 2 > 2 ? 2 : (S - 2 < 1 ? 1 : S - 2);
 
-    // publish the oldest pending stage: its cp.async group has completed (caller waited); SE: scale in place first
-    auto publish = [&]() {
-      if (SE) {
-        const uint32_t e = sktab[arr_kb * 8 + j];
-        if (e & KT_VALID) {
-          const int c = kt_c(e);
-          const uint32_t a_dst = sbase + (uint32_t)arr_stage * stage_bytes + row_off;
+    auto publish = [&]() {           // SE only: the oldest group has landed (caller waited)
+      const uint32_t e = sktab[arr_kb * 8 + j];
+      if (e & KT_VALID) {
+        const int c = kt_c(e);
+        const uint32_t a_dst = sbase + (uint32_t)arr_stage * stage_bytes;
 #pragma unroll
-          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-            uint4 u;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
-                         : "r"(a_dst + (uint32_t)i * ROW_STEP) : "memory");
-            const float4* sp = reinterpret_cast<const float4*>(p.a_scale + (int64_t)img[i] * p.a_scale_stride + c);
-            const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-            float2 f;
-            f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * s0.x, f.y * s0.y);
-            f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * s0.z, f.y * s0.w);
-            f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * s1.x, f.y * s1.y);
-            f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * s1.z, f.y * s1.w);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_dst + (uint32_t)i * ROW_STEP), "r"(u.x), "r"(u.y),
-                         "r"(u.z), "r"(u.w) : "memory");
-          }
+        for (int i = 0; i < ROWS; ++i) {
+          const uint32_t addr = a_dst + dst_off(i);
+          uint4 u;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+          const float4* sp = reinterpret_cast<const float4*>(p.a_scale + (int64_t)img[i] * p.a_scale_stride + c);
+          const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+          float2 f;
+          f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * s0.x, f.y * s0.y);
+          f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * s0.z, f.y * s0.w);
+          f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * s1.x, f.y * s1.y);
+          f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * s1.z, f.y * s1.w);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
         }
       }
       fence_proxy_async();
@@ -346,14 +340,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
     };
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(tile, NT, G);
+      const TileCoord tc = decode_tile(tile, NT, G, MT * TC_BM);
       // per row: pixel offset of tap (0,0) and a 9-bit mask of the taps that fall inside the image, so the k-loop
       // spends ~5 instructions per 16-byte gather (test bit, 2 selects, one 64-bit multiply-add, cp.async)
-      int pixoff[ROWS_PER_THREAD];
-      uint32_t vmask[ROWS_PER_THREAD];
+      int pixoff[ROWS];
+      uint32_t vmask[ROWS];
 #pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        const int m = tc.m0 + rbase + 32 * i;
+      for (int i = 0; i < ROWS; ++i) {
+        const int m = tc.m0 + (i >> 2) * TC_BM + rbase + 32 * (i & 3);
         pixoff[i] = 0; vmask[i] = 0u; img[i] = 0;
         if (m < p.M) {
           const int b = m / hw;
@@ -380,36 +374,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
         const bool srcb = (e & KT_SRCB) != 0;
         const int ky = kt_ky(e), kx = kt_kx(e);
         const int pstride = srcb ? p.b_pix_stride : p.a_pix_stride;
-        // address of this chunk for a row whose tap-(0,0) pixel offset is 0
         const uint32_t tapbit = (e & KT_VALID) ? (1u << (ky * 3 + kx)) : 0u;
+        // address of this chunk for a row whose tap-(0,0) pixel offset is 0
         const bf16* kbase = tapbit == 0u ? any_src
                                          : (srcb ? (srcB + p.b_ch_off + tc.g * p.b_group_stride) : (srcA + p.a_ch_off)) + kt_c(e) +
                                                (int64_t)(ky * p.W + kx) * pstride;
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && t == 0 && trace_n < 1024;
+        if (tr) p.trace[2048 + trace_n] = clock64();
         if (lane == 0) mbar_wait(empty_bar(stage), phase ^ 1u, 0, hint_ns);
+        if (tr) p.trace[3072 + trace_n++] = clock64();
         __syncwarp();
         const uint32_t a_dst = sbase + (uint32_t)stage * stage_bytes;
         if (t == 0) {
           if (p.tc.flags & 4) mbar_arrive(full_bar(stage));       // experiment: no B traffic
           else {
             mbar_arrive_expect_tx(full_bar(stage), b_bytes);
-            bulk_copy_g2s(a_dst + A_STAGE_BYTES, wtile + (size_t)kb * BN * 64, b_bytes, full_bar(stage));
+            bulk_copy_g2s(a_dst + A_BYTES, wtile + (size_t)kb * BN * 64, b_bytes, full_bar(stage));
           }
         }
         if (!(p.tc.flags & 8)) {                                   // experiment: no A traffic
 #pragma unroll
-          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          for (int i = 0; i < ROWS; ++i) {
             const bool ok = (vmask[i] & tapbit) != 0u;
             const bf16* src = kbase + (int64_t)(ok ? pixoff[i] : 0) * pstride;
-            cp_async16(a_dst + row_off + (uint32_t)i * ROW_STEP, src, ok ? 16u : 0u);
+            cp_async16(a_dst + dst_off(i), src, ok ? 16u : 0u);
           }
         }
-        if (async_arrive) {
+        if (!SE) {
           cp_async_mbar_arrive_noinc(full_bar(stage));   // never blocks: only the empty barrier paces the producers
         } else {
           cp_async_commit();
           ++pending;
           if (pending > (uint32_t)lag) {     // keep `lag` k-blocks of gathers in flight, publish the oldest
-            cp_async_wait_dyn(lag);
+            if (lag == 1) cp_async_wait<1>(); else cp_async_wait<2>();
             publish();
           }
         }
@@ -421,30 +418,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
         while (pending > 0) publish();
       }
     }
-    cp_async_wait<0>();
-    while (pending > 0) publish();
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0;
+      int trace_n = 0;
       uint32_t phase = 0;
       uint32_t titer = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
-        const uint32_t acc = titer & 1u;
-        mbar_wait(tempty_bar(acc), ((titer >> 1) & 1u) ^ 1u, 0, hint_ns);
+        // MT == 1: two accumulators alternate (epilogue overlaps the next main loop); MT == 2: both belong to this tile
+        const uint32_t acc = MT == 1 ? (titer & 1u) : 0u;
+        const uint32_t use = MT == 1 ? (titer >> 1) : titer;
+        mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u, 0, hint_ns);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
         for (int kb = 0; kb < NKB; ++kb) {
+          const bool tr = p.trace != nullptr && blockIdx.x == 0 && trace_n < 1024;
+          if (tr) p.trace[trace_n] = clock64();
           mbar_wait(full_bar(stage), phase, 0, hint_ns);
+          if (tr) p.trace[1024 + trace_n++] = clock64();
           tc_fence_after();
           const uint32_t a_addr = sbase + (uint32_t)stage * stage_bytes;
-          const uint64_t adesc = umma_desc_sw128(a_addr);
-          const uint64_t bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + A_BYTES);
           if (!(p.tc.flags & 16))                                   // experiment: no MMA
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row: +2 in 16-byte units
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row: +2 in 16-byte units
+#pragma unroll
+            for (int h = 0; h < MT; ++h)
+              umma_f16(d_tmem + (uint32_t)h * (uint32_t)BN, umma_desc_sw128(a_addr + (uint32_t)h * A_STAGE_BYTES) + (uint64_t)(2 * k),
+                       bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(empty_bar(stage));
           stage = (stage + 1 == S) ? 0 : stage + 1;
           phase ^= (stage == 0) ? 1u : 0u;
@@ -457,17 +461,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
     // ------------------------------------------------------------------ epilogue (8 warps: 4 lane quarters x 2 column halves)
     const int ew = warp;                       // 0..7
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                  // which 16-column chunks (even / odd)
+    const int half = ew >> 2;                  // MT == 1: which 16-column chunks (even / odd); MT == 2: which 128-row sub-tile
     const int etid = threadIdx.x;              // 0..255
-    const int row = q * 32 + lane;
+    const int row = (MT == 2 ? half * TC_BM : 0) + q * 32 + lane;
     const bf16* res1 = reinterpret_cast<const bf16*>(p.res1);
     const bf16* res2 = reinterpret_cast<const bf16*>(p.res2);
     float* sscale = staged;                    // [BN]
     float* sbias = staged + 256;               // [ncase][BN]
     uint32_t titer = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
-      const TileCoord tc = decode_tile(tile, NT, G);
-      const uint32_t acc = titer & 1u;
+      const TileCoord tc = decode_tile(tile, NT, G, MT * TC_BM);
+      const uint32_t acc = MT == 1 ? (titer & 1u) : 0u;
+      const uint32_t use = MT == 1 ? (titer >> 1) : titer;
       // stage this tile's per-column scale / bias (the previous tile's readers are past this barrier)
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       {
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-      if (lane == 0) mbar_wait(tfull_bar(acc), (titer >> 1) & 1u, epi_backoff_ns, hint_ns);
+      if (lane == 0) mbar_wait(tfull_bar(acc), use & 1u, epi_backoff_ns, hint_ns);
       __syncwarp();
       tc_fence_after();
       const int m = tc.m0 + row;
@@ -495,8 +500,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
       const int64_t r1row = p.res1_row_mod ? (m % p.res1_row_mod) : m;
       const int nvalid = min(p.N, p.n_valid[tc.g]);
       const int chb = p.out_ch_base[tc.g];
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN;
-      for (int c0 = half * 16; c0 < BN; c0 += 32) {
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (MT == 1 ? acc : (uint32_t)half) * (uint32_t)BN;
+      for (int c0 = (MT == 1 ? half * 16 : 0); c0 < BN; c0 += (MT == 1 ? 32 : 16)) {
         const int n0 = tc.nt * BN + c0;
         if (n0 >= p.N) break;                       // warp-uniform
         uint32_t raw16[16];
@@ -542,9 +547,15 @@ __global__ void pack_conv_weight_tc_kernel(bf16* __restrict__ dst, const float* 
 }
 
 int g_num_sms = 0;
-bool g_attr_set[2] = {false, false};
+unsigned long long* g_trace = nullptr;
 
 }  // namespace
+
+static int tc_stages(int MT, int BN) {
+  int stage_bytes = MT * (int)A_STAGE_BYTES + BN * 128;
+  int s = (208 * 1024) / stage_bytes;
+  return s > TC_MAX_STAGES ? TC_MAX_STAGES : (s < 2 ? 2 : s);
+}
 
 int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan) {
   FTC_REQUIRE(p.K % KBLOCK == 0 && p.K > 0, "K must be a positive multiple of 64");
@@ -563,11 +574,12 @@ int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan) {
   plan->NT = best_nt;
   plan->NKB = p.K / KBLOCK;
   plan->flags = 0;
-  int stage_bytes = (int)A_STAGE_BYTES + best_bn * 128;
-  int s = (202 * 1024) / stage_bytes;
-  plan->stages = s > TC_MAX_STAGES ? TC_MAX_STAGES : (s < 3 ? 3 : s);
+  plan->MT = 1;
+  plan->stages = tc_stages(1, best_bn);
   return 0;
 }
+
+void conv_gemm_tc_set_trace(unsigned long long* dev_ptr) { g_trace = dev_ptr; }
 
 size_t conv_tc_weight_bytes(const ConvTcPlan& plan, int G) {
   return (size_t)G * plan.NT * plan.NKB * plan.BN * 128;
@@ -588,6 +600,7 @@ int conv_gemm_tc(const ConvGemmParams& p_in, cudaStream_t stream) {
   if (env_flags < 0) { const char* e = getenv("FTC_TC_FLAGS"); env_flags = e ? atoi(e) : 0; }
   ConvGemmParams p = p_in;
   p.tc.flags = env_flags;
+  p.trace = g_trace;
   FTC_REQUIRE(p.dtype == DT_BF16, "tcgen05 path is bf16 only");
   FTC_REQUIRE(p.G >= 1 && p.G <= MAX_GROUPS, "groups out of range");
   FTC_REQUIRE(p.tc.BN >= 16 && p.tc.BN <= 256 && p.tc.BN % 16 == 0, "bad tc plan");
@@ -600,20 +613,29 @@ int conv_gemm_tc(const ConvGemmParams& p_in, cudaStream_t stream) {
     FTC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const bool se = p.a_scale != nullptr;
-  if (!g_attr_set[se ? 1 : 0]) {
-    if (se) FTC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    else FTC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    g_attr_set[se ? 1 : 0] = true;
-  }
-  const int m_tiles = ceil_div(p.M, TC_BM);
+  // tile height is a launch-time choice (the weight image only depends on BN): 256-row tiles when the main loop is
+  // long enough to amortise the non-overlapped epilogue and there are enough rows to fill the machine
+  p.tc.MT = (p.tc.NKB >= 12 && p.M >= 2 * TC_BM * 128 && !(p.tc.flags & 512)) ? 2 : 1;
+  p.tc.stages = tc_stages(p.tc.MT, p.tc.BN);
+  const int m_tiles = ceil_div(p.M, TC_BM * p.tc.MT);
   const int num_tiles = m_tiles * p.tc.NT * p.G;
-  size_t smem = (size_t)p.tc.stages * (A_STAGE_BYTES + (size_t)p.tc.BN * 128) + 1024 + 256 + STAGED_FLOATS * 4 + TC_MAX_KTAB * 4;
+  size_t smem = (size_t)p.tc.stages * ((size_t)p.tc.MT * A_STAGE_BYTES + (size_t)p.tc.BN * 128) + 1024 + 256 + STAGED_FLOATS * 4 + TC_MAX_KTAB * 4;
   FTC_REQUIRE(p.tc.NKB * 8 <= TC_MAX_KTAB, "K too large for the shared-memory chunk table");
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: the CTA owns all 512 TMEM columns
   FTC_REQUIRE(smem <= 227 * 1024, "smem budget");
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  if (se) conv_gemm_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p, num_tiles);
-  else conv_gemm_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p, num_tiles);
+#define TC_LAUNCH(SE_, MT_)                                                                                        \
+  do {                                                                                                             \
+    static bool attr_done = false;                                                                                 \
+    if (!attr_done) {                                                                                              \
+      FTC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<SE_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_done = true;                                                                                            \
+    }                                                                                                              \
+    conv_gemm_tc_kernel<SE_, MT_><<<grid, TC_THREADS, smem, stream>>>(p, num_tiles);                               \
+  } while (0)
+  if (se) { if (p.tc.MT == 2) TC_LAUNCH(true, 2); else TC_LAUNCH(true, 1); }
+  else { if (p.tc.MT == 2) TC_LAUNCH(false, 2); else TC_LAUNCH(false, 1); }
+#undef TC_LAUNCH
   FTC_POST_LAUNCH();
   return 0;
 }

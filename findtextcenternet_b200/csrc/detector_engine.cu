@@ -48,7 +48,7 @@ struct GemmOp {
   bool has_scale = true;
   size_t w_off = 0, scale_off = 0, bias_off = 0, ktab_off = 0;
   std::vector<uint32_t> ktab;
-  ConvTcPlan tc{0, 0, 0, 0, 0};
+  ConvTcPlan tc{0, 0, 0, 0, 1, 0};
 };
 
 struct Op {

@@ -1,0 +1,67 @@
+// Fused multi-tensor Schedule-Free AdamW step (models/adamw_schedulefree.py:157-184, the foreach branch) in ONE launch:
+// per element 4 reads (y, grad, exp_avg_sq, z) + 4 writes instead of ~12 foreach passes over 262 M parameters.
+#include "../../include/ftc_b200.h"
+#include "common.cuh"
+
+namespace ftc {
+
+struct SfChunk { int tensor; int pad; int64_t offset; };   // one CTA handles elements [offset, offset + CHUNK) of `tensor`
+
+namespace {
+constexpr int SF_CHUNK = 8192;
+
+__global__ void __launch_bounds__(256) adamw_sf_step_kernel(const SfChunk* __restrict__ chunks, float* const* __restrict__ ys,
+                                                            float* const* __restrict__ grads, float* const* __restrict__ vs,
+                                                            float* const* __restrict__ zs, const int64_t* __restrict__ numels,
+                                                            float beta1, float beta2, float bias_correction2, float eps,
+                                                            float decay, float lr, float ckp1) {
+  const SfChunk c = chunks[blockIdx.x];
+  float* y = ys[c.tensor] + c.offset;
+  float* g = grads[c.tensor] + c.offset;
+  float* v = vs[c.tensor] + c.offset;
+  float* z = zs[c.tensor] + c.offset;
+  const int64_t left = numels[c.tensor] - c.offset;
+  const int n = left < SF_CHUNK ? (int)left : SF_CHUNK;
+  const float one_m_beta2 = 1.0f - beta2;
+  const float y_alpha = lr * (beta1 * (1.0f - ckp1) - 1.0f);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float gi = g[i];
+    float vi = v[i] * beta2;                       // _foreach_mul_(exp_avg_sq, beta2)
+    vi = vi + one_m_beta2 * (gi * gi);             // _foreach_addcmul_(exp_avg_sq, grad, grad, value=1-beta2)
+    v[i] = vi;
+    const float denom = sqrtf(vi / bias_correction2) + eps;
+    float gn = gi / denom;                          // grad is normalised IN PLACE in the reference
+    float yi = y[i];
+    if (decay != 0.0f) gn = gn + decay * yi;
+    g[i] = gn;
+    const float zi = z[i];
+    // torch lerp: weight < 0.5 ? start + weight*(end-start) : end - (end-start)*(1-weight)
+    const float diff = zi - yi;
+    yi = ckp1 < 0.5f ? yi + ckp1 * diff : zi - diff * (1.0f - ckp1);
+    yi = yi + y_alpha * gn;
+    y[i] = yi;
+    z[i] = zi - lr * gn;
+  }
+}
+}  // namespace
+}  // namespace ftc
+
+using namespace ftc;
+
+extern "C" {
+
+int ftc_adamw_sf_chunk_elems(void) { return SF_CHUNK; }
+
+int ftc_adamw_sf_step(int n_chunks, const void* chunks, const void* const* ys, const void* const* grads,
+                      const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, float beta1, float beta2,
+                      float bias_correction2, float eps, float weight_decay, float lr, float ckp1, void* stream) {
+  FTC_REQUIRE(n_chunks >= 0 && chunks && ys && grads && exp_avg_sqs && zs && numels, "bad argument");
+  if (n_chunks == 0) return 0;
+  adamw_sf_step_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(
+      (const SfChunk*)chunks, (float* const*)ys, (float* const*)grads, (float* const*)exp_avg_sqs, (float* const*)zs, numels,
+      beta1, beta2, bias_correction2, eps, weight_decay, lr, ckp1);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -46,7 +46,7 @@ struct Lin {
   bool has_bias = false, has_tab = false;
   int tab_rows = 0;
   std::vector<uint32_t> ktab;
-  ConvTcPlan tc{0, 0, 0, 0, 0};
+  ConvTcPlan tc{0, 0, 0, 0, 1, 0};
 };
 
 struct LNw { size_t g_off = 0, b_off = 0; };

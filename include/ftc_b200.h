@@ -121,6 +121,15 @@ int ftc_transformer_predict(ftc_transformer* t, const float* enc_input, int batc
 int ftc_mask_predict_step(const float* logits, int ld, int head_ld, const int64_t* dec_in, int64_t* ids, float* prob,
                           int64_t* next_in, int* flags, int rows, void* stream);
 
+/* ---- train step: fused multi-tensor Schedule-Free AdamW update (models/adamw_schedulefree.py:157-184) ----
+ * chunks: device array of {int32 tensor, int32 pad, int64 offset} (one CTA per ftc_adamw_sf_chunk_elems() elements);
+ * ys/grads/exp_avg_sqs/zs: device arrays of fp32 device pointers, numels: device int64 per tensor.
+ * Updates exp_avg_sq, grad (normalised in place, as the reference does), y (= the parameter) and z. */
+int ftc_adamw_sf_chunk_elems(void);
+int ftc_adamw_sf_step(int n_chunks, const void* chunks, const void* const* ys, const void* const* grads,
+                      const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, float beta1, float beta2,
+                      float bias_correction2, float eps, float weight_decay, float lr, float ckp1, void* stream);
+
 /* ---- single ops (unit-test / building-block entry points) ---- */
 /* dense conv (k in {1,3}) or linear as implicit GEMM on NHWC activations.
  * x: [B,H,W,Cin] (dtype), w_oihw: fp32 [Cout,Cin,k,k] (packed on the fly into `wpack`),
@@ -134,6 +143,9 @@ int ftc_op_dwconv3x3(const void* x, void* out, int dtype, int batch, int h, int 
 /* hid: fp32 scratch [batch, s]; `sum` is zeroed (re-armed) on return */
 int ftc_op_se_fc(float* sum, float* scale_out, float* hid, int batch, int c, int s, float inv_hw, const float* w1,
                  const float* b1, const float* w2t, const float* b2, void* stream);
+/* debug: device buffer of 4096 u64 receiving clock64 stamps of CTA 0 of every following tcgen05 conv launch
+ * ([0,1024) MMA full-wait start, [1024,2048) end, [2048,3072) producer empty-wait start, [3072,4096) end); NULL = off */
+int ftc_debug_set_trace(void* dev_u64_4096);
 int ftc_op_upsample2x(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream);
 
 #ifdef __cplusplus

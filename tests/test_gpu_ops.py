@@ -34,6 +34,9 @@ CONV_CASES = [
     (1, 12, 12, 640, 1280, 1, 1, 1, False),   # N=1280 -> 5 x 256
     (1, 48, 48, 192, 16, 3, 1, 0, False),     # tiny N
     (3, 10, 10, 8, 24, 3, 1, 2, False),       # K=72 -> padded k-block, GELU
+    (4, 96, 96, 128, 192, 3, 1, 2, True),     # M=36864, K=1152: 256-row tile path (two accumulators per B stage)
+    (3, 111, 100, 128, 96, 3, 1, 1, False),   # M=33300: ragged 256-row tiles
+    (2, 130, 128, 768, 320, 1, 1, 0, True),   # 1x1, K=768, N=320 -> 2 x 160, 256-row tiles
 ]
 
 
