@@ -172,6 +172,37 @@ def golden_transformer():
     print("transformer goldens written")
 
 
+OPT_SHAPES = [(257,), (64, 33), (8, 4, 3, 3), (10000,)]
+OPT_CFG = dict(lr=2.5e-3, weight_decay=1e-2, warmup_steps=3)
+
+
+def optimizer_inputs(step):
+    g = torch.Generator().manual_seed(4242 + step)
+    return [torch.randn(s, generator=g) * (0.5 + step) for s in OPT_SHAPES]
+
+
+def golden_optimizer():
+    """models/adamw_schedulefree.py::AdamWScheduleFree: 5 steps (3 warm-up), weight decay, then optimizer.eval()."""
+    from models.adamw_schedulefree import AdamWScheduleFree
+    params = [torch.nn.Parameter(p.clone()) for p in optimizer_inputs(-1)]
+    opt = AdamWScheduleFree(params, **OPT_CFG)
+    opt.train()
+    out = {}
+    for step in range(5):
+        for p, g in zip(params, optimizer_inputs(step)):
+            p.grad = g.clone()
+        opt.step()
+        for i, p in enumerate(params):
+            out[f"s{step}_y{i}"] = p.detach().numpy().copy()
+            out[f"s{step}_z{i}"] = opt.state[p]["z"].numpy().copy()
+            out[f"s{step}_v{i}"] = opt.state[p]["exp_avg_sq"].numpy().copy()
+    opt.eval()
+    for i, p in enumerate(params):
+        out[f"eval_x{i}"] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, "optimizer_seed0.npz"), **out)
+    print("optimizer goldens written")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
@@ -180,3 +211,5 @@ if __name__ == "__main__":
         golden_detector()
     if what in ("transformer", "all"):
         golden_transformer()
+    if what in ("optimizer", "all"):
+        golden_optimizer()
