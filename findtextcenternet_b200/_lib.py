@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libftc_b200.so")
 FTC_MAX_STAGES = 8
 FTC_MAX_HEADS = 9
 PREC_F32, PREC_BF16 = 0, 1
-GEMM_SIMT, GEMM_TCGEN05 = 0, 1
+GEMM_SIMT, GEMM_TCGEN05, GEMM_TCGEN05_IM2COL = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_SWIGLU = 0, 1, 2, 3
 DT_F32, DT_BF16 = 0, 1
 INPUT_NCHW_UNIT, INPUT_NHWC_255 = 0, 1
@@ -48,7 +48,7 @@ class TransformerConfig(C.Structure):
 
 
 # every symbol include/ftc_b200.h declares: name -> (restype, argtypes)
-_vp, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+_vp, _i, _f, _d, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_int64
 SYMBOLS = {
     "ftc_version": (_i, []),
     "ftc_last_error": (C.c_char_p, []),
@@ -75,7 +75,7 @@ SYMBOLS = {
     "ftc_transformer_predict": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, C.POINTER(_i), C.POINTER(_i), _vp, _sz, _vp]),
     "ftc_mask_predict_step": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "ftc_adamw_sf_chunk_elems": (_i, []),
-    "ftc_adamw_sf_step": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _vp]),
+    "ftc_adamw_sf_step": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _d, _d, _d, _vp]),
     "ftc_peak_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "ftc_peak_pick": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ftc_op_conv2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),

@@ -1,4 +1,5 @@
 // C-ABI plumbing (error text, launch counter, version) and the single-op entry points of include/ftc_b200.h.
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -63,6 +64,8 @@ size_t ftc_op_conv2d_wpack_bytes(int cin, int cout, int ksize) {
   int K = 0;
   std::vector<uint32_t> kt = make_ktab(cin, 0, ksize, &K);
   int npad = (cout + 15) / 16 * 16;
+  int Ktma = ksize * ksize * 64 * ((cin + 63) / 64);     // TMA paths pad the channels to whole 64-wide chunks
+  if (Ktma > K) K = Ktma;
   return align_up((size_t)npad * K * 4, 256) + align_up(kt.size() * 4, 256) + 256;
 }
 
@@ -80,15 +83,16 @@ int ftc_op_conv2d(const void* x, int dtype, int batch, int h, int w, int cin, co
   const size_t es = dtype == DT_BF16 ? 2 : 4;
   const int npad = (cout + 15) / 16 * 16;
   char* wp = (char*)wpack;
-  uint32_t* ktab_d = (uint32_t*)(wp + align_up((size_t)npad * K * 4, 256));
-  FTC_CHECK_CUDA(cudaMemsetAsync(wp, 0, (size_t)npad * K * es, s));
+  const int Kmax = std::max(K, ksize * ksize * 64 * ((cin + 63) / 64));
+  uint32_t* ktab_d = (uint32_t*)(wp + align_up((size_t)npad * Kmax * 4, 256));
+  FTC_CHECK_CUDA(cudaMemsetAsync(wp, 0, (size_t)npad * Kmax * es, s));
   FTC_CHECK_CUDA(cudaMemcpyAsync(ktab_d, kt.data(), kt.size() * 4, cudaMemcpyHostToDevice, s));
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   p.B = batch; p.H = h; p.W = w; p.stride = stride; p.pad = (ksize - 1) / 2;
   p.Ho = (h - 1) / stride + 1; p.Wo = (w - 1) / stride + 1;
   p.M = batch * p.Ho * p.Wo; p.N = cout; p.G = 1; p.K = K;
-  p.srcA = x; p.a_pix_stride = cin; p.ktab = ktab_d;
+  p.srcA = x; p.a_pix_stride = cin; p.ktab = ktab_d; p.CA = cin; p.CB = 0;
   p.a_scale = a_scale; p.a_scale_stride = cin;
   p.w = wp; p.scale = scale; p.bias_tab = bias; p.ncase = 1; p.act = act;
   p.res1 = residual; p.res1_stride = cout;
@@ -96,12 +100,14 @@ int ftc_op_conv2d(const void* x, int dtype, int batch, int h, int w, int cin, co
   p.out_ch_base[0] = 0; p.n_valid[0] = cout;
   p.dtype = dtype;
   int rc;
-  if (backend == FTC_GEMM_TCGEN05) {
+  if (backend == FTC_GEMM_TCGEN05 || backend == FTC_GEMM_TCGEN05_IM2COL) {
     FTC_REQUIRE(dtype == DT_BF16, "tcgen05 backend needs bf16");
     ConvTcPlan plan;
-    rc = conv_gemm_tc_plan(p, &plan);
+    rc = conv_gemm_tc_plan(p, &plan, backend == FTC_GEMM_TCGEN05);
     if (rc) return rc;
-    rc = pack_conv_weight_tc(wp, w_oihw, cout, cin, ksize, ksize, 0, cin, 0, K, 0, plan.BN, nullptr, s);
+    p.K = plan.NKB * KBLOCK;
+    rc = pack_conv_weight_tc(wp, w_oihw, cout, cin, ksize, ksize, 0, cin, 0, p.K, 0, plan.BN, nullptr, s,
+                             plan.tma == TMA_HALO ? 1 : 0);
     if (rc) return rc;
     p.tc = plan;
     rc = conv_gemm_tc(p, s);

@@ -39,7 +39,12 @@ struct ConvTcPlan {
   int MT;       // 128-row sub-tiles per CTA tile (1 or 2)
   int flags;    // experiment bits (env FTC_TC_FLAGS; results are garbage when >= 4): 1 try_wait suspend hint, 2 epilogue
                 // poll backoff, 4 skip B copies, 8 skip A gathers, 16 skip MMAs, 32 skip epilogue math/stores
+  int tma;      // operand-A path: TMA_NONE = cp.async im2col gather (conv_gemm_tc.cu); TMA_ROWS / TMA_HALO = tensor-tile
+                // TMA loads (conv_gemm_tma.cu).  Fixes the k-block ORDER of the packed weights (see pack_conv_weight_tc)
+  int nGA, nGB; // TMA paths: 64-channel chunks of source A / source B; K = 64 * ksize^2 * (nGA + nGB)
 };
+enum TmaMode : int { TMA_NONE = 0, TMA_ROWS = 1, TMA_HALO = 2 };
+constexpr int HALO_TW = 16;        // halo tiles are 16 pixels wide and 8 (MT=1) or 16 (MT=2) rows high
 
 struct ConvGemmParams {
   // geometry
@@ -53,6 +58,7 @@ struct ConvGemmParams {
   // sources (element type = dtype)
   const void* srcA; int a_pix_stride; int a_ch_off;
   const void* srcB; int b_pix_stride; int b_ch_off; int b_group_stride;
+  int CA, CB;           // channels taken from source A / B per tap (plan input of the TMA paths; 0 = not given)
   const uint32_t* ktab; // K / KCHUNK entries
   const float* a_scale; // optional [B, a_scale_stride] multiplier on source A channels (SE), 1x1 only
   int a_scale_stride;
@@ -78,13 +84,19 @@ struct ConvGemmParams {
 int conv_gemm_simt(const ConvGemmParams& p, cudaStream_t stream);
 // tcgen05/TMEM implementation: bf16 only, the product path.  p.tc must come from conv_gemm_tc_plan and the
 // weights must have been packed with pack_conv_weight_tc for the same plan.
-int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan);
+//   allow_tma: pick a TMA operand path when the geometry allows it (needs p.CA/p.CB, H, W, stride, pad, pixel strides);
+//   the plan may then change K (per-source channel padding to 64): callers must use plan->NKB * 64 as the packed K.
+int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan, bool allow_tma = false);
 int conv_gemm_tc(const ConvGemmParams& p, cudaStream_t stream);
+int conv_gemm_tma(const ConvGemmParams& p, cudaStream_t stream);   // called by conv_gemm_tc when p.tc.tma != TMA_NONE
 // tcgen05 weight image: per (padded row tile, k-block) one [BN rows][64 k] bf16 block in the 128B-swizzled
 // K-major shared-memory layout, so that a stage's B operand is ONE contiguous cp.async.bulk.
-//   row R = o_off + o (o_off in padded-row space: group g starts at g*NT*BN), k = k_off + (ky*kw+kx)*C + c
+//   row R = o_off + o (o_off in padded-row space: group g starts at g*NT*BN)
+//   halo_order = 0: k = k_off + (ky*kw+kx)*C + c                      (tap-major; im2col kernel and every 1x1)
+//   halo_order = 1: k = k_off + ((c/64)*9 + kx*3 + ky)*64 + c%64      (TMA_HALO: per 64-channel chunk and column
+//                   shift kx one halo tile serves the three row taps ky; k_off of source B = 9*64*nGA)
 int pack_conv_weight_tc(void* dst, const float* src, int O, int Itot, int kh, int kw, int c_off, int C, int k_off,
-                        int Kpad, int o_off, int BN, const float* cscale, cudaStream_t s);
+                        int Kpad, int o_off, int BN, const float* cscale, cudaStream_t s, int halo_order = 0);
 size_t conv_tc_weight_bytes(const ConvTcPlan& plan, int G);
 void conv_gemm_tc_set_trace(unsigned long long* dev_ptr);   // 4 x 1024 u64: MMA wait start/end, producer wait start/end
 

@@ -1,0 +1,455 @@
+// tcgen05 / TMEM implicit-GEMM convolution with TMA tensor-tile operand staging (sm_100a, bf16 -> fp32 accumulate).
+//
+// Same math, parameters and epilogue as conv_gemm_tc.cu; what changes is how operand A reaches shared memory:
+//   TMA_ROWS (1x1 conv / Linear): A is the [M, C] activation matrix; one cp.async.bulk.tensor box of (128*MT rows x 64
+//             channels) per k-block lands directly in the 128B-swizzled K-major layout tcgen05.mma reads.
+//   TMA_HALO (3x3, stride 1, pad 1, W % 16 == 0): the CTA tile is a 16-wide x 8*MT-high pixel patch of ONE image.  For
+//             each (64-channel chunk, column shift kx) ONE box of (8*MT+2 rows x 16 px x 64 ch) is loaded -- TMA's
+//             out-of-bounds zero fill IS the conv padding -- and serves the three row taps ky = 0,1,2 as three UMMA
+//             descriptors whose start address differs by 16 px * 128 B = 2 KB (a multiple of the 1 KB swizzle atom).
+//             Operand A therefore crosses L2->SM 3*(1+2/(8*MT)) times instead of the 9 times of an im2col gather.
+// Roles (14 warps, one persistent CTA per SM): warps 0-7 epilogue, warp 8 TMA producer (one lane), warp 9 MMA issuer
+// (one lane), warps 10-13 SE scalers (only when the A operand carries a per-(image, channel) squeeze-excite factor:
+// they rescale the landed tile in shared memory between the TMA completion and the MMA).  A and B (weights, one
+// cp.async.bulk of the pre-swizzled block per k-block) travel through two independent mbarrier rings, so a halo tile
+// stays resident for its three k-blocks while weight blocks stream underneath.
+#include <cuda.h>
+
+#include "tc_common.cuh"
+
+namespace ftc {
+
+namespace {
+
+constexpr int TM_BM = 128;
+constexpr int TM_EPI_WARPS = 8;
+constexpr int TM_EPI_THREADS = TM_EPI_WARPS * 32;
+constexpr int TM_TMA_WARP = 8, TM_MMA_WARP = 9, TM_SCALE_WARP0 = 10, TM_SCALE_WARPS = 4;
+constexpr int TM_THREADS = (TM_EPI_WARPS + 2 + TM_SCALE_WARPS) * 32;   // 448
+constexpr int TM_STAGED_FLOATS = 10 * 256;     // per-tile scale[BN] + bias[ncase<=9][BN]
+constexpr int TM_MAX_SLOTS = 8;
+constexpr int TM_NBARS = 5 * TM_MAX_SLOTS + 4;
+constexpr uint32_t TM_SUB_BYTES = TM_BM * 128;  // one 128-row sub-tile of A = 16 KB
+
+struct TmaLaunch {
+  int nA, nB;             // ring depths (A slots, B slots)
+  uint32_t a_slot_bytes;  // bytes of one A slot
+  int NKG, nsub;          // k-groups per tile; k-blocks per k-group (1 rows, 3 halo)
+  int tiles_x, tiles_y;   // halo: 16 x (8*MT) tiles per image
+  int nbuf;               // TMEM accumulator sets (2: epilogue of tile i overlaps main loop of tile i+1)
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+struct TmaTile { int m0, b, y0, x0, g, nt; };
+template <int MT, bool HALO>
+__device__ __forceinline__ TmaTile decode_tma_tile(int tile, int NT, int G, const TmaLaunch& L) {
+  const int per_m = NT * G;
+  const int mt = tile / per_m;
+  const int rest = tile - mt * per_m;
+  TmaTile t;
+  t.g = rest / NT;
+  t.nt = rest - t.g * NT;
+  t.m0 = mt * (MT * TM_BM);
+  t.b = 0; t.y0 = 0; t.x0 = 0;
+  if (HALO) {
+    const int per_img = L.tiles_x * L.tiles_y;
+    t.b = mt / per_img;
+    const int r = mt - t.b * per_img;
+    const int ty = r / L.tiles_x;
+    t.y0 = ty * (8 * MT);
+    t.x0 = (r - ty * L.tiles_x) * HALO_TW;
+  }
+  return t;
+}
+
+template <bool SE, int MT, bool HALO>
+__global__ void __launch_bounds__(TM_THREADS, 1)
+conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ CUtensorMap tmA,
+                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmaLaunch L, const int num_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024 B alignment
+  uint8_t* smem = smem_raw + (sbase - raw);
+  const int BN = p.tc.BN, NT = p.tc.NT, G = p.G;
+  const uint32_t b_bytes = (uint32_t)BN * 128u;
+  const uint32_t a_ring = sbase;
+  const uint32_t b_ring = sbase + (uint32_t)L.nA * L.a_slot_bytes;
+  const uint32_t ring_bytes = (uint32_t)L.nA * L.a_slot_bytes + (uint32_t)L.nB * b_bytes;
+  const uint32_t bar0 = sbase + ring_bytes;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (TM_MAX_SLOTS + s); };
+  auto a_raw = [&](int s) { return bar0 + 8u * (2 * TM_MAX_SLOTS + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (3 * TM_MAX_SLOTS + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (4 * TM_MAX_SLOTS + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (5 * TM_MAX_SLOTS + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (5 * TM_MAX_SLOTS + 2 + a); };
+  uint8_t* after_bars = smem + ring_bytes + 8 * TM_NBARS;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(after_bars);
+  float* staged = reinterpret_cast<float*>(after_bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == TM_TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == TM_MMA_WARP) {
+    if (lane == 0) {
+      for (int s = 0; s < L.nA; ++s) {
+        mbar_init(a_full(s), SE ? TM_SCALE_WARPS : 1);
+        mbar_init(a_empty(s), 1);
+        mbar_init(a_raw(s), 1);
+      }
+      for (int s = 0; s < L.nB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TM_EPI_WARPS); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const int hw = p.Ho * p.Wo;
+  const int NKG = L.NKG, nsub = L.nsub;
+
+  if (warp == TM_TMA_WARP) {
+    // ------------------------------------------------------------------ TMA producer (A tensor tiles + B bulk copies)
+    if (lane == 0) {
+      const bf16* wgt = reinterpret_cast<const bf16*>(p.w);
+      const int nGA = p.tc.nGA;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
+        const bf16* wtile = wgt + (size_t)(tc.g * NT + tc.nt) * p.tc.NKB * ((size_t)BN * 64);
+        int kb = 0;
+        for (int kg = 0; kg < NKG; ++kg) {
+          int chunk = kg, dx = 0;
+          bool srcb = false;
+          if (HALO) {
+            const int q = kg / 3;
+            dx = kg - 3 * q;
+            srcb = q >= nGA;
+            chunk = srcb ? q - nGA : q;
+          }
+          mbar_wait(a_empty(as), aph ^ 1u);
+          const uint32_t bar = SE ? a_raw(as) : a_full(as);
+          mbar_arrive_expect_tx(bar, L.a_slot_bytes);
+          const CUtensorMap* tm = srcb ? &tmB : &tmA;
+          const int c = (srcb ? p.b_ch_off + tc.g * p.b_group_stride : p.a_ch_off) + chunk * 64;
+          if (HALO) tma_load_4d(a_ring + (uint32_t)as * L.a_slot_bytes, tm, c, tc.x0 + dx - 1, tc.y0 - 1, tc.b, bar);
+          else tma_load_4d(a_ring + (uint32_t)as * L.a_slot_bytes, tm, c, tc.m0, 0, 0, bar);
+          as = (as + 1 == L.nA) ? 0 : as + 1;
+          aph ^= (as == 0) ? 1u : 0u;
+          for (int sub = 0; sub < nsub; ++sub, ++kb) {
+            mbar_wait(b_empty(bs), bph ^ 1u);
+            mbar_arrive_expect_tx(b_full(bs), b_bytes);
+            bulk_copy_g2s(b_ring + (uint32_t)bs * b_bytes, wtile + (size_t)kb * BN * 64, b_bytes, b_full(bs));
+            bs = (bs + 1 == L.nB) ? 0 : bs + 1;
+            bph ^= (bs == 0) ? 1u : 0u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == TM_MMA_WARP) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM_BM >> 4) << 24);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      uint32_t titer = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+        const uint32_t buf = L.nbuf == 2 ? (titer & 1u) : 0u;
+        const uint32_t use = L.nbuf == 2 ? (titer >> 1) : titer;
+        mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)(MT * BN);
+        uint32_t accum = 0;
+        for (int kg = 0; kg < NKG; ++kg) {
+          mbar_wait(a_full(as), aph);
+          const uint32_t a_addr = a_ring + (uint32_t)as * L.a_slot_bytes;
+          for (int sub = 0; sub < nsub; ++sub) {
+            mbar_wait(b_full(bs), bph);
+            tc_fence_after();
+            const uint64_t bdesc = umma_desc_sw128(b_ring + (uint32_t)bs * b_bytes);
+            const uint32_t a_sub = a_addr + (HALO ? (uint32_t)sub * (HALO_TW * 128u) : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row: +2 in 16-byte units
+#pragma unroll
+              for (int h = 0; h < MT; ++h)
+                umma_f16(d_tmem + (uint32_t)h * (uint32_t)BN, umma_desc_sw128(a_sub + (uint32_t)h * TM_SUB_BYTES) + (uint64_t)(2 * k),
+                         bdesc + (uint64_t)(2 * k), idesc, (k == 0 && h < MT) ? accum : 1u);
+              accum = 1u;
+            }
+            umma_commit(b_empty(bs));
+            bs = (bs + 1 == L.nB) ? 0 : bs + 1;
+            bph ^= (bs == 0) ? 1u : 0u;
+          }
+          umma_commit(a_empty(as));
+          as = (as + 1 == L.nA) ? 0 : as + 1;
+          aph ^= (as == 0) ? 1u : 0u;
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+    __syncwarp();
+  } else if (warp >= TM_SCALE_WARP0) {
+    // ------------------------------------------------------------------ SE scalers (rows mode only)
+    if (SE) {
+      const int t = threadIdx.x - TM_SCALE_WARP0 * 32;   // 0..127
+      const int j = t & 7;                               // 16-byte chunk (8 channels) of the 128-byte row
+      const int rb = t >> 3;                             // rows rb + 16*i
+      const uint32_t row_off = (uint32_t)(rb >> 3) * 1024u + (uint32_t)(rb & 7) * 128u + (uint32_t)((j ^ (rb & 7)) << 4);
+      constexpr int ROWS = 8 * MT;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
+        int img[ROWS];
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+          int m = tc.m0 + rb + 16 * i;
+          m = m < p.M ? m : p.M - 1;
+          img[i] = m / hw;
+        }
+        for (int kg = 0; kg < NKG; ++kg) {
+          mbar_wait(a_raw(as), aph);
+          const int c = kg * 64 + j * 8;
+          if (c < p.CA) {
+            const uint32_t a_dst = a_ring + (uint32_t)as * L.a_slot_bytes + row_off;
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i) {
+              const uint32_t addr = a_dst + (uint32_t)i * 2048u;
+              uint4 u;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+              const float4* sp = reinterpret_cast<const float4*>(p.a_scale + (int64_t)img[i] * p.a_scale_stride + c);
+              const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+              float2 f;
+              f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * s0.x, f.y * s0.y);
+              f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * s0.z, f.y * s0.w);
+              f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * s1.x, f.y * s1.y);
+              f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * s1.z, f.y * s1.w);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full(as));
+          as = (as + 1 == L.nA) ? 0 : as + 1;
+          aph ^= (as == 0) ? 1u : 0u;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps: 4 lane quarters x 2 halves)
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int half = warp >> 2;                // MT == 1: even / odd 16-column chunks; MT == 2: which 128-row sub-tile
+    const int etid = threadIdx.x;              // 0..255
+    const int row = (MT == 2 ? half * TM_BM : 0) + q * 32 + lane;
+    const bf16* res1 = reinterpret_cast<const bf16*>(p.res1);
+    const bf16* res2 = reinterpret_cast<const bf16*>(p.res2);
+    float* sscale = staged;                    // [BN]
+    float* sbias = staged + 256;               // [ncase][BN]
+    uint32_t titer = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+      const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
+      const uint32_t buf = L.nbuf == 2 ? (titer & 1u) : 0u;
+      const uint32_t use = L.nbuf == 2 ? (titer >> 1) : titer;
+      // stage this tile's per-column scale / bias (the previous tile's readers are past this barrier)
+      asm volatile("bar.sync 1, %0;" ::"n"(TM_EPI_THREADS) : "memory");
+      {
+        const int ncol0 = tc.nt * BN;
+        for (int c = etid; c < BN; c += TM_EPI_THREADS) {
+          const int n = ncol0 + c;
+          sscale[c] = (p.scale && n < p.N) ? __ldg(p.scale + (int64_t)tc.g * p.N + n) : 1.f;
+        }
+        for (int c = etid; c < p.ncase * BN; c += TM_EPI_THREADS) {
+          const int cs_ = c / BN, cc = c - cs_ * BN;
+          const int n = ncol0 + cc;
+          sbias[c] = (p.bias_tab && n < p.N) ? __ldg(p.bias_tab + ((int64_t)cs_ * G + tc.g) * p.N + n) : 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TM_EPI_THREADS) : "memory");
+      int m, b = 0, oy = 0, ox = 0;
+      bool mvalid = true;
+      if (HALO) {
+        b = tc.b; oy = tc.y0 + (row >> 4); ox = tc.x0 + (row & 15);
+        m = (b * p.Ho + oy) * p.Wo + ox;
+      } else {
+        m = tc.m0 + row;
+        mvalid = m < p.M;
+        if (mvalid) { b = m / hw; const int r = m - b * hw; oy = r / p.Wo; ox = r - oy * p.Wo; }
+      }
+      int cs = 0;
+      if (p.ncase == 9) cs = (oy == 0 ? 0 : (oy == p.Ho - 1 ? 2 : 1)) * 3 + (ox == 0 ? 0 : (ox == p.Wo - 1 ? 2 : 1));
+      const int64_t r1row = p.res1_row_mod ? (m % p.res1_row_mod) : m;
+      const int nvalid = min(p.N, p.n_valid[tc.g]);
+      const int chb = p.out_ch_base[tc.g];
+      if (lane == 0) mbar_wait(tfull_bar(buf), use & 1u);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * (uint32_t)MT + (MT == 2 ? (uint32_t)half : 0u)) * (uint32_t)BN;
+      for (int c0 = (MT == 1 ? half * 16 : 0); c0 < BN; c0 += (MT == 1 ? 32 : 16)) {
+        const int n0 = tc.nt * BN + c0;
+        if (n0 >= p.N) break;                       // warp-uniform
+        uint32_t raw16[16];
+        __syncwarp();                               // tcgen05.ld is warp-collective: reconverge first
+        tmem_ld16(t_addr + (uint32_t)c0, raw16);
+        tmem_ld_wait();
+        if (mvalid)
+          epilogue_store(p, raw16, tc.g, n0, m, b, oy, ox, hw, r1row, nvalid, chb, sscale + c0, sbias + cs * BN + c0, res1, res2);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TM_MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_tma_sms = 0;
+
+int encode_map(CUtensorMap* tm, const void* base, uint64_t channels, uint64_t pix_stride, uint64_t d1, uint64_t d2, uint64_t d3,
+               uint32_t box1, uint32_t box2) {
+  FTC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA source must be 16-byte aligned");
+  FTC_REQUIRE(pix_stride % 8 == 0, "TMA pixel stride must be a multiple of 16 bytes");
+  cuuint64_t dims[4] = {channels, d1, d2, d3};
+  cuuint64_t strides[3] = {pix_stride * 2, pix_stride * 2 * d1, pix_stride * 2 * d1 * d2};
+  cuuint32_t box[4] = {64, box1, box2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return -2;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
+  static int env_mt = -1;
+  if (env_mt < 0) { const char* e = getenv("FTC_TMA_MT"); env_mt = e ? atoi(e) : 0; }
+  ConvGemmParams p = p_in;
+  FTC_REQUIRE(p.dtype == DT_BF16, "tcgen05 path is bf16 only");
+  FTC_REQUIRE(p.G >= 1 && p.G <= MAX_GROUPS, "groups out of range");
+  FTC_REQUIRE(p.tc.BN >= 16 && p.tc.BN <= 256 && p.tc.BN % 16 == 0, "bad tc plan");
+  FTC_REQUIRE(p.act != ACT_SWIGLU || p.out_layout == OUT_NHWC, "swiglu needs NHWC out");
+  FTC_REQUIRE(p.stride == 1, "TMA paths are stride 1");
+  const bool halo = p.tc.tma == TMA_HALO;
+  const bool se = p.a_scale != nullptr;
+  FTC_REQUIRE(!(se && halo), "SE operand scaling is a 1x1 feature");
+  FTC_REQUIRE(p.tc.nGA + p.tc.nGB > 0, "TMA plan without sources");
+  FTC_REQUIRE(p.tc.nGA == 0 || p.srcA, "source A missing");
+  FTC_REQUIRE(p.tc.nGB == 0 || p.srcB, "source B missing");
+  if (g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FTC_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    FTC_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    g_encode = (EncodeTiledFn)fn;
+    int dev = 0;
+    FTC_CHECK_CUDA(cudaGetDevice(&dev));
+    FTC_CHECK_CUDA(cudaDeviceGetAttribute(&g_tma_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  TmaLaunch L;
+  memset(&L, 0, sizeof(L));
+  int MT = (p.tc.NKB >= 12 && p.M >= 2 * TM_BM * 128) ? 2 : 1;
+  if (env_mt == 1 || env_mt == 2) MT = env_mt;
+  const uint32_t b_bytes = (uint32_t)p.tc.BN * 128u;
+  int m_tiles;
+  if (halo) {
+    FTC_REQUIRE(p.pad == 1 && p.W % HALO_TW == 0 && p.H % (8 * MT) == 0 && p.Ho == p.H && p.Wo == p.W, "halo geometry");
+    FTC_REQUIRE(p.tc.NKB == 9 * (p.tc.nGA + p.tc.nGB), "halo plan does not match K");
+    L.tiles_x = p.W / HALO_TW; L.tiles_y = p.H / (8 * MT);
+    L.NKG = 3 * (p.tc.nGA + p.tc.nGB); L.nsub = 3;
+    L.a_slot_bytes = (uint32_t)(8 * MT + 2) * HALO_TW * 128u;
+    m_tiles = p.B * L.tiles_x * L.tiles_y;
+  } else {
+    FTC_REQUIRE(p.pad == 0 && p.tc.nGB == 0 && p.tc.NKB == p.tc.nGA, "rows plan does not match K");
+    L.tiles_x = L.tiles_y = 1;
+    L.NKG = p.tc.nGA; L.nsub = 1;
+    L.a_slot_bytes = (uint32_t)MT * TM_SUB_BYTES;
+    m_tiles = ceil_div(p.M, TM_BM * MT);
+  }
+  L.nbuf = (2 * MT * p.tc.BN <= 512) ? 2 : 1;
+  const size_t fixed = 1024 + 8 * TM_NBARS + 16 + TM_STAGED_FLOATS * 4 + 256;
+  const size_t avail = 227 * 1024 - fixed;
+  if (halo) {
+    L.nA = (3 * (size_t)L.a_slot_bytes + 4 * (size_t)b_bytes <= avail) ? 3 : 2;
+    size_t nb = (avail - (size_t)L.nA * L.a_slot_bytes) / b_bytes;
+    L.nB = nb > TM_MAX_SLOTS ? TM_MAX_SLOTS : (int)nb;
+    FTC_REQUIRE(L.nB >= 3, "smem budget (halo)");
+  } else {
+    size_t n = avail / ((size_t)L.a_slot_bytes + b_bytes);
+    L.nA = L.nB = n > TM_MAX_SLOTS ? TM_MAX_SLOTS : (int)n;
+    FTC_REQUIRE(L.nA >= 2, "smem budget (rows)");
+  }
+  size_t smem = fixed + (size_t)L.nA * L.a_slot_bytes + (size_t)L.nB * b_bytes;
+  if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: the CTA owns all 512 TMEM columns
+  FTC_REQUIRE(smem <= 227 * 1024, "smem budget");
+
+  alignas(64) CUtensorMap tmA, tmB;
+  const bf16* a_base = reinterpret_cast<const bf16*>(p.srcA);
+  const bf16* b_base = reinterpret_cast<const bf16*>(p.srcB);
+  int rc = 0;
+  if (halo) {
+    if (p.tc.nGA) rc = encode_map(&tmA, a_base, (uint64_t)(p.a_ch_off + p.CA), p.a_pix_stride, p.W, p.H, p.B, HALO_TW, 8 * MT + 2);
+    if (rc) return rc;
+    if (p.tc.nGB) rc = encode_map(&tmB, b_base, (uint64_t)p.b_pix_stride, p.b_pix_stride, p.W, p.H, p.B, HALO_TW, 8 * MT + 2);
+    if (rc) return rc;
+    if (!p.tc.nGA) tmA = tmB;
+    if (!p.tc.nGB) tmB = tmA;
+  } else {
+    rc = encode_map(&tmA, a_base, (uint64_t)(p.a_ch_off + p.CA), p.a_pix_stride, (uint64_t)p.M, 1, 1, TM_BM * MT, 1);
+    if (rc) return rc;
+    tmB = tmA;
+  }
+  const int num_tiles = m_tiles * p.tc.NT * p.G;
+  const int grid = num_tiles < g_tma_sms ? num_tiles : g_tma_sms;
+  p.tc.MT = MT;
+#define TMA_LAUNCH(SE_, MT_, HALO_)                                                                                   \
+  do {                                                                                                                \
+    static bool attr_done = false;                                                                                    \
+    if (!attr_done) {                                                                                                 \
+      FTC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tma_kernel<SE_, MT_, HALO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          227 * 1024));                                                               \
+      attr_done = true;                                                                                               \
+    }                                                                                                                 \
+    conv_gemm_tma_kernel<SE_, MT_, HALO_><<<grid, TM_THREADS, smem, stream>>>(p, tmA, tmB, L, num_tiles);             \
+  } while (0)
+  if (halo) { if (MT == 2) TMA_LAUNCH(false, 2, true); else TMA_LAUNCH(false, 1, true); }
+  else if (se) { if (MT == 2) TMA_LAUNCH(true, 2, false); else TMA_LAUNCH(true, 1, false); }
+  else { if (MT == 2) TMA_LAUNCH(false, 2, false); else TMA_LAUNCH(false, 1, false); }
+#undef TMA_LAUNCH
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+}  // namespace ftc

@@ -84,12 +84,15 @@ struct ftc_detector {
   size_t walloc(size_t bytes) { size_t o = weight_bytes; weight_bytes = align_up(weight_bytes + bytes, 256); return o; }
   void need(int buf, size_t elems) { if (buf >= 0 && buf < BUF_COUNT && elems > buf_elems[buf]) buf_elems[buf] = elems; }
 
-  bool use_tc = false;
+  bool use_tc = false, allow_tma = false;
   // weight bytes of a GEMM op in the layout of the selected backend (fills g.tc for tcgen05)
   size_t gemm_weight_bytes(GemmOp& g) {
     if (use_tc) {
-      ConvGemmParams q; memset(&q, 0, sizeof(q)); q.N = g.N; q.K = g.K;
-      conv_gemm_tc_plan(q, &g.tc);
+      ConvGemmParams q; memset(&q, 0, sizeof(q)); q.N = g.N; q.K = g.K; q.G = g.G;
+      q.H = g.H; q.W = g.W; q.stride = g.stride; q.pad = (g.ksize - 1) / 2;
+      q.CA = g.CA; q.CB = g.CB; q.a_pix_stride = g.a_pix_stride; q.b_pix_stride = g.b_pix_stride; q.b_group_stride = g.b_group_stride;
+      conv_gemm_tc_plan(q, &g.tc, allow_tma);
+      g.K = g.tc.NKB * KBLOCK;           // the TMA paths pad the channels of each source to whole 64-wide chunks
       return conv_tc_weight_bytes(g.tc, g.G);
     }
     return (size_t)g.G * g.N * g.K * esize;
@@ -97,9 +100,12 @@ struct ftc_detector {
   // pack channels [c_off, c_off+C) of an OIHW fp32 weight as group `grp`'s rows, k columns from k_off
   static int pack_w(const GemmOp& gc, int dt, bool tc, char* base, const float* w, int O, int Itot, int ks, int c_off, int C,
                     int k_off, int grp, const float* cscale, cudaStream_t s) {
-    if (tc)
+    if (tc) {
+      const bool halo = gc.tc.tma == TMA_HALO;
+      if (halo && k_off) k_off = 9 * KBLOCK * gc.tc.nGA;     // second source starts after source A's padded chunks
       return pack_conv_weight_tc(base + gc.w_off, w, O, Itot, ks, ks, c_off, C, k_off, gc.K, grp * gc.tc.NT * gc.tc.BN, gc.tc.BN,
-                                 cscale, s);
+                                 cscale, s, halo ? 1 : 0);
+    }
     return pack_conv_weight(base + gc.w_off, dt, w, O, Itot, ks, ks, c_off, C, k_off, gc.K, grp * gc.N, cscale, s);
   }
 
@@ -145,7 +151,8 @@ int ftc_detector::build() {
   const ftc_detector_config& c = cfg;
   dtype = c.precision == FTC_PREC_BF16 ? DT_BF16 : DT_F32;
   esize = dtype == DT_BF16 ? 2 : 4;
-  use_tc = c.gemm_backend == FTC_GEMM_TCGEN05;
+  use_tc = c.gemm_backend == FTC_GEMM_TCGEN05 || c.gemm_backend == FTC_GEMM_TCGEN05_IM2COL;
+  allow_tma = c.gemm_backend == FTC_GEMM_TCGEN05;
   FTC_REQUIRE(!use_tc || dtype == DT_BF16, "the tcgen05 backend needs FTC_PREC_BF16");
   FTC_REQUIRE(c.height % 32 == 0 && c.width % 32 == 0, "input size must be a multiple of 32");
   FTC_REQUIRE(c.n_stages >= 5 && c.n_stages <= FTC_MAX_STAGES, "stage count");
@@ -453,6 +460,7 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
         p.M = B * g.Ho * g.Wo; p.N = g.N; p.G = g.G; p.K = g.K;
         p.srcA = bp(g.bufA); p.a_pix_stride = g.a_pix_stride; p.a_ch_off = 0;
         p.srcB = bp(g.bufB); p.b_pix_stride = g.b_pix_stride; p.b_ch_off = g.b_ch_off; p.b_group_stride = g.b_group_stride;
+        p.CA = g.CA; p.CB = g.CB;
         p.ktab = (const uint32_t*)(P + g.ktab_off);
         p.a_scale = g.se ? se_scale : nullptr; p.a_scale_stride = g.CA;
         p.w = P + g.w_off;

@@ -13,8 +13,8 @@ constexpr int SF_CHUNK = 8192;
 __global__ void __launch_bounds__(256) adamw_sf_step_kernel(const SfChunk* __restrict__ chunks, float* const* __restrict__ ys,
                                                             float* const* __restrict__ grads, float* const* __restrict__ vs,
                                                             float* const* __restrict__ zs, const int64_t* __restrict__ numels,
-                                                            float beta1, float beta2, float bias_correction2, float eps,
-                                                            float decay, float lr, float ckp1) {
+                                                            float beta2, float one_m_beta2, float bias_correction2, float eps,
+                                                            float decay, float lr, float ckp1, float y_alpha) {
   const SfChunk c = chunks[blockIdx.x];
   float* y = ys[c.tensor] + c.offset;
   float* g = grads[c.tensor] + c.offset;
@@ -22,8 +22,6 @@ __global__ void __launch_bounds__(256) adamw_sf_step_kernel(const SfChunk* __res
   float* z = zs[c.tensor] + c.offset;
   const int64_t left = numels[c.tensor] - c.offset;
   const int n = left < SF_CHUNK ? (int)left : SF_CHUNK;
-  const float one_m_beta2 = 1.0f - beta2;
-  const float y_alpha = lr * (beta1 * (1.0f - ckp1) - 1.0f);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float gi = g[i];
     float vi = v[i] * beta2;                       // _foreach_mul_(exp_avg_sq, beta2)
@@ -53,13 +51,16 @@ extern "C" {
 int ftc_adamw_sf_chunk_elems(void) { return SF_CHUNK; }
 
 int ftc_adamw_sf_step(int n_chunks, const void* chunks, const void* const* ys, const void* const* grads,
-                      const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, float beta1, float beta2,
-                      float bias_correction2, float eps, float weight_decay, float lr, float ckp1, void* stream) {
+                      const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, double beta1, double beta2,
+                      double bias_correction2, double eps, double weight_decay, double lr, double ckp1, void* stream) {
   FTC_REQUIRE(n_chunks >= 0 && chunks && ys && grads && exp_avg_sqs && zs && numels, "bad argument");
   if (n_chunks == 0) return 0;
   adamw_sf_step_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(
       (const SfChunk*)chunks, (float* const*)ys, (float* const*)grads, (float* const*)exp_avg_sqs, (float* const*)zs, numels,
-      beta1, beta2, bias_correction2, eps, weight_decay, lr, ckp1);
+      // scalars arrive as the Python doubles of the reference and are rounded to fp32 once, as torch does for
+      // value= / alpha= / weight= arguments of the foreach ops (1 - beta2 in fp32 would differ by 1.3e-5 relative)
+      (float)beta2, (float)(1.0 - beta2), (float)bias_correction2, (float)eps, (float)weight_decay, (float)lr, (float)ckp1,
+      (float)(lr * (beta1 * (1.0 - ckp1) - 1.0)));
   FTC_POST_LAUNCH();
   return 0;
 }

@@ -203,7 +203,7 @@ int ftc_transformer::build() {
   const ftc_transformer_config& c = cfg;
   dtype = c.precision == FTC_PREC_BF16 ? DT_BF16 : DT_F32;
   esize = dtype == DT_BF16 ? 2 : 4;
-  use_tc = c.gemm_backend == FTC_GEMM_TCGEN05;
+  use_tc = c.gemm_backend == FTC_GEMM_TCGEN05 || c.gemm_backend == FTC_GEMM_TCGEN05_IM2COL;
   FTC_REQUIRE(!use_tc || dtype == DT_BF16, "the tcgen05 backend needs FTC_PREC_BF16");
   d = c.embed_dim; heads = c.head_num;
   FTC_REQUIRE(d % 64 == 0 && d <= 1024, "embed_dim must be a multiple of 64, <= 1024");

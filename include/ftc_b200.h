@@ -21,7 +21,10 @@ extern "C" {
 #define FTC_MAX_HEADS 9
 
 enum { FTC_PREC_F32 = 0, FTC_PREC_BF16 = 1 };
-enum { FTC_GEMM_SIMT = 0, FTC_GEMM_TCGEN05 = 1 };
+/* SIMT: CUDA-core fp32-accumulate parity path.  TCGEN05: tensor-core path, operand A staged by TMA tensor tiles where the
+ * geometry allows (1x1; 3x3 stride 1 with W % 16 == 0), else by the cp.async im2col gather.  TCGEN05_IM2COL: tensor-core
+ * path with the im2col gather everywhere (A/B comparison of the two operand pipelines). */
+enum { FTC_GEMM_SIMT = 0, FTC_GEMM_TCGEN05 = 1, FTC_GEMM_TCGEN05_IM2COL = 2 };
 /* layout/range of the `images` argument of ftc_detector_forward:
  *   NCHW_UNIT: [B,3,H,W] fp32 in [0,1]   (models/detector.py:217 CenterNetDetection.forward input)
  *   NHWC_255 : [B,H,W,3] fp32 in 0..255  (process_ocr_base.py:49-51 call_detector input; /255 as process_ocr_torch.py:44) */
@@ -127,8 +130,8 @@ int ftc_mask_predict_step(const float* logits, int ld, int head_ld, const int64_
  * Updates exp_avg_sq, grad (normalised in place, as the reference does), y (= the parameter) and z. */
 int ftc_adamw_sf_chunk_elems(void);
 int ftc_adamw_sf_step(int n_chunks, const void* chunks, const void* const* ys, const void* const* grads,
-                      const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, float beta1, float beta2,
-                      float bias_correction2, float eps, float weight_decay, float lr, float ckp1, void* stream);
+                      const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, double beta1, double beta2,
+                      double bias_correction2, double eps, double weight_decay, double lr, double ckp1, void* stream);
 
 /* ---- single ops (unit-test / building-block entry points) ---- */
 /* dense conv (k in {1,3}) or linear as implicit GEMM on NHWC activations.

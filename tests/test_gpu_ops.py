@@ -37,11 +37,15 @@ CONV_CASES = [
     (4, 96, 96, 128, 192, 3, 1, 2, True),     # M=36864, K=1152: 256-row tile path (two accumulators per B stage)
     (3, 111, 100, 128, 96, 3, 1, 1, False),   # M=33300: ragged 256-row tiles
     (2, 130, 128, 768, 320, 1, 1, 0, True),   # 1x1, K=768, N=320 -> 2 x 160, 256-row tiles
+    (2, 32, 48, 96, 192, 3, 1, 2, True),      # TMA halo tiles (W % 16 == 0), Cin=96 -> second chunk half out of bounds
+    (3, 16, 16, 64, 100, 3, 1, 0, False),     # halo, one tile per image, N=100 -> 112
+    (2, 128, 128, 128, 96, 3, 1, 1, True),    # halo, M=32768: 16x16 tiles (two accumulators), double-buffered TMEM
+    (1, 33, 7, 96, 40, 1, 1, 1, False),       # TMA rows: ragged M=231, Cin=96
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("mode", ["simt_f32", "simt_bf16", "tc_bf16"])
+@pytest.mark.parametrize("mode", ["simt_f32", "simt_bf16", "tc_bf16", "tc_im2col_bf16"])
 def test_conv2d(case, mode):
     _lib, ops = _ops()
     b, h, w, cin, cout, k, stride, act, use_res = case
@@ -61,7 +65,7 @@ def test_conv2d(case, mode):
     if resq is not None:
         ref = ref + resq.permute(0, 3, 1, 2)
     ref = ref.permute(0, 2, 3, 1)
-    backend = _lib.GEMM_TCGEN05 if mode == "tc_bf16" else _lib.GEMM_SIMT
+    backend = {"tc_bf16": _lib.GEMM_TCGEN05, "tc_im2col_bf16": _lib.GEMM_TCGEN05_IM2COL}.get(mode, _lib.GEMM_SIMT)
     out = ops.conv2d(x.to(dt).cuda(), wt, stride, scale, bias, act, None if res is None else res.to(dt).cuda(),
                      None, backend)
     torch.cuda.synchronize()
@@ -70,13 +74,14 @@ def test_conv2d(case, mode):
     assert rel_l2(out.float().cpu().numpy(), ref.numpy()) < tol
 
 
-@pytest.mark.parametrize("mode", ["simt_f32", "tc_bf16"])
-def test_conv2d_se_scaled_operand(mode):
+@pytest.mark.parametrize("shape", [(3, 12, 12, 384, 96), (8, 64, 64, 768, 128)])   # 2nd: M=32768, 12 k-blocks -> 256-row tiles
+@pytest.mark.parametrize("mode", ["simt_f32", "tc_bf16", "tc_im2col_bf16"])
+def test_conv2d_se_scaled_operand(mode, shape):
     """1x1 project conv with the SE excitation applied to the A operand (torchvision efficientnet.py MBConv:
     block[2] scale then block[3] conv)."""
     _lib, ops = _ops()
     g = torch.Generator().manual_seed(3)
-    b, h, w, cin, cout = 3, 12, 12, 384, 96
+    b, h, w, cin, cout = shape
     dt = torch.float32 if mode == "simt_f32" else torch.bfloat16
     x = torch.randn(b, h, w, cin, generator=g)
     wt = torch.randn(cout, cin, 1, 1, generator=g) / np.sqrt(cin)
@@ -88,7 +93,7 @@ def test_conv2d_se_scaled_operand(mode):
     else:
         wq = wt
     ref = F.conv2d(xs.permute(0, 3, 1, 2), wq).permute(0, 2, 3, 1)
-    backend = _lib.GEMM_TCGEN05 if mode == "tc_bf16" else _lib.GEMM_SIMT
+    backend = {"tc_bf16": _lib.GEMM_TCGEN05, "tc_im2col_bf16": _lib.GEMM_TCGEN05_IM2COL}.get(mode, _lib.GEMM_SIMT)
     out = ops.conv2d(x.to(dt).cuda(), wt, 1, None, None, 0, None, a_scale.cuda(), backend)
     assert rel_l2(out.float().cpu().numpy(), ref.numpy()) < (1e-4 if mode == "simt_f32" else 1e-2)
 
