@@ -28,7 +28,8 @@ constexpr int TM_TMA_WARP = 8, TM_MMA_WARP = 9, TM_SCALE_WARP0 = 10, TM_SCALE_WA
 constexpr int TM_THREADS = (TM_EPI_WARPS + 2 + TM_SCALE_WARPS) * 32;   // 448
 constexpr int TM_STAGED_FLOATS = 10 * 256;     // per-tile scale[BN] + bias[ncase<=9][BN]
 constexpr int TM_MAX_SLOTS = 8;
-constexpr int TM_NBARS = 5 * TM_MAX_SLOTS + 4;
+constexpr int TM_NBARS = 5 * TM_MAX_SLOTS + 4 + 2 * TM_EPI_WARPS;   // + per-warp residual ring (2 deep)
+constexpr uint32_t TM_BOX_BYTES = 32 * 64;   // one staged epilogue box: 32 rows x 32 bf16 channels
 constexpr uint32_t TM_SUB_BYTES = TM_BM * 128;  // one 128-row sub-tile of A = 16 KB
 
 struct TmaLaunch {
@@ -37,6 +38,9 @@ struct TmaLaunch {
   int NKG, nsub;          // k-groups per tile; k-blocks per k-group (1 rows, 3 halo)
   int tiles_x, tiles_y;   // halo: 16 x (8*MT) tiles per image
   int nbuf;               // TMEM accumulator sets (2: epilogue of tile i overlaps main loop of tile i+1)
+  int se_tab;             // SE: channels per image of the shared-memory bf16 scale table (0 = per-row global loads)
+  int staged;             // epilogue: 1 = bf16 NHWC output staged in shared memory and written with TMA tensor stores
+  int res_tma;            // staged epilogue: 1 = the residual tile is prefetched with TMA loads (per-warp 2-deep ring)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -47,6 +51,28 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
 }
 
 struct TmaTile { int m0, b, y0, x0, g, nt; };
@@ -74,7 +100,8 @@ __device__ __forceinline__ TmaTile decode_tma_tile(int tile, int NT, int G, cons
 template <bool SE, int MT, bool HALO>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_constant__ CUtensorMap tmA,
-                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmaLaunch L, const int num_tiles) {
+                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                     const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ TmaLaunch L, const int num_tiles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024 B alignment
@@ -84,7 +111,10 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   const uint32_t a_ring = sbase;
   const uint32_t b_ring = sbase + (uint32_t)L.nA * L.a_slot_bytes;
   const uint32_t ring_bytes = (uint32_t)L.nA * L.a_slot_bytes + (uint32_t)L.nB * b_bytes;
-  const uint32_t bar0 = sbase + ring_bytes;
+  // staged epilogue: per epilogue warp two output boxes (+ two residual boxes), 2 KB each, right behind the rings
+  const uint32_t box_base = sbase + ring_bytes;
+  const uint32_t box_bytes = L.staged ? (uint32_t)TM_EPI_WARPS * (L.res_tma ? 4u : 2u) * TM_BOX_BYTES : 0u;
+  const uint32_t bar0 = box_base + box_bytes;
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (TM_MAX_SLOTS + s); };
   auto a_raw = [&](int s) { return bar0 + 8u * (2 * TM_MAX_SLOTS + s); };
@@ -92,7 +122,8 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   auto b_empty = [&](int s) { return bar0 + 8u * (4 * TM_MAX_SLOTS + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (5 * TM_MAX_SLOTS + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (5 * TM_MAX_SLOTS + 2 + a); };
-  uint8_t* after_bars = smem + ring_bytes + 8 * TM_NBARS;
+  auto res_bar = [&](int w, int i) { return bar0 + 8u * (5 * TM_MAX_SLOTS + 4 + 2 * w + i); };
+  uint8_t* after_bars = smem + ring_bytes + box_bytes + 8 * TM_NBARS;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(after_bars);
   float* staged = reinterpret_cast<float*>(after_bars + 16);
 
@@ -100,6 +131,8 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   if (warp == TM_TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (L.staged) tma_prefetch_desc(&tmOut);
+    if (L.res_tma) tma_prefetch_desc(&tmRes);
   }
   if (warp == TM_MMA_WARP) {
     if (lane == 0) {
@@ -110,6 +143,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       }
       for (int s = 0; s < L.nB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
       for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TM_EPI_WARPS); }
+      for (int w = 0; w < TM_EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -216,6 +250,57 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       constexpr int ROWS = 8 * MT;
       int as = 0;
       uint32_t aph = 0;
+      if (L.se_tab) {
+        // fast path (a tile spans at most two images): the scale rows of both images are staged once per tile in shared
+        // memory as bf16 and applied with packed bf16 multiplies -- 7 instructions per 16-byte chunk instead of ~45
+        // (two dependent global loads, 8 unpack / FMUL / pack).  The scale is rounded to bf16 (the activation it
+        // multiplies already is); the product is rounded once, as before.
+        __nv_bfloat16* sc_tab = reinterpret_cast<__nv_bfloat16*>(staged + TM_STAGED_FLOATS);
+        const int CAp = L.se_tab;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
+          const int b0 = tc.m0 / hw;
+          const int nb = (b0 + 1) * hw - tc.m0;          // tile rows [0, nb) are image b0, the rest image b0 + 1
+          const int b1 = min(b0 + 1, p.B - 1);
+          asm volatile("bar.sync 2, %0;" ::"n"(TM_SCALE_WARPS * 32) : "memory");   // previous tile's table reads are done
+          for (int idx = t * 4; idx < 2 * CAp; idx += TM_SCALE_WARPS * 32 * 4) {
+            const int second = idx >= CAp ? 1 : 0;
+            const int c = idx - second * CAp;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < p.CA) v = __ldg(reinterpret_cast<const float4*>(p.a_scale + (int64_t)(second ? b1 : b0) * p.a_scale_stride + c));
+            __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(sc_tab + idx);
+            dst[0] = __floats2bfloat162_rn(v.x, v.y);
+            dst[1] = __floats2bfloat162_rn(v.z, v.w);
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(TM_SCALE_WARPS * 32) : "memory");
+          for (int kg = 0; kg < NKG; ++kg) {
+            const int c = kg * 64 + j * 8;
+            const uint4 s0 = *reinterpret_cast<const uint4*>(sc_tab + c);
+            const uint4 s1 = *reinterpret_cast<const uint4*>(sc_tab + CAp + c);
+            mbar_wait(a_raw(as), aph);
+            if (!(p.tc.flags & 64)) {
+              const uint32_t a_dst = a_ring + (uint32_t)as * L.a_slot_bytes + row_off;
+#pragma unroll
+              for (int i = 0; i < ROWS; ++i) {
+                const uint32_t addr = a_dst + (uint32_t)i * 2048u;
+                const uint4 sc = (rb + 16 * i < nb) ? s0 : s1;
+                uint4 u;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+                const __nv_bfloat162* sh = reinterpret_cast<const __nv_bfloat162*>(&sc);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __hmul2(h[e], sh[e]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full(as));
+            as = (as + 1 == L.nA) ? 0 : as + 1;
+            aph ^= (as == 0) ? 1u : 0u;
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
         int img[ROWS];
@@ -228,7 +313,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         for (int kg = 0; kg < NKG; ++kg) {
           mbar_wait(a_raw(as), aph);
           const int c = kg * 64 + j * 8;
-          if (c < p.CA) {
+          if (c < p.CA && !(p.tc.flags & 64)) {
             const uint32_t a_dst = a_ring + (uint32_t)as * L.a_slot_bytes + row_off;
 #pragma unroll
             for (int i = 0; i < ROWS; ++i) {
@@ -265,6 +350,132 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
     float* sscale = staged;                    // [BN]
     float* sbias = staged + 256;               // [ncase][BN]
     uint32_t titer = 0;
+    if (L.staged) {
+      // ---- staged epilogue: every warp owns 32 accumulator rows and walks 32-column chunks.  A chunk is converted to
+      // bf16 in a 2 KB shared-memory box (64-byte rows, SWIZZLE_64B so that the 32 row-owning lanes spread over all
+      // banks) and leaves through ONE TMA tensor store, which writes whole 64-byte row segments (the direct path wrote
+      // 32 scattered 16-byte pieces per store instruction and was LSU-bound).  The residual tile comes in the same way
+      // through a two-deep per-warp TMA ring that is issued before the accumulator is waited for.
+      const uint32_t my_boxes = box_base + (uint32_t)warp * (L.res_tma ? 4u : 2u) * TM_BOX_BYTES;
+      const uint32_t out_box0 = my_boxes, res_box0 = my_boxes + 2u * TM_BOX_BYTES;
+      const uint32_t sw = (uint32_t)((lane >> 1) & 3);                 // SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3
+      const uint32_t row_b = (uint32_t)lane * 64u;
+      const int cstart = MT == 1 ? half * 32 : 0, cstep = MT == 1 ? 64 : 32;
+      const int nchunk = BN > cstart ? (BN - cstart + cstep - 1) / cstep : 0;
+      uint32_t n_out = 0, n_res_issued = 0, n_res_used = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+        const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
+        const uint32_t buf = L.nbuf == 2 ? (titer & 1u) : 0u;
+        const uint32_t use = L.nbuf == 2 ? (titer >> 1) : titer;
+        // box coordinates of this warp's 32 rows
+        int k1, k2, k3;
+        if (HALO) { k1 = tc.x0; k2 = tc.y0 + (MT == 2 ? half * 8 : 0) + q * 2; k3 = tc.b; }
+        else { k1 = tc.m0 + (MT == 2 ? half * TM_BM : 0) + q * 32; k2 = 0; k3 = 0; }
+        const int ch_out = p.out_ch_base[tc.g] + tc.nt * BN;
+        const int ch_res = tc.g * p.N + tc.nt * BN;
+        auto issue_res = [&](int i) {
+          const uint32_t slot = n_res_issued & 1u;
+          mbar_arrive_expect_tx(res_bar(warp, slot), TM_BOX_BYTES);
+          tma_load_4d(res_box0 + slot * TM_BOX_BYTES, &tmRes, ch_res + cstart + i * cstep, k1, k2, k3, res_bar(warp, slot));
+          ++n_res_issued;
+        };
+        if (L.res_tma && lane == 0) {
+          if (nchunk > 0) issue_res(0);
+          if (nchunk > 1) issue_res(1);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TM_EPI_THREADS) : "memory");
+        {
+          const int ncol0 = tc.nt * BN;
+          for (int c = etid; c < BN; c += TM_EPI_THREADS) {
+            const int n = ncol0 + c;
+            sscale[c] = (p.scale && n < p.N) ? __ldg(p.scale + (int64_t)tc.g * p.N + n) : 1.f;
+          }
+          for (int c = etid; c < p.ncase * BN; c += TM_EPI_THREADS) {
+            const int cs_ = c / BN, cc = c - cs_ * BN;
+            const int n = ncol0 + cc;
+            sbias[c] = (p.bias_tab && n < p.N) ? __ldg(p.bias_tab + ((int64_t)cs_ * G + tc.g) * p.N + n) : 0.f;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TM_EPI_THREADS) : "memory");
+        int cs = 0;
+        if (p.ncase == 9) {
+          const int oy = tc.y0 + (row >> 4), ox = tc.x0 + (row & 15);     // ncase 9 only occurs on halo (3x3) tiles
+          cs = (oy == 0 ? 0 : (oy == p.Ho - 1 ? 2 : 1)) * 3 + (ox == 0 ? 0 : (ox == p.Wo - 1 ? 2 : 1));
+        }
+        if (lane == 0) mbar_wait(tfull_bar(buf), use & 1u);
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * (uint32_t)MT + (MT == 2 ? (uint32_t)half : 0u)) * (uint32_t)BN;
+        for (int i = 0; i < nchunk; ++i) {
+          const int c0 = cstart + i * cstep;
+          if (tc.nt * BN + c0 >= p.N) break;          // warp-uniform
+          uint32_t raw[32];
+          __syncwarp();
+          tmem_ld32(t_addr + (uint32_t)c0, raw);
+          tmem_ld_wait();
+          float v[32];
+          const float* ss = sscale + c0;
+          const float* sb = sbias + cs * BN + c0;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(ss + e);
+            const float4 bi = *reinterpret_cast<const float4*>(sb + e);
+            v[e + 0] = fmaf(__uint_as_float(raw[e + 0]), sc.x, bi.x);
+            v[e + 1] = fmaf(__uint_as_float(raw[e + 1]), sc.y, bi.y);
+            v[e + 2] = fmaf(__uint_as_float(raw[e + 2]), sc.z, bi.z);
+            v[e + 3] = fmaf(__uint_as_float(raw[e + 3]), sc.w, bi.w);
+          }
+          if (p.act == ACT_SILU) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = silu_tanh(v[e]);
+          } else if (p.act == ACT_GELU) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = gelu_tanh3(v[e]);
+          }
+          if (L.res_tma) {
+            const uint32_t slot = n_res_used & 1u;
+            mbar_wait(res_bar(warp, slot), (n_res_used >> 1) & 1u);
+            const uint32_t rb_ = res_box0 + slot * TM_BOX_BYTES + row_b;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(rb_ + (((uint32_t)j ^ sw) << 4)) : "memory");
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[8 * j + 2 * e] += f.x; v[8 * j + 2 * e + 1] += f.y; }
+            }
+            ++n_res_used;
+            __syncwarp();                               // every lane has read the box before it is refilled
+            if (lane == 0 && i + 2 < nchunk) issue_res(i + 2);
+          }
+          if (!(p.tc.flags & 32)) {
+            const uint32_t ob = out_box0 + (n_out & 1u) * TM_BOX_BYTES;
+            if (lane == 0) bulk_wait_read<1>();         // the store that last read this box (two chunks ago) is done
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ob + row_b + (((uint32_t)j ^ sw) << 4)), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmOut, ob, ch_out + c0, k1, k2, k3);
+              bulk_commit();
+            }
+            ++n_out;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));
+      }
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
       const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
       const uint32_t buf = L.nbuf == 2 ? (titer & 1u) : 0u;
@@ -306,6 +517,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       for (int c0 = (MT == 1 ? half * 16 : 0); c0 < BN; c0 += (MT == 1 ? 32 : 16)) {
         const int n0 = tc.nt * BN + c0;
         if (n0 >= p.N) break;                       // warp-uniform
+        if (p.tc.flags & 256) continue;             // ablation: no TMEM reads, no epilogue math
         uint32_t raw16[16];
         __syncwarp();                               // tcgen05.ld is warp-collective: reconverge first
         tmem_ld16(t_addr + (uint32_t)c0, raw16);
@@ -334,16 +546,18 @@ EncodeTiledFn g_encode = nullptr;
 int g_tma_sms = 0;
 
 int encode_map(CUtensorMap* tm, const void* base, uint64_t channels, uint64_t pix_stride, uint64_t d1, uint64_t d2, uint64_t d3,
-               uint32_t box1, uint32_t box2) {
-  FTC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA source must be 16-byte aligned");
+               uint32_t box1, uint32_t box2, uint32_t box0 = 64) {
+  FTC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA tensor must be 16-byte aligned");
   FTC_REQUIRE(pix_stride % 8 == 0, "TMA pixel stride must be a multiple of 16 bytes");
   cuuint64_t dims[4] = {channels, d1, d2, d3};
   cuuint64_t strides[3] = {pix_stride * 2, pix_stride * 2 * d1, pix_stride * 2 * d1 * d2};
-  cuuint32_t box[4] = {64, box1, box2, 1};
+  cuuint32_t box[4] = {box0, box1, box2, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  // operand tiles: 64 channels = 128-byte rows, SWIZZLE_128B (the UMMA K-major layout); epilogue boxes: 32 channels =
+  // 64-byte rows, SWIZZLE_64B
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, box0 == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
     return -2;
@@ -354,9 +568,13 @@ int encode_map(CUtensorMap* tm, const void* base, uint64_t channels, uint64_t pi
 }  // namespace
 
 int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
-  static int env_mt = -1;
-  if (env_mt < 0) { const char* e = getenv("FTC_TMA_MT"); env_mt = e ? atoi(e) : 0; }
+  static int env_mt = -1, env_flags = 0;
+  if (env_mt < 0) {
+    const char* e = getenv("FTC_TMA_MT"); env_mt = e ? atoi(e) : 0;
+    e = getenv("FTC_TMA_FLAGS"); env_flags = e ? atoi(e) : 0;   // ablations (results are garbage): 32 no stores, 64 no SE
+  }                                                             // scaling, 128 no residual loads, 256 no epilogue at all
   ConvGemmParams p = p_in;
+  p.tc.flags = env_flags;
   FTC_REQUIRE(p.dtype == DT_BF16, "tcgen05 path is bf16 only");
   FTC_REQUIRE(p.G >= 1 && p.G <= MAX_GROUPS, "groups out of range");
   FTC_REQUIRE(p.tc.BN >= 16 && p.tc.BN <= 256 && p.tc.BN % 16 == 0, "bad tc plan");
@@ -380,7 +598,11 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
   }
   TmaLaunch L;
   memset(&L, 0, sizeof(L));
-  int MT = (p.tc.NKB >= 12 && p.M >= 2 * TM_BM * 128) ? 2 : 1;
+  // 256-row tiles halve the weight traffic per MAC.  They keep two accumulator sets (epilogue overlapped with the next
+  // main loop) only for BN <= 128; wider tiles take them when the main loop is long enough to amortise the exposed
+  // epilogue.  Either way there must be about a wave of tiles left.
+  const long tiles2 = (long)ceil_div(p.M, 2 * TM_BM) * p.tc.NT * p.G;
+  int MT = ((p.tc.BN <= 128 || p.tc.NKB >= 12) && tiles2 >= 120) ? 2 : 1;
   if (env_mt == 1 || env_mt == 2) MT = env_mt;
   const uint32_t b_bytes = (uint32_t)p.tc.BN * 128u;
   int m_tiles;
@@ -399,7 +621,23 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
     m_tiles = ceil_div(p.M, TM_BM * MT);
   }
   L.nbuf = (2 * MT * p.tc.BN <= 512) ? 2 : 1;
-  const size_t fixed = 1024 + 8 * TM_NBARS + 16 + TM_STAGED_FLOATS * 4 + 256;
+  // SE scale table: two images x (channels padded to 64) bf16, when a tile cannot span more than two images
+  if (se && p.Ho * p.Wo >= MT * TM_BM && p.tc.nGA * 64 <= 4096 && p.a_scale_stride % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(p.a_scale) & 15) == 0)
+    L.se_tab = p.tc.nGA * 64;
+  // staged (TMA-store) epilogue: plain bf16 NHWC outputs whose n-tiles are whole 32-channel boxes
+  {
+    bool ok = p.out_layout == OUT_NHWC && p.act != ACT_SWIGLU && p.tc.BN % 32 == 0 && p.tc.BN * p.tc.NT == p.N &&
+              (p.ncase == 1 || halo) && p.res2 == nullptr && p.out_stride % 8 == 0 &&
+              (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && !(env_flags & 1024);
+    for (int g = 0; g < p.G && ok; ++g) ok = p.n_valid[g] == p.N;
+    if (ok && p.res1)
+      ok = p.res1_row_mod == 0 && p.res1_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.res1) & 15) == 0;
+    L.staged = ok ? 1 : 0;
+    L.res_tma = (ok && p.res1) ? 1 : 0;
+  }
+  const size_t box_bytes = L.staged ? (size_t)TM_EPI_WARPS * (L.res_tma ? 4 : 2) * TM_BOX_BYTES : 0;
+  const size_t fixed = 1024 + 8 * TM_NBARS + 16 + TM_STAGED_FLOATS * 4 + 256 + (size_t)L.se_tab * 4 + box_bytes;
   const size_t avail = 227 * 1024 - fixed;
   if (halo) {
     L.nA = (3 * (size_t)L.a_slot_bytes + 4 * (size_t)b_bytes <= avail) ? 3 : 2;
@@ -431,6 +669,17 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
     if (rc) return rc;
     tmB = tmA;
   }
+  alignas(64) CUtensorMap tmOut = tmA, tmRes = tmA;
+  if (L.staged) {
+    if (halo) rc = encode_map(&tmOut, p.out, (uint64_t)p.out_stride, p.out_stride, p.Wo, p.Ho, p.B, HALO_TW, 2, 32);
+    else rc = encode_map(&tmOut, p.out, (uint64_t)p.out_stride, p.out_stride, (uint64_t)p.M, 1, 1, 32, 1, 32);
+    if (rc) return rc;
+    if (L.res_tma) {
+      if (halo) rc = encode_map(&tmRes, p.res1, (uint64_t)p.res1_stride, p.res1_stride, p.Wo, p.Ho, p.B, HALO_TW, 2, 32);
+      else rc = encode_map(&tmRes, p.res1, (uint64_t)p.res1_stride, p.res1_stride, (uint64_t)p.M, 1, 1, 32, 1, 32);
+      if (rc) return rc;
+    }
+  }
   const int num_tiles = m_tiles * p.tc.NT * p.G;
   const int grid = num_tiles < g_tma_sms ? num_tiles : g_tma_sms;
   p.tc.MT = MT;
@@ -442,7 +691,7 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
                                           227 * 1024));                                                               \
       attr_done = true;                                                                                               \
     }                                                                                                                 \
-    conv_gemm_tma_kernel<SE_, MT_, HALO_><<<grid, TM_THREADS, smem, stream>>>(p, tmA, tmB, L, num_tiles);             \
+    conv_gemm_tma_kernel<SE_, MT_, HALO_><<<grid, TM_THREADS, smem, stream>>>(p, tmA, tmB, tmOut, tmRes, L, num_tiles); \
   } while (0)
   if (halo) { if (MT == 2) TMA_LAUNCH(false, 2, true); else TMA_LAUNCH(false, 1, true); }
   else if (se) { if (MT == 2) TMA_LAUNCH(true, 2, false); else TMA_LAUNCH(true, 1, false); }

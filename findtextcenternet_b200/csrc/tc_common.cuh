@@ -111,6 +111,17 @@ __device__ __forceinline__ float silu_tanh(float x) {
   return fmaf(h, t, h);
 }
 
+// erf-GELU with ONE SFU op per element: x*Phi(x), Phi(x) ~ 0.5 + 0.5*tanh(x*(a + b*x^2 + c*x^4)) (minimax fit over
+// [-8, 8]: max abs error 2.5e-5 plus tanh.approx's 2^-11, well below the bf16 rounding of the stored output).  erff()
+// costs ~25 instructions per element and made the (non-overlapped) 256x192 head epilogues 30% of those kernels.
+__device__ __forceinline__ float gelu_tanh3(float x) {
+  const float x2 = fminf(x * x, 64.f);
+  const float u = x * fmaf(x2, fmaf(x2, -3.51516792e-04f, 3.70056461e-02f), 7.97507884e-01f);
+  float h = 0.5f * x, t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return fmaf(h, t, h);
+}
+
 // one row x 16 accumulator columns: scale / bias / activation / residuals / store.
 // sscale / sbias point at this tile's staged per-column vectors in shared memory (column c0 of the tile).
 __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const uint32_t (&raw16)[16], int g, int n0, int m,
@@ -133,9 +144,10 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
     for (int i = 0; i < 16; ++i) v[i] = silu_tanh(v[i]);
   } else if (p.act == ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 16; ++i) v[i] = gelu_tanh3(v[i]);
   }
-  if (res1) {
+  const bool dbg_nostore = (p.tc.flags & 32) && v[0] != 12345.678f;   // ablation: keep the math, drop the stores
+  if (res1 && !(p.tc.flags & 128)) {
     const bf16* rp = res1 + r1row * p.res1_stride + (int64_t)g * p.N + n0;
     if (full16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
       float a[8], c[8];
@@ -147,7 +159,7 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
       for (int i = 0; i < 16; ++i) if (n0 + i < p.N) v[i] += __bfloat162float(rp[i]);
     }
   }
-  if (res2) {
+  if (res2 && !(p.tc.flags & 128)) {
     const bf16* rp = res2 + (int64_t)m * p.res2_stride + (int64_t)g * p.N + n0;
     if (full16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
       float a[8], c[8];
@@ -159,6 +171,7 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
       for (int i = 0; i < 16; ++i) if (n0 + i < p.N) v[i] += __bfloat162float(rp[i]);
     }
   }
+  if (dbg_nostore) return;
   if (p.act == ACT_SWIGLU) {
     // interleaved (x1, xg) column pairs -> x1 * silu(xg), 8 outputs per 16 columns
     float o[8];
