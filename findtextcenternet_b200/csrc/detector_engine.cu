@@ -58,6 +58,9 @@ struct Op {
   int n_heads = 0, head0 = 0, od[8] = {0}, pix_stride = 0, out_ch = 0;
   int bufIn = BUF_NONE, bufOut = BUF_NONE, C = 0, H = 0, W = 0, stride = 1, S = 0;
   size_t w_off = 0, scale_off = 0, bias_off = 0, w2_off = 0, b1_off = 0, b2_off = 0;
+  bool fused_se = false;             // DW: squeeze + fc1 folded into the depthwise kernel (w1 at se_w1_off); SE: fc2 only
+  int parity = 0;                    // which of the two hid_pre accumulators this block uses
+  size_t se_w1_off = 0;
 };
 
 }  // namespace
@@ -182,6 +185,7 @@ int ftc_detector::build() {
 
   // ---- backbone stages ----
   int cur = BUF_X0;
+  int n_fused_se = 0;
   int tap_bufs[3] = {BUF_T1, BUF_T2, BUF_T3};
   int tap_C[4] = {0, 0, 0, 0}, tap_H[4] = {0, 0, 0, 0};
   int ntap = 0;
@@ -207,8 +211,12 @@ int ftc_detector::build() {
       } else {
         int sq = cin / 4 > 1 ? cin / 4 : 1;
         add_conv_bn(p + ".0", cur, BUF_E, cin, exp, H, W, 1, 1, ACT_SILU, BUF_NONE, false, EPS_BB);
+        const bool fused_se = dwconv3x3_se_supported(H, W, exp, stride) && !getenv("FTC_NO_DW_STRIP");
+        const size_t se_w1_off = walloc((size_t)sq * exp * 4);
+        const int parity = fused_se ? (n_fused_se++ & 1) : 0;
         {
           Op op; op.type = Op::DW; op.bufIn = BUF_E; op.bufOut = BUF_D; op.C = exp; op.H = H; op.W = W; op.stride = stride;
+          op.fused_se = fused_se; op.parity = parity; op.se_w1_off = se_w1_off; op.S = sq;
           op.w_off = walloc(9 * exp * 4); op.scale_off = walloc(exp * 4); op.bias_off = walloc(exp * 4);
           need(BUF_D, (size_t)Ho * Wo * exp);
           if ((size_t)exp > se_c_max) se_c_max = exp;
@@ -226,7 +234,8 @@ int ftc_detector::build() {
         }
         {
           Op op; op.type = Op::SE; op.C = exp; op.S = sq; op.H = Ho; op.W = Wo;
-          op.w_off = walloc((size_t)sq * exp * 4); op.b1_off = walloc(sq * 4);
+          op.fused_se = fused_se; op.parity = parity;
+          op.w_off = se_w1_off; op.b1_off = walloc(sq * 4);
           op.w2_off = walloc((size_t)sq * exp * 4); op.b2_off = walloc(exp * 4);
           const Op oc = op; const std::string q = p + ".2";
           pack_tasks.push_back([=](const Lookup& L, char* base, cudaStream_t s) -> int {
@@ -423,7 +432,9 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
   float* se_sum = (float*)(ws + off); off += align_up(d->se_c_max * B * 4, 256);
   float* se_scale = (float*)(ws + off); off += align_up(d->se_c_max * B * 4, 256);
   float* se_hid = (float*)(ws + off); off += align_up((size_t)256 * B * 4, 256);
+  float* se_hid2 = (float*)(ws + off); off += align_up((size_t)2 * 256 * B * 4, 256);   // two fc1 accumulators (block parity)
   FTC_CHECK_CUDA(cudaMemsetAsync(se_sum, 0, d->se_c_max * B * 4, s));
+  FTC_CHECK_CUDA(cudaMemsetAsync(se_hid2, 0, (size_t)2 * 256 * B * 4, s));
   auto bp = [&](int id) -> void* {
     if (id == BUF_NONE) return nullptr;
     if (id == BUF_EXT_HEAT9) return heat9;
@@ -442,12 +453,21 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
                        (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), s);
         break;
       case Op::DW:
-        rc = dwconv3x3(bp(op.bufIn), bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, op.stride, (const float*)(P + op.w_off),
-                       (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), se_sum, s);
+        if (op.fused_se)
+          rc = dwconv3x3_se(bp(op.bufIn), bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, (const float*)(P + op.w_off),
+                            (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), (const float*)(P + op.se_w1_off),
+                            op.S, se_hid2 + (size_t)op.parity * 256 * B, s);
+        else
+          rc = dwconv3x3(bp(op.bufIn), bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, op.stride, (const float*)(P + op.w_off),
+                         (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), se_sum, s);
         break;
       case Op::SE:
-        rc = se_fc(se_sum, se_scale, se_hid, B, op.C, op.S, 1.0f / (float)(op.H * op.W), (const float*)(P + op.w_off),
-                   (const float*)(P + op.b1_off), (const float*)(P + op.w2_off), (const float*)(P + op.b2_off), s);
+        if (op.fused_se)
+          rc = se_fc2_hid(se_hid2 + (size_t)op.parity * 256 * B, se_hid2 + (size_t)(op.parity ^ 1) * 256 * B, 256, se_scale, B, op.C,
+                          op.S, (const float*)(P + op.b1_off), (const float*)(P + op.w2_off), (const float*)(P + op.b2_off), s);
+        else
+          rc = se_fc(se_sum, se_scale, se_hid, B, op.C, op.S, 1.0f / (float)(op.H * op.W), (const float*)(P + op.w_off),
+                     (const float*)(P + op.b1_off), (const float*)(P + op.w2_off), (const float*)(P + op.b2_off), s);
         break;
       case Op::TOPS:
         rc = head_top_conv(bp(op.bufIn), d->dtype, op.pix_stride, op.head0, op.n_heads, op.od, (const float*)(P + op.w_off),
@@ -509,7 +529,7 @@ size_t ftc_detector_workspace_bytes(const ftc_detector* d, int batch) {
   if (!d) return 0;
   size_t off = 0;
   for (int i = 0; i < BUF_COUNT; ++i) off += align_up(d->buf_elems[i] * batch * d->esize, 256);
-  off += 2 * align_up(d->se_c_max * batch * 4, 256) + align_up((size_t)256 * batch * 4, 256);
+  off += 2 * align_up(d->se_c_max * batch * 4, 256) + align_up((size_t)256 * batch * 4, 256) + align_up((size_t)2 * 256 * batch * 4, 256);
   return off + 256;
 }
 

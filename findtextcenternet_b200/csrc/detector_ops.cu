@@ -240,6 +240,169 @@ int dwconv3x3(const void* in, void* out, int dtype, int B, int H, int W, int C, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stride-1 depthwise 3x3 + BN + SiLU with the SE squeeze AND the first SE layer folded in (the MBConv blocks after the
+// first of each stage: 78 of the 80 depthwise convs of EfficientNetV2-XL).
+// One CTA = one image x 32 channels, walking the image in strips of 8 output rows through a two-deep cp.async ring, so
+// loads of strip s+1 overlap the FMAs of strip s inside the CTA.  Each thread owns one output column and 4 channels.
+// Because a CTA sees ALL pixels of its channels, the squeeze needs no atomics: mean[b, c] is final inside the CTA, and by
+// linearity the CTA adds its 32-channel share of fc1 -- sum_c w1[s, c] * mean[b, c] -- straight into hid_pre[b, s]
+// (S atomics per CTA).  What is left of SE is one tiny kernel (se_fc2_hid) instead of two, and the se_sum round trip.
+template <typename T, int TH>
+__global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C,
+                                                              const float* __restrict__ w, const float* __restrict__ scale,
+                                                              const float* __restrict__ bias, const float* __restrict__ w1,
+                                                              int S, float inv_hw, float* __restrict__ hid_pre) {
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  constexpr int CB = 32;                                // channels per CTA
+  constexpr int PPP = (int)(CB * sizeof(T) / 16);       // 16-byte pieces per pixel
+  constexpr int EPP = (int)(16 / sizeof(T));
+  const int IW = W + 2;
+  const int strip_elems = (TH + 2) * IW * CB;
+  T* ring = reinterpret_cast<T*>(dw_smem);              // [2][(TH+2)][IW][CB]
+  float* red = reinterpret_cast<float*>(dw_smem + (size_t)2 * strip_elems * sizeof(T));   // [W][CB] then mean[CB]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int b = blockIdx.y, cb = blockIdx.x * CB;
+  const T* img = in + (int64_t)b * H * W * C + cb;
+  T* oimg = out + (int64_t)b * H * W * C + cb;
+  const int nstrips = H / TH;
+  auto prefetch = [&](int s) {
+    T* dst = ring + (size_t)(s & 1) * strip_elems;
+    const int iy0 = s * TH - 1;
+    for (int i = tid; i < (TH + 2) * IW * PPP; i += nthr) {
+      const int pix = i / PPP, piece = i - pix * PPP;
+      const int py = pix / IW, px = pix - py * IW;
+      const int iy = iy0 + py, ix = px - 1;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      const T* src = ok ? img + ((int64_t)iy * W + ix) * C + piece * EPP : img;
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + (size_t)pix * CB + piece * EPP);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(0);
+  const int quad = tid & 7, col = tid >> 3;            // 4 channels, one output column
+  const int c0 = cb + quad * 4;
+  float wk[9][4], sc[4], bi[4], ssum[4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) load4(w + t * C + c0, wk[t]);
+  load4(scale + c0, sc); load4(bias + c0, bi);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ssum[j] = 0.f;
+  for (int s = 0; s < nstrips; ++s) {
+    if (s + 1 < nstrips) {
+      prefetch(s + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const T* tcol = ring + (size_t)(s & 1) * strip_elems + (size_t)col * CB + quad * 4;
+    float r[3][3][4];
+    auto load_row = [&](int slot, int trow) {
+      const T* rp = tcol + (size_t)trow * IW * CB;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) load4(rp + kx * CB, r[slot][kx]);
+    };
+    load_row(0, 0); load_row(1, 1);
+    T* op = oimg + ((int64_t)(s * TH) * W + col) * C + quad * 4;
+#pragma unroll
+    for (int py = 0; py < TH; ++py) {
+      load_row((py + 2) % 3, py + 2);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(r[(py + ky) % 3][kx][j], wk[ky * 3 + kx][j], acc[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float t = fmaf(acc[j], sc[j], bi[j]);
+        acc[j] = sizeof(T) == 4 ? silu_precise(t) : silu_tanh_f(t);
+        ssum[j] += acc[j];
+      }
+      store4(op + (int64_t)py * W * C, acc);
+    }
+    __syncthreads();                                    // the strip buffer is refilled two iterations later
+  }
+  // ---- squeeze (complete for these 32 channels) + this CTA's share of fc1 ----
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[col * CB + quad * 4 + j] = ssum[j];
+  __syncthreads();
+  float* mean = red + (size_t)W * CB;
+  if (tid < CB) {
+    float t = 0.f;
+    for (int q = 0; q < W; ++q) t += red[q * CB + tid];
+    mean[tid] = t * inv_hw;
+  }
+  __syncthreads();
+  for (int sidx = tid; sidx < S; sidx += nthr) {
+    const float* wr = w1 + (int64_t)sidx * C + cb;
+    float t = 0.f;
+#pragma unroll
+    for (int c = 0; c < CB; c += 4) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + c));
+      t = fmaf(wv.x, mean[c], t); t = fmaf(wv.y, mean[c + 1], t); t = fmaf(wv.z, mean[c + 2], t); t = fmaf(wv.w, mean[c + 3], t);
+    }
+    atomicAdd(&hid_pre[(int64_t)b * S + sidx], t);
+  }
+}
+
+bool dwconv3x3_se_supported(int H, int W, int C, int stride) {
+  return stride == 1 && W * 8 <= 384 && W >= 4 && H % 8 == 0 && C % 32 == 0;
+}
+
+int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int C, const float* w, const float* scale,
+                 const float* bias, const float* w1, int S, float* hid_pre, cudaStream_t s) {
+  FTC_REQUIRE(dwconv3x3_se_supported(H, W, C, 1), "dwconv3x3_se: unsupported geometry");
+  FTC_REQUIRE(B <= 65535, "batch");
+  constexpr int TH = 8;
+  const size_t es = dtype == DT_F32 ? 4 : 2;
+  const size_t smem = 2 * (size_t)(TH + 2) * (W + 2) * 32 * es + (size_t)(W + 1) * 32 * sizeof(float);
+  FTC_REQUIRE(smem <= 200 * 1024, "dwconv3x3_se: strip does not fit shared memory");
+  dim3 grid(C / 32, B);
+  const int threads = W * 8;
+  const float inv_hw = 1.0f / (float)(H * W);
+#define DWS_LAUNCH(TT)                                                                                                 \
+  do {                                                                                                                 \
+    static bool done = false;                                                                                          \
+    if (!done) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<TT, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; } \
+    dwconv3x3_strip_kernel<TT, TH><<<grid, threads, smem, s>>>((const TT*)in, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre); \
+  } while (0)
+  if (dtype == DT_F32) DWS_LAUNCH(float); else DWS_LAUNCH(bf16);
+#undef DWS_LAUNCH
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+// second half of SE for the folded path: scale[b,c] = sigmoid(b2[c] + w2t[:,c] . silu(hid_pre[b,:] + b1)); clears the
+// OTHER layer-parity accumulator (nobody reads it any more) so that the next block finds zeros
+__global__ void __launch_bounds__(256) se_fc2_hid_kernel(const float* __restrict__ hid_pre, float* __restrict__ hid_clear,
+                                                         float* __restrict__ scale_out, int C, int S, int clear_n,
+                                                         const float* __restrict__ b1, const float* __restrict__ w2t,
+                                                         const float* __restrict__ b2) {
+  __shared__ float sh[256];
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < S; k += blockDim.x) sh[k] = silu_precise(hid_pre[(int64_t)b * S + k] + b1[k]);
+  if (blockIdx.x == 0)
+    for (int k = threadIdx.x; k < clear_n; k += blockDim.x) hid_clear[(int64_t)b * clear_n + k] = 0.f;
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = b2[c];
+  for (int k = 0; k < S; ++k) t = fmaf(w2t[(int64_t)k * C + c], sh[k], t);
+  scale_out[(int64_t)b * C + c] = sigmoid_precise(t);
+}
+
+int se_fc2_hid(const float* hid_pre, float* hid_clear, int clear_n, float* scale_out, int B, int C, int S, const float* b1,
+               const float* w2t, const float* b2, cudaStream_t s) {
+  FTC_REQUIRE(S <= 256 && clear_n <= 256, "SE: squeeze <= 256");
+  se_fc2_hid_kernel<<<dim3(ceil_div(C, 256), B), 256, 0, s>>>(hid_pre, hid_clear, scale_out, C, S, clear_n, b1, w2t, b2);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // SE excitation in two small grid-filling kernels (one block per image was latency-bound: 0.22 ms per layer):
 //   fc1: one warp per (image, squeeze unit)   hid[b,s] = silu(b1[s] + w1[s,:] . mean[b,:])
 //   fc2: one thread per (image, channel)      scale[b,c] = sigmoid(b2[c] + w2t[:,c] . hid[b,:]); re-arms sum[b,c] = 0
@@ -290,44 +453,51 @@ int se_fc(float* sum, float* scale_out, float* hid, int B, int C, int S, float i
 
 // ------------------------------------------------------------------------------------------------
 // bilinear x2 align_corners=True
+// One CTA per output row (b, oy): the row pair y0/y1 and its weights are CTA constants, warps stride over output pixels
+// and lanes over 16-byte channel chunks -- no integer division anywhere, every load / store is a 512-byte-per-warp run.
 template <typename T>
-__global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H,
-                                                         int W, int C, float sy, float sx) {
+__global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C,
+                                                         float sy, float sx) {
   const int Ho = 2 * H, Wo = 2 * W, CH = C / 8;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t total = (int64_t)B * Ho * Wo * CH;
-  if (idx >= total) return;
-  int ch = idx % CH;
-  int64_t pix = idx / CH;
-  int ox = pix % Wo;
-  int64_t t = pix / Wo;
-  int oy = t % Ho;
-  int b = t / Ho;
-  float fy = sy * oy, fx = sx * ox;
-  int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
-  int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-  float ly = fminf(fmaxf(fy - y0, 0.f), 1.f), lx = fminf(fmaxf(fx - x0, 0.f), 1.f);
-  float hy = 1.f - ly, hx = 1.f - lx;
-  const T* base = in + (int64_t)b * H * W * C + ch * 8;
-  float a[8], bb[8], c[8], d[8], o[8];
-  load8(base + ((int64_t)y0 * W + x0) * C, a);
-  load8(base + ((int64_t)y0 * W + x1) * C, bb);
-  load8(base + ((int64_t)y1 * W + x0) * C, c);
-  load8(base + ((int64_t)y1 * W + x1) * C, d);
+  const int b = blockIdx.y, oy = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float fy = sy * oy;
+  const int y0 = min((int)fy, H - 1), y1 = min(y0 + 1, H - 1);
+  const float ly = fminf(fmaxf(fy - y0, 0.f), 1.f), hy = 1.f - ly;
+  const T* row0 = in + ((int64_t)b * H + y0) * W * C;
+  const T* row1 = in + ((int64_t)b * H + y1) * W * C;
+  T* orow = out + ((int64_t)b * Ho + oy) * Wo * C;
+  for (int ox = warp; ox < Wo; ox += 8) {
+    const float fx = sx * ox;
+    const int x0 = min((int)fx, W - 1), x1 = min(x0 + 1, W - 1);
+    const float lx = fminf(fmaxf(fx - x0, 0.f), 1.f), hx = 1.f - lx;
+    const T* p00 = row0 + (int64_t)x0 * C;
+    const T* p01 = row0 + (int64_t)x1 * C;
+    const T* p10 = row1 + (int64_t)x0 * C;
+    const T* p11 = row1 + (int64_t)x1 * C;
+    T* po = orow + (int64_t)ox * C;
+    for (int ch = lane; ch < CH; ch += 32) {
+      float a[8], bb[8], c[8], d[8], o[8];
+      load8(p00 + ch * 8, a);
+      load8(p01 + ch * 8, bb);
+      load8(p10 + ch * 8, c);
+      load8(p11 + ch * 8, d);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = hy * (hx * a[j] + lx * bb[j]) + ly * (hx * c[j] + lx * d[j]);
-  store8(out + pix * C + ch * 8, o);
+      for (int j = 0; j < 8; ++j) o[j] = hy * (hx * a[j] + lx * bb[j]) + ly * (hx * c[j] + lx * d[j]);
+      store8(po + ch * 8, o);
+    }
+  }
 }
 
 int upsample2x(const void* in, void* out, int dtype, int B, int H, int W, int C, cudaStream_t s) {
   FTC_REQUIRE(C % 8 == 0, "upsample channels must be a multiple of 8");
-  int64_t total = (int64_t)B * 4 * H * W * (C / 8);
-  int grid = (int)((total + 255) / 256);
+  FTC_REQUIRE(B <= 65535, "upsample batch");
+  dim3 grid(2 * H, B);
   float sy = (float)(H - 1) / (float)(2 * H - 1), sx = (float)(W - 1) / (float)(2 * W - 1);
   if (dtype == DT_F32)
-    upsample2x_kernel<float><<<grid, 256, 0, s>>>((const float*)in, (float*)out, B, H, W, C, sy, sx);
+    upsample2x_kernel<float><<<grid, 256, 0, s>>>((const float*)in, (float*)out, H, W, C, sy, sx);
   else
-    upsample2x_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, (bf16*)out, B, H, W, C, sy, sx);
+    upsample2x_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, (bf16*)out, H, W, C, sy, sx);
   FTC_POST_LAUNCH();
   return 0;
 }
@@ -419,6 +589,103 @@ __global__ void __launch_bounds__(256) head_top_conv_kernel(const HeadTopParams 
   }
 }
 
+// bf16 variant on the warp-level tensor cores (mma.sync m16n8k16, fp32 accumulate).  The op is pure operand bandwidth
+// (N <= 2 per head), so the design minimises shared-memory reads per MAC: a CTA stages one head's 10x18x192 halo tile
+// once (pixel stride padded to 200 channels: conflict-free ldmatrix), each of its 6 warps owns 32 channels and ALL 8x16
+// output pixels, loads every (input row, column shift, 16-channel step) fragment once with ldmatrix.x4 and feeds it to
+// the up-to-three output rows it contributes to (ky = 0..2).  The 18 weight fragments of a warp live in registers.
+// Shared-memory reads: 2.7x the tile instead of 9x; the CUDA-core version above was FMA/LDS bound at 11 TFLOP/s.
+__global__ void __launch_bounds__(192) head_top_mma_kernel(const HeadTopParams p) {
+  extern __shared__ __align__(16) unsigned char ht_smem[];
+  constexpr int CD = 192, PS = 200, CH = CD / 8, TH = 8, TW = 16, IH = TH + 2, IW = TW + 2, NW = 6;
+  bf16* tile = reinterpret_cast<bf16*>(ht_smem);                   // [IH*IW][PS]
+  float* part = reinterpret_cast<float*>(ht_smem);                 // [NW][128][2], aliases the tile after the MMAs
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+  const int oy0 = ty * TH, ox0 = tx * TW;
+  const bf16* src = reinterpret_cast<const bf16*>(p.y) + (size_t)(p.head0 + h) * CD;
+  for (int i = tid; i < IH * IW * CH; i += NW * 32) {
+    const int pix = i / CH, ch = i - pix * CH;
+    const int py = pix / IW, px = pix - py * IW;
+    const int iy = oy0 - 1 + py, ix = ox0 - 1 + px;
+    const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+    const bf16* g = ok ? src + (((int64_t)b * p.H + iy) * p.W + ix) * p.pix_stride + ch * 8 : src;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + (size_t)pix * PS + ch * 8);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(g), "r"(ok ? 16u : 0u) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // B fragments (k16 x n8, "col" layout): lane holds k = (lane%4)*2 + {0,1} (+8), n = lane/4; columns >= od are zero
+  const int od = p.od[h];
+  uint32_t wf[9][2][2];
+  {
+    const int n = lane >> 2, kk = (lane & 3) * 2;
+    const float* wrow = p.w + (size_t)(p.row_base[h] + (n < od ? n : 0)) * (9 * CD) + warp * 32 + kk;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+        if (n < od) {
+          lo = __ldg(reinterpret_cast<const float2*>(wrow + tap * CD + ks * 16));
+          hi = __ldg(reinterpret_cast<const float2*>(wrow + tap * CD + ks * 16 + 8));
+        }
+        __nv_bfloat162 l2 = __floats2bfloat162_rn(lo.x, lo.y), h2 = __floats2bfloat162_rn(hi.x, hi.y);
+        wf[tap][ks][0] = *reinterpret_cast<uint32_t*>(&l2);
+        wf[tap][ks][1] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+  }
+  float acc[TH][4];
+#pragma unroll
+  for (int r = 0; r < TH; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ldmatrix.x4 row addresses: matrix (lane/8): pixels (lane%8) + 8*((lane/8)&1), channels + 8*((lane/8)>>1)
+  const uint32_t lane_off = (uint32_t)((((lane & 7) + 8 * ((lane >> 3) & 1)) * PS + 8 * (lane >> 4) + warp * 32) * 2);
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile) + lane_off;
+#pragma unroll
+  for (int iy = 0; iy < IH; ++iy)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        const uint32_t addr = tile_s + (uint32_t)(((iy * IW + kx) * PS + ks * 16) * 2);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr) : "memory");
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int oy = iy - ky;
+          if (oy >= 0 && oy < TH)
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(acc[oy][0]), "+f"(acc[oy][1]), "+f"(acc[oy][2]), "+f"(acc[oy][3])
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(wf[ky * 3 + kx][ks][0]), "r"(wf[ky * 3 + kx][ks][1]));
+        }
+      }
+  __syncthreads();                                   // every warp is done with the tile: reuse it for the partial sums
+  if ((lane & 3) == 0) {
+    const int g = lane >> 2;
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+      float* pp = part + ((size_t)warp * 128 + r * TW + g) * 2;
+      pp[0] = acc[r][0]; pp[1] = acc[r][1];
+      pp[16] = acc[r][2]; pp[17] = acc[r][3];          // pixel g + 8
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < od * 128; i += NW * 32) {
+    const int o = i >> 7, pix = i & 127;
+    float t = p.bias[p.row_base[h] + o];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += part[((size_t)w * 128 + pix) * 2 + o];
+    const int oy = oy0 + pix / TW, ox = ox0 + pix % TW;
+    if (oy < p.H && ox < p.W)
+      p.out[(((int64_t)b * p.out_ch + p.row_base[h] + o) * p.H + oy) * p.W + ox] = t;
+  }
+}
+
 int head_top_conv(const void* y, int dtype, int pix_stride, int head0, int n_heads, const int* od, const float* w,
                   const float* bias, float* out, int out_ch, int B, int H, int W, cudaStream_t s) {
   FTC_REQUIRE(n_heads >= 1 && n_heads <= 8, "head_top_conv handles up to 8 heads");
@@ -439,8 +706,10 @@ int head_top_conv(const void* y, int dtype, int pix_stride, int head0, int n_hea
     if (!attr_done[0]) { FTC_CHECK_CUDA(cudaFuncSetAttribute(head_top_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[0] = true; }
     head_top_conv_kernel<float><<<grid, 256, smem, s>>>(p);
   } else {
-    if (!attr_done[1]) { FTC_CHECK_CUDA(cudaFuncSetAttribute(head_top_conv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done[1] = true; }
-    head_top_conv_kernel<bf16><<<grid, 256, smem, s>>>(p);
+    FTC_REQUIRE(pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "head_top_conv: bf16 source alignment");
+    smem = (size_t)10 * 18 * 200 * 2;
+    if (!attr_done[1]) { FTC_CHECK_CUDA(cudaFuncSetAttribute(head_top_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_done[1] = true; }
+    head_top_mma_kernel<<<grid, 192, smem, s>>>(p);
   }
   FTC_POST_LAUNCH();
   return 0;

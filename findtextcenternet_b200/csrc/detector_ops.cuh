@@ -21,6 +21,15 @@ int dwconv3x3(const void* in, void* out, int dtype, int B, int H, int W, int C, 
 int se_fc(float* sum, float* scale_out, float* hid, int B, int C, int S, float inv_hw, const float* w1 /*[S][C]*/,
           const float* b1, const float* w2t /*[S][C]*/, const float* b2, cudaStream_t s);
 
+// stride-1 depthwise 3x3 + BN + SiLU with the SE squeeze and fc1 folded in (one CTA per image x 32 channels):
+//   hid_pre[b, s] += sum_c w1[s, c] * mean_hw(out[b, :, :, c])   (hid_pre [B, S] fp32 must be zero on entry)
+bool dwconv3x3_se_supported(int H, int W, int C, int stride);
+int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int C, const float* w /*[9][C]*/, const float* scale,
+                 const float* bias, const float* w1 /*[S][C]*/, int S, float* hid_pre, cudaStream_t s);
+// scale[b,c] = sigmoid(b2[c] + w2t[:,c] . silu(hid_pre[b,:] + b1)); zeroes hid_clear [B, clear_n]
+int se_fc2_hid(const float* hid_pre, float* hid_clear, int clear_n, float* scale_out, int B, int C, int S, const float* b1,
+               const float* w2t, const float* b2, cudaStream_t s);
+
 // bilinear x2, align_corners=True, NHWC (nn.UpsamplingBilinear2d, models/detector.py:170)
 int upsample2x(const void* in, void* out, int dtype, int B, int H, int W, int C, cudaStream_t s);
 
