@@ -247,6 +247,23 @@ int dwconv3x3(const void* in, void* out, int dtype, int B, int H, int W, int C, 
 // Because a CTA sees ALL pixels of its channels, the squeeze needs no atomics: mean[b, c] is final inside the CTA, and by
 // linearity the CTA adds its 32-channel share of fc1 -- sum_c w1[s, c] * mean[b, c] -- straight into hid_pre[b, s]
 // (S atomics per CTA).  What is left of SE is one tiny kernel (se_fc2_hid) instead of two, and the se_sum round trip.
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ void load4p(const float* p, f32x2 (&v)[2]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = pk2(a.x, a.y); v[1] = pk2(a.z, a.w);
+}
+__device__ __forceinline__ void load4p(const bf16* p, f32x2 (&v)[2]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  v[0] = pk2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u));
+  v[1] = pk2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+}
+
 template <typename T, int TH>
 __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C,
                                                               const float* __restrict__ w, const float* __restrict__ scale,
@@ -265,16 +282,21 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const T* __rest
   const T* img = in + (int64_t)b * H * W * C + cb;
   T* oimg = out + (int64_t)b * H * W * C + cb;
   const int nstrips = H / TH;
+  // strip loader: one flat loop over (row, pixel, 16-byte piece); row = item / row_items by reciprocal multiply (exact for
+  // the < 2^12 items of a strip), pixel / piece by shifts -- a real integer division here cost a third of the kernel
+  const int row_items = IW * PPP;
+  const uint32_t row_inv = (1u << 20) / (uint32_t)row_items + 1u;
   auto prefetch = [&](int s) {
     T* dst = ring + (size_t)(s & 1) * strip_elems;
     const int iy0 = s * TH - 1;
-    for (int i = tid; i < (TH + 2) * IW * PPP; i += nthr) {
-      const int pix = i / PPP, piece = i - pix * PPP;
-      const int py = pix / IW, px = pix - py * IW;
+    for (int i = tid; i < (TH + 2) * row_items; i += nthr) {
+      const int py = (int)(((uint32_t)i * row_inv) >> 20);
+      const int j = i - py * row_items;
+      const int px = j / PPP, piece = j & (PPP - 1);
       const int iy = iy0 + py, ix = px - 1;
       const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
       const T* src = ok ? img + ((int64_t)iy * W + ix) * C + piece * EPP : img;
-      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + (size_t)pix * CB + piece * EPP);
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + (size_t)i * EPP);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16u : 0u) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -282,12 +304,12 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const T* __rest
   prefetch(0);
   const int quad = tid & 7, col = tid >> 3;            // 4 channels, one output column
   const int c0 = cb + quad * 4;
-  float wk[9][4], sc[4], bi[4], ssum[4];
+  f32x2 wk[9][2], sc[2], bi[2], ssum[2];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) load4(w + t * C + c0, wk[t]);
-  load4(scale + c0, sc); load4(bias + c0, bi);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) ssum[j] = 0.f;
+  for (int t = 0; t < 9; ++t) load4p(w + t * C + c0, wk[t]);
+  load4p(scale + c0, sc); load4p(bias + c0, bi);
+  ssum[0] = ssum[1] = pk2(0.f, 0.f);
+  const f32x2 half2 = pk2(0.5f, 0.5f);
   for (int s = 0; s < nstrips; ++s) {
     if (s + 1 < nstrips) {
       prefetch(s + 1);
@@ -297,37 +319,51 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const T* __rest
     }
     __syncthreads();
     const T* tcol = ring + (size_t)(s & 1) * strip_elems + (size_t)col * CB + quad * 4;
-    float r[3][3][4];
+    f32x2 r[3][3][2];
     auto load_row = [&](int slot, int trow) {
       const T* rp = tcol + (size_t)trow * IW * CB;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) load4(rp + kx * CB, r[slot][kx]);
+      for (int kx = 0; kx < 3; ++kx) load4p(rp + kx * CB, r[slot][kx]);
     };
     load_row(0, 0); load_row(1, 1);
     T* op = oimg + ((int64_t)(s * TH) * W + col) * C + quad * 4;
 #pragma unroll
     for (int py = 0; py < TH; ++py) {
       load_row((py + 2) % 3, py + 2);
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float o[4];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+      for (int h = 0; h < 2; ++h) {
+        // same operation order as the scalar kernel: acc = fma(x, w, acc) over (ky, kx), then BN, then SiLU
+        f32x2 acc = fmul2(r[py % 3][0][h], wk[0][h]);
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = fmaf(r[(py + ky) % 3][kx][j], wk[ky * 3 + kx][j], acc[j]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float t = fmaf(acc[j], sc[j], bi[j]);
-        acc[j] = sizeof(T) == 4 ? silu_precise(t) : silu_tanh_f(t);
-        ssum[j] += acc[j];
+        for (int t = 1; t < 9; ++t) acc = ffma2(r[(py + t / 3) % 3][t % 3][h], wk[t][h], acc);
+        const f32x2 t2 = ffma2(acc, sc[h], bi[h]);
+        float x0, x1;
+        if (sizeof(T) == 4) {
+          upk2(t2, x0, x1);
+          x0 = silu_precise(x0); x1 = silu_precise(x1);
+        } else {
+          const f32x2 hh = fmul2(t2, half2);
+          float h0, h1, t0, t1;
+          upk2(hh, h0, h1);
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+          upk2(ffma2(hh, pk2(t0, t1), hh), x0, x1);
+        }
+        ssum[h] = fadd2(ssum[h], pk2(x0, x1));
+        o[2 * h] = x0; o[2 * h + 1] = x1;
       }
-      store4(op + (int64_t)py * W * C, acc);
+      store4(op + (int64_t)py * W * C, o);
     }
     __syncthreads();                                    // the strip buffer is refilled two iterations later
   }
   // ---- squeeze (complete for these 32 channels) + this CTA's share of fc1 ----
-#pragma unroll
-  for (int j = 0; j < 4; ++j) red[col * CB + quad * 4 + j] = ssum[j];
+  {
+    float s0, s1, s2, s3;
+    upk2(ssum[0], s0, s1); upk2(ssum[1], s2, s3);
+    float* rp = red + col * CB + quad * 4;
+    rp[0] = s0; rp[1] = s1; rp[2] = s2; rp[3] = s3;
+  }
   __syncthreads();
   float* mean = red + (size_t)W * CB;
   if (tid < CB) {
