@@ -40,7 +40,11 @@ struct TmaLaunch {
   int nbuf;               // TMEM accumulator sets (2: epilogue of tile i overlaps main loop of tile i+1)
   int se_tab;             // SE: channels per image of the shared-memory bf16 scale table (0 = per-row global loads)
   int staged;             // epilogue: 1 = bf16 NHWC output staged in shared memory and written with TMA tensor stores
-  int res_tma;            // staged epilogue: 1 = the residual tile is prefetched with TMA loads (per-warp 2-deep ring)
+  int res_tma;            // staged epilogue: 1 = the residual tile is prefetched with TMA loads (per-warp ring)
+  int box_depth;          // staged epilogue: boxes per warp for the output (and again for the residual ring): 1 or 2
+  int bstat;              // weight-stationary schedule: a CTA walks a CONTIGUOUS range of tiles in (group, n-tile)-major
+                          // order and keeps the whole [BN x K] weight tile resident in its nB = NKB slots across m-tiles
+  int m_tiles;
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -79,8 +83,9 @@ struct TmaTile { int m0, b, y0, x0, g, nt; };
 template <int MT, bool HALO>
 __device__ __forceinline__ TmaTile decode_tma_tile(int tile, int NT, int G, const TmaLaunch& L) {
   const int per_m = NT * G;
-  const int mt = tile / per_m;
-  const int rest = tile - mt * per_m;
+  int mt, rest;
+  if (L.bstat) { rest = tile / L.m_tiles; mt = tile - rest * L.m_tiles; }
+  else { mt = tile / per_m; rest = tile - mt * per_m; }
   TmaTile t;
   t.g = rest / NT;
   t.nt = rest - t.g * NT;
@@ -113,7 +118,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   const uint32_t ring_bytes = (uint32_t)L.nA * L.a_slot_bytes + (uint32_t)L.nB * b_bytes;
   // staged epilogue: per epilogue warp two output boxes (+ two residual boxes), 2 KB each, right behind the rings
   const uint32_t box_base = sbase + ring_bytes;
-  const uint32_t box_bytes = L.staged ? (uint32_t)TM_EPI_WARPS * (L.res_tma ? 4u : 2u) * TM_BOX_BYTES : 0u;
+  const uint32_t box_bytes = L.staged ? (uint32_t)TM_EPI_WARPS * (L.res_tma ? 2u : 1u) * (uint32_t)L.box_depth * TM_BOX_BYTES : 0u;
   const uint32_t bar0 = box_base + box_bytes;
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (TM_MAX_SLOTS + s); };
@@ -157,6 +162,12 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   const uint32_t tmem_base = *tmem_holder;
   const int hw = p.Ho * p.Wo;
   const int NKG = L.NKG, nsub = L.nsub;
+  int t_first = blockIdx.x, t_last = num_tiles, t_step = gridDim.x;
+  if (L.bstat) {
+    t_first = (int)((long long)blockIdx.x * num_tiles / gridDim.x);
+    t_last = (int)((long long)(blockIdx.x + 1) * num_tiles / gridDim.x);
+    t_step = 1;
+  }
 
   if (warp == TM_TMA_WARP) {
     // ------------------------------------------------------------------ TMA producer (A tensor tiles + B bulk copies)
@@ -165,9 +176,14 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       const int nGA = p.tc.nGA;
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int prev_gn = -1;
+      for (int tile = t_first; tile < t_last; tile += t_step) {
         const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
         const bf16* wtile = wgt + (size_t)(tc.g * NT + tc.nt) * p.tc.NKB * ((size_t)BN * 64);
+        // weight-stationary: slot kb holds k-block kb; it is (re)loaded only when the CTA moves to another n-tile.  The
+        // ring bookkeeping below then advances exactly one lap per reload, so the phase logic is the ring's own.
+        const bool loadB = !L.bstat || (tc.g * NT + tc.nt) != prev_gn;
+        prev_gn = tc.g * NT + tc.nt;
         int kb = 0;
         for (int kg = 0; kg < NKG; ++kg) {
           int chunk = kg, dx = 0;
@@ -187,7 +203,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           else tma_load_4d(a_ring + (uint32_t)as * L.a_slot_bytes, tm, c, tc.m0, 0, 0, bar);
           as = (as + 1 == L.nA) ? 0 : as + 1;
           aph ^= (as == 0) ? 1u : 0u;
-          for (int sub = 0; sub < nsub; ++sub, ++kb) {
+          for (int sub = 0; sub < nsub && loadB; ++sub, ++kb) {
             mbar_wait(b_empty(bs), bph ^ 1u);
             mbar_arrive_expect_tx(b_full(bs), b_bytes);
             bulk_copy_g2s(b_ring + (uint32_t)bs * b_bytes, wtile + (size_t)kb * BN * 64, b_bytes, b_full(bs));
@@ -205,9 +221,17 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       uint32_t titer = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+      int prev_gn = -1;
+      for (int tile = t_first; tile < t_last; tile += t_step, ++titer) {
         const uint32_t buf = L.nbuf == 2 ? (titer & 1u) : 0u;
         const uint32_t use = L.nbuf == 2 ? (titer >> 1) : titer;
+        bool newB = true, lastB = true;       // weight-stationary: wait for the weights once, release them on the last m-tile
+        if (L.bstat) {
+          const int gn = tile / L.m_tiles;
+          newB = gn != prev_gn;
+          prev_gn = gn;
+          lastB = tile + 1 >= t_last || (tile + 1) / L.m_tiles != gn;
+        }
         mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (uint32_t)(MT * BN);
@@ -216,7 +240,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           mbar_wait(a_full(as), aph);
           const uint32_t a_addr = a_ring + (uint32_t)as * L.a_slot_bytes;
           for (int sub = 0; sub < nsub; ++sub) {
-            mbar_wait(b_full(bs), bph);
+            if (newB) mbar_wait(b_full(bs), bph);
             tc_fence_after();
             const uint64_t bdesc = umma_desc_sw128(b_ring + (uint32_t)bs * b_bytes);
             const uint32_t a_sub = a_addr + (HALO ? (uint32_t)sub * (HALO_TW * 128u) : 0u);
@@ -228,9 +252,9 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
                          bdesc + (uint64_t)(2 * k), idesc, (k == 0 && h < MT) ? accum : 1u);
               accum = 1u;
             }
-            umma_commit(b_empty(bs));
+            if (lastB) umma_commit(b_empty(bs));
             bs = (bs + 1 == L.nB) ? 0 : bs + 1;
-            bph ^= (bs == 0) ? 1u : 0u;
+            if (!L.bstat || lastB) bph ^= (bs == 0) ? 1u : 0u;
           }
           umma_commit(a_empty(as));
           as = (as + 1 == L.nA) ? 0 : as + 1;
@@ -257,7 +281,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         // multiplies already is); the product is rounded once, as before.
         __nv_bfloat16* sc_tab = reinterpret_cast<__nv_bfloat16*>(staged + TM_STAGED_FLOATS);
         const int CAp = L.se_tab;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = t_first; tile < t_last; tile += t_step) {
           const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
           const int b0 = tc.m0 / hw;
           const int nb = (b0 + 1) * hw - tc.m0;          // tile rows [0, nb) are image b0, the rest image b0 + 1
@@ -301,7 +325,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           }
         }
       } else
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = t_first; tile < t_last; tile += t_step) {
         const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
         int img[ROWS];
 #pragma unroll
@@ -356,14 +380,15 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       // banks) and leaves through ONE TMA tensor store, which writes whole 64-byte row segments (the direct path wrote
       // 32 scattered 16-byte pieces per store instruction and was LSU-bound).  The residual tile comes in the same way
       // through a two-deep per-warp TMA ring that is issued before the accumulator is waited for.
-      const uint32_t my_boxes = box_base + (uint32_t)warp * (L.res_tma ? 4u : 2u) * TM_BOX_BYTES;
-      const uint32_t out_box0 = my_boxes, res_box0 = my_boxes + 2u * TM_BOX_BYTES;
+      const uint32_t depth = (uint32_t)L.box_depth, dmask = depth - 1u, dshift = depth >> 1;   // depth 1 or 2
+      const uint32_t my_boxes = box_base + (uint32_t)warp * (L.res_tma ? 2u : 1u) * depth * TM_BOX_BYTES;
+      const uint32_t out_box0 = my_boxes, res_box0 = my_boxes + depth * TM_BOX_BYTES;
       const uint32_t sw = (uint32_t)((lane >> 1) & 3);                 // SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3
       const uint32_t row_b = (uint32_t)lane * 64u;
       const int cstart = MT == 1 ? half * 32 : 0, cstep = MT == 1 ? 64 : 32;
       const int nchunk = BN > cstart ? (BN - cstart + cstep - 1) / cstep : 0;
       uint32_t n_out = 0, n_res_issued = 0, n_res_used = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+      for (int tile = t_first; tile < t_last; tile += t_step, ++titer) {
         const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
         const uint32_t buf = L.nbuf == 2 ? (titer & 1u) : 0u;
         const uint32_t use = L.nbuf == 2 ? (titer >> 1) : titer;
@@ -374,14 +399,14 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         const int ch_out = p.out_ch_base[tc.g] + tc.nt * BN;
         const int ch_res = tc.g * p.N + tc.nt * BN;
         auto issue_res = [&](int i) {
-          const uint32_t slot = n_res_issued & 1u;
+          const uint32_t slot = n_res_issued & dmask;
           mbar_arrive_expect_tx(res_bar(warp, slot), TM_BOX_BYTES);
           tma_load_4d(res_box0 + slot * TM_BOX_BYTES, &tmRes, ch_res + cstart + i * cstep, k1, k2, k3, res_bar(warp, slot));
           ++n_res_issued;
         };
         if (L.res_tma && lane == 0) {
           if (nchunk > 0) issue_res(0);
-          if (nchunk > 1) issue_res(1);
+          if (nchunk > 1 && depth == 2) issue_res(1);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TM_EPI_THREADS) : "memory");
         {
@@ -433,8 +458,8 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             for (int e = 0; e < 32; ++e) v[e] = gelu_tanh3(v[e]);
           }
           if (L.res_tma) {
-            const uint32_t slot = n_res_used & 1u;
-            mbar_wait(res_bar(warp, slot), (n_res_used >> 1) & 1u);
+            const uint32_t slot = n_res_used & dmask;
+            mbar_wait(res_bar(warp, slot), (n_res_used >> dshift) & 1u);
             const uint32_t rb_ = res_box0 + slot * TM_BOX_BYTES + row_b;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -446,11 +471,13 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             }
             ++n_res_used;
             __syncwarp();                               // every lane has read the box before it is refilled
-            if (lane == 0 && i + 2 < nchunk) issue_res(i + 2);
+            if (lane == 0 && i + (int)depth < nchunk) issue_res(i + (int)depth);
           }
           if (!(p.tc.flags & 32)) {
-            const uint32_t ob = out_box0 + (n_out & 1u) * TM_BOX_BYTES;
-            if (lane == 0) bulk_wait_read<1>();         // the store that last read this box (two chunks ago) is done
+            const uint32_t ob = out_box0 + (n_out & dmask) * TM_BOX_BYTES;
+            if (lane == 0) {                            // the store that last read this box is done
+              if (depth == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -476,7 +503,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       if (lane == 0) bulk_wait_read<0>();
       __syncwarp();
     } else
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+    for (int tile = t_first; tile < t_last; tile += t_step, ++titer) {
       const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
       const uint32_t buf = L.nbuf == 2 ? (titer & 1u) : 0u;
       const uint32_t use = L.nbuf == 2 ? (titer >> 1) : titer;
@@ -605,6 +632,12 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
   int MT = ((p.tc.BN <= 128 || p.tc.NKB >= 12) && tiles2 >= 120) ? 2 : 1;
   if (env_mt == 1 || env_mt == 2) MT = env_mt;
   const uint32_t b_bytes = (uint32_t)p.tc.BN * 128u;
+  if (!halo && !se && MT == 2 && p.tc.NKB <= TM_MAX_SLOTS && env_mt == 0) {
+    // prefer the weight-stationary schedule (below) with 128-row tiles over 256-row tiles that cannot hold the weights
+    const size_t fixed0 = 1024 + 8 * TM_NBARS + 16 + TM_STAGED_FLOATS * 4 + 256 + (size_t)TM_EPI_WARPS * (p.res1 ? 4 : 2) * TM_BOX_BYTES;
+    const size_t avail0 = 227 * 1024 - fixed0, wbytes = (size_t)p.tc.NKB * b_bytes;
+    if (wbytes + 3 * 2 * (size_t)TM_SUB_BYTES > avail0 && wbytes + 3 * (size_t)TM_SUB_BYTES <= avail0) MT = 1;
+  }
   int m_tiles;
   if (halo) {
     FTC_REQUIRE(p.pad == 1 && p.W % HALO_TW == 0 && p.H % (8 * MT) == 0 && p.Ho == p.H && p.Wo == p.W, "halo geometry");
@@ -636,7 +669,10 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
     L.staged = ok ? 1 : 0;
     L.res_tma = (ok && p.res1) ? 1 : 0;
   }
-  const size_t box_bytes = L.staged ? (size_t)TM_EPI_WARPS * (L.res_tma ? 4 : 2) * TM_BOX_BYTES : 0;
+  // SE kernels need a third A slot (TMA -> scaler -> MMA hand-off) more than deep epilogue staging: their main loops are
+  // long (K >= 768), so single boxes cost nothing there
+  L.box_depth = se ? 1 : 2;
+  const size_t box_bytes = L.staged ? (size_t)TM_EPI_WARPS * (L.res_tma ? 2 : 1) * L.box_depth * TM_BOX_BYTES : 0;
   const size_t fixed = 1024 + 8 * TM_NBARS + 16 + TM_STAGED_FLOATS * 4 + 256 + (size_t)L.se_tab * 4 + box_bytes;
   const size_t avail = 227 * 1024 - fixed;
   if (halo) {
@@ -645,9 +681,25 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
     L.nB = nb > TM_MAX_SLOTS ? TM_MAX_SLOTS : (int)nb;
     FTC_REQUIRE(L.nB >= 3, "smem budget (halo)");
   } else {
+    // weight-stationary schedule (short K, many m-tiles per n-tile: the MBConv expand convs): the [BN x K] weight tile
+    // stays in shared memory and only activations stream, which removes the dominant L2 -> SM traffic term
+    // N*K*(M/tile rows) of these L2-bandwidth-bound GEMMs
+    if (!se && p.tc.NKB <= TM_MAX_SLOTS && !(env_flags & 2048) &&
+        (size_t)p.tc.NKB * b_bytes + 3 * (size_t)L.a_slot_bytes <= avail && (long)m_tiles * p.tc.NT * p.G >= 4L * g_tma_sms) {
+      L.bstat = 1;
+      L.m_tiles = m_tiles;
+      L.nB = p.tc.NKB;
+      size_t na = (avail - (size_t)L.nB * b_bytes) / L.a_slot_bytes;
+      L.nA = na > TM_MAX_SLOTS ? TM_MAX_SLOTS : (int)na;
+    } else {
     size_t n = avail / ((size_t)L.a_slot_bytes + b_bytes);
     L.nA = L.nB = n > TM_MAX_SLOTS ? TM_MAX_SLOTS : (int)n;
     FTC_REQUIRE(L.nA >= 2, "smem budget (rows)");
+    // spend what is left on one more slot of either ring (A first: with SE it feeds a three-party hand-off)
+    size_t left = avail - (size_t)L.nA * ((size_t)L.a_slot_bytes + b_bytes);
+    if (L.nA < TM_MAX_SLOTS && left >= L.a_slot_bytes) { ++L.nA; left -= L.a_slot_bytes; }
+    if (L.nB < TM_MAX_SLOTS && left >= b_bytes) { ++L.nB; left -= b_bytes; }
+    }
   }
   size_t smem = fixed + (size_t)L.nA * L.a_slot_bytes + (size_t)L.nB * b_bytes;
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: the CTA owns all 512 TMEM columns

@@ -15,6 +15,10 @@ ops = eng.forward_timed(x)
 names = {0: "stem", 1: "conv3x3", 2: "conv1x1", 3: "dw+se", 4: "se_fc", 5: "upsample", 6: "top_small"}
 tot = sum(o[1] for o in ops)
 print(f"batch {B}: {tot:.2f} ms total, {len(ops)} ops")
+os.makedirs("gpurun_out", exist_ok=True)
+with open("gpurun_out/ops_all.txt", "w") as f:
+    for i, (k, ms, fl) in enumerate(ops):
+        f.write(f"{i} {names.get(k, k)} {ms:.4f} {fl/1e9:.2f}\n")
 agg = collections.OrderedDict()
 for i, (k, ms, fl) in enumerate(ops):
     a = agg.setdefault(k, [0, 0.0, 0.0]); a[0] += 1; a[1] += ms; a[2] += fl
