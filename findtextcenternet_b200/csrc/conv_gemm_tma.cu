@@ -388,6 +388,8 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       const int cstart = MT == 1 ? half * 32 : 0, cstep = MT == 1 ? 64 : 32;
       const int nchunk = BN > cstart ? (BN - cstart + cstep - 1) / cstep : 0;
       uint32_t n_out = 0, n_res_issued = 0, n_res_used = 0;
+      // SiLU as h + h*tanh(h), h = x/2: the 1/2 is folded into the staged BN scale / bias (exact: a power of two)
+      const float act_pre = p.act == ACT_SILU ? 0.5f : 1.f;
       for (int tile = t_first; tile < t_last; tile += t_step, ++titer) {
         const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
         const uint32_t buf = L.nbuf == 2 ? (titer & 1u) : 0u;
@@ -413,12 +415,12 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           const int ncol0 = tc.nt * BN;
           for (int c = etid; c < BN; c += TM_EPI_THREADS) {
             const int n = ncol0 + c;
-            sscale[c] = (p.scale && n < p.N) ? __ldg(p.scale + (int64_t)tc.g * p.N + n) : 1.f;
+            sscale[c] = act_pre * ((p.scale && n < p.N) ? __ldg(p.scale + (int64_t)tc.g * p.N + n) : 1.f);
           }
           for (int c = etid; c < p.ncase * BN; c += TM_EPI_THREADS) {
             const int cs_ = c / BN, cc = c - cs_ * BN;
             const int n = ncol0 + cc;
-            sbias[c] = (p.bias_tab && n < p.N) ? __ldg(p.bias_tab + ((int64_t)cs_ * G + tc.g) * p.N + n) : 0.f;
+            sbias[c] = act_pre * ((p.bias_tab && n < p.N) ? __ldg(p.bias_tab + ((int64_t)cs_ * G + tc.g) * p.N + n) : 0.f);
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TM_EPI_THREADS) : "memory");
@@ -438,24 +440,42 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           __syncwarp();
           tmem_ld32(t_addr + (uint32_t)c0, raw);
           tmem_ld_wait();
-          float v[32];
-          const float* ss = sscale + c0;
-          const float* sb = sbias + cs * BN + c0;
+          // packed fp32 math (FFMA2): the epilogue warps are issue-bound on the short-K convs
+          f32x2 vv[16];
+          {
+            const ulonglong2* ss = reinterpret_cast<const ulonglong2*>(sscale + c0);
+            const ulonglong2* sb = reinterpret_cast<const ulonglong2*>(sbias + cs * BN + c0);
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const float4 sc = *reinterpret_cast<const float4*>(ss + e);
-            const float4 bi = *reinterpret_cast<const float4*>(sb + e);
-            v[e + 0] = fmaf(__uint_as_float(raw[e + 0]), sc.x, bi.x);
-            v[e + 1] = fmaf(__uint_as_float(raw[e + 1]), sc.y, bi.y);
-            v[e + 2] = fmaf(__uint_as_float(raw[e + 2]), sc.z, bi.z);
-            v[e + 3] = fmaf(__uint_as_float(raw[e + 3]), sc.w, bi.w);
+            for (int e = 0; e < 8; ++e) {
+              const ulonglong2 sc = ss[e], bi = sb[e];
+              vv[2 * e] = ffma2(pk2(__uint_as_float(raw[4 * e]), __uint_as_float(raw[4 * e + 1])), sc.x, bi.x);
+              vv[2 * e + 1] = ffma2(pk2(__uint_as_float(raw[4 * e + 2]), __uint_as_float(raw[4 * e + 3])), sc.y, bi.y);
+            }
           }
           if (p.act == ACT_SILU) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = silu_tanh(v[e]);
+            for (int e = 0; e < 16; ++e) {
+              float h0, h1, t0, t1;
+              upk2(vv[e], h0, h1);
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+              vv[e] = ffma2(vv[e], pk2(t0, t1), vv[e]);
+            }
           } else if (p.act == ACT_GELU) {
+            const f32x2 ca = pk2(7.97507884e-01f, 7.97507884e-01f), cb2 = pk2(3.70056461e-02f, 3.70056461e-02f);
+            const f32x2 cc = pk2(-3.51516792e-04f, -3.51516792e-04f), half2 = pk2(0.5f, 0.5f);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = gelu_tanh3(v[e]);
+            for (int e = 0; e < 16; ++e) {                 // gelu_tanh3 on pairs
+              float q0, q1, t0, t1;
+              upk2(fmul2(vv[e], vv[e]), q0, q1);
+              const f32x2 x2 = pk2(fminf(q0, 64.f), fminf(q1, 64.f));
+              const f32x2 u = fmul2(vv[e], ffma2(x2, ffma2(x2, cc, cb2), ca));
+              upk2(u, q0, q1);
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(q0));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(q1));
+              const f32x2 h = fmul2(vv[e], half2);
+              vv[e] = ffma2(h, pk2(t0, t1), h);
+            }
           }
           if (L.res_tma) {
             const uint32_t slot = n_res_used & dmask;
@@ -465,9 +485,10 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             for (int j = 0; j < 4; ++j) {
               uint4 u;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(rb_ + (((uint32_t)j ^ sw) << 4)) : "memory");
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+              const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[8 * j + 2 * e] += f.x; v[8 * j + 2 * e + 1] += f.y; }
+              for (int e = 0; e < 4; ++e)
+                vv[4 * j + e] = fadd2(vv[4 * j + e], pk2(__uint_as_float(uu[e] << 16), __uint_as_float(uu[e] & 0xFFFF0000u)));
             }
             ++n_res_used;
             __syncwarp();                               // every lane has read the box before it is refilled
@@ -484,7 +505,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
               uint4 u;
               __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+              for (int e = 0; e < 4; ++e) { float lo, hi; upk2(vv[4 * j + e], lo, hi); h[e] = __floats2bfloat162_rn(lo, hi); }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ob + row_b + (((uint32_t)j ^ sw) << 4)), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
             }
             fence_proxy_async();

@@ -247,13 +247,6 @@ int dwconv3x3(const void* in, void* out, int dtype, int B, int H, int W, int C, 
 // Because a CTA sees ALL pixels of its channels, the squeeze needs no atomics: mean[b, c] is final inside the CTA, and by
 // linearity the CTA adds its 32-channel share of fc1 -- sum_c w1[s, c] * mean[b, c] -- straight into hid_pre[b, s]
 // (S atomics per CTA).  What is left of SE is one tiny kernel (se_fc2_hid) instead of two, and the se_sum round trip.
-// packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction)
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ void load4p(const float* p, f32x2 (&v)[2]) {
   const float4 a = *reinterpret_cast<const float4*>(p);
   v[0] = pk2(a.x, a.y); v[1] = pk2(a.z, a.w);
