@@ -227,10 +227,19 @@ def run_ours(args):
                 d = by_kind.setdefault(k, [0.0, 0.0, 0])
                 d[0] += m; d[1] += f; d[2] += 1
             names = {0: "stem", 1: "conv3x3_tc", 2: "conv1x1_tc", 3: "depthwise_se", 4: "se_fc", 5: "upsample", 6: "head_top_small"}
+            traffic, traffic_src = None, None
+            for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+                if name.endswith("_traffic.json"):          # newest committed ncu DRAM-bytes capture (tools/launch_list.sh)
+                    with open(os.path.join(ROOT, "profiles", name)) as f:
+                        tj = json.load(f)
+                    if tj.get("batch") == B:
+                        traffic, traffic_src = tj["dram_bytes_per_launch_avg"], "profiles/" + name
+                    break
             roofline = {
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "traffic": None,
-                "kernel": "conv_gemm_tc_kernel (tcgen05 implicit-GEMM conv), %d launches per forward" % n_gemm,
+                "frac": achieved / peaks["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "conv_gemm_tma_kernel / conv_gemm_tc_kernel (tcgen05 implicit-GEMM conv, TMA or cp.async operand "
+                          "staging), %d launches per forward" % n_gemm,
                 "flop_per_launch_avg": gemm_fl / max(n_gemm, 1), "ms_per_launch_avg": gemm_ms / max(n_gemm, 1),
                 "share_of_step": gemm_ms / all_ms, "peak_source": peaks["src"] + " bf16_tflops_sustained",
                 "whole_forward_tflops": FLOP_PER_IMAGE * (value / world) / 1e12,
