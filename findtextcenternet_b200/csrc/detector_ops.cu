@@ -1,6 +1,7 @@
 // Bandwidth-bound detector kernels + device-side weight packing.  See detector_ops.cuh for the
 // reference lines each op follows.  All activations are NHWC; fp32 (parity mode) or bf16 (product mode).
 #include "detector_ops.cuh"
+#include "tma_util.cuh"
 #include <math.h>
 
 namespace ftc {
@@ -258,11 +259,13 @@ __device__ __forceinline__ void load4p(const bf16* p, f32x2 (&v)[2]) {
 }
 
 template <typename T, int TH>
-__global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C,
+__global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmIn, T* __restrict__ out, int H, int W, int C,
                                                               const float* __restrict__ w, const float* __restrict__ scale,
                                                               const float* __restrict__ bias, const float* __restrict__ w1,
                                                               int S, float inv_hw, float* __restrict__ hid_pre) {
-  extern __shared__ __align__(16) unsigned char dw_smem[];
+  extern __shared__ __align__(16) unsigned char dw_smem_raw[];
+  // TMA destinations need 128-byte alignment; the dynamic shared window only guarantees 16
+  unsigned char* dw_smem = dw_smem_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(dw_smem_raw) & 127u)) & 127u);
   constexpr int CB = 32;                                // channels per CTA
   constexpr int PPP = (int)(CB * sizeof(T) / 16);       // 16-byte pieces per pixel
   constexpr int EPP = (int)(16 / sizeof(T));
@@ -272,27 +275,36 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const T* __rest
   float* red = reinterpret_cast<float*>(dw_smem + (size_t)2 * strip_elems * sizeof(T));   // [W][CB] then mean[CB]
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int b = blockIdx.y, cb = blockIdx.x * CB;
-  const T* img = in + (int64_t)b * H * W * C + cb;
   T* oimg = out + (int64_t)b * H * W * C + cb;
   const int nstrips = H / TH;
-  // strip loader: one flat loop over (row, pixel, 16-byte piece); row = item / row_items by reciprocal multiply (exact for
-  // the < 2^12 items of a strip), pixel / piece by shifts -- a real integer division here cost a third of the kernel
-  const int row_items = IW * PPP;
-  const uint32_t row_inv = (1u << 20) / (uint32_t)row_items + 1u;
+  // strip loader: ONE TMA tensor box per strip -- (TH+2) rows x (W+2) pixels x 32 channels of image b, issued by one thread;
+  // out-of-bounds zero fill is the conv padding.  (The cp.async version spent ~20 % of the kernel's issue slots on its
+  // address arithmetic.)
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(red + (size_t)(W + 1) * CB);   // two mbarriers behind red / mean
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmIn)) : "memory");
+  }
+  __syncthreads();
+  const uint32_t strip_bytes = (uint32_t)(strip_elems * sizeof(T));
   auto prefetch = [&](int s) {
-    T* dst = ring + (size_t)(s & 1) * strip_elems;
-    const int iy0 = s * TH - 1;
-    for (int i = tid; i < (TH + 2) * row_items; i += nthr) {
-      const int py = (int)(((uint32_t)i * row_inv) >> 20);
-      const int j = i - py * row_items;
-      const int px = j / PPP, piece = j & (PPP - 1);
-      const int iy = iy0 + py, ix = px - 1;
-      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-      const T* src = ok ? img + ((int64_t)iy * W + ix) * C + piece * EPP : img;
-      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + (size_t)i * EPP);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+    if (tid == 0) {
+      const uint32_t bar = bar0 + 8u * (uint32_t)(s & 1);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (size_t)(s & 1) * strip_elems);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(strip_bytes) : "memory");
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                   ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmIn)), "r"(cb), "r"(-1), "r"(s * TH - 1), "r"(b), "r"(bar) : "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto wait_strip = [&](int s) {
+    const uint32_t bar = bar0 + 8u * (uint32_t)(s & 1), parity = (uint32_t)(s >> 1) & 1u;
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
   };
   prefetch(0);
   const int quad = tid & 7, col = tid >> 3;            // 4 channels, one output column
@@ -304,13 +316,8 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const T* __rest
   ssum[0] = ssum[1] = pk2(0.f, 0.f);
   const f32x2 half2 = pk2(0.5f, 0.5f);
   for (int s = 0; s < nstrips; ++s) {
-    if (s + 1 < nstrips) {
-      prefetch(s + 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
+    if (s + 1 < nstrips) prefetch(s + 1);
+    wait_strip(s);
     const T* tcol = ring + (size_t)(s & 1) * strip_elems + (size_t)col * CB + quad * 4;
     f32x2 r[3][3][2];
     auto load_row = [&](int slot, int trow) {
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(512, 2) dwconv3x3_strip_mma_kernel(const bf16*
 }
 
 bool dwconv3x3_se_supported(int H, int W, int C, int stride) {
-  return stride == 1 && W * 8 <= 384 && W >= 4 && H % 8 == 0 && C % 32 == 0;
+  return stride == 1 && W * 8 <= 384 && W >= 4 && W % 2 == 0 && H % 8 == 0 && C % 32 == 0;
 }
 
 int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int C, const float* w, const float* scale,
@@ -559,16 +566,21 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
   FTC_REQUIRE(B <= 65535, "batch");
   constexpr int TH = 8;
   const size_t es = dtype == DT_F32 ? 4 : 2;
-  const size_t smem = 2 * (size_t)(TH + 2) * (W + 2) * 32 * es + (size_t)(W + 1) * 32 * sizeof(float);
+  const size_t smem = 2 * (size_t)(TH + 2) * (W + 2) * 32 * es + (size_t)(W + 1) * 32 * sizeof(float) + 16 + 128;   // + mbarriers + alignment slack
   FTC_REQUIRE(smem <= 200 * 1024, "dwconv3x3_se: strip does not fit shared memory");
   dim3 grid(C / 32, B);
   const int threads = W * 8;
   const float inv_hw = 1.0f / (float)(H * W);
+  alignas(64) CUtensorMap tmIn;
+  {
+    int rc = tma_encode_nhwc(&tmIn, in, dtype, C, C, W, H, B, 32, W + 2, TH + 2, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
 #define DWS_LAUNCH(TT)                                                                                                 \
   do {                                                                                                                 \
     static bool done = false;                                                                                          \
     if (!done) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<TT, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; } \
-    dwconv3x3_strip_kernel<TT, TH><<<grid, threads, smem, s>>>((const TT*)in, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre); \
+    dwconv3x3_strip_kernel<TT, TH><<<grid, threads, smem, s>>>(tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre); \
   } while (0)
   // the mma.sync variant is correct but measured SLOWER on B200 (0.26 vs 0.17 ms at 48x48x1536, B=32: its BN/SiLU/SE
   // epilogue and fragment exchange cost as many issue slots as the FMAs they replace); kept behind FTC_DW_MMA=1

@@ -86,7 +86,8 @@ struct ftc_transformer {
     l.ktab = make_ktab(K, 0, 1, &l.Kpad);
     if (use_tc) {
       ConvGemmParams q; memset(&q, 0, sizeof(q)); q.N = N; q.K = l.Kpad;
-      conv_gemm_tc_plan(q, &l.tc);
+      q.CA = K; q.stride = 1; q.pad = 0; q.a_pix_stride = 8;      // rows-mode TMA operand path (the real row stride is a launch argument)
+      conv_gemm_tc_plan(q, &l.tc, !getenv("FTC_TF_NO_TMA"));
       l.w_off = walloc(conv_tc_weight_bytes(l.tc, G));
     } else {
       l.w_off = walloc((size_t)G * N * l.Kpad * esize);
@@ -365,7 +366,7 @@ int run_lin(const ftc_transformer* t, const Lin& l, const void* A, int a_stride,
   char* P = t->packed;
   p.B = M; p.H = 1; p.W = 1; p.Ho = 1; p.Wo = 1; p.stride = 1; p.pad = 0;
   p.M = M; p.N = l.N; p.G = l.G; p.K = l.Kpad;
-  p.srcA = A; p.a_pix_stride = a_stride;
+  p.srcA = A; p.a_pix_stride = a_stride; p.CA = l.K;
   p.ktab = (const uint32_t*)(P + l.ktab_off);
   p.w = P + l.w_off;
   p.scale = nullptr;

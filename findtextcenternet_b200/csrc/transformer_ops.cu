@@ -308,6 +308,181 @@ int decoder_embed_ln(const int64_t* tokens, const float* e0, const float* e1, co
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// bf16 attention on the warp-level tensor cores (mma.sync m16n8k16, fp32 accumulate), flash style: one CTA per
+// (64 query rows, head, batch), 4 warps x 16 rows; K and V of the (batch, head) sit in shared memory as bf16 (row stride
+// padded by 16 B: conflict-free ldmatrix); keys are walked in chunks of 32 with an online softmax in the exp2 domain; the
+// S accumulator fragments are re-packed in registers as the A operand of P.V.  (The CUDA-core kernel above was 67 % of the
+// cfg#4 transformer forward.)
+template <int HD>
+__global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restrict__ q, int q_stride, int q_off,
+                                                            const bf16* __restrict__ k, const bf16* __restrict__ v, int kv_stride,
+                                                            int k_off, int v_off, const float* __restrict__ mask,
+                                                            bf16* __restrict__ out, int out_stride, int Lt, int Ls, float scale_log2) {
+  extern __shared__ __align__(16) unsigned char att_smem[];
+  constexpr int RS = HD + 8;                       // padded row stride (elements)
+  constexpr int KS = HD / 16;                      // k-steps over the head dim
+  constexpr int NO = HD / 8;                       // output n-tiles
+  const int Lp = (Ls + 31) & ~31;
+  bf16* Ks = reinterpret_cast<bf16*>(att_smem);    // [Lp][RS]
+  bf16* Vs = Ks + (size_t)Lp * RS;                 // [Lp][RS]
+  float* Ms = reinterpret_cast<float*>(Vs + (size_t)Lp * RS);   // [Lp] additive mask in the exp2 domain (0 / -inf)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64 + warp * 16;
+  const bf16* kb = k + (int64_t)b * Ls * kv_stride + k_off + h * HD;
+  const bf16* vb = v + (int64_t)b * Ls * kv_stride + v_off + h * HD;
+  constexpr int PPR = HD / 8;                      // 16-byte pieces per row
+  for (int i = tid; i < Lp * PPR; i += 128) {
+    const int j = i / PPR, pc = i - j * PPR;
+    const bool ok = j < Ls;
+    const uint32_t dk = (uint32_t)__cvta_generic_to_shared(Ks + (size_t)j * RS + pc * 8);
+    const uint32_t dv = (uint32_t)__cvta_generic_to_shared(Vs + (size_t)j * RS + pc * 8);
+    const bf16* sk = ok ? kb + (int64_t)j * kv_stride + pc * 8 : kb;
+    const bf16* sv = ok ? vb + (int64_t)j * kv_stride + pc * 8 : vb;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dk), "l"(sk), "r"(ok ? 16u : 0u) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dv), "l"(sv), "r"(ok ? 16u : 0u) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int j = tid; j < Lp; j += 128) Ms[j] = j < Ls ? (mask ? mask[(int64_t)b * Ls + j] : 0.f) : -INFINITY;
+  // Q fragments straight from global memory (rows clamped; out-of-range rows are not stored)
+  const int g = lane >> 2, qd = lane & 3;
+  uint32_t qa[KS][4];
+  {
+    const int r0 = min(q0 + g, Lt - 1), r1 = min(q0 + g + 8, Lt - 1);
+    const bf16* qp0 = q + ((int64_t)b * Lt + r0) * q_stride + q_off + h * HD + qd * 2;
+    const bf16* qp1 = q + ((int64_t)b * Lt + r1) * q_stride + q_off + h * HD + qd * 2;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(qp0 + ks * 16);
+      qa[ks][1] = *reinterpret_cast<const uint32_t*>(qp1 + ks * 16);
+      qa[ks][2] = *reinterpret_cast<const uint32_t*>(qp0 + ks * 16 + 8);
+      qa[ks][3] = *reinterpret_cast<const uint32_t*>(qp1 + ks * 16 + 8);
+    }
+  }
+  float o[NO][4];
+#pragma unroll
+  for (int n = 0; n < NO; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[n][e] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (q0 >= Lt) return;                            // whole warp beyond the sequence (after the only barrier)
+  const uint32_t ks_s = (uint32_t)__cvta_generic_to_shared(Ks), vs_s = (uint32_t)__cvta_generic_to_shared(Vs);
+  // ldmatrix lane addresses: K (non-transposed): key = lane & 7, head-dim block = lane >> 3;
+  //                          V (transposed):     key = (lane & 7) + 8 * ((lane >> 3) & 1), head-dim block = lane >> 4
+  const uint32_t k_lane = (uint32_t)(((lane & 7) * RS + (lane >> 3) * 8) * 2);
+  const uint32_t v_lane = (uint32_t)((((lane & 7) + 8 * ((lane >> 3) & 1)) * RS + (lane >> 4) * 8) * 2);
+  for (int c0 = 0; c0 < Lp; c0 += 32) {
+    float sacc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KS; kk += 2) {         // one ldmatrix.x4 = this n-tile's B fragments for two k-steps
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(ks_s + (uint32_t)(((c0 + nt * 8) * RS + kk * 16) * 2) + k_lane) : "memory");
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(sacc[nt][0]), "+f"(sacc[nt][1]), "+f"(sacc[nt][2]), "+f"(sacc[nt][3])
+                     : "r"(qa[kk][0]), "r"(qa[kk][1]), "r"(qa[kk][2]), "r"(qa[kk][3]), "r"(b0), "r"(b1));
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(sacc[nt][0]), "+f"(sacc[nt][1]), "+f"(sacc[nt][2]), "+f"(sacc[nt][3])
+                     : "r"(qa[kk + 1][0]), "r"(qa[kk + 1][1]), "r"(qa[kk + 1][2]), "r"(qa[kk + 1][3]), "r"(b2), "r"(b3));
+      }
+    }
+    // scale + mask, chunk row maxima (rows g and g + 8; a row lives in the 4 lanes of a quad)
+    float cm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float m0 = Ms[c0 + nt * 8 + qd * 2], m1 = Ms[c0 + nt * 8 + qd * 2 + 1];
+      sacc[nt][0] = fmaf(sacc[nt][0], scale_log2, m0); sacc[nt][1] = fmaf(sacc[nt][1], scale_log2, m1);
+      sacc[nt][2] = fmaf(sacc[nt][2], scale_log2, m0); sacc[nt][3] = fmaf(sacc[nt][3], scale_log2, m1);
+      cm[0] = fmaxf(cm[0], fmaxf(sacc[nt][0], sacc[nt][1]));
+      cm[1] = fmaxf(cm[1], fmaxf(sacc[nt][2], sacc[nt][3]));
+    }
+    float alpha[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      cm[r] = fmaxf(cm[r], __shfl_xor_sync(0xffffffffu, cm[r], 1));
+      cm[r] = fmaxf(cm[r], __shfl_xor_sync(0xffffffffu, cm[r], 2));
+      const float mnew = fmaxf(mrow[r], cm[r]);
+      const float msafe = mnew == -INFINITY ? 0.f : mnew;       // fully masked so far: keep everything at zero
+      alpha[r] = exp2f(mrow[r] - msafe);
+      mrow[r] = mnew;
+      cm[r] = msafe;
+      lrow[r] *= alpha[r];
+    }
+#pragma unroll
+    for (int n = 0; n < NO; ++n) { o[n][0] *= alpha[0]; o[n][1] *= alpha[0]; o[n][2] *= alpha[1]; o[n][3] *= alpha[1]; }
+    uint32_t pa[2][4];                              // P as A fragments: k-step j covers n-tiles 2j, 2j+1
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float p0 = exp2f(sacc[nt][0] - cm[0]), p1 = exp2f(sacc[nt][1] - cm[0]);
+      const float p2 = exp2f(sacc[nt][2] - cm[1]), p3 = exp2f(sacc[nt][3] - cm[1]);
+      lrow[0] += p0 + p1; lrow[1] += p2 + p3;
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+      pa[nt >> 1][(nt & 1) * 2] = *reinterpret_cast<uint32_t*>(&lo);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+#pragma unroll
+    for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+      for (int n = 0; n < NO; n += 2) {             // one ldmatrix.x4.trans = V fragments of two output n-tiles
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(vs_s + (uint32_t)(((c0 + kc * 16) * RS + n * 8) * 2) + v_lane) : "memory");
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(o[n][0]), "+f"(o[n][1]), "+f"(o[n][2]), "+f"(o[n][3])
+                     : "r"(pa[kc][0]), "r"(pa[kc][1]), "r"(pa[kc][2]), "r"(pa[kc][3]), "r"(b0), "r"(b1));
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(o[n + 1][0]), "+f"(o[n + 1][1]), "+f"(o[n + 1][2]), "+f"(o[n + 1][3])
+                     : "r"(pa[kc][0]), "r"(pa[kc][1]), "r"(pa[kc][2]), "r"(pa[kc][3]), "r"(b2), "r"(b3));
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+  }
+  const float inv0 = 1.f / lrow[0], inv1 = 1.f / lrow[1];
+  const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+  for (int n = 0; n < NO; ++n) {
+    if (r0 < Lt) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(o[n][0] * inv0, o[n][1] * inv0);
+      *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)b * Lt + r0) * out_stride + h * HD + n * 8 + qd * 2) = t;
+    }
+    if (r1 < Lt) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(o[n][2] * inv1, o[n][3] * inv1);
+      *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)b * Lt + r1) * out_stride + h * HD + n * 8 + qd * 2) = t;
+    }
+  }
+}
+
+template <int HD>
+static int launch_attention_mma(const void* q, int q_stride, int q_off, const void* k, const void* v, int kv_stride, int k_off,
+                                int v_off, const float* mask, void* out, int out_stride, int B, int heads, int Lt, int Ls,
+                                cudaStream_t s) {
+  const int Lp = (Ls + 31) & ~31;
+  const size_t smem = 2 * (size_t)Lp * (HD + 8) * 2 + (size_t)Lp * 4;
+  FTC_REQUIRE(smem <= 227 * 1024, "attention: sequence too long for the shared-memory K/V tile");
+  static bool attr_done = false;
+  if (!attr_done) {
+    FTC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+  attention_mma_kernel<HD><<<dim3((Lt + 63) / 64, heads, B), 128, smem, s>>>(
+      (const bf16*)q, q_stride, q_off, (const bf16*)k, (const bf16*)v, kv_stride, k_off, v_off, mask, (bf16*)out, out_stride, Lt, Ls,
+      scale_log2);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
 template <typename T, int HD>
 static int launch_attention(const void* q, int q_stride, int q_off, const void* k, const void* v, int kv_stride, int k_off,
                             int v_off, const float* mask, void* out, int out_stride, int B, int heads, int Lt, int Ls,
@@ -334,6 +509,13 @@ int attention(const void* q, int q_stride, int q_off, const void* k, const void*
     if (hd == 32) ATT(float, 32);
     if (hd == 64) ATT(float, 64);
   } else {
+    // tensor-core path: 4-byte fragment loads / stores need even offsets and strides, cp.async needs 16-byte rows
+    const bool mma_ok = q_stride % 2 == 0 && q_off % 2 == 0 && out_stride % 2 == 0 && kv_stride % 8 == 0 && k_off % 8 == 0 &&
+                        v_off % 8 == 0 && B <= 65535 && heads <= 65535 && !getenv("FTC_ATT_NO_MMA") &&
+                        (reinterpret_cast<uintptr_t>(k) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(q) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+    if (mma_ok && hd == 32) return launch_attention_mma<32>(q, q_stride, q_off, k, v, kv_stride, k_off, v_off, mask, out, out_stride, B, heads, Lt, Ls, s);
+    if (mma_ok && hd == 64) return launch_attention_mma<64>(q, q_stride, q_off, k, v, kv_stride, k_off, v_off, mask, out, out_stride, B, heads, Lt, Ls, s);
     if (hd == 16) ATT(bf16, 16);
     if (hd == 32) ATT(bf16, 32);
     if (hd == 64) ATT(bf16, 64);
