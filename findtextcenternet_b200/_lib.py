@@ -84,6 +84,9 @@ SYMBOLS = {
     "ftc_op_se_fc": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "ftc_debug_set_trace": (_i, [_vp]),
     "ftc_op_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ftc_op_dwconv3x3_se": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ftc_op_head_top_conv": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ftc_op_attention": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -86,3 +86,43 @@ def peak_pick(heat9: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(heat9.device):
         _lib.check(lib.ftc_peak_pick(heat9.contiguous().data_ptr(), out.data_ptr(), b, h, w, _s(heat9)), "ftc_peak_pick")
     return out
+
+
+def dwconv3x3_se(x: torch.Tensor, w9c, scale, bias, w1, b1, w2t, b2):
+    """Stride-1 MBConv middle: depthwise 3x3 + BN + SiLU with folded SE squeeze/fc1, then fc2 -> (out, se_scale [B, C])."""
+    lib = _lib.load()
+    b, h, w, c = x.shape
+    s = w1.shape[0]
+    out = torch.empty_like(x)
+    hid = torch.zeros(b, s, dtype=torch.float32, device=x.device)
+    sc = torch.empty(b, c, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ftc_op_dwconv3x3_se(x.data_ptr(), out.data_ptr(), _dt(x), b, h, w, c, w9c.data_ptr(), scale.data_ptr(),
+                                           bias.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(), b2.data_ptr(), s,
+                                           hid.data_ptr(), sc.data_ptr(), _s(x)), "ftc_op_dwconv3x3_se")
+    return out, sc
+
+
+def head_top_conv(y: torch.Tensor, od, w_rows: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """y [B,H,W,n_heads*192] NHWC -> NCHW fp32 [B, sum(od), H, W]; w_rows fp32 [sum(od), 9*192] tap-major."""
+    import ctypes
+    lib = _lib.load()
+    b, h, w, ct = y.shape
+    arr = (ctypes.c_int * len(od))(*od)
+    out = torch.empty(b, sum(od), h, w, dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.check(lib.ftc_op_head_top_conv(y.data_ptr(), _dt(y), ct, len(od), arr, w_rows.data_ptr(), bias.data_ptr(),
+                                            out.data_ptr(), b, h, w, _s(y)), "ftc_op_head_top_conv")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B, Lt, d], k/v [B, Ls, d] (contiguous) -> [B, Lt, d]; mask fp32 [B, Ls] additive."""
+    lib = _lib.load()
+    b, lt, d = q.shape
+    ls = k.shape[1]
+    out = torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        _lib.check(lib.ftc_op_attention(q.data_ptr(), d, 0, k.data_ptr(), v.data_ptr(), d, 0, 0, _p(mask), out.data_ptr(), d,
+                                        _dt(q), b, heads, d // heads, lt, ls, _s(q)), "ftc_op_attention")
+    return out

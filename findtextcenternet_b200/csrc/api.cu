@@ -144,6 +144,33 @@ int ftc_debug_set_trace(void* dev_u64_4096) {
   return 0;
 }
 
+int ftc_op_dwconv3x3_se(const void* x, void* out, int dtype, int batch, int h, int w, int c, const float* w9c,
+                        const float* scale, const float* bias, const float* w1, const float* b1, const float* w2t,
+                        const float* b2, int s, float* hid_pre, float* scale_out, void* stream) {
+  FTC_REQUIRE(x && out && w9c && scale && bias && w1 && b1 && w2t && b2 && hid_pre && scale_out, "null argument");
+  FTC_REQUIRE(dwconv3x3_se_supported(h, w, c, 1), "dwconv3x3_se: unsupported geometry");
+  int rc = dwconv3x3_se(x, out, dtype, batch, h, w, c, w9c, scale, bias, w1, s, hid_pre, (cudaStream_t)stream);
+  if (rc) return rc;
+  // fc2 reads hid_pre; the "other parity" accumulator it clears is not used here: clear nothing (clear_n = 0)
+  return se_fc2_hid(hid_pre, hid_pre, 0, scale_out, batch, c, s, b1, w2t, b2, (cudaStream_t)stream);
+}
+
+int ftc_op_head_top_conv(const void* y, int dtype, int pix_stride, int n_heads, const int* od, const float* w,
+                         const float* bias, float* out, int batch, int h, int wd, void* stream) {
+  FTC_REQUIRE(y && od && w && bias && out && n_heads >= 1 && n_heads <= 8, "bad argument");
+  int out_ch = 0;
+  for (int i = 0; i < n_heads; ++i) out_ch += od[i];
+  return head_top_conv(y, dtype, pix_stride, 0, n_heads, od, w, bias, out, out_ch, batch, h, wd, (cudaStream_t)stream);
+}
+
+int ftc_op_attention(const void* q, int q_stride, int q_off, const void* k, const void* v, int kv_stride, int k_off, int v_off,
+                     const float* mask, void* out, int out_stride, int dtype, int batch, int heads, int hd, int lt, int ls,
+                     void* stream) {
+  FTC_REQUIRE(q && k && v && out && batch > 0 && heads > 0 && lt > 0 && ls > 0, "bad argument");
+  return attention(q, q_stride, q_off, k, v, kv_stride, k_off, v_off, mask, out, out_stride, dtype, batch, heads, hd, lt, ls,
+                   (cudaStream_t)stream);
+}
+
 int ftc_op_upsample2x(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream) {
   FTC_REQUIRE(x && out, "null argument");
   return upsample2x(x, out, dtype, batch, h, w, c, (cudaStream_t)stream);

@@ -385,8 +385,11 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       const uint32_t out_box0 = my_boxes, res_box0 = my_boxes + depth * TM_BOX_BYTES;
       const uint32_t sw = (uint32_t)((lane >> 1) & 3);                 // SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3
       const uint32_t row_b = (uint32_t)lane * 64u;
-      const int cstart = MT == 1 ? half * 32 : 0, cstep = MT == 1 ? 64 : 32;
+      // a chunk = one output box of 32 channels = 32 accumulator columns (64 for SwiGLU, which gates column pairs)
+      const int cw = p.act == ACT_SWIGLU ? 64 : 32;
+      const int cstart = MT == 1 ? half * cw : 0, cstep = MT == 1 ? 2 * cw : cw;
       const int nchunk = BN > cstart ? (BN - cstart + cstep - 1) / cstep : 0;
+      const bool res1_direct = p.res1 != nullptr && !L.res_tma;
       uint32_t n_out = 0, n_res_issued = 0, n_res_used = 0;
       // SiLU as h + h*tanh(h), h = x/2: the 1/2 is folded into the staged BN scale / bias (exact: a power of two)
       const float act_pre = p.act == ACT_SILU ? 0.5f : 1.f;
@@ -398,7 +401,8 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         int k1, k2, k3;
         if (HALO) { k1 = tc.x0; k2 = tc.y0 + (MT == 2 ? half * 8 : 0) + q * 2; k3 = tc.b; }
         else { k1 = tc.m0 + (MT == 2 ? half * TM_BM : 0) + q * 32; k2 = 0; k3 = 0; }
-        const int ch_out = p.out_ch_base[tc.g] + tc.nt * BN;
+        const int ch_out = p.out_ch_base[tc.g] + (p.act == ACT_SWIGLU ? (tc.nt * BN) >> 1 : tc.nt * BN);
+        const int m_row = (HALO ? 0 : tc.m0) + row;       // rows mode: this lane's output row (direct residual loads)
         const int ch_res = tc.g * p.N + tc.nt * BN;
         auto issue_res = [&](int i) {
           const uint32_t slot = n_res_issued & dmask;
@@ -437,11 +441,32 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           const int c0 = cstart + i * cstep;
           if (tc.nt * BN + c0 >= p.N) break;          // warp-uniform
           uint32_t raw[32];
+          f32x2 vv[16];
+          if (p.act == ACT_SWIGLU) {
+            // interleaved (x1, xg) column pairs -> x1 * silu(xg): 64 accumulator columns give this box's 32 outputs
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              __syncwarp();
+              tmem_ld32(t_addr + (uint32_t)(c0 + hh * 32), raw);
+              tmem_ld_wait();
+              const ulonglong2* sb = reinterpret_cast<const ulonglong2*>(sbias + cs * BN + c0 + hh * 32);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const ulonglong2 bi = sb[e];
+                float x1a, xga, x1b, xgb, ta, tb;
+                upk2(fadd2(pk2(__uint_as_float(raw[4 * e]), __uint_as_float(raw[4 * e + 1])), bi.x), x1a, xga);
+                upk2(fadd2(pk2(__uint_as_float(raw[4 * e + 2]), __uint_as_float(raw[4 * e + 3])), bi.y), x1b, xgb);
+                const float ha = 0.5f * xga, hb = 0.5f * xgb;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(ha));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(hb));
+                vv[hh * 8 + e] = pk2(x1a * fmaf(ha, ta, ha), x1b * fmaf(hb, tb, hb));
+              }
+            }
+          } else {
           __syncwarp();
           tmem_ld32(t_addr + (uint32_t)c0, raw);
           tmem_ld_wait();
           // packed fp32 math (FFMA2): the epilogue warps are issue-bound on the short-K convs
-          f32x2 vv[16];
           {
             const ulonglong2* ss = reinterpret_cast<const ulonglong2*>(sscale + c0);
             const ulonglong2* sb = reinterpret_cast<const ulonglong2*>(sbias + cs * BN + c0);
@@ -477,6 +502,23 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
               vv[e] = ffma2(h, pk2(t0, t1), h);
             }
           }
+          }
+          // residuals that cannot come through the TMA ring (row-periodic tables, a second residual): 64 bytes per lane
+          auto add_direct = [&](const bf16* base, int64_t rrow, int stride) {
+            const uint4* rp = reinterpret_cast<const uint4*>(base + rrow * stride + (int64_t)tc.g * p.N + tc.nt * BN + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = __ldg(rp + j);
+              const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                vv[4 * j + e] = fadd2(vv[4 * j + e], pk2(__uint_as_float(uu[e] << 16), __uint_as_float(uu[e] & 0xFFFF0000u)));
+            }
+          };
+          if (!HALO && m_row < p.M) {
+            if (res1_direct) add_direct(res1, p.res1_row_mod ? (int64_t)(m_row % p.res1_row_mod) : (int64_t)m_row, p.res1_stride);
+            if (res2) add_direct(res2, (int64_t)m_row, p.res2_stride);
+          }
           if (L.res_tma) {
             const uint32_t slot = n_res_used & dmask;
             mbar_wait(res_bar(warp, slot), (n_res_used >> dshift) & 1u);
@@ -511,7 +553,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_4d(&tmOut, ob, ch_out + c0, k1, k2, k3);
+              tma_store_4d(&tmOut, ob, ch_out + (p.act == ACT_SWIGLU ? c0 >> 1 : c0), k1, k2, k3);
               bulk_commit();
             }
             ++n_out;
@@ -681,14 +723,17 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
     L.se_tab = p.tc.nGA * 64;
   // staged (TMA-store) epilogue: plain bf16 NHWC outputs whose n-tiles are whole 32-channel boxes
   {
-    bool ok = p.out_layout == OUT_NHWC && p.act != ACT_SWIGLU && p.tc.BN % 32 == 0 && p.tc.BN * p.tc.NT == p.N &&
-              (p.ncase == 1 || halo) && p.res2 == nullptr && p.out_stride % 8 == 0 &&
-              (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && !(env_flags & 1024);
-    for (int g = 0; g < p.G && ok; ++g) ok = p.n_valid[g] == p.N;
-    if (ok && p.res1)
-      ok = p.res1_row_mod == 0 && p.res1_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.res1) & 15) == 0;
+    const bool swiglu = p.act == ACT_SWIGLU;
+    bool ok = p.out_layout == OUT_NHWC && p.tc.BN % (swiglu ? 64 : 32) == 0 && p.tc.BN * p.tc.NT == p.N &&
+              (p.ncase == 1 || halo) && p.out_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+              !(env_flags & 1024);
+    for (int g = 0; g < p.G && ok; ++g) ok = p.n_valid[g] == p.N && p.out_ch_base[g] % 8 == 0;
+    if (ok && swiglu) ok = p.res1 == nullptr && p.res2 == nullptr && p.scale == nullptr;
+    if (ok && p.res1) ok = p.res1_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.res1) & 15) == 0 && (p.G * p.N) % 8 == 0;
+    if (ok && p.res2) ok = !halo && p.res2_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.res2) & 15) == 0;
+    if (ok && p.res1 && p.res1_row_mod) ok = !halo;          // periodic tables are read directly (rows mode only)
     L.staged = ok ? 1 : 0;
-    L.res_tma = (ok && p.res1) ? 1 : 0;
+    L.res_tma = (ok && p.res1 && p.res1_row_mod == 0) ? 1 : 0;
   }
   // SE kernels need a third A slot (TMA -> scaler -> MMA hand-off) more than deep epilogue staging: their main loops are
   // long (K >= 768), so single boxes cost nothing there

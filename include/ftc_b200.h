@@ -150,6 +150,22 @@ int ftc_op_se_fc(float* sum, float* scale_out, float* hid, int batch, int c, int
  * ([0,1024) MMA full-wait start, [1024,2048) end, [2048,3072) producer empty-wait start, [3072,4096) end); NULL = off */
 int ftc_debug_set_trace(void* dev_u64_4096);
 int ftc_op_upsample2x(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream);
+/* MBConv middle (torchvision efficientnet.py:137-149 + ops/misc.py:251-261), stride 1: depthwise 3x3 + BN + SiLU with the SE
+ * squeeze and fc1 folded into the same kernel, then fc2 + sigmoid.  hid_pre: fp32 [batch, s], zero on entry, holds the
+ * fc1 pre-activations afterwards; scale_out: fp32 [batch, c].  Returns an error for unsupported geometry
+ * (needs w <= 48, w even, h % 8 == 0, c % 32 == 0). */
+int ftc_op_dwconv3x3_se(const void* x, void* out, int dtype, int batch, int h, int w, int c, const float* w9c,
+                        const float* scale, const float* bias, const float* w1, const float* b1, const float* w2t,
+                        const float* b2, int s, float* hid_pre, float* scale_out, void* stream);
+/* Leafmap.top_conv of the 1-/2-channel heads (models/detector.py:188-190): y NHWC (dtype) with head i at channels
+ * [i*192, i*192+192), w fp32 [sum(od)][9*192] tap-major, out NCHW fp32 [batch, sum(od), h, w] */
+int ftc_op_head_top_conv(const void* y, int dtype, int pix_stride, int n_heads, const int* od, const float* w,
+                         const float* bias, float* out, int batch, int h, int wd, void* stream);
+/* softmax(q k^T / sqrt(hd) + mask) v per (batch, head) (models/transformer.py:133): q [B*Lt, q_stride] at column
+ * q_off + h*hd, k/v [B*Ls, kv_stride] at k_off/v_off + h*hd, mask fp32 [B, Ls] additive or NULL, out [B*Lt, out_stride] */
+int ftc_op_attention(const void* q, int q_stride, int q_off, const void* k, const void* v, int kv_stride, int k_off, int v_off,
+                     const float* mask, void* out, int out_stride, int dtype, int batch, int heads, int hd, int lt, int ls,
+                     void* stream);
 
 #ifdef __cplusplus
 }

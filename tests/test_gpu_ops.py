@@ -128,6 +128,71 @@ def test_dwconv_se(dt, stride):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 48, 48, 192), (3, 24, 24, 96), (1, 16, 12, 32)])
+def test_dwconv_se_folded(dt, shape):
+    """Strip depthwise kernel with folded SE squeeze + fc1, then fc2 (torchvision MBConv middle, stride 1)."""
+    _lib, ops = _ops()
+    g = torch.Generator().manual_seed(15)
+    b, h, w, c = shape
+    s = max(c // 16, 4)
+    x = torch.randn(b, h, w, c, generator=g).to(dt)
+    wt = torch.randn(c, 1, 3, 3, generator=g) / 3
+    scale = 0.5 + torch.rand(c, generator=g)
+    bias = 0.2 * torch.randn(c, generator=g)
+    w1 = torch.randn(s, c, generator=g) / np.sqrt(c); b1 = 0.1 * torch.randn(s, generator=g)
+    w2 = torch.randn(c, s, generator=g) / np.sqrt(s); b2 = 0.1 * torch.randn(c, generator=g)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, 1, 1, 1, c)
+    ref = F.silu(ref * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    ref_scale = torch.sigmoid(F.linear(F.silu(F.linear(ref.mean((2, 3)), w1, b1)), w2, b2))
+    out, sc = ops.dwconv3x3_se(x.cuda(), wt.view(c, 9).t().contiguous().cuda(), scale.cuda(), bias.cuda(), w1.cuda(), b1.cuda(),
+                               w2.t().contiguous().cuda(), b2.cuda())
+    tol = 1e-5 if dt == torch.float32 else 1e-2
+    assert rel_l2(out.float().cpu().numpy(), ref.permute(0, 2, 3, 1).numpy()) < tol
+    assert rel_l2(sc.cpu().numpy(), ref_scale.numpy()) < (1e-4 if dt == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_head_top_conv(dt):
+    """Leafmap.top_conv of the small heads (models/detector.py:188-190) against F.conv2d."""
+    _lib, ops = _ops()
+    g = torch.Generator().manual_seed(16)
+    od = [1, 2, 1]
+    b, h, w = 2, 24, 40
+    y = torch.randn(b, h, w, len(od) * 192, generator=g).to(dt)
+    ws = [torch.randn(o, 192, 3, 3, generator=g) / 40 for o in od]
+    bs = [0.1 * torch.randn(o, generator=g) for o in od]
+    refs = []
+    for i, (wt, bb) in enumerate(zip(ws, bs)):
+        yi = y[..., i * 192:(i + 1) * 192].float().permute(0, 3, 1, 2)
+        wq = wt.to(dt).float() if dt == torch.bfloat16 else wt
+        refs.append(F.conv2d(yi, wq, bb, 1, 1))
+    ref = torch.cat(refs, 1)
+    rows = torch.cat([wt.permute(0, 2, 3, 1).reshape(wt.shape[0], -1) for wt in ws], 0).contiguous()   # [rows][tap][c]
+    out = ops.head_top_conv(y.cuda(), od, rows.cuda(), torch.cat(bs).cuda())
+    assert rel_l2(out.cpu().numpy(), ref.numpy()) < (1e-5 if dt == torch.float32 else 5e-3)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cfg", [(3, 100, 100, 16, 32), (2, 100, 37, 16, 32), (2, 150, 400, 12, 64), (1, 17, 65, 4, 64)])
+def test_attention_matches_sdpa(dt, cfg):
+    """F.scaled_dot_product_attention with an additive key-pad mask (models/transformer.py:126-134)."""
+    _lib, ops = _ops()
+    b, lt, ls, heads, hd = cfg
+    g = torch.Generator().manual_seed(17)
+    d = heads * hd
+    q = torch.randn(b, lt, d, generator=g).to(dt); k = torch.randn(b, ls, d, generator=g).to(dt); v = torch.randn(b, ls, d, generator=g).to(dt)
+    mask = torch.zeros(b, ls)
+    for i in range(b):
+        mask[i, ls - 1 - 3 * i:] = float("-inf")
+    def split(t, l):
+        return t.float().view(b, l, heads, hd).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(split(q, lt), split(k, ls), split(v, ls), attn_mask=mask.view(b, 1, 1, ls))
+    ref = ref.transpose(1, 2).reshape(b, lt, d)
+    out = ops.attention(q.cuda(), k.cuda(), v.cuda(), heads, mask.cuda())
+    assert rel_l2(out.float().cpu().numpy(), ref.numpy()) < (1e-5 if dt == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_upsample2x_align_corners(dt):
     _lib, ops = _ops()
     g = torch.Generator().manual_seed(6)
