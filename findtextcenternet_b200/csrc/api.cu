@@ -16,6 +16,11 @@ static std::atomic<int64_t> g_launches{0};
 
 void set_error(const std::string& msg) { g_err = msg; }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FTC_NO_PDL"); v = (e && atoi(e) != 0) ? 0 : 1; }
+  return v;
+}
 
 std::vector<uint32_t> make_ktab(int CA, int CB, int ksize, int* Kout) {
   int taps = ksize * ksize;

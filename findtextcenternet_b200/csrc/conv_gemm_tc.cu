@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();
   const int G = p.G;
   const int hw = p.Ho * p.Wo;
   const uint32_t hint_ns = (p.tc.flags & 1) ? 100000u : 0u;          // experiment knobs (FTC_TC_FLAGS)
@@ -463,7 +465,7 @@ int conv_gemm_tc(const ConvGemmParams& p_in, cudaStream_t stream) {
       FTC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<SE_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_done = true;                                                                                            \
     }                                                                                                              \
-    conv_gemm_tc_kernel<SE_, MT_><<<grid, TC_THREADS, smem, stream>>>(p, num_tiles);                               \
+    FTC_CHECK_CUDA(launch_pdl(conv_gemm_tc_kernel<SE_, MT_>, dim3(grid), dim3(TC_THREADS), smem, stream, p, num_tiles)); \
   } while (0)
   if (se) { if (p.tc.MT == 2) TC_LAUNCH(true, 2); else TC_LAUNCH(true, 1); }
   else { if (p.tc.MT == 2) TC_LAUNCH(false, 2); else TC_LAUNCH(false, 1); }

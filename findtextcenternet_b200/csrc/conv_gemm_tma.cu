@@ -160,6 +160,8 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();                 // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
   const int hw = p.Ho * p.Wo;
   const int NKG = L.NKG, nsub = L.nsub;
   int t_first = blockIdx.x, t_last = num_tiles, t_step = gridDim.x;
@@ -809,7 +811,7 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
                                           227 * 1024));                                                               \
       attr_done = true;                                                                                               \
     }                                                                                                                 \
-    conv_gemm_tma_kernel<SE_, MT_, HALO_><<<grid, TM_THREADS, smem, stream>>>(p, tmA, tmB, tmOut, tmRes, L, num_tiles); \
+    FTC_CHECK_CUDA(launch_pdl(conv_gemm_tma_kernel<SE_, MT_, HALO_>, dim3(grid), dim3(TM_THREADS), smem, stream, p, tmA, tmB, tmOut, tmRes, L, num_tiles)); \
   } while (0)
   if (halo) { if (MT == 2) TMA_LAUNCH(false, 2, true); else TMA_LAUNCH(false, 1, true); }
   else if (se) { if (MT == 2) TMA_LAUNCH(true, 2, false); else TMA_LAUNCH(true, 1, false); }

@@ -288,6 +288,8 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmIn)) : "memory");
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t strip_bytes = (uint32_t)(strip_elems * sizeof(T));
   auto prefetch = [&](int s) {
     if (tid == 0) {
@@ -580,7 +582,7 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
   do {                                                                                                                 \
     static bool done = false;                                                                                          \
     if (!done) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<TT, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; } \
-    dwconv3x3_strip_kernel<TT, TH><<<grid, threads, smem, s>>>(tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre); \
+    FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre)); \
   } while (0)
   // the mma.sync variant is correct but measured SLOWER on B200 (0.26 vs 0.17 ms at 48x48x1536, B=32: its BN/SiLU/SE
   // epilogue and fragment exchange cost as many issue slots as the FMAs they replace); kept behind FTC_DW_MMA=1
@@ -612,6 +614,8 @@ __global__ void __launch_bounds__(256) se_fc2_hid_kernel(const float* __restrict
                                                          const float* __restrict__ b2) {
   __shared__ float sh[256];
   const int b = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int k = threadIdx.x; k < S; k += blockDim.x) sh[k] = silu_precise(hid_pre[(int64_t)b * S + k] + b1[k]);
   if (blockIdx.x == 0)
     for (int k = threadIdx.x; k < clear_n; k += blockDim.x) hid_clear[(int64_t)b * clear_n + k] = 0.f;
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(256) se_fc2_hid_kernel(const float* __restrict
 int se_fc2_hid(const float* hid_pre, float* hid_clear, int clear_n, float* scale_out, int B, int C, int S, const float* b1,
                const float* w2t, const float* b2, cudaStream_t s) {
   FTC_REQUIRE(S <= 256 && clear_n <= 256, "SE: squeeze <= 256");
-  se_fc2_hid_kernel<<<dim3(ceil_div(C, 256), B), 256, 0, s>>>(hid_pre, hid_clear, scale_out, C, S, clear_n, b1, w2t, b2);
+  FTC_CHECK_CUDA(launch_pdl(se_fc2_hid_kernel, dim3(ceil_div(C, 256), B), dim3(256), 0, s, hid_pre, hid_clear, scale_out, C, S, clear_n, b1, w2t, b2));
   FTC_POST_LAUNCH();
   return 0;
 }

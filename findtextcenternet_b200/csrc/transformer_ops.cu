@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_vec_kernel(const bf16* __r
                                                                  int M, float eps) {
   constexpr int D = NV * 256;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (warp >= M) return;
   const bf16* ip = in + (int64_t)warp * D + lane * 8;
   float x[NV][8];
@@ -330,10 +332,10 @@ int layernorm_rows(const void* in, void* out, int dtype, const float* gamma, con
   const bool vec_ok = dtype == DT_BF16 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
                       ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
   if (dtype == DT_F32) layernorm_rows_kernel<float><<<grid, 256, 0, s>>>((const float*)in, (float*)out, gamma, beta, M, d, eps);
-  else if (vec_ok && d == 256) layernorm_rows_vec_kernel<1><<<grid, 256, 0, s>>>((const bf16*)in, (bf16*)out, gamma, beta, M, eps);
-  else if (vec_ok && d == 512) layernorm_rows_vec_kernel<2><<<grid, 256, 0, s>>>((const bf16*)in, (bf16*)out, gamma, beta, M, eps);
-  else if (vec_ok && d == 768) layernorm_rows_vec_kernel<3><<<grid, 256, 0, s>>>((const bf16*)in, (bf16*)out, gamma, beta, M, eps);
-  else if (vec_ok && d == 1024) layernorm_rows_vec_kernel<4><<<grid, 256, 0, s>>>((const bf16*)in, (bf16*)out, gamma, beta, M, eps);
+  else if (vec_ok && d == 256) FTC_CHECK_CUDA(launch_pdl(layernorm_rows_vec_kernel<1>, dim3(grid), dim3(256), 0, s, (const bf16*)in, (bf16*)out, gamma, beta, M, eps));
+  else if (vec_ok && d == 512) FTC_CHECK_CUDA(launch_pdl(layernorm_rows_vec_kernel<2>, dim3(grid), dim3(256), 0, s, (const bf16*)in, (bf16*)out, gamma, beta, M, eps));
+  else if (vec_ok && d == 768) FTC_CHECK_CUDA(launch_pdl(layernorm_rows_vec_kernel<3>, dim3(grid), dim3(256), 0, s, (const bf16*)in, (bf16*)out, gamma, beta, M, eps));
+  else if (vec_ok && d == 1024) FTC_CHECK_CUDA(launch_pdl(layernorm_rows_vec_kernel<4>, dim3(grid), dim3(256), 0, s, (const bf16*)in, (bf16*)out, gamma, beta, M, eps));
   else layernorm_rows_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, (bf16*)out, gamma, beta, M, d, eps);
   FTC_POST_LAUNCH();
   return 0;
@@ -375,6 +377,8 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restri
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64 + warp * 16;
   const bf16* kb = k + (int64_t)b * Ls * kv_stride + k_off + h * HD;
   const bf16* vb = v + (int64_t)b * Ls * kv_stride + v_off + h * HD;
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int PPR = HD / 8;                      // 16-byte pieces per row
   for (int i = tid; i < Lp * PPR; i += 128) {
     const int j = i / PPR, pc = i - j * PPR;
@@ -520,9 +524,8 @@ static int launch_attention_mma(const void* q, int q_stride, int q_off, const vo
     attr_done = true;
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
-  attention_mma_kernel<HD><<<dim3((Lt + 63) / 64, heads, B), 128, smem, s>>>(
-      (const bf16*)q, q_stride, q_off, (const bf16*)k, (const bf16*)v, kv_stride, k_off, v_off, mask, (bf16*)out, out_stride, Lt, Ls,
-      scale_log2);
+  FTC_CHECK_CUDA(launch_pdl(attention_mma_kernel<HD>, dim3((Lt + 63) / 64, heads, B), dim3(128), smem, s, (const bf16*)q, q_stride, q_off,
+                            (const bf16*)k, (const bf16*)v, kv_stride, k_off, v_off, mask, (bf16*)out, out_stride, Lt, Ls, scale_log2));
   FTC_POST_LAUNCH();
   return 0;
 }
