@@ -144,6 +144,72 @@ int ftc_mask_predict_step(const float* logits, int ld, int head_ld, const int64_
   return mask_predict_step(logits, ld, head_ld, dec_in, ids, prob, next_in, flags, rows, (cudaStream_t)stream);
 }
 
+int ftc_debug_set_gemm_tuning(int mt, int flags, int box_depth, int plan_bn, int no_bstat) {
+  GemmTuning& t = gemm_tuning();
+  t.mt = mt; t.flags = flags & 0xFFFFFF; t.box_depth = box_depth; t.plan_bn = plan_bn; t.no_bstat = no_bstat & 1;
+  t.epi8 = (no_bstat >> 1) & 1;   // bit 1 of no_bstat: keep 8 epilogue warps
+  return 0;
+}
+
+// timing harness for one tcgen05 1x1-conv / linear shape (debug; allocates and frees its own buffers):
+// out[M,N] = act(x[M,K] (* se[b,K]) W^T * scale + bias) (+ res); M = batch * hw rows
+int ftc_debug_bench_gemm(int batch, int hw, int k, int n, int act, int use_se, int use_res, int iters, float* ms_out) {
+  FTC_REQUIRE(batch > 0 && hw > 0 && k % 8 == 0 && n > 0 && iters > 0 && ms_out, "bad argument");
+  const int M = batch * hw;
+  void *x = nullptr, *out = nullptr, *res = nullptr, *wp = nullptr, *flush = nullptr;
+  float *wf = nullptr, *sc = nullptr, *bi = nullptr, *se = nullptr;
+  const size_t flush_bytes = 256u << 20;
+  FTC_CHECK_CUDA(cudaMalloc(&x, (size_t)M * k * 2)); FTC_CHECK_CUDA(cudaMalloc(&out, (size_t)M * n * 2));
+  FTC_CHECK_CUDA(cudaMalloc(&res, (size_t)M * n * 2)); FTC_CHECK_CUDA(cudaMalloc(&wf, (size_t)n * k * 4));
+  FTC_CHECK_CUDA(cudaMalloc(&sc, (size_t)n * 4)); FTC_CHECK_CUDA(cudaMalloc(&bi, (size_t)n * 4));
+  FTC_CHECK_CUDA(cudaMalloc(&se, (size_t)batch * k * 4)); FTC_CHECK_CUDA(cudaMalloc(&flush, flush_bytes));
+  FTC_CHECK_CUDA(cudaMemset(x, 0x3c, (size_t)M * k * 2)); FTC_CHECK_CUDA(cudaMemset(res, 0x3c, (size_t)M * n * 2));
+  FTC_CHECK_CUDA(cudaMemset(wf, 0x3b, (size_t)n * k * 4)); FTC_CHECK_CUDA(cudaMemset(sc, 0x3c, (size_t)n * 4));
+  FTC_CHECK_CUDA(cudaMemset(bi, 0x3c, (size_t)n * 4)); FTC_CHECK_CUDA(cudaMemset(se, 0x3c, (size_t)batch * k * 4));
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = batch; p.H = hw; p.W = 1; p.stride = 1; p.pad = 0; p.Ho = hw; p.Wo = 1;
+  p.M = M; p.N = n; p.G = 1;
+  p.srcA = x; p.a_pix_stride = k; p.CA = k; p.CB = 0;
+  int K = 0;
+  std::vector<uint32_t> kt = make_ktab(k, 0, 1, &K);
+  p.K = K;
+  ConvTcPlan plan;
+  int rc = conv_gemm_tc_plan(p, &plan, true);
+  if (rc) return rc;
+  p.K = plan.NKB * KBLOCK;
+  const size_t wbytes = conv_tc_weight_bytes(plan, 1);
+  uint32_t* ktd = nullptr;
+  FTC_CHECK_CUDA(cudaMalloc(&wp, wbytes)); FTC_CHECK_CUDA(cudaMalloc((void**)&ktd, kt.size() * 4));
+  FTC_CHECK_CUDA(cudaMemset(wp, 0, wbytes));
+  FTC_CHECK_CUDA(cudaMemcpy(ktd, kt.data(), kt.size() * 4, cudaMemcpyHostToDevice));
+  rc = pack_conv_weight_tc(wp, wf, n, k, 1, 1, 0, k, 0, p.K, 0, plan.BN, nullptr, 0, 0);
+  if (rc) return rc;
+  p.ktab = ktd; p.w = wp; p.scale = sc; p.bias_tab = bi; p.ncase = 1; p.act = act;
+  p.a_scale = use_se ? se : nullptr; p.a_scale_stride = k;
+  p.res1 = use_res ? res : nullptr; p.res1_stride = n;
+  p.out = out; p.out_layout = OUT_NHWC; p.out_stride = n; p.out_ch_base[0] = 0; p.n_valid[0] = n;
+  p.dtype = DT_BF16; p.tc = plan;
+  cudaEvent_t e0, e1;
+  FTC_CHECK_CUDA(cudaEventCreate(&e0)); FTC_CHECK_CUDA(cudaEventCreate(&e1));
+  float total = 0.f;
+  for (int it = -2; it < iters && rc == 0; ++it) {
+    FTC_CHECK_CUDA(cudaMemsetAsync(flush, it & 1, flush_bytes, 0));    // evict: the real producer's output is larger than L2
+    FTC_CHECK_CUDA(cudaEventRecord(e0, 0));
+    rc = conv_gemm_tc(p, 0);
+    FTC_CHECK_CUDA(cudaEventRecord(e1, 0));
+    FTC_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    FTC_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (it >= 0) total += ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(x); cudaFree(out); cudaFree(res); cudaFree(wf); cudaFree(sc); cudaFree(bi); cudaFree(se); cudaFree(flush); cudaFree(wp); cudaFree(ktd);
+  if (rc) return rc;
+  *ms_out = total / iters;
+  return 0;
+}
+
 int ftc_debug_set_trace(void* dev_u64_4096) {
   conv_gemm_tc_set_trace((unsigned long long*)dev_u64_4096);
   return 0;

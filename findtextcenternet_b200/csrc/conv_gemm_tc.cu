@@ -384,6 +384,7 @@ int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan, bool allow_tma)
     if (best_pad < 0 || pad < best_pad) { best_pad = pad; best_bn = bn; best_nt = nt; }
   }
   FTC_REQUIRE(best_bn > 0, "no N tiling");
+  if (gemm_tuning().plan_bn > 0 && p.N % gemm_tuning().plan_bn == 0) { best_bn = gemm_tuning().plan_bn; best_nt = p.N / best_bn; }
   plan->BN = best_bn;
   plan->NT = best_nt;
   plan->NKB = p.K / KBLOCK;
@@ -412,6 +413,16 @@ int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan, bool allow_tma)
 }
 
 void conv_gemm_tc_set_trace(unsigned long long* dev_ptr) { g_trace = dev_ptr; }
+
+GemmTuning& gemm_tuning() {
+  static GemmTuning t = [] {
+    GemmTuning v{0, 0, 0, 0, 0, 0};
+    const char* e = getenv("FTC_TMA_MT"); v.mt = e ? atoi(e) : 0;
+    e = getenv("FTC_TMA_FLAGS"); v.flags = e ? atoi(e) : 0;     // ablations (results are garbage): 32 no stores, 64 no SE
+    return v;                                                   // scaling, 128 no residual loads, 256 no epilogue at all
+  }();
+  return t;
+}
 
 size_t conv_tc_weight_bytes(const ConvTcPlan& plan, int G) {
   return (size_t)G * plan.NT * plan.NKB * plan.BN * 128;

@@ -28,7 +28,8 @@ constexpr int TM_TMA_WARP = 8, TM_MMA_WARP = 9, TM_SCALE_WARP0 = 10, TM_SCALE_WA
 constexpr int TM_THREADS = (TM_EPI_WARPS + 2 + TM_SCALE_WARPS) * 32;   // 448
 constexpr int TM_STAGED_FLOATS = 10 * 256;     // per-tile scale[BN] + bias[ncase<=9][BN]
 constexpr int TM_MAX_SLOTS = 8;
-constexpr int TM_NBARS = 5 * TM_MAX_SLOTS + 4 + 2 * TM_EPI_WARPS;   // + per-warp residual ring (2 deep)
+constexpr int TM_MAX_EPI_WARPS = TM_EPI_WARPS + TM_SCALE_WARPS;     // without SE the scaler warps join the staged epilogue
+constexpr int TM_NBARS = 5 * TM_MAX_SLOTS + 4 + 2 * TM_MAX_EPI_WARPS;   // + per-warp residual ring (2 deep)
 constexpr uint32_t TM_BOX_BYTES = 32 * 64;   // one staged epilogue box: 32 rows x 32 bf16 channels
 constexpr uint32_t TM_SUB_BYTES = TM_BM * 128;  // one 128-row sub-tile of A = 16 KB
 
@@ -45,6 +46,7 @@ struct TmaLaunch {
   int bstat;              // weight-stationary schedule: a CTA walks a CONTIGUOUS range of tiles in (group, n-tile)-major
                           // order and keeps the whole [BN x K] weight tile resident in its nB = NKB slots across m-tiles
   int m_tiles;
+  int n_epi;              // epilogue warps: 8, or 12 when the (idle) scaler warps join the staged epilogue
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -118,7 +120,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   const uint32_t ring_bytes = (uint32_t)L.nA * L.a_slot_bytes + (uint32_t)L.nB * b_bytes;
   // staged epilogue: per epilogue warp two output boxes (+ two residual boxes), 2 KB each, right behind the rings
   const uint32_t box_base = sbase + ring_bytes;
-  const uint32_t box_bytes = L.staged ? (uint32_t)TM_EPI_WARPS * (L.res_tma ? 2u : 1u) * (uint32_t)L.box_depth * TM_BOX_BYTES : 0u;
+  const uint32_t box_bytes = L.staged ? (uint32_t)L.n_epi * (L.res_tma ? 2u : 1u) * (uint32_t)L.box_depth * TM_BOX_BYTES : 0u;
   const uint32_t bar0 = box_base + box_bytes;
   auto a_full = [&](int s) { return bar0 + 8u * s; };
   auto a_empty = [&](int s) { return bar0 + 8u * (TM_MAX_SLOTS + s); };
@@ -147,8 +149,8 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         mbar_init(a_raw(s), 1);
       }
       for (int s = 0; s < L.nB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TM_EPI_WARPS); }
-      for (int w = 0; w < TM_EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (uint32_t)L.n_epi); }
+      for (int w = 0; w < TM_MAX_EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -198,11 +200,14 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           }
           mbar_wait(a_empty(as), aph ^ 1u);
           const uint32_t bar = SE ? a_raw(as) : a_full(as);
-          mbar_arrive_expect_tx(bar, L.a_slot_bytes);
           const CUtensorMap* tm = srcb ? &tmB : &tmA;
           const int c = (srcb ? p.b_ch_off + tc.g * p.b_group_stride : p.a_ch_off) + chunk * 64;
-          if (HALO) tma_load_4d(a_ring + (uint32_t)as * L.a_slot_bytes, tm, c, tc.x0 + dx - 1, tc.y0 - 1, tc.b, bar);
-          else tma_load_4d(a_ring + (uint32_t)as * L.a_slot_bytes, tm, c, tc.m0, 0, 0, bar);
+          if FTC_ABL(512) mbar_arrive(bar);                  // ablation: no operand-A traffic
+          else {
+            mbar_arrive_expect_tx(bar, L.a_slot_bytes);
+            if (HALO) tma_load_4d(a_ring + (uint32_t)as * L.a_slot_bytes, tm, c, tc.x0 + dx - 1, tc.y0 - 1, tc.b, bar);
+            else tma_load_4d(a_ring + (uint32_t)as * L.a_slot_bytes, tm, c, tc.m0, 0, 0, bar);
+          }
           as = (as + 1 == L.nA) ? 0 : as + 1;
           aph ^= (as == 0) ? 1u : 0u;
           for (int sub = 0; sub < nsub && loadB; ++sub, ++kb) {
@@ -250,6 +255,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row: +2 in 16-byte units
 #pragma unroll
               for (int h = 0; h < MT; ++h)
+                if (!FTC_ABL(4096))                       // ablation: no MMAs (commits still fire)
                 umma_f16(d_tmem + (uint32_t)h * (uint32_t)BN, umma_desc_sw128(a_sub + (uint32_t)h * TM_SUB_BYTES) + (uint64_t)(2 * k),
                          bdesc + (uint64_t)(2 * k), idesc, (k == 0 && h < MT) ? accum : 1u);
               accum = 1u;
@@ -266,7 +272,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       }
     }
     __syncwarp();
-  } else if (warp >= TM_SCALE_WARP0) {
+  } else if (warp >= TM_SCALE_WARP0 && (SE || L.n_epi <= TM_EPI_WARPS)) {
     // ------------------------------------------------------------------ SE scalers (rows mode only)
     if (SE) {
       const int t = threadIdx.x - TM_SCALE_WARP0 * 32;   // 0..127
@@ -304,7 +310,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             const uint4 s0 = *reinterpret_cast<const uint4*>(sc_tab + c);
             const uint4 s1 = *reinterpret_cast<const uint4*>(sc_tab + CAp + c);
             mbar_wait(a_raw(as), aph);
-            if (!(p.tc.flags & 64)) {
+            if (!FTC_ABL(64)) {
               const uint32_t a_dst = a_ring + (uint32_t)as * L.a_slot_bytes + row_off;
 #pragma unroll
               for (int i = 0; i < ROWS; ++i) {
@@ -339,7 +345,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         for (int kg = 0; kg < NKG; ++kg) {
           mbar_wait(a_raw(as), aph);
           const int c = kg * 64 + j * 8;
-          if (c < p.CA && !(p.tc.flags & 64)) {
+          if (c < p.CA && !FTC_ABL(64)) {
             const uint32_t a_dst = a_ring + (uint32_t)as * L.a_slot_bytes + row_off;
 #pragma unroll
             for (int i = 0; i < ROWS; ++i) {
@@ -367,9 +373,12 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps: 4 lane quarters x 2 halves)
-    const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int half = warp >> 2;                // MT == 1: even / odd 16-column chunks; MT == 2: which 128-row sub-tile
-    const int etid = threadIdx.x;              // 0..255
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read (hardware: warp id % 4)
+    const int half = warp >> 2;                // direct path: MT == 1: even / odd 16-column chunks; MT == 2: 128-row sub-tile
+    const int ewarp = warp < TM_EPI_WARPS ? warp : warp - 2;       // dense epilogue-warp index (warps 10-13 -> 8-11)
+    const int ew = warp < TM_EPI_WARPS ? (warp >> 2) : 2;          // index among the warps that share this lane quarter
+    const int etid = ewarp * 32 + lane;
+    const int n_ethreads = L.n_epi * 32;
     const int row = (MT == 2 ? half * TM_BM : 0) + q * 32 + lane;
     const bf16* res1 = reinterpret_cast<const bf16*>(p.res1);
     const bf16* res2 = reinterpret_cast<const bf16*>(p.res2);
@@ -382,67 +391,83 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       // banks) and leaves through ONE TMA tensor store, which writes whole 64-byte row segments (the direct path wrote
       // 32 scattered 16-byte pieces per store instruction and was LSU-bound).  The residual tile comes in the same way
       // through a two-deep per-warp TMA ring that is issued before the accumulator is waited for.
+      // Work items: (128-row sub-tile h, 32-channel box i) of the tile; the 2 (with SE scalers busy) or 3 warps that share a
+      // TMEM lane quarter take them round-robin.
       const uint32_t depth = (uint32_t)L.box_depth, dmask = depth - 1u, dshift = depth >> 1;   // depth 1 or 2
-      const uint32_t my_boxes = box_base + (uint32_t)warp * (L.res_tma ? 2u : 1u) * depth * TM_BOX_BYTES;
+      const uint32_t my_boxes = box_base + (uint32_t)ewarp * (L.res_tma ? 2u : 1u) * depth * TM_BOX_BYTES;
       const uint32_t out_box0 = my_boxes, res_box0 = my_boxes + depth * TM_BOX_BYTES;
       const uint32_t sw = (uint32_t)((lane >> 1) & 3);                 // SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3
       const uint32_t row_b = (uint32_t)lane * 64u;
       // a chunk = one output box of 32 channels = 32 accumulator columns (64 for SwiGLU, which gates column pairs)
       const int cw = p.act == ACT_SWIGLU ? 64 : 32;
-      const int cstart = MT == 1 ? half * cw : 0, cstep = MT == 1 ? 2 * cw : cw;
-      const int nchunk = BN > cstart ? (BN - cstart + cstep - 1) / cstep : 0;
+      const int per_sub = BN / cw, n_items = MT * per_sub, n_share = L.n_epi >> 2;
       const bool res1_direct = p.res1 != nullptr && !L.res_tma;
       uint32_t n_out = 0, n_res_issued = 0, n_res_used = 0;
       // SiLU as h + h*tanh(h), h = x/2: the 1/2 is folded into the staged BN scale / bias (exact: a power of two)
       const float act_pre = p.act == ACT_SILU ? 0.5f : 1.f;
+      int staged_gn = -1;
       for (int tile = t_first; tile < t_last; tile += t_step, ++titer) {
         const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
         const uint32_t buf = L.nbuf == 2 ? (titer & 1u) : 0u;
         const uint32_t use = L.nbuf == 2 ? (titer >> 1) : titer;
-        // box coordinates of this warp's 32 rows
-        int k1, k2, k3;
-        if (HALO) { k1 = tc.x0; k2 = tc.y0 + (MT == 2 ? half * 8 : 0) + q * 2; k3 = tc.b; }
-        else { k1 = tc.m0 + (MT == 2 ? half * TM_BM : 0) + q * 32; k2 = 0; k3 = 0; }
         const int ch_out = p.out_ch_base[tc.g] + (p.act == ACT_SWIGLU ? (tc.nt * BN) >> 1 : tc.nt * BN);
-        const int m_row = (HALO ? 0 : tc.m0) + row;       // rows mode: this lane's output row (direct residual loads)
         const int ch_res = tc.g * p.N + tc.nt * BN;
-        auto issue_res = [&](int i) {
+        // box coordinates of the 32 rows (q, sub-tile h) of this warp
+        auto box_k1 = [&](int h) { return HALO ? tc.x0 : tc.m0 + h * TM_BM + q * 32; };
+        auto box_k2 = [&](int h) { return HALO ? tc.y0 + h * 8 + q * 2 : 0; };
+        const int k3 = HALO ? tc.b : 0;
+        auto issue_res = [&](int it) {
+          const int h = it / per_sub, c0 = (it - h * per_sub) * cw;
           const uint32_t slot = n_res_issued & dmask;
-          mbar_arrive_expect_tx(res_bar(warp, slot), TM_BOX_BYTES);
-          tma_load_4d(res_box0 + slot * TM_BOX_BYTES, &tmRes, ch_res + cstart + i * cstep, k1, k2, k3, res_bar(warp, slot));
+          mbar_arrive_expect_tx(res_bar(ewarp, slot), TM_BOX_BYTES);
+          tma_load_4d(res_box0 + slot * TM_BOX_BYTES, &tmRes, ch_res + c0, box_k1(h), box_k2(h), k3, res_bar(ewarp, slot));
           ++n_res_issued;
         };
         if (L.res_tma && lane == 0) {
-          if (nchunk > 0) issue_res(0);
-          if (nchunk > 1 && depth == 2) issue_res(1);
+          if (ew < n_items) issue_res(ew);
+          if (ew + n_share < n_items && depth == 2) issue_res(ew + n_share);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(TM_EPI_THREADS) : "memory");
-        {
+        // per-column scale / bias of this (group, n-tile): staged once and kept while consecutive tiles share it (always
+        // under the weight-stationary schedule; whenever NT * G == 1)
+        if (tc.g * NT + tc.nt != staged_gn) {
+          staged_gn = tc.g * NT + tc.nt;
+          asm volatile("bar.sync 1, %0;" ::"r"(n_ethreads) : "memory");
           const int ncol0 = tc.nt * BN;
-          for (int c = etid; c < BN; c += TM_EPI_THREADS) {
+          for (int c = etid; c < BN; c += n_ethreads) {
             const int n = ncol0 + c;
             sscale[c] = act_pre * ((p.scale && n < p.N) ? __ldg(p.scale + (int64_t)tc.g * p.N + n) : 1.f);
           }
-          for (int c = etid; c < p.ncase * BN; c += TM_EPI_THREADS) {
+          for (int c = etid; c < p.ncase * BN; c += n_ethreads) {
             const int cs_ = c / BN, cc = c - cs_ * BN;
             const int n = ncol0 + cc;
             sbias[c] = act_pre * ((p.bias_tab && n < p.N) ? __ldg(p.bias_tab + ((int64_t)cs_ * G + tc.g) * p.N + n) : 0.f);
           }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(TM_EPI_THREADS) : "memory");
-        int cs = 0;
-        if (p.ncase == 9) {
-          const int oy = tc.y0 + (row >> 4), ox = tc.x0 + (row & 15);     // ncase 9 only occurs on halo (3x3) tiles
-          cs = (oy == 0 ? 0 : (oy == p.Ho - 1 ? 2 : 1)) * 3 + (ox == 0 ? 0 : (ox == p.Wo - 1 ? 2 : 1));
+          asm volatile("bar.sync 1, %0;" ::"r"(n_ethreads) : "memory");
         }
         if (lane == 0) mbar_wait(tfull_bar(buf), use & 1u);
         __syncwarp();
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * (uint32_t)MT + (MT == 2 ? (uint32_t)half : 0u)) * (uint32_t)BN;
-        for (int i = 0; i < nchunk; ++i) {
-          const int c0 = cstart + i * cstep;
-          if (tc.nt * BN + c0 >= p.N) break;          // warp-uniform
-          uint32_t raw[32];
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(MT * BN);
+        auto t_item = [&](int it) {                     // TMEM address of an item: sub-tile h at column h * BN, box at c0
+          const int h = it / per_sub;
+          return t_base + (uint32_t)(h * BN + (it - h * per_sub) * cw);
+        };
+        uint32_t raw[32];
+        if (p.act != ACT_SWIGLU && ew < n_items) {
+          __syncwarp();
+          tmem_ld32(t_item(ew), raw);
+        }
+        for (int it = ew; it < n_items; it += n_share) {
+          const int h = it / per_sub, c0 = (it - h * per_sub) * cw;
+          const uint32_t t_addr = t_base + (uint32_t)(h * BN);
+          const int k1 = box_k1(h), k2 = box_k2(h);
+          const int row_t = h * TM_BM + q * 32 + lane;          // this lane's row inside the tile
+          const int m_row = (HALO ? 0 : tc.m0) + row_t;         // rows mode: output row (direct residual loads)
+          int cs = 0;
+          if (p.ncase == 9) {
+            const int oy = tc.y0 + (row_t >> 4), ox = tc.x0 + (row_t & 15);   // ncase 9 only occurs on halo (3x3) tiles
+            cs = (oy == 0 ? 0 : (oy == p.Ho - 1 ? 2 : 1)) * 3 + (ox == 0 ? 0 : (ox == p.Wo - 1 ? 2 : 1));
+          }
           f32x2 vv[16];
           if (p.act == ACT_SWIGLU) {
             // interleaved (x1, xg) column pairs -> x1 * silu(xg): 64 accumulator columns give this box's 32 outputs
@@ -465,8 +490,9 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
               }
             }
           } else {
-          __syncwarp();
-          tmem_ld32(t_addr + (uint32_t)c0, raw);
+          // software-pipelined TMEM reads: chunk i was requested one iteration ago (or before the loop); chunk i+1 is
+          // requested as soon as the scale/bias FMAs have consumed the registers, so its latency hides behind the
+          // activation / pack / store work of chunk i (the TMEM read port moves only 64 B/clk per SM)
           tmem_ld_wait();
           // packed fp32 math (FFMA2): the epilogue warps are issue-bound on the short-K convs
           {
@@ -479,13 +505,20 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
               vv[2 * e + 1] = ffma2(pk2(__uint_as_float(raw[4 * e + 2]), __uint_as_float(raw[4 * e + 3])), sc.y, bi.y);
             }
           }
+          if (it + n_share < n_items) {
+            __syncwarp();
+            tmem_ld32(t_item(it + n_share), raw);
+          }
           if (p.act == ACT_SILU) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               float h0, h1, t0, t1;
               upk2(vv[e], h0, h1);
-              asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
-              asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+              if FTC_ABL(8192) { t0 = h0; t1 = h1; }      // ablation: no SFU
+              else {
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+              }
               vv[e] = ffma2(vv[e], pk2(t0, t1), vv[e]);
             }
           } else if (p.act == ACT_GELU) {
@@ -523,7 +556,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           }
           if (L.res_tma) {
             const uint32_t slot = n_res_used & dmask;
-            mbar_wait(res_bar(warp, slot), (n_res_used >> dshift) & 1u);
+            mbar_wait(res_bar(ewarp, slot), (n_res_used >> dshift) & 1u);
             const uint32_t rb_ = res_box0 + slot * TM_BOX_BYTES + row_b;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -536,9 +569,9 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             }
             ++n_res_used;
             __syncwarp();                               // every lane has read the box before it is refilled
-            if (lane == 0 && i + (int)depth < nchunk) issue_res(i + (int)depth);
+            if (lane == 0 && it + (int)depth * n_share < n_items) issue_res(it + (int)depth * n_share);
           }
-          if (!(p.tc.flags & 32)) {
+          if (!FTC_ABL(32)) {
             const uint32_t ob = out_box0 + (n_out & dmask) * TM_BOX_BYTES;
             if (lane == 0) {                            // the store that last read this box is done
               if (depth == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
@@ -552,11 +585,13 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
               for (int e = 0; e < 4; ++e) { float lo, hi; upk2(vv[4 * j + e], lo, hi); h[e] = __floats2bfloat162_rn(lo, hi); }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ob + row_b + (((uint32_t)j ^ sw) << 4)), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_4d(&tmOut, ob, ch_out + (p.act == ACT_SWIGLU ? c0 >> 1 : c0), k1, k2, k3);
-              bulk_commit();
+            if (!FTC_ABL(16384)) {                  // ablation bit: keep the st.shared, drop fence + TMA store
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&tmOut, ob, ch_out + (p.act == ACT_SWIGLU ? c0 >> 1 : c0), k1, k2, k3);
+                bulk_commit();
+              }
             }
             ++n_out;
           }
@@ -609,7 +644,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       for (int c0 = (MT == 1 ? half * 16 : 0); c0 < BN; c0 += (MT == 1 ? 32 : 16)) {
         const int n0 = tc.nt * BN + c0;
         if (n0 >= p.N) break;                       // warp-uniform
-        if (p.tc.flags & 256) continue;             // ablation: no TMEM reads, no epilogue math
+        if FTC_ABL(256) continue;             // ablation: no TMEM reads, no epilogue math
         uint32_t raw16[16];
         __syncwarp();                               // tcgen05.ld is warp-collective: reconverge first
         tmem_ld16(t_addr + (uint32_t)c0, raw16);
@@ -660,11 +695,7 @@ int encode_map(CUtensorMap* tm, const void* base, uint64_t channels, uint64_t pi
 }  // namespace
 
 int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
-  static int env_mt = -1, env_flags = 0;
-  if (env_mt < 0) {
-    const char* e = getenv("FTC_TMA_MT"); env_mt = e ? atoi(e) : 0;
-    e = getenv("FTC_TMA_FLAGS"); env_flags = e ? atoi(e) : 0;   // ablations (results are garbage): 32 no stores, 64 no SE
-  }                                                             // scaling, 128 no residual loads, 256 no epilogue at all
+  const int env_mt = gemm_tuning().mt, env_flags = gemm_tuning().flags;
   ConvGemmParams p = p_in;
   p.tc.flags = env_flags;
   FTC_REQUIRE(p.dtype == DT_BF16, "tcgen05 path is bf16 only");
@@ -740,7 +771,11 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
   // SE kernels need a third A slot (TMA -> scaler -> MMA hand-off) more than deep epilogue staging: their main loops are
   // long (K >= 768), so single boxes cost nothing there
   L.box_depth = se ? 1 : 2;
-  const size_t box_bytes = L.staged ? (size_t)TM_EPI_WARPS * (L.res_tma ? 2 : 1) * L.box_depth * TM_BOX_BYTES : 0;
+  if (gemm_tuning().box_depth == 1 || gemm_tuning().box_depth == 2) L.box_depth = gemm_tuning().box_depth;
+  // without SE the four scaler warps would idle: they join the staged epilogue (3 instead of 2 warps per TMEM lane quarter;
+  // the epilogue of the short-K convs is latency-bound with 2)
+  L.n_epi = (L.staged && !se && !L.res_tma && !gemm_tuning().epi8) ? TM_MAX_EPI_WARPS : TM_EPI_WARPS;
+  const size_t box_bytes = L.staged ? (size_t)L.n_epi * (L.res_tma ? 2 : 1) * L.box_depth * TM_BOX_BYTES : 0;
   const size_t fixed = 1024 + 8 * TM_NBARS + 16 + TM_STAGED_FLOATS * 4 + 256 + (size_t)L.se_tab * 4 + box_bytes;
   const size_t avail = 227 * 1024 - fixed;
   if (halo) {
@@ -752,7 +787,7 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
     // weight-stationary schedule (short K, many m-tiles per n-tile: the MBConv expand convs): the [BN x K] weight tile
     // stays in shared memory and only activations stream, which removes the dominant L2 -> SM traffic term
     // N*K*(M/tile rows) of these L2-bandwidth-bound GEMMs
-    if (!se && p.tc.NKB <= TM_MAX_SLOTS && !(env_flags & 2048) &&
+    if (!se && p.tc.NKB <= TM_MAX_SLOTS && !(env_flags & 2048) && !gemm_tuning().no_bstat &&
         (size_t)p.tc.NKB * b_bytes + 3 * (size_t)L.a_slot_bytes <= avail && (long)m_tiles * p.tc.NT * p.G >= 4L * g_tma_sms) {
       L.bstat = 1;
       L.m_tiles = m_tiles;

@@ -4,6 +4,14 @@
 #pragma once
 #include "conv_gemm.cuh"
 
+// Ablation bits of ConvTcPlan::flags (FTC_TMA_FLAGS / ftc_debug_set_gemm_tuning) are compiled in only with -DFTC_ABLATION
+// (python -m findtextcenternet_b200.build --ablation): the runtime tests cost ~30 of the 230 instructions of an epilogue chunk.
+#ifdef FTC_ABLATION
+#define FTC_ABL(bit) (p.tc.flags & (bit))
+#else
+#define FTC_ABL(bit) (false)
+#endif
+
 namespace ftc {
 namespace {
 
@@ -146,8 +154,8 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = gelu_tanh3(v[i]);
   }
-  const bool dbg_nostore = (p.tc.flags & 32) && v[0] != 12345.678f;   // ablation: keep the math, drop the stores
-  if (res1 && !(p.tc.flags & 128)) {
+  const bool dbg_nostore = FTC_ABL(32) && v[0] != 12345.678f;   // ablation: keep the math, drop the stores
+  if (res1 && !FTC_ABL(128)) {
     const bf16* rp = res1 + r1row * p.res1_stride + (int64_t)g * p.N + n0;
     if (full16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
       float a[8], c[8];
@@ -159,7 +167,7 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
       for (int i = 0; i < 16; ++i) if (n0 + i < p.N) v[i] += __bfloat162float(rp[i]);
     }
   }
-  if (res2 && !(p.tc.flags & 128)) {
+  if (res2 && !FTC_ABL(128)) {
     const bf16* rp = res2 + (int64_t)m * p.res2_stride + (int64_t)g * p.N + n0;
     if (full16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
       float a[8], c[8];

@@ -149,6 +149,12 @@ int ftc_op_se_fc(float* sum, float* scale_out, float* hid, int batch, int c, int
 /* debug: device buffer of 4096 u64 receiving clock64 stamps of CTA 0 of every following tcgen05 conv launch
  * ([0,1024) MMA full-wait start, [1024,2048) end, [2048,3072) producer empty-wait start, [3072,4096) end); NULL = off */
 int ftc_debug_set_trace(void* dev_u64_4096);
+/* debug / tuning: overrides of the tcgen05 GEMM launch heuristics (0 = automatic): mt 1|2 rows-per-tile/128, flags = ablation
+ * bits, box_depth 1|2, plan_bn = forced n-tile (must divide N), no_bstat = 1 disables the weight-stationary schedule */
+int ftc_debug_set_gemm_tuning(int mt, int flags, int box_depth, int plan_bn, int no_bstat);
+/* debug / tuning: average CUDA-event time (ms, L2 flushed before each run) of one bf16 1x1-conv shape on the tcgen05 path:
+ * out[batch*hw, n] = act(x[batch*hw, k] (* se[batch, k]) W^T * scale + bias) (+ res) */
+int ftc_debug_bench_gemm(int batch, int hw, int k, int n, int act, int use_se, int use_res, int iters, float* ms_out);
 int ftc_op_upsample2x(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream);
 /* MBConv middle (torchvision efficientnet.py:137-149 + ops/misc.py:251-261), stride 1: depthwise 3x3 + BN + SiLU with the SE
  * squeeze and fc1 folded into the same kernel, then fc2 + sigmoid.  hid_pre: fp32 [batch, s], zero on entry, holds the

@@ -1,0 +1,35 @@
+"""Shape sweep of the tcgen05 1x1-conv kernel under tuning overrides (ftc_debug_bench_gemm / ftc_debug_set_gemm_tuning).
+Usage: python tools/bench_gemm.py  -> table of ms and TFLOP/s per (shape, variant)"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from findtextcenternet_b200 import _lib
+lib = _lib.load()
+torch.zeros(1, device="cuda")
+B = 32
+# (name, hw, K, N, act, se, res)
+SHAPES = [("st4 exp", 2304, 192, 768, 1, 0, 0), ("st4 proj", 2304, 768, 192, 0, 1, 1),
+          ("st5 exp", 2304, 256, 1536, 1, 0, 0), ("st5 proj", 2304, 1536, 256, 0, 1, 1),
+          ("st6 exp", 576, 512, 3072, 1, 0, 0), ("st6 proj", 576, 3072, 512, 0, 1, 1),
+          ("st7 exp", 576, 640, 3840, 1, 0, 0), ("st7 proj", 576, 3840, 640, 0, 1, 1),
+          ("st2 proj", 36864, 256, 64, 0, 0, 1), ("st3 proj", 9216, 384, 96, 0, 0, 1)]
+# (name, mt, flags, box_depth, plan_bn, no_bstat)
+VARIANTS = [("auto", 0, 0, 0, 0, 0), ("epi8", 0, 0, 0, 0, 2), ("nobstat", 0, 0, 0, 0, 1), ("nobstat epi8", 0, 0, 0, 0, 3), ("mt2", 2, 0, 0, 0, 0),
+            ("bn128", 0, 0, 0, 128, 0), ("bn128 epi8", 0, 0, 0, 128, 2)]
+if os.environ.get('FTC_BENCH_VARIANTS'):
+    VARIANTS = [v for v in VARIANTS if v[0] in os.environ['FTC_BENCH_VARIANTS'].split(',')]
+if len(sys.argv) > 1:
+    SHAPES = [s for s in SHAPES if any(a in s[0] for a in sys.argv[1:])]
+print(f"{'shape':10s} " + " ".join(f"{v[0]:>22s}" for v in VARIANTS))
+for name, hw, k, n, act, se, res in SHAPES:
+    cells = []
+    for vname, mt, fl, bd, bn, nb in VARIANTS:
+        lib.ftc_debug_set_gemm_tuning(mt, fl, bd, bn, nb)
+        ms = ctypes.c_float(0)
+        rc = lib.ftc_debug_bench_gemm(B, hw, k, n, act, se, res, 10, ctypes.byref(ms))
+        if rc != 0:
+            cells.append(f"{'err':>22s}")
+            continue
+        tf = 2.0 * B * hw * k * n / (ms.value * 1e-3) / 1e12
+        cells.append(f"{ms.value*1e3:15.1f}us {tf:4.0f}T")
+    print(f"{name:10s} " + " ".join(cells), flush=True)
