@@ -1,0 +1,136 @@
+"""Training losses — mirror of the reference ``loss_func.py`` (same names, arguments and result keys) over the fused CUDA
+kernels of csrc/loss_ops.cu.  CUDA tensors only (no CPU fallback).
+
+* ``loss_function(fmask, labelmap, idmap, heatmap, decoder_outputs)``  — loss_func.py:94-177 (train1)
+* ``loss_function3(outputs, labelcode, mask)``                          — loss_func.py:179-213 (train3)
+* ``CoVWeightingLoss``                                                   — loss_func.py:8-72
+* ``heatmap_loss_grad(...)``: d(sum_i alpha_i loss_i)/d heatmap for the eight map losses (the analytic backward of the map part).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+modulo_list = [1091, 1093, 1097]          # util_func.py:5
+MAP_LOSSES = ["keymap_loss", "size_loss", "textline_loss", "separator_loss", "code1_loss", "code2_loss", "code4_loss", "code8_loss"]
+
+
+def _s(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if not t.is_cuda:
+            raise RuntimeError("findtextcenternet_b200.loss_func runs on CUDA tensors only (no CPU fallback)")
+
+
+def heatmap_losses(labelmap: torch.Tensor, idmap: torch.Tensor, heatmap: torch.Tensor) -> torch.Tensor:
+    """fp32[9] on device: the eight map losses in MAP_LOSSES order + weight1_count."""
+    lib = _lib.load()
+    _need_cuda(labelmap, idmap, heatmap)
+    b, c, h, w = heatmap.shape
+    assert c == 9 and labelmap.shape == (b, 5, h, w) and idmap.shape == (b, 2, h, w)
+    hm = heatmap.detach().float().contiguous(); lm = labelmap.float().contiguous(); im = idmap.to(torch.int64).contiguous()
+    out = torch.empty(9, dtype=torch.float32, device=hm.device)
+    scratch = torch.empty(int(lib.ftc_heatmap_loss_scratch_bytes()), dtype=torch.uint8, device=hm.device)
+    with torch.cuda.device(hm.device):
+        _lib.check(lib.ftc_heatmap_loss(hm.data_ptr(), lm.data_ptr(), im.data_ptr(), b, h, w, out.data_ptr(), scratch.data_ptr(), _s(hm)),
+                   "ftc_heatmap_loss")
+    return out
+
+
+def heatmap_loss_grad(labelmap, idmap, heatmap, alphas: torch.Tensor, losses9: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(labelmap, idmap, heatmap)
+    b, c, h, w = heatmap.shape
+    hm = heatmap.detach().float().contiguous(); lm = labelmap.float().contiguous(); im = idmap.to(torch.int64).contiguous()
+    al = alphas.to(device=hm.device, dtype=torch.float32).contiguous()
+    grad = torch.empty_like(hm)
+    with torch.cuda.device(hm.device):
+        _lib.check(lib.ftc_heatmap_loss_grad(hm.data_ptr(), lm.data_ptr(), im.data_ptr(), b, h, w, al.data_ptr(), losses9.data_ptr(),
+                                             grad.data_ptr(), _s(hm)), "ftc_heatmap_loss_grad")
+    return grad
+
+
+def _ce_rows(logits, target, weight, select, count_select) -> torch.Tensor:
+    lib = _lib.load()
+    ls = [l.detach().float() for l in logits]
+    ls = [l if l.stride(-1) == 1 else l.contiguous() for l in ls]
+    rows = ls[0].shape[0]
+    out = torch.zeros(4, dtype=torch.float64, device=ls[0].device)
+    tg = target.to(torch.int64).contiguous()
+    wt = None if weight is None else weight.float().contiguous()
+    se = None if select is None else select.to(torch.uint8).contiguous()
+    cs = None if count_select is None else count_select.to(torch.uint8).contiguous()
+    p = lambda t: None if t is None else t.data_ptr()
+    with torch.cuda.device(out.device):
+        _lib.check(lib.ftc_ce_rows(ls[0].data_ptr(), ls[1].data_ptr(), ls[2].data_ptr(), ls[0].stride(0), ls[1].stride(0), ls[2].stride(0),
+                                   modulo_list[0], modulo_list[1], modulo_list[2], tg.data_ptr(), p(wt), p(se), p(cs), rows, out.data_ptr(),
+                                   _s(out)), "ftc_ce_rows")
+    return out
+
+
+def loss_function(fmask, labelmap, idmap, heatmap, decoder_outputs):
+    """loss_func.py:94-177.  Returns the reference's dict (0-d CUDA tensors)."""
+    _need_cuda(fmask, labelmap, idmap, heatmap, *decoder_outputs)
+    key_th3 = 0.99
+    m9 = heatmap_losses(labelmap, idmap, heatmap)
+    keyvals = labelmap[:, 0].flatten()[fmask].float()
+    target_id = idmap[:, 0].flatten()[fmask]
+    pos = target_id > 0
+    weight3 = torch.clamp_min(keyvals - key_th3, 0.) / (1 - key_th3)
+    o = _ce_rows(decoder_outputs, target_id, weight3, (keyvals > key_th3) & pos, (keyvals == 1) & pos)
+    id_loss = (o[0] / torch.clamp_min(o[1], 1.0)).float()
+    res = {k: m9[i] for i, k in enumerate(MAP_LOSSES)}
+    res["id_loss"] = id_loss
+    res["loss"] = m9[:8].sum() + id_loss
+    res["correct"] = o[2].to(torch.int64)
+    res["total"] = o[3].to(torch.int64)
+    return res
+
+
+def loss_function3(outputs, labelcode, mask):
+    """loss_func.py:179-213: outputs = 3 x [B, L, m_i] logits, labelcode int64 [B, L], mask bool [B, L]."""
+    _need_cuda(labelcode, mask, *outputs)
+    flat = [o.reshape(-1, o.shape[-1]) for o in outputs]
+    m = mask.reshape(-1)
+    o = _ce_rows(flat, labelcode.reshape(-1), None, m, m)
+    return {"loss": (o[0] / o[1]).float(), "correct": o[2].to(torch.int64), "total": o[3].to(torch.int64)}
+
+
+class CoVWeightingLoss(torch.nn.Module):
+    """loss_func.py:8-72 (Multi-Loss Weighting with Coefficient of Variations): Welford statistics of the loss ratios."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        self.device = kwargs.pop("device", "cpu")
+        self.losses = kwargs.pop("losses", [])
+        self.num_losses = len(self.losses)
+        super().__init__(*args, **kwargs)
+        self.current_iter = -1
+        z = lambda: torch.zeros((self.num_losses,), dtype=torch.float32, device=self.device)
+        self.alphas, self.running_mean_L, self.running_mean_l, self.running_S_l = z(), z(), z(), z()
+        self.running_std_l = None
+
+    def forward(self, losses):
+        L = torch.stack([losses[key].detach().to(torch.float32) for key in self.losses])
+        if not self.train:          # (sic) the reference tests the bound method, which is always truthy (loss_func.py:30)
+            return torch.sum(L)
+        self.current_iter += 1
+        L0 = L.clone() if self.current_iter == 0 else self.running_mean_L
+        l = L / L0
+        if self.current_iter <= 1:
+            self.alphas = torch.ones((self.num_losses,), dtype=torch.float32, device=self.device) / self.num_losses
+        else:
+            ls = self.running_std_l / self.running_mean_l
+            self.alphas = ls / torch.sum(ls)
+        mean_param = 0.0 if self.current_iter == 0 else (1. - 1 / (self.current_iter + 1))
+        x_l = l.clone()
+        new_mean_l = mean_param * self.running_mean_l + (1 - mean_param) * x_l
+        self.running_S_l = self.running_S_l + (x_l - self.running_mean_l) * (x_l - new_mean_l)
+        self.running_mean_l = new_mean_l
+        running_variance_l = self.running_S_l / (self.current_iter + 1)
+        self.running_std_l = torch.sqrt(running_variance_l.clamp_min(1e-16))
+        self.running_mean_L = mean_param * self.running_mean_L + (1 - mean_param) * L.clone()
+        return sum(self.alphas[i] * losses[key].to(torch.float32) for i, key in enumerate(self.losses))

@@ -142,3 +142,47 @@ def transformer_inputs(batch: int, enc_len: int, dec_len: int, seed: int = 0):
     dec[msk] = arch.DECODER_MSK
     dec[:, 0] = arch.DECODER_SOT
     return enc, dec, lens
+
+
+def loss_inputs(seed=0, B=2, H=48, W=48, n_sel=96):
+    """Synthetic train1 batch in the style of SURVEY.md 8d config 3 (Gaussian key peaks hitting exactly 1.0, log-size ellipses,
+    code points / 4-bit flags on the same blobs) + random detector / decoder outputs.  Deterministic in `seed`."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    labelmap = torch.zeros(B, 5, H, W)
+    idmap = torch.zeros(B, 2, H, W, dtype=torch.int64)
+    for b in range(B):
+        for k in range(12):
+            cy, cx = int(torch.randint(2, H - 2, (1,), generator=g)), int(torch.randint(2, W - 2, (1,), generator=g))
+            gauss = torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * 1.5 ** 2))
+            labelmap[b, 0] = torch.maximum(labelmap[b, 0], gauss)
+            blob = gauss > 0.5
+            labelmap[b, 1][blob] = float(torch.rand(1, generator=g)) + 1.5
+            labelmap[b, 2][blob] = float(torch.rand(1, generator=g)) + 1.5
+            idmap[b, 0][blob] = 0x3042 + 37 * k + 1000 * b
+            idmap[b, 1][blob] = int(torch.randint(0, 16, (1,), generator=g))
+        labelmap[b, 3] = (torch.rand(H, W, generator=g) > 0.8).float() * torch.rand(H, W, generator=g)
+        labelmap[b, 4] = (torch.rand(H, W, generator=g) > 0.9).float()
+    heatmap = torch.randn(B, 9, H, W, generator=g) * 2.0
+    # fmask as TextDetectorModel.get_fmask does: the n_sel largest key values of the batch (models/detector.py:270-281)
+    flat = labelmap[:, 0].flatten()
+    idx = torch.argsort(flat, descending=True)[:n_sel]
+    fmask = torch.zeros_like(flat, dtype=torch.bool)
+    fmask[idx] = True
+    n = int(fmask.sum())
+    tid = idmap[:, 0].flatten()[fmask]
+    dec = []
+    for m in (1091, 1093, 1097):
+        lg = torch.randn(n, m, generator=g)
+        hit = torch.rand(n, generator=g) < 0.7           # most rows predict their target residue
+        lg[torch.arange(n)[hit], (tid % m)[hit]] += 8.0
+        dec.append(lg)
+    # train3-style batch
+    out3 = [torch.randn(3, 20, m, generator=g) for m in (1091, 1093, 1097)]
+    labelcode = torch.randint(0, 0x3FFFF, (3, 20), generator=g)
+    for o, m in zip(out3, (1091, 1093, 1097)):
+        sel = torch.rand(3, 20, generator=g) < 0.6
+        o[sel] = o[sel].scatter(1, (labelcode % m)[sel][:, None], 9.0)
+    mask3 = torch.rand(3, 20, generator=g) < 0.8
+    return dict(labelmap=labelmap, idmap=idmap, heatmap=heatmap, fmask=fmask, dec0=dec[0], dec1=dec[1], dec2=dec[2],
+                out3_0=out3[0], out3_1=out3[1], out3_2=out3[2], labelcode=labelcode, mask3=mask3)

@@ -133,6 +133,23 @@ int ftc_adamw_sf_step(int n_chunks, const void* chunks, const void* const* ys, c
                       const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, double beta1, double beta2,
                       double bias_correction2, double eps, double weight_decay, double lr, double ckp1, void* stream);
 
+/* ---- train step: losses (loss_func.py) ----
+ * ftc_heatmap_loss: loss_function :94-126 (the map part).  heatmap fp32 [B,9,H,W] logits, labelmap fp32 [B,5,H,W], idmap int64
+ * [B,2,H,W]; losses9 (device fp32[9]) = keymap_loss (focal, x10), size_loss, textline_loss, separator_loss, code1/2/4/8_loss,
+ * weight1_count.  scratch: ftc_heatmap_loss_scratch_bytes().  Deterministic (per-CTA double partials, one-CTA finish).
+ * ftc_heatmap_loss_grad: grad[B,9,H,W] = d(sum_i alpha8[i] * losses9[i]) / d heatmap (alpha8: device fp32[8], e.g. CoV weights).
+ * ftc_ce_rows: three-head residue cross entropy of `rows` rows (loss_function :128-161 on the fmask pixels, loss_function3
+ * :179-213): out4 (device double[4]) = { sum_rows w * (ce0+ce1+ce2), sum_rows w, #rows with all three argmax == target % m,
+ * #rows counted }; w = weight[row] (or 1) where select[row] (or all); hits/rows are counted where count_select[row] (or all). */
+size_t ftc_heatmap_loss_scratch_bytes(void);
+int ftc_heatmap_loss(const float* heatmap, const float* labelmap, const int64_t* idmap, int batch, int h, int w, float* losses9,
+                     void* scratch, void* stream);
+int ftc_heatmap_loss_grad(const float* heatmap, const float* labelmap, const int64_t* idmap, int batch, int h, int w,
+                          const float* alpha8, const float* losses9, float* grad, void* stream);
+int ftc_ce_rows(const float* logits0, const float* logits1, const float* logits2, int ld0, int ld1, int ld2, int m0, int m1, int m2,
+                const int64_t* target, const float* weight, const unsigned char* select, const unsigned char* count_select, int rows,
+                double* out4, void* stream);
+
 /* ---- single ops (unit-test / building-block entry points) ---- */
 /* dense conv (k in {1,3}) or linear as implicit GEMM on NHWC activations.
  * x: [B,H,W,Cin] (dtype), w_oihw: fp32 [Cout,Cin,k,k] (packed on the fly into `wpack`),

@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference)
 on the synthetic checkpoints.  Runs only in the build container (the GPU box has no
-/root/reference); the outputs are committed.  Usage:  python oracle/make_golden.py [detector|transformer|all]
+/root/reference); the outputs are committed.  Usage:  python oracle/make_golden.py [detector|transformer|optimizer|loss|all]
 """
 import io
 import os
@@ -203,6 +203,36 @@ def golden_optimizer():
     print("optimizer goldens written")
 
 
+def golden_loss():
+    """loss_func.py: loss_function, loss_function3, CoVWeightingLoss (6 iterations) and autograd d loss / d heatmap."""
+    import loss_func as R
+    x = synthetic.loss_inputs(0)
+    out = {}
+    hm = x["heatmap"].clone().requires_grad_(True)
+    res = R.loss_function(x["fmask"], x["labelmap"], x["idmap"], hm, [x["dec0"], x["dec1"], x["dec2"]])
+    for k, v in res.items():
+        out["train1_" + k] = np.asarray(v.detach().numpy() if torch.is_tensor(v) else v)
+    names = ["keymap_loss", "size_loss", "textline_loss", "separator_loss", "code1_loss", "code2_loss", "code4_loss", "code8_loss"]
+    alphas = torch.tensor([0.3, 0.05, 0.1, 0.15, 0.1, 0.1, 0.1, 0.1])
+    sum(a * res[k] for a, k in zip(alphas, names)).backward()
+    out["train1_alphas"] = alphas.numpy()
+    out["train1_grad_heatmap"] = hm.grad.numpy()
+    res3 = R.loss_function3([x["out3_0"], x["out3_1"], x["out3_2"]], x["labelcode"], x["mask3"])
+    for k, v in res3.items():
+        out["train3_" + k] = np.asarray(v.detach().numpy() if torch.is_tensor(v) else v)
+    cov = R.CoVWeightingLoss(losses=names + ["id_loss"])
+    g = torch.Generator().manual_seed(99)
+    seq, tot, alph = [], [], []
+    for it in range(6):
+        vals = torch.rand(9, generator=g) * (2.0 / (1 + it)) + 0.1
+        seq.append(vals.numpy())
+        tot.append(float(cov({k: vals[i] for i, k in enumerate(names + ["id_loss"])})))
+        alph.append(cov.alphas.numpy().copy())
+    out["cov_inputs"], out["cov_totals"], out["cov_alphas"] = np.stack(seq), np.asarray(tot, np.float32), np.stack(alph)
+    np.savez_compressed(os.path.join(GOLD, "loss_seed0.npz"), **out)
+    print("loss goldens written:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
@@ -213,3 +243,5 @@ if __name__ == "__main__":
         golden_transformer()
     if what in ("optimizer", "all"):
         golden_optimizer()
+    if what in ("loss", "all"):
+        golden_loss()
