@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256) adamw_sf_step_kernel(const SfChunk* __res
                                                             float* const* __restrict__ grads, float* const* __restrict__ vs,
                                                             float* const* __restrict__ zs, const int64_t* __restrict__ numels,
                                                             float beta2, float one_m_beta2, float bias_correction2, float eps,
-                                                            float decay, float lr, float ckp1, float y_alpha) {
+                                                            float decay, float lr, float ckp1, float y_alpha, int normalize) {
   const SfChunk c = chunks[blockIdx.x];
   float* y = ys[c.tensor] + c.offset;
   float* g = grads[c.tensor] + c.offset;
@@ -27,8 +27,9 @@ __global__ void __launch_bounds__(256) adamw_sf_step_kernel(const SfChunk* __res
     float vi = v[i] * beta2;                       // _foreach_mul_(exp_avg_sq, beta2)
     vi = vi + one_m_beta2 * (gi * gi);             // _foreach_addcmul_(exp_avg_sq, grad, grad, value=1-beta2)
     v[i] = vi;
-    const float denom = sqrtf(vi / bias_correction2) + eps;
-    float gn = gi / denom;                          // grad is normalised IN PLACE in the reference
+    // RAdam schedule-free skips the Adam normalisation while the SMA is too short (rho_t <= 4): plain (or silent) SGD phase
+    float gn = gi;
+    if (normalize) gn = gi / (sqrtf(vi / bias_correction2) + eps);   // grad is normalised IN PLACE in the reference
     float yi = y[i];
     if (decay != 0.0f) gn = gn + decay * yi;
     g[i] = gn;
@@ -60,7 +61,21 @@ int ftc_adamw_sf_step(int n_chunks, const void* chunks, const void* const* ys, c
       // scalars arrive as the Python doubles of the reference and are rounded to fp32 once, as torch does for
       // value= / alpha= / weight= arguments of the foreach ops (1 - beta2 in fp32 would differ by 1.3e-5 relative)
       (float)beta2, (float)(1.0 - beta2), (float)bias_correction2, (float)eps, (float)weight_decay, (float)lr, (float)ckp1,
-      (float)(lr * (beta1 * (1.0 - ckp1) - 1.0)));
+      (float)(lr * (beta1 * (1.0 - ckp1) - 1.0)), 1);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_radam_sf_step(int n_chunks, const void* chunks, const void* const* ys, const void* const* grads,
+                      const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, double beta1, double beta2,
+                      double bias_correction2, double eps, double weight_decay, double lr, double ckp1, int adam_step,
+                      void* stream) {
+  FTC_REQUIRE(n_chunks >= 0 && chunks && ys && grads && exp_avg_sqs && zs && numels, "bad argument");
+  if (n_chunks == 0) return 0;
+  adamw_sf_step_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(
+      (const SfChunk*)chunks, (float* const*)ys, (float* const*)grads, (float* const*)exp_avg_sqs, (float* const*)zs, numels,
+      (float)beta2, (float)(1.0 - beta2), (float)bias_correction2, (float)eps, (float)weight_decay, (float)lr, (float)ckp1,
+      (float)(lr * (beta1 * (1.0 - ckp1) - 1.0)), adam_step ? 1 : 0);
   FTC_POST_LAUNCH();
   return 0;
 }

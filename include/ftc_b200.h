@@ -132,6 +132,12 @@ int ftc_adamw_sf_chunk_elems(void);
 int ftc_adamw_sf_step(int n_chunks, const void* chunks, const void* const* ys, const void* const* grads,
                       const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, double beta1, double beta2,
                       double bias_correction2, double eps, double weight_decay, double lr, double ckp1, void* stream);
+/* Schedule-Free RAdam (models/radam_schedulefree.py:109-236, train3.py:121): same update with the rectified lr computed by
+ * the caller; adam_step = 0 during the early phase (rho_t <= 4), where the gradient is NOT normalised (:182-190) */
+int ftc_radam_sf_step(int n_chunks, const void* chunks, const void* const* ys, const void* const* grads,
+                      const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, double beta1, double beta2,
+                      double bias_correction2, double eps, double weight_decay, double lr, double ckp1, int adam_step,
+                      void* stream);
 
 /* ---- train step: losses (loss_func.py) ----
  * ftc_heatmap_loss: loss_function :94-126 (the map part).  heatmap fp32 [B,9,H,W] logits, labelmap fp32 [B,5,H,W], idmap int64

@@ -203,6 +203,34 @@ def golden_optimizer():
     print("optimizer goldens written")
 
 
+RADAM_CFGS = {"silent": dict(lr=2.5e-3, weight_decay=1e-2), "sgd": dict(lr=2.5e-3, silent_sgd_phase=False, betas=(0.9, 0.99))}
+
+
+def golden_radam():
+    """models/radam_schedulefree.py::RAdamScheduleFree: 8 steps crossing rho_t = 4 (silent phase, and the SGD-phase variant
+    with beta2 = 0.99), then optimizer.eval()."""
+    from models.radam_schedulefree import RAdamScheduleFree
+    out = {}
+    for name, cfg in RADAM_CFGS.items():
+        params = [torch.nn.Parameter(p.clone()) for p in optimizer_inputs(-1)]
+        opt = RAdamScheduleFree(params, **cfg)
+        opt.train()
+        for step in range(8):
+            for p, g in zip(params, optimizer_inputs(step)):
+                p.grad = g.clone()
+            opt.step()
+            for i, p in enumerate(params[:3]):             # the three small tensors at every step; all four after eval()
+                out[f"{name}_s{step}_y{i}"] = p.detach().numpy().copy()
+                out[f"{name}_s{step}_z{i}"] = opt.state[p]["z"].numpy().copy()
+                out[f"{name}_s{step}_v{i}"] = opt.state[p]["exp_avg_sq"].numpy().copy()
+            out[f"{name}_s{step}_lr"] = np.float64(opt.param_groups[0]["scheduled_lr"])
+        opt.eval()
+        for i, p in enumerate(params):
+            out[f"{name}_eval_x{i}"] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, "optimizer_radam_seed0.npz"), **out)
+    print("radam goldens written")
+
+
 def golden_loss():
     """loss_func.py: loss_function, loss_function3, CoVWeightingLoss (6 iterations) and autograd d loss / d heatmap."""
     import loss_func as R
@@ -243,5 +271,7 @@ if __name__ == "__main__":
         golden_transformer()
     if what in ("optimizer", "all"):
         golden_optimizer()
+    if what in ("radam", "all"):
+        golden_radam()
     if what in ("loss", "all"):
         golden_loss()

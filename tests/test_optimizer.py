@@ -57,3 +57,55 @@ def test_fused_adamw_schedulefree_matches_reference(gold):
     for i, p in enumerate(params):
         np.testing.assert_allclose(p.detach().cpu().numpy(), gold[f"eval_x{i}"], rtol=2e-5, atol=1e-6)
     assert opt.param_groups[0]["k"] == 5 and set(opt.state[params[0]].keys()) == {"z", "exp_avg_sq"}
+
+
+# ---- RAdamScheduleFree (reference models/radam_schedulefree.py, train3.py:121) ----
+@pytest.fixture(scope="module")
+def gold_radam():
+    return np.load(os.path.join(GOLDEN, "optimizer_radam_seed0.npz"))
+
+
+@pytest.mark.parametrize("name", ["silent", "sgd"])
+def test_radam_oracle_matches_reference(gold_radam, name):
+    from oracle.make_golden import RADAM_CFGS
+    from oracle.optimizer_oracle import RAdamScheduleFreeOracle
+    o = RAdamScheduleFreeOracle([p.numpy() for p in _inputs(-1)], **RADAM_CFGS[name])
+    for step in range(8):
+        o.step([g.numpy() for g in _inputs(step)])
+        for i in range(3):
+            np.testing.assert_allclose(o.y[i], gold_radam[f"{name}_s{step}_y{i}"], rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(o.z[i], gold_radam[f"{name}_s{step}_z{i}"], rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(o.v[i], gold_radam[f"{name}_s{step}_v{i}"], rtol=2e-6, atol=1e-12)
+    for i, x in enumerate(o.eval_params()):
+        np.testing.assert_allclose(x, gold_radam[f"{name}_eval_x{i}"], rtol=2e-5, atol=1e-6)
+    # the fixture crosses rho_t = 4: the scheduled lr is 0 (silent) / lr (SGD phase) first and rectified afterwards
+    lrs = [float(gold_radam[f"{name}_s{s}_lr"]) for s in range(8)]
+    assert lrs[-1] > 0 and lrs[-1] != lrs[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["silent", "sgd"])
+def test_fused_radam_schedulefree_matches_reference(gold_radam, name):
+    from oracle.make_golden import RADAM_CFGS
+    from findtextcenternet_b200 import _lib
+    from findtextcenternet_b200.models.radam_schedulefree import RAdamScheduleFree
+    params = [torch.nn.Parameter(p.clone().cuda()) for p in _inputs(-1)]
+    opt = RAdamScheduleFree(params, **RADAM_CFGS[name])
+    with pytest.raises(Exception):
+        opt.step()
+    opt.train()
+    l0 = _lib.launch_count()
+    for step in range(8):
+        for p, g in zip(params, _inputs(step)):
+            p.grad = g.clone().cuda()
+        opt.step()
+        assert abs(opt.param_groups[0]["scheduled_lr"] - float(gold_radam[f"{name}_s{step}_lr"])) < 1e-15
+        for i, p in enumerate(params[:3]):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), gold_radam[f"{name}_s{step}_y{i}"], rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(opt.state[p]["z"].cpu().numpy(), gold_radam[f"{name}_s{step}_z{i}"], rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(opt.state[p]["exp_avg_sq"].cpu().numpy(), gold_radam[f"{name}_s{step}_v{i}"], rtol=2e-6, atol=1e-12)
+    assert _lib.launch_count() - l0 == 8
+    opt.eval()
+    for i, p in enumerate(params):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), gold_radam[f"{name}_eval_x{i}"], rtol=2e-5, atol=1e-6)
+    assert set(opt.param_groups[0].keys()) >= {"silent_sgd_phase", "scheduled_lr", "weight_sum", "lr_max", "k", "train_mode"}
