@@ -90,6 +90,7 @@ SYMBOLS = {
     "ftc_debug_set_trace": (_i, [_vp]),
     "ftc_debug_set_gemm_tuning": (_i, [_i, _i, _i, _i, _i]),
     "ftc_debug_bench_gemm": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float)]),
+    "ftc_debug_bench_conv3x3": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float)]),
     "ftc_op_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ftc_op_dwconv3x3_se": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "ftc_op_head_top_conv": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -153,26 +153,37 @@ int ftc_debug_set_gemm_tuning(int mt, int flags, int box_depth, int plan_bn, int
 
 // timing harness for one tcgen05 1x1-conv / linear shape (debug; allocates and frees its own buffers):
 // out[M,N] = act(x[M,K] (* se[b,K]) W^T * scale + bias) (+ res); M = batch * hw rows
+static int debug_bench_conv(int batch, int h, int w, int ksize, int k, int n, int act, int use_se, int use_res, int iters, float* ms_out);
+
 int ftc_debug_bench_gemm(int batch, int hw, int k, int n, int act, int use_se, int use_res, int iters, float* ms_out) {
+  return debug_bench_conv(batch, hw, 1, 1, k, n, act, use_se, use_res, iters, ms_out);
+}
+
+int ftc_debug_bench_conv3x3(int batch, int h, int w, int cin, int cout, int act, int use_res, int iters, float* ms_out) {
+  return debug_bench_conv(batch, h, w, 3, cin, cout, act, 0, use_res, iters, ms_out);
+}
+
+static int debug_bench_conv(int batch, int h, int w, int ksize, int k, int n, int act, int use_se, int use_res, int iters, float* ms_out) {
+  const int hw = h * w;
   FTC_REQUIRE(batch > 0 && hw > 0 && k % 8 == 0 && n > 0 && iters > 0 && ms_out, "bad argument");
   const int M = batch * hw;
   void *x = nullptr, *out = nullptr, *res = nullptr, *wp = nullptr, *flush = nullptr;
   float *wf = nullptr, *sc = nullptr, *bi = nullptr, *se = nullptr;
   const size_t flush_bytes = 256u << 20;
   FTC_CHECK_CUDA(cudaMalloc(&x, (size_t)M * k * 2)); FTC_CHECK_CUDA(cudaMalloc(&out, (size_t)M * n * 2));
-  FTC_CHECK_CUDA(cudaMalloc(&res, (size_t)M * n * 2)); FTC_CHECK_CUDA(cudaMalloc(&wf, (size_t)n * k * 4));
+  FTC_CHECK_CUDA(cudaMalloc(&res, (size_t)M * n * 2)); FTC_CHECK_CUDA(cudaMalloc(&wf, (size_t)n * k * 9 * 4));
   FTC_CHECK_CUDA(cudaMalloc(&sc, (size_t)n * 4)); FTC_CHECK_CUDA(cudaMalloc(&bi, (size_t)n * 4));
   FTC_CHECK_CUDA(cudaMalloc(&se, (size_t)batch * k * 4)); FTC_CHECK_CUDA(cudaMalloc(&flush, flush_bytes));
   FTC_CHECK_CUDA(cudaMemset(x, 0x3c, (size_t)M * k * 2)); FTC_CHECK_CUDA(cudaMemset(res, 0x3c, (size_t)M * n * 2));
-  FTC_CHECK_CUDA(cudaMemset(wf, 0x3b, (size_t)n * k * 4)); FTC_CHECK_CUDA(cudaMemset(sc, 0x3c, (size_t)n * 4));
+  FTC_CHECK_CUDA(cudaMemset(wf, 0x3b, (size_t)n * k * 9 * 4)); FTC_CHECK_CUDA(cudaMemset(sc, 0x3c, (size_t)n * 4));
   FTC_CHECK_CUDA(cudaMemset(bi, 0x3c, (size_t)n * 4)); FTC_CHECK_CUDA(cudaMemset(se, 0x3c, (size_t)batch * k * 4));
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
-  p.B = batch; p.H = hw; p.W = 1; p.stride = 1; p.pad = 0; p.Ho = hw; p.Wo = 1;
+  p.B = batch; p.H = h; p.W = w; p.stride = 1; p.pad = (ksize - 1) / 2; p.Ho = h; p.Wo = w;
   p.M = M; p.N = n; p.G = 1;
   p.srcA = x; p.a_pix_stride = k; p.CA = k; p.CB = 0;
   int K = 0;
-  std::vector<uint32_t> kt = make_ktab(k, 0, 1, &K);
+  std::vector<uint32_t> kt = make_ktab(k, 0, ksize, &K);
   p.K = K;
   ConvTcPlan plan;
   int rc = conv_gemm_tc_plan(p, &plan, true);
@@ -183,7 +194,7 @@ int ftc_debug_bench_gemm(int batch, int hw, int k, int n, int act, int use_se, i
   FTC_CHECK_CUDA(cudaMalloc(&wp, wbytes)); FTC_CHECK_CUDA(cudaMalloc((void**)&ktd, kt.size() * 4));
   FTC_CHECK_CUDA(cudaMemset(wp, 0, wbytes));
   FTC_CHECK_CUDA(cudaMemcpy(ktd, kt.data(), kt.size() * 4, cudaMemcpyHostToDevice));
-  rc = pack_conv_weight_tc(wp, wf, n, k, 1, 1, 0, k, 0, p.K, 0, plan.BN, nullptr, 0, 0);
+  rc = pack_conv_weight_tc(wp, wf, n, k, ksize, ksize, 0, k, 0, p.K, 0, plan.BN, nullptr, 0, plan.tma == TMA_HALO ? 1 : 0);
   if (rc) return rc;
   p.ktab = ktd; p.w = wp; p.scale = sc; p.bias_tab = bi; p.ncase = 1; p.act = act;
   p.a_scale = use_se ? se : nullptr; p.a_scale_stride = k;

@@ -231,8 +231,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
       }
     }
   } else if (warp == MMA_WARP) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp walks the loop, one elected
+    // lane issues: descriptor arithmetic stays warp-uniform, see conv_gemm_tma.cu)
+    const bool leader = elect_one_sync();
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0;
       int trace_n = 0;
@@ -246,14 +248,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
         for (int kb = 0; kb < NKB; ++kb) {
-          const bool tr = p.trace != nullptr && blockIdx.x == 0 && trace_n < 1024;
+          const bool tr = leader && p.trace != nullptr && blockIdx.x == 0 && trace_n < 1024;
           if (tr) p.trace[trace_n] = clock64();
           mbar_wait(full_bar(stage), phase, 0, hint_ns);
           if (tr) p.trace[1024 + trace_n++] = clock64();
           tc_fence_after();
           const uint32_t a_addr = sbase + (uint32_t)stage * stage_bytes;
           const uint64_t bdesc = umma_desc_sw128(a_addr + A_BYTES);
-          if (!(p.tc.flags & 16))                                   // experiment: no MMA
+          if (leader && !(p.tc.flags & 16))                         // (experiment bit: no MMA)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row: +2 in 16-byte units
 #pragma unroll
@@ -261,11 +263,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
               umma_f16(d_tmem + (uint32_t)h * (uint32_t)BN, umma_desc_sw128(a_addr + (uint32_t)h * A_STAGE_BYTES) + (uint64_t)(2 * k),
                        bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));
+          if (leader) umma_commit(empty_bar(stage));
           stage = (stage + 1 == S) ? 0 : stage + 1;
           phase ^= (stage == 0) ? 1u : 0u;
         }
-        umma_commit(tfull_bar(acc));
+        if (leader) umma_commit(tfull_bar(acc));
       }
     }
     __syncwarp();

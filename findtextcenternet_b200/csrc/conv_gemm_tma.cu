@@ -223,7 +223,12 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
     __syncwarp();
   } else if (warp == TM_MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The WHOLE warp walks the loop (barrier waits, descriptor arithmetic: warp-uniform, so it stays on the uniform datapath)
+    // and one elected lane issues the tcgen05 instructions.  With everything under `if (lane == 0)` the compiler moved
+    // every descriptor through ELECT / R2UR.BROADCAST sequences: ~17 dependent instructions per MMA, which made the N = 32
+    // convs of stage 1 MMA-ISSUE bound (72 MMAs of 16 tensor-cycles each per tile).
+    const bool leader = elect_one_sync();
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM_BM >> 4) << 24);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
@@ -255,20 +260,20 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row: +2 in 16-byte units
 #pragma unroll
               for (int h = 0; h < MT; ++h)
-                if (!FTC_ABL(4096))                       // ablation: no MMAs (commits still fire)
+                if (leader && !FTC_ABL(4096))             // (ablation bit: no MMAs, commits still fire)
                 umma_f16(d_tmem + (uint32_t)h * (uint32_t)BN, umma_desc_sw128(a_sub + (uint32_t)h * TM_SUB_BYTES) + (uint64_t)(2 * k),
                          bdesc + (uint64_t)(2 * k), idesc, (k == 0 && h < MT) ? accum : 1u);
               accum = 1u;
             }
-            if (lastB) umma_commit(b_empty(bs));
+            if (lastB && leader) umma_commit(b_empty(bs));
             bs = (bs + 1 == L.nB) ? 0 : bs + 1;
             if (!L.bstat || lastB) bph ^= (bs == 0) ? 1u : 0u;
           }
-          umma_commit(a_empty(as));
+          if (leader) umma_commit(a_empty(as));
           as = (as + 1 == L.nA) ? 0 : as + 1;
           aph ^= (as == 0) ? 1u : 0u;
         }
-        umma_commit(tfull_bar(buf));
+        if (leader) umma_commit(tfull_bar(buf));
       }
     }
     __syncwarp();
@@ -406,27 +411,33 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       // SiLU as h + h*tanh(h), h = x/2: the 1/2 is folded into the staged BN scale / bias (exact: a power of two)
       const float act_pre = p.act == ACT_SILU ? 0.5f : 1.f;
       int staged_gn = -1;
+      // Residual boxes are fetched by a load cursor that runs `depth` items AHEAD of the consumer across tile boundaries: the
+      // box of the next tile is already in flight while this tile's main loop runs (short-K convs exposed the ~2-3k-cycle
+      // HBM latency of a load issued at tile start on every tile).
+      int ld_tile = t_first, ld_it = ew;
+      auto issue_next_res = [&]() {
+        if (ld_tile >= t_last || ew >= n_items) return;
+        const TmaTile t2 = decode_tma_tile<MT, HALO>(ld_tile, NT, G, L);
+        const int h = ld_it / per_sub, c0 = (ld_it - h * per_sub) * cw;
+        const uint32_t slot = n_res_issued & dmask;
+        mbar_arrive_expect_tx(res_bar(ewarp, slot), TM_BOX_BYTES);
+        tma_load_4d(res_box0 + slot * TM_BOX_BYTES, &tmRes, t2.g * p.N + t2.nt * BN + c0, HALO ? t2.x0 : t2.m0 + h * TM_BM + q * 32,
+                    HALO ? t2.y0 + h * 8 + q * 2 : 0, HALO ? t2.b : 0, res_bar(ewarp, slot));
+        ++n_res_issued;
+        ld_it += n_share;
+        if (ld_it >= n_items) { ld_it = ew; ld_tile += t_step; }
+      };
+      if (L.res_tma && lane == 0)
+        for (uint32_t d = 0; d < depth; ++d) issue_next_res();
       for (int tile = t_first; tile < t_last; tile += t_step, ++titer) {
         const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
         const uint32_t buf = L.nbuf == 2 ? (titer & 1u) : 0u;
         const uint32_t use = L.nbuf == 2 ? (titer >> 1) : titer;
         const int ch_out = p.out_ch_base[tc.g] + (p.act == ACT_SWIGLU ? (tc.nt * BN) >> 1 : tc.nt * BN);
-        const int ch_res = tc.g * p.N + tc.nt * BN;
         // box coordinates of the 32 rows (q, sub-tile h) of this warp
         auto box_k1 = [&](int h) { return HALO ? tc.x0 : tc.m0 + h * TM_BM + q * 32; };
         auto box_k2 = [&](int h) { return HALO ? tc.y0 + h * 8 + q * 2 : 0; };
         const int k3 = HALO ? tc.b : 0;
-        auto issue_res = [&](int it) {
-          const int h = it / per_sub, c0 = (it - h * per_sub) * cw;
-          const uint32_t slot = n_res_issued & dmask;
-          mbar_arrive_expect_tx(res_bar(ewarp, slot), TM_BOX_BYTES);
-          tma_load_4d(res_box0 + slot * TM_BOX_BYTES, &tmRes, ch_res + c0, box_k1(h), box_k2(h), k3, res_bar(ewarp, slot));
-          ++n_res_issued;
-        };
-        if (L.res_tma && lane == 0) {
-          if (ew < n_items) issue_res(ew);
-          if (ew + n_share < n_items && depth == 2) issue_res(ew + n_share);
-        }
         // per-column scale / bias of this (group, n-tile): staged once and kept while consecutive tiles share it (always
         // under the weight-stationary schedule; whenever NT * G == 1)
         if (tc.g * NT + tc.nt != staged_gn) {
@@ -569,7 +580,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             }
             ++n_res_used;
             __syncwarp();                               // every lane has read the box before it is refilled
-            if (lane == 0 && it + (int)depth * n_share < n_items) issue_res(it + (int)depth * n_share);
+            if (lane == 0) issue_next_res();
           }
           if (!FTC_ABL(32)) {
             const uint32_t ob = out_box0 + (n_out & dmask) * TM_BOX_BYTES;
@@ -725,7 +736,9 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
   // main loop) only for BN <= 128; wider tiles take them when the main loop is long enough to amortise the exposed
   // epilogue.  Either way there must be about a wave of tiles left.
   const long tiles2 = (long)ceil_div(p.M, 2 * TM_BM) * p.tc.NT * p.G;
-  int MT = ((p.tc.BN <= 128 || p.tc.NKB >= 12) && tiles2 >= 120) ? 2 : 1;
+  // (measured, tools/bench_gemm.py: with a single accumulator set the exposed epilogue costs more than the saved weight
+  //  traffic up to ~30 k-blocks: 3x3 96->384 18 k-blocks 196 vs 224 us, 1x1 K=1536 84 vs 87 us; K=3072 69 vs 73 us the other way)
+  int MT = ((p.tc.BN <= 128 || p.tc.NKB >= 32) && tiles2 >= 120) ? 2 : 1;
   if (env_mt == 1 || env_mt == 2) MT = env_mt;
   const uint32_t b_bytes = (uint32_t)p.tc.BN * 128u;
   if (!halo && !se && MT == 2 && p.tc.NKB <= TM_MAX_SLOTS && env_mt == 0) {
@@ -783,6 +796,9 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
     size_t nb = (avail - (size_t)L.nA * L.a_slot_bytes) / b_bytes;
     L.nB = nb > TM_MAX_SLOTS ? TM_MAX_SLOTS : (int)nb;
     FTC_REQUIRE(L.nB >= 3, "smem budget (halo)");
+    // small-N convs (stage 1: 4 KB weight blocks) leave most of the shared memory unused: deepen the A ring so that more than
+    // one tile's halo boxes are in flight (a tile needs 3 * (nGA + nGB) of them)
+    while (L.nA < TM_MAX_SLOTS && (size_t)(L.nA + 1) * L.a_slot_bytes + (size_t)L.nB * b_bytes <= avail) ++L.nA;
   } else {
     // weight-stationary schedule (short K, many m-tiles per n-tile: the MBConv expand convs): the [BN x K] weight tile
     // stays in shared memory and only activations stream, which removes the dominant L2 -> SM traffic term

@@ -178,6 +178,8 @@ int ftc_debug_set_gemm_tuning(int mt, int flags, int box_depth, int plan_bn, int
 /* debug / tuning: average CUDA-event time (ms, L2 flushed before each run) of one bf16 1x1-conv shape on the tcgen05 path:
  * out[batch*hw, n] = act(x[batch*hw, k] (* se[batch, k]) W^T * scale + bias) (+ res) */
 int ftc_debug_bench_gemm(int batch, int hw, int k, int n, int act, int use_se, int use_res, int iters, float* ms_out);
+/* same for a 3x3 stride-1 pad-1 conv on [batch, h, w, cin] */
+int ftc_debug_bench_conv3x3(int batch, int h, int w, int cin, int cout, int act, int use_res, int iters, float* ms_out);
 int ftc_op_upsample2x(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream);
 /* MBConv middle (torchvision efficientnet.py:137-149 + ops/misc.py:251-261), stride 1: depthwise 3x3 + BN + SiLU with the SE
  * squeeze and fc1 folded into the same kernel, then fc2 + sigmoid.  hid_pre: fp32 [batch, s], zero on entry, holds the

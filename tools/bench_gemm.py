@@ -14,12 +14,15 @@ SHAPES = [("st4 exp", 2304, 192, 768, 1, 0, 0), ("st4 proj", 2304, 768, 192, 0, 
           ("st7 exp", 576, 640, 3840, 1, 0, 0), ("st7 proj", 576, 3840, 640, 0, 1, 1),
           ("st2 proj", 36864, 256, 64, 0, 0, 1), ("st3 proj", 9216, 384, 96, 0, 0, 1)]
 # (name, mt, flags, box_depth, plan_bn, no_bstat)
-VARIANTS = [("auto", 0, 0, 0, 0, 0), ("epi8", 0, 0, 0, 0, 2), ("nobstat", 0, 0, 0, 0, 1), ("nobstat epi8", 0, 0, 0, 0, 3), ("mt2", 2, 0, 0, 0, 0),
-            ("bn128", 0, 0, 0, 128, 0), ("bn128 epi8", 0, 0, 0, 128, 2)]
+VARIANTS = [("auto", 0, 0, 0, 0, 0), ("epi8", 0, 0, 0, 0, 2), ("mt1", 1, 0, 0, 0, 0), ("mt1 epi8", 1, 0, 0, 0, 2), ("mt2", 2, 0, 0, 0, 0),
+            ("mt2 epi8", 2, 0, 0, 0, 2), ("box1", 0, 0, 1, 0, 0), ("mt1 box1", 1, 0, 1, 0, 0), ("mt2 box1", 2, 0, 1, 0, 0)]
 if os.environ.get('FTC_BENCH_VARIANTS'):
     VARIANTS = [v for v in VARIANTS if v[0] in os.environ['FTC_BENCH_VARIANTS'].split(',')]
 if len(sys.argv) > 1:
     SHAPES = [s for s in SHAPES if any(a in s[0] for a in sys.argv[1:])]
+SHAPES3 = [("st1 3x3", 384, 384, 32, 32, 1, 1), ("st2 3x3", 192, 192, 64, 256, 1, 0), ("st3 3x3", 96, 96, 96, 384, 1, 0)]
+if len(sys.argv) > 1:
+    SHAPES3 = [s for s in SHAPES3 if any(a in s[0] for a in sys.argv[1:])]
 print(f"{'shape':10s} " + " ".join(f"{v[0]:>22s}" for v in VARIANTS))
 for name, hw, k, n, act, se, res in SHAPES:
     cells = []
@@ -31,5 +34,18 @@ for name, hw, k, n, act, se, res in SHAPES:
             cells.append(f"{'err':>22s}")
             continue
         tf = 2.0 * B * hw * k * n / (ms.value * 1e-3) / 1e12
+        cells.append(f"{ms.value*1e3:15.1f}us {tf:4.0f}T")
+    print(f"{name:10s} " + " ".join(cells), flush=True)
+
+for name, h, w, cin, cout, act, res in SHAPES3:
+    cells = []
+    for vname, mt, fl, bd, bn, nb in VARIANTS:
+        lib.ftc_debug_set_gemm_tuning(mt, fl, bd, bn, nb)
+        ms = ctypes.c_float(0)
+        rc = lib.ftc_debug_bench_conv3x3(B, h, w, cin, cout, act, res, 10, ctypes.byref(ms))
+        if rc != 0:
+            cells.append(f"{'err':>22s}")
+            continue
+        tf = 2.0 * B * h * w * 9 * cin * cout / (ms.value * 1e-3) / 1e12
         cells.append(f"{ms.value*1e3:15.1f}us {tf:4.0f}T")
     print(f"{name:10s} " + " ".join(cells), flush=True)
