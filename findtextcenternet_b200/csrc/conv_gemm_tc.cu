@@ -407,7 +407,7 @@ int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan, bool allow_tma)
       if (nGA > 4 && nGA <= 8 && plan->BN > 128 && p.N % 128 == 0 && p.N >= 1024 && getenv("FTC_BSTAT_BN")) {
         plan->BN = 128; plan->NT = p.N / 128;
       }
-    } else if (p.pad == 1 && strides_ok && chunks_ok && p.W % HALO_TW == 0 && p.H % 16 == 0 && !(env_no_tma & 4)) {
+    } else if (p.pad == 1 && strides_ok && chunks_ok && p.H % 8 == 0 && !(env_no_tma & 4)) {
       plan->tma = TMA_HALO; plan->nGA = nGA; plan->nGB = nGB; plan->NKB = 9 * (nGA + nGB);
     }
   }

@@ -638,6 +638,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       if (HALO) {
         b = tc.b; oy = tc.y0 + (row >> 4); ox = tc.x0 + (row & 15);
         m = (b * p.Ho + oy) * p.Wo + ox;
+        mvalid = ox < p.Wo;                      // ragged last tile column (W % 16 != 0)
       } else {
         m = tc.m0 + row;
         mvalid = m < p.M;
@@ -749,9 +750,10 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
   }
   int m_tiles;
   if (halo) {
-    FTC_REQUIRE(p.pad == 1 && p.W % HALO_TW == 0 && p.H % (8 * MT) == 0 && p.Ho == p.H && p.Wo == p.W, "halo geometry");
+    if (p.H % 16 != 0) MT = 1;             // 8-row tiles; a ragged last tile COLUMN is fine: TMA zero-fills loads and clips stores
+    FTC_REQUIRE(p.pad == 1 && p.H % (8 * MT) == 0 && p.Ho == p.H && p.Wo == p.W, "halo geometry");
     FTC_REQUIRE(p.tc.NKB == 9 * (p.tc.nGA + p.tc.nGB), "halo plan does not match K");
-    L.tiles_x = p.W / HALO_TW; L.tiles_y = p.H / (8 * MT);
+    L.tiles_x = ceil_div(p.W, HALO_TW); L.tiles_y = p.H / (8 * MT);
     L.NKG = 3 * (p.tc.nGA + p.tc.nGB); L.nsub = 3;
     L.a_slot_bytes = (uint32_t)(8 * MT + 2) * HALO_TW * 128u;
     m_tiles = p.B * L.tiles_x * L.tiles_y;
