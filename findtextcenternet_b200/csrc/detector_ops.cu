@@ -709,6 +709,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ i
     const T* p10 = row1 + (int64_t)x0 * C;
     const T* p11 = row1 + (int64_t)x1 * C;
     T* po = orow + (int64_t)ox * C;
+#pragma unroll 2
     for (int ch = lane; ch < CH; ch += 32) {
       float a[8], bb[8], c[8], d[8], o[8];
       load8(p00 + ch * 8, a);

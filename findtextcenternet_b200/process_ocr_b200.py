@@ -100,7 +100,8 @@ class OCR_b200_Processer(_Base):
                      max_peaks: int = 1024):
         """tiles: float32 [B,768,768,3] in 0..255 (host, ideally pinned, or device).  Runs detector + per-tile peak
         compaction/box decode (process_ocr_base.py:487-538) on the device and returns host arrays
-        (count int32 [B], locations float32 [B,max_peaks,9], glyphfeatures float32 [B,max_peaks,100])."""
+        (count int32 [B], locations float32 [B,max_peaks,9], glyphfeatures float32 [B,max_peaks,100]) in pinned buffers that
+        are reused by the call after the next one (copy them if they must live longer)."""
         x = tiles.to(self.device, non_blocking=True)
         eng = self.detector.detector.engine(self.device)
         meta = torch.tensor([tile_meta(ox, oy, page_w, page_h, self.step_ratio) for ox, oy in offsets], dtype=torch.int32)
@@ -108,4 +109,15 @@ class OCR_b200_Processer(_Base):
         with torch.no_grad():
             heat9, feat, _ = eng.forward(x, False, nhwc255=True)
             count, loc, gfeat = peak_decode(heat9, feat, meta, page_w, page_h, self.cut_off, max_peaks)
-        return count.cpu(), loc.cpu(), gfeat.cpu()
+        # results leave through persistent PINNED host buffers (one async copy each, one sync): a pageable .cpu() of the
+        # [B, max_peaks, 109] arrays cost more than a millisecond per call
+        key = (tuple(count.shape), tuple(loc.shape), tuple(gfeat.shape))
+        if getattr(self, "_out_key", None) != key:
+            self._out_key, self._out_turn = key, 0
+            self._out_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (count, loc, gfeat)] for _ in range(2)]
+        self._out_turn ^= 1
+        host = self._out_host[self._out_turn]          # two sets in rotation: a result stays valid across ONE further call
+        for h, d in zip(host, (count, loc, gfeat)):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return tuple(host)
