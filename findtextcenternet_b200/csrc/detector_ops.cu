@@ -623,7 +623,8 @@ __global__ void __launch_bounds__(256) se_fc2_hid_kernel(const float* __restrict
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float t = b2[c];
-  for (int k = 0; k < S; ++k) t = fmaf(w2t[(int64_t)k * C + c], sh[k], t);
+#pragma unroll 8
+  for (int k = 0; k < S; ++k) t = fmaf(__ldg(w2t + (int64_t)k * C + c), sh[k], t);   // 8 loads in flight (same summation order)
   scale_out[(int64_t)b * C + c] = sigmoid_precise(t);
 }
 
