@@ -148,6 +148,7 @@ int ftc_debug_set_gemm_tuning(int mt, int flags, int box_depth, int plan_bn, int
   GemmTuning& t = gemm_tuning();
   t.mt = mt; t.flags = flags & 0xFFFFFF; t.box_depth = box_depth; t.plan_bn = plan_bn; t.no_bstat = no_bstat & 1;
   t.epi8 = (no_bstat >> 1) & 1;   // bit 1 of no_bstat: keep 8 epilogue warps
+  t.nb = (no_bstat >> 4) & 15;    // bits 4-7: forced weight-ring depth of the rows path (0 = automatic)
   return 0;
 }
 

@@ -104,7 +104,7 @@ std::vector<uint32_t> make_ktab(int CA, int CB, int ksize, int* Kout);
 
 // tuning overrides (0 = automatic), initialised from the environment (FTC_TMA_MT, FTC_TMA_FLAGS) and settable through
 // ftc_debug_set_gemm_tuning for shape sweeps (tools/bench_gemm.py)
-struct GemmTuning { int mt, flags, box_depth, plan_bn, no_bstat, epi8; };
+struct GemmTuning { int mt, flags, box_depth, plan_bn, no_bstat, epi8, nb; };
 GemmTuning& gemm_tuning();
 
 }  // namespace ftc

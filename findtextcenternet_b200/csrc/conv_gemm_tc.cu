@@ -418,7 +418,7 @@ void conv_gemm_tc_set_trace(unsigned long long* dev_ptr) { g_trace = dev_ptr; }
 
 GemmTuning& gemm_tuning() {
   static GemmTuning t = [] {
-    GemmTuning v{0, 0, 0, 0, 0, 0};
+    GemmTuning v{0, 0, 0, 0, 0, 0, 0};
     const char* e = getenv("FTC_TMA_MT"); v.mt = e ? atoi(e) : 0;
     e = getenv("FTC_TMA_FLAGS"); v.flags = e ? atoi(e) : 0;     // ablations (results are garbage): 32 no stores, 64 no SE
     return v;                                                   // scaling, 128 no residual loads, 256 no epilogue at all

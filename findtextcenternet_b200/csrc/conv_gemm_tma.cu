@@ -816,10 +816,16 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
     size_t n = avail / ((size_t)L.a_slot_bytes + b_bytes);
     L.nA = L.nB = n > TM_MAX_SLOTS ? TM_MAX_SLOTS : (int)n;
     FTC_REQUIRE(L.nA >= 2, "smem budget (rows)");
+
     // spend what is left on one more slot of either ring (A first: with SE it feeds a three-party hand-off)
     size_t left = avail - (size_t)L.nA * ((size_t)L.a_slot_bytes + b_bytes);
     if (L.nA < TM_MAX_SLOTS && left >= L.a_slot_bytes) { ++L.nA; left -= L.a_slot_bytes; }
     if (L.nB < TM_MAX_SLOTS && left >= b_bytes) { ++L.nB; left -= b_bytes; }
+    if (gemm_tuning().nb >= 2 && gemm_tuning().nb <= L.nB) {       // tuning: shallower weight ring, deeper activation ring
+      L.nB = gemm_tuning().nb;
+      size_t na = (avail - (size_t)L.nB * b_bytes) / L.a_slot_bytes;
+      L.nA = na > TM_MAX_SLOTS ? TM_MAX_SLOTS : (int)na;
+    }
     }
   }
   size_t smem = fixed + (size_t)L.nA * L.a_slot_bytes + (size_t)L.nB * b_bytes;

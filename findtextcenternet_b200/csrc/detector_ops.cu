@@ -830,26 +830,31 @@ __global__ void __launch_bounds__(256) head_top_conv_kernel(const HeadTopParams 
 // output pixels, loads every (input row, column shift, 16-channel step) fragment once with ldmatrix.x4 and feeds it to
 // the up-to-three output rows it contributes to (ky = 0..2).  The 18 weight fragments of a warp live in registers.
 // Shared-memory reads: 2.7x the tile instead of 9x; the CUDA-core version above was FMA/LDS bound at 11 TFLOP/s.
-__global__ void __launch_bounds__(192) head_top_mma_kernel(const HeadTopParams p) {
-  extern __shared__ __align__(16) unsigned char ht_smem[];
-  constexpr int CD = 192, PS = 200, CH = CD / 8, TH = 8, TW = 16, IH = TH + 2, IW = TW + 2, NW = 6;
-  bf16* tile = reinterpret_cast<bf16*>(ht_smem);                   // [IH*IW][PS]
+__global__ void __launch_bounds__(192) head_top_mma_kernel(const HeadTopParams p, const __grid_constant__ CUtensorMap tmY) {
+  extern __shared__ __align__(16) unsigned char ht_smem_raw[];
+  constexpr int CD = 192, TH = 8, TW = 16, IH = TH + 2, IW = TW + 2, NW = 6;
+  constexpr uint32_t SLAB = 23552;                                 // one 64-channel slab: 180 pixels x 128 B, padded to 1 KB
+  // The halo tile arrives as THREE TMA boxes (64 channels x 18 px x 10 rows, zero-filled outside the image) in the 128B-swizzled
+  // layout: pixel p of slab s is the 128-byte row p, its 16-byte chunk c sits at chunk (c ^ (p & 7)) -- conflict-free for ldmatrix
+  // without padding, and no per-thread copy loop (the cp.async version spent more instructions loading than computing).
+  unsigned char* ht_smem = ht_smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(ht_smem_raw) & 1023u)) & 1023u);
   float* part = reinterpret_cast<float*>(ht_smem);                 // [NW][128][2], aliases the tile after the MMAs
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.y, b = blockIdx.z;
   const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
   const int oy0 = ty * TH, ox0 = tx * TW;
-  const bf16* src = reinterpret_cast<const bf16*>(p.y) + (size_t)(p.head0 + h) * CD;
-  for (int i = tid; i < IH * IW * CH; i += NW * 32) {
-    const int pix = i / CH, ch = i - pix * CH;
-    const int py = pix / IW, px = pix - py * IW;
-    const int iy = oy0 - 1 + py, ix = ox0 - 1 + px;
-    const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-    const bf16* g = ok ? src + (((int64_t)b * p.H + iy) * p.W + ix) * p.pix_stride + ch * 8 : src;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + (size_t)pix * PS + ch * 8);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(g), "r"(ok ? 16u : 0u) : "memory");
+  const uint32_t tile_s0 = (uint32_t)__cvta_generic_to_shared(ht_smem);
+  const uint32_t bar = tile_s0 + 3 * SLAB;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(3u * (uint32_t)(IH * IW * 128)) : "memory");
+#pragma unroll
+    for (int sl = 0; sl < 3; ++sl)
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                   ::"r"(tile_s0 + (uint32_t)sl * SLAB), "l"(reinterpret_cast<uint64_t>(&tmY)), "r"((p.head0 + h) * CD + sl * 64),
+                     "r"(ox0 - 1), "r"(oy0 - 1), "r"(b), "r"(bar) : "memory");
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
   // B fragments (k16 x n8, "col" layout): lane holds k = (lane%4)*2 + {0,1} (+8), n = lane/4; columns >= od are zero
   const int od = p.od[h];
   uint32_t wf[9][2][2];
@@ -875,11 +880,18 @@ __global__ void __launch_bounds__(192) head_top_mma_kernel(const HeadTopParams p
   for (int r = 0; r < TH; ++r)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  // ldmatrix.x4 row addresses: matrix (lane/8): pixels (lane%8) + 8*((lane/8)&1), channels + 8*((lane/8)>>1)
-  const uint32_t lane_off = (uint32_t)((((lane & 7) + 8 * ((lane >> 3) & 1)) * PS + 8 * (lane >> 4) + warp * 32) * 2);
-  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile) + lane_off;
+  __syncthreads();                                   // barrier initialised before anybody polls it
+  {
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                   : "=r"(ok) : "r"(bar) : "memory");
+  }
+  // ldmatrix.x4 row addresses: matrix (lane/8): pixels (lane%8) + 8*((lane/8)&1), channels + 8*((lane/8)>>1).
+  // This warp's 32 channels are half of slab warp/2: 16-byte chunks (warp&1)*4 + ks*2 + (lane>>4) of the pixel's 128-byte row.
+  const int lpix = (lane & 7) + 8 * ((lane >> 3) & 1);
+  const uint32_t slab_s = tile_s0 + (uint32_t)(warp >> 1) * SLAB;
+  const int cbase = (warp & 1) * 4 + (lane >> 4);
 #pragma unroll
   for (int iy = 0; iy < IH; ++iy)
 #pragma unroll
@@ -887,7 +899,8 @@ __global__ void __launch_bounds__(192) head_top_mma_kernel(const HeadTopParams p
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         uint32_t a0, a1, a2, a3;
-        const uint32_t addr = tile_s + (uint32_t)(((iy * IW + kx) * PS + ks * 16) * 2);
+        const int pix = iy * IW + kx + lpix;
+        const uint32_t addr = slab_s + (uint32_t)pix * 128u + (uint32_t)(((cbase + ks * 2) ^ (pix & 7)) << 4);
         asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                      : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr) : "memory");
 #pragma unroll
@@ -942,9 +955,14 @@ int head_top_conv(const void* y, int dtype, int pix_stride, int head0, int n_hea
     head_top_conv_kernel<float><<<grid, 256, smem, s>>>(p);
   } else {
     FTC_REQUIRE(pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "head_top_conv: bf16 source alignment");
-    smem = (size_t)10 * 18 * 200 * 2;
+    smem = 3 * 23552 + 16 + 1024;          // three swizzled slabs + mbarrier + 1 KB alignment slack
+    alignas(64) CUtensorMap tmY;
+    {
+      int rc = tma_encode_nhwc(&tmY, y, DT_BF16, (uint64_t)pix_stride, (uint64_t)pix_stride, W, H, B, 64, 18, 10, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
     if (!attr_done[1]) { FTC_CHECK_CUDA(cudaFuncSetAttribute(head_top_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_done[1] = true; }
-    head_top_mma_kernel<<<grid, 192, smem, s>>>(p);
+    head_top_mma_kernel<<<grid, 192, smem, s>>>(p, tmY);
   }
   FTC_POST_LAUNCH();
   return 0;

@@ -14,8 +14,8 @@ SHAPES = [("st4 exp", 2304, 192, 768, 1, 0, 0), ("st4 proj", 2304, 768, 192, 0, 
           ("st7 exp", 576, 640, 3840, 1, 0, 0), ("st7 proj", 576, 3840, 640, 0, 1, 1),
           ("st2 proj", 36864, 256, 64, 0, 0, 1), ("st3 proj", 9216, 384, 96, 0, 0, 1)]
 # (name, mt, flags, box_depth, plan_bn, no_bstat)
-VARIANTS = [("auto", 0, 0, 0, 0, 0), ("epi8", 0, 0, 0, 0, 2), ("mt1", 1, 0, 0, 0, 0), ("mt1 epi8", 1, 0, 0, 0, 2), ("mt2", 2, 0, 0, 0, 0),
-            ("mt2 epi8", 2, 0, 0, 0, 2), ("box1", 0, 0, 1, 0, 0), ("mt1 box1", 1, 0, 1, 0, 0), ("mt2 box1", 2, 0, 1, 0, 0)]
+VARIANTS = [("auto", 0, 0, 0, 0, 0), ("nb2", 0, 0, 0, 0, 2 << 4), ("mt1", 1, 0, 0, 0, 0), ("mt1 nb2", 1, 0, 0, 0, 2 << 4),
+            ("mt2", 2, 0, 0, 0, 0), ("mt2 nb2", 2, 0, 0, 0, 2 << 4)]
 if os.environ.get('FTC_BENCH_VARIANTS'):
     VARIANTS = [v for v in VARIANTS if v[0] in os.environ['FTC_BENCH_VARIANTS'].split(',')]
 if len(sys.argv) > 1:
@@ -32,6 +32,7 @@ for name, hw, k, n, act, se, res in SHAPES:
         rc = lib.ftc_debug_bench_gemm(B, hw, k, n, act, se, res, 10, ctypes.byref(ms))
         if rc != 0:
             cells.append(f"{'err':>22s}")
+            print("   error:", name, vname, lib.ftc_last_error().decode(), file=sys.stderr)
             continue
         tf = 2.0 * B * hw * k * n / (ms.value * 1e-3) / 1e12
         cells.append(f"{ms.value*1e3:15.1f}us {tf:4.0f}T")
