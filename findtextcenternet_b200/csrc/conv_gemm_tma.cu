@@ -404,12 +404,17 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       const uint32_t sw = (uint32_t)((lane >> 1) & 3);                 // SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3
       const uint32_t row_b = (uint32_t)lane * 64u;
       // a chunk = one output box of 32 channels = 32 accumulator columns (64 for SwiGLU, which gates column pairs)
-      const int cw = p.act == ACT_SWIGLU ? 64 : 32;
+      const int act = p.act;                                          // hoisted out of the item loop (was re-read from the
+      const bool has_res2 = res2 != nullptr;                          // parameter bank per item)
+      const int cw = act == ACT_SWIGLU ? 64 : 32;
       const int per_sub = BN / cw, n_items = MT * per_sub, n_share = L.n_epi >> 2;
-      const bool res1_direct = p.res1 != nullptr && !L.res_tma;
+      const bool res_tma = L.res_tma != 0, res1_direct = p.res1 != nullptr && !res_tma, nine = p.ncase == 9, deep = depth == 2;
+      const bool any_direct = !HALO && (res1_direct || has_res2);
+      const uint32_t swo[4] = {(0u ^ sw) << 4, (1u ^ sw) << 4, (2u ^ sw) << 4, (3u ^ sw) << 4};   // swizzled 16-byte chunk offsets
+      const int Ho1 = p.Ho - 1, Wo1 = p.Wo - 1;
       uint32_t n_out = 0, n_res_issued = 0, n_res_used = 0;
       // SiLU as h + h*tanh(h), h = x/2: the 1/2 is folded into the staged BN scale / bias (exact: a power of two)
-      const float act_pre = p.act == ACT_SILU ? 0.5f : 1.f;
+      const float act_pre = act == ACT_SILU ? 0.5f : 1.f;
       int staged_gn = -1;
       // Residual boxes are fetched by a load cursor that runs `depth` items AHEAD of the consumer across tile boundaries: the
       // box of the next tile is already in flight while this tile's main loop runs (short-K convs exposed the ~2-3k-cycle
@@ -418,7 +423,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       auto issue_next_res = [&]() {
         if (ld_tile >= t_last || ew >= n_items) return;
         const TmaTile t2 = decode_tma_tile<MT, HALO>(ld_tile, NT, G, L);
-        const int h = ld_it / per_sub, c0 = (ld_it - h * per_sub) * cw;
+        const int h = (MT == 2 && ld_it >= per_sub) ? 1 : 0, c0 = (ld_it - h * per_sub) * cw;   // MT <= 2: no division
         const uint32_t slot = n_res_issued & dmask;
         mbar_arrive_expect_tx(res_bar(ewarp, slot), TM_BOX_BYTES);
         tma_load_4d(res_box0 + slot * TM_BOX_BYTES, &tmRes, t2.g * p.N + t2.nt * BN + c0, HALO ? t2.x0 : t2.m0 + h * TM_BM + q * 32,
@@ -433,7 +438,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
         const uint32_t buf = L.nbuf == 2 ? (titer & 1u) : 0u;
         const uint32_t use = L.nbuf == 2 ? (titer >> 1) : titer;
-        const int ch_out = p.out_ch_base[tc.g] + (p.act == ACT_SWIGLU ? (tc.nt * BN) >> 1 : tc.nt * BN);
+        const int ch_out = p.out_ch_base[tc.g] + (act == ACT_SWIGLU ? (tc.nt * BN) >> 1 : tc.nt * BN);
         // box coordinates of the 32 rows (q, sub-tile h) of this warp
         auto box_k1 = [&](int h) { return HALO ? tc.x0 : tc.m0 + h * TM_BM + q * 32; };
         auto box_k2 = [&](int h) { return HALO ? tc.y0 + h * 8 + q * 2 : 0; };
@@ -460,27 +465,27 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         tc_fence_after();
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(MT * BN);
         auto t_item = [&](int it) {                     // TMEM address of an item: sub-tile h at column h * BN, box at c0
-          const int h = it / per_sub;
+          const int h = (MT == 2 && it >= per_sub) ? 1 : 0;
           return t_base + (uint32_t)(h * BN + (it - h * per_sub) * cw);
         };
         uint32_t raw[32];
-        if (p.act != ACT_SWIGLU && ew < n_items) {
+        if (act != ACT_SWIGLU && ew < n_items) {
           __syncwarp();
           tmem_ld32(t_item(ew), raw);
         }
         for (int it = ew; it < n_items; it += n_share) {
-          const int h = it / per_sub, c0 = (it - h * per_sub) * cw;
+          const int h = (MT == 2 && it >= per_sub) ? 1 : 0, c0 = (it - h * per_sub) * cw;
           const uint32_t t_addr = t_base + (uint32_t)(h * BN);
           const int k1 = box_k1(h), k2 = box_k2(h);
           const int row_t = h * TM_BM + q * 32 + lane;          // this lane's row inside the tile
           const int m_row = (HALO ? 0 : tc.m0) + row_t;         // rows mode: output row (direct residual loads)
           int cs = 0;
-          if (p.ncase == 9) {
+          if (nine) {
             const int oy = tc.y0 + (row_t >> 4), ox = tc.x0 + (row_t & 15);   // ncase 9 only occurs on halo (3x3) tiles
-            cs = (oy == 0 ? 0 : (oy == p.Ho - 1 ? 2 : 1)) * 3 + (ox == 0 ? 0 : (ox == p.Wo - 1 ? 2 : 1));
+            cs = (oy == 0 ? 0 : (oy == Ho1 ? 2 : 1)) * 3 + (ox == 0 ? 0 : (ox == Wo1 ? 2 : 1));
           }
           f32x2 vv[16];
-          if (p.act == ACT_SWIGLU) {
+          if (act == ACT_SWIGLU) {
             // interleaved (x1, xg) column pairs -> x1 * silu(xg): 64 accumulator columns give this box's 32 outputs
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -520,7 +525,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             __syncwarp();
             tmem_ld32(t_item(it + n_share), raw);
           }
-          if (p.act == ACT_SILU) {
+          if (act == ACT_SILU) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               float h0, h1, t0, t1;
@@ -532,7 +537,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
               }
               vv[e] = ffma2(vv[e], pk2(t0, t1), vv[e]);
             }
-          } else if (p.act == ACT_GELU) {
+          } else if (act == ACT_GELU) {
             const f32x2 ca = pk2(7.97507884e-01f, 7.97507884e-01f), cb2 = pk2(3.70056461e-02f, 3.70056461e-02f);
             const f32x2 cc = pk2(-3.51516792e-04f, -3.51516792e-04f), half2 = pk2(0.5f, 0.5f);
 #pragma unroll
@@ -561,18 +566,18 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
                 vv[4 * j + e] = fadd2(vv[4 * j + e], pk2(__uint_as_float(uu[e] << 16), __uint_as_float(uu[e] & 0xFFFF0000u)));
             }
           };
-          if (!HALO && m_row < p.M) {
+          if (any_direct && m_row < p.M) {
             if (res1_direct) add_direct(res1, p.res1_row_mod ? (int64_t)(m_row % p.res1_row_mod) : (int64_t)m_row, p.res1_stride);
-            if (res2) add_direct(res2, (int64_t)m_row, p.res2_stride);
+            if (has_res2) add_direct(res2, (int64_t)m_row, p.res2_stride);
           }
-          if (L.res_tma) {
+          if (res_tma) {
             const uint32_t slot = n_res_used & dmask;
             mbar_wait(res_bar(ewarp, slot), (n_res_used >> dshift) & 1u);
             const uint32_t rb_ = res_box0 + slot * TM_BOX_BYTES + row_b;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 u;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(rb_ + (((uint32_t)j ^ sw) << 4)) : "memory");
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(rb_ + swo[j]) : "memory");
               const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e)
@@ -585,7 +590,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           if (!FTC_ABL(32)) {
             const uint32_t ob = out_box0 + (n_out & dmask) * TM_BOX_BYTES;
             if (lane == 0) {                            // the store that last read this box is done
-              if (depth == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+              if (deep) bulk_wait_read<1>(); else bulk_wait_read<0>();
             }
             __syncwarp();
 #pragma unroll
@@ -594,13 +599,13 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
               __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
               for (int e = 0; e < 4; ++e) { float lo, hi; upk2(vv[4 * j + e], lo, hi); h[e] = __floats2bfloat162_rn(lo, hi); }
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ob + row_b + (((uint32_t)j ^ sw) << 4)), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ob + row_b + swo[j]), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
             }
             if (!FTC_ABL(16384)) {                  // ablation bit: keep the st.shared, drop fence + TMA store
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) {
-                tma_store_4d(&tmOut, ob, ch_out + (p.act == ACT_SWIGLU ? c0 >> 1 : c0), k1, k2, k3);
+                tma_store_4d(&tmOut, ob, ch_out + (act == ACT_SWIGLU ? c0 >> 1 : c0), k1, k2, k3);
                 bulk_commit();
               }
             }
