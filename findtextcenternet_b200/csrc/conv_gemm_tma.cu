@@ -790,7 +790,9 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
   }
   // SE kernels need a third A slot (TMA -> scaler -> MMA hand-off) more than deep epilogue staging: their main loops are
   // long (K >= 768), so single boxes cost nothing there
-  L.box_depth = se ? 1 : 2;
+  // (the weight-stationary kernels also take single boxes: the 2 KB per warp buy another activation slot, measured 90 vs 103 us)
+  const bool want_bstat = !halo && !se && p.tc.NKB <= TM_MAX_SLOTS && p.tc.NKB <= 4;
+  L.box_depth = (se || want_bstat) ? 1 : 2;
   if (gemm_tuning().box_depth == 1 || gemm_tuning().box_depth == 2) L.box_depth = gemm_tuning().box_depth;
   // without SE the four scaler warps would idle: they join the staged epilogue (3 instead of 2 warps per TMEM lane quarter;
   // the epilogue of the short-K convs is latency-bound with 2)

@@ -14,8 +14,8 @@ SHAPES = [("st4 exp", 2304, 192, 768, 1, 0, 0), ("st4 proj", 2304, 768, 192, 0, 
           ("st7 exp", 576, 640, 3840, 1, 0, 0), ("st7 proj", 576, 3840, 640, 0, 1, 1),
           ("st2 proj", 36864, 256, 64, 0, 0, 1), ("st3 proj", 9216, 384, 96, 0, 0, 1)]
 # (name, mt, flags, box_depth, plan_bn, no_bstat)
-VARIANTS = [("auto", 0, 0, 0, 0, 0), ("nb2", 0, 0, 0, 0, 2 << 4), ("mt1", 1, 0, 0, 0, 0), ("mt1 nb2", 1, 0, 0, 0, 2 << 4),
-            ("mt2", 2, 0, 0, 0, 0), ("mt2 nb2", 2, 0, 0, 0, 2 << 4)]
+VARIANTS = [("auto", 0, 0, 0, 0, 0), ("bn128", 0, 0, 0, 128, 0), ("bn128 mt2", 2, 0, 0, 128, 0), ("bn192", 0, 0, 0, 192, 0), ("bn64", 0, 0, 0, 64, 0),
+            ("nobstat", 0, 0, 0, 0, 1), ("box1", 0, 0, 1, 0, 0)]
 if os.environ.get('FTC_BENCH_VARIANTS'):
     VARIANTS = [v for v in VARIANTS if v[0] in os.environ['FTC_BENCH_VARIANTS'].split(',')]
 if len(sys.argv) > 1:
