@@ -423,6 +423,8 @@ GemmTuning& gemm_tuning() {
   static GemmTuning t = [] {
     GemmTuning v{0, 0, 0, 0, 0, 0, 0};
     const char* e = getenv("FTC_TMA_MT"); v.mt = e ? atoi(e) : 0;
+    e = getenv("FTC_TMA_BOX_DEPTH"); v.box_depth = e ? atoi(e) : 0;
+    e = getenv("FTC_TMA_EPI8"); v.epi8 = e ? atoi(e) : 0;
     e = getenv("FTC_TMA_FLAGS"); v.flags = e ? atoi(e) : 0;     // ablations (results are garbage): 32 no stores, 64 no SE
     return v;                                                   // scaling, 128 no residual loads, 256 no epilogue at all
   }();
