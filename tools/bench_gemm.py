@@ -12,10 +12,13 @@ SHAPES = [("st4 exp", 2304, 192, 768, 1, 0, 0), ("st4 proj", 2304, 768, 192, 0, 
           ("st5 exp", 2304, 256, 1536, 1, 0, 0), ("st5 proj", 2304, 1536, 256, 0, 1, 1),
           ("st6 exp", 576, 512, 3072, 1, 0, 0), ("st6 proj", 576, 3072, 512, 0, 1, 1),
           ("st7 exp", 576, 640, 3840, 1, 0, 0), ("st7 proj", 576, 3840, 640, 0, 1, 1),
-          ("st2 proj", 36864, 256, 64, 0, 0, 1), ("st3 proj", 9216, 384, 96, 0, 0, 1)]
+          ("st2 proj", 36864, 256, 64, 0, 0, 1), ("st3 proj", 9216, 384, 96, 0, 0, 1),
+          # transformer cfg#4 (M = 256 x 100 = 32 x 800 rows): fused QKV, out-proj (+residual), SwiGLU up (as plain), down (+residual)
+          ("tf qkv", 800, 512, 1536, 0, 0, 0), ("tf out", 800, 512, 512, 0, 0, 1), ("tf w1g", 800, 512, 2048, 0, 0, 0),
+          ("tf w2", 800, 1024, 512, 0, 0, 1), ("tf heads", 800, 512, 3312, 0, 0, 0)]
 # (name, mt, flags, box_depth, plan_bn, no_bstat)
-VARIANTS = [("auto", 0, 0, 0, 0, 0), ("bn128", 0, 0, 0, 128, 0), ("bn128 mt2", 2, 0, 0, 128, 0), ("bn192", 0, 0, 0, 192, 0), ("bn64", 0, 0, 0, 64, 0),
-            ("nobstat", 0, 0, 0, 0, 1), ("box1", 0, 0, 1, 0, 0)]
+VARIANTS = [("auto", 0, 0, 0, 0, 0), ("mt1", 1, 0, 0, 0, 0), ("mt2", 2, 0, 0, 0, 0), ("bn128", 0, 0, 0, 128, 0), ("bn128 mt2", 2, 0, 0, 128, 0),
+            ("bn192", 0, 0, 0, 192, 0), ("box1", 0, 0, 1, 0, 0), ("epi8", 0, 0, 0, 0, 2)]
 if os.environ.get('FTC_BENCH_VARIANTS'):
     VARIANTS = [v for v in VARIANTS if v[0] in os.environ['FTC_BENCH_VARIANTS'].split(',')]
 if len(sys.argv) > 1:
