@@ -360,8 +360,8 @@ int decoder_embed_ln(const int64_t* tokens, const float* e0, const float* e1, co
 // padded by 16 B: conflict-free ldmatrix); keys are walked in chunks of 32 with an online softmax in the exp2 domain; the
 // S accumulator fragments are re-packed in registers as the A operand of P.V.  (The CUDA-core kernel above was 67 % of the
 // cfg#4 transformer forward.)
-template <int HD>
-__global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restrict__ q, int q_stride, int q_off,
+template <int HD, int NW>
+__global__ void __launch_bounds__(NW * 32) attention_mma_kernel(const bf16* __restrict__ q, int q_stride, int q_off,
                                                             const bf16* __restrict__ k, const bf16* __restrict__ v, int kv_stride,
                                                             int k_off, int v_off, const float* __restrict__ mask,
                                                             bf16* __restrict__ out, int out_stride, int Lt, int Ls, float scale_log2) {
@@ -374,13 +374,13 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restri
   bf16* Vs = Ks + (size_t)Lp * RS;                 // [Lp][RS]
   float* Ms = reinterpret_cast<float*>(Vs + (size_t)Lp * RS);   // [Lp] additive mask in the exp2 domain (0 / -inf)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64 + warp * 16;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (NW * 16) + warp * 16;
   const bf16* kb = k + (int64_t)b * Ls * kv_stride + k_off + h * HD;
   const bf16* vb = v + (int64_t)b * Ls * kv_stride + v_off + h * HD;
   pdl_launch_dependents();
   pdl_wait();
   constexpr int PPR = HD / 8;                      // 16-byte pieces per row
-  for (int i = tid; i < Lp * PPR; i += 128) {
+  for (int i = tid; i < Lp * PPR; i += NW * 32) {
     const int j = i / PPR, pc = i - j * PPR;
     const bool ok = j < Ls;
     const uint32_t dk = (uint32_t)__cvta_generic_to_shared(Ks + (size_t)j * RS + pc * 8);
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restri
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dv), "l"(sv), "r"(ok ? 16u : 0u) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int j = tid; j < Lp; j += 128) Ms[j] = j < Ls ? (mask ? mask[(int64_t)b * Ls + j] : 0.f) : -INFINITY;
+  for (int j = tid; j < Lp; j += NW * 32) Ms[j] = j < Ls ? (mask ? mask[(int64_t)b * Ls + j] : 0.f) : -INFINITY;
   // Q fragments straight from global memory (rows clamped; out-of-range rows are not stored)
   const int g = lane >> 2, qd = lane & 3;
   uint32_t qa[KS][4];
@@ -518,14 +518,22 @@ static int launch_attention_mma(const void* q, int q_stride, int q_off, const vo
   const int Lp = (Ls + 31) & ~31;
   const size_t smem = 2 * (size_t)Lp * (HD + 8) * 2 + (size_t)Lp * 4;
   FTC_REQUIRE(smem <= 227 * 1024, "attention: sequence too long for the shared-memory K/V tile");
-  static bool attr_done = false;
-  if (!attr_done) {
-    FTC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
-  }
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
-  FTC_CHECK_CUDA(launch_pdl(attention_mma_kernel<HD>, dim3((Lt + 63) / 64, heads, B), dim3(128), smem, s, (const bf16*)q, q_stride, q_off,
-                            (const bf16*)k, (const bf16*)v, kv_stride, k_off, v_off, mask, (bf16*)out, out_stride, Lt, Ls, scale_log2));
+  // 8 warps (128 query rows) per CTA when the sequence is longer than 64: K / V of a (batch, head) are staged once instead of
+  // once per 64 rows
+#define ATT_MMA_LAUNCH(NW_)                                                                                                  \
+  do {                                                                                                                       \
+    static bool attr_done = false;                                                                                           \
+    if (!attr_done) {                                                                                                        \
+      FTC_CHECK_CUDA(cudaFuncSetAttribute(attention_mma_kernel<HD, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_done = true;                                                                                                      \
+    }                                                                                                                        \
+    FTC_CHECK_CUDA(launch_pdl(attention_mma_kernel<HD, NW_>, dim3((Lt + NW_ * 16 - 1) / (NW_ * 16), heads, B), dim3(NW_ * 32), smem, s, \
+                              (const bf16*)q, q_stride, q_off, (const bf16*)k, (const bf16*)v, kv_stride, k_off, v_off, mask,  \
+                              (bf16*)out, out_stride, Lt, Ls, scale_log2));                                                  \
+  } while (0)
+  if (Lt > 64) ATT_MMA_LAUNCH(8); else ATT_MMA_LAUNCH(4);
+#undef ATT_MMA_LAUNCH
   FTC_POST_LAUNCH();
   return 0;
 }
