@@ -47,7 +47,12 @@ struct TmaLaunch {
                           // order and keeps the whole [BN x K] weight tile resident in its nB = NKB slots across m-tiles
   int m_tiles;
   int n_epi;              // epilogue warps: 8, or 12 when the (idle) scaler warps join the staged epilogue
+  // exact division by multiply-shift (q = (t * magic) >> 40, t < 2^23, divisor <= 2^17): a tile decode costs four integer
+  // divisions in every role of every CTA per tile, ~120 instructions each time with the hardware-less 32-bit divide
+  unsigned long long mg_per_m, mg_nt, mg_per_img, mg_tiles_x, mg_m_tiles;
 };
+__host__ __device__ inline unsigned long long div_magic(int d) { return ((1ull << 40) + (unsigned long long)d - 1) / (unsigned long long)d; }
+__device__ __forceinline__ int fast_div(int t, unsigned long long magic) { return (int)(((unsigned long long)(unsigned)t * magic) >> 40); }
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
   asm volatile(
@@ -86,18 +91,18 @@ template <int MT, bool HALO>
 __device__ __forceinline__ TmaTile decode_tma_tile(int tile, int NT, int G, const TmaLaunch& L) {
   const int per_m = NT * G;
   int mt, rest;
-  if (L.bstat) { rest = tile / L.m_tiles; mt = tile - rest * L.m_tiles; }
-  else { mt = tile / per_m; rest = tile - mt * per_m; }
+  if (L.bstat) { rest = fast_div(tile, L.mg_m_tiles); mt = tile - rest * L.m_tiles; }
+  else { mt = fast_div(tile, L.mg_per_m); rest = tile - mt * per_m; }
   TmaTile t;
-  t.g = rest / NT;
+  t.g = fast_div(rest, L.mg_nt);
   t.nt = rest - t.g * NT;
   t.m0 = mt * (MT * TM_BM);
   t.b = 0; t.y0 = 0; t.x0 = 0;
   if (HALO) {
     const int per_img = L.tiles_x * L.tiles_y;
-    t.b = mt / per_img;
+    t.b = fast_div(mt, L.mg_per_img);
     const int r = mt - t.b * per_img;
-    const int ty = r / L.tiles_x;
+    const int ty = fast_div(r, L.mg_tiles_x);
     t.y0 = ty * (8 * MT);
     t.x0 = (r - ty * L.tiles_x) * HALO_TW;
   }
@@ -239,10 +244,10 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         const uint32_t use = L.nbuf == 2 ? (titer >> 1) : titer;
         bool newB = true, lastB = true;       // weight-stationary: wait for the weights once, release them on the last m-tile
         if (L.bstat) {
-          const int gn = tile / L.m_tiles;
+          const int gn = fast_div(tile, L.mg_m_tiles);
           newB = gn != prev_gn;
           prev_gn = gn;
-          lastB = tile + 1 >= t_last || (tile + 1) / L.m_tiles != gn;
+          lastB = tile + 1 >= t_last || fast_div(tile + 1, L.mg_m_tiles) != gn;
         }
         mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
         tc_fence_after();
@@ -867,6 +872,10 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
     }
   }
   const int num_tiles = m_tiles * p.tc.NT * p.G;
+  FTC_REQUIRE(num_tiles < (1 << 23) && m_tiles < (1 << 17), "tile count exceeds the multiply-shift division range");
+  L.m_tiles = m_tiles;
+  L.mg_per_m = div_magic(p.tc.NT * p.G); L.mg_nt = div_magic(p.tc.NT); L.mg_per_img = div_magic(L.tiles_x * L.tiles_y);
+  L.mg_tiles_x = div_magic(L.tiles_x); L.mg_m_tiles = div_magic(m_tiles);
   const int grid = num_tiles < g_tma_sms ? num_tiles : g_tma_sms;
   p.tc.MT = MT;
 #define TMA_LAUNCH(SE_, MT_, HALO_)                                                                                   \
