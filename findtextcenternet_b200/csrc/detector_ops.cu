@@ -12,7 +12,7 @@ template <typename T, int COUT, bool NHWC255>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ img, T* __restrict__ out, int B,
                                                         int H, int W, const float* __restrict__ w,
                                                         const float* __restrict__ scale, const float* __restrict__ bias) {
-  __shared__ float sw[27 * COUT];
+  __shared__ __align__(16) float sw[27 * COUT];
   __shared__ float ss[COUT], sb[COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) { ss[i] = scale[i]; sb[i] = bias[i]; }
@@ -23,9 +23,10 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
   int b = m / (Ho * Wo);
   int r = m - (int64_t)b * Ho * Wo;
   int oy = r / Wo, ox = r - oy * Wo;
-  float acc[COUT];
+  // packed fp32 pairs (FFMA2): the 27 x COUT FMAs per pixel made this kernel issue-bound at 3x its HBM time; same fma order
+  f32x2 acc2[COUT / 2];
 #pragma unroll
-  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+  for (int o = 0; o < COUT / 2; ++o) acc2[o] = pk2(0.f, 0.f);
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -40,10 +41,18 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
           else
             v = img[(((int64_t)b * 3 + c) * H + iy) * W + ix] * 2.f - 1.f;
         }
-        const float* wk = &sw[((c * 3 + ky) * 3 + kx) * COUT];
+        const f32x2 v2 = pk2(v, v);
+        const ulonglong2* wk = reinterpret_cast<const ulonglong2*>(&sw[((c * 3 + ky) * 3 + kx) * COUT]);
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wk[o], acc[o]);
+        for (int o = 0; o < COUT / 4; ++o) {
+          const ulonglong2 w4 = wk[o];
+          acc2[2 * o] = ffma2(v2, w4.x, acc2[2 * o]);
+          acc2[2 * o + 1] = ffma2(v2, w4.y, acc2[2 * o + 1]);
+        }
       }
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT / 2; ++o) upk2(acc2[o], acc[2 * o], acc[2 * o + 1]);
   T* op = out + m * COUT;
 #pragma unroll
   for (int o0 = 0; o0 < COUT; o0 += 8) {
