@@ -474,6 +474,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           return t_base + (uint32_t)(h * BN + (it - h * per_sub) * cw);
         };
         uint32_t raw[32];
+        bool released = false;
         if (act != ACT_SWIGLU && ew < n_items) {
           __syncwarp();
           tmem_ld32(t_item(ew), raw);
@@ -515,6 +516,14 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           // requested as soon as the scale/bias FMAs have consumed the registers, so its latency hides behind the
           // activation / pack / store work of chunk i (the TMEM read port moves only 64 B/clk per SM)
           tmem_ld_wait();
+          if (it + n_share >= n_items) {
+            // this warp's last accumulator read of the tile is in registers: hand the TMEM buffer back NOW, so that the MMA
+            // of the tile after next does not wait for the activation / pack / store work below
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+            released = true;
+          }
           // packed fp32 math (FFMA2): the epilogue warps are issue-bound on the short-K convs
           {
             const ulonglong2* ss = reinterpret_cast<const ulonglong2*>(sscale + c0);
@@ -617,9 +626,11 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             ++n_out;
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(buf));
+        if (!released) {                               // SwiGLU path, or a warp without items in this tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
       }
       if (lane == 0) bulk_wait_read<0>();
       __syncwarp();

@@ -17,8 +17,10 @@ SHAPES = [("st4 exp", 2304, 192, 768, 1, 0, 0), ("st4 proj", 2304, 768, 192, 0, 
           ("tf qkv", 800, 512, 1536, 0, 0, 0), ("tf out", 800, 512, 512, 0, 0, 1), ("tf w1g", 800, 512, 2048, 0, 0, 0),
           ("tf w2", 800, 1024, 512, 0, 0, 1), ("tf heads", 800, 512, 3312, 0, 0, 0)]
 # (name, mt, flags, box_depth, plan_bn, no_bstat)
-VARIANTS = [("auto", 0, 0, 0, 0, 0), ("mt1", 1, 0, 0, 0, 0), ("mt2", 2, 0, 0, 0, 0), ("bn128", 0, 0, 0, 128, 0), ("bn128 mt2", 2, 0, 0, 128, 0),
-            ("bn192", 0, 0, 0, 192, 0), ("box1", 0, 0, 1, 0, 0), ("epi8", 0, 0, 0, 0, 2)]
+VARIANTS = [("auto", 0, 0, 0, 0, 0), ("mt1", 1, 0, 0, 0, 0), ("mt2", 2, 0, 0, 0, 0), ("bn128", 0, 0, 0, 128, 0), ("bn192", 0, 0, 0, 192, 0),
+            ("box1", 0, 0, 1, 0, 0), ("epi8", 0, 0, 0, 0, 2),
+            # ablations (need a -DFTC_ABLATION build: python -m findtextcenternet_b200.build --ablation)
+            ("nostore", 0, 32, 0, 0, 0), ("noepi", 0, 256, 0, 0, 0), ("noA", 0, 512, 0, 0, 0), ("noMMA", 0, 4096, 0, 0, 0), ("nores", 0, 128, 0, 0, 0)]
 if os.environ.get('FTC_BENCH_VARIANTS'):
     VARIANTS = [v for v in VARIANTS if v[0] in os.environ['FTC_BENCH_VARIANTS'].split(',')]
 if len(sys.argv) > 1:
