@@ -418,6 +418,7 @@ int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan, bool allow_tma)
 }
 
 void conv_gemm_tc_set_trace(unsigned long long* dev_ptr) { g_trace = dev_ptr; }
+unsigned long long* conv_gemm_trace_ptr() { return g_trace; }
 
 GemmTuning& gemm_tuning() {
   static GemmTuning t = [] {

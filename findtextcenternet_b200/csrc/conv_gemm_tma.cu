@@ -27,7 +27,7 @@ constexpr int TM_EPI_THREADS = TM_EPI_WARPS * 32;
 constexpr int TM_TMA_WARP = 8, TM_MMA_WARP = 9, TM_SCALE_WARP0 = 10, TM_SCALE_WARPS = 4;
 constexpr int TM_THREADS = (TM_EPI_WARPS + 2 + TM_SCALE_WARPS) * 32;   // 448
 constexpr int TM_STAGED_FLOATS = 10 * 256;     // per-tile scale[BN] + bias[ncase<=9][BN]
-constexpr int TM_MAX_SLOTS = 8;
+constexpr int TM_MAX_SLOTS = 12;   // ring depth limit per operand (12: a whole 3x3 single-chunk weight set can stay resident)
 constexpr int TM_MAX_EPI_WARPS = TM_EPI_WARPS + TM_SCALE_WARPS;     // without SE the scaler warps join the staged epilogue
 constexpr int TM_NBARS = 5 * TM_MAX_SLOTS + 4 + 2 * TM_MAX_EPI_WARPS;   // + per-warp residual ring (2 deep)
 constexpr uint32_t TM_BOX_BYTES = 32 * 64;   // one staged epilogue box: 32 rows x 32 bf16 channels
@@ -86,6 +86,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
+// pipeline trace of CTA 0 (-DFTC_ABLATION builds only): role r writes stamp j of its i-th tile to trace[r * 1024 + i * 4 + j]
+#ifdef FTC_ABLATION
+#define FTC_TRACE(role, i, j) do { if (p.trace && blockIdx.x == 0 && (i) < 256) p.trace[(role) * 1024 + (i) * 4 + (j)] = clock64(); } while (0)
+#else
+#define FTC_TRACE(role, i, j) do { } while (0)
+#endif
 struct TmaTile { int m0, b, y0, x0, g, nt; };
 template <int MT, bool HALO>
 __device__ __forceinline__ TmaTile decode_tma_tile(int tile, int NT, int G, const TmaLaunch& L) {
@@ -186,7 +192,9 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int prev_gn = -1;
-      for (int tile = t_first; tile < t_last; tile += t_step) {
+      int tr_i = 0;
+      for (int tile = t_first; tile < t_last; tile += t_step, ++tr_i) {
+        FTC_TRACE(0, tr_i, 0);
         const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
         const bf16* wtile = wgt + (size_t)(tc.g * NT + tc.nt) * p.tc.NKB * ((size_t)BN * 64);
         // weight-stationary: slot kb holds k-block kb; it is (re)loaded only when the CTA moves to another n-tile.  The
@@ -204,6 +212,8 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             chunk = srcb ? q - nGA : q;
           }
           mbar_wait(a_empty(as), aph ^ 1u);
+          if (kg == 0) FTC_TRACE(0, tr_i, 1);
+          if (kg == NKG - 1) FTC_TRACE(0, tr_i, 2);
           const uint32_t bar = SE ? a_raw(as) : a_full(as);
           const CUtensorMap* tm = srcb ? &tmB : &tmA;
           const int c = (srcb ? p.b_ch_off + tc.g * p.b_group_stride : p.a_ch_off) + chunk * 64;
@@ -249,12 +259,15 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           prev_gn = gn;
           lastB = tile + 1 >= t_last || fast_div(tile + 1, L.mg_m_tiles) != gn;
         }
+        if (leader) FTC_TRACE(1, (int)titer, 0);
         mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
+        if (leader) FTC_TRACE(1, (int)titer, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (uint32_t)(MT * BN);
         uint32_t accum = 0;
         for (int kg = 0; kg < NKG; ++kg) {
           mbar_wait(a_full(as), aph);
+          if (leader && kg == 0) FTC_TRACE(1, (int)titer, 2);
           const uint32_t a_addr = a_ring + (uint32_t)as * L.a_slot_bytes;
           for (int sub = 0; sub < nsub; ++sub) {
             if (newB) mbar_wait(b_full(bs), bph);
@@ -279,6 +292,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           aph ^= (as == 0) ? 1u : 0u;
         }
         if (leader) umma_commit(tfull_bar(buf));
+        if (leader) FTC_TRACE(1, (int)titer, 3);
       }
     }
     __syncwarp();
@@ -465,8 +479,10 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           }
           asm volatile("bar.sync 1, %0;" ::"r"(n_ethreads) : "memory");
         }
+        if (warp == 0 && lane == 0) FTC_TRACE(2, (int)titer, 0);
         if (lane == 0) mbar_wait(tfull_bar(buf), use & 1u);
         __syncwarp();
+        if (warp == 0 && lane == 0) FTC_TRACE(2, (int)titer, 1);
         tc_fence_after();
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(MT * BN);
         auto t_item = [&](int it) {                     // TMEM address of an item: sub-tile h at column h * BN, box at c0
@@ -626,6 +642,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
             ++n_out;
           }
         }
+        if (warp == 0 && lane == 0) FTC_TRACE(2, (int)titer, 2);
         if (!released) {                               // SwiGLU path, or a warp without items in this tile
           tc_fence_before();
           __syncwarp();
@@ -731,6 +748,7 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
   const int env_mt = gemm_tuning().mt, env_flags = gemm_tuning().flags;
   ConvGemmParams p = p_in;
   p.tc.flags = env_flags;
+  p.trace = conv_gemm_trace_ptr();
   FTC_REQUIRE(p.dtype == DT_BF16, "tcgen05 path is bf16 only");
   FTC_REQUIRE(p.G >= 1 && p.G <= MAX_GROUPS, "groups out of range");
   FTC_REQUIRE(p.tc.BN >= 16 && p.tc.BN <= 256 && p.tc.BN % 16 == 0, "bad tc plan");
@@ -816,7 +834,17 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
   const size_t box_bytes = L.staged ? (size_t)L.n_epi * (L.res_tma ? 2 : 1) * L.box_depth * TM_BOX_BYTES : 0;
   const size_t fixed = 1024 + 8 * TM_NBARS + 16 + TM_STAGED_FLOATS * 4 + 256 + (size_t)L.se_tab * 4 + box_bytes;
   const size_t avail = 227 * 1024 - fixed;
-  if (halo) {
+  if (halo && !se && p.tc.NT * p.G == 1 && p.tc.NKB <= TM_MAX_SLOTS && !gemm_tuning().no_bstat &&
+      (size_t)p.tc.NKB * b_bytes <= 48 * 1024 && (size_t)p.tc.NKB * b_bytes + 3 * (size_t)L.a_slot_bytes <= avail &&
+      m_tiles >= 4 * g_tma_sms) {
+    // weight-stationary 3x3 (stage 1: 32 -> 32 channels, 36 KB of weights): the tcgen05 trace showed the single producer
+    // thread as the bottleneck of this conv - 12 TMA / bulk operations per 256-pixel tile at ~450 cycles each against
+    // ~1.2k cycles of MMA.  With the nine weight blocks resident only the three halo boxes per tile are left.
+    L.bstat = 1;
+    L.nB = p.tc.NKB;
+    size_t na = (avail - (size_t)L.nB * b_bytes) / L.a_slot_bytes;
+    L.nA = na > TM_MAX_SLOTS ? TM_MAX_SLOTS : (int)na;
+  } else if (halo) {
     L.nA = (3 * (size_t)L.a_slot_bytes + 4 * (size_t)b_bytes <= avail) ? 3 : 2;
     size_t nb = (avail - (size_t)L.nA * L.a_slot_bytes) / b_bytes;
     L.nB = nb > TM_MAX_SLOTS ? TM_MAX_SLOTS : (int)nb;
