@@ -18,7 +18,7 @@ SHAPES = [("st4 exp", 2304, 192, 768, 1, 0, 0), ("st4 proj", 2304, 768, 192, 0, 
           ("tf w2", 800, 1024, 512, 0, 0, 1), ("tf heads", 800, 512, 3312, 0, 0, 0)]
 # (name, mt, flags, box_depth, plan_bn, no_bstat)
 VARIANTS = [("auto", 0, 0, 0, 0, 0), ("mt1", 1, 0, 0, 0, 0), ("mt2", 2, 0, 0, 0, 0), ("bn128", 0, 0, 0, 128, 0), ("bn192", 0, 0, 0, 192, 0),
-            ("box1", 0, 0, 1, 0, 0), ("epi8", 0, 0, 0, 0, 2),
+            ("box1", 0, 0, 1, 0, 0), ("box2", 0, 0, 2, 0, 0), ("epi8", 0, 0, 0, 0, 2), ("epi8 box2", 0, 0, 2, 0, 2),
             # ablations (need a -DFTC_ABLATION build: python -m findtextcenternet_b200.build --ablation)
             ("nostore", 0, 32, 0, 0, 0), ("noepi", 0, 256, 0, 0, 0), ("noA", 0, 512, 0, 0, 0), ("noMMA", 0, 4096, 0, 0, 0), ("nores", 0, 128, 0, 0, 0)]
 if os.environ.get('FTC_BENCH_VARIANTS'):
