@@ -80,3 +80,13 @@ def test_cov_weighting_matches_reference(gold):
         tot = cov({k: vals[i] for i, k in enumerate(NAMES + ["id_loss"])})
         assert abs(float(tot) - float(gold["cov_totals"][it])) <= 1e-6 * max(1.0, abs(float(gold["cov_totals"][it])))
         assert np.allclose(cov.alphas.numpy(), gold["cov_alphas"][it], rtol=1e-6, atol=1e-8)
+
+
+def test_loss_functions_have_no_cpu_fallback(batch):
+    """The product path refuses CPU tensors instead of silently computing the losses with torch ops."""
+    from findtextcenternet_b200 import loss_func as LF
+    x = batch
+    with pytest.raises(RuntimeError):
+        LF.loss_function(x["fmask"], x["labelmap"], x["idmap"], x["heatmap"], [x["dec0"], x["dec1"], x["dec2"]])
+    with pytest.raises(RuntimeError):
+        LF.loss_function3([x["out3_0"], x["out3_1"], x["out3_2"]], x["labelcode"], x["mask3"])
