@@ -11,7 +11,8 @@ from typing import Optional
 from . import arch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libftc_b200.so")
+# FTC_B200_LIB: A/B a differently built library from the tools/ scripts (same C-ABI); the default is the in-tree build
+LIB_PATH = os.environ.get("FTC_B200_LIB") or os.path.join(_HERE, "lib", "libftc_b200.so")
 
 FTC_MAX_STAGES = 8
 FTC_MAX_HEADS = 9

@@ -45,8 +45,17 @@ def _deps_mtime() -> float:
 def build(force: bool = False, verbose: bool = False, ablation: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
+    # the flavour (plain / -DFTC_ABLATION) of the objects on disk is recorded next to them: a plain build after an
+    # ablation build must recompile, not reuse the instrumented library
+    stamp = os.path.join(OBJDIR, "flavour.txt")
+    flavour = "ablation" if ablation else "plain"
+    have = open(stamp).read().strip() if os.path.exists(stamp) else "plain"
+    if have != flavour:
+        force = True
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
         return LIB
+    with open(stamp, "w") as f:
+        f.write(flavour + "\n")
     nvcc = _nvcc()
     hdr_mtime = max(os.path.getmtime(os.path.join(d, f)) for d in (CSRC, INCLUDE) for f in os.listdir(d)
                     if f.endswith((".cuh", ".h")))

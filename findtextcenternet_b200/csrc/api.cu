@@ -112,7 +112,7 @@ int ftc_op_conv2d(const void* x, int dtype, int batch, int h, int w, int cin, co
     if (rc) return rc;
     p.K = plan.NKB * KBLOCK;
     rc = pack_conv_weight_tc(wp, w_oihw, cout, cin, ksize, ksize, 0, cin, 0, p.K, 0, plan.BN, nullptr, s,
-                             plan.tma == TMA_HALO ? 1 : 0);
+                             plan.tma == TMA_HALO ? (plan.kb32 ? 2 : 1) : 0);
     if (rc) return rc;
     p.tc = plan;
     rc = conv_gemm_tc(p, s);
@@ -195,7 +195,7 @@ static int debug_bench_conv(int batch, int h, int w, int ksize, int k, int n, in
   FTC_CHECK_CUDA(cudaMalloc(&wp, wbytes)); FTC_CHECK_CUDA(cudaMalloc((void**)&ktd, kt.size() * 4));
   FTC_CHECK_CUDA(cudaMemset(wp, 0, wbytes));
   FTC_CHECK_CUDA(cudaMemcpy(ktd, kt.data(), kt.size() * 4, cudaMemcpyHostToDevice));
-  rc = pack_conv_weight_tc(wp, wf, n, k, ksize, ksize, 0, k, 0, p.K, 0, plan.BN, nullptr, 0, plan.tma == TMA_HALO ? 1 : 0);
+  rc = pack_conv_weight_tc(wp, wf, n, k, ksize, ksize, 0, k, 0, p.K, 0, plan.BN, nullptr, 0, plan.tma == TMA_HALO ? (plan.kb32 ? 2 : 1) : 0);
   if (rc) return rc;
   p.ktab = ktd; p.w = wp; p.scale = sc; p.bias_tab = bi; p.ncase = 1; p.act = act;
   p.a_scale = use_se ? se : nullptr; p.a_scale_stride = k;

@@ -42,6 +42,7 @@ struct ConvTcPlan {
   int tma;      // operand-A path: TMA_NONE = cp.async im2col gather (conv_gemm_tc.cu); TMA_ROWS / TMA_HALO = tensor-tile
                 // TMA loads (conv_gemm_tma.cu).  Fixes the k-block ORDER of the packed weights (see pack_conv_weight_tc)
   int nGA, nGB; // TMA paths: 64-channel chunks of source A / source B; K = 64 * ksize^2 * (nGA + nGB)
+  int kb32;     // TMA_HALO with <= 32 input channels: 32-wide k-blocks (64-byte rows, SWIZZLE_64B) instead of zero-padding to 64
 };
 enum TmaMode : int { TMA_NONE = 0, TMA_ROWS = 1, TMA_HALO = 2 };
 constexpr int HALO_TW = 16;        // halo tiles are 16 pixels wide and 8 (MT=1) or 16 (MT=2) rows high
@@ -93,6 +94,7 @@ int conv_gemm_tma(const ConvGemmParams& p, cudaStream_t stream);   // called by 
 // K-major shared-memory layout, so that a stage's B operand is ONE contiguous cp.async.bulk.
 //   row R = o_off + o (o_off in padded-row space: group g starts at g*NT*BN)
 //   halo_order = 0: k = k_off + (ky*kw+kx)*C + c                      (tap-major; im2col kernel and every 1x1)
+//   halo_order = 2: k = (kx*3 + ky)*32 + c, 32-wide k-blocks in the 64B-swizzled image (TMA_HALO with plan.kb32)
 //   halo_order = 1: k = k_off + ((c/64)*9 + kx*3 + ky)*64 + c%64      (TMA_HALO: per 64-channel chunk and column
 //                   shift kx one halo tile serves the three row taps ky; k_off of source B = 9*64*nGA)
 int pack_conv_weight_tc(void* dst, const float* src, int O, int Itot, int kh, int kw, int c_off, int C, int k_off,

@@ -353,6 +353,14 @@ __global__ void pack_conv_weight_tc_kernel(bf16* __restrict__ dst, const float* 
   if (cscale) v *= cscale[c];
   int R = o_off + o;
   int tile = R / BN, rr = R - tile * BN;
+  if (halo_order == 2) {
+    // 32-wide k-blocks, 64-byte rows, SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3, 8-row groups of 512 B
+    const int k = (kx * 3 + ky) * 32 + c;
+    const int kb = k >> 5, kk = k & 31, chunk = kk >> 3, within = kk & 7;
+    const int64_t off = ((int64_t)tile * NKB + kb) * ((int64_t)BN * 32) + (rr >> 3) * 256 + (rr & 7) * 32 + ((chunk ^ ((rr >> 1) & 3)) << 3) + within;
+    dst[off] = __float2bfloat16_rn(v);
+    return;
+  }
   int k = halo_order ? k_off + ((c >> 6) * 9 + kx * 3 + ky) * 64 + (c & 63) : k_off + r;
   int kb = k >> 6, kk = k & 63;
   int chunk = kk >> 3, within = kk & 7;
@@ -393,7 +401,7 @@ int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan, bool allow_tma)
   plan->flags = 0;
   plan->MT = 1;
   plan->stages = tc_stages(1, best_bn);
-  plan->tma = TMA_NONE; plan->nGA = plan->nGB = 0;
+  plan->tma = TMA_NONE; plan->nGA = plan->nGB = 0; plan->kb32 = 0;
   if (allow_tma && !(env_no_tma & 1) && (p.CA + p.CB) > 0 && p.stride == 1) {
     const bool strides_ok = (p.CA == 0 || p.a_pix_stride % 8 == 0) && (p.CB == 0 || (p.b_pix_stride % 8 == 0 && p.b_group_stride % 8 == 0));
     const int nGA = (p.CA + 63) / 64, nGB = (p.CB + 63) / 64;
@@ -412,6 +420,9 @@ int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan, bool allow_tma)
       }
     } else if (p.pad == 1 && strides_ok && chunks_ok && p.H % 8 == 0 && !(env_no_tma & 4)) {
       plan->tma = TMA_HALO; plan->nGA = nGA; plan->nGB = nGB; plan->NKB = 9 * (nGA + nGB);
+      // <= 32 input channels (stage 1): 32-wide k-blocks; padding to 64 doubled the MMA count and every tcgen05.mma streams
+      // its whole A operand from shared memory whatever N is (65 cycles each at N = 32: tools/trace_tma.py)
+      if (p.CB == 0 && p.CA == 32 && !getenv("FTC_NO_KB32")) plan->kb32 = 1;
     }
   }
   return 0;

@@ -125,7 +125,9 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
   const uint32_t sbase = (raw + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024 B alignment
   uint8_t* smem = smem_raw + (sbase - raw);
   const int BN = p.tc.BN, NT = p.tc.NT, G = p.G;
-  const uint32_t b_bytes = (uint32_t)BN * 128u;
+  const bool kb32 = HALO && p.tc.kb32 != 0;               // 32-channel k-blocks: 64-byte operand rows, SWIZZLE_64B
+  const uint32_t rowb = kb32 ? 64u : 128u;
+  const uint32_t b_bytes = (uint32_t)BN * rowb;
   const uint32_t a_ring = sbase;
   const uint32_t b_ring = sbase + (uint32_t)L.nA * L.a_slot_bytes;
   const uint32_t ring_bytes = (uint32_t)L.nA * L.a_slot_bytes + (uint32_t)L.nB * b_bytes;
@@ -196,7 +198,8 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
       for (int tile = t_first; tile < t_last; tile += t_step, ++tr_i) {
         FTC_TRACE(0, tr_i, 0);
         const TmaTile tc = decode_tma_tile<MT, HALO>(tile, NT, G, L);
-        const bf16* wtile = wgt + (size_t)(tc.g * NT + tc.nt) * p.tc.NKB * ((size_t)BN * 64);
+        const size_t kel = kb32 ? 32 : 64;                  // elements per weight row of a k-block
+        const bf16* wtile = wgt + (size_t)(tc.g * NT + tc.nt) * p.tc.NKB * ((size_t)BN * kel);
         // weight-stationary: slot kb holds k-block kb; it is (re)loaded only when the CTA moves to another n-tile.  The
         // ring bookkeeping below then advances exactly one lap per reload, so the phase logic is the ring's own.
         const bool loadB = !L.bstat || (tc.g * NT + tc.nt) != prev_gn;
@@ -228,7 +231,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
           for (int sub = 0; sub < nsub && loadB; ++sub, ++kb) {
             mbar_wait(b_empty(bs), bph ^ 1u);
             mbar_arrive_expect_tx(b_full(bs), b_bytes);
-            bulk_copy_g2s(b_ring + (uint32_t)bs * b_bytes, wtile + (size_t)kb * BN * 64, b_bytes, b_full(bs));
+            bulk_copy_g2s(b_ring + (uint32_t)bs * b_bytes, wtile + (size_t)kb * BN * kel, b_bytes, b_full(bs));
             bs = (bs + 1 == L.nB) ? 0 : bs + 1;
             bph ^= (bs == 0) ? 1u : 0u;
           }
@@ -245,6 +248,12 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
     const bool leader = elect_one_sync();
     {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM_BM >> 4) << 24);
+      // loop-invariant descriptor pieces: swizzle mode / SBO / version bits, and every byte offset in 16-byte units
+      const uint64_t desc0 = kb32 ? umma_desc_sw64(0) : umma_desc_sw128(0);
+      const uint32_t a_ring16 = a_ring >> 4, b_ring16 = b_ring >> 4, a_slot16 = L.a_slot_bytes >> 4, b16 = b_bytes >> 4;
+      const uint32_t tap16 = (HALO_TW * rowb) >> 4, sub16 = (TM_BM * rowb) >> 4;
+      int ksteps = kb32 ? 2 : 4;
+      asm volatile("" : "+r"(ksteps));   // keep it in a register: the compiler otherwise re-reads the plan flag per k-block
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       uint32_t titer = 0;
@@ -268,19 +277,26 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvGemmParams p, const __grid_cons
         for (int kg = 0; kg < NKG; ++kg) {
           mbar_wait(a_full(as), aph);
           if (leader && kg == 0) FTC_TRACE(1, (int)titer, 2);
-          const uint32_t a_addr = a_ring + (uint32_t)as * L.a_slot_bytes;
+          const uint64_t a_desc = desc0 + (uint64_t)(a_ring16 + (uint32_t)as * a_slot16);
           for (int sub = 0; sub < nsub; ++sub) {
             if (newB) mbar_wait(b_full(bs), bph);
             tc_fence_after();
-            const uint64_t bdesc = umma_desc_sw128(b_ring + (uint32_t)bs * b_bytes);
-            const uint32_t a_sub = a_addr + (HALO ? (uint32_t)sub * (HALO_TW * 128u) : 0u);
+            // descriptors advance by plain 64-bit adds in 16-byte units (shared addresses stay below 256 KB, so the 14-bit
+            // start-address field never carries): the issuing warp's dependent uniform-register chain per k-block is what
+            // paces small-N tiles, not the tensor pipe
+            const uint64_t bdesc = desc0 + (uint64_t)(b_ring16 + (uint32_t)bs * b16);
+            const uint64_t adesc = a_desc + (HALO ? (uint64_t)((uint32_t)sub * tap16) : 0ull);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row: +2 in 16-byte units
+            for (int k = 0; k < 4; ++k) {   // (K = 16 bf16 = 32 B) steps inside the swizzle row: +2 in 16-byte units
+              if (k >= ksteps) break;       // 64-byte rows hold two steps
+              if (FTC_ABL(8192) && k >= 1) break;         // (ablation: one K step per k-block)
 #pragma unroll
-              for (int h = 0; h < MT; ++h)
+              for (int h = 0; h < MT; ++h) {
+                if (FTC_ABL(32768) && h >= 1) break;      // (ablation: one accumulator)
                 if (leader && !FTC_ABL(4096))             // (ablation bit: no MMAs, commits still fire)
-                umma_f16(d_tmem + (uint32_t)h * (uint32_t)BN, umma_desc_sw128(a_sub + (uint32_t)h * TM_SUB_BYTES) + (uint64_t)(2 * k),
-                         bdesc + (uint64_t)(2 * k), idesc, (k == 0 && h < MT) ? accum : 1u);
+                umma_f16(d_tmem + (uint32_t)h * (uint32_t)BN, adesc + (uint64_t)((uint32_t)h * sub16 + 2u * k), bdesc + (uint64_t)(2 * k),
+                         idesc, (k == 0 && h < MT) ? accum : 1u);
+              }
               accum = 1u;
             }
             if (lastB && leader) umma_commit(b_empty(bs));
@@ -780,7 +796,9 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
   //  traffic up to ~30 k-blocks: 3x3 96->384 18 k-blocks 196 vs 224 us, 1x1 K=1536 84 vs 87 us; K=3072 69 vs 73 us the other way)
   int MT = ((p.tc.BN <= 128 || p.tc.NKB >= 32) && tiles2 >= 120) ? 2 : 1;
   if (env_mt == 1 || env_mt == 2) MT = env_mt;
-  const uint32_t b_bytes = (uint32_t)p.tc.BN * 128u;
+  const bool kb32 = halo && p.tc.kb32 != 0;
+  const uint32_t rowb = kb32 ? 64u : 128u;
+  const uint32_t b_bytes = (uint32_t)p.tc.BN * rowb;
   if (!halo && !se && MT == 2 && p.tc.NKB <= TM_MAX_SLOTS && env_mt == 0) {
     // prefer the weight-stationary schedule (below) with 128-row tiles over 256-row tiles that cannot hold the weights
     const size_t fixed0 = 1024 + 8 * TM_NBARS + 16 + TM_STAGED_FLOATS * 4 + 256 + (size_t)TM_EPI_WARPS * (p.res1 ? 4 : 2) * TM_BOX_BYTES;
@@ -794,7 +812,7 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
     FTC_REQUIRE(p.tc.NKB == 9 * (p.tc.nGA + p.tc.nGB), "halo plan does not match K");
     L.tiles_x = ceil_div(p.W, HALO_TW); L.tiles_y = p.H / (8 * MT);
     L.NKG = 3 * (p.tc.nGA + p.tc.nGB); L.nsub = 3;
-    L.a_slot_bytes = (uint32_t)(8 * MT + 2) * HALO_TW * 128u;
+    L.a_slot_bytes = (uint32_t)(8 * MT + 2) * HALO_TW * rowb;
     m_tiles = p.B * L.tiles_x * L.tiles_y;
   } else {
     FTC_REQUIRE(p.pad == 0 && p.tc.nGB == 0 && p.tc.NKB == p.tc.nGA, "rows plan does not match K");
@@ -888,7 +906,7 @@ int conv_gemm_tma(const ConvGemmParams& p_in, cudaStream_t stream) {
   const bf16* b_base = reinterpret_cast<const bf16*>(p.srcB);
   int rc = 0;
   if (halo) {
-    if (p.tc.nGA) rc = encode_map(&tmA, a_base, (uint64_t)(p.a_ch_off + p.CA), p.a_pix_stride, p.W, p.H, p.B, HALO_TW, 8 * MT + 2);
+    if (p.tc.nGA) rc = encode_map(&tmA, a_base, (uint64_t)(p.a_ch_off + p.CA), p.a_pix_stride, p.W, p.H, p.B, HALO_TW, 8 * MT + 2, kb32 ? 32 : 64);
     if (rc) return rc;
     if (p.tc.nGB) rc = encode_map(&tmB, b_base, (uint64_t)p.b_pix_stride, p.b_pix_stride, p.W, p.H, p.B, HALO_TW, 8 * MT + 2);
     if (rc) return rc;

@@ -107,7 +107,7 @@ struct ftc_detector {
       const bool halo = gc.tc.tma == TMA_HALO;
       if (halo && k_off) k_off = 9 * KBLOCK * gc.tc.nGA;     // second source starts after source A's padded chunks
       return pack_conv_weight_tc(base + gc.w_off, w, O, Itot, ks, ks, c_off, C, k_off, gc.K, grp * gc.tc.NT * gc.tc.BN, gc.tc.BN,
-                                 cscale, s, halo ? 1 : 0);
+                                 cscale, s, halo ? (gc.tc.kb32 ? 2 : 1) : 0);
     }
     return pack_conv_weight(base + gc.w_off, dt, w, O, Itot, ks, ks, c_off, C, k_off, gc.K, grp * gc.N, cscale, s);
   }

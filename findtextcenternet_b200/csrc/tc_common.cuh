@@ -116,6 +116,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 }
 
 
+// K-major, 64B-swizzle variant (rows of 64 B, 8-row groups 512 B apart): the 32-channel k-blocks of the <= 32-channel 3x3 convs
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
+
 // SiLU with ONE SFU op per element: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx.f32, rel. error ~2^-11:
 // below bf16 output rounding).  The exp+rcp form costs two MUFU ops and made N=256 SiLU epilogues SFU-bound.
 __device__ __forceinline__ float silu_tanh(float x) {

@@ -41,6 +41,8 @@ CONV_CASES = [
     (3, 16, 16, 64, 100, 3, 1, 0, False),     # halo, one tile per image, N=100 -> 112
     (2, 128, 128, 128, 96, 3, 1, 1, True),    # halo, M=32768: 16x16 tiles (two accumulators), double-buffered TMEM
     (1, 33, 7, 96, 40, 1, 1, 1, False),       # TMA rows: ragged M=231, Cin=96
+    (2, 32, 48, 32, 32, 3, 1, 1, True),       # halo, Cin=32: 32-wide k-blocks (SWIZZLE_64B operands), residual, weight-stationary off (few tiles)
+    (3, 64, 64, 32, 64, 3, 1, 1, False),      # halo, Cin=32, two accumulators
 ]
 
 

@@ -8,6 +8,8 @@ lib = _lib.load()
 what = sys.argv[1] if len(sys.argv) > 1 else "st1"
 tr = torch.zeros(4096, dtype=torch.int64, device="cuda")
 lib.ftc_debug_set_trace(tr.data_ptr())
+if len(sys.argv) > 2:   # ablation flags / MT override: trace_tma.py st1 <flags> [mt]
+    lib.ftc_debug_set_gemm_tuning(int(sys.argv[3]) if len(sys.argv) > 3 else 0, int(sys.argv[2]), 0, 0, 0)
 ms = ctypes.c_float(0)
 if what == "st1":
     rc = lib.ftc_debug_bench_conv3x3(32, 384, 384, 32, 32, 1, 1, 1, ctypes.byref(ms))
