@@ -95,6 +95,20 @@ SYMBOLS = {
     "ftc_op_upsample2x": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ftc_op_dwconv3x3_se": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "ftc_op_head_top_conv": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ftc_train_reduce_scratch_bytes": (_sz, [_i64, _i]),
+    "ftc_train_bn_stats": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp]),
+    "ftc_train_bn_act": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
+    "ftc_train_bn_act_bwd": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp]),
+    "ftc_train_conv2d_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ftc_train_conv2d_dgrad": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ftc_train_dwconv3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ftc_train_dwconv3x3_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ftc_train_dwconv3x3_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ftc_train_spatial_sum": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "ftc_train_scale_bc": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp]),
+    "ftc_train_se_fc": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ftc_train_se_fc_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ftc_train_upsample2x_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ftc_op_attention": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

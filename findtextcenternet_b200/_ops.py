@@ -126,3 +126,197 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, mas
         _lib.check(lib.ftc_op_attention(q.data_ptr(), d, 0, k.data_ptr(), v.data_ptr(), d, 0, 0, _p(mask), out.data_ptr(), d,
                                         _dt(q), b, heads, d // heads, lt, ls, _s(q)), "ftc_op_attention")
     return out
+
+
+# ---- train-step building blocks (csrc/train_ops.cu; include/ftc_b200.h "train step: forward in train mode + backward") ----
+def _f32(t: torch.Tensor, dev) -> torch.Tensor:
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _reduce_scratch(rows: int, c: int, dev) -> torch.Tensor:
+    n = int(_lib.load().ftc_train_reduce_scratch_bytes(rows, c))
+    return torch.empty(n // 4, dtype=torch.float32, device=dev)
+
+
+def bn_stats(x: torch.Tensor):
+    """x [..., C] contiguous -> (batch mean, biased batch variance) fp32 [C]."""
+    lib = _lib.load()
+    assert x.is_cuda and x.is_contiguous()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    mean = torch.empty(c, dtype=torch.float32, device=x.device)
+    var = torch.empty(c, dtype=torch.float32, device=x.device)
+    scratch = _reduce_scratch(rows, c, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ftc_train_bn_stats(x.data_ptr(), _dt(x), rows, c, mean.data_ptr(), var.data_ptr(), scratch.data_ptr(),
+                                          _s(x)), "ftc_train_bn_stats")
+    return mean, var
+
+
+def bn_act(x, mean, var, gamma, beta, eps: float, act: int, residual=None) -> torch.Tensor:
+    lib = _lib.load()
+    assert x.is_cuda and x.is_contiguous()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    y = torch.empty_like(x)
+    res = None if residual is None else residual.contiguous()
+    g, b = _f32(gamma, x.device), _f32(beta, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ftc_train_bn_act(x.data_ptr(), y.data_ptr(), _dt(x), rows, c, mean.data_ptr(), var.data_ptr(),
+                                        g.data_ptr(), b.data_ptr(), eps, act, _p(res), _s(x)), "ftc_train_bn_act")
+    return y
+
+
+def bn_act_bwd(x, dy, mean, var, gamma, beta, eps: float, act: int):
+    """-> (dx, dgamma, dbeta)"""
+    lib = _lib.load()
+    assert x.is_cuda and x.is_contiguous()
+    dy = dy.contiguous()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    dx = torch.empty_like(x)
+    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+    scratch = _reduce_scratch(rows, c, x.device)
+    g, b = _f32(gamma, x.device), _f32(beta, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ftc_train_bn_act_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), _dt(x), rows, c, mean.data_ptr(),
+                                            var.data_ptr(), g.data_ptr(), b.data_ptr(), eps, act, dbeta.data_ptr(),
+                                            dgamma.data_ptr(), scratch.data_ptr(), _s(x)), "ftc_train_bn_act_bwd")
+    return dx, dgamma, dbeta
+
+
+def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, stride: int = 1) -> torch.Tensor:
+    """x [B,H,W,Cin], dy [B,Ho,Wo,Cout] NHWC -> dW fp32 [Cout,Cin,k,k]."""
+    lib = _lib.load()
+    assert x.is_cuda and x.is_contiguous() and dy.dtype == x.dtype
+    dy = dy.contiguous()
+    b, h, w, cin = x.shape
+    cout = dy.shape[-1]
+    assert dy.shape == (b, (h - 1) // stride + 1, (w - 1) // stride + 1, cout), (x.shape, dy.shape)
+    dw = torch.empty(cout, cin, ksize, ksize, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ftc_train_conv2d_wgrad(x.data_ptr(), dy.data_ptr(), _dt(x), b, h, w, cin, cout, ksize, stride,
+                                              dw.data_ptr(), _s(x)), "ftc_train_conv2d_wgrad")
+    return dw
+
+
+def conv2d_dgrad(dy: torch.Tensor, w_oihw: torch.Tensor, h: int, w: int, stride: int = 1, add=None) -> torch.Tensor:
+    """dy [B,Ho,Wo,Cout] NHWC, weights [Cout,Cin,k,k] -> dx [B,h,w,Cin] (+ add)."""
+    lib = _lib.load()
+    assert dy.is_cuda
+    dy = dy.contiguous()
+    b = dy.shape[0]
+    cout, cin, k, _ = w_oihw.shape
+    assert dy.shape == (b, (h - 1) // stride + 1, (w - 1) // stride + 1, cout), (dy.shape, w_oihw.shape, h, w)
+    w32 = _f32(w_oihw, dy.device)
+    dx = torch.empty(b, h, w, cin, dtype=dy.dtype, device=dy.device)
+    ad = None if add is None else add.contiguous()
+    with torch.cuda.device(dy.device):
+        _lib.check(lib.ftc_train_conv2d_dgrad(dy.data_ptr(), _dt(dy), b, h, w, cin, cout, k, stride, w32.data_ptr(), _p(ad),
+                                              dx.data_ptr(), _s(dy)), "ftc_train_conv2d_dgrad")
+    return dx
+
+
+def dwconv3x3_raw(x: torch.Tensor, w9c: torch.Tensor, stride: int = 1) -> torch.Tensor:
+    lib = _lib.load()
+    assert x.is_cuda and x.is_contiguous()
+    b, h, w, c = x.shape
+    out = torch.empty(b, (h - 1) // stride + 1, (w - 1) // stride + 1, c, dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ftc_train_dwconv3x3(x.data_ptr(), out.data_ptr(), _dt(x), b, h, w, c, stride, w9c.data_ptr(), _s(x)),
+                   "ftc_train_dwconv3x3")
+    return out
+
+
+def dwconv3x3_dgrad(dy: torch.Tensor, w9c: torch.Tensor, h: int, w: int, stride: int = 1) -> torch.Tensor:
+    lib = _lib.load()
+    dy = dy.contiguous()
+    b, _, _, c = dy.shape
+    dx = torch.empty(b, h, w, c, dtype=dy.dtype, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _lib.check(lib.ftc_train_dwconv3x3_dgrad(dy.data_ptr(), dx.data_ptr(), _dt(dy), b, h, w, c, stride, w9c.data_ptr(),
+                                                 _s(dy)), "ftc_train_dwconv3x3_dgrad")
+    return dx
+
+
+def dwconv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, stride: int = 1) -> torch.Tensor:
+    """-> dW fp32 [9, C] tap-major."""
+    lib = _lib.load()
+    assert x.is_cuda and x.is_contiguous() and dy.dtype == x.dtype
+    dy = dy.contiguous()
+    b, h, w, c = x.shape
+    dw = torch.empty(9, c, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ftc_train_dwconv3x3_wgrad(x.data_ptr(), dy.data_ptr(), _dt(x), b, h, w, c, stride, dw.data_ptr(), _s(x)),
+                   "ftc_train_dwconv3x3_wgrad")
+    return dw
+
+
+def spatial_sum(x: torch.Tensor, y: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
+    """x (, y) [B, ..., C] -> fp32 [B, C] = scale * sum over the middle axes of x (* y)."""
+    lib = _lib.load()
+    assert x.is_cuda and x.is_contiguous()
+    b, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (b * c)
+    yy = None if y is None else y.contiguous()
+    out = torch.empty(b, c, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ftc_train_spatial_sum(x.data_ptr(), _p(yy), _dt(x), b, hw, c, scale, out.data_ptr(), _s(x)),
+                   "ftc_train_spatial_sum")
+    return out
+
+
+def scale_bc(x: torch.Tensor, scale: torch.Tensor, bias: Optional[torch.Tensor] = None, bias_mul: float = 0.0) -> torch.Tensor:
+    """y = x * scale[b, c] (+ bias_mul * bias[b, c]); scale / bias fp32 [B, C]."""
+    lib = _lib.load()
+    assert x.is_cuda and x.is_contiguous() and scale.dtype == torch.float32 and scale.is_contiguous()
+    b, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (b * c)
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ftc_train_scale_bc(x.data_ptr(), scale.data_ptr(), _p(bias), bias_mul, y.data_ptr(), _dt(x), b, hw, c,
+                                          _s(x)), "ftc_train_scale_bc")
+    return y
+
+
+def se_fc_train(mean: torch.Tensor, w1, b1, w2, b2):
+    """mean fp32 [B, C]; W1 [S, C], W2 [C, S] -> (hid_pre [B, S], gate [B, C])."""
+    lib = _lib.load()
+    b, c = mean.shape
+    s = w1.shape[0]
+    hid = torch.empty(b, s, dtype=torch.float32, device=mean.device)
+    gate = torch.empty(b, c, dtype=torch.float32, device=mean.device)
+    with torch.cuda.device(mean.device):
+        _lib.check(lib.ftc_train_se_fc(mean.data_ptr(), b, c, s, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                       hid.data_ptr(), gate.data_ptr(), _s(mean)), "ftc_train_se_fc")
+    return hid, gate
+
+
+def se_fc_train_bwd(dgate, gate, hid_pre, mean, w1, w2):
+    """-> (dmean [B, C], dW1 [S, C], db1 [S], dW2 [C, S], db2 [C])"""
+    lib = _lib.load()
+    b, c = mean.shape
+    s = w1.shape[0]
+    dev = mean.device
+    f = dict(dtype=torch.float32, device=dev)
+    dgp, dhp, dmean = torch.empty(b, c, **f), torch.empty(b, s, **f), torch.empty(b, c, **f)
+    dw1, db1, dw2, db2 = torch.empty(s, c, **f), torch.empty(s, **f), torch.empty(c, s, **f), torch.empty(c, **f)
+    dgate = dgate.contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(lib.ftc_train_se_fc_bwd(dgate.data_ptr(), gate.data_ptr(), hid_pre.data_ptr(), mean.data_ptr(), b, c, s,
+                                           w1.data_ptr(), w2.data_ptr(), dgp.data_ptr(), dhp.data_ptr(), dmean.data_ptr(),
+                                           dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(), _s(mean)),
+                   "ftc_train_se_fc_bwd")
+    return dmean, dw1, db1, dw2, db2
+
+
+def upsample2x_bwd(dy: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    dy = dy.contiguous()
+    b, ho, wo, c = dy.shape
+    dx = torch.empty(b, ho // 2, wo // 2, c, dtype=dy.dtype, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _lib.check(lib.ftc_train_upsample2x_bwd(dy.data_ptr(), dx.data_ptr(), _dt(dy), b, ho // 2, wo // 2, c, _s(dy)),
+                   "ftc_train_upsample2x_bwd")
+    return dx

@@ -1,0 +1,842 @@
+// Train-step building blocks of the detector (train1.py:128-170: forward in train mode, backward), first correct path:
+// CUDA-core kernels with fp32 math over NHWC fp32 / bf16 tensors.  The forward convolutions of a train step run through
+// the same implicit-GEMM kernels as inference (raw output: no folded BatchNorm); this file adds what inference never
+// needs -- batch statistics, the BatchNorm + activation pair and its backward, the weight / data gradients of the dense and
+// depthwise convolutions, the squeeze-excitation gate and its backward, and the adjoint of the bilinear upsample.
+//
+// Reference semantics (the modules autograd differentiates in train1.py):
+//   nn.BatchNorm2d / BatchNorm1d in train mode (torch batch_norm: batch mean, BIASED variance for the normalisation, UNBIASED
+//     variance into running_var), torchvision Conv2dNormActivation (ops/misc.py:69-126), SiLU, nn.GELU (erf),
+//   torchvision MBConv / FusedMBConv (efficientnet.py:105-231), SqueezeExcitation (ops/misc.py:225-261),
+//   nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True; models/detector.py:167-186).
+#include <algorithm>
+
+#include "../../include/ftc_b200.h"
+#include "common.cuh"
+
+namespace ftc {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// derivative of the activation at pre-activation z
+__device__ __forceinline__ float act_grad(float z, int act) {
+  if (act == ACT_SILU) {
+    float s = sigmoid_precise(z);
+    return s * (1.f + z * (1.f - s));
+  }
+  if (act == ACT_GELU) {   // d/dz [ z * Phi(z) ] = Phi(z) + z * phi(z)
+    float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752440f));
+    float pdf = 0.39894228040143267794f * expf(-0.5f * z * z);
+    return cdf + z * pdf;
+  }
+  return 1.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column reductions over a row-major [rows, C] matrix (NHWC activations: rows = B*H*W).
+// Stage 1: CTA = (64 channels) x (4 row lanes); each CTA owns a contiguous chunk of rows and writes fp32 partials
+// part[q][chunk][C]; stage 2: one thread per channel sums the partials in double.  Deterministic.
+constexpr int RED_CH = 64, RED_LANES = 4, RED_THREADS = RED_CH * RED_LANES;
+
+struct BnArgs {
+  const float* mean; const float* var; const float* gamma; const float* beta;
+  float eps; int act;
+};
+
+// MODE 0: (sum x, sum x^2) ; MODE 1: (sum dz, sum dz*xhat) with dz = dy * act'(gamma*xhat+beta)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(RED_THREADS) col_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t rows,
+                                                                 int C, int64_t rows_per_chunk, float* __restrict__ part,
+                                                                 BnArgs bn) {
+  __shared__ float sm[2][RED_LANES][RED_CH];
+  const int cl = threadIdx.x % RED_CH, lane = threadIdx.x / RED_CH;
+  const int c = blockIdx.x * RED_CH + cl;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t r1 = min(rows, r0 + rows_per_chunk);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    float mean = 0.f, rstd = 1.f, g = 1.f, bta = 0.f;
+    if (MODE == 1) { mean = bn.mean[c]; rstd = rsqrtf(bn.var[c] + bn.eps); g = bn.gamma[c]; bta = bn.beta[c]; }
+    for (int64_t r = r0 + lane; r < r1; r += RED_LANES) {
+      float v = to_f(x[r * C + c]);
+      if (MODE == 0) {
+        s0 += v;
+        s1 = fmaf(v, v, s1);
+      } else {
+        float xh = (v - mean) * rstd;
+        float dz = to_f(dy[r * C + c]) * act_grad(fmaf(g, xh, bta), bn.act);
+        s0 += dz;
+        s1 = fmaf(dz, xh, s1);
+      }
+    }
+  }
+  sm[0][lane][cl] = s0;
+  sm[1][lane][cl] = s1;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int l = 0; l < RED_LANES; ++l) { a += sm[0][l][cl]; b += sm[1][l][cl]; }
+    const int64_t nchunk = gridDim.y;
+    part[((int64_t)0 * nchunk + blockIdx.y) * C + c] = a;
+    part[((int64_t)1 * nchunk + blockIdx.y) * C + c] = b;
+  }
+}
+
+// FIN 0: out0 = mean, out1 = biased variance ; FIN 1: out0 = sum0, out1 = sum1
+template <int FIN>
+__global__ void col_reduce_finish_kernel(const float* __restrict__ part, int nchunk, int C, int64_t rows, float* __restrict__ out0,
+                                         float* __restrict__ out1) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    a += (double)part[((int64_t)0 * nchunk + k) * C + c];
+    b += (double)part[((int64_t)1 * nchunk + k) * C + c];
+  }
+  if (FIN == 0) {
+    double m = a / (double)rows;
+    double v = b / (double)rows - m * m;
+    out0[c] = (float)m;
+    out1[c] = (float)(v > 0.0 ? v : 0.0);
+  } else {
+    out0[c] = (float)a;
+    out1[c] = (float)b;
+  }
+}
+
+int red_chunks(int64_t rows) {
+  // ~512 rows per CTA lane group keeps fp32 partial sums short; at most 4096 chunks
+  int64_t n = (rows + 511) / 512;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(n, 4096));
+}
+
+// y = act(gamma * xhat + beta) (+ residual)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t total, int C, BnArgs bn,
+                                                     const T* __restrict__ residual) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float xh = (to_f(x[i]) - bn.mean[c]) * rsqrtf(bn.var[c] + bn.eps);
+    float v = apply_act<true>(fmaf(bn.gamma[c], xh, bn.beta[c]), bn.act);
+    if (residual) v += to_f(residual[i]);
+    y[i] = from_f<T>(v);
+  }
+}
+
+// dx = gamma * rstd * (dz - sum_dz / rows - xhat * sum_dz_xhat / rows)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+                                                         int64_t total, int C, float inv_rows, BnArgs bn,
+                                                         const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float rstd = rsqrtf(bn.var[c] + bn.eps), g = bn.gamma[c];
+    float xh = (to_f(x[i]) - bn.mean[c]) * rstd;
+    float dz = to_f(dy[i]) * act_grad(fmaf(g, xh, bn.beta[c]), bn.act);
+    float v = g * rstd * (dz - sum_dz[c] * inv_rows - xh * sum_dz_xhat[c] * inv_rows);
+    dx[i] = from_f<T>(v);
+  }
+}
+
+int ew_grid(int64_t total) { return (int)std::min<int64_t>((total + 255) / 256, 148 * 16); }
+
+// ------------------------------------------------------------------------------------------------
+// Dense convolution gradients, implicit GEMM on CUDA cores (64 x 64 x 16 tiles, 4 x 4 outputs per thread).
+// k x k, pad (k-1)/2, stride 1|2; x [B,H,W,Cin], dy [B,Ho,Wo,Cout] NHWC; weights / gradient fp32 OIHW (the nn.Conv2d
+// parameter layout, so the result lands in .grad unchanged).
+constexpr int GB = 64, GK = 16, GT = 256;
+
+struct ConvGeom { int B, H, W, Cin, Ho, Wo, Cout, k, stride, pad; };
+
+// dW[co][ci][ky][kx] += sum_m dy[m][co] * x[b, oy*s - p + ky, ox*s - p + kx, ci]; M split over blockIdx.z, fp32 atomics
+template <typename T>
+__global__ void __launch_bounds__(GT) conv_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, ConvGeom g,
+                                                        int64_t M, int64_t m_per_split, float* __restrict__ dw) {
+  __shared__ float As[GK][GB + 4];   // dy   [m][co]
+  __shared__ float Bs[GK][GB + 4];   // xcol [m][kk]
+  const int tid = threadIdx.x;
+  const int co0 = blockIdx.y * GB, kk0 = blockIdx.x * GB;
+  const int KK = g.k * g.k * g.Cin;
+  const int64_t ms = (int64_t)blockIdx.z * m_per_split, me = min(M, ms + m_per_split);
+  // loader mapping: column (co or kk) = tid & 63, rows tid >> 6 + 4 i
+  const int lc = tid & 63, lr = tid >> 6;
+  const int co_l = co0 + lc;
+  const int kk_l = kk0 + lc;
+  int ky = 0, kx = 0, ci = 0;
+  if (kk_l < KK) { int tap = kk_l / g.Cin; ci = kk_l - tap * g.Cin; ky = tap / g.k; kx = tap - ky * g.k; }
+  const int hw = g.Ho * g.Wo;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int64_t m0 = ms; m0 < me; m0 += GK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = lr + 4 * i;
+      const int64_t m = m0 + r;
+      float a = 0.f, b = 0.f;
+      if (m < me) {
+        if (co_l < g.Cout) a = to_f(dy[m * g.Cout + co_l]);
+        if (kk_l < KK) {
+          int bi = (int)(m / hw);
+          int rem = (int)(m - (int64_t)bi * hw);
+          int oy = rem / g.Wo, ox = rem - oy * g.Wo;
+          int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
+          if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) b = to_f(x[(((int64_t)bi * g.H + iy) * g.W + ix) * g.Cin + ci]);
+        }
+      }
+      As[r][lc] = a;
+      Bs[r][lc] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= g.Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kk = kk0 + tx * 4 + j;
+      if (kk >= KK) continue;
+      int tap = kk / g.Cin, c = kk - tap * g.Cin;
+      atomicAdd(dw + ((int64_t)co * g.Cin + c) * g.k * g.k + tap, acc[i][j]);
+    }
+  }
+}
+
+// dX[b,iy,ix,ci] = sum_{ky,kx,co} dy[b,oy,ox,co] * W[co][ci][ky][kx], oy*s - p + ky = iy, ox*s - p + kx = ix  (+ add)
+template <typename T>
+__global__ void __launch_bounds__(GT) conv_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w, ConvGeom g, int64_t M,
+                                                        const T* __restrict__ add, T* __restrict__ dx) {
+  __shared__ float As[GK][GB + 4];   // gathered dy [kd][m]
+  __shared__ float Bs[GK][GB + 4];   // weights     [kd][ci]
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * GB;
+  const int ci0 = blockIdx.y * GB;
+  const int KD = g.k * g.k * g.Cout, kk2 = g.k * g.k;
+  // loader mapping: kd = tid & 15 (16 consecutive channels of one pixel), rows / columns tid >> 4 + 16 i
+  const int lk = tid & 15, lq = tid >> 4;
+  const int hw = g.H * g.W;
+  int pb[4], py[4], px[4];
+  bool pok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + lq + 16 * i;
+    pok[i] = m < M;
+    int bi = 0, iy = 0, ix = 0;
+    if (pok[i]) { bi = (int)(m / hw); int rem = (int)(m - (int64_t)bi * hw); iy = rem / g.W; ix = rem - iy * g.W; }
+    pb[i] = bi; py[i] = iy; px[i] = ix;
+  }
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int kd0 = 0; kd0 < KD; kd0 += GK) {
+    const int kd = kd0 + lk;
+    int tap = 0, co = 0, ky = 0, kx = 0;
+    const bool kok = kd < KD;
+    if (kok) { tap = kd / g.Cout; co = kd - tap * g.Cout; ky = tap / g.k; kx = tap - ky * g.k; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = 0.f;
+      if (kok && pok[i]) {
+        int ny = py[i] + g.pad - ky, nx = px[i] + g.pad - kx;
+        if (ny >= 0 && nx >= 0 && ny % g.stride == 0 && nx % g.stride == 0) {
+          int oy = ny / g.stride, ox = nx / g.stride;
+          if (oy < g.Ho && ox < g.Wo) a = to_f(dy[(((int64_t)pb[i] * g.Ho + oy) * g.Wo + ox) * g.Cout + co]);
+        }
+      }
+      As[lk][lq + 16 * i] = a;
+      float b = 0.f;
+      const int c = ci0 + lq + 16 * i;
+      if (kok && c < g.Cin) b = w[((int64_t)co * g.Cin + c) * kk2 + tap];
+      Bs[lk][lq + 16 * i] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = ci0 + tx * 4 + j;
+      if (c >= g.Cin) continue;
+      float v = acc[i][j];
+      if (add) v += to_f(add[m * g.Cin + c]);
+      dx[m * g.Cin + c] = from_f<T>(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise 3x3 (pad 1, stride 1|2), weights fp32 [9][C] tap-major.  Raw output (train-mode BatchNorm follows).
+template <typename T>
+__global__ void __launch_bounds__(256) dw_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int Ho,
+                                                     int Wo, int stride, const float* __restrict__ w) {
+  const int64_t total = (int64_t)B * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t p = i / C;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * stride - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * stride - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        acc = fmaf(to_f(x[(((int64_t)b * H + iy) * W + ix) * C + c]), w[(ky * 3 + kx) * C + c], acc);
+      }
+    }
+    y[i] = from_f<T>(acc);
+  }
+}
+
+// dx[b,iy,ix,c] = sum_{ky,kx} dy[b,oy,ox,c] * w[ky,kx,c], oy*s - 1 + ky = iy, ox*s - 1 + kx = ix
+template <typename T>
+__global__ void __launch_bounds__(256) dw_dgrad_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int H, int W, int C,
+                                                       int Ho, int Wo, int stride, const float* __restrict__ w) {
+  const int64_t total = (int64_t)B * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t p = i / C;
+    const int ix = (int)(p % W); p /= W;
+    const int iy = (int)(p % H);
+    const int b = (int)(p / H);
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ny = iy + 1 - ky;
+      if (ny < 0 || ny % stride != 0) continue;
+      const int oy = ny / stride;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int nx = ix + 1 - kx;
+        if (nx < 0 || nx % stride != 0) continue;
+        const int ox = nx / stride;
+        if (ox >= Wo) continue;
+        acc = fmaf(to_f(dy[(((int64_t)b * Ho + oy) * Wo + ox) * C + c]), w[(ky * 3 + kx) * C + c], acc);
+      }
+    }
+    dx[i] = from_f<T>(acc);
+  }
+}
+
+// dw[t][c] += sum_{b,oy,ox} dy[b,oy,ox,c] * x[b, oy*s-1+ky, ox*s-1+kx, c]; CTA = 32 channels x 8 pixel lanes, pixel range
+// split over blockIdx.y, fp32 atomics into a zeroed buffer
+template <typename T>
+__global__ void __launch_bounds__(256) dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, int B, int H, int W, int C,
+                                                       int Ho, int Wo, int stride, int64_t pix_per_split, float* __restrict__ dw) {
+  __shared__ float sm[8][9][32];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const int64_t P = (int64_t)B * Ho * Wo;
+  const int64_t p0 = (int64_t)blockIdx.y * pix_per_split, p1 = min(P, p0 + pix_per_split);
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  if (c < C) {
+    for (int64_t p = p0 + lane; p < p1; p += 8) {
+      int64_t q = p;
+      const int ox = (int)(q % Wo); q /= Wo;
+      const int oy = (int)(q % Ho);
+      const int b = (int)(q / Ho);
+      const float g = to_f(dy[p * C + c]);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * stride - 1 + ky;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * stride - 1 + kx;
+          if (ix < 0 || ix >= W) continue;
+          acc[ky * 3 + kx] = fmaf(g, to_f(x[(((int64_t)b * H + iy) * W + ix) * C + c]), acc[ky * 3 + kx]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) sm[lane][t][cl] = acc[t];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * 32; i += 256) {
+    const int t = i / 32, cc = i - t * 32;
+    if (blockIdx.x * 32 + cc >= C) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) s += sm[l][t][cc];
+    atomicAdd(dw + (int64_t)t * C + blockIdx.x * 32 + cc, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Squeeze-excitation pieces.  x [B, HW, C].
+// spatial sums: out[b][c] = scale * sum_hw f(x, y)  with f = x (MUL 0) or x*y (MUL 1); CTA = (64 channels x 4 lanes) per image
+template <typename T, int MUL>
+__global__ void __launch_bounds__(RED_THREADS) spatial_sum_kernel(const T* __restrict__ x, const T* __restrict__ y, int HW, int C,
+                                                                  float scale, float* __restrict__ out) {
+  __shared__ float sm[RED_LANES][RED_CH];
+  const int cl = threadIdx.x % RED_CH, lane = threadIdx.x / RED_CH;
+  const int c = blockIdx.x * RED_CH + cl, b = blockIdx.y;
+  // two-level accumulation (runs of 64 pixels) keeps the fp32 sums of up to 36 864 pixels accurate
+  float total = 0.f;
+  if (c < C) {
+    const T* xb = x + (int64_t)b * HW * C + c;
+    const T* yb = MUL ? y + (int64_t)b * HW * C + c : nullptr;
+    float run = 0.f;
+    int n = 0;
+    for (int p = lane; p < HW; p += RED_LANES) {
+      float v = to_f(xb[(int64_t)p * C]);
+      if (MUL) v *= to_f(yb[(int64_t)p * C]);
+      run += v;
+      if (++n == 64) { total += run; run = 0.f; n = 0; }
+    }
+    total += run;
+  }
+  sm[lane][cl] = total;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int l = 0; l < RED_LANES; ++l) s += sm[l][cl];
+    out[(int64_t)b * C + c] = s * scale;
+  }
+}
+
+// y = x * s[b][c]     (also StochasticDepth "row" mode with s constant per image)
+template <typename T>
+__global__ void __launch_bounds__(256) scale_bc_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ y, int HW,
+                                                       int C, int64_t total, const float* __restrict__ bias_bc, float bias_mul) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int b = (int)(i / ((int64_t)HW * C));
+    float v = to_f(x[i]) * s[(int64_t)b * C + c];
+    if (bias_bc) v = fmaf(bias_bc[(int64_t)b * C + c], bias_mul, v);
+    y[i] = from_f<T>(v);
+  }
+}
+
+// SE excitation of one image per CTA: hid_pre = W1 mean + b1 ; hid = silu ; gate_pre = W2 hid + b2 ; gate = sigmoid
+// W1 [S][C], W2 [C][S] row-major (the squeezed conv weights of ops/misc.py:247-248)
+__global__ void __launch_bounds__(256) se_fc_fwd_kernel(const float* __restrict__ mean, int C, int S, const float* __restrict__ w1,
+                                                        const float* __restrict__ b1, const float* __restrict__ w2,
+                                                        const float* __restrict__ b2, float* __restrict__ hid_pre,
+                                                        float* __restrict__ gate) {
+  extern __shared__ float se_sm[];   // [S] hidden activations
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* mb = mean + (int64_t)b * C;
+  for (int s = warp; s < S; s += 8) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(w1[(int64_t)s * C + c], mb[c], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      a += b1[s];
+      hid_pre[(int64_t)b * S + s] = a;
+      se_sm[s] = silu_precise(a);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = b2[c];
+    for (int s = 0; s < S; ++s) a = fmaf(w2[(int64_t)c * S + s], se_sm[s], a);
+    gate[(int64_t)b * C + c] = sigmoid_precise(a);
+  }
+}
+
+// backward, data side, one image per CTA: dgp = dgate * gate (1 - gate) ; dhid = W2^T dgp ; dhp = dhid * silu'(hid_pre) ;
+// dmean = W1^T dhp
+__global__ void __launch_bounds__(256) se_fc_bwd_data_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
+                                                             const float* __restrict__ hid_pre, int C, int S,
+                                                             const float* __restrict__ w1, const float* __restrict__ w2,
+                                                             float* __restrict__ dgp, float* __restrict__ dhp,
+                                                             float* __restrict__ dmean) {
+  extern __shared__ float se_sm[];   // [C] dgp, then [S] dhp
+  float* s_dgp = se_sm;
+  float* s_dhp = se_sm + C;
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float gt = gate[(int64_t)b * C + c];
+    float v = dgate[(int64_t)b * C + c] * gt * (1.f - gt);
+    s_dgp[c] = v;
+    dgp[(int64_t)b * C + c] = v;
+  }
+  __syncthreads();
+  for (int s = warp; s < S; s += 8) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(w2[(int64_t)c * S + s], s_dgp[c], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      float v = a * act_grad(hid_pre[(int64_t)b * S + s], ACT_SILU);
+      s_dhp[s] = v;
+      dhp[(int64_t)b * S + s] = v;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = 0.f;
+    for (int s = 0; s < S; ++s) a = fmaf(w1[(int64_t)s * C + c], s_dhp[s], a);
+    dmean[(int64_t)b * C + c] = a;
+  }
+}
+
+// backward, weight side: dW2[c][s] = sum_b dgp[b][c] silu(hid_pre[b][s]) ; dW1[s][c] = sum_b dhp[b][s] mean[b][c] ; biases
+__global__ void __launch_bounds__(256) se_fc_bwd_weight_kernel(const float* __restrict__ dgp, const float* __restrict__ dhp,
+                                                               const float* __restrict__ hid_pre, const float* __restrict__ mean,
+                                                               int B, int C, int S, float* __restrict__ dw1, float* __restrict__ db1,
+                                                               float* __restrict__ dw2, float* __restrict__ db2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)C * S) return;
+  {   // dW2 element (c, s) = i
+    const int c = (int)(i / S), s = (int)(i - (int64_t)c * S);
+    float a = 0.f, bsum = 0.f;
+    for (int b = 0; b < B; ++b) {
+      float g = dgp[(int64_t)b * C + c];
+      a = fmaf(g, silu_precise(hid_pre[(int64_t)b * S + s]), a);
+      bsum += g;
+    }
+    dw2[i] = a;
+    if (s == 0) db2[c] = bsum;
+  }
+  {   // dW1 element (s, c) = i
+    const int s = (int)(i / C), c = (int)(i - (int64_t)s * C);
+    float a = 0.f, bsum = 0.f;
+    for (int b = 0; b < B; ++b) {
+      float g = dhp[(int64_t)b * S + s];
+      a = fmaf(g, mean[(int64_t)b * C + c], a);
+      bsum += g;
+    }
+    dw1[i] = a;
+    if (c == 0) db1[s] = bsum;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjoint of the bilinear x2 upsample (align_corners=True): dx[b,iy,ix,:] = sum over the output pixels whose 2x2 source
+// footprint contains (iy, ix), with the forward's own weights.  Source coordinate of output o: f = o * (n-1)/(2n-1)
+// (computed as in upsample2x_kernel, detector_ops.cu), so the candidates of input index j are the outputs with floor(f) in
+// {j-1, j}: o in [2j-2, 2j+3] clipped.  CTA per input row, warps over pixels, lanes over channels.
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int H, int W, int C,
+                                                             float sy, float sx) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int b = blockIdx.y, iy = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // row candidates and their weights (CTA constants)
+  float wy[6];
+  int oys[6];
+  int ny = 0;
+  for (int oy = max(0, 2 * iy - 2); oy <= min(Ho - 1, 2 * iy + 3); ++oy) {
+    const float fy = sy * oy;
+    const int y0 = min((int)fy, H - 1), y1 = min(y0 + 1, H - 1);
+    const float ly = fminf(fmaxf(fy - y0, 0.f), 1.f), hy = 1.f - ly;
+    float wgt = 0.f;
+    if (y0 == iy) wgt += hy;
+    if (y1 == iy) wgt += ly;
+    if (wgt != 0.f) { wy[ny] = wgt; oys[ny] = oy; ++ny; }
+  }
+  for (int ix = warp; ix < W; ix += 8) {
+    float wx[6];
+    int oxs[6];
+    int nx = 0;
+    for (int ox = max(0, 2 * ix - 2); ox <= min(Wo - 1, 2 * ix + 3); ++ox) {
+      const float fx = sx * ox;
+      const int x0 = min((int)fx, W - 1), x1 = min(x0 + 1, W - 1);
+      const float lx = fminf(fmaxf(fx - x0, 0.f), 1.f), hx = 1.f - lx;
+      float wgt = 0.f;
+      if (x0 == ix) wgt += hx;
+      if (x1 == ix) wgt += lx;
+      if (wgt != 0.f) { wx[nx] = wgt; oxs[nx] = ox; ++nx; }
+    }
+    T* po = dx + (((int64_t)b * H + iy) * W + ix) * C;
+    for (int c = lane; c < C; c += 32) {
+      float acc = 0.f;
+      for (int a = 0; a < ny; ++a) {
+        const T* row = dy + (((int64_t)b * Ho + oys[a]) * Wo) * C + c;
+        float r = 0.f;
+        for (int k = 0; k < nx; ++k) r = fmaf(wx[k], to_f(row[(int64_t)oxs[k] * C]), r);
+        acc = fmaf(wy[a], r, acc);
+      }
+      po[c] = from_f<T>(acc);
+    }
+  }
+}
+
+template <typename T> const T* cp(const void* p) { return reinterpret_cast<const T*>(p); }
+template <typename T> T* mp(void* p) { return reinterpret_cast<T*>(p); }
+
+bool dtype_ok(int dt) { return dt == DT_F32 || dt == DT_BF16; }
+
+}  // namespace
+}  // namespace ftc
+
+using namespace ftc;
+
+extern "C" {
+
+size_t ftc_train_reduce_scratch_bytes(int64_t rows, int c) {
+  return (size_t)2 * red_chunks(rows) * (size_t)c * sizeof(float);
+}
+
+int ftc_train_bn_stats(const void* x, int dtype, int64_t rows, int c, float* mean, float* var, void* scratch, void* stream) {
+  FTC_REQUIRE(x && mean && var && scratch && rows > 0 && c > 0 && dtype_ok(dtype), "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nchunk = red_chunks(rows);
+  const int64_t rpc = (rows + nchunk - 1) / nchunk;
+  dim3 grid(ceil_div(c, RED_CH), nchunk);
+  BnArgs bn = {};
+  if (dtype == DT_F32)
+    col_reduce_kernel<float, 0><<<grid, RED_THREADS, 0, s>>>(cp<float>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
+  else
+    col_reduce_kernel<bf16, 0><<<grid, RED_THREADS, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
+  FTC_POST_LAUNCH();
+  col_reduce_finish_kernel<0><<<ceil_div(c, 128), 128, 0, s>>>((const float*)scratch, nchunk, c, rows, mean, var);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_bn_act(const void* x, void* y, int dtype, int64_t rows, int c, const float* mean, const float* var,
+                     const float* gamma, const float* beta, float eps, int act, const void* residual, void* stream) {
+  FTC_REQUIRE(x && y && mean && var && gamma && beta && rows > 0 && c > 0 && dtype_ok(dtype), "bad argument");
+  FTC_REQUIRE(act == ACT_NONE || act == ACT_SILU || act == ACT_GELU, "activation");
+  cudaStream_t s = (cudaStream_t)stream;
+  BnArgs bn = {mean, var, gamma, beta, eps, act};
+  const int64_t total = rows * c;
+  if (dtype == DT_F32)
+    bn_act_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x), mp<float>(y), total, c, bn, cp<float>(residual));
+  else
+    bn_act_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), total, c, bn, cp<bf16>(residual));
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t rows, int c, const float* mean,
+                         const float* var, const float* gamma, const float* beta, float eps, int act, float* dbeta,
+                         float* dgamma, void* scratch, void* stream) {
+  FTC_REQUIRE(x && dy && dx && mean && var && gamma && beta && dbeta && dgamma && scratch && rows > 0 && c > 0 && dtype_ok(dtype),
+              "bad argument");
+  FTC_REQUIRE(act == ACT_NONE || act == ACT_SILU || act == ACT_GELU, "activation");
+  cudaStream_t s = (cudaStream_t)stream;
+  BnArgs bn = {mean, var, gamma, beta, eps, act};
+  const int nchunk = red_chunks(rows);
+  const int64_t rpc = (rows + nchunk - 1) / nchunk;
+  dim3 grid(ceil_div(c, RED_CH), nchunk);
+  if (dtype == DT_F32)
+    col_reduce_kernel<float, 1><<<grid, RED_THREADS, 0, s>>>(cp<float>(x), cp<float>(dy), rows, c, rpc, (float*)scratch, bn);
+  else
+    col_reduce_kernel<bf16, 1><<<grid, RED_THREADS, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
+  FTC_POST_LAUNCH();
+  col_reduce_finish_kernel<1><<<ceil_div(c, 128), 128, 0, s>>>((const float*)scratch, nchunk, c, rows, dbeta, dgamma);
+  FTC_POST_LAUNCH();
+  const int64_t total = rows * c;
+  const float inv_rows = (float)(1.0 / (double)rows);
+  if (dtype == DT_F32)
+    bn_act_bwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x), cp<float>(dy), mp<float>(dx), total, c, inv_rows, bn, dbeta,
+                                                           dgamma);
+  else
+    bn_act_bwd_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), total, c, inv_rows, bn, dbeta,
+                                                          dgamma);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+static int conv_geom(ConvGeom* g, int batch, int h, int w, int cin, int cout, int ksize, int stride) {
+  FTC_REQUIRE(batch > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "bad geometry");
+  FTC_REQUIRE(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
+  FTC_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
+  g->B = batch; g->H = h; g->W = w; g->Cin = cin; g->Cout = cout; g->k = ksize; g->stride = stride; g->pad = (ksize - 1) / 2;
+  g->Ho = (h - 1) / stride + 1; g->Wo = (w - 1) / stride + 1;
+  return 0;
+}
+
+int ftc_train_conv2d_wgrad(const void* x, const void* dy, int dtype, int batch, int h, int w, int cin, int cout, int ksize,
+                           int stride, float* dw_oihw, void* stream) {
+  FTC_REQUIRE(x && dy && dw_oihw && dtype_ok(dtype), "bad argument");
+  ConvGeom g;
+  int rc = conv_geom(&g, batch, h, w, cin, cout, ksize, stride);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int KK = ksize * ksize * cin;
+  const int64_t M = (int64_t)batch * g.Ho * g.Wo;
+  FTC_CHECK_CUDA(cudaMemsetAsync(dw_oihw, 0, (size_t)cout * KK * sizeof(float), s));
+  const int tiles = ceil_div(KK, GB) * ceil_div(cout, GB);
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>((148 * 4 + tiles - 1) / tiles, (M + 255) / 256));
+  splits = std::min<int64_t>(splits, 65535);
+  int64_t mps = (M + splits - 1) / splits;
+  mps = (mps + GK - 1) / GK * GK;
+  splits = (M + mps - 1) / mps;
+  dim3 grid(ceil_div(KK, GB), ceil_div(cout, GB), (unsigned)splits);
+  if (dtype == DT_F32)
+    conv_wgrad_kernel<float><<<grid, GT, 0, s>>>(cp<float>(x), cp<float>(dy), g, M, mps, dw_oihw);
+  else
+    conv_wgrad_kernel<bf16><<<grid, GT, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), g, M, mps, dw_oihw);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_conv2d_dgrad(const void* dy, int dtype, int batch, int h, int w, int cin, int cout, int ksize, int stride,
+                           const float* w_oihw, const void* add, void* dx, void* stream) {
+  FTC_REQUIRE(dy && w_oihw && dx && dtype_ok(dtype), "bad argument");
+  ConvGeom g;
+  int rc = conv_geom(&g, batch, h, w, cin, cout, ksize, stride);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t M = (int64_t)batch * h * w;
+  FTC_REQUIRE((M + GB - 1) / GB <= 0x7fffffff, "too many pixels");
+  dim3 grid((unsigned)((M + GB - 1) / GB), ceil_div(cin, GB));
+  if (dtype == DT_F32)
+    conv_dgrad_kernel<float><<<grid, GT, 0, s>>>(cp<float>(dy), w_oihw, g, M, cp<float>(add), mp<float>(dx));
+  else
+    conv_dgrad_kernel<bf16><<<grid, GT, 0, s>>>(cp<bf16>(dy), w_oihw, g, M, cp<bf16>(add), mp<bf16>(dx));
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_dwconv3x3(const void* x, void* y, int dtype, int batch, int h, int w, int c, int stride, const float* w9c,
+                        void* stream) {
+  FTC_REQUIRE(x && y && w9c && dtype_ok(dtype) && batch > 0 && (stride == 1 || stride == 2), "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
+  const int64_t total = (int64_t)batch * ho * wo * c;
+  if (dtype == DT_F32)
+    dw_fwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x), mp<float>(y), batch, h, w, c, ho, wo, stride, w9c);
+  else
+    dw_fwd_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), batch, h, w, c, ho, wo, stride, w9c);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_dwconv3x3_dgrad(const void* dy, void* dx, int dtype, int batch, int h, int w, int c, int stride, const float* w9c,
+                              void* stream) {
+  FTC_REQUIRE(dy && dx && w9c && dtype_ok(dtype) && batch > 0 && (stride == 1 || stride == 2), "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
+  const int64_t total = (int64_t)batch * h * w * c;
+  if (dtype == DT_F32)
+    dw_dgrad_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(dy), mp<float>(dx), batch, h, w, c, ho, wo, stride, w9c);
+  else
+    dw_dgrad_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(cp<bf16>(dy), mp<bf16>(dx), batch, h, w, c, ho, wo, stride, w9c);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_dwconv3x3_wgrad(const void* x, const void* dy, int dtype, int batch, int h, int w, int c, int stride, float* dw9c,
+                              void* stream) {
+  FTC_REQUIRE(x && dy && dw9c && dtype_ok(dtype) && batch > 0 && (stride == 1 || stride == 2), "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
+  FTC_CHECK_CUDA(cudaMemsetAsync(dw9c, 0, (size_t)9 * c * sizeof(float), s));
+  const int64_t P = (int64_t)batch * ho * wo;
+  const int cblocks = ceil_div(c, 32);
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>((148 * 8 + cblocks - 1) / cblocks, (P + 63) / 64));
+  splits = std::min<int64_t>(splits, 65535);
+  const int64_t pps = (P + splits - 1) / splits;
+  splits = (P + pps - 1) / pps;
+  dim3 grid(cblocks, (unsigned)splits);
+  if (dtype == DT_F32)
+    dw_wgrad_kernel<float><<<grid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), batch, h, w, c, ho, wo, stride, pps, dw9c);
+  else
+    dw_wgrad_kernel<bf16><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), batch, h, w, c, ho, wo, stride, pps, dw9c);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_spatial_sum(const void* x, const void* y, int dtype, int batch, int hw, int c, float scale, float* out,
+                          void* stream) {
+  FTC_REQUIRE(x && out && dtype_ok(dtype) && batch > 0 && batch <= 65535 && hw > 0 && c > 0, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(ceil_div(c, RED_CH), batch);
+  if (dtype == DT_F32) {
+    if (y) spatial_sum_kernel<float, 1><<<grid, RED_THREADS, 0, s>>>(cp<float>(x), cp<float>(y), hw, c, scale, out);
+    else spatial_sum_kernel<float, 0><<<grid, RED_THREADS, 0, s>>>(cp<float>(x), nullptr, hw, c, scale, out);
+  } else {
+    if (y) spatial_sum_kernel<bf16, 1><<<grid, RED_THREADS, 0, s>>>(cp<bf16>(x), cp<bf16>(y), hw, c, scale, out);
+    else spatial_sum_kernel<bf16, 0><<<grid, RED_THREADS, 0, s>>>(cp<bf16>(x), nullptr, hw, c, scale, out);
+  }
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_scale_bc(const void* x, const float* scale_bc, const float* bias_bc, float bias_mul, void* y, int dtype, int batch,
+                       int hw, int c, void* stream) {
+  FTC_REQUIRE(x && scale_bc && y && dtype_ok(dtype) && batch > 0 && hw > 0 && c > 0, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t total = (int64_t)batch * hw * c;
+  if (dtype == DT_F32)
+    scale_bc_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x), scale_bc, mp<float>(y), hw, c, total, bias_bc, bias_mul);
+  else
+    scale_bc_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(cp<bf16>(x), scale_bc, mp<bf16>(y), hw, c, total, bias_bc, bias_mul);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_se_fc(const float* mean, int batch, int c, int sq, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* hid_pre, float* gate, void* stream) {
+  FTC_REQUIRE(mean && w1 && b1 && w2 && b2 && hid_pre && gate && batch > 0 && c > 0 && sq > 0 && sq <= 4096, "bad argument");
+  se_fc_fwd_kernel<<<batch, 256, (size_t)sq * sizeof(float), (cudaStream_t)stream>>>(mean, c, sq, w1, b1, w2, b2, hid_pre, gate);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_se_fc_bwd(const float* dgate, const float* gate, const float* hid_pre, const float* mean, int batch, int c, int sq,
+                        const float* w1, const float* w2, float* dgp, float* dhp, float* dmean, float* dw1, float* db1,
+                        float* dw2, float* db2, void* stream) {
+  FTC_REQUIRE(dgate && gate && hid_pre && mean && w1 && w2 && dgp && dhp && dmean && dw1 && db1 && dw2 && db2, "null argument");
+  FTC_REQUIRE(batch > 0 && c > 0 && sq > 0 && (size_t)(c + sq) * sizeof(float) <= 48 * 1024, "bad geometry");
+  cudaStream_t s = (cudaStream_t)stream;
+  se_fc_bwd_data_kernel<<<batch, 256, (size_t)(c + sq) * sizeof(float), s>>>(dgate, gate, hid_pre, c, sq, w1, w2, dgp, dhp, dmean);
+  FTC_POST_LAUNCH();
+  const int64_t n = (int64_t)c * sq;
+  se_fc_bwd_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dgp, dhp, hid_pre, mean, batch, c, sq, dw1, db1, dw2, db2);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_upsample2x_bwd(const void* dy, void* dx, int dtype, int batch, int h, int w, int c, void* stream) {
+  FTC_REQUIRE(dy && dx && dtype_ok(dtype) && batch > 0 && batch <= 65535 && h > 0 && w > 0 && c > 0, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(h, batch);
+  const float sy = (float)(h - 1) / (float)(2 * h - 1), sx = (float)(w - 1) / (float)(2 * w - 1);
+  if (dtype == DT_F32)
+    upsample2x_bwd_kernel<float><<<grid, 256, 0, s>>>(cp<float>(dy), mp<float>(dx), h, w, c, sy, sx);
+  else
+    upsample2x_bwd_kernel<bf16><<<grid, 256, 0, s>>>(cp<bf16>(dy), mp<bf16>(dx), h, w, c, sy, sx);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -20,11 +20,11 @@ from ..engine import DetectorEngine, default_precision
 from ._tree import Node, populate
 
 
-def _no_train(mod: nn.Module):
-    if mod.training and torch.is_grad_enabled():
-        raise NotImplementedError(
-            "findtextcenternet_b200: the train-mode (autograd) detector step is not built yet; "
-            "call .eval() / torch.no_grad() for the sm_100a inference engine")
+def _train_step(mod: nn.Module) -> bool:
+    """train1.py:128-170 calls the model in train mode with autograd on: that goes through the per-layer train kernels
+    (findtextcenternet_b200/train_ops.py: batch-statistics BatchNorm, StochasticDepth, a tape for backward); everything
+    else (eval(), no_grad) through the fused inference engine."""
+    return mod.training and torch.is_grad_enabled()
 
 
 class BackboneModel(nn.Module):
@@ -87,13 +87,15 @@ class CenterNetDetection(nn.Module):
         return self._engine
 
     def _run(self, x: Tensor, want_heat10: bool):
-        _no_train(self)
         if not x.is_cuda:
             raise RuntimeError("findtextcenternet_b200 detector: input must be a CUDA tensor (no CPU path)")
         with torch.no_grad():
             return self.engine(x.device).forward(x, want_heat10)
 
     def forward(self, x):
+        if _train_step(self):
+            from ..train_ops import detection_train_forward
+            return detection_train_forward(self, x)
         heat9, feat, _ = self._run(x, False)
         return heat9, feat
 
@@ -106,7 +108,9 @@ class SimpleDecoder(nn.Module):
         populate(self, arch.simple_decoder_specs("dec"), strip="dec.", backbone_prefix="\0")
 
     def forward(self, x) -> List[Tensor]:
-        _no_train(self)
+        if _train_step(self):
+            from ..train_ops import simple_decoder_train_forward
+            return simple_decoder_train_forward(self, x)
         from ..linear import mlp_decoder_forward
         return mlp_decoder_forward(self, x)
 

@@ -1,0 +1,302 @@
+"""Train-mode forward + backward of the detector (train1.py:128-170 calls ``model(image, fmask)`` in train mode and
+``loss.backward()``): each autograd node is one C-ABI kernel call of include/ftc_b200.h ("train step" section,
+csrc/train_ops.cu) or one of the shared implicit-GEMM convolution kernels; torch provides the tape, device memory and the
+layout glue (NCHW<->NHWC permutes, the Leafmap channel concat, the fmask gather) only.  No CPU path: CPU tensors raise.
+
+Reference semantics: torchvision ``Conv2dNormActivation`` / ``FusedMBConv`` / ``MBConv`` / ``SqueezeExcitation`` /
+``StochasticDepth("row")`` (efficientnet.py:105-231, ops/misc.py:69-126,225-261, ops/stochastic_depth.py),
+``Leafmap.forward`` (models/detector.py:192-201), ``SimpleDecoder`` (:232-254), ``nn.BatchNorm2d`` in train mode
+(batch statistics, momentum 0.1, unbiased running variance).
+
+Status: first correct path (CUDA-core gradients in fp32 / bf16 storage; stride-1 data gradients of bf16 convolutions reuse
+the tcgen05 forward kernel with transposed, flipped weights).  ``K`` is the kernel namespace; the CPU tests swap in
+``oracle.train_oracle`` to check the host-side graph logic against the reference's autograd.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+
+from . import _lib, _ops, arch
+
+K = _ops
+BN_MOMENTUM = 0.1              # nn.BatchNorm2d / BatchNorm1d default; torchvision passes only eps
+STOCHASTIC_DEPTH_PROB = 0.2    # torchvision EfficientNet.__init__ default (the reference does not override it)
+
+
+def _backend(x: Tensor) -> int:
+    return _lib.GEMM_TCGEN05 if x.dtype == torch.bfloat16 else _lib.GEMM_SIMT
+
+
+class _Conv2d(Function):
+    """nn.Conv2d(k in {1,3}, padding=(k-1)//2, stride, bias optional) on NHWC tensors; weight OIHW."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride):
+        ctx.save_for_backward(x, w)
+        ctx.stride, ctx.has_bias = stride, bias is not None
+        return K.conv2d(x, w, stride, None, bias, _lib.ACT_NONE, None, None, _backend(x))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        cout, cin, k, _ = w.shape
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if ctx.stride == 1 and x.dtype == torch.bfloat16 and cout % 8 == 0:
+                # stride-1 data gradient = the same convolution with the taps rotated 180 degrees and the channel roles
+                # swapped: runs on the tcgen05 forward kernel
+                wt = w.detach().float().flip(2, 3).transpose(0, 1).contiguous()
+                dx = K.conv2d(dy, wt, 1, None, None, _lib.ACT_NONE, None, None, _lib.GEMM_TCGEN05)
+            else:
+                dx = K.conv2d_dgrad(dy, w, x.shape[1], x.shape[2], ctx.stride)
+        if ctx.needs_input_grad[1]:
+            dw = K.conv2d_wgrad(x, dy, k, ctx.stride).to(w.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            mean, _ = K.bn_stats(dy)
+            db = mean * float(dy.numel() // cout)
+        return dx, dw, db, None
+
+
+class _BNAct(Function):
+    """y = act(BatchNorm_train(x)) (+ residual); mean / var are the batch statistics of x (their dependence on x is part of
+    the backward formula, autograd sees them as constants)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mean, var, eps, act, residual):
+        ctx.save_for_backward(x, gamma, beta, mean, var)
+        ctx.eps, ctx.act, ctx.has_res = eps, act, residual is not None
+        return K.bn_act(x, mean, var, gamma, beta, eps, act, residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, var = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx, dgamma, dbeta = K.bn_act_bwd(x, dy, mean, var, gamma, beta, ctx.eps, ctx.act)
+        return dx, dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None, None, None, None, (dy if ctx.has_res else None)
+
+
+class _DwConv3x3(Function):
+    @staticmethod
+    def forward(ctx, x, w, stride):
+        w9c = w.detach().float().reshape(w.shape[0], 9).t().contiguous()
+        ctx.save_for_backward(x, w9c)
+        ctx.stride, ctx.wshape, ctx.wdtype = stride, w.shape, w.dtype
+        return K.dwconv3x3_raw(x, w9c, stride)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w9c = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = K.dwconv3x3_dgrad(dy, w9c, x.shape[1], x.shape[2], ctx.stride) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = K.dwconv3x3_wgrad(x, dy, ctx.stride).t().reshape(ctx.wshape).to(ctx.wdtype)
+        return dx, dw, None
+
+
+class _SqueezeExcite(Function):
+    """torchvision SqueezeExcitation: x * sigmoid(fc2(silu(fc1(mean_hw(x)))))."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        b, h, w, c = x.shape
+        s = w1.shape[0]
+        w1m, w2m = w1.detach().float().reshape(s, c).contiguous(), w2.detach().float().reshape(c, s).contiguous()
+        mean = K.spatial_sum(x, None, 1.0 / (h * w))
+        hid_pre, gate = K.se_fc_train(mean, w1m, b1.detach().float().contiguous(), w2m, b2.detach().float().contiguous())
+        ctx.save_for_backward(x, mean, hid_pre, gate, w1m, w2m)
+        ctx.shapes = (w1.shape, w2.shape, w1.dtype)
+        return K.scale_bc(x, gate)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, hid_pre, gate, w1m, w2m = ctx.saved_tensors
+        dy = dy.contiguous()
+        b, h, w, c = x.shape
+        dgate = K.spatial_sum(dy, x, 1.0)
+        dmean, dw1, db1, dw2, db2 = K.se_fc_train_bwd(dgate, gate, hid_pre, mean, w1m, w2m)
+        dx = K.scale_bc(dy, gate, dmean, 1.0 / (h * w))
+        s1, s2, dt = ctx.shapes
+        return dx, dw1.reshape(s1).to(dt), db1.to(dt), dw2.reshape(s2).to(dt), db2.to(dt)
+
+
+class _Upsample2x(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return K.upsample2x(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.upsample2x_bwd(dy.contiguous())
+
+
+class _RowScale(Function):
+    """StochasticDepth "row" mode: x * noise[b] (noise = bernoulli(1 - p) / (1 - p), ops/stochastic_depth.py:32-39)."""
+
+    @staticmethod
+    def forward(ctx, x, noise):
+        sc = noise.float().reshape(-1, 1).expand(x.shape[0], x.shape[-1]).contiguous()
+        ctx.save_for_backward(sc)
+        return K.scale_bc(x, sc)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (sc,) = ctx.saved_tensors
+        return K.scale_bc(dy.contiguous(), sc), None
+
+
+# ---- layer helpers over the parameter containers of models/_tree.py ------------------------------------------------
+def _sub(node, name):
+    return getattr(node, str(name))
+
+
+def conv2d(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, stride: int = 1) -> Tensor:
+    return _Conv2d.apply(x, w, bias, stride)
+
+
+def batchnorm_act(x: Tensor, bn, eps: float, act: int, residual: Optional[Tensor] = None) -> Tensor:
+    """Train-mode BatchNorm (+ activation, + residual after it); updates running_mean / running_var /
+    num_batches_tracked like torch (momentum 0.1, unbiased variance into running_var)."""
+    with torch.no_grad():
+        mean, var = K.bn_stats(x)
+        n = x.numel() // x.shape[-1]
+        bn.running_mean.mul_(1 - BN_MOMENTUM).add_(mean.to(bn.running_mean.dtype), alpha=BN_MOMENTUM)
+        unbiased = var * (float(n) / max(n - 1, 1))
+        bn.running_var.mul_(1 - BN_MOMENTUM).add_(unbiased.to(bn.running_var.dtype), alpha=BN_MOMENTUM)
+        bn.num_batches_tracked += 1
+    return _BNAct.apply(x, bn.weight, bn.bias, mean, var, eps, act, residual)
+
+
+def conv_bn_act(x: Tensor, node, eps: float, act: int, stride: int = 1, residual: Optional[Tensor] = None) -> Tensor:
+    """torchvision Conv2dNormActivation: node.0 = conv (no bias), node.1 = BatchNorm2d."""
+    w = _sub(node, 0).weight
+    if w.shape[1] == 1 and w.shape[0] > 1 and w.shape[-1] == 3 and x.shape[-1] == w.shape[0]:
+        y = _DwConv3x3.apply(x, w, stride)
+    else:
+        y = conv2d(x, w, None, stride)
+    return batchnorm_act(y, _sub(node, 1), eps, act, residual)
+
+
+def _stochastic_depth(branch: Tensor, inp: Tensor, p: float, noise: Optional[Tensor]) -> Tensor:
+    """result = StochasticDepth(p, "row")(branch) + input (efficientnet.py:166-169)."""
+    if p == 0.0 and noise is None:
+        return None   # caller fuses the add into the preceding kernel
+    if noise is None:
+        survival = 1.0 - p
+        noise = torch.empty(branch.shape[0], dtype=torch.float32, device=branch.device).bernoulli_(survival)
+        if survival > 0.0:
+            noise.div_(survival)
+    return _RowScale.apply(branch, noise) + inp
+
+
+def _block(x: Tensor, blk, st: arch.StageCfg, cin: int, stride: int, sd_prob: float, noise: Optional[Tensor]) -> Tensor:
+    eps = arch.BACKBONE_BN_EPS
+    res = x if (stride == 1 and cin == st.cout) else None
+    fuse_res = res is not None and sd_prob == 0.0 and noise is None
+    r = res if fuse_res else None
+    b = blk.block
+    if st.fused:
+        if st.expand != 1:
+            y = conv_bn_act(x, _sub(b, 0), eps, _lib.ACT_SILU, stride)
+            y = conv_bn_act(y, _sub(b, 1), eps, _lib.ACT_NONE, 1, r)
+        else:
+            y = conv_bn_act(x, _sub(b, 0), eps, _lib.ACT_SILU, stride, r)     # residual after the SiLU
+    else:
+        y = conv_bn_act(x, _sub(b, 0), eps, _lib.ACT_SILU, 1)
+        y = conv_bn_act(y, _sub(b, 1), eps, _lib.ACT_SILU, stride)
+        se = _sub(b, 2)
+        y = _SqueezeExcite.apply(y, se.fc1.weight, se.fc1.bias, se.fc2.weight, se.fc2.bias)
+        y = conv_bn_act(y, _sub(b, 3), eps, _lib.ACT_NONE, 1, r)
+    if res is not None and not fuse_res:
+        y = _stochastic_depth(y, res, sd_prob, noise)
+    return y
+
+
+def backbone_train_forward(features, x_nhwc: Tensor, model_size: str = "xl", sd_prob: float = STOCHASTIC_DEPTH_PROB,
+                           sd_noise: Optional[dict] = None) -> List[Tensor]:
+    """BackboneModel.forward (models/detector.py:139-146) in train mode -> taps [x1, x2, x3, x4] (NHWC).
+    sd_noise: optional {block index: noise [B]} to pin the StochasticDepth draws (tests)."""
+    _, stages, _ = arch.backbone_cfg(model_size)
+    total = sum(st.layers for st in stages)
+    cpad = (-x_nhwc.shape[-1]) % 8
+    stem = _sub(features, 0)
+    w0 = _sub(stem, 0).weight
+    if cpad:   # the GEMM kernels take channel counts in multiples of 8: zero channels, zero weights
+        x_nhwc = torch.nn.functional.pad(x_nhwc, (0, cpad))
+        w0 = torch.nn.functional.pad(w0, (0, 0, 0, 0, 0, cpad))
+    y = batchnorm_act(conv2d(x_nhwc.contiguous(), w0, None, 2), _sub(stem, 1), arch.BACKBONE_BN_EPS, _lib.ACT_SILU)
+    taps = []
+    bid = 0
+    for si, st in enumerate(stages, start=1):
+        stage = _sub(features, si)
+        for li in range(st.layers):
+            cin = st.cin if li == 0 else st.cout
+            stride = st.stride if li == 0 else 1
+            p = sd_prob * float(bid) / total
+            noise = None if sd_noise is None else sd_noise.get(bid)
+            y = _block(y, _sub(stage, li), st, cin, stride, p, noise)
+            bid += 1
+        if si in arch.TAP_FEATURE_IDX:
+            taps.append(y)
+    y = conv_bn_act(y, _sub(features, len(stages) + 1), arch.BACKBONE_BN_EPS, _lib.ACT_SILU)
+    taps.append(y)
+    return taps
+
+
+def leafmap_train_forward(leaf, taps: List[Tensor]) -> Tensor:
+    """Leafmap.forward (models/detector.py:192-201) in train mode; NHWC in, NHWC [B,H,W,out_dim] out."""
+    y = None
+    n = len(taps)
+    for i in range(n):
+        x = taps[n - 1 - i]
+        x = batchnorm_act(x, _sub(leaf.in_bn, n - 1 - i), arch.HEAD_BN_EPS, _lib.ACT_NONE)
+        if y is not None:
+            x = torch.cat([y, x], dim=-1)
+        up = _sub(leaf.upsamplers, i)
+        y = conv_bn_act(x, up, arch.HEAD_BN_EPS, _lib.ACT_GELU)
+        if i < n - 1:
+            y = _Upsample2x.apply(y)
+    top = _sub(leaf.top_conv, 0)
+    return conv2d(y, top.weight, top.bias, 1)
+
+
+def detection_train_forward(det, x: Tensor, sd_prob: float = STOCHASTIC_DEPTH_PROB, sd_noise: Optional[dict] = None
+                            ) -> Tuple[Tensor, Tensor]:
+    """CenterNetDetection.forward (models/detector.py:217-230) in train mode: x NCHW in [0,1] -> (heatmap [B,9,H/4,W/4],
+    feature [B,100,H/4,W/4]) fp32 NCHW with autograd history."""
+    if not x.is_cuda:
+        raise RuntimeError("findtextcenternet_b200 detector: input must be a CUDA tensor (no CPU path)")
+    dt = torch.float32 if det.precision == "fp32" else torch.bfloat16
+    xh = (x.float() * 2 - 1).permute(0, 2, 3, 1).to(dt).contiguous()
+    taps = backbone_train_forward(det.backbone.features, xh, det.model_size, sd_prob, sd_noise)
+    outs = [leafmap_train_forward(getattr(det, name), taps).float() for name, _ in arch.HEADS]
+    heat = torch.cat(outs[:-1], dim=-1).permute(0, 3, 1, 2).contiguous()
+    feat = outs[-1].permute(0, 3, 1, 2).contiguous()
+    return heat, feat
+
+
+def simple_decoder_train_forward(dec, x: Tensor) -> List[Tensor]:
+    """SimpleDecoder.forward (models/detector.py:250-254) in train mode: x [N,100] -> 3 x [N, modulo] fp32."""
+    if not x.is_cuda:
+        raise RuntimeError("findtextcenternet_b200 SimpleDecoder: input must be a CUDA tensor (no CPU path)")
+    from .engine import default_precision
+    prec = getattr(dec, "precision", None) or default_precision()
+    dt = torch.float32 if prec == "fp32" else torch.bfloat16
+    n = x.shape[0]
+    cpad = (-x.shape[1]) % 8
+    xp = torch.nn.functional.pad(x.to(dt), (0, cpad)).reshape(n, 1, 1, -1).contiguous()
+    outs = []
+    for i, m in enumerate(arch.MODULO_LIST):
+        blk = _sub(dec.blocks, i)
+        w0 = torch.nn.functional.pad(_sub(blk, 0).weight, (0, cpad))[:, :, None, None]
+        y = batchnorm_act(conv2d(xp, w0), _sub(blk, 1), arch.HEAD_BN_EPS, _lib.ACT_GELU)
+        y = batchnorm_act(conv2d(y, _sub(blk, 3).weight[:, :, None, None]), _sub(blk, 4), arch.HEAD_BN_EPS, _lib.ACT_GELU)
+        lin = _sub(blk, 6)
+        o = conv2d(y, lin.weight[:, :, None, None], lin.bias)
+        outs.append(o.reshape(n, m).float())
+    return outs

@@ -198,6 +198,60 @@ int ftc_op_attention(const void* q, int q_stride, int q_off, const void* k, cons
                      const float* mask, void* out, int out_stride, int dtype, int batch, int heads, int hd, int lt, int ls,
                      void* stream);
 
+
+/* ---- train step: forward in train mode + backward of the detector blocks (train1.py:128-170 differentiates
+ * models/detector.py:217-268 through torch autograd; here each autograd node is one of the entries below, see
+ * findtextcenternet_b200/train_ops.py).  First correct path: CUDA-core kernels, fp32 math, NHWC fp32 / bf16 tensors (dtype =
+ * FTC_PREC_*).  The forward convolutions of a train step are ftc_op_conv2d with scale = bias = NULL (raw output).
+ *
+ * BatchNorm in train mode (nn.BatchNorm2d / BatchNorm1d, torch batch_norm) over x [rows, c] (rows = B*H*W):
+ *   ftc_train_bn_stats   mean[c], var[c] = batch mean and BIASED variance (fp32); scratch: ftc_train_reduce_scratch_bytes
+ *   ftc_train_bn_act     y = act(gamma * (x - mean) * rsqrt(var + eps) + beta) (+ residual); act = none | SiLU | GELU(erf)
+ *                        (torchvision Conv2dNormActivation ops/misc.py:69-126; Leafmap conv-BN-GELU models/detector.py:162-186)
+ *   ftc_train_bn_act_bwd dbeta[c] = sum dz, dgamma[c] = sum dz * xhat, dx = gamma * rstd * (dz - dbeta/rows - xhat * dgamma/rows)
+ *                        with dz = dy * act'(gamma * xhat + beta) recomputed from x (the residual's gradient is dy itself) */
+size_t ftc_train_reduce_scratch_bytes(int64_t rows, int c);
+int ftc_train_bn_stats(const void* x, int dtype, int64_t rows, int c, float* mean, float* var, void* scratch, void* stream);
+int ftc_train_bn_act(const void* x, void* y, int dtype, int64_t rows, int c, const float* mean, const float* var,
+                     const float* gamma, const float* beta, float eps, int act, const void* residual, void* stream);
+int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t rows, int c, const float* mean,
+                         const float* var, const float* gamma, const float* beta, float eps, int act, float* dbeta,
+                         float* dgamma, void* scratch, void* stream);
+/* gradients of nn.Conv2d(k = 1 | 3, padding = (k-1)/2, stride = 1 | 2, bias-free): x [batch,h,w,cin], dy [batch,ho,wo,cout] NHWC;
+ * weights and their gradient fp32 OIHW (the parameter's own layout).  wgrad OVERWRITES dw_oihw (fp32 atomics over pixel
+ * splits); dgrad writes dx = conv_transpose(dy, w) (+ add, e.g. the gradient arriving over a residual connection). */
+int ftc_train_conv2d_wgrad(const void* x, const void* dy, int dtype, int batch, int h, int w, int cin, int cout, int ksize,
+                           int stride, float* dw_oihw, void* stream);
+int ftc_train_conv2d_dgrad(const void* dy, int dtype, int batch, int h, int w, int cin, int cout, int ksize, int stride,
+                           const float* w_oihw, const void* add, void* dx, void* stream);
+/* depthwise 3x3 (pad 1, stride 1 | 2) of MBConv (efficientnet.py:136-147): raw forward, data gradient, weight gradient;
+ * weights fp32 [9][c] tap-major (as ftc_op_dwconv3x3); h, w are the INPUT extents; wgrad overwrites dw9c */
+int ftc_train_dwconv3x3(const void* x, void* y, int dtype, int batch, int h, int w, int c, int stride, const float* w9c,
+                        void* stream);
+int ftc_train_dwconv3x3_dgrad(const void* dy, void* dx, int dtype, int batch, int h, int w, int c, int stride, const float* w9c,
+                              void* stream);
+int ftc_train_dwconv3x3_wgrad(const void* x, const void* dy, int dtype, int batch, int h, int w, int c, int stride, float* dw9c,
+                              void* stream);
+/* SqueezeExcitation (torchvision ops/misc.py:225-261) on x [batch, hw, c]:
+ *   ftc_train_spatial_sum  out[b][c] = scale * sum_hw x (* y when y != NULL): the squeeze mean (scale = 1/hw) and, in the
+ *                          backward, dgate = sum_hw dy * x
+ *   ftc_train_se_fc        hid_pre = W1 mean + b1, gate = sigmoid(W2 silu(hid_pre) + b2); W1 [sq][c], W2 [c][sq]
+ *   ftc_train_scale_bc     y = x * scale_bc[b][c] (+ bias_mul * bias_bc[b][c]): the excitation, its data gradient
+ *                          dx = dy * gate + dmean / hw, and StochasticDepth "row" mode (scale constant per image)
+ *   ftc_train_se_fc_bwd    dgate -> dmean [batch][c] and dW1, db1, dW2, db2 (overwritten); dgp [batch][c], dhp [batch][sq] scratch */
+int ftc_train_spatial_sum(const void* x, const void* y, int dtype, int batch, int hw, int c, float scale, float* out,
+                          void* stream);
+int ftc_train_scale_bc(const void* x, const float* scale_bc, const float* bias_bc, float bias_mul, void* y, int dtype, int batch,
+                       int hw, int c, void* stream);
+int ftc_train_se_fc(const float* mean, int batch, int c, int sq, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* hid_pre, float* gate, void* stream);
+int ftc_train_se_fc_bwd(const float* dgate, const float* gate, const float* hid_pre, const float* mean, int batch, int c, int sq,
+                        const float* w1, const float* w2, float* dgp, float* dhp, float* dmean, float* dw1, float* db1,
+                        float* dw2, float* db2, void* stream);
+/* adjoint of nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True, models/detector.py:167-186): dy [batch,2h,2w,c] ->
+ * dx [batch,h,w,c] */
+int ftc_train_upsample2x_bwd(const void* dy, void* dx, int dtype, int batch, int h, int w, int c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

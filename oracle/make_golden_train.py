@@ -1,0 +1,105 @@
+"""Generate tests/golden/train_xl64_seed0.npz: ONE train-mode forward + backward of the UNMODIFIED reference
+``TextDetectorModel`` (imported from /root/reference, torch autograd on CPU, fp32) on the seeded synthetic checkpoint.
+
+Runs only in the build container (the GPU box has no /root/reference); the output is committed.
+    python oracle/make_golden_train.py
+
+Contents: input x [2,3,64,64] (the reference network is fully convolutional; 64 px keeps the XL model's 2 444-entry state
+dict but makes the CPU run seconds), a fixed fmask, the heatmap and the three SimpleDecoder outputs, the random cotangents
+w_heat / w_dec{i} that define the scalar  L = sum(heat * w_heat) + sum_i sum(dec_i * w_dec_i),  and for EVERY parameter the
+gradient's L2 norm and its dot product with a deterministic +-1 probe (two fingerprints per tensor instead of 262 M floats),
+plus a few small gradients and updated BatchNorm buffers in full.  StochasticDepth is switched off (p = 0) on the
+reference's blocks so the run is deterministic; train_ops.py is called with sd_prob = 0 to match.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from findtextcenternet_b200 import synthetic  # noqa: E402
+
+FULL = ("detector.backbone.features.0.1.weight", "detector.backbone.features.0.0.weight",
+        "detector.backbone.features.4.0.block.1.0.weight", "detector.backbone.features.4.0.block.2.fc1.weight",
+        "detector.backbone.features.4.0.block.2.fc2.bias", "detector.backbone.features.7.7.block.3.1.bias",
+        "detector.keyheatmap.in_bn.3.weight", "detector.sizes.top_conv.0.bias", "detector.feature.upsamplers.3.1.weight",
+        "decoder.blocks.1.4.bias", "decoder.blocks.2.6.bias")
+BUFS = ("detector.backbone.features.0.1.running_mean", "detector.backbone.features.0.1.running_var",
+        "detector.backbone.features.6.3.block.1.1.running_var", "detector.code4.upsamplers.2.1.running_mean",
+        "decoder.blocks.0.1.running_var", "detector.backbone.features.0.1.num_batches_tracked")
+
+
+def probe(shape, i):
+    n = int(np.prod(shape)) if len(shape) else 1
+    idx = np.arange(n, dtype=np.int64)
+    v = (((idx * 2654435761 + i * 40503) >> 7) & 1).astype(np.float64) * 2 - 1
+    return v.reshape(shape)
+
+
+def run(dtype):
+    from models.detector import TextDetectorModel
+    from torchvision.ops import StochasticDepth
+    torch.manual_seed(0)
+    model = TextDetectorModel(pre_weights=False)
+    model.load_state_dict(synthetic.detector_state_dict(0), strict=True)
+    model = model.to(dtype).train()
+    for m in model.modules():
+        if isinstance(m, StochasticDepth):
+            m.p = 0.0
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(2, 3, 64, 64, generator=g)
+    fmask = torch.rand(2 * 16 * 16, generator=g) < 0.25
+    heat, dec = model(x.to(dtype), fmask)
+    w_heat = torch.randn(heat.shape, generator=g)
+    w_dec = [torch.randn(d.shape, generator=g) / 30 for d in dec]
+    loss = (heat * w_heat.to(dtype)).sum() + sum((d * w.to(dtype)).sum() for d, w in zip(dec, w_dec))
+    loss.backward()
+    return model, x, fmask, heat.detach(), [d.detach() for d in dec], w_heat, w_dec, float(loss.detach())
+
+
+def main():
+    # truth = the reference in float64 (same modules, .double()); the fp32 run of the same reference gives, per parameter,
+    # the rounding noise a correct fp32 implementation is entitled to (BatchNorm betas / conv biases that feed another
+    # batch-statistics layer have near-zero true gradients and fp32 noise far above them)
+    model, x, fmask, heat, dec, w_heat, w_dec, loss = run(torch.float64)
+    model32, _, _, heat32, dec32, _, _, loss32 = run(torch.float32)
+    out = {"x": x.numpy(), "fmask": fmask.numpy(), "heatmap": heat.float().numpy(), "w_heat": w_heat.numpy(),
+           "heatmap_fp32_err": np.array(float((heat32.double() - heat).norm() / heat.norm()))}
+    for i in range(3):
+        out[f"dec{i}"] = dec[i].float().numpy()
+        out[f"w_dec{i}"] = w_dec[i].numpy()
+    names, norms, dots, errs = [], [], [], []
+    p32 = dict(model32.named_parameters())
+    for i, (n, p) in enumerate(model.named_parameters()):
+        assert p.grad is not None, n
+        gd = p.grad.numpy()
+        names.append(n)
+        norms.append(float(np.linalg.norm(gd)))
+        dots.append(float((gd * probe(gd.shape, i)).sum()))
+        errs.append(float(np.linalg.norm(p32[n].grad.double().numpy() - gd)))
+    out["grad_names"] = np.array(names)
+    out["grad_norm"] = np.array(norms)
+    out["grad_dot"] = np.array(dots)
+    out["grad_fp32_err"] = np.array(errs)
+    params = dict(model.named_parameters())
+    for k in FULL:
+        out["full/" + k] = params[k].grad.float().numpy()
+    bufs = dict(model.named_buffers())
+    for k in BUFS:
+        out["buf/" + k] = bufs[k].double().numpy()
+    path = os.path.join(GOLD, "train_xl64_seed0.npz")
+    np.savez_compressed(path, **out)
+    rel = np.array(errs) / (np.array(norms) + 1e-30)
+    print("wrote", path, os.path.getsize(path), "bytes; loss", loss, loss32, "fmask rows", int(fmask.sum()))
+    print("reference fp32-vs-fp64 gradient error: median %.2e, p99 %.2e, max %.2e; heatmap %.2e" %
+          (np.median(rel), np.quantile(rel, 0.99), rel.max(), float(out["heatmap_fp32_err"])))
+
+
+if __name__ == "__main__":
+    main()

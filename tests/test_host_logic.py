@@ -54,7 +54,7 @@ def test_product_path_has_no_cpu_fallback():
     t = Transformer(**ModelDimensions(embed_dim=64, head_num=4, enc_block_num=1, dec_block_num=1).__dict__).eval()
     with pytest.raises(RuntimeError):
         t(torch.zeros(1, 8, 106), torch.zeros(1, 8, dtype=torch.long))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):     # the train-mode (autograd) path has no CPU route either
         m.train().detector(torch.zeros(1, 3, 768, 768))
     # nothing under the package imports the oracle
     pkg = os.path.join(ROOT, "findtextcenternet_b200")

@@ -1,0 +1,206 @@
+"""CPU: the train-step oracle (oracle/train_oracle.py) against torch autograd over the modules the reference differentiates,
+and the host-side autograd graph of findtextcenternet_b200/train_ops.py (kernel namespace swapped for the oracle) against the
+reference-generated golden of a full train-mode forward + backward (tests/golden/train_xl64_seed0.npz)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, rel_l2
+from oracle import train_oracle as TO
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("k,stride,h,w", [(1, 1, 5, 7), (3, 1, 6, 5), (3, 2, 8, 6), (3, 2, 7, 9), (1, 2, 6, 6)])
+def test_conv_grads_match_autograd(k, stride, h, w):
+    g = torch.Generator().manual_seed(k * 10 + stride)
+    x = torch.randn(2, 5, h, w, generator=g, requires_grad=True)
+    wt = torch.randn(6, 5, k, k, generator=g, requires_grad=True)
+    y = F.conv2d(x, wt, None, stride, (k - 1) // 2)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    assert rel_l2(TO.conv2d(nhwc(x.detach()), wt, stride), nhwc(y.detach())) < 1e-6
+    assert rel_l2(TO.conv2d_wgrad(nhwc(x.detach()), nhwc(dy), k, stride), wt.grad) < 1e-6
+    add = torch.randn(2, h, w, 5, generator=g)
+    dx = TO.conv2d_dgrad(nhwc(dy), wt, h, w, stride, add)
+    assert rel_l2(dx, nhwc(x.grad) + add) < 1e-6
+
+
+@pytest.mark.parametrize("act", [TO.ACT_NONE, TO.ACT_SILU, TO.ACT_GELU])
+def test_bn_act_matches_autograd(act):
+    g = torch.Generator().manual_seed(act)
+    x = (torch.randn(3, 6, 5, 4, generator=g) * 2 + 0.5).requires_grad_()
+    gamma = torch.randn(6, generator=g).requires_grad_()
+    beta = torch.randn(6, generator=g).requires_grad_()
+    res = torch.randn(3, 6, 5, 4, generator=g)
+    rm, rv = torch.zeros(6), torch.ones(6)
+    z = F.batch_norm(x, rm, rv, gamma, beta, True, 0.1, 1e-3)
+    y = {TO.ACT_NONE: lambda t: t, TO.ACT_SILU: F.silu, TO.ACT_GELU: F.gelu}[act](z) + res
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    xs = nhwc(x.detach())
+    mean, var = TO.bn_stats(xs)
+    n = xs.numel() // 6
+    assert rel_l2(mean * 0.1, rm) < 1e-5 and rel_l2(0.9 + 0.1 * var * n / (n - 1), rv) < 1e-5
+    assert rel_l2(TO.bn_act(xs, mean, var, gamma, beta, 1e-3, act, nhwc(res)), nhwc(y.detach())) < 1e-6
+    dx, dgamma, dbeta = TO.bn_act_bwd(xs, nhwc(dy), mean, var, gamma, beta, 1e-3, act)
+    assert rel_l2(dx, nhwc(x.grad)) < 1e-5
+    assert rel_l2(dgamma, gamma.grad) < 1e-5 and rel_l2(dbeta, beta.grad) < 1e-5
+
+
+@pytest.mark.parametrize("stride,h,w", [(1, 6, 5), (2, 8, 6), (2, 7, 5)])
+def test_depthwise_matches_autograd(stride, h, w):
+    g = torch.Generator().manual_seed(stride)
+    c = 7
+    x = torch.randn(2, c, h, w, generator=g, requires_grad=True)
+    wt = torch.randn(c, 1, 3, 3, generator=g, requires_grad=True)
+    y = F.conv2d(x, wt, None, stride, 1, 1, c)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    w9c = wt.detach().reshape(c, 9).t().contiguous()
+    assert rel_l2(TO.dwconv3x3_raw(nhwc(x.detach()), w9c, stride), nhwc(y.detach())) < 1e-6
+    assert rel_l2(TO.dwconv3x3_dgrad(nhwc(dy), w9c, h, w, stride), nhwc(x.grad)) < 1e-6
+    assert rel_l2(TO.dwconv3x3_wgrad(nhwc(x.detach()), nhwc(dy), stride).t().reshape(c, 1, 3, 3), wt.grad) < 1e-6
+
+
+def test_squeeze_excite_matches_torchvision_autograd():
+    from torchvision.ops.misc import SqueezeExcitation
+    from functools import partial
+    torch.manual_seed(0)
+    c, s = 12, 3
+    se = SqueezeExcitation(c, s, activation=partial(torch.nn.SiLU, inplace=True))   # efficientnet.py:149
+    x = torch.randn(2, c, 5, 4, requires_grad=True)
+    y = se(x)
+    dy = torch.randn(y.shape)
+    y.backward(dy)
+    xs, dys = nhwc(x.detach()), nhwc(dy)
+    w1, w2 = se.fc1.weight.detach().reshape(s, c), se.fc2.weight.detach().reshape(c, s)
+    mean = TO.spatial_sum(xs, None, 1.0 / 20)
+    hid_pre, gate = TO.se_fc_train(mean, w1, se.fc1.bias.detach(), w2, se.fc2.bias.detach())
+    assert rel_l2(TO.scale_bc(xs, gate), nhwc(y.detach())) < 1e-6
+    dgate = TO.spatial_sum(dys, xs, 1.0)
+    dmean, dw1, db1, dw2, db2 = TO.se_fc_train_bwd(dgate, gate, hid_pre, mean, w1, w2)
+    assert rel_l2(TO.scale_bc(dys, gate, dmean, 1.0 / 20), nhwc(x.grad)) < 1e-5
+    assert rel_l2(dw1, se.fc1.weight.grad.reshape(s, c)) < 1e-5 and rel_l2(db1, se.fc1.bias.grad) < 1e-5
+    assert rel_l2(dw2, se.fc2.weight.grad.reshape(c, s)) < 1e-5 and rel_l2(db2, se.fc2.bias.grad) < 1e-5
+
+
+@pytest.mark.parametrize("h,w", [(1, 1), (2, 3), (6, 6), (24, 5)])
+def test_upsample_adjoint_matches_autograd(h, w):
+    g = torch.Generator().manual_seed(h)
+    x = torch.randn(2, 3, h, w, generator=g, requires_grad=True)
+    y = torch.nn.UpsamplingBilinear2d(scale_factor=2)(x)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    assert rel_l2(TO.upsample2x(nhwc(x.detach())), nhwc(y.detach())) < 1e-6
+    assert rel_l2(TO.upsample2x_bwd(nhwc(dy)), nhwc(x.grad)) < 1e-6
+
+
+def test_upsample_adjoint_candidate_window():
+    """csrc/train_ops.cu::upsample2x_bwd_kernel only visits outputs 2j-2 .. 2j+3 for input index j: every output whose
+    footprint touches j must lie inside that window."""
+    for n in (1, 2, 3, 6, 12, 24, 48, 96, 192):
+        m = TO._interp_matrix(n)
+        for j in range(n):
+            touched = torch.nonzero(m[:, j]).flatten().tolist()
+            assert touched and min(touched) >= 2 * j - 2 and max(touched) <= 2 * j + 3, (n, j, touched)
+
+
+@pytest.fixture()
+def oracle_kernels(monkeypatch):
+    """Route the autograd nodes of train_ops.py through the CPU oracle (checks the graph logic, not the kernels)."""
+    from findtextcenternet_b200 import train_ops
+
+    class Ns:
+        pass
+
+    ns = Ns()
+    for name in ("conv2d", "conv2d_wgrad", "conv2d_dgrad", "bn_stats", "bn_act", "bn_act_bwd", "dwconv3x3_raw", "dwconv3x3_dgrad",
+                 "dwconv3x3_wgrad", "spatial_sum", "scale_bc", "se_fc_train", "se_fc_train_bwd", "upsample2x", "upsample2x_bwd"):
+        setattr(ns, name, getattr(TO, name))
+    monkeypatch.setattr(train_ops, "K", ns)
+    # the product wrappers refuse CPU tensors; the graph test runs them on CPU on purpose
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    return train_ops
+
+
+def test_row_scale_node(oracle_kernels):
+    x = torch.randn(3, 4, 5, 6, requires_grad=True)
+    noise = torch.tensor([0.0, 1.25, 1.25])
+    y = oracle_kernels._RowScale.apply(x, noise)
+    y.backward(torch.ones_like(y))
+    assert torch.allclose(y, x.detach() * noise[:, None, None, None])
+    assert torch.allclose(x.grad, noise[:, None, None, None].expand_as(x))
+
+
+def _golden_train():
+    p = os.path.join(GOLDEN, "train_xl64_seed0.npz")
+    if not os.path.exists(p):
+        pytest.skip("tests/golden/train_xl64_seed0.npz missing (oracle/make_golden_train.py)")
+    return np.load(p)
+
+
+@pytest.mark.slow
+def test_train_graph_matches_reference_golden(oracle_kernels):
+    """Full TextDetectorModel train-mode forward + backward (StochasticDepth off, as in the golden) through train_ops.py with
+    oracle kernels == the unmodified reference under torch autograd: outputs, updated BatchNorm buffers, every gradient."""
+    from findtextcenternet_b200 import synthetic
+    from findtextcenternet_b200.models.detector import TextDetectorModel
+    gold = _golden_train()
+    model = TextDetectorModel(pre_weights=False)
+    model.load_state_dict(synthetic.detector_state_dict(0))
+    model.detector.set_precision("fp32")
+    model.decoder.precision = "fp32"
+    model.train()
+    x = torch.from_numpy(gold["x"])
+    fmask = torch.from_numpy(gold["fmask"])
+    heat, feat = oracle_kernels.detection_train_forward(model.detector, x, sd_prob=0.0)
+    f = feat.permute(0, 2, 3, 1).flatten(0, -2)
+    dec = model.decoder(f[fmask])
+    assert rel_l2(heat.detach(), gold["heatmap"]) < 1e-3     # fp32 reference through ~110 batch-statistics layers
+    for i in range(3):
+        assert rel_l2(dec[i].detach(), gold[f"dec{i}"]) < 1e-3
+    loss = (heat * torch.from_numpy(gold["w_heat"])).sum() + sum((dec[i] * torch.from_numpy(gold[f"w_dec{i}"])).sum() for i in range(3))
+    loss.backward()
+    names = [str(n) for n in gold["grad_names"]]
+    params = dict(model.named_parameters())
+    assert set(names) == set(params)
+    # truth = the reference in float64; grad_fp32_err[i] = || reference fp32 gradient - truth ||: the noise any fp32-storage
+    # implementation carries (BatchNorm betas feeding another batch-statistics layer have ~zero true gradients)
+    bad = []
+    for i, n in enumerate(names):
+        g = params[n].grad
+        assert g is not None, n
+        ref_norm, ref_dot, noise = float(gold["grad_norm"][i]), float(gold["grad_dot"][i]), float(gold["grad_fp32_err"][i])
+        tol = 2e-3 * ref_norm + 4.0 * noise + 1e-9
+        probe = torch.from_numpy(synthetic_probe(g.shape, i))
+        e_norm = abs(float(g.double().norm()) - ref_norm)
+        e_dot = abs(float((g.double() * probe).sum()) - ref_dot)
+        if e_norm > tol or e_dot > 8.0 * tol:
+            bad.append((n, e_norm, e_dot, tol))
+    assert not bad, bad[:10]
+    for k in [k for k in gold.files if k.startswith("full/")]:
+        i = names.index(k[5:])
+        tol = 2e-3 + 4.0 * float(gold["grad_fp32_err"][i]) / float(gold["grad_norm"][i])
+        assert rel_l2(params[k[5:]].grad, gold[k]) < tol, (k, tol)
+    bufs = dict(model.named_buffers())
+    for k in [k for k in gold.files if k.startswith("buf/")]:
+        assert rel_l2(bufs[k[4:]].double(), gold[k]) < 1e-5, k
+
+
+def synthetic_probe(shape, i):
+    """Deterministic +-1 probe tensor used to fingerprint a gradient with one dot product (same in make_golden_train.py)."""
+    n = int(np.prod(shape)) if len(shape) else 1
+    idx = np.arange(n, dtype=np.int64)
+    v = (((idx * 2654435761 + i * 40503) >> 7) & 1).astype(np.float64) * 2 - 1
+    return v.reshape(shape)
