@@ -82,6 +82,7 @@ SYMBOLS = {
     "ftc_heatmap_loss": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "ftc_heatmap_loss_grad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ftc_ce_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "ftc_ce_rows_grad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "ftc_peak_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "ftc_peak_pick": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ftc_op_conv2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),

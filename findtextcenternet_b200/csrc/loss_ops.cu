@@ -217,6 +217,45 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
   }
 }
 
+
+// backward of ce_rows' out[0] / max(out[1], 1) (the id_loss of loss_function :128-161, the loss of loss_function3): one warp per
+// row, d logits_g[row, j] = coef * w_row * (softmax_g(row)[j] - [j == target % m_g]) on the selected rows, 0 elsewhere;
+// coef (device scalar) = upstream gradient / max(sum of weights, 1)
+__global__ void __launch_bounds__(256) ce_rows_grad_kernel(const float* __restrict__ l0, const float* __restrict__ l1,
+                                                           const float* __restrict__ l2, int ld0, int ld1, int ld2, int m0, int m1,
+                                                           int m2, const int64_t* __restrict__ target,
+                                                           const float* __restrict__ weight, const unsigned char* __restrict__ select,
+                                                           int rows, const float* __restrict__ coef, float* __restrict__ g0,
+                                                           float* __restrict__ g1, float* __restrict__ g2) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bool sel = select == nullptr || select[row] != 0;
+  const float cw = sel ? coef[0] * (weight ? weight[row] : 1.f) : 0.f;
+  const int64_t tgt = target[row];
+  const float* lp[3] = {l0 + (int64_t)row * ld0, l1 + (int64_t)row * ld1, l2 + (int64_t)row * ld2};
+  float* gp[3] = {g0 + (int64_t)row * m0, g1 + (int64_t)row * m1, g2 + (int64_t)row * m2};
+  const int mm[3] = {m0, m1, m2};
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    const int m = mm[g];
+    if (cw == 0.f) {
+      for (int j = lane; j < m; j += 32) gp[g][j] = 0.f;
+      continue;
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < m; j += 32) mx = fmaxf(mx, lp[g][j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float s = 0.f;
+    for (int j = lane; j < m; j += 32) s += expf(lp[g][j] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.f / s;
+    const int t = (int)(((tgt % m) + m) % m);
+    for (int j = lane; j < m; j += 32) gp[g][j] = cw * (expf(lp[g][j] - mx) * inv - (j == t ? 1.f : 0.f));
+  }
+}
+
 }  // namespace
 }  // namespace ftc
 
@@ -259,6 +298,17 @@ int ftc_ce_rows(const float* logits0, const float* logits1, const float* logits2
   if (rows == 0) return 0;
   ce_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(logits0, logits1, logits2, ld0, ld1, ld2, m0, m1, m2, target, weight, select, count_select,
                                                 rows, out4);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_ce_rows_grad(const float* logits0, const float* logits1, const float* logits2, int ld0, int ld1, int ld2, int m0, int m1,
+                     int m2, const int64_t* target, const float* weight, const unsigned char* select, int rows, const float* coef,
+                     float* grad0, float* grad1, float* grad2, void* stream) {
+  FTC_REQUIRE(logits0 && logits1 && logits2 && target && coef && grad0 && grad1 && grad2 && rows >= 0, "bad argument");
+  if (rows == 0) return 0;
+  ce_rows_grad_kernel<<<(int)(((int64_t)rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      logits0, logits1, logits2, ld0, ld1, ld2, m0, m1, m2, target, weight, select, rows, coef, grad0, grad1, grad2);
   FTC_POST_LAUNCH();
   return 0;
 }

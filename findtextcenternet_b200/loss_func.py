@@ -54,6 +54,54 @@ def heatmap_loss_grad(labelmap, idmap, heatmap, alphas: torch.Tensor, losses9: t
     return grad
 
 
+class _HeatmapLosses(torch.autograd.Function):
+    """fp32[9] map losses with the analytic backward of csrc/loss_ops.cu (ftc_heatmap_loss_grad): the upstream gradient of the
+    eight losses is exactly the kernel's alpha vector."""
+
+    @staticmethod
+    def forward(ctx, heatmap, labelmap, idmap):
+        out = heatmap_losses(labelmap, idmap, heatmap)
+        ctx.save_for_backward(heatmap, labelmap, idmap, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        heatmap, labelmap, idmap, out = ctx.saved_tensors
+        grad = heatmap_loss_grad(labelmap, idmap, heatmap, g[:8].float().contiguous(), out)
+        return grad.to(heatmap.dtype), None, None
+
+
+class _CEMean(torch.autograd.Function):
+    """out4[0] / max(out4[1], 1) of ftc_ce_rows with ftc_ce_rows_grad as its backward; also returns the detached out4."""
+
+    @staticmethod
+    def forward(ctx, l0, l1, l2, target, weight, select, count_select, clamp_den):
+        o = _ce_rows((l0, l1, l2), target, weight, select, count_select)
+        den = torch.clamp_min(o[1], 1.0) if clamp_den else o[1]
+        ctx.save_for_backward(l0, l1, l2, target, weight, select, den)
+        ctx.mark_non_differentiable(o)
+        return (o[0] / den).float(), o
+
+    @staticmethod
+    def backward(ctx, g, _):
+        lib = _lib.load()
+        l0, l1, l2, target, weight, select, den = ctx.saved_tensors
+        ls = [l.detach().float().contiguous() for l in (l0, l1, l2)]
+        rows = ls[0].shape[0]
+        grads = [torch.empty_like(l) for l in ls]
+        coef = (g.double() / den).float().reshape(1).contiguous()
+        tg = target.to(torch.int64).contiguous()
+        wt = None if weight is None else weight.float().contiguous()
+        se = None if select is None else select.to(torch.uint8).contiguous()
+        p = lambda t: None if t is None else t.data_ptr()
+        with torch.cuda.device(coef.device):
+            _lib.check(lib.ftc_ce_rows_grad(ls[0].data_ptr(), ls[1].data_ptr(), ls[2].data_ptr(), ls[0].stride(0), ls[1].stride(0),
+                                            ls[2].stride(0), modulo_list[0], modulo_list[1], modulo_list[2], tg.data_ptr(), p(wt),
+                                            p(se), rows, coef.data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(),
+                                            grads[2].data_ptr(), _s(coef)), "ftc_ce_rows_grad")
+        return grads[0].to(l0.dtype), grads[1].to(l1.dtype), grads[2].to(l2.dtype), None, None, None, None, None
+
+
 def _ce_rows(logits, target, weight, select, count_select) -> torch.Tensor:
     lib = _lib.load()
     ls = [l.detach().float() for l in logits]
@@ -76,13 +124,13 @@ def loss_function(fmask, labelmap, idmap, heatmap, decoder_outputs):
     """loss_func.py:94-177.  Returns the reference's dict (0-d CUDA tensors)."""
     _need_cuda(fmask, labelmap, idmap, heatmap, *decoder_outputs)
     key_th3 = 0.99
-    m9 = heatmap_losses(labelmap, idmap, heatmap)
+    m9 = _HeatmapLosses.apply(heatmap, labelmap, idmap)      # differentiable w.r.t. heatmap (train1.py:151 loss.backward())
     keyvals = labelmap[:, 0].flatten()[fmask].float()
     target_id = idmap[:, 0].flatten()[fmask]
     pos = target_id > 0
     weight3 = torch.clamp_min(keyvals - key_th3, 0.) / (1 - key_th3)
-    o = _ce_rows(decoder_outputs, target_id, weight3, (keyvals > key_th3) & pos, (keyvals == 1) & pos)
-    id_loss = (o[0] / torch.clamp_min(o[1], 1.0)).float()
+    id_loss, o = _CEMean.apply(decoder_outputs[0], decoder_outputs[1], decoder_outputs[2], target_id, weight3,
+                               (keyvals > key_th3) & pos, (keyvals == 1) & pos, True)
     res = {k: m9[i] for i, k in enumerate(MAP_LOSSES)}
     res["id_loss"] = id_loss
     res["loss"] = m9[:8].sum() + id_loss
@@ -96,8 +144,8 @@ def loss_function3(outputs, labelcode, mask):
     _need_cuda(labelcode, mask, *outputs)
     flat = [o.reshape(-1, o.shape[-1]) for o in outputs]
     m = mask.reshape(-1)
-    o = _ce_rows(flat, labelcode.reshape(-1), None, m, m)
-    return {"loss": (o[0] / o[1]).float(), "correct": o[2].to(torch.int64), "total": o[3].to(torch.int64)}
+    loss, o = _CEMean.apply(flat[0], flat[1], flat[2], labelcode.reshape(-1), None, m, m, False)
+    return {"loss": loss, "correct": o[2].to(torch.int64), "total": o[3].to(torch.int64)}
 
 
 class CoVWeightingLoss(torch.nn.Module):

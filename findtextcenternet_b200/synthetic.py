@@ -186,3 +186,33 @@ def loss_inputs(seed=0, B=2, H=48, W=48, n_sel=96):
     mask3 = torch.rand(3, 20, generator=g) < 0.8
     return dict(labelmap=labelmap, idmap=idmap, heatmap=heatmap, fmask=fmask, dec0=dec[0], dec1=dec[1], dec2=dec[2],
                 out3_0=out3[0], out3_1=out3[1], out3_2=out3[2], labelcode=labelcode, mask3=mask3)
+
+
+def train1_batch(batch: int, seed: int = 0, size: int = 768, device="cpu", peaks_per_image: int = 40):
+    """Synthetic train1 batch of SURVEY.md 8d config 3: image [B,3,size,size] uniform [0,1); labelmap [B,5,size/4,size/4] with
+    ch0 = max of Gaussians (sigma 1.5 px, exactly 1.0 at integer centres, dataset/processer.pyx:133-159), ch1/ch2 = log-size
+    values on small blobs (:161-182), ch3/ch4 in [0,1]; idmap [B,2,...] int64: code point on the blobs, 4-bit flags (:184-202)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    hs = size // arch.SCALE
+    image = torch.rand(batch, 3, size, size, generator=g)
+    yy, xx = torch.meshgrid(torch.arange(hs).float(), torch.arange(hs).float(), indexing="ij")
+    labelmap = torch.zeros(batch, 5, hs, hs)
+    idmap = torch.zeros(batch, 2, hs, hs, dtype=torch.int64)
+    n_peaks = max(2, min(peaks_per_image, hs * hs // 40))
+    for b in range(batch):
+        cys = torch.randint(2, hs - 2, (n_peaks,), generator=g)
+        cxs = torch.randint(2, hs - 2, (n_peaks,), generator=g)
+        for k in range(n_peaks):
+            cy, cx = int(cys[k]), int(cxs[k])
+            y0, y1, x0, x1 = max(cy - 6, 0), min(cy + 7, hs), max(cx - 6, 0), min(cx + 7, hs)
+            gauss = torch.exp(-((yy[y0:y1, x0:x1] - cy) ** 2 + (xx[y0:y1, x0:x1] - cx) ** 2) / (2 * 1.5 ** 2))
+            labelmap[b, 0, y0:y1, x0:x1] = torch.maximum(labelmap[b, 0, y0:y1, x0:x1], gauss)
+            blob = gauss > 0.5
+            labelmap[b, 1, y0:y1, x0:x1][blob] = float(torch.rand(1, generator=g)) + 1.5
+            labelmap[b, 2, y0:y1, x0:x1][blob] = float(torch.rand(1, generator=g)) + 1.5
+            idmap[b, 0, y0:y1, x0:x1][blob] = 0x3042 + k
+            idmap[b, 1, y0:y1, x0:x1][blob] = int(torch.randint(0, 16, (1,), generator=g))
+        labelmap[b, 3] = (torch.rand(hs, hs, generator=g) > 0.8).float() * torch.rand(hs, hs, generator=g)
+        labelmap[b, 4] = (torch.rand(hs, hs, generator=g) > 0.9).float()
+    out = dict(image=image, labelmap=labelmap, idmap=idmap)
+    return {k: v.to(device) for k, v in out.items()}

@@ -1,0 +1,54 @@
+"""The train1 step (train1.py:128-191) on the B200 kernels: train-mode forward, losses, CoV weighting, backward, gradient
+all-reduce across one-process-per-GPU replicas (the reference is single-device), schedule-free AdamW.
+
+    fmask = model.get_fmask(labelmap, fmask)                                    # train1.py:183
+    loss, rawloss = train1_step(model, optimizer, cov, image, labelmap, idmap, fmask)
+
+Every arithmetic piece is a C-ABI kernel call (train_ops.py, loss_func.py, models/adamw_schedulefree.py); torch supplies the
+autograd tape, memory and torch.distributed.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import shard
+from .loss_func import loss_function
+
+# train1.py:104-111 -- the order fixes the CoV statistics vectors
+TRAIN1_LOSSES = ["keymap_loss", "size_loss", "textline_loss", "separator_loss", "id_loss",
+                 "code1_loss", "code2_loss", "code4_loss", "code8_loss"]
+
+
+def train1_step(model, optimizer, cov, image, labelmap, idmap, fmask, iters_to_accumulate: int = 1, step_now: bool = True,
+                group=None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """One iteration of the train1.py loop body (:183-191).  With torch.distributed initialised (world size > 1) the gradients
+    are averaged over ranks in reverse-order flat buckets before the optimizer step, and the nine raw losses that drive the
+    CoV weights are averaged too, so every replica keeps bit-identical loss weights and parameters."""
+    heatmap, decoder_outputs = model(image, fmask)
+    rawloss = loss_function(fmask, labelmap, idmap, heatmap, decoder_outputs)
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if distributed:
+        rawloss = _sync_loss_values(rawloss, group)
+    loss = cov(rawloss)
+    (loss / iters_to_accumulate).backward()
+    if step_now:
+        if distributed:
+            shard.allreduce_gradients([p for p in model.parameters() if p.requires_grad], group=group)
+        optimizer.step()
+        optimizer.zero_grad()
+    return loss.detach(), {k: v.detach() for k, v in rawloss.items()}
+
+
+def _sync_loss_values(rawloss: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
+    """Replace each loss VALUE by its mean over ranks while keeping the local gradient path: v + (mean - v).detach()."""
+    keys = [k for k in TRAIN1_LOSSES if k in rawloss]
+    vals = torch.stack([rawloss[k].detach().float() for k in keys])
+    dist.all_reduce(vals, op=dist.ReduceOp.SUM, group=group)
+    vals /= dist.get_world_size(group)
+    out = dict(rawloss)
+    for i, k in enumerate(keys):
+        out[k] = rawloss[k] + (vals[i] - rawloss[k].detach())
+    return out

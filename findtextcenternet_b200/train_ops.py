@@ -27,8 +27,12 @@ BN_MOMENTUM = 0.1              # nn.BatchNorm2d / BatchNorm1d default; torchvisi
 STOCHASTIC_DEPTH_PROB = 0.2    # torchvision EfficientNet.__init__ default (the reference does not override it)
 
 
-def _backend(x: Tensor) -> int:
-    return _lib.GEMM_TCGEN05 if x.dtype == torch.bfloat16 else _lib.GEMM_SIMT
+def _backend(x: Tensor, cin: int = 64, cout: int = 64) -> int:
+    """tcgen05 for bf16 convolutions with GEMM-sized channel counts; the stem (3 -> 32) and the 1-/2-channel top convs are
+    bandwidth-bound slivers and stay on the CUDA-core kernel (as in the inference plan)."""
+    if x.dtype != torch.bfloat16 or cin < 32 or cout < 16:
+        return _lib.GEMM_SIMT
+    return _lib.GEMM_TCGEN05
 
 
 class _Conv2d(Function):
@@ -38,7 +42,7 @@ class _Conv2d(Function):
     def forward(ctx, x, w, bias, stride):
         ctx.save_for_backward(x, w)
         ctx.stride, ctx.has_bias = stride, bias is not None
-        return K.conv2d(x, w, stride, None, bias, _lib.ACT_NONE, None, None, _backend(x))
+        return K.conv2d(x, w, stride, None, bias, _lib.ACT_NONE, None, None, _backend(x, w.shape[1], w.shape[0]))
 
     @staticmethod
     def backward(ctx, dy):
@@ -47,7 +51,7 @@ class _Conv2d(Function):
         cout, cin, k, _ = w.shape
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            if ctx.stride == 1 and x.dtype == torch.bfloat16 and cout % 8 == 0:
+            if ctx.stride == 1 and cout % 8 == 0 and _backend(x, cout, cin) == _lib.GEMM_TCGEN05:
                 # stride-1 data gradient = the same convolution with the taps rotated 180 degrees and the channel roles
                 # swapped: runs on the tcgen05 forward kernel
                 wt = w.detach().float().flip(2, 3).transpose(0, 1).contiguous()

@@ -155,6 +155,12 @@ int ftc_heatmap_loss_grad(const float* heatmap, const float* labelmap, const int
 int ftc_ce_rows(const float* logits0, const float* logits1, const float* logits2, int ld0, int ld1, int ld2, int m0, int m1, int m2,
                 const int64_t* target, const float* weight, const unsigned char* select, const unsigned char* count_select, int rows,
                 double* out4, void* stream);
+/* backward of ftc_ce_rows' weighted mean  out4[0] / max(out4[1], 1)  w.r.t. the three logit matrices (dense fp32 [rows, m_i]):
+ * grad_i[row, j] = coef * w_row * (softmax_i(row)[j] - [j == target % m_i]) on the selected rows, 0 elsewhere; coef: device fp32
+ * scalar = upstream gradient / max(out4[1], 1)  (autograd of F.cross_entropy in loss_func.py:139-147, 191-197) */
+int ftc_ce_rows_grad(const float* logits0, const float* logits1, const float* logits2, int ld0, int ld1, int ld2, int m0, int m1,
+                     int m2, const int64_t* target, const float* weight, const unsigned char* select, int rows, const float* coef,
+                     float* grad0, float* grad1, float* grad2, void* stream);
 
 /* ---- single ops (unit-test / building-block entry points) ---- */
 /* dense conv (k in {1,3}) or linear as implicit GEMM on NHWC activations.

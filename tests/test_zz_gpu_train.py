@@ -1,0 +1,265 @@
+"""GPU: the train-step kernels (csrc/train_ops.cu through the C-ABI) against the CPU oracle (oracle/train_oracle.py, pinned to
+torch autograd and to the reference golden by tests/test_train_oracle.py) on the same seeded inputs, then the whole
+train-mode forward + backward of TextDetectorModel against the reference golden (tests/golden/train_xl64_seed0.npz).
+
+Sorted last on purpose (zz): written in a session without GPU time left; a surprise here must not mask the older suites.
+Tolerances: fp32 tensors 2e-5 relative (fp32 accumulation order), bf16 storage 2e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_l2
+from oracle import train_oracle as TO
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)]
+
+
+def dev(t, dt=None):
+    t = t.cuda()
+    return t.to(dt) if dt is not None else t
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+@pytest.mark.parametrize("dt,tol", DTYPES)
+@pytest.mark.parametrize("rows,c", [(37, 5), (4096, 64), (70000, 200)])
+def test_bn_stats_and_bn_act(dt, tol, rows, c):
+    from findtextcenternet_b200 import _ops
+    x = (rnd(rows, c, seed=1) * 1.7 + 0.3).to(dt)
+    gamma, beta = rnd(c, seed=2), rnd(c, seed=3)
+    res = rnd(rows, c, seed=4).to(dt)
+    mean, var = _ops.bn_stats(dev(x))
+    m0, v0 = TO.bn_stats(x.float())
+    assert rel_l2(mean.cpu(), m0) < 1e-5 and rel_l2(var.cpu(), v0) < 1e-4
+    for act in (TO.ACT_NONE, TO.ACT_SILU, TO.ACT_GELU):
+        y = _ops.bn_act(dev(x), dev(m0), dev(v0), dev(gamma), dev(beta), 1e-3, act, dev(res))
+        y0 = TO.bn_act(x.float(), m0, v0, gamma, beta, 1e-3, act, res.float())
+        assert rel_l2(y.float().cpu(), y0) < tol, act
+        dy = rnd(rows, c, seed=5 + act).to(dt)
+        dx, dg, db = _ops.bn_act_bwd(dev(x), dev(dy), dev(m0), dev(v0), dev(gamma), dev(beta), 1e-3, act)
+        dx0, dg0, db0 = TO.bn_act_bwd(x.float(), dy.float(), m0, v0, gamma, beta, 1e-3, act)
+        assert rel_l2(dg.cpu(), dg0) < 1e-4 and rel_l2(db.cpu(), db0) < 1e-4, act
+        assert rel_l2(dx.float().cpu(), dx0) < max(tol, 1e-4), act
+
+
+@pytest.mark.parametrize("dt,tol", DTYPES)
+@pytest.mark.parametrize("b,h,w,cin,cout,k,stride", [
+    (2, 6, 5, 8, 16, 3, 1), (2, 9, 7, 24, 40, 3, 2), (3, 8, 8, 16, 8, 1, 1), (2, 12, 10, 3, 32, 3, 2),
+    (1, 16, 16, 192, 1, 3, 1), (2, 7, 6, 100, 72, 1, 1), (500, 1, 1, 104, 80, 1, 1), (2, 24, 24, 64, 130, 3, 1)])
+def test_conv_wgrad_dgrad(dt, tol, b, h, w, cin, cout, k, stride):
+    from findtextcenternet_b200 import _ops
+    x = rnd(b, h, w, cin, seed=1).to(dt)
+    wt = rnd(cout, cin, k, k, seed=2, scale=0.2)
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    dy = rnd(b, ho, wo, cout, seed=3).to(dt)
+    dw = _ops.conv2d_wgrad(dev(x), dev(dy), k, stride)
+    assert rel_l2(dw.cpu(), TO.conv2d_wgrad(x.float(), dy.float(), k, stride)) < 2e-5
+    add = rnd(b, h, w, cin, seed=4).to(dt)
+    for a in (None, add):
+        dx = _ops.conv2d_dgrad(dev(dy), dev(wt), h, w, stride, None if a is None else dev(a))
+        dx0 = TO.conv2d_dgrad(dy.float(), wt, h, w, stride, None if a is None else a.float())
+        assert rel_l2(dx.float().cpu(), dx0) < tol
+
+
+@pytest.mark.parametrize("cin,cout,k", [(64, 32, 3), (32, 64, 1), (192, 192, 3)])
+def test_stride1_dgrad_through_the_tcgen05_forward_kernel(cin, cout, k):
+    """bf16 stride-1 data gradient = forward conv with rotated taps and swapped channel roles (train_ops._Conv2d.backward)."""
+    from findtextcenternet_b200 import _lib, _ops
+    b, h, w = 2, 16, 32
+    wt = rnd(cout, cin, k, k, seed=2, scale=0.1)
+    dy = rnd(b, h, w, cout, seed=3).to(torch.bfloat16)
+    wflip = wt.flip(2, 3).transpose(0, 1).contiguous()
+    dx = _ops.conv2d(dev(dy), wflip, 1, None, None, _lib.ACT_NONE, None, None, _lib.GEMM_TCGEN05)
+    assert rel_l2(dx.float().cpu(), TO.conv2d_dgrad(dy.float(), wt.to(torch.bfloat16).float(), h, w, 1)) < 1e-2
+
+
+@pytest.mark.parametrize("dt,tol", DTYPES)
+@pytest.mark.parametrize("b,h,w,c,stride", [(2, 6, 5, 8, 1), (2, 9, 8, 40, 2), (3, 12, 12, 96, 1), (2, 7, 7, 33, 2)])
+def test_depthwise_fwd_dgrad_wgrad(dt, tol, b, h, w, c, stride):
+    from findtextcenternet_b200 import _ops
+    x = rnd(b, h, w, c, seed=1).to(dt)
+    w9c = rnd(9, c, seed=2, scale=0.3)
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    dy = rnd(b, ho, wo, c, seed=3).to(dt)
+    assert rel_l2(_ops.dwconv3x3_raw(dev(x), dev(w9c), stride).float().cpu(), TO.dwconv3x3_raw(x.float(), w9c, stride)) < tol
+    assert rel_l2(_ops.dwconv3x3_dgrad(dev(dy), dev(w9c), h, w, stride).float().cpu(),
+                  TO.dwconv3x3_dgrad(dy.float(), w9c, h, w, stride)) < tol
+    assert rel_l2(_ops.dwconv3x3_wgrad(dev(x), dev(dy), stride).cpu(), TO.dwconv3x3_wgrad(x.float(), dy.float(), stride)) < 2e-5
+
+
+@pytest.mark.parametrize("dt,tol", DTYPES)
+@pytest.mark.parametrize("b,hw,c,s", [(2, 20, 12, 3), (3, 576, 768, 48), (2, 2304, 3072, 128)])
+def test_squeeze_excite_pieces(dt, tol, b, hw, c, s):
+    from findtextcenternet_b200 import _ops
+    x = rnd(b, hw, 1, c, seed=1).to(dt)
+    dy = rnd(b, hw, 1, c, seed=2).to(dt)
+    w1, b1 = rnd(s, c, seed=3, scale=c ** -0.5), rnd(s, seed=4)
+    w2, b2 = rnd(c, s, seed=5, scale=s ** -0.5), rnd(c, seed=6)
+    mean = _ops.spatial_sum(dev(x), None, 1.0 / hw)
+    mean0 = TO.spatial_sum(x.float(), None, 1.0 / hw)
+    assert rel_l2(mean.cpu(), mean0) < 1e-5
+    hid, gate = _ops.se_fc_train(dev(mean0), dev(w1), dev(b1), dev(w2), dev(b2))
+    hid0, gate0 = TO.se_fc_train(mean0, w1, b1, w2, b2)
+    assert rel_l2(hid.cpu(), hid0) < 1e-4 and rel_l2(gate.cpu(), gate0) < 1e-4
+    assert rel_l2(_ops.scale_bc(dev(x), dev(gate0)).float().cpu(), TO.scale_bc(x.float(), gate0)) < tol
+    dgate = _ops.spatial_sum(dev(dy), dev(x), 1.0)
+    dgate0 = TO.spatial_sum(dy.float(), x.float(), 1.0)
+    assert rel_l2(dgate.cpu(), dgate0) < 1e-5
+    outs = _ops.se_fc_train_bwd(dev(dgate0), dev(gate0), dev(hid0), dev(mean0), dev(w1), dev(w2))
+    for a, r in zip(outs, TO.se_fc_train_bwd(dgate0, gate0, hid0, mean0, w1, w2)):
+        assert rel_l2(a.cpu(), r) < 1e-4
+    dmean0 = outs[0].cpu()
+    assert rel_l2(_ops.scale_bc(dev(dy), dev(gate0), dev(dmean0), 1.0 / hw).float().cpu(),
+                  TO.scale_bc(dy.float(), gate0, dmean0, 1.0 / hw)) < tol
+
+
+@pytest.mark.parametrize("dt,tol", DTYPES)
+@pytest.mark.parametrize("b,h,w,c", [(2, 1, 1, 8), (2, 3, 5, 8), (2, 24, 24, 192), (1, 96, 96, 16)])
+def test_upsample_adjoint(dt, tol, b, h, w, c):
+    from findtextcenternet_b200 import _ops
+    dy = rnd(b, 2 * h, 2 * w, c, seed=1).to(dt)
+    assert rel_l2(_ops.upsample2x_bwd(dev(dy)).float().cpu(), TO.upsample2x_bwd(dy.float())) < tol
+    # adjoint identity against the forward kernel itself: <U x, dy> == <x, U^T dy>
+    x = rnd(b, h, w, c, seed=2)
+    lhs = float((_ops.upsample2x(dev(x)).double() * dev(dy).double()).sum())
+    rhs = float((dev(x).double() * _ops.upsample2x_bwd(dev(dy.float())).double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0) + (2e-2 * abs(lhs) if dt == torch.bfloat16 else 0)
+
+
+def _model(prec):
+    from findtextcenternet_b200 import synthetic
+    from findtextcenternet_b200.models.detector import TextDetectorModel
+    model = TextDetectorModel(pre_weights=False)
+    model.load_state_dict(synthetic.detector_state_dict(0))
+    model.detector.set_precision(prec)
+    model.decoder.precision = prec
+    return model.cuda().train()
+
+
+def _probe(shape, i):
+    n = int(np.prod(shape)) if len(shape) else 1
+    idx = np.arange(n, dtype=np.int64)
+    return ((((idx * 2654435761 + i * 40503) >> 7) & 1).astype(np.float64) * 2 - 1).reshape(shape)
+
+
+def test_train_step_fp32_matches_reference_golden():
+    """train1.py:128-170 shape of work: model(image, fmask) in train mode, scalar loss, backward -- every one of the 2 444
+    parameter gradients against the float64 run of the unmodified reference (tolerance = 2e-3 + 4x the reference's own fp32
+    rounding noise per tensor), outputs to 1e-3, BatchNorm buffers updated like torch."""
+    from findtextcenternet_b200 import _lib, train_ops
+    gold = np.load(os.path.join(GOLDEN, "train_xl64_seed0.npz"))
+    model = _model("fp32")
+    l0 = _lib.launch_count()
+    x = torch.from_numpy(gold["x"]).cuda()
+    fmask = torch.from_numpy(gold["fmask"]).cuda()
+    heat, feat = train_ops.detection_train_forward(model.detector, x, sd_prob=0.0)
+    dec = model.decoder(feat.permute(0, 2, 3, 1).flatten(0, -2)[fmask])
+    assert rel_l2(heat.detach().cpu(), gold["heatmap"]) < 1e-3
+    for i in range(3):
+        assert rel_l2(dec[i].detach().cpu(), gold[f"dec{i}"]) < 1e-3
+    loss = (heat * torch.from_numpy(gold["w_heat"]).cuda()).sum()
+    loss = loss + sum((dec[i] * torch.from_numpy(gold[f"w_dec{i}"]).cuda()).sum() for i in range(3))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - l0 > 2000, "train kernels were not launched"
+    names = [str(n) for n in gold["grad_names"]]
+    params = dict(model.named_parameters())
+    bad = []
+    for i, n in enumerate(names):
+        g = params[n].grad
+        assert g is not None, n
+        g = g.double().cpu()
+        ref_norm, ref_dot, noise = float(gold["grad_norm"][i]), float(gold["grad_dot"][i]), float(gold["grad_fp32_err"][i])
+        tol = 2e-3 * ref_norm + 4.0 * noise + 1e-9
+        if abs(float(g.norm()) - ref_norm) > tol or abs(float((g * torch.from_numpy(_probe(g.shape, i))).sum()) - ref_dot) > 8 * tol:
+            bad.append((n, float(g.norm()), ref_norm, tol))
+    assert not bad, (len(bad), bad[:10])
+    for k in [k for k in gold.files if k.startswith("full/")]:
+        i = names.index(k[5:])
+        tol = 2e-3 + 4.0 * float(gold["grad_fp32_err"][i]) / float(gold["grad_norm"][i])
+        assert rel_l2(params[k[5:]].grad.cpu(), gold[k]) < tol, k
+    bufs = dict(model.named_buffers())
+    for k in [k for k in gold.files if k.startswith("buf/")]:
+        assert rel_l2(bufs[k[4:]].double().cpu(), gold[k]) < 2e-3, k
+
+
+def test_train_step_bf16_runs_and_tracks_fp32():
+    """bf16 storage (tcgen05 forward convs and stride-1 data gradients, CUDA-core weight gradients): finite everywhere, head
+    outputs and the large gradients within bf16 noise of the float64 reference."""
+    from findtextcenternet_b200 import train_ops
+    gold = np.load(os.path.join(GOLDEN, "train_xl64_seed0.npz"))
+    model = _model("bf16")
+    x = torch.from_numpy(gold["x"]).cuda()
+    heat, feat = train_ops.detection_train_forward(model.detector, x, sd_prob=0.0)
+    assert rel_l2(heat.detach().cpu(), gold["heatmap"]) < 0.5      # 8-sample batch statistics at the 2x2 levels amplify bf16 noise
+    ((heat * torch.from_numpy(gold["w_heat"]).cuda()).sum() + 0.01 * feat.sum()).backward()
+    for n, p in model.detector.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n
+
+
+def test_stochastic_depth_draws_and_module_surface():
+    """model(x, fmask) in train mode (the train1.py call) with StochasticDepth on: runs, gradients finite; pinned noise that
+    drops every residual branch of an image leaves that image's tap equal to the identity path."""
+    from findtextcenternet_b200 import synthetic
+    model = _model("fp32")
+    x = synthetic.detector_input(2, 0, "rand")[:, :, :64, :64].contiguous().cuda()
+    fmask = torch.zeros(2 * 16 * 16, dtype=torch.bool, device="cuda")
+    fmask[::5] = True
+    heat, dec = model(x, fmask)
+    assert heat.shape == (2, 9, 16, 16) and [tuple(d.shape) for d in dec] == [(int(fmask.sum()), m) for m in (1091, 1093, 1097)]
+    (heat.sum() + sum(d.sum() for d in dec)).backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+
+
+def test_loss_function_backward_matches_autograd_of_the_oracle():
+    """loss_function / loss_function3 are differentiable (train1.py:151, train3.py: loss.backward()): d loss / d heatmap and
+    d loss / d decoder logits from the analytic kernels == torch autograd over the CPU oracle (fp32, rel-L2 1e-4)."""
+    from findtextcenternet_b200 import loss_func as LF, synthetic
+    from oracle import loss_oracle as LO
+    b = synthetic.loss_inputs(0)
+    names = ("heatmap", "dec0", "dec1", "dec2")
+    cpu = {k: b[k].clone().requires_grad_() for k in names}
+    r = LO.loss_function(b["fmask"], b["labelmap"], b["idmap"], cpu["heatmap"], [cpu["dec0"], cpu["dec1"], cpu["dec2"]])
+    wts = {k: 0.3 + 0.1 * i for i, k in enumerate(LF.MAP_LOSSES + ["id_loss"])}
+    sum(wts[k] * r[k] for k in wts).backward()
+    gpu = {k: b[k].cuda().requires_grad_() for k in names}
+    x = {k: v.cuda() for k, v in b.items()}
+    rg = LF.loss_function(x["fmask"], x["labelmap"], x["idmap"], gpu["heatmap"], [gpu["dec0"], gpu["dec1"], gpu["dec2"]])
+    sum(wts[k] * rg[k] for k in wts).backward()
+    for k in names:
+        assert rel_l2(gpu[k].grad.cpu(), cpu[k].grad) < 1e-4, k
+    o_cpu = [b[f"out3_{i}"].clone().requires_grad_() for i in range(3)]
+    LO.loss_function3(o_cpu, b["labelcode"], b["mask3"])["loss"].backward()
+    o_gpu = [b[f"out3_{i}"].cuda().requires_grad_() for i in range(3)]
+    LF.loss_function3(o_gpu, x["labelcode"], x["mask3"])["loss"].backward()
+    for a, c in zip(o_gpu, o_cpu):
+        assert rel_l2(a.grad.cpu(), c.grad) < 1e-4
+
+
+def test_train1_step_decreases_the_loss():
+    """findtextcenternet_b200.train.train1_step == the body of the train1.py loop (:183-191): three steps on one synthetic
+    batch lower the CoV-weighted loss and move every parameter."""
+    from findtextcenternet_b200 import synthetic, train
+    from findtextcenternet_b200.loss_func import CoVWeightingLoss
+    from findtextcenternet_b200.models.adamw_schedulefree import AdamWScheduleFree
+    model = _model("fp32")
+    batch = synthetic.train1_batch(2, seed=0, size=64, device="cuda")
+    opt = AdamWScheduleFree([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+    cov = CoVWeightingLoss(device="cuda", losses=train.TRAIN1_LOSSES)
+    opt.train()
+    before = [p.detach().clone() for p in list(model.parameters())[:50]]
+    losses = []
+    fmask = None
+    for _ in range(3):
+        fmask = model.get_fmask(batch["labelmap"], fmask)
+        loss, raw = train.train1_step(model, opt, cov, batch["image"], batch["labelmap"], batch["idmap"], fmask)
+        losses.append(float(raw["loss"]))
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < losses[0], losses
+    assert all(not torch.equal(a, p.detach()) for a, p in zip(before, list(model.parameters())[:50]))
