@@ -123,6 +123,18 @@ assert calls >= 2
 for i, p in enumerate(model.parameters()):
     mean = sum(grads_all[r][i] for r in range(world)) / world
     assert torch.allclose(p.grad, mean, atol=1e-6), i
+# train1_step: the nine raw losses that drive the CoV weights take their cross-rank mean VALUE but keep the local gradient path
+from findtextcenternet_b200.train import TRAIN1_LOSSES, _sync_loss_values
+leaf = torch.full((len(TRAIN1_LOSSES),), float(rank + 1), requires_grad=True)
+raw = {k: leaf[i] * (i + 1) for i, k in enumerate(TRAIN1_LOSSES)}
+raw["correct"] = torch.tensor(3)
+synced = _sync_loss_values(raw)
+mean_rank = sum(r + 1 for r in range(world)) / world
+for i, k in enumerate(TRAIN1_LOSSES):
+    assert abs(float(synced[k]) - mean_rank * (i + 1)) < 1e-6, (k, float(synced[k]))
+assert int(synced["correct"]) == 3
+sum(synced[k] for k in TRAIN1_LOSSES).backward()
+assert torch.allclose(leaf.grad, torch.arange(1, len(TRAIN1_LOSSES) + 1, dtype=torch.float32))
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
