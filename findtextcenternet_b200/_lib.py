@@ -110,6 +110,14 @@ SYMBOLS = {
     "ftc_train_se_fc": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ftc_train_se_fc_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ftc_train_upsample2x_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ftc_train_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _f, _vp]),
+    "ftc_train_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ftc_train_swiglu": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
+    "ftc_train_swiglu_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
+    "ftc_train_embed3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _i64, _i, _vp]),
+    "ftc_train_embed3_bwd": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ftc_train_attention_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i]),
+    "ftc_train_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ftc_op_attention": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

@@ -320,3 +320,107 @@ def upsample2x_bwd(dy: torch.Tensor) -> torch.Tensor:
         _lib.check(lib.ftc_train_upsample2x_bwd(dy.data_ptr(), dx.data_ptr(), _dt(dy), b, ho // 2, wo // 2, c, _s(dy)),
                    "ftc_train_upsample2x_bwd")
     return dx
+
+
+# ---- Transformer train-step pieces ----
+def layernorm_train(x, gamma, beta, eps: float = 1e-5, r1=None, r2=None):
+    """y = LN(x (+ r1) (+ r2)); -> (y, xs, mean, rstd) with xs the summed input (x itself without residuals)."""
+    lib = _lib.load()
+    assert x.is_cuda and x.is_contiguous()
+    d = x.shape[-1]
+    rows = x.numel() // d
+    y = torch.empty_like(x)
+    has_res = r1 is not None or r2 is not None
+    xs = torch.empty_like(x) if has_res else None
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    g, b = _f32(gamma, x.device), _f32(beta, x.device)
+    a1 = None if r1 is None else r1.contiguous()
+    a2 = None if r2 is None else r2.contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ftc_train_layernorm(x.data_ptr(), _p(a1), _p(a2), _p(xs), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                           _dt(x), rows, d, g.data_ptr(), b.data_ptr(), eps, _s(x)), "ftc_train_layernorm")
+    return y, (xs if has_res else x), mean, rstd
+
+
+def layernorm_train_bwd(xs, dy, mean, rstd, gamma):
+    """-> (dx, dgamma, dbeta)"""
+    lib = _lib.load()
+    dy = dy.contiguous()
+    d = xs.shape[-1]
+    rows = xs.numel() // d
+    dx = torch.empty_like(xs)
+    dgamma = torch.empty(d, dtype=torch.float32, device=xs.device)
+    dbeta = torch.empty(d, dtype=torch.float32, device=xs.device)
+    scratch = _reduce_scratch(rows, d, xs.device)
+    g = _f32(gamma, xs.device)
+    with torch.cuda.device(xs.device):
+        _lib.check(lib.ftc_train_layernorm_bwd(xs.data_ptr(), dy.data_ptr(), dx.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                               _dt(xs), rows, d, g.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                               scratch.data_ptr(), _s(xs)), "ftc_train_layernorm_bwd")
+    return dx, dgamma, dbeta
+
+
+def swiglu(x1, xg):
+    lib = _lib.load()
+    assert x1.is_cuda and x1.is_contiguous() and xg.is_contiguous() and x1.dtype == xg.dtype
+    h = torch.empty_like(x1)
+    with torch.cuda.device(x1.device):
+        _lib.check(lib.ftc_train_swiglu(x1.data_ptr(), xg.data_ptr(), h.data_ptr(), _dt(x1), x1.numel(), _s(x1)), "ftc_train_swiglu")
+    return h
+
+
+def swiglu_bwd(x1, xg, dh):
+    lib = _lib.load()
+    dh = dh.contiguous()
+    dx1, dxg = torch.empty_like(x1), torch.empty_like(xg)
+    with torch.cuda.device(x1.device):
+        _lib.check(lib.ftc_train_swiglu_bwd(x1.data_ptr(), xg.data_ptr(), dh.data_ptr(), dx1.data_ptr(), dxg.data_ptr(), _dt(x1),
+                                            x1.numel(), _s(x1)), "ftc_train_swiglu_bwd")
+    return dx1, dxg
+
+
+def embed3(tokens, tables, dtype):
+    """tokens int64 [...]; tables: three fp32 [m_i, D] -> [..., D] (dtype) = sum_i tables[i][tokens mod m_i]."""
+    lib = _lib.load()
+    assert tokens.is_cuda and tokens.dtype == torch.int64
+    tok = tokens.contiguous()
+    t = [_f32(e, tok.device) for e in tables]
+    d = t[0].shape[1]
+    out = torch.empty(*tok.shape, d, dtype=dtype, device=tok.device)
+    with torch.cuda.device(tok.device):
+        _lib.check(lib.ftc_train_embed3(tok.data_ptr(), t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[0].shape[0],
+                                        t[1].shape[0], t[2].shape[0], out.data_ptr(), _dt(out), tok.numel(), d, _s(tok)),
+                   "ftc_train_embed3")
+    return out
+
+
+def embed3_bwd(tokens, dy, ms):
+    """-> three fp32 [m_i, D] table gradients"""
+    lib = _lib.load()
+    tok = tokens.contiguous()
+    dy = dy.contiguous()
+    d = dy.shape[-1]
+    outs = [torch.empty(m, d, dtype=torch.float32, device=dy.device) for m in ms]
+    with torch.cuda.device(dy.device):
+        _lib.check(lib.ftc_train_embed3_bwd(tok.data_ptr(), dy.data_ptr(), _dt(dy), tok.numel(), d, ms[0], ms[1], ms[2],
+                                            outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), _s(dy)),
+                   "ftc_train_embed3_bwd")
+    return outs
+
+
+def attention_bwd(q, k, v, dout, heads: int, mask=None):
+    """q / dout [B, Lt, D], k / v [B, Ls, D] contiguous, mask fp32 [B, Ls] additive -> (dq, dk, dv) fp32."""
+    lib = _lib.load()
+    assert q.is_cuda and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    dout = dout.contiguous()
+    b, lt, d = q.shape
+    ls = k.shape[1]
+    f = dict(dtype=torch.float32, device=q.device)
+    dq, dk, dv = torch.empty(b, lt, d, **f), torch.empty(b, ls, d, **f), torch.empty(b, ls, d, **f)
+    scratch = torch.empty(int(lib.ftc_train_attention_bwd_scratch_bytes(b, heads, lt, ls)) // 4, **f)
+    with torch.cuda.device(q.device):
+        _lib.check(lib.ftc_train_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), _p(mask), dout.data_ptr(), dq.data_ptr(),
+                                               dk.data_ptr(), dv.data_ptr(), scratch.data_ptr(), _dt(q), b, heads, d // heads, lt, ls,
+                                               _s(q)), "ftc_train_attention_bwd")
+    return dq, dk, dv

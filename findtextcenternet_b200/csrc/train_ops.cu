@@ -596,6 +596,226 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Transformer train-step pieces (train3.py:132-137 differentiates models/transformer.py:58-253).
+// LayerNorm over the last axis of [rows, D] with up to two residual inputs folded in (EncoderBlock / DecoderBlock:
+// LN(ff + _x + skip), models/transformer.py:149-160,196-211): xs = x (+ r1) (+ r2) is written out because the backward
+// needs it; mean / rstd fp32 per row.  One warp per row.
+template <typename T>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r1, const T* __restrict__ r2,
+                                                     T* __restrict__ xs, T* __restrict__ y, float* __restrict__ mean_out,
+                                                     float* __restrict__ rstd_out, int64_t rows, int D,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int64_t base = row * D;
+  float s = 0.f;
+  for (int e = lane; e < D; e += 32) {
+    float v = to_f(x[base + e]);
+    if (r1) v += to_f(r1[base + e]);
+    if (r2) v += to_f(r2[base + e]);
+    if (xs) { xs[base + e] = from_f<T>(v); v = to_f(from_f<T>(v)); }   // statistics of the stored (rounded) sum
+    s += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / D;
+  const T* src = xs ? xs : x;     // same thread wrote the elements it re-reads
+  float q = 0.f;
+  for (int e = lane; e < D; e += 32) { float d = to_f(src[base + e]) - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / D + eps);
+  for (int e = lane; e < D; e += 32) y[base + e] = from_f<T>(fmaf((to_f(src[base + e]) - mean) * rstd, gamma[e], beta[e]));
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma
+template <typename T>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ xs, const T* __restrict__ dy, T* __restrict__ dx,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd, int64_t rows,
+                                                     int D, const float* __restrict__ gamma) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int64_t base = row * D;
+  const float mu = mean[row], rs = rstd[row];
+  float a = 0.f, b = 0.f;
+  for (int e = lane; e < D; e += 32) {
+    float g = to_f(dy[base + e]) * gamma[e];
+    float xh = (to_f(xs[base + e]) - mu) * rs;
+    a += g;
+    b = fmaf(g, xh, b);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  a /= D; b /= D;
+  for (int e = lane; e < D; e += 32) {
+    float g = to_f(dy[base + e]) * gamma[e];
+    float xh = (to_f(xs[base + e]) - mu) * rs;
+    dx[base + e] = from_f<T>(rs * (g - a - xh * b));
+  }
+}
+
+// column partials of (dy, dy * xhat) with per-ROW statistics: same two-stage scheme as col_reduce_kernel
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) ln_col_reduce_kernel(const T* __restrict__ xs, const T* __restrict__ dy,
+                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                    int64_t rows, int D, int64_t rows_per_chunk,
+                                                                    float* __restrict__ part) {
+  __shared__ float sm[2][RED_LANES][RED_CH];
+  const int cl = threadIdx.x % RED_CH, lane = threadIdx.x / RED_CH;
+  const int c = blockIdx.x * RED_CH + cl;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < D) {
+    for (int64_t r = r0 + lane; r < r1; r += RED_LANES) {
+      float g = to_f(dy[r * D + c]);
+      s0 += g;
+      s1 = fmaf(g, (to_f(xs[r * D + c]) - mean[r]) * rstd[r], s1);
+    }
+  }
+  sm[0][lane][cl] = s0;
+  sm[1][lane][cl] = s1;
+  __syncthreads();
+  if (lane == 0 && c < D) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int l = 0; l < RED_LANES; ++l) { a += sm[0][l][cl]; b += sm[1][l][cl]; }
+    const int64_t nchunk = gridDim.y;
+    part[((int64_t)0 * nchunk + blockIdx.y) * D + c] = a;
+    part[((int64_t)1 * nchunk + blockIdx.y) * D + c] = b;
+  }
+}
+
+// SwiGLU gate (models/transformer.py:66-69): h = x1 * silu(xg) and its backward
+template <typename T>
+__global__ void __launch_bounds__(256) swiglu_fwd_kernel(const T* __restrict__ x1, const T* __restrict__ xg, T* __restrict__ h,
+                                                         int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    h[i] = from_f<T>(to_f(x1[i]) * silu_precise(to_f(xg[i])));
+}
+template <typename T>
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const T* __restrict__ x1, const T* __restrict__ xg, const T* __restrict__ dh,
+                                                         T* __restrict__ dx1, T* __restrict__ dxg, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = to_f(xg[i]), d = to_f(dh[i]);
+    dx1[i] = from_f<T>(d * silu_precise(g));
+    dxg[i] = from_f<T>(d * to_f(x1[i]) * act_grad(g, ACT_SILU));
+  }
+}
+
+// Decoder token embedding (models/transformer.py:226-233): out[row] = sum_i E_i[token[row] mod m_i]; tables fp32 [m_i][D]
+struct Embed3 { const float* e[3]; float* de[3]; int m[3]; };
+template <typename T>
+__global__ void __launch_bounds__(256) embed3_fwd_kernel(const int64_t* __restrict__ tok, Embed3 tb, T* __restrict__ out,
+                                                         int64_t rows, int D) {
+  const int64_t total = rows * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / D;
+    const int e = (int)(i - row * D);
+    const int64_t t = tok[row];
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v += tb.e[k][(int64_t)(((t % tb.m[k]) + tb.m[k]) % tb.m[k]) * D + e];
+    out[i] = from_f<T>(v);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) embed3_bwd_kernel(const int64_t* __restrict__ tok, Embed3 tb, const T* __restrict__ dy,
+                                                         int64_t rows, int D) {
+  const int64_t total = rows * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / D;
+    const int e = (int)(i - row * D);
+    const int64_t t = tok[row];
+    const float g = to_f(dy[i]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) atomicAdd(tb.de[k] + (int64_t)(((t % tb.m[k]) + tb.m[k]) % tb.m[k]) * D + e, g);
+  }
+}
+
+// Attention backward (F.scaled_dot_product_attention with an additive key mask, models/transformer.py:133).
+// q / dout / dq: [B*Lt, D], k / v / dk / dv: [B*Ls, D], head h at columns h*hd.  Two kernels, no atomics:
+//  A (warp per query row): recompute s = scale q.k + mask, p = softmax(s); dP_j = dout.v_j; dS = p * (dP - sum_j p dP);
+//    store p and dS rows in the [B,H,Lt,Ls] scratch; dq = scale * sum_j dS_j k_j
+//  B (warp per key row):   dv_j = sum_i p_ij dout_i ; dk_j = scale * sum_i dS_ij q_i
+constexpr int ATT_MAX_HD = 128;
+template <typename T>
+__global__ void __launch_bounds__(128) attn_bwd_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                                                            const float* __restrict__ mask, const T* __restrict__ dout,
+                                                            float* __restrict__ P, float* __restrict__ dS, float* __restrict__ dq,
+                                                            int H, int hd, int Lt, int Ls, int D, float scale) {
+  extern __shared__ float att_sm[];   // per warp: q[hd], do[hd], s[Ls], dp[Ls]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + warp, h = blockIdx.y, b = blockIdx.z;
+  if (i >= Lt) return;                 // whole warp exits together (no block-level barrier below)
+  float* sq = att_sm + (size_t)warp * (2 * hd + 2 * Ls);
+  float* sdo = sq + hd;
+  float* ss = sdo + hd;
+  float* sdp = ss + Ls;
+  const int64_t qrow = ((int64_t)b * Lt + i) * D + (int64_t)h * hd;
+  for (int e = lane; e < hd; e += 32) { sq[e] = to_f(q[qrow + e]); sdo[e] = to_f(dout[qrow + e]); }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j = lane; j < Ls; j += 32) {
+    const int64_t krow = ((int64_t)b * Ls + j) * D + (int64_t)h * hd;
+    float a = 0.f, c = 0.f;
+    for (int e = 0; e < hd; ++e) { a = fmaf(sq[e], to_f(k[krow + e]), a); c = fmaf(sdo[e], to_f(v[krow + e]), c); }
+    a = a * scale + (mask ? mask[(int64_t)b * Ls + j] : 0.f);
+    ss[j] = a;
+    sdp[j] = c;
+    mx = fmaxf(mx, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float l = 0.f;
+  for (int j = lane; j < Ls; j += 32) { float p = expf(ss[j] - mx); ss[j] = p; l += p; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  const float inv = 1.f / l;
+  float delta = 0.f;
+  for (int j = lane; j < Ls; j += 32) { float p = ss[j] * inv; ss[j] = p; delta = fmaf(p, sdp[j], delta); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+  const int64_t prow = (((int64_t)b * H + h) * Lt + i) * Ls;
+  for (int j = lane; j < Ls; j += 32) {
+    const float p = ss[j], ds = p * (sdp[j] - delta);
+    P[prow + j] = p;
+    dS[prow + j] = ds;
+    sdp[j] = ds;
+  }
+  __syncwarp();
+  for (int e = lane; e < hd; e += 32) {
+    float a = 0.f;
+    for (int j = 0; j < Ls; ++j) a = fmaf(sdp[j], to_f(k[((int64_t)b * Ls + j) * D + (int64_t)h * hd + e]), a);
+    dq[qrow + e] = a * scale;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) attn_bwd_cols_kernel(const T* __restrict__ q, const T* __restrict__ dout,
+                                                            const float* __restrict__ P, const float* __restrict__ dS,
+                                                            float* __restrict__ dk, float* __restrict__ dv, int H, int hd, int Lt,
+                                                            int Ls, int D, float scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 4 + warp, h = blockIdx.y, b = blockIdx.z;
+  if (j >= Ls) return;
+  const int64_t krow = ((int64_t)b * Ls + j) * D + (int64_t)h * hd;
+  const int64_t pbase = (((int64_t)b * H + h) * Lt) * Ls + j;
+  for (int e = lane; e < hd; e += 32) {
+    float av = 0.f, ak = 0.f;
+    for (int i = 0; i < Lt; ++i) {
+      const int64_t qrow = ((int64_t)b * Lt + i) * D + (int64_t)h * hd + e;
+      av = fmaf(P[pbase + (int64_t)i * Ls], to_f(dout[qrow]), av);
+      ak = fmaf(dS[pbase + (int64_t)i * Ls], to_f(q[qrow]), ak);
+    }
+    dv[krow + e] = av;
+    dk[krow + e] = ak * scale;
+  }
+}
+
 template <typename T> const T* cp(const void* p) { return reinterpret_cast<const T*>(p); }
 template <typename T> T* mp(void* p) { return reinterpret_cast<T*>(p); }
 
@@ -835,6 +1055,125 @@ int ftc_train_upsample2x_bwd(const void* dy, void* dx, int dtype, int batch, int
     upsample2x_bwd_kernel<float><<<grid, 256, 0, s>>>(cp<float>(dy), mp<float>(dx), h, w, c, sy, sx);
   else
     upsample2x_bwd_kernel<bf16><<<grid, 256, 0, s>>>(cp<bf16>(dy), mp<bf16>(dx), h, w, c, sy, sx);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_layernorm(const void* x, const void* r1, const void* r2, void* xs, void* y, float* mean, float* rstd, int dtype,
+                        int64_t rows, int d, const float* gamma, const float* beta, float eps, void* stream) {
+  FTC_REQUIRE(x && y && mean && rstd && gamma && beta && rows > 0 && d > 0 && dtype_ok(dtype), "bad argument");
+  FTC_REQUIRE((r1 == nullptr && r2 == nullptr) || xs != nullptr, "xs is required when residuals are given");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
+  if (dtype == DT_F32)
+    ln_fwd_kernel<float><<<grid, 256, 0, s>>>(cp<float>(x), cp<float>(r1), cp<float>(r2), mp<float>(xs), mp<float>(y), mean, rstd, rows, d,
+                                            gamma, beta, eps);
+  else
+    ln_fwd_kernel<bf16><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(r1), cp<bf16>(r2), mp<bf16>(xs), mp<bf16>(y), mean, rstd, rows, d, gamma,
+                                           beta, eps);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_layernorm_bwd(const void* xs, const void* dy, void* dx, const float* mean, const float* rstd, int dtype, int64_t rows,
+                            int d, const float* gamma, float* dgamma, float* dbeta, void* scratch, void* stream) {
+  FTC_REQUIRE(xs && dy && dx && mean && rstd && gamma && dgamma && dbeta && scratch && rows > 0 && d > 0 && dtype_ok(dtype),
+              "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
+  const int nchunk = red_chunks(rows);
+  const int64_t rpc = (rows + nchunk - 1) / nchunk;
+  dim3 rgrid(ceil_div(d, RED_CH), nchunk);
+  if (dtype == DT_F32) {
+    ln_bwd_kernel<float><<<grid, 256, 0, s>>>(cp<float>(xs), cp<float>(dy), mp<float>(dx), mean, rstd, rows, d, gamma);
+    FTC_POST_LAUNCH();
+    ln_col_reduce_kernel<float><<<rgrid, RED_THREADS, 0, s>>>(cp<float>(xs), cp<float>(dy), mean, rstd, rows, d, rpc, (float*)scratch);
+  } else {
+    ln_bwd_kernel<bf16><<<grid, 256, 0, s>>>(cp<bf16>(xs), cp<bf16>(dy), mp<bf16>(dx), mean, rstd, rows, d, gamma);
+    FTC_POST_LAUNCH();
+    ln_col_reduce_kernel<bf16><<<rgrid, RED_THREADS, 0, s>>>(cp<bf16>(xs), cp<bf16>(dy), mean, rstd, rows, d, rpc, (float*)scratch);
+  }
+  FTC_POST_LAUNCH();
+  col_reduce_finish_kernel<1><<<ceil_div(d, 128), 128, 0, s>>>((const float*)scratch, nchunk, d, rows, dbeta, dgamma);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_swiglu(const void* x1, const void* xg, void* h, int dtype, int64_t total, void* stream) {
+  FTC_REQUIRE(x1 && xg && h && total > 0 && dtype_ok(dtype), "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DT_F32) swiglu_fwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x1), cp<float>(xg), mp<float>(h), total);
+  else swiglu_fwd_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(cp<bf16>(x1), cp<bf16>(xg), mp<bf16>(h), total);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_swiglu_bwd(const void* x1, const void* xg, const void* dh, void* dx1, void* dxg, int dtype, int64_t total,
+                         void* stream) {
+  FTC_REQUIRE(x1 && xg && dh && dx1 && dxg && total > 0 && dtype_ok(dtype), "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DT_F32)
+    swiglu_bwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x1), cp<float>(xg), cp<float>(dh), mp<float>(dx1), mp<float>(dxg), total);
+  else
+    swiglu_bwd_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(cp<bf16>(x1), cp<bf16>(xg), cp<bf16>(dh), mp<bf16>(dx1), mp<bf16>(dxg), total);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_embed3(const int64_t* tokens, const float* e0, const float* e1, const float* e2, int m0, int m1, int m2, void* out,
+                     int dtype, int64_t rows, int d, void* stream) {
+  FTC_REQUIRE(tokens && e0 && e1 && e2 && out && rows > 0 && d > 0 && m0 > 0 && m1 > 0 && m2 > 0 && dtype_ok(dtype), "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  Embed3 tb = {{e0, e1, e2}, {nullptr, nullptr, nullptr}, {m0, m1, m2}};
+  if (dtype == DT_F32) embed3_fwd_kernel<float><<<ew_grid(rows * d), 256, 0, s>>>(tokens, tb, mp<float>(out), rows, d);
+  else embed3_fwd_kernel<bf16><<<ew_grid(rows * d), 256, 0, s>>>(tokens, tb, mp<bf16>(out), rows, d);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_train_embed3_bwd(const int64_t* tokens, const void* dy, int dtype, int64_t rows, int d, int m0, int m1, int m2, float* de0,
+                         float* de1, float* de2, void* stream) {
+  FTC_REQUIRE(tokens && dy && de0 && de1 && de2 && rows > 0 && d > 0 && m0 > 0 && m1 > 0 && m2 > 0 && dtype_ok(dtype), "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  FTC_CHECK_CUDA(cudaMemsetAsync(de0, 0, (size_t)m0 * d * sizeof(float), s));
+  FTC_CHECK_CUDA(cudaMemsetAsync(de1, 0, (size_t)m1 * d * sizeof(float), s));
+  FTC_CHECK_CUDA(cudaMemsetAsync(de2, 0, (size_t)m2 * d * sizeof(float), s));
+  Embed3 tb = {{nullptr, nullptr, nullptr}, {de0, de1, de2}, {m0, m1, m2}};
+  if (dtype == DT_F32) embed3_bwd_kernel<float><<<ew_grid(rows * d), 256, 0, s>>>(tokens, tb, cp<float>(dy), rows, d);
+  else embed3_bwd_kernel<bf16><<<ew_grid(rows * d), 256, 0, s>>>(tokens, tb, cp<bf16>(dy), rows, d);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+size_t ftc_train_attention_bwd_scratch_bytes(int batch, int heads, int lt, int ls) {
+  return (size_t)2 * batch * heads * lt * ls * sizeof(float);
+}
+
+int ftc_train_attention_bwd(const void* q, const void* k, const void* v, const float* mask, const void* dout, float* dq, float* dk,
+                            float* dv, void* scratch, int dtype, int batch, int heads, int hd, int lt, int ls, void* stream) {
+  FTC_REQUIRE(q && k && v && dout && dq && dk && dv && scratch && dtype_ok(dtype), "bad argument");
+  FTC_REQUIRE(batch > 0 && batch <= 65535 && heads > 0 && heads <= 65535 && hd > 0 && hd <= ATT_MAX_HD && lt > 0 && ls > 0, "bad geometry");
+  const size_t smem = (size_t)4 * (2 * hd + 2 * ls) * sizeof(float);
+  FTC_REQUIRE(smem <= 200 * 1024, "key sequence too long for the per-warp staging");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int D = heads * hd;
+  const float scale = 1.0f / sqrtf((float)hd);
+  float* P = (float*)scratch;
+  float* dS = P + (size_t)batch * heads * lt * ls;
+  dim3 ga(ceil_div(lt, 4), heads, batch), gb(ceil_div(ls, 4), heads, batch);
+  if (dtype == DT_F32) {
+    if (smem > 48 * 1024) FTC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_bwd_rows_kernel<float><<<ga, 128, smem, s>>>(cp<float>(q), cp<float>(k), cp<float>(v), mask, cp<float>(dout), P, dS, dq, heads, hd, lt,
+                                                     ls, D, scale);
+    FTC_POST_LAUNCH();
+    attn_bwd_cols_kernel<float><<<gb, 128, 0, s>>>(cp<float>(q), cp<float>(dout), P, dS, dk, dv, heads, hd, lt, ls, D, scale);
+  } else {
+    if (smem > 48 * 1024) FTC_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_rows_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_bwd_rows_kernel<bf16><<<ga, 128, smem, s>>>(cp<bf16>(q), cp<bf16>(k), cp<bf16>(v), mask, cp<bf16>(dout), P, dS, dq, heads, hd, lt, ls,
+                                                    D, scale);
+    FTC_POST_LAUNCH();
+    attn_bwd_cols_kernel<bf16><<<gb, 128, 0, s>>>(cp<bf16>(q), cp<bf16>(dout), P, dS, dk, dv, heads, hd, lt, ls, D, scale);
+  }
   FTC_POST_LAUNCH();
   return 0;
 }

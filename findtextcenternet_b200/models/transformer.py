@@ -38,8 +38,7 @@ class ModelDimensions:   # models/transformer.py:255-264
 def _no_train(mod: nn.Module):
     if mod.training and torch.is_grad_enabled():
         raise NotImplementedError(
-            "findtextcenternet_b200: the train-mode (autograd) transformer step is not built yet; "
-            "call .eval() / torch.no_grad() for the sm_100a inference engine")
+            "findtextcenternet_b200: TransformerPredictor is an inference loop; call .eval() / torch.no_grad()")
 
 
 class Encoder(nn.Module):
@@ -112,6 +111,7 @@ class Transformer(nn.Module, _EngineOwner):
                  max_dec_seq_len=5000, dropout=0.1):
         super().__init__()
         self.head_num = head_num
+        self.dropout = dropout
         self.max_len = max(max_enc_seq_len, max_dec_seq_len)
         self.encoder = Encoder(input_dim=enc_input_dim, embed_dim=embed_dim, head_num=head_num, max_seq_len=max_enc_seq_len,
                                block_num=enc_block_num, dropout=dropout)
@@ -120,7 +120,10 @@ class Transformer(nn.Module, _EngineOwner):
         self._init_engine()
 
     def forward(self, enc_input, dec_input):
-        _no_train(self)
+        if self.training and torch.is_grad_enabled():
+            # train3.py:132-137: train mode with autograd on -> per-layer kernels with a tape (train_ops.py)
+            from ..train_ops import transformer_train_forward
+            return transformer_train_forward(self, enc_input, dec_input)
         if not enc_input.is_cuda:
             raise RuntimeError("findtextcenternet_b200 transformer: input must be a CUDA tensor (no CPU path)")
         with torch.no_grad():

@@ -52,3 +52,20 @@ def _sync_loss_values(rawloss: Dict[str, torch.Tensor], group=None) -> Dict[str,
     for i, k in enumerate(keys):
         out[k] = rawloss[k] + (vals[i] - rawloss[k].detach())
     return out
+
+
+def train3_step(model, optimizer, encoder_input, decoder_input, label_code, msk_token: int = 3, group=None
+                ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """One iteration of the train3.py loop body (:132-150): ``outputs = model(encoder_input, decoder_input)`` in train mode,
+    ``loss_function3(outputs, label_code, decoder_input == decoder_MSK)``, backward, (gradient all-reduce,) optimizer step.
+    The reference wraps the step in fp16 autocast + GradScaler; here precision is the model's ``set_precision`` (bf16 storage
+    with fp32 accumulation needs no loss scaling)."""
+    from .loss_func import loss_function3
+    optimizer.zero_grad()
+    outputs = model(encoder_input, decoder_input)
+    rawloss = loss_function3(outputs, label_code, decoder_input == msk_token)
+    rawloss["loss"].backward()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        shard.allreduce_gradients([p for p in model.parameters() if p.requires_grad], group=group)
+    optimizer.step()
+    return rawloss["loss"].detach(), {k: v.detach() for k, v in rawloss.items()}

@@ -304,3 +304,137 @@ def simple_decoder_train_forward(dec, x: Tensor) -> List[Tensor]:
         o = conv2d(y, lin.weight[:, :, None, None], lin.bias)
         outs.append(o.reshape(n, m).float())
     return outs
+
+
+# ====================================================================================================================
+# Transformer train step (train3.py:132-137: ``outputs = model(encoder_input, decoder_input)`` in train mode, then
+# ``loss_function3`` and ``backward()``).  dropout = 0 (ModelDimensions default, models/transformer.py:257-264): train-mode
+# arithmetic equals eval-mode arithmetic, what is added is the tape.
+class _LayerNorm(Function):
+    """y = nn.LayerNorm(x (+ r1) (+ r2)); the residual sums of EncoderBlock / DecoderBlock are folded into the kernel."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, r1, r2, eps):
+        y, xs, mean, rstd = K.layernorm_train(x, gamma, beta, eps, r1, r2)
+        ctx.save_for_backward(xs, mean, rstd, gamma)
+        ctx.res = (r1 is not None, r2 is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, mean, rstd, gamma = ctx.saved_tensors
+        dx, dgamma, dbeta = K.layernorm_train_bwd(xs, dy.contiguous(), mean, rstd, gamma)
+        return dx, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), (dx if ctx.res[0] else None), (dx if ctx.res[1] else None), None
+
+
+class _SwiGLUGate(Function):
+    @staticmethod
+    def forward(ctx, x1, xg):
+        ctx.save_for_backward(x1, xg)
+        return K.swiglu(x1, xg)
+
+    @staticmethod
+    def backward(ctx, dh):
+        x1, xg = ctx.saved_tensors
+        return K.swiglu_bwd(x1, xg, dh.contiguous())
+
+
+class _Embed3(Function):
+    @staticmethod
+    def forward(ctx, tokens, e0, e1, e2, dtype):
+        ctx.save_for_backward(tokens)
+        ctx.ms = (e0.shape[0], e1.shape[0], e2.shape[0])
+        ctx.dt = e0.dtype
+        return K.embed3(tokens, (e0, e1, e2), dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (tokens,) = ctx.saved_tensors
+        d0, d1, d2 = K.embed3_bwd(tokens, dy.contiguous(), ctx.ms)
+        return None, d0.to(ctx.dt), d1.to(ctx.dt), d2.to(ctx.dt), None
+
+
+class _Attention(Function):
+    """F.scaled_dot_product_attention(q, k, v, additive key mask) on [B, L, heads*hd] tensors."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, heads):
+        ctx.save_for_backward(q, k, v, mask)
+        ctx.heads = heads
+        return K.attention(q, k, v, heads, mask)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, mask = ctx.saved_tensors
+        dq, dk, dv = K.attention_bwd(q, k, v, dout.contiguous(), ctx.heads, mask)
+        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    """nn.Linear on [..., C] through the shared GEMM kernels ([rows,1,1,C] 1x1 convolution); C padded to a multiple of 8."""
+    shp = x.shape
+    cpad = (-shp[-1]) % 8
+    if cpad:
+        x = torch.nn.functional.pad(x, (0, cpad))
+        weight = torch.nn.functional.pad(weight, (0, cpad))
+    y = conv2d(x.reshape(-1, 1, 1, x.shape[-1]).contiguous(), weight[:, :, None, None], bias)
+    return y.reshape(*shp[:-1], weight.shape[0])
+
+
+def _pos(x: Tensor, table: Tensor) -> Tensor:
+    """PositionalEncoding.forward (models/transformer.py:45-56): x + encoding[:L] (a learnable parameter)."""
+    return x + table[: x.shape[1]].unsqueeze(0).to(x.dtype)
+
+
+def _mha(m, heads: int, query: Tensor, key: Optional[Tensor], mask: Optional[Tensor]) -> Tensor:
+    """MultiheadAttn.forward (models/transformer.py:99-137): positions on q and k only, v = raw key input, no biases."""
+    if key is None:
+        key, pos_k = query, m.pos_emb_q.encoding
+    else:
+        pos_k = m.pos_emb_k.encoding
+    q = linear(_pos(query, m.pos_emb_q.encoding), m.q_proj.weight)
+    k = linear(_pos(key, pos_k), m.k_proj.weight)
+    v = linear(key, m.v_proj.weight)
+    a = _Attention.apply(q.contiguous(), k.contiguous(), v.contiguous(), mask, heads)
+    return linear(a, m.out_proj.weight)
+
+
+def _ff(ff, x: Tensor) -> Tensor:
+    """SwiGLU.forward (models/transformer.py:66-71)."""
+    h = _SwiGLUGate.apply(linear(x, ff.w1.weight, ff.w1.bias).contiguous(), linear(x, ff.wg.weight, ff.wg.bias).contiguous())
+    return linear(h, ff.w2.weight, ff.w2.bias)
+
+
+def _ln(x: Tensor, norm, r1=None, r2=None) -> Tensor:
+    return _LayerNorm.apply(x.contiguous(), norm.weight, norm.bias, r1, r2, 1e-5)
+
+
+def transformer_train_forward(model, enc_input: Tensor, dec_input: Tensor) -> List[Tensor]:
+    """Transformer.forward (models/transformer.py:248-253) in train mode with a tape -> 3 x [B, Ld, m_i] fp32."""
+    if not enc_input.is_cuda:
+        raise RuntimeError("findtextcenternet_b200 transformer: input must be a CUDA tensor (no CPU path)")
+    if getattr(model, "dropout", 0.0):
+        raise NotImplementedError("findtextcenternet_b200: train-mode dropout > 0 is not built (ModelDimensions default is 0.0)")
+    dt = torch.float32 if model.precision == "fp32" else torch.bfloat16
+    enc, dec = model.encoder, model.decoder
+    heads = enc.head_num
+    key_pad = torch.all(enc_input == 0, dim=-1)
+    mask = torch.zeros(key_pad.shape, dtype=torch.float32, device=enc_input.device).masked_fill_(key_pad, float("-inf"))
+    x = _pos(linear(enc_input.to(dt), enc.embed.weight), enc.pos_emb.encoding)
+    x = _ln(x, enc.norm)
+    for i in range(enc.block_num):
+        blk = _sub(enc.blocks, i)
+        skip = x
+        x = _ln(_mha(blk.mha, heads, x, None, mask), blk.norm1, skip)
+        x = _ln(_ff(blk.ff, x), blk.norm2, x, skip)
+    y = x
+    emb = [_sub(dec.embed, i).weight for i in range(3)]
+    x = _pos(_Embed3.apply(dec_input.to(torch.int64), emb[0], emb[1], emb[2], dt), dec.pos_emb.encoding)
+    x = _ln(x, dec.norm)
+    for i in range(dec.block_num):
+        blk = _sub(dec.blocks, i)
+        skip = x
+        x = _ln(_mha(blk.self_attn, heads, x, None, None), blk.norm1, skip)
+        x = _ln(_mha(blk.cross_attn, heads, x, y, mask), blk.norm2, x)
+        x = _ln(_ff(blk.ff, x), blk.norm3, x, skip)
+    return [linear(x, _sub(dec.out_layers, i).weight, _sub(dec.out_layers, i).bias).float() for i in range(3)]

@@ -258,6 +258,35 @@ int ftc_train_se_fc_bwd(const float* dgate, const float* gate, const float* hid_
  * dx [batch,h,w,c] */
 int ftc_train_upsample2x_bwd(const void* dy, void* dx, int dtype, int batch, int h, int w, int c, void* stream);
 
+/* ---- train step of the Transformer (train3.py:132-137 differentiates models/transformer.py:58-253; dropout = 0 as in
+ * ModelDimensions :257-264).  Linear layers are ftc_op_conv2d / ftc_train_conv2d_{wgrad,dgrad} on [rows,1,1,C] tensors.
+ *   ftc_train_layernorm      y = LN(x (+ r1) (+ r2)) * gamma + beta over the last axis (nn.LayerNorm, eps 1e-5; the block outputs
+ *                            LN(ff + _x + skip) :149-160,196-211); xs = the summed input (required when r1 / r2 are given; the
+ *                            backward reads it), mean / rstd fp32 [rows]
+ *   ftc_train_layernorm_bwd  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma (also the gradient of r1, r2);
+ *                            dgamma[d] = sum_rows dy * xhat, dbeta[d] = sum_rows dy; scratch: ftc_train_reduce_scratch_bytes(rows, d)
+ *   ftc_train_swiglu(_bwd)   h = x1 * silu(xg) (SwiGLU.forward :66-69) and dx1 = dh * silu(xg), dxg = dh * x1 * silu'(xg)
+ *   ftc_train_embed3(_bwd)   out[row] = sum_i E_i[token[row] mod m_i] (Decoder.forward :226-233, fp32 tables [m_i][d]); the backward
+ *                            OVERWRITES the three table gradients (zero + fp32 atomics)
+ *   ftc_train_attention_bwd  backward of softmax(q k^T / sqrt(hd) + mask) v (F.scaled_dot_product_attention :133; forward =
+ *                            ftc_op_attention): q / dout [batch*lt, heads*hd], k / v [batch*ls, heads*hd] (dtype), mask fp32
+ *                            [batch, ls] additive or NULL; dq / dk / dv fp32, same shapes; scratch holds the recomputed
+ *                            probabilities and dS: ftc_train_attention_bwd_scratch_bytes */
+int ftc_train_layernorm(const void* x, const void* r1, const void* r2, void* xs, void* y, float* mean, float* rstd, int dtype,
+                        int64_t rows, int d, const float* gamma, const float* beta, float eps, void* stream);
+int ftc_train_layernorm_bwd(const void* xs, const void* dy, void* dx, const float* mean, const float* rstd, int dtype, int64_t rows,
+                            int d, const float* gamma, float* dgamma, float* dbeta, void* scratch, void* stream);
+int ftc_train_swiglu(const void* x1, const void* xg, void* h, int dtype, int64_t total, void* stream);
+int ftc_train_swiglu_bwd(const void* x1, const void* xg, const void* dh, void* dx1, void* dxg, int dtype, int64_t total,
+                         void* stream);
+int ftc_train_embed3(const int64_t* tokens, const float* e0, const float* e1, const float* e2, int m0, int m1, int m2, void* out,
+                     int dtype, int64_t rows, int d, void* stream);
+int ftc_train_embed3_bwd(const int64_t* tokens, const void* dy, int dtype, int64_t rows, int d, int m0, int m1, int m2, float* de0,
+                         float* de1, float* de2, void* stream);
+size_t ftc_train_attention_bwd_scratch_bytes(int batch, int heads, int lt, int ls);
+int ftc_train_attention_bwd(const void* q, const void* k, const void* v, const float* mask, const void* dout, float* dq, float* dk,
+                            float* dv, void* scratch, int dtype, int batch, int heads, int hd, int lt, int ls, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,5 +101,69 @@ def main():
           (np.median(rel), np.quantile(rel, 0.99), rel.max(), float(out["heatmap_fp32_err"])))
 
 
+TF_DIMS = dict(enc_input_dim=106, embed_dim=64, head_num=4, enc_block_num=2, dec_block_num=2, max_enc_seq_len=24,
+               max_dec_seq_len=24, dropout=0.0)   # cross-attn pos_emb_k is sized by the DECODER length (models/transformer.py:186)
+TF_FULL = ("encoder.embed.weight", "encoder.pos_emb.encoding", "encoder.blocks.1.mha.pos_emb_q.encoding",
+           "encoder.blocks.0.mha.k_proj.weight", "encoder.blocks.1.norm2.weight", "encoder.blocks.0.ff.wg.bias",
+           "decoder.embed.1.weight", "decoder.blocks.1.cross_attn.pos_emb_k.encoding", "decoder.blocks.0.cross_attn.v_proj.weight",
+           "decoder.blocks.1.norm3.bias", "decoder.blocks.0.ff.w2.weight", "decoder.out_layers.2.bias")
+
+
+def run_transformer(dtype):
+    from models.transformer import Transformer
+    model = Transformer(**TF_DIMS)
+    dims = {k: v for k, v in TF_DIMS.items() if k != "dropout"}
+    model.load_state_dict(synthetic.transformer_state_dict(0, **dims), strict=True)
+    model = model.to(dtype).train()
+    enc, dec, _ = synthetic.transformer_inputs(3, 24, 16, 0)
+    # Transformer.forward (models/transformer.py:248-253) line by line, with the mask cast to the run's dtype: torch's CPU SDPA
+    # silently mis-handles a float32 additive mask next to float64 q/k/v (encoder output off by 50 %), which would corrupt
+    # the float64 truth; in float32 this is exactly model(enc, dec)
+    key_mask = torch.all(enc == 0, dim=-1)
+    key_mask = torch.where(key_mask[:, None, None, :], float("-inf"), 0).to(dtype)
+    enc_output = model.encoder(enc.to(dtype), key_mask=key_mask)
+    outs = model.decoder(dec, enc_output, key_mask=key_mask)
+    g = torch.Generator().manual_seed(4321)
+    ws = [torch.randn(o.shape, generator=g) / 10 for o in outs]
+    sum((o * w.to(dtype)).sum() for o, w in zip(outs, ws)).backward()
+    return model, enc, dec, [o.detach() for o in outs], ws
+
+
+def main_transformer():
+    """tests/golden/train_transformer_seed0.npz: Transformer.forward in train mode + backward (train3.py:132-137) of the
+    unmodified reference, float64 truth + the fp32 run's per-tensor noise, every gradient fingerprinted."""
+    model, enc, dec, outs, ws = run_transformer(torch.float64)
+    model32, _, _, outs32, _ = run_transformer(torch.float32)
+    out = {"enc": enc.numpy(), "dec": dec.numpy()}
+    for i in range(3):
+        out[f"out{i}"] = outs[i].float().numpy()
+        out[f"w{i}"] = ws[i].numpy()
+    names, norms, dots, errs = [], [], [], []
+    p32 = dict(model32.named_parameters())
+    for i, (n, p) in enumerate(model.named_parameters()):
+        names.append(n)
+        if p.grad is None:      # self-attention never touches pos_emb_k (models/transformer.py:107-109): no gradient at all
+            norms.append(-1.0); dots.append(0.0); errs.append(0.0)
+            continue
+        gd = p.grad.numpy()
+        norms.append(float(np.linalg.norm(gd)))
+        dots.append(float((gd * probe(gd.shape, i)).sum()))
+        errs.append(float(np.linalg.norm(p32[n].grad.double().numpy() - gd)))
+    out["grad_names"], out["grad_norm"], out["grad_dot"], out["grad_fp32_err"] = (np.array(names), np.array(norms), np.array(dots),
+                                                                                   np.array(errs))
+    params = dict(model.named_parameters())
+    for k in TF_FULL:
+        out["full/" + k] = params[k].grad.float().numpy()
+    path = os.path.join(GOLD, "train_transformer_seed0.npz")
+    np.savez_compressed(path, **out)
+    rel = np.array(errs)[np.array(norms) > 0] / np.array(norms)[np.array(norms) > 0]
+    print("wrote", path, os.path.getsize(path), "bytes;", len(names), "gradients; reference fp32-vs-fp64 error median %.2e max %.2e"
+          % (np.median(rel), rel.max()))
+
+
 if __name__ == "__main__":
-    main()
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("detector", "all"):
+        main()
+    if what in ("transformer", "all"):
+        main_transformer()

@@ -212,3 +212,86 @@ def upsample2x(x):
 def upsample2x_bwd(dy):
     my, mx = _interp_matrix(dy.shape[1] // 2), _interp_matrix(dy.shape[2] // 2)
     return torch.einsum("oh,pw,bopc->bhwc", my, mx, dy.double()).to(dy.dtype).contiguous()
+
+
+# ---- Transformer pieces (models/transformer.py:58-253) -----------------------------------------------------------------
+def layernorm_train(x, gamma, beta, eps=1e-5, r1=None, r2=None):
+    xs = x.double()
+    if r1 is not None:
+        xs = xs + r1.double()
+    if r2 is not None:
+        xs = xs + r2.double()
+    xs = xs.to(x.dtype)                       # the kernel stores the sum in the activation dtype and normalises that
+    v = xs.double()
+    mean = v.mean(-1)
+    rstd = 1.0 / torch.sqrt(((v - mean[..., None]) ** 2).mean(-1) + eps)
+    y = (v - mean[..., None]) * rstd[..., None] * gamma.detach().double() + beta.detach().double()
+    return y.to(x.dtype), xs, mean.reshape(-1).float(), rstd.reshape(-1).float()
+
+
+def layernorm_train_bwd(xs, dy, mean, rstd, gamma):
+    d = xs.shape[-1]
+    v = xs.double().reshape(-1, d)
+    xh = (v - mean.double()[:, None]) * rstd.double()[:, None]
+    g = dy.double().reshape(-1, d) * gamma.detach().double()
+    dx = rstd.double()[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    dyf = dy.double().reshape(-1, d)
+    return dx.reshape(xs.shape).to(xs.dtype), (dyf * xh).sum(0).float(), dyf.sum(0).float()
+
+
+def swiglu(x1, xg):
+    return (x1.double() * _act(xg.double(), ACT_SILU)).to(x1.dtype)
+
+
+def swiglu_bwd(x1, xg, dh):
+    d = dh.double()
+    return (d * _act(xg.double(), ACT_SILU)).to(x1.dtype), (d * x1.double() * _act_grad(xg.double(), ACT_SILU)).to(x1.dtype)
+
+
+def embed3(tokens, tables, dtype):
+    out = 0
+    for e in tables:
+        out = out + e.detach().double()[tokens % e.shape[0]]
+    return out.to(dtype)
+
+
+def embed3_bwd(tokens, dy, ms):
+    d = dy.shape[-1]
+    outs = []
+    for m in ms:
+        g = torch.zeros(m, d, dtype=torch.float64)
+        g.index_add_(0, (tokens % m).reshape(-1), dy.double().reshape(-1, d))
+        outs.append(g.float())
+    return outs
+
+
+def _heads(t, heads):
+    b, l, d = t.shape
+    return t.double().reshape(b, l, heads, d // heads).permute(0, 2, 1, 3)
+
+
+def _probs(q, k, heads, mask):
+    qh, kh = _heads(q, heads), _heads(k, heads)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(qh.shape[-1])
+    if mask is not None:
+        s = s + mask.double()[:, None, None, :]
+    return torch.softmax(s, -1), qh, kh
+
+
+def attention(q, k, v, heads, mask=None):
+    p, _, _ = _probs(q, k, heads, mask)
+    o = p @ _heads(v, heads)
+    return o.permute(0, 2, 1, 3).reshape(q.shape).to(q.dtype)
+
+
+def attention_bwd(q, k, v, dout, heads, mask=None):
+    """dV = P^T dO; dP = dO V^T; dS = P (dP - rowsum(P dP)); dQ = dS K / sqrt(hd); dK = dS^T Q / sqrt(hd)"""
+    p, qh, kh = _probs(q, k, heads, mask)
+    vh, doh = _heads(v, heads), _heads(dout, heads)
+    dv = p.transpose(-1, -2) @ doh
+    dp = doh @ vh.transpose(-1, -2)
+    ds = p * (dp - (p * dp).sum(-1, keepdim=True))
+    sc = 1.0 / math.sqrt(qh.shape[-1])
+    dq, dk = ds @ kh * sc, ds.transpose(-1, -2) @ qh * sc
+    back = lambda t, ref: t.permute(0, 2, 1, 3).reshape(ref.shape).float()
+    return back(dq, q), back(dk, k), back(dv, v)

@@ -126,7 +126,8 @@ def oracle_kernels(monkeypatch):
 
     ns = Ns()
     for name in ("conv2d", "conv2d_wgrad", "conv2d_dgrad", "bn_stats", "bn_act", "bn_act_bwd", "dwconv3x3_raw", "dwconv3x3_dgrad",
-                 "dwconv3x3_wgrad", "spatial_sum", "scale_bc", "se_fc_train", "se_fc_train_bwd", "upsample2x", "upsample2x_bwd"):
+                 "dwconv3x3_wgrad", "spatial_sum", "scale_bc", "se_fc_train", "se_fc_train_bwd", "upsample2x", "upsample2x_bwd",
+                 "layernorm_train", "layernorm_train_bwd", "swiglu", "swiglu_bwd", "embed3", "embed3_bwd", "attention", "attention_bwd"):
         setattr(ns, name, getattr(TO, name))
     monkeypatch.setattr(train_ops, "K", ns)
     # the product wrappers refuse CPU tensors; the graph test runs them on CPU on purpose
@@ -204,3 +205,110 @@ def synthetic_probe(shape, i):
     idx = np.arange(n, dtype=np.int64)
     v = (((idx * 2654435761 + i * 40503) >> 7) & 1).astype(np.float64) * 2 - 1
     return v.reshape(shape)
+
+
+# ---- Transformer pieces ---------------------------------------------------------------------------------------------
+def test_layernorm_swiglu_embed_match_autograd():
+    g = torch.Generator().manual_seed(3)
+    d = 24
+    x, r1, r2 = (torch.randn(3, 5, d, generator=g, requires_grad=True) for _ in range(3))
+    gamma, beta = torch.randn(d, generator=g).requires_grad_(), torch.randn(d, generator=g).requires_grad_()
+    y = F.layer_norm(x + r1 + r2, [d], gamma, beta, 1e-5)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    y0, xs, mean, rstd = TO.layernorm_train(x.detach(), gamma, beta, 1e-5, r1.detach(), r2.detach())
+    assert rel_l2(y0, y.detach()) < 1e-6
+    dx, dg, db = TO.layernorm_train_bwd(xs, dy, mean, rstd, gamma)
+    assert rel_l2(dx, x.grad) < 1e-5 and rel_l2(dx, r2.grad) < 1e-5
+    assert rel_l2(dg, gamma.grad) < 1e-5 and rel_l2(db, beta.grad) < 1e-5
+    a, b = torch.randn(4, 7, generator=g, requires_grad=True), torch.randn(4, 7, generator=g, requires_grad=True)
+    h = a * F.silu(b)
+    dh = torch.randn(h.shape, generator=g)
+    h.backward(dh)
+    assert rel_l2(TO.swiglu(a.detach(), b.detach()), h.detach()) < 1e-6
+    da, dbb = TO.swiglu_bwd(a.detach(), b.detach(), dh)
+    assert rel_l2(da, a.grad) < 1e-6 and rel_l2(dbb, b.grad) < 1e-6
+    tabs = [torch.randn(m, 6, generator=g, requires_grad=True) for m in (11, 13, 17)]
+    tok = torch.randint(0, 5000, (3, 9), generator=g)
+    e = sum(t[tok % t.shape[0]] for t in tabs)
+    de = torch.randn(e.shape, generator=g)
+    e.backward(de)
+    assert rel_l2(TO.embed3(tok, tabs, torch.float32), e.detach()) < 1e-6
+    for got, t in zip(TO.embed3_bwd(tok, de, (11, 13, 17)), tabs):
+        assert rel_l2(got, t.grad) < 1e-6
+
+
+@pytest.mark.parametrize("lt,ls,masked", [(5, 5, False), (7, 9, True)])
+def test_attention_backward_matches_sdpa_autograd(lt, ls, masked):
+    g = torch.Generator().manual_seed(lt)
+    b, heads, hd = 2, 3, 8
+    q = torch.randn(b, lt, heads * hd, generator=g, requires_grad=True)
+    k = torch.randn(b, ls, heads * hd, generator=g, requires_grad=True)
+    v = torch.randn(b, ls, heads * hd, generator=g, requires_grad=True)
+    mask = None
+    if masked:
+        mask = torch.zeros(b, ls)
+        mask[0, 6:] = float("-inf")
+        mask[1, 3:] = float("-inf")
+    sp = lambda t, l: t.view(b, l, heads, hd).transpose(1, 2)
+    o = F.scaled_dot_product_attention(sp(q, lt), sp(k, ls), sp(v, ls), None if mask is None else mask[:, None, None, :])
+    o = o.transpose(1, 2).reshape(b, lt, heads * hd)
+    do = torch.randn(o.shape, generator=g)
+    o.backward(do)
+    assert rel_l2(TO.attention(q.detach(), k.detach(), v.detach(), heads, mask), o.detach()) < 1e-6
+    dq, dk, dv = TO.attention_bwd(q.detach(), k.detach(), v.detach(), do, heads, mask)
+    assert rel_l2(dq, q.grad) < 1e-5 and rel_l2(dk, k.grad) < 1e-5 and rel_l2(dv, v.grad) < 1e-5
+
+
+TF_DIMS = dict(enc_input_dim=106, embed_dim=64, head_num=4, enc_block_num=2, dec_block_num=2, max_enc_seq_len=24,
+               max_dec_seq_len=24)
+
+
+def check_gradients_against_golden(gold, params, rel_tol):
+    """Every parameter gradient vs the float64 reference fingerprints (L2 norm, +-1-probe dot product), tolerance =
+    rel_tol * norm + 4 x the reference's own fp32 noise for that tensor; parameters the reference leaves without a gradient
+    (norm -1) must have none here either."""
+    names = [str(n) for n in gold["grad_names"]]
+    assert set(names) == set(params)
+    bad = []
+    for i, n in enumerate(names):
+        g = params[n].grad
+        ref_norm, ref_dot, noise = float(gold["grad_norm"][i]), float(gold["grad_dot"][i]), float(gold["grad_fp32_err"][i])
+        if ref_norm < 0:
+            if g is not None and float(g.abs().max()) != 0.0:
+                bad.append((n, "reference has no gradient"))
+            continue
+        if g is None:
+            bad.append((n, "missing"))
+            continue
+        g = g.double().cpu()
+        tol = rel_tol * ref_norm + 4.0 * noise + 1e-9
+        e_norm = abs(float(g.norm()) - ref_norm)
+        e_dot = abs(float((g * torch.from_numpy(synthetic_probe(g.shape, i))).sum()) - ref_dot)
+        if e_norm > tol or e_dot > 8.0 * tol:
+            bad.append((n, e_norm, e_dot, tol))
+    assert not bad, (len(bad), bad[:10])
+    for k in [k for k in gold.files if k.startswith("full/")]:
+        i = names.index(k[5:])
+        tol = rel_tol + 4.0 * float(gold["grad_fp32_err"][i]) / float(gold["grad_norm"][i])
+        assert rel_l2(params[k[5:]].grad.cpu(), gold[k]) < tol, (k, tol)
+
+
+def test_transformer_train_graph_matches_reference_golden(oracle_kernels):
+    """Transformer.forward in train mode + backward through train_ops.py with oracle kernels == the unmodified reference in
+    float64 (tests/golden/train_transformer_seed0.npz): logits and all 96 parameter gradients (incl. the learnable position
+    tables and the three residue embeddings); pos_emb_k of the self-attention layers gets no gradient on either side."""
+    from findtextcenternet_b200 import synthetic
+    from findtextcenternet_b200.models.transformer import Transformer
+    p = os.path.join(GOLDEN, "train_transformer_seed0.npz")
+    if not os.path.exists(p):
+        pytest.skip("golden missing (oracle/make_golden_train.py transformer)")
+    gold = np.load(p)
+    model = Transformer(**TF_DIMS, dropout=0.0)
+    model.load_state_dict(synthetic.transformer_state_dict(0, **TF_DIMS))
+    model.set_precision("fp32").train()
+    outs = model(torch.from_numpy(gold["enc"]), torch.from_numpy(gold["dec"]))
+    for i in range(3):
+        assert rel_l2(outs[i].detach(), gold[f"out{i}"]) < 1e-5
+    sum((o * torch.from_numpy(gold[f"w{i}"])).sum() for i, o in enumerate(outs)).backward()
+    check_gradients_against_golden(gold, dict(model.named_parameters()), 1e-4)

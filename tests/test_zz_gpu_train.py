@@ -263,3 +263,106 @@ def test_train1_step_decreases_the_loss():
     assert all(np.isfinite(losses)), losses
     assert losses[-1] < losses[0], losses
     assert all(not torch.equal(a, p.detach()) for a, p in zip(before, list(model.parameters())[:50]))
+
+
+# ---- Transformer train step (train3.py) ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt,tol", DTYPES)
+@pytest.mark.parametrize("rows,d", [(7, 64), (300, 512), (1000, 768)])
+def test_layernorm_train_fwd_bwd(dt, tol, rows, d):
+    from findtextcenternet_b200 import _ops
+    x, r1, r2 = (rnd(rows, d, seed=s).to(dt) for s in (1, 2, 3))
+    gamma, beta = rnd(d, seed=4) + 1.0, rnd(d, seed=5)
+    dy = rnd(rows, d, seed=6).to(dt)
+    for res in ((None, None), (r1, None), (r1, r2)):
+        a1, a2 = (None if r is None else dev(r) for r in res)
+        y, xs, mean, rstd = _ops.layernorm_train(dev(x), dev(gamma), dev(beta), 1e-5, a1, a2)
+        y0, xs0, mean0, rstd0 = TO.layernorm_train(x, gamma, beta, 1e-5, res[0], res[1])
+        assert rel_l2(y.float().cpu(), y0.float()) < tol and rel_l2(xs.float().cpu(), xs0.float()) < tol
+        assert rel_l2(mean.cpu(), mean0) < 1e-4 + tol and rel_l2(rstd.cpu(), rstd0) < 1e-4 + tol
+        dx, dg, db = _ops.layernorm_train_bwd(dev(xs0), dev(dy), dev(mean0), dev(rstd0), dev(gamma))
+        dx0, dg0, db0 = TO.layernorm_train_bwd(xs0, dy, mean0, rstd0, gamma)
+        assert rel_l2(dx.float().cpu(), dx0.float()) < max(tol, 1e-4)
+        assert rel_l2(dg.cpu(), dg0) < 1e-4 and rel_l2(db.cpu(), db0) < 1e-4
+
+
+@pytest.mark.parametrize("dt,tol", DTYPES)
+def test_swiglu_and_embed3(dt, tol):
+    from findtextcenternet_b200 import _ops
+    a, b, dh = (rnd(37, 130, seed=s).to(dt) for s in (1, 2, 3))
+    assert rel_l2(_ops.swiglu(dev(a), dev(b)).float().cpu(), TO.swiglu(a, b).float()) < tol
+    da, db = _ops.swiglu_bwd(dev(a), dev(b), dev(dh))
+    da0, db0 = TO.swiglu_bwd(a, b, dh)
+    assert rel_l2(da.float().cpu(), da0.float()) < tol and rel_l2(db.float().cpu(), db0.float()) < tol
+    tabs = [rnd(m, 64, seed=10 + m) for m in (1091, 1093, 1097)]
+    tok = torch.randint(0, 0x3FFFF, (5, 33), generator=torch.Generator().manual_seed(7))
+    e = _ops.embed3(dev(tok), [dev(t) for t in tabs], dt)
+    assert rel_l2(e.float().cpu(), TO.embed3(tok, tabs, dt).float()) < tol
+    de = rnd(5, 33, 64, seed=8).to(dt)
+    for got, ref in zip(_ops.embed3_bwd(dev(tok), dev(de), (1091, 1093, 1097)), TO.embed3_bwd(tok, de, (1091, 1093, 1097))):
+        assert rel_l2(got.cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("dt,tol", DTYPES)
+@pytest.mark.parametrize("b,heads,hd,lt,ls,masked", [(2, 3, 16, 5, 5, False), (2, 4, 32, 16, 24, True), (3, 12, 64, 40, 100, True),
+                                                     (1, 2, 64, 70, 400, True)])
+def test_attention_backward(dt, tol, b, heads, hd, lt, ls, masked):
+    from findtextcenternet_b200 import _ops
+    d = heads * hd
+    q, do = rnd(b, lt, d, seed=1).to(dt), rnd(b, lt, d, seed=4).to(dt)
+    k, v = rnd(b, ls, d, seed=2).to(dt), rnd(b, ls, d, seed=3).to(dt)
+    mask = None
+    if masked:
+        mask = torch.zeros(b, ls)
+        for i in range(b):
+            mask[i, ls - 1 - 3 * i - ls // 4:] = float("-inf")
+    o = _ops.attention(dev(q), dev(k), dev(v), heads, None if mask is None else dev(mask))
+    assert rel_l2(o.float().cpu(), TO.attention(q.float(), k.float(), v.float(), heads, mask)) < max(tol, 1e-4)
+    got = _ops.attention_bwd(dev(q), dev(k), dev(v), dev(do), heads, None if mask is None else dev(mask))
+    ref = TO.attention_bwd(q.float(), k.float(), v.float(), do.float(), heads, mask)
+    for g, r in zip(got, ref):
+        assert rel_l2(g.cpu(), r) < 1e-4
+
+
+def _transformer(prec):
+    from findtextcenternet_b200 import synthetic
+    from findtextcenternet_b200.models.transformer import Transformer
+    from test_train_oracle import TF_DIMS
+    model = Transformer(**TF_DIMS, dropout=0.0)
+    model.load_state_dict(synthetic.transformer_state_dict(0, **TF_DIMS))
+    return model.set_precision(prec).cuda().train()
+
+
+def test_transformer_train_step_fp32_matches_reference_golden():
+    """train3.py:132-137 shape of work on the CUDA kernels: logits to 1e-4 and all 96 parameter gradients against the float64
+    run of the unmodified reference."""
+    from test_train_oracle import check_gradients_against_golden
+    gold = np.load(os.path.join(GOLDEN, "train_transformer_seed0.npz"))
+    model = _transformer("fp32")
+    outs = model(torch.from_numpy(gold["enc"]).cuda(), torch.from_numpy(gold["dec"]).cuda())
+    for i in range(3):
+        assert rel_l2(outs[i].detach().cpu(), gold[f"out{i}"]) < 1e-4
+    sum((o * torch.from_numpy(gold[f"w{i}"]).cuda()).sum() for i, o in enumerate(outs)).backward()
+    check_gradients_against_golden(gold, dict(model.named_parameters()), 1e-3)
+
+
+def test_transformer_train3_step_bf16_and_optimizer():
+    """bf16 storage end to end (tcgen05 linears, mma.sync attention forward, CUDA-core backward pieces): logits near the fp32
+    reference, finite gradients.  Then the train3.py loop body (loss_function3 + RAdamScheduleFree, :132-150) in fp32: the
+    first five RAdam steps are silent (rho_t <= 4, lr 0), after that the loss on the fixed batch goes down."""
+    from findtextcenternet_b200.loss_func import loss_function3
+    from findtextcenternet_b200.models.radam_schedulefree import RAdamScheduleFree
+    gold = np.load(os.path.join(GOLDEN, "train_transformer_seed0.npz"))
+    enc, dec = torch.from_numpy(gold["enc"]).cuda(), torch.from_numpy(gold["dec"]).cuda()
+    label = torch.randint(0, 0x3FFFF, dec.shape, generator=torch.Generator().manual_seed(5)).cuda()
+    model = _transformer("bf16")
+    outs = model(enc, dec)
+    assert rel_l2(outs[0].detach().cpu(), gold["out0"]) < 0.1
+    loss_function3(outs, label, dec == 3)["loss"].backward()
+    assert all(p.grad is None or bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+    assert sum(p.grad is not None for p in model.parameters()) >= 90
+    model = _transformer("fp32")
+    opt = RAdamScheduleFree([p for p in model.parameters() if p.requires_grad], lr=1e-2)
+    opt.train()
+    from findtextcenternet_b200 import train
+    losses = [float(train.train3_step(model, opt, enc, dec, label)[0]) for _ in range(12)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0] - 1e-4, losses
