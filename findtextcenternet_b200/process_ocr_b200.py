@@ -43,6 +43,17 @@ def tile_meta(x_i: int, y_i: int, img_w: int, img_h: int, step_ratio: float = 0.
     return [x_i, y_i, x_min, x_max, y_min, y_max]
 
 
+def page_tiles(im0: np.ndarray, step_ratio: float = 0.6):
+    """The tiling of ``call_OCR`` (process_ocr_base.py:62-76): white-pad the RGB page so that 768x768 windows at stride
+    int(768 * step_ratio) cover it, return (padded uint8 page, [(offset_x, offset_y), ...] in the reference's row-major order)."""
+    stepx, stepy = int(arch.WIDTH * step_ratio), int(arch.HEIGHT * step_ratio)
+    padx = max(0, (arch.WIDTH - im0.shape[1]) % stepx, arch.WIDTH - im0.shape[1])
+    pady = max(0, (arch.HEIGHT - im0.shape[0]) % stepy, arch.HEIGHT - im0.shape[0])
+    im0 = np.pad(im0, [[0, pady], [0, padx], [0, 0]], "constant", constant_values=255)
+    offsets = [(x, y) for y in range(0, im0.shape[0] - arch.HEIGHT + 1, stepy) for x in range(0, im0.shape[1] - arch.WIDTH + 1, stepx)]
+    return im0, offsets
+
+
 class OCR_b200_Processer(_Base):
     def __init__(self, model_size="xl", precision: Optional[str] = None, device: Optional[torch.device] = None,
                  detector_state_dict=None, transformer_state_dict=None, transformer_config=None):
@@ -121,3 +132,30 @@ class OCR_b200_Processer(_Base):
             h.copy_(d, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return tuple(host)
+
+    def detect_page(self, im0: np.ndarray, max_peaks: int = 1024, tile_batch: int = 32):
+        """One page (uint8 RGB [H,W,3]) -> (locations float32 [n,9], glyphfeatures float32 [n,100]): every tile of the
+        reference's tiling (``page_tiles``) through ``detect_tiles`` in batches of ``tile_batch``, peaks concatenated in the
+        reference's order (tile by tile, descending score inside a tile; process_ocr_base.py:487-538).  The page-map outputs of
+        ``run_detector`` (textline / separator maps for ``linedetect``) still come from ``call_detector`` per tile."""
+        page, offsets = page_tiles(im0, self.step_ratio)
+        locs, feats = [], []
+        for i in range(0, len(offsets), tile_batch):
+            offs = offsets[i:i + tile_batch]
+            tiles = torch.empty(len(offs), arch.HEIGHT, arch.WIDTH, 3, dtype=torch.float32).pin_memory()
+            for j, (x, y) in enumerate(offs):
+                tiles[j] = torch.from_numpy(page[y:y + arch.HEIGHT, x:x + arch.WIDTH].astype(np.float32))
+            count, loc, gfeat = self.detect_tiles(tiles, offs, page.shape[1], page.shape[0], max_peaks)
+            for j in range(len(offs)):
+                n = int(count[j])
+                locs.append(loc[j, :n].clone())
+                feats.append(gfeat[j, :n].clone())
+        return torch.cat(locs).numpy(), torch.cat(feats).numpy()
+
+    def call_transformer_batch(self, encoder_inputs):
+        """All feature chunks of a page (or of many pages) in ONE predictor call: float32 [N, max_encoderlen, 106] ->
+        int64 [N, max_decoderlen] (the reference decodes chunk by chunk at batch 1, process_ocr_base.py:235)."""
+        if self.transformer is None:
+            self._load_transformer()
+        x = torch.from_numpy(np.ascontiguousarray(encoder_inputs, dtype=np.float32)).to(self.device)
+        return self.transformer(x).cpu().numpy()

@@ -150,3 +150,24 @@ def test_gloo_world2_sharding_and_gradient_allreduce(tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") >= 2   # the two ranks interleave their prints
+
+
+@pytest.mark.parametrize("h,w", [(640, 533), (768, 768), (769, 1000), (2048, 2048), (300, 2000)])
+def test_page_tiles_match_the_reference_tiling(h, w):
+    """process_ocr_base.py:62-76 restated line by line: pad amounts, padded size, tile offsets and their order."""
+    from findtextcenternet_b200.process_ocr_b200 import page_tiles
+    width = height = 768
+    stepx = stepy = int(768 * 0.6)
+    im0 = np.full((h, w, 3), 7, dtype=np.uint8)
+    padx = max(0, (width - im0.shape[1]) % stepx, width - im0.shape[1])
+    pady = max(0, (height - im0.shape[0]) % stepy, height - im0.shape[0])
+    ref = np.pad(im0, [[0, pady], [0, padx], [0, 0]], "constant", constant_values=((255, 255), (255, 255), (255, 255)))
+    ref_offsets = []
+    for y in range(0, ref.shape[0] - height + 1, stepy):
+        for x in range(0, ref.shape[1] - width + 1, stepx):
+            ref_offsets.append((x, y))
+    page, offsets = page_tiles(im0)
+    assert page.shape == ref.shape and np.array_equal(page, ref)
+    assert offsets == ref_offsets
+    if (h, w) == (2048, 2048):
+        assert page.shape[:2] == (2148, 2148) and len(offsets) == 16      # SURVEY.md 8d config 5

@@ -366,3 +366,23 @@ def test_transformer_train3_step_bf16_and_optimizer():
     from findtextcenternet_b200 import train
     losses = [float(train.train3_step(model, opt, enc, dec, label)[0]) for _ in range(12)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0] - 1e-4, losses
+
+
+def test_detect_page_equals_tile_by_tile_decode():
+    """OCR_b200_Processer.detect_page (BASELINE.json configs[4] host path: reference tiling -> batched detector + device peak
+    decode) returns exactly the concatenation of per-tile detect_tiles calls."""
+    from findtextcenternet_b200 import synthetic
+    from findtextcenternet_b200.process_ocr_b200 import OCR_b200_Processer, page_tiles
+    proc = OCR_b200_Processer(detector_state_dict=synthetic.detector_state_dict(0))
+    rng = np.random.default_rng(0)
+    im = (rng.random((900, 1000, 3)) * 255).astype(np.uint8)
+    loc, feat = proc.detect_page(im, tile_batch=3)
+    page, offsets = page_tiles(im)
+    assert len(offsets) == 4 and loc.shape[1] == 9 and feat.shape == (loc.shape[0], 100)
+    ref = []
+    for x, y in offsets:
+        tile = torch.from_numpy(page[y:y + 768, x:x + 768].astype(np.float32))[None]
+        c, l, _ = proc.detect_tiles(tile, [(x, y)], page.shape[1], page.shape[0])
+        ref.append(l[0, :int(c[0])].clone())
+    ref = torch.cat(ref).numpy()
+    assert ref.shape == loc.shape and np.allclose(ref, loc, rtol=1e-3, atol=1e-3)
