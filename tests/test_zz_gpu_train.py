@@ -373,7 +373,8 @@ def test_detect_page_equals_tile_by_tile_decode():
     decode) returns exactly the concatenation of per-tile detect_tiles calls."""
     from findtextcenternet_b200 import synthetic
     from findtextcenternet_b200.process_ocr_b200 import OCR_b200_Processer, page_tiles
-    proc = OCR_b200_Processer(detector_state_dict=synthetic.detector_state_dict(0))
+    # fp32 parity path: per-pixel arithmetic does not depend on the batch size, so the comparison is exact up to rounding
+    proc = OCR_b200_Processer(detector_state_dict=synthetic.detector_state_dict(0), precision="fp32")
     rng = np.random.default_rng(0)
     im = (rng.random((900, 1000, 3)) * 255).astype(np.uint8)
     loc, feat = proc.detect_page(im, tile_batch=3)
