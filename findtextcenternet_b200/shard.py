@@ -42,20 +42,22 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int 
     Returns the number of all-reduce calls issued.  262 M fp32 gradients of the detector = 1.05 GB = 16 buckets."""
     world = dist.get_world_size(group)
     grads = [p.grad for p in reversed(list(params)) if p.grad is not None]
-    calls, i = 0, 0
+    pending, i = [], 0
     while i < len(grads):
         bucket, size = [], 0
-        dtype, device = grads[i].dtype, grads[i].device
+        dtype = grads[i].dtype
         while i < len(grads) and grads[i].dtype == dtype and (size == 0 or size + grads[i].numel() * grads[i].element_size() <= bucket_bytes):
             bucket.append(grads[i])
             size += grads[i].numel() * grads[i].element_size()
             i += 1
         flat = torch.cat([g.reshape(-1) for g in bucket])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        # asynchronous: bucket k's all-reduce runs (NCCL stream / gloo thread) while bucket k+1 is being flattened
+        pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, bucket))
+    for work, flat, bucket in pending:
+        work.wait()
         flat.div_(world)
         off = 0
         for g in bucket:
             g.copy_(flat[off: off + g.numel()].view_as(g))
             off += g.numel()
-        calls += 1
-    return calls
+    return len(pending)

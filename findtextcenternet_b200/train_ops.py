@@ -27,6 +27,12 @@ BN_MOMENTUM = 0.1              # nn.BatchNorm2d / BatchNorm1d default; torchvisi
 STOCHASTIC_DEPTH_PROB = 0.2    # torchvision EfficientNet.__init__ default (the reference does not override it)
 
 
+def _need_cuda(t: Tensor, what: str) -> None:
+    """The product path has no CPU route (the CPU graph test swaps this check out together with the kernel namespace)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"findtextcenternet_b200 {what}: input must be a CUDA tensor (no CPU path)")
+
+
 def _backend(x: Tensor, cin: int = 64, cout: int = 64) -> int:
     """tcgen05 for bf16 convolutions with GEMM-sized channel counts; the stem (3 -> 32) and the 1-/2-channel top convs are
     bandwidth-bound slivers and stay on the CUDA-core kernel (as in the inference plan)."""
@@ -273,8 +279,7 @@ def detection_train_forward(det, x: Tensor, sd_prob: float = STOCHASTIC_DEPTH_PR
                             ) -> Tuple[Tensor, Tensor]:
     """CenterNetDetection.forward (models/detector.py:217-230) in train mode: x NCHW in [0,1] -> (heatmap [B,9,H/4,W/4],
     feature [B,100,H/4,W/4]) fp32 NCHW with autograd history."""
-    if not x.is_cuda:
-        raise RuntimeError("findtextcenternet_b200 detector: input must be a CUDA tensor (no CPU path)")
+    _need_cuda(x, "detector")
     dt = torch.float32 if det.precision == "fp32" else torch.bfloat16
     xh = (x.float() * 2 - 1).permute(0, 2, 3, 1).to(dt).contiguous()
     taps = backbone_train_forward(det.backbone.features, xh, det.model_size, sd_prob, sd_noise)
@@ -286,8 +291,7 @@ def detection_train_forward(det, x: Tensor, sd_prob: float = STOCHASTIC_DEPTH_PR
 
 def simple_decoder_train_forward(dec, x: Tensor) -> List[Tensor]:
     """SimpleDecoder.forward (models/detector.py:250-254) in train mode: x [N,100] -> 3 x [N, modulo] fp32."""
-    if not x.is_cuda:
-        raise RuntimeError("findtextcenternet_b200 SimpleDecoder: input must be a CUDA tensor (no CPU path)")
+    _need_cuda(x, "SimpleDecoder")
     from .engine import default_precision
     prec = getattr(dec, "precision", None) or default_precision()
     dt = torch.float32 if prec == "fp32" else torch.bfloat16
@@ -411,8 +415,7 @@ def _ln(x: Tensor, norm, r1=None, r2=None) -> Tensor:
 
 def transformer_train_forward(model, enc_input: Tensor, dec_input: Tensor) -> List[Tensor]:
     """Transformer.forward (models/transformer.py:248-253) in train mode with a tape -> 3 x [B, Ld, m_i] fp32."""
-    if not enc_input.is_cuda:
-        raise RuntimeError("findtextcenternet_b200 transformer: input must be a CUDA tensor (no CPU path)")
+    _need_cuda(enc_input, "transformer")
     if getattr(model, "dropout", 0.0):
         raise NotImplementedError("findtextcenternet_b200: train-mode dropout > 0 is not built (ModelDimensions default is 0.0)")
     dt = torch.float32 if model.precision == "fp32" else torch.bfloat16
