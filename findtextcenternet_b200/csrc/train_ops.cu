@@ -10,6 +10,7 @@
 //   torchvision MBConv / FusedMBConv (efficientnet.py:105-231), SqueezeExcitation (ops/misc.py:225-261),
 //   nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True; models/detector.py:167-186).
 #include <algorithm>
+#include <stdlib.h>
 
 #include "../../include/ftc_b200.h"
 #include "common.cuh"
@@ -217,6 +218,135 @@ __global__ void __launch_bounds__(GT) conv_wgrad_kernel(const T* __restrict__ x,
       atomicAdd(dw + ((int64_t)co * g.Cin + c) * g.k * g.k + tap, acc[i][j]);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient on the warp-level tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate) -- STAGED: compiled in, selected
+// only with FTC_WGRAD_MMA=1 until its first run on hardware (written in a session without GPU time).
+//   dW[co][kk] = sum_m dy[m][co] * xcol[m][kk]: both operands have the reduction index m as their SLOW axis in memory (NHWC),
+//   so the smem tiles keep the global layout ([m][co] and [m][kk], rows padded by 16 B) and BOTH fragments come from
+//   ldmatrix.trans (the same idiom as the V operand of attention_mma_kernel, transformer_ops.cu).
+// CTA = 128 co x 128 kk, 8 warps as 2 (co) x 4 (kk): warp tile 64 x 32 = 4 x 4 mma tiles; 32 pixels per stage, two stages of
+// 16-byte cp.async (im2col gather with zero fill); pixel range split over blockIdx.z, fp32 atomics into OIHW.
+constexpr int WM_T = 128, WM_M = 32, WM_LD = WM_T + 8;
+__global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, ConvGeom g,
+                                                             int64_t M, int64_t m_per_split, float* __restrict__ dw) {
+  __shared__ __align__(16) bf16 sA[2][WM_M][WM_LD];   // dy   [m][co]
+  __shared__ __align__(16) bf16 sB[2][WM_M][WM_LD];   // xcol [m][kk]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int co0 = blockIdx.y * WM_T, kk0 = blockIdx.x * WM_T;
+  const int KK = g.k * g.k * g.Cin;
+  const int64_t ms = (int64_t)blockIdx.z * m_per_split, me = min(M, ms + m_per_split);
+  const int hw = g.Ho * g.Wo;
+  // loader: 512 16-byte pieces per operand per stage; thread handles pieces tid and tid + 256: row = p >> 4, chunk = p & 15
+  int l_row[2], l_co[2], l_ci[2], l_ky[2], l_kx[2];
+  bool l_cok[2], l_kok[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int p = tid + 256 * i;
+    l_row[i] = p >> 4;
+    const int ch = (p & 15) * 8;
+    l_co[i] = co0 + ch;
+    l_cok[i] = l_co[i] < g.Cout;
+    const int kk = kk0 + ch;
+    l_kok[i] = kk < KK;
+    const int tap = l_kok[i] ? kk / g.Cin : 0;
+    l_ci[i] = l_kok[i] ? kk - tap * g.Cin : 0;
+    l_ky[i] = tap / g.k;
+    l_kx[i] = tap - l_ky[i] * g.k;
+  }
+  auto load_stage = [&](int st, int64_t m0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t m = m0 + l_row[i];
+      const bool mok = m < me;
+      const int ch = ((tid + 256 * i) & 15) * 8;
+      {
+        const bool ok = mok && l_cok[i];
+        const bf16* src = ok ? dy + m * g.Cout + l_co[i] : dy;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sA[st][l_row[i]][ch]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+      }
+      {
+        bool ok = mok && l_kok[i];
+        const bf16* src = x;
+        if (ok) {
+          const int bi = (int)(m / hw);
+          const int rem = (int)(m - (int64_t)bi * hw);
+          const int oy = rem / g.Wo, ox = rem - oy * g.Wo;
+          const int iy = oy * g.stride - g.pad + l_ky[i], ix = ox * g.stride - g.pad + l_kx[i];
+          ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+          if (ok) src = x + (((int64_t)bi * g.H + iy) * g.W + ix) * g.Cin + l_ci[i];
+        }
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sB[st][l_row[i]][ch]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int wy = warp >> 2, wx = warp & 3;
+  float acc[4][4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
+  // ldmatrix.trans lane offsets (elements): A: k = (lane & 7) + 8 * (lane >> 4), co block = (lane >> 3) & 1
+  //                                        B: k = (lane & 7) + 8 * ((lane >> 3) & 1), kk block = lane >> 4
+  const int a_k = (lane & 7) + 8 * (lane >> 4), a_c = 8 * ((lane >> 3) & 1);
+  const int b_k = (lane & 7) + 8 * ((lane >> 3) & 1), b_c = 8 * (lane >> 4);
+  const int64_t nst = (me - ms + WM_M - 1) / WM_M;
+  if (nst > 0) load_stage(0, ms);
+  for (int64_t it = 0; it < nst; ++it) {
+    const int st = (int)(it & 1);
+    if (it + 1 < nst) {
+      load_stage(st ^ 1, ms + (it + 1) * WM_M);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < WM_M / 16; ++ks) {
+      uint32_t af[4][4], bfr[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&sA[st][ks * 16 + a_k][wy * 64 + mt * 16 + a_c]);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(af[mt][0]), "=r"(af[mt][1]), "=r"(af[mt][2]), "=r"(af[mt][3]) : "r"(addr) : "memory");
+      }
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&sB[st][ks * 16 + b_k][wx * 32 + np * 16 + b_c]);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(bfr[2 * np][0]), "=r"(bfr[2 * np][1]), "=r"(bfr[2 * np + 1][0]), "=r"(bfr[2 * np + 1][1]) : "r"(addr) : "memory");
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+                       : "r"(af[mt][0]), "r"(af[mt][1]), "r"(af[mt][2]), "r"(af[mt][3]), "r"(bfr[nt][0]), "r"(bfr[nt][1]));
+    }
+    __syncthreads();
+  }
+  const int gq = lane >> 2, tq = lane & 3;
+  const int kk2 = g.k * g.k;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int co = co0 + wy * 64 + mt * 16 + gq + 8 * (e >> 1);
+        const int kk = kk0 + wx * 32 + nt * 8 + 2 * tq + (e & 1);
+        if (co < g.Cout && kk < KK) {
+          const int tap = kk / g.Cin, c = kk - tap * g.Cin;
+          atomicAdd(dw + ((int64_t)co * g.Cin + c) * kk2 + tap, acc[mt][nt][e]);
+        }
+      }
 }
 
 // dX[b,iy,ix,ci] = sum_{ky,kx,co} dy[b,oy,ox,co] * W[co][ci][ky][kx], oy*s - p + ky = iy, ox*s - p + kx = ix  (+ add)
@@ -919,6 +1049,19 @@ int ftc_train_conv2d_wgrad(const void* x, const void* dy, int dtype, int batch, 
   int64_t mps = (M + splits - 1) / splits;
   mps = (mps + GK - 1) / GK * GK;
   splits = (M + mps - 1) / mps;
+  static const bool use_mma = [] { const char* e = getenv("FTC_WGRAD_MMA"); return e && atoi(e) != 0; }();
+  if (use_mma && dtype == DT_BF16 && cin % 8 == 0 && cout % 8 == 0) {
+    const int tiles2 = ceil_div(KK, WM_T) * ceil_div(cout, WM_T);
+    int64_t sp = std::max<int64_t>(1, std::min<int64_t>((148 * 2 + tiles2 - 1) / tiles2, (M + 255) / 256));
+    sp = std::min<int64_t>(sp, 65535);
+    int64_t per = (M + sp - 1) / sp;
+    per = (per + WM_M - 1) / WM_M * WM_M;
+    sp = (M + per - 1) / per;
+    dim3 grid2(ceil_div(KK, WM_T), ceil_div(cout, WM_T), (unsigned)sp);
+    conv_wgrad_mma_kernel<<<grid2, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), g, M, per, dw_oihw);
+    FTC_POST_LAUNCH();
+    return 0;
+  }
   dim3 grid(ceil_div(KK, GB), ceil_div(cout, GB), (unsigned)splits);
   if (dtype == DT_F32)
     conv_wgrad_kernel<float><<<grid, GT, 0, s>>>(cp<float>(x), cp<float>(dy), g, M, mps, dw_oihw);

@@ -387,3 +387,17 @@ def test_detect_page_equals_tile_by_tile_decode():
         ref.append(l[0, :int(c[0])].clone())
     ref = torch.cat(ref).numpy()
     assert ref.shape == loc.shape and np.allclose(ref, loc, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.skipif(os.environ.get("FTC_WGRAD_MMA") != "1", reason="staged mma.sync weight-gradient kernel: run with FTC_WGRAD_MMA=1")
+@pytest.mark.parametrize("b,h,w,cin,cout,k,stride", [
+    (2, 6, 5, 8, 16, 3, 1), (2, 9, 7, 24, 40, 3, 2), (3, 8, 8, 16, 8, 1, 1), (2, 24, 24, 64, 136, 3, 1), (4, 48, 48, 192, 768, 1, 1),
+    (2, 13, 11, 264, 72, 3, 1)])
+def test_staged_mma_weight_gradient(b, h, w, cin, cout, k, stride):
+    """conv_wgrad_mma_kernel (ldmatrix.trans + mma.sync, FTC_WGRAD_MMA=1) against the oracle: bf16 operands, fp32 accumulation."""
+    from findtextcenternet_b200 import _ops
+    x = rnd(b, h, w, cin, seed=1).to(torch.bfloat16)
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    dy = rnd(b, ho, wo, cout, seed=3).to(torch.bfloat16)
+    dw = _ops.conv2d_wgrad(dev(x), dev(dy), k, stride)
+    assert rel_l2(dw.cpu(), TO.conv2d_wgrad(x.float(), dy.float(), k, stride)) < 2e-5
