@@ -1,7 +1,11 @@
 // Common device/host helpers for the findtextCenterNet B200 (sm_100a) hot path.
 #pragma once
+#ifdef FTC_EMU   // oracle/emu: the plain SIMT kernels compiled for host threads (CPU-side kernel checks, never shipped)
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -81,6 +85,7 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+#ifndef FTC_EMU
 // packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction; the issue-bound epilogues and
 // the depthwise kernel use them to halve their FP instruction count)
 typedef unsigned long long f32x2;
@@ -108,6 +113,8 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+#endif  // FTC_EMU
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(GT) conv_wgrad_kernel(const T* __restrict__ x,
   }
 }
 
+#ifndef FTC_EMU
 // ------------------------------------------------------------------------------------------------
 // Weight gradient on the warp-level tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate) -- STAGED: compiled in, selected
 // only with FTC_WGRAD_MMA=1 until its first run on hardware (written in a session without GPU time).
@@ -348,6 +349,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const bf16* __restr
         }
       }
 }
+
+#endif  // FTC_EMU
 
 // dX[b,iy,ix,ci] = sum_{ky,kx,co} dy[b,oy,ox,co] * W[co][ci][ky][kx], oy*s - p + ky = iy, ox*s - p + kx = ix  (+ add)
 template <typename T>
@@ -1049,6 +1052,7 @@ int ftc_train_conv2d_wgrad(const void* x, const void* dy, int dtype, int batch, 
   int64_t mps = (M + splits - 1) / splits;
   mps = (mps + GK - 1) / GK * GK;
   splits = (M + mps - 1) / mps;
+#ifndef FTC_EMU
   static const bool use_mma = [] { const char* e = getenv("FTC_WGRAD_MMA"); return e && atoi(e) != 0; }();
   if (use_mma && dtype == DT_BF16 && cin % 8 == 0 && cout % 8 == 0) {
     const int tiles2 = ceil_div(KK, WM_T) * ceil_div(cout, WM_T);
@@ -1062,6 +1066,7 @@ int ftc_train_conv2d_wgrad(const void* x, const void* dy, int dtype, int batch, 
     FTC_POST_LAUNCH();
     return 0;
   }
+#endif
   dim3 grid(ceil_div(KK, GB), ceil_div(cout, GB), (unsigned)splits);
   if (dtype == DT_F32)
     conv_wgrad_kernel<float><<<grid, GT, 0, s>>>(cp<float>(x), cp<float>(dy), g, M, mps, dw_oihw);

@@ -1,0 +1,192 @@
+"""CPU: the REAL kernel source of csrc/train_ops.cu / csrc/loss_ops.cu executed on host threads through the CUDA-on-CPU shim
+(oracle/emu: one OS thread per CUDA thread, barriers for __syncthreads / __syncwarp / shuffles) and compared with
+oracle/train_oracle.py.  This checks what a compile cannot: index arithmetic, shared-memory reductions, warp shuffles,
+split / atomic accumulation, launch geometry -- for the kernels that had no GPU run yet as much as for those that had.
+Shapes are tiny (every CUDA thread is an OS thread)."""
+import ctypes as C
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import train_oracle as TO
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+@pytest.fixture(scope="module")
+def emu():
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "emu"))
+    import build_emu
+    lib = C.CDLL(build_emu.build())
+    lib.ftc_last_error.restype = C.c_char_p
+    lib.ftc_train_reduce_scratch_bytes.restype = C.c_size_t
+    lib.ftc_train_reduce_scratch_bytes.argtypes = [C.c_int64, C.c_int]
+    lib.ftc_train_attention_bwd_scratch_bytes.restype = C.c_size_t
+    return lib
+
+
+def P(t):
+    return C.c_void_p(None if t is None else t.data_ptr())
+
+
+def ok(lib, rc):
+    assert rc == 0, lib.ftc_last_error()
+
+
+def rnd(*shape, seed=0, scale=1.0, dt=torch.float32):
+    return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale).to(dt)
+
+
+def scratch(lib, rows, c):
+    return torch.empty(lib.ftc_train_reduce_scratch_bytes(rows, c) // 4)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,c,act", [(37, 5, 1), (600, 70, 2), (9, 130, 0)])
+def test_emu_batchnorm_kernels(emu, dt, rows, c, act):
+    x = (rnd(rows, c, seed=1) * 1.7 + 0.3).to(dt)
+    gamma, beta, res, dy = rnd(c, seed=2), rnd(c, seed=3), rnd(rows, c, seed=4, dt=dt), rnd(rows, c, seed=5, dt=dt)
+    mean, var, sc = torch.empty(c), torch.empty(c), scratch(emu, rows, c)
+    ok(emu, emu.ftc_train_bn_stats(P(x), DT[dt], C.c_int64(rows), c, P(mean), P(var), P(sc), None))
+    m0, v0 = TO.bn_stats(x.float())
+    assert rel_l2(mean, m0) < 1e-5 and rel_l2(var, v0) < 1e-4
+    y = torch.empty_like(x)
+    ok(emu, emu.ftc_train_bn_act(P(x), P(y), DT[dt], C.c_int64(rows), c, P(m0), P(v0), P(gamma), P(beta), C.c_float(1e-3), act, P(res), None))
+    tol = 2e-5 if dt == torch.float32 else 2e-2
+    assert rel_l2(y.float(), TO.bn_act(x.float(), m0, v0, gamma, beta, 1e-3, act, res.float())) < tol
+    dx, dbeta, dgamma = torch.empty_like(x), torch.empty(c), torch.empty(c)
+    ok(emu, emu.ftc_train_bn_act_bwd(P(x), P(dy), P(dx), DT[dt], C.c_int64(rows), c, P(m0), P(v0), P(gamma), P(beta), C.c_float(1e-3), act,
+                                     P(dbeta), P(dgamma), P(sc), None))
+    dx0, dg0, db0 = TO.bn_act_bwd(x.float(), dy.float(), m0, v0, gamma, beta, 1e-3, act)
+    assert rel_l2(dgamma, dg0) < 1e-4 and rel_l2(dbeta, db0) < 1e-4 and rel_l2(dx.float(), dx0) < max(tol, 1e-4)
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout,k,stride", [(2, 6, 5, 8, 16, 3, 1), (1, 7, 6, 3, 70, 3, 2), (2, 4, 4, 72, 5, 1, 1)])
+def test_emu_conv_gradients(emu, b, h, w, cin, cout, k, stride):
+    x, wt = rnd(b, h, w, cin, seed=1), rnd(cout, cin, k, k, seed=2, scale=0.2)
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    dy, add = rnd(b, ho, wo, cout, seed=3), rnd(b, h, w, cin, seed=4)
+    dw = torch.empty(cout, cin, k, k)
+    ok(emu, emu.ftc_train_conv2d_wgrad(P(x), P(dy), 0, b, h, w, cin, cout, k, stride, P(dw), None))
+    assert rel_l2(dw, TO.conv2d_wgrad(x, dy, k, stride)) < 2e-5
+    dx = torch.empty(b, h, w, cin)
+    ok(emu, emu.ftc_train_conv2d_dgrad(P(dy), 0, b, h, w, cin, cout, k, stride, P(wt), P(add), P(dx), None))
+    assert rel_l2(dx, TO.conv2d_dgrad(dy, wt, h, w, stride, add)) < 2e-5
+
+
+@pytest.mark.parametrize("stride,h,w,c", [(1, 5, 4, 40), (2, 7, 6, 9)])
+def test_emu_depthwise_and_se_and_upsample(emu, stride, h, w, c):
+    b = 2
+    x, w9c = rnd(b, h, w, c, seed=1), rnd(9, c, seed=2, scale=0.3)
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    dy = rnd(b, ho, wo, c, seed=3)
+    y, dx, dw = torch.empty(b, ho, wo, c), torch.empty(b, h, w, c), torch.empty(9, c)
+    ok(emu, emu.ftc_train_dwconv3x3(P(x), P(y), 0, b, h, w, c, stride, P(w9c), None))
+    ok(emu, emu.ftc_train_dwconv3x3_dgrad(P(dy), P(dx), 0, b, h, w, c, stride, P(w9c), None))
+    ok(emu, emu.ftc_train_dwconv3x3_wgrad(P(x), P(dy), 0, b, h, w, c, stride, P(dw), None))
+    assert rel_l2(y, TO.dwconv3x3_raw(x, w9c, stride)) < 1e-5 and rel_l2(dx, TO.dwconv3x3_dgrad(dy, w9c, h, w, stride)) < 1e-5
+    assert rel_l2(dw, TO.dwconv3x3_wgrad(x, dy, stride)) < 1e-5
+    # squeeze-excitation pieces on the same tensor
+    s = 3
+    hw = h * w
+    w1, b1, w2, b2 = rnd(s, c, seed=5, scale=0.3), rnd(s, seed=6), rnd(c, s, seed=7, scale=0.5), rnd(c, seed=8)
+    mean = torch.empty(b, c)
+    ok(emu, emu.ftc_train_spatial_sum(P(x), None, 0, b, hw, c, C.c_float(1.0 / hw), P(mean), None))
+    mean0 = TO.spatial_sum(x, None, 1.0 / hw)
+    assert rel_l2(mean, mean0) < 1e-5
+    hid, gate = torch.empty(b, s), torch.empty(b, c)
+    ok(emu, emu.ftc_train_se_fc(P(mean0), b, c, s, P(w1), P(b1), P(w2), P(b2), P(hid), P(gate), None))
+    hid0, gate0 = TO.se_fc_train(mean0, w1, b1, w2, b2)
+    assert rel_l2(hid, hid0) < 1e-5 and rel_l2(gate, gate0) < 1e-5
+    g = rnd(b, h, w, c, seed=9)
+    dgate = torch.empty(b, c)
+    ok(emu, emu.ftc_train_spatial_sum(P(g), P(x), 0, b, hw, c, C.c_float(1.0), P(dgate), None))
+    dgate0 = TO.spatial_sum(g, x, 1.0)
+    assert rel_l2(dgate, dgate0) < 1e-5
+    outs = [torch.empty(b, c), torch.empty(b, s), torch.empty(b, c), torch.empty(s, c), torch.empty(s), torch.empty(c, s), torch.empty(c)]
+    ok(emu, emu.ftc_train_se_fc_bwd(P(dgate0), P(gate0), P(hid0), P(mean0), b, c, s, P(w1), P(w2), *[P(t) for t in outs], None))
+    for got, ref in zip(outs[2:], TO.se_fc_train_bwd(dgate0, gate0, hid0, mean0, w1, w2)):
+        assert rel_l2(got, ref) < 1e-5
+    dxs = torch.empty(b, h, w, c)
+    ok(emu, emu.ftc_train_scale_bc(P(g), P(gate0), P(outs[2]), C.c_float(1.0 / hw), P(dxs), 0, b, hw, c, None))
+    assert rel_l2(dxs, TO.scale_bc(g, gate0, outs[2], 1.0 / hw)) < 1e-5
+    # upsample adjoint
+    du = rnd(b, 2 * h, 2 * w, c, seed=10)
+    dxu = torch.empty(b, h, w, c)
+    ok(emu, emu.ftc_train_upsample2x_bwd(P(du), P(dxu), 0, b, h, w, c, None))
+    assert rel_l2(dxu, TO.upsample2x_bwd(du)) < 1e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_emu_layernorm_swiglu_embed(emu, dt):
+    rows, d = 13, 72
+    x, r1, r2, dy = (rnd(rows, d, seed=s, dt=dt) for s in (1, 2, 3, 6))
+    gamma, beta = rnd(d, seed=4) + 1.0, rnd(d, seed=5)
+    tol = 2e-5 if dt == torch.float32 else 2e-2
+    for res in ((None, None), (r1, None), (r1, r2)):
+        y, xs, mean, rstd = torch.empty_like(x), torch.empty_like(x), torch.empty(rows), torch.empty(rows)
+        has = res[0] is not None
+        ok(emu, emu.ftc_train_layernorm(P(x), P(res[0]), P(res[1]), P(xs) if has else None, P(y), P(mean), P(rstd), DT[dt],
+                                        C.c_int64(rows), d, P(gamma), P(beta), C.c_float(1e-5), None))
+        y0, xs0, mean0, rstd0 = TO.layernorm_train(x, gamma, beta, 1e-5, res[0], res[1])
+        assert rel_l2(y.float(), y0.float()) < tol and rel_l2(mean, mean0) < 1e-4 + tol and rel_l2(rstd, rstd0) < 1e-4 + tol
+        if has:
+            assert rel_l2(xs.float(), xs0.float()) < tol
+        dx, dg, db, sc = torch.empty_like(x), torch.empty(d), torch.empty(d), scratch(emu, rows, d)
+        ok(emu, emu.ftc_train_layernorm_bwd(P(xs0), P(dy), P(dx), P(mean0), P(rstd0), DT[dt], C.c_int64(rows), d, P(gamma), P(dg), P(db),
+                                            P(sc), None))
+        dx0, dg0, db0 = TO.layernorm_train_bwd(xs0, dy, mean0, rstd0, gamma)
+        assert rel_l2(dx.float(), dx0.float()) < max(tol, 1e-4) and rel_l2(dg, dg0) < 1e-4 and rel_l2(db, db0) < 1e-4
+    a, b, dh = (rnd(7, 33, seed=s, dt=dt) for s in (7, 8, 9))
+    h, da, dbb = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+    ok(emu, emu.ftc_train_swiglu(P(a), P(b), P(h), DT[dt], C.c_int64(a.numel()), None))
+    ok(emu, emu.ftc_train_swiglu_bwd(P(a), P(b), P(dh), P(da), P(dbb), DT[dt], C.c_int64(a.numel()), None))
+    da0, db0 = TO.swiglu_bwd(a, b, dh)
+    assert rel_l2(h.float(), TO.swiglu(a, b).float()) < tol and rel_l2(da.float(), da0.float()) < tol and rel_l2(dbb.float(), db0.float()) < tol
+    ms = (11, 13, 17)
+    tabs = [rnd(m, 24, seed=20 + m) for m in ms]
+    tok = torch.randint(0, 5000, (3, 9), generator=torch.Generator().manual_seed(7))
+    e = torch.empty(3, 9, 24, dtype=dt)
+    ok(emu, emu.ftc_train_embed3(P(tok), P(tabs[0]), P(tabs[1]), P(tabs[2]), *ms, P(e), DT[dt], C.c_int64(27), 24, None))
+    assert rel_l2(e.float(), TO.embed3(tok, tabs, dt).float()) < tol
+    de = rnd(3, 9, 24, seed=11, dt=dt)
+    dts = [torch.empty(m, 24) for m in ms]
+    ok(emu, emu.ftc_train_embed3_bwd(P(tok), P(de), DT[dt], C.c_int64(27), 24, *ms, *[P(t) for t in dts], None))
+    for got, ref in zip(dts, TO.embed3_bwd(tok, de, ms)):
+        assert rel_l2(got, ref) < 1e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("b,heads,hd,lt,ls,masked", [(1, 2, 16, 5, 5, False), (2, 2, 32, 6, 37, True)])
+def test_emu_attention_backward(emu, dt, b, heads, hd, lt, ls, masked):
+    d = heads * hd
+    q, do = rnd(b, lt, d, seed=1, dt=dt), rnd(b, lt, d, seed=4, dt=dt)
+    k, v = rnd(b, ls, d, seed=2, dt=dt), rnd(b, ls, d, seed=3, dt=dt)
+    mask = None
+    if masked:
+        mask = torch.zeros(b, ls)
+        mask[0, 30:] = float("-inf")
+        mask[1, 9:] = float("-inf")
+    dq, dk, dv = torch.empty(b, lt, d), torch.empty(b, ls, d), torch.empty(b, ls, d)
+    sc = torch.empty(emu.ftc_train_attention_bwd_scratch_bytes(b, heads, lt, ls) // 4)
+    ok(emu, emu.ftc_train_attention_bwd(P(q), P(k), P(v), P(mask), P(do), P(dq), P(dk), P(dv), P(sc), DT[dt], b, heads, hd, lt, ls, None))
+    for got, ref in zip((dq, dk, dv), TO.attention_bwd(q.float(), k.float(), v.float(), do.float(), heads, mask)):
+        assert rel_l2(got, ref) < 1e-4
+
+
+def test_emu_ce_rows_grad(emu):
+    rows, ms = 9, (1091, 1093, 1097)
+    ls = [rnd(rows, m, seed=m) for m in ms]
+    tgt = torch.randint(0, 0x3FFFF, (rows,), generator=torch.Generator().manual_seed(1))
+    wgt = torch.rand(rows, generator=torch.Generator().manual_seed(2))
+    sel = (torch.rand(rows, generator=torch.Generator().manual_seed(3)) < 0.7).to(torch.uint8)
+    coef = torch.tensor([0.37])
+    gs = [torch.empty_like(l) for l in ls]
+    ok(emu, emu.ftc_ce_rows_grad(P(ls[0]), P(ls[1]), P(ls[2]), *ms, *ms, P(tgt), P(wgt), P(sel), rows, P(coef), *[P(g) for g in gs], None))
+    for l, m, g in zip(ls, ms, gs):
+        ref = 0.37 * (wgt * sel)[:, None] * (torch.softmax(l, -1) - torch.nn.functional.one_hot(tgt % m, m).float())
+        assert rel_l2(g, ref) < 1e-5
