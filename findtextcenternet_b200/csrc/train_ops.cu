@@ -220,7 +220,6 @@ __global__ void __launch_bounds__(GT) conv_wgrad_kernel(const T* __restrict__ x,
   }
 }
 
-#ifndef FTC_EMU
 // ------------------------------------------------------------------------------------------------
 // Weight gradient on the warp-level tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate) -- STAGED: compiled in, selected
 // only with FTC_WGRAD_MMA=1 until its first run on hardware (written in a session without GPU time).
@@ -229,6 +228,26 @@ __global__ void __launch_bounds__(GT) conv_wgrad_kernel(const T* __restrict__ x,
 //   ldmatrix.trans (the same idiom as the V operand of attention_mma_kernel, transformer_ops.cu).
 // CTA = 128 co x 128 kk, 8 warps as 2 (co) x 4 (kk): warp tile 64 x 32 = 4 x 4 mma tiles; 32 pixels per stage, two stages of
 // 16-byte cp.async (im2col gather with zero fill); pixel range split over blockIdx.z, fp32 atomics into OIHW.
+// warp-level tensor-core primitives: PTX on the device; oracle/emu/cuda_emu.h provides host-thread versions with the PTX ISA's
+// documented fragment layouts (same names), so the kernel below also runs under the CPU emulation
+#ifndef FTC_EMU
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {   // 16 bytes, zero fill if !valid
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(valid ? 16u : 0u) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+#endif
+
 constexpr int WM_T = 128, WM_M = 32, WM_LD = WM_T + 8;
 __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, ConvGeom g,
                                                              int64_t M, int64_t m_per_split, float* __restrict__ dw) {
@@ -265,8 +284,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const bf16* __restr
       {
         const bool ok = mok && l_cok[i];
         const bf16* src = ok ? dy + m * g.Cout + l_co[i] : dy;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sA[st][l_row[i]][ch]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+        cp_async16(&sA[st][l_row[i]][ch], src, ok);
       }
       {
         bool ok = mok && l_kok[i];
@@ -279,11 +297,10 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const bf16* __restr
           ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
           if (ok) src = x + (((int64_t)bi * g.H + iy) * g.W + ix) * g.Cin + l_ci[i];
         }
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sB[st][l_row[i]][ch]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+        cp_async16(&sB[st][l_row[i]][ch], src, ok);
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    cp_async_commit();
   };
   const int wy = warp >> 2, wx = warp & 3;
   float acc[4][4][4];
@@ -303,33 +320,22 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const bf16* __restr
     const int st = (int)(it & 1);
     if (it + 1 < nst) {
       load_stage(st ^ 1, ms + (it + 1) * WM_M);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      cp_async_wait<1>();
     } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      cp_async_wait<0>();
     }
     __syncthreads();
 #pragma unroll
     for (int ks = 0; ks < WM_M / 16; ++ks) {
-      uint32_t af[4][4], bfr[4][2];
+      uint32_t af[4][4], bq[2][4];     // bq[np] = {b0, b1 of n-tile 2np, b0, b1 of n-tile 2np+1}
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
-        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&sA[st][ks * 16 + a_k][wy * 64 + mt * 16 + a_c]);
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(af[mt][0]), "=r"(af[mt][1]), "=r"(af[mt][2]), "=r"(af[mt][3]) : "r"(addr) : "memory");
-      }
+      for (int mt = 0; mt < 4; ++mt) ldmatrix_x4_trans(af[mt], &sA[st][ks * 16 + a_k][wy * 64 + mt * 16 + a_c]);
 #pragma unroll
-      for (int np = 0; np < 2; ++np) {
-        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&sB[st][ks * 16 + b_k][wx * 32 + np * 16 + b_c]);
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(bfr[2 * np][0]), "=r"(bfr[2 * np][1]), "=r"(bfr[2 * np + 1][0]), "=r"(bfr[2 * np + 1][1]) : "r"(addr) : "memory");
-      }
+      for (int np = 0; np < 2; ++np) ldmatrix_x4_trans(bq[np], &sB[st][ks * 16 + b_k][wx * 32 + np * 16 + b_c]);
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                       : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
-                       : "r"(af[mt][0]), "r"(af[mt][1]), "r"(af[mt][2]), "r"(af[mt][3]), "r"(bfr[nt][0]), "r"(bfr[nt][1]));
+        for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[mt][nt], af[mt], bq[nt >> 1][(nt & 1) * 2], bq[nt >> 1][(nt & 1) * 2 + 1]);
     }
     __syncthreads();
   }
@@ -349,8 +355,6 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const bf16* __restr
         }
       }
 }
-
-#endif  // FTC_EMU
 
 // dX[b,iy,ix,ci] = sum_{ky,kx,co} dy[b,oy,ox,co] * W[co][ci][ky][kx], oy*s - p + ky = iy, ox*s - p + kx = ix  (+ add)
 template <typename T>
@@ -1052,7 +1056,6 @@ int ftc_train_conv2d_wgrad(const void* x, const void* dy, int dtype, int batch, 
   int64_t mps = (M + splits - 1) / splits;
   mps = (mps + GK - 1) / GK * GK;
   splits = (M + mps - 1) / mps;
-#ifndef FTC_EMU
   static const bool use_mma = [] { const char* e = getenv("FTC_WGRAD_MMA"); return e && atoi(e) != 0; }();
   if (use_mma && dtype == DT_BF16 && cin % 8 == 0 && cout % 8 == 0) {
     const int tiles2 = ceil_div(KK, WM_T) * ceil_div(cout, WM_T);
@@ -1066,7 +1069,6 @@ int ftc_train_conv2d_wgrad(const void* x, const void* dy, int dtype, int batch, 
     FTC_POST_LAUNCH();
     return 0;
   }
-#endif
   dim3 grid(ceil_div(KK, GB), ceil_div(cout, GB), (unsigned)splits);
   if (dtype == DT_F32)
     conv_wgrad_kernel<float><<<grid, GT, 0, s>>>(cp<float>(x), cp<float>(dy), g, M, mps, dw_oihw);

@@ -24,6 +24,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
         B.bar = std::make_unique<std::barrier<>>(nthr);
         for (int w = 0; w < nwarp; ++w) B.wbar.push_back(std::make_unique<std::barrier<>>(std::min(32, nthr - 32 * w)));
         B.xch.assign(nthr, 0);
+        B.frag.assign((size_t)nthr * 6, 0);
         blk = &B;
         std::vector<std::thread> ths;
         ths.reserve(nthr);

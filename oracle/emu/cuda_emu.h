@@ -25,7 +25,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __grid_constant__
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 
 struct dim3 {
@@ -75,6 +75,7 @@ struct Block {
   std::unique_ptr<std::barrier<>> bar;
   std::vector<std::unique_ptr<std::barrier<>>> wbar;
   std::vector<uint64_t> xch;      // per thread exchange slot
+  std::vector<uint32_t> frag;     // per thread: 4 A + 2 B fragment registers of an emulated mma.sync
 };
 extern thread_local emu_idx t_idx;
 extern thread_local int t_lin;
@@ -105,4 +106,50 @@ template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o) {
 template <typename T> inline T atomicAdd(T* p, T v) {
   std::lock_guard<std::mutex> g(emu::atomic_lock);
   T old = *p; *p = old + v; return old;
+}
+
+// ---- warp-level tensor-core primitives, host-thread versions (fragment layouts as documented in the PTX ISA for
+// ldmatrix .m8n8.x4(.trans).b16 and mma.sync.m16n8k16.row.col bf16) ----
+inline void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  if (valid) memcpy(smem_dst, gmem_src, 16); else memset(smem_dst, 0, 16);
+}
+inline void cp_async_commit() {}
+template <int N> inline void cp_async_wait() {}
+inline void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  // lane 8j + q supplies the address of row q of 8x8 matrix j; with .trans thread i receives, from each matrix,
+  // the pair (M[2*(i%4)][i/4], M[2*(i%4)+1][i/4]) packed low / high
+  const int lane = emu::t_lin & 31, base = emu::t_lin & ~31;
+  emu::blk->xch[emu::t_lin] = (uint64_t)(uintptr_t)smem_row;
+  __syncwarp();
+  for (int j = 0; j < 4; ++j) {
+    const uint16_t* row_lo = (const uint16_t*)(uintptr_t)emu::blk->xch[base + 8 * j + 2 * (lane % 4)];
+    const uint16_t* row_hi = (const uint16_t*)(uintptr_t)emu::blk->xch[base + 8 * j + 2 * (lane % 4) + 1];
+    r[j] = (uint32_t)row_lo[lane / 4] | ((uint32_t)row_hi[lane / 4] << 16);
+  }
+  __syncwarp();
+}
+inline float emu_bf16_bits(uint32_t reg, int half) {
+  uint32_t u = ((reg >> (16 * half)) & 0xffffu) << 16; float f; memcpy(&f, &u, 4); return f;
+}
+inline void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  // A (16x16, row): a0 = (row g, k 2t..2t+1), a1 = (row g+8, same k), a2 = (row g, k 2t+8..), a3 = (row g+8, k 2t+8..)
+  // B (16x8, col):  b0 = (k 2t..2t+1, n g), b1 = (k 2t+8.., n g);  C/D: c0,c1 = (row g, n 2t, 2t+1), c2,c3 = (row g+8, ...)
+  const int lane = emu::t_lin & 31, base = emu::t_lin & ~31;
+  uint32_t* f = emu::blk->frag.data();
+  for (int i = 0; i < 4; ++i) f[(size_t)emu::t_lin * 6 + i] = a[i];
+  f[(size_t)emu::t_lin * 6 + 4] = b0;
+  f[(size_t)emu::t_lin * 6 + 5] = b1;
+  __syncwarp();
+  const int g = lane >> 2, t = lane & 3;
+  for (int e = 0; e < 4; ++e) {
+    const int row = g + 8 * (e >> 1), n = 2 * t + (e & 1);
+    float sum = 0.f;
+    for (int k = 0; k < 16; ++k) {
+      const int la = (row % 8) * 4 + (k % 8) / 2, ra = (row >= 8 ? 1 : 0) + (k >= 8 ? 2 : 0);
+      const int lb = n * 4 + (k % 8) / 2, rb = 4 + (k >= 8 ? 1 : 0);
+      sum += emu_bf16_bits(f[(size_t)(base + la) * 6 + ra], k % 2) * emu_bf16_bits(f[(size_t)(base + lb) * 6 + rb], k % 2);
+    }
+    c[e] += sum;
+  }
+  __syncwarp();
 }

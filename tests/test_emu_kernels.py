@@ -190,3 +190,33 @@ def test_emu_ce_rows_grad(emu):
     for l, m, g in zip(ls, ms, gs):
         ref = 0.37 * (wgt * sel)[:, None] * (torch.softmax(l, -1) - torch.nn.functional.one_hot(tgt % m, m).float())
         assert rel_l2(g, ref) < 1e-5
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout,k,stride", [(2, 6, 5, 8, 16, 3, 1), (1, 9, 7, 24, 40, 3, 2), (3, 5, 4, 16, 8, 1, 1),
+                                                     (1, 4, 5, 136, 200, 1, 1), (1, 6, 6, 16, 136, 3, 1)])
+def test_emu_mma_weight_gradient(emu, monkeypatch, b, h, w, cin, cout, k, stride):
+    """The staged mma.sync weight-gradient kernel (FTC_WGRAD_MMA=1): its tiling, cp.async im2col loader, ldmatrix.trans lane
+    addressing, fragment-to-output mapping and split-pixel accumulation, executed with host versions of the three PTX
+    primitives that follow the PTX ISA fragment layouts."""
+    import subprocess
+    code = f"""
+import ctypes as C, sys, torch
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+from oracle import train_oracle as TO
+lib = C.CDLL({os.path.join(ROOT, 'oracle', '_ref', 'libftc_emu.so')!r})
+g = torch.Generator().manual_seed(1)
+x = torch.randn({b}, {h}, {w}, {cin}, generator=g).to(torch.bfloat16)
+ho, wo = ({h} - 1) // {stride} + 1, ({w} - 1) // {stride} + 1
+dy = torch.randn({b}, ho, wo, {cout}, generator=g).to(torch.bfloat16)
+dw = torch.empty({cout}, {cin}, {k}, {k})
+rc = lib.ftc_train_conv2d_wgrad(C.c_void_p(x.data_ptr()), C.c_void_p(dy.data_ptr()), 1, {b}, {h}, {w}, {cin}, {cout}, {k}, {stride},
+                                C.c_void_p(dw.data_ptr()), None)
+assert rc == 0
+ref = TO.conv2d_wgrad(x.float(), dy.float(), {k}, {stride})
+err = float((dw.double() - ref.double()).norm() / ref.double().norm())
+assert err < 2e-5, err
+print("ok", err)
+"""
+    # the kernel is selected by an environment switch read once per process: run each case in a fresh interpreter
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FTC_WGRAD_MMA="1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
