@@ -220,3 +220,42 @@ print("ok", err)
     # the kernel is selected by an environment switch read once per process: run each case in a fresh interpreter
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FTC_WGRAD_MMA="1"), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_emu_edge_cases(emu):
+    """Degenerate geometry: one row / one pixel / one channel, extents below a tile, zero variance, a single key."""
+    # BatchNorm over a single row: variance 0 -> rstd = 1/sqrt(eps); backward gives dx = 0 (the mean absorbs everything)
+    x, gamma, beta, dy = rnd(1, 3, seed=1), rnd(3, seed=2), rnd(3, seed=3), rnd(1, 3, seed=4)
+    mean, var, sc = torch.empty(3), torch.empty(3), scratch(emu, 1, 3)
+    ok(emu, emu.ftc_train_bn_stats(P(x), 0, C.c_int64(1), 3, P(mean), P(var), P(sc), None))
+    assert torch.allclose(mean, x[0]) and float(var.abs().max()) == 0.0
+    dx, db, dg = torch.empty_like(x), torch.empty(3), torch.empty(3)
+    ok(emu, emu.ftc_train_bn_act_bwd(P(x), P(dy), P(dx), 0, C.c_int64(1), 3, P(mean), P(var), P(gamma), P(beta), C.c_float(1e-3), 0,
+                                     P(db), P(dg), P(sc), None))
+    assert float(dx.abs().max()) < 1e-6 and torch.allclose(db, dy[0]) and float(dg.abs().max()) < 1e-6
+    # 1x1 image, 3x3 conv (only the centre tap sees data), one output channel
+    x, dy = rnd(1, 1, 1, 8, seed=5), rnd(1, 1, 1, 1, seed=6)
+    dw = torch.empty(1, 8, 3, 3)
+    ok(emu, emu.ftc_train_conv2d_wgrad(P(x), P(dy), 0, 1, 1, 1, 8, 1, 3, 1, P(dw), None))
+    ref = torch.zeros(1, 8, 3, 3)
+    ref[0, :, 1, 1] = x[0, 0, 0] * dy[0, 0, 0, 0]
+    assert torch.allclose(dw, ref, atol=1e-6)
+    wt = rnd(1, 8, 3, 3, seed=7)
+    dxx = torch.empty(1, 1, 1, 8)
+    ok(emu, emu.ftc_train_conv2d_dgrad(P(dy), 0, 1, 1, 1, 8, 1, 3, 1, P(wt), None, P(dxx), None))
+    assert torch.allclose(dxx[0, 0, 0], wt[0, :, 1, 1] * dy[0, 0, 0, 0], atol=1e-6)
+    # attention with one query and one key: softmax = 1 -> dq = dk = 0, dv = dout
+    q, k, v, do = (rnd(1, 1, 16, seed=s) for s in (8, 9, 10, 11))
+    dq, dk, dv = torch.empty(1, 1, 16), torch.empty(1, 1, 16), torch.empty(1, 1, 16)
+    sc = torch.empty(emu.ftc_train_attention_bwd_scratch_bytes(1, 1, 1, 1) // 4)
+    ok(emu, emu.ftc_train_attention_bwd(P(q), P(k), P(v), None, P(do), P(dq), P(dk), P(dv), P(sc), 0, 1, 1, 16, 1, 1, None))
+    assert float(dq.abs().max()) < 1e-6 and float(dk.abs().max()) < 1e-6 and torch.allclose(dv, do)
+    # embedding of negative tokens wraps like Python's % (the reference uses torch's %, same convention)
+    tabs = [rnd(m, 8, seed=m) for m in (5, 7, 11)]
+    tok = torch.tensor([[-1, 0, 12]])
+    e = torch.empty(1, 3, 8)
+    ok(emu, emu.ftc_train_embed3(P(tok), P(tabs[0]), P(tabs[1]), P(tabs[2]), 5, 7, 11, P(e), 0, C.c_int64(3), 8, None))
+    assert rel_l2(e, TO.embed3(tok, tabs, torch.float32)) < 1e-6
+    # bad arguments fail loudly instead of launching
+    assert emu.ftc_train_conv2d_wgrad(P(x), P(dy), 0, 1, 1, 1, 8, 1, 5, 1, P(dw), None) != 0 and b"ksize" in emu.ftc_last_error()
+    assert emu.ftc_train_bn_stats(None, 0, C.c_int64(1), 3, P(mean), P(var), P(sc), None) != 0
