@@ -953,6 +953,32 @@ __global__ void __launch_bounds__(128) attn_bwd_cols_kernel(const T* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Page maps of run_detector (process_ocr_base.py:480-520): every tile contributes sigmoid(heatmap channel) inside its
+// validity window (0 outside) and the page keeps the maximum where tiles overlap.  Maps: key (ch 0), textline (ch 3),
+// separator (ch 4), code1/2/4/8 (ch 5-8) of the 9-channel heatmap.  Values are >= 0, so the float maximum is an integer
+// atomicMax on the bit pattern; HBM-bound (7 of 9 channels read once, page written by atomics into L2).
+__global__ void __launch_bounds__(256) page_maps_kernel(const float* __restrict__ heat9, int B, int H, int W,
+                                                        const int* __restrict__ tile_meta, int* __restrict__ page, int PH, int PW,
+                                                        int scale) {
+  const int64_t total = (int64_t)B * 7 * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    int64_t r = i / W;
+    const int y = (int)(r % H); r /= H;
+    const int m = (int)(r % 7);
+    const int b = (int)(r / 7);
+    const int* tm = tile_meta + b * 6;
+    const int py = tm[1] / scale + y, px = tm[0] / scale + x;
+    if (py >= PH || px >= PW) continue;
+    const int ch = m == 0 ? 0 : m + 2;
+    float v = 0.f;
+    if (x >= tm[2] && x < tm[3] && y >= tm[4] && y < tm[5])
+      v = (tanhf(heat9[(((int64_t)b * 9 + ch) * H + y) * W + x] * 0.5f) + 1.0f) * 0.5f;   // util_func.py:14 sigmoid
+    if (v > 0.f) atomicMax(page + ((int64_t)m * PH + py) * PW + px, __float_as_int(v));
+  }
+}
+
 template <typename T> const T* cp(const void* p) { return reinterpret_cast<const T*>(p); }
 template <typename T> T* mp(void* p) { return reinterpret_cast<T*>(p); }
 
@@ -1324,6 +1350,15 @@ int ftc_train_attention_bwd(const void* q, const void* k, const void* v, const f
     FTC_POST_LAUNCH();
     attn_bwd_cols_kernel<bf16><<<gb, 128, 0, s>>>(cp<bf16>(q), cp<bf16>(dout), P, dS, dk, dv, heads, hd, lt, ls, D, scale);
   }
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_page_maps(const float* heat9, int batch, int h, int w, const int* tile_meta, float* page, int page_h4, int page_w4, int scale,
+                  void* stream) {
+  FTC_REQUIRE(heat9 && tile_meta && page && batch > 0 && h > 0 && w > 0 && page_h4 > 0 && page_w4 > 0 && scale > 0, "bad argument");
+  page_maps_kernel<<<ew_grid((int64_t)batch * 7 * h * w), 256, 0, (cudaStream_t)stream>>>(heat9, batch, h, w, tile_meta, (int*)page, page_h4,
+                                                                                         page_w4, scale);
   FTC_POST_LAUNCH();
   return 0;
 }

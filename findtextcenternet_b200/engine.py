@@ -172,6 +172,27 @@ def peak_decode(heat9: torch.Tensor, feat: torch.Tensor, tile_meta: torch.Tensor
     return count, loc, gfeat
 
 
+def page_maps(heat9: torch.Tensor, tile_meta: torch.Tensor, page_h: int, page_w: int, out: Optional[torch.Tensor] = None
+              ) -> torch.Tensor:
+    """The seven page-level maps of run_detector (process_ocr_base.py:480-520) on the device: fp32 [7, page_h/4, page_w/4] =
+    (keymap_all, lines_all, seps_all, code_all[0..3]); per tile sigmoid * validity mask, maximum over overlapping tiles.
+    ``out``: maps of earlier tile batches of the same page to keep merging into."""
+    lib = _lib.load()
+    if not (heat9.is_cuda and tile_meta.is_cuda):
+        raise RuntimeError("page_maps needs CUDA tensors (no CPU path)")
+    b, c, h, w = heat9.shape
+    assert c == 9
+    heat9 = heat9.float().contiguous()
+    tile_meta = tile_meta.to(torch.int32).contiguous()
+    shape = (7, page_h // arch.SCALE, page_w // arch.SCALE)
+    page = out if out is not None else torch.zeros(shape, dtype=torch.float32, device=heat9.device)
+    assert tuple(page.shape) == shape and page.dtype == torch.float32 and page.is_contiguous() and page.device == heat9.device
+    with torch.cuda.device(heat9.device):
+        _lib.check(lib.ftc_page_maps(heat9.data_ptr(), b, h, w, tile_meta.data_ptr(), page.data_ptr(), page.shape[1], page.shape[2],
+                                     arch.SCALE, _stream_ptr(heat9.device)), "ftc_page_maps")
+    return page
+
+
 class TransformerEngine:
     """One ``ftc_transformer`` plan + packed weights (models/transformer.py Encoder + Decoder)."""
 

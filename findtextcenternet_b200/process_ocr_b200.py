@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import arch
-from .engine import peak_decode
+from .engine import page_maps, peak_decode
 
 try:  # running inside a reference checkout
     from process_ocr_base import OCR_Processer as _Base  # type: ignore
@@ -108,7 +108,7 @@ class OCR_b200_Processer(_Base):
 
     # ---- batched device-side path --------------------------------------------------------------------
     def detect_tiles(self, tiles: torch.Tensor, offsets: Sequence[Tuple[int, int]], page_w: int, page_h: int,
-                     max_peaks: int = 1024):
+                     max_peaks: int = 1024, maps: Optional[torch.Tensor] = None):
         """tiles: float32 [B,768,768,3] in 0..255 (host, ideally pinned, or device).  Runs detector + per-tile peak
         compaction/box decode (process_ocr_base.py:487-538) on the device and returns host arrays
         (count int32 [B], locations float32 [B,max_peaks,9], glyphfeatures float32 [B,max_peaks,100]) in pinned buffers that
@@ -120,6 +120,8 @@ class OCR_b200_Processer(_Base):
         with torch.no_grad():
             heat9, feat, _ = eng.forward(x, False, nhwc255=True)
             count, loc, gfeat = peak_decode(heat9, feat, meta, page_w, page_h, self.cut_off, max_peaks)
+            if maps is not None:     # device tensor [7, page_h/4, page_w/4]: merge this batch's tiles into the page maps
+                page_maps(heat9, meta, page_h, page_w, out=maps)
         # results leave through persistent PINNED host buffers (one async copy each, one sync): a pageable .cpu() of the
         # [B, max_peaks, 109] arrays cost more than a millisecond per call
         key = (tuple(count.shape), tuple(loc.shape), tuple(gfeat.shape))
@@ -133,23 +135,28 @@ class OCR_b200_Processer(_Base):
         torch.cuda.current_stream(self.device).synchronize()
         return tuple(host)
 
-    def detect_page(self, im0: np.ndarray, max_peaks: int = 1024, tile_batch: int = 32):
+    def detect_page(self, im0: np.ndarray, max_peaks: int = 1024, tile_batch: int = 32, return_maps: bool = False):
         """One page (uint8 RGB [H,W,3]) -> (locations float32 [n,9], glyphfeatures float32 [n,100]): every tile of the
         reference's tiling (``page_tiles``) through ``detect_tiles`` in batches of ``tile_batch``, peaks concatenated in the
-        reference's order (tile by tile, descending score inside a tile; process_ocr_base.py:487-538).  The page-map outputs of
-        ``run_detector`` (textline / separator maps for ``linedetect``) still come from ``call_detector`` per tile."""
+        reference's order (tile by tile, descending score inside a tile; process_ocr_base.py:487-538).  With ``return_maps``
+        also the page maps of ``run_detector`` merged on the device (``ftc_page_maps``): float32 [7, H/4, W/4] = keymap_all,
+        lines_all, seps_all, code_all[0..3] of the padded page (lines_all / seps_all feed ``linedetect``)."""
         page, offsets = page_tiles(im0, self.step_ratio)
         locs, feats = [], []
+        maps = (torch.zeros(7, page.shape[0] // arch.SCALE, page.shape[1] // arch.SCALE, dtype=torch.float32, device=self.device)
+                if return_maps else None)
         for i in range(0, len(offsets), tile_batch):
             offs = offsets[i:i + tile_batch]
             tiles = torch.empty(len(offs), arch.HEIGHT, arch.WIDTH, 3, dtype=torch.float32).pin_memory()
             for j, (x, y) in enumerate(offs):
                 tiles[j] = torch.from_numpy(page[y:y + arch.HEIGHT, x:x + arch.WIDTH].astype(np.float32))
-            count, loc, gfeat = self.detect_tiles(tiles, offs, page.shape[1], page.shape[0], max_peaks)
+            count, loc, gfeat = self.detect_tiles(tiles, offs, page.shape[1], page.shape[0], max_peaks, maps)
             for j in range(len(offs)):
                 n = int(count[j])
                 locs.append(loc[j, :n].clone())
                 feats.append(gfeat[j, :n].clone())
+        if return_maps:
+            return torch.cat(locs).numpy(), torch.cat(feats).numpy(), maps.cpu().numpy()
         return torch.cat(locs).numpy(), torch.cat(feats).numpy()
 
     def call_transformer_batch(self, encoder_inputs):

@@ -216,3 +216,12 @@ def train1_batch(batch: int, seed: int = 0, size: int = 768, device="cpu", peaks
         labelmap[b, 4] = (torch.rand(hs, hs, generator=g) > 0.9).float()
     out = dict(image=image, labelmap=labelmap, idmap=idmap)
     return {k: v.to(device) for k, v in out.items()}
+
+
+def page_maps_inputs(seed: int, n_tiles: int) -> torch.Tensor:
+    """Seeded 9-channel tile heatmaps [n,9,192,192] (the 10-channel draws of oracle/make_golden_train.py::main_pagemaps minus the
+    peak channel) for the page-map tests."""
+    g = torch.Generator().manual_seed(seed)
+    hq = arch.HEIGHT // arch.SCALE
+    tiles = [torch.randn(1, 10, hq, hq, generator=g).mul_(2.0) for _ in range(n_tiles)]
+    return torch.cat([torch.cat([t[:, :1], t[:, 2:]], dim=1) for t in tiles])

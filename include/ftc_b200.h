@@ -287,6 +287,13 @@ size_t ftc_train_attention_bwd_scratch_bytes(int batch, int heads, int lt, int l
 int ftc_train_attention_bwd(const void* q, const void* k, const void* v, const float* mask, const void* dout, float* dq, float* dk,
                             float* dv, void* scratch, int dtype, int batch, int heads, int hd, int lt, int ls, void* stream);
 
+/* ---- page maps of run_detector (process_ocr_base.py:480-520), on the device: for every tile b (tile_meta as in ftc_peak_decode:
+ * offset_x, offset_y, x_min, x_max, y_min, y_max) v = sigmoid(heat9[b, ch]) inside the validity window, 0 outside, and
+ * page[m][offset_y/scale + y][offset_x/scale + x] = max(page, v) for m = key (ch 0), textline (3), separator (4), code1/2/4/8
+ * (5-8).  page: fp32 [7][page_h4][page_w4], ZEROED by the caller; tiles may overlap (atomic maximum). */
+int ftc_page_maps(const float* heat9, int batch, int h, int w, const int* tile_meta, float* page, int page_h4, int page_w4, int scale,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -205,3 +205,19 @@ def decode_tile(heatmap10: np.ndarray, features: np.ndarray, x_i=0, y_i=0, img_w
     if not locs:
         return np.zeros([0, 9]), np.zeros([0, arch.FEATURE_DIM], dtype=np.float32)
     return np.array(locs), np.array(feats)
+
+
+def page_maps(heat9, offsets, page_w, page_h, step_ratio=0.6):
+    """The seven page maps of run_detector (process_ocr_base.py:480-520) from 9-channel tile heatmaps [B,9,192,192] (numpy):
+    (keymap_all, lines_all, seps_all, code_all[0..3]) stacked [7, page_h//4, page_w//4]."""
+    s = arch.SCALE
+    x_s, y_s = arch.WIDTH // s, arch.HEIGHT // s
+    out = np.zeros([7, page_h // s, page_w // s], dtype=np.float32)
+    chans = [0, 3, 4, 5, 6, 7, 8]       # 9-channel layout: key, w, h, textline, sep, code1, code2, code4, code8
+    for b, (x_i, y_i) in enumerate(offsets):
+        mask = tile_mask(x_i, y_i, page_w, page_h, step_ratio)
+        x_is, y_is = x_i // s, y_i // s
+        for m, ch in enumerate(chans):
+            p = np_sigmoid(heat9[b, ch]) * mask
+            out[m, y_is:y_is + y_s, x_is:x_is + x_s] = np.maximum(p, out[m, y_is:y_is + y_s, x_is:x_is + x_s])
+    return out

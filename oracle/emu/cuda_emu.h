@@ -103,6 +103,11 @@ template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o) {
   T r; memcpy(&r, &other, sizeof(T));
   return r;
 }
+inline int atomicMax(int* p, int v) {
+  std::lock_guard<std::mutex> g(emu::atomic_lock);
+  int old = *p; if (v > old) *p = v; return old;
+}
+inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 template <typename T> inline T atomicAdd(T* p, T v) {
   std::lock_guard<std::mutex> g(emu::atomic_lock);
   T old = *p; *p = old + v; return old;

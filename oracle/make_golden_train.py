@@ -161,8 +161,46 @@ def main_transformer():
           % (np.median(rel), rel.max()))
 
 
+def main_pagemaps():
+    """tests/golden/page_maps_seed0.npz: lines_all / seps_all as returned by the UNMODIFIED reference ``run_detector``
+    (process_ocr_base.py:474-650) for a 900x1000 page whose four tiles get seeded random heatmaps from a stub backend (peak
+    channel at -10 so the greedy box selection has nothing to do); stored with the 9-channel heatmaps that produced them."""
+    from process_ocr_base import OCR_Processer
+    from findtextcenternet_b200.process_ocr_b200 import page_tiles
+    g = torch.Generator().manual_seed(77)
+    page, offsets = page_tiles(np.full((900, 1000, 3), 255, dtype=np.uint8))
+    heat10 = [torch.randn(1, 10, 192, 192, generator=g).mul_(2.0).numpy() for _ in offsets]
+    for h in heat10:
+        h[0, 1] = -10.0
+
+    class Stub(OCR_Processer):
+        def __init__(self):
+            super().__init__()
+            self.n = 0
+
+        def call_detector(self, image_input):
+            h = heat10[self.n]
+            self.n += 1
+            return h, np.zeros((1, 100, 192, 192), dtype=np.float32)
+
+        def call_transformer(self, encoder_input):
+            raise NotImplementedError
+
+    ds = [{"input": None, "offsetx": x, "offsety": y} for x, y in offsets]
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        _, _, lines, seps = Stub().run_detector(ds, page)
+    # the heatmaps are regenerated from the seed by the tests (page_maps_inputs below); the maps are kept at every 3rd pixel
+    path = os.path.join(GOLD, "page_maps_seed0.npz")
+    np.savez_compressed(path, seed=np.array(77), offsets=np.array(offsets), page_hw=np.array(page.shape[:2]),
+                        lines_all_s3=lines[::3, ::3].copy(), seps_all_s3=seps[::3, ::3].copy())
+    print("wrote", path, os.path.getsize(path), "bytes", lines.shape, float(lines.max()))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("pagemaps", "all"):
+        main_pagemaps()
     if what in ("detector", "all"):
         main()
     if what in ("transformer", "all"):

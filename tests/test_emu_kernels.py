@@ -259,3 +259,25 @@ def test_emu_edge_cases(emu):
     # bad arguments fail loudly instead of launching
     assert emu.ftc_train_conv2d_wgrad(P(x), P(dy), 0, 1, 1, 1, 8, 1, 5, 1, P(dw), None) != 0 and b"ksize" in emu.ftc_last_error()
     assert emu.ftc_train_bn_stats(None, 0, C.c_int64(1), 3, P(mean), P(var), P(sc), None) != 0
+
+
+def test_emu_page_maps(emu):
+    """ftc_page_maps (tile sigmoid * validity window, atomic maximum over overlapping tiles) on host threads vs the oracle, on
+    a shrunken geometry (tiles 12x12 at stride 7 on a 19x19 page map) so that every CUDA thread can be an OS thread."""
+    import numpy as np
+    g = torch.Generator().manual_seed(5)
+    h = w = 12
+    offs = [(0, 0), (28, 0), (0, 28), (28, 28)]                # in image pixels (scale 4): 7 map pixels apart
+    heat = torch.randn(4, 9, h, w, generator=g) * 2
+    meta = torch.tensor([[0, 0, 0, 9, 0, 9], [28, 0, 3, 12, 0, 9], [0, 28, 0, 9, 3, 12], [28, 28, 3, 12, 3, 12]], dtype=torch.int32)
+    page = torch.zeros(7, 19, 19)
+    ok(emu, emu.ftc_page_maps(P(heat), 4, h, w, P(meta), P(page), 19, 19, 4, None))
+    ref = np.zeros((7, 19, 19), dtype=np.float32)
+    for b in range(4):
+        ox, oy, x0, x1, y0, y1 = (int(v) for v in meta[b])
+        mask = np.zeros((h, w), dtype=bool)
+        mask[y0:y1, x0:x1] = True
+        for m, ch in enumerate([0, 3, 4, 5, 6, 7, 8]):
+            p = ((np.tanh(heat[b, ch].numpy() / 2) + 1) / 2) * mask
+            ref[m, oy // 4:oy // 4 + h, ox // 4:ox // 4 + w] = np.maximum(p, ref[m, oy // 4:oy // 4 + h, ox // 4:ox // 4 + w])
+    assert np.abs(page.numpy() - ref).max() < 1e-6

@@ -120,3 +120,20 @@ def test_predictor_early_exit_variants(variant, boost, golden_transformer):
     assert np.array_equal(ids.numpy(), golden_transformer[f"tiny_{variant}_pred_ids"])
     if variant == "peaked":
         assert len(trace) == 1   # "[0 early stop]"
+
+
+def test_page_maps_oracle_matches_reference_run_detector():
+    """oracle page_maps == lines_all / seps_all returned by the unmodified reference run_detector (stub backend, 4 tiles)."""
+    import os
+    from conftest import GOLDEN
+    from findtextcenternet_b200 import synthetic
+    from oracle import detector_oracle as DO
+    gold = np.load(os.path.join(GOLDEN, "page_maps_seed0.npz"))
+    offsets = [tuple(int(v) for v in o) for o in gold["offsets"]]
+    ph, pw = (int(v) for v in gold["page_hw"])
+    heat9 = synthetic.page_maps_inputs(int(gold["seed"]), len(offsets)).numpy()
+    maps = DO.page_maps(heat9, offsets, pw, ph)
+    assert maps.shape == (7, ph // 4, pw // 4)
+    assert np.abs(maps[1][::3, ::3] - gold["lines_all_s3"]).max() < 1e-6
+    assert np.abs(maps[2][::3, ::3] - gold["seps_all_s3"]).max() < 1e-6
+    assert maps[1].max() > 0.99 and (maps[1] == 0).sum() == 0          # every page pixel is covered by some tile window

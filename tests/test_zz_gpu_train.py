@@ -377,8 +377,9 @@ def test_detect_page_equals_tile_by_tile_decode():
     proc = OCR_b200_Processer(detector_state_dict=synthetic.detector_state_dict(0), precision="fp32")
     rng = np.random.default_rng(0)
     im = (rng.random((900, 1000, 3)) * 255).astype(np.uint8)
-    loc, feat = proc.detect_page(im, tile_batch=3)
+    loc, feat, maps = proc.detect_page(im, tile_batch=3, return_maps=True)
     page, offsets = page_tiles(im)
+    assert maps.shape == (7, page.shape[0] // 4, page.shape[1] // 4) and maps.min() > 0.0 and maps.max() <= 1.0
     assert len(offsets) == 4 and loc.shape[1] == 9 and feat.shape == (loc.shape[0], 100)
     ref = []
     for x, y in offsets:
@@ -401,3 +402,21 @@ def test_staged_mma_weight_gradient(b, h, w, cin, cout, k, stride):
     dy = rnd(b, ho, wo, cout, seed=3).to(torch.bfloat16)
     dw = _ops.conv2d_wgrad(dev(x), dev(dy), k, stride)
     assert rel_l2(dw.cpu(), TO.conv2d_wgrad(x.float(), dy.float(), k, stride)) < 2e-5
+
+
+def test_page_maps_on_device_match_reference_run_detector():
+    """engine.page_maps (ftc_page_maps) == lines_all / seps_all of the unmodified reference run_detector (golden) and the
+    oracle's seven maps."""
+    from findtextcenternet_b200 import synthetic
+    from findtextcenternet_b200.engine import page_maps
+    from findtextcenternet_b200.process_ocr_b200 import tile_meta
+    from oracle import detector_oracle as DO
+    gold = np.load(os.path.join(GOLDEN, "page_maps_seed0.npz"))
+    offsets = [tuple(int(v) for v in o) for o in gold["offsets"]]
+    ph, pw = (int(v) for v in gold["page_hw"])
+    heat9 = synthetic.page_maps_inputs(int(gold["seed"]), len(offsets))
+    meta = torch.tensor([tile_meta(x, y, pw, ph) for x, y in offsets], dtype=torch.int32)
+    maps = page_maps(heat9.cuda(), meta.cuda(), ph, pw).cpu().numpy()
+    assert np.abs(maps[1][::3, ::3] - gold["lines_all_s3"]).max() < 1e-5
+    assert np.abs(maps[2][::3, ::3] - gold["seps_all_s3"]).max() < 1e-5
+    assert np.abs(maps - DO.page_maps(heat9.numpy(), offsets, pw, ph)).max() < 1e-5
