@@ -379,7 +379,7 @@ def test_detect_page_equals_tile_by_tile_decode():
     im = (rng.random((900, 1000, 3)) * 255).astype(np.uint8)
     loc, feat, maps = proc.detect_page(im, tile_batch=3, return_maps=True)
     page, offsets = page_tiles(im)
-    assert maps.shape == (7, page.shape[0] // 4, page.shape[1] // 4) and maps.min() > 0.0 and maps.max() <= 1.0
+    assert maps.shape == (7, page.shape[0] // 4, page.shape[1] // 4) and maps.min() >= 0.0 and maps.max() <= 1.0 and maps.max() > 0.0
     assert len(offsets) == 4 and loc.shape[1] == 9 and feat.shape == (loc.shape[0], 100)
     ref = []
     for x, y in offsets:
