@@ -21,6 +21,9 @@ cat gpurun_out/r2_train_b*.json
 # 4. configs[4]: 2048x2048 page end to end
 timeout 120 python tools/bench_page.py --pages 3 --chunks 32 > gpurun_out/r2_page.json 2> gpurun_out/r2_page.err
 cat gpurun_out/r2_page.json
+# 4b. train3 step throughput (Transformer backward)
+timeout 120 python tools/bench_train3.py --batch 64 --steps 2 --warmup 1 > gpurun_out/r2_train3.json 2> gpurun_out/r2_train3.err
+cat gpurun_out/r2_train3.json
 # 5. where the train step's time goes: launch list of one B=2 step (profiler numbers are for shares only)
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r2_train_launches.csv \
   python tools/bench_train.py --batch 2 --steps 1 --warmup 0 > gpurun_out/r2_train_ncu.log 2>&1
