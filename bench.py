@@ -271,7 +271,31 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
+    if world == 1 and not args.no_train1:
+        line["train1"] = train1_side_measurement()
     print(json.dumps(line), flush=True)
+
+
+def train1_side_measurement(batch: int = 4, timeout_s: int = 240):
+    """Auxiliary, clearly labelled: the train1 step (BASELINE.json configs[2]: fwd + loss_func + bwd + AdamWScheduleFree) timed by
+    tools/bench_train.py in a CHILD process (its own CUDA context, hard timeout), so that nothing it does can disturb the
+    headline forward numbers above.  First-correct-path kernels (CUDA-core weight gradients) at a small per-GPU batch: a
+    progress marker, not the configs[2] headline (batch 16 per GPU)."""
+    try:
+        import torch
+        torch.cuda.empty_cache()
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_train.py"), "--batch", str(batch), "--steps", "2", "--warmup", "1"]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+        rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not rows:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        d = json.loads(rows[-1])
+        return {"metric": d["metric"], "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "batch_per_gpu": batch,
+                "steps": d["steps"], "warmup": d["warmup"], "dtype": d["dtype"], "gpu_launches": d["gpu_launches"],
+                "losses": d["losses"], "peak_mem_gb": d["peak_mem_gb"],
+                "note": "first correct path (CUDA-core weight gradients, per-call weight packing); child process, CUDA events"}
+    except Exception as e:      # the side measurement must never cost the headline line
+        return {"error": repr(e)[:300]}
 
 
 def main():
@@ -283,6 +307,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16_simt", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train1", action="store_true", help="skip the auxiliary train1-step measurement (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
