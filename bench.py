@@ -273,10 +273,14 @@ def run_ours(args):
     }
     if world == 1 and not args.no_train1:
         line["train1"] = train1_side_measurement()
+        if "error" not in line["train1"]:
+            # same step with the staged mma.sync weight-gradient kernel (off by default until it has run on hardware): its
+            # loss trajectory next to the default path's is the first hardware evidence for or against it
+            line["train1_wgrad_mma_staged"] = train1_side_measurement(env={"FTC_WGRAD_MMA": "1"})
     print(json.dumps(line), flush=True)
 
 
-def train1_side_measurement(batch: int = 4, timeout_s: int = 240):
+def train1_side_measurement(batch: int = 4, timeout_s: int = 200, env=None):
     """Auxiliary, clearly labelled: the train1 step (BASELINE.json configs[2]: fwd + loss_func + bwd + AdamWScheduleFree) timed by
     tools/bench_train.py in a CHILD process (its own CUDA context, hard timeout), so that nothing it does can disturb the
     headline forward numbers above.  First-correct-path kernels (CUDA-core weight gradients) at a small per-GPU batch: a
@@ -285,7 +289,7 @@ def train1_side_measurement(batch: int = 4, timeout_s: int = 240):
         import torch
         torch.cuda.empty_cache()
         cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_train.py"), "--batch", str(batch), "--steps", "2", "--warmup", "1"]
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=dict(os.environ, **(env or {})))
         rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if r.returncode != 0 or not rows:
             return {"error": (r.stderr or r.stdout)[-300:]}
