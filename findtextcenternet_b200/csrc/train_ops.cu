@@ -141,6 +141,115 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ x
   }
 }
 
+// ---- 16-byte-vector versions of the three BatchNorm kernels (C % 8 == 0, every real layer): a thread owns 8 consecutive
+// channels, so its per-channel constants live in registers and every load / store is a full 16-byte piece; the scalar kernels
+// above remain for odd channel counts.  Reduction CTA = 8 chunk lanes (64 channels, one 128-byte line of bf16 per row) x 32
+// row lanes.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) col_reduce_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t rows, int C,
+                                                             int64_t rows_per_chunk, float* __restrict__ part, BnArgs bn) {
+  __shared__ float sm[2][32][RED_CH + 1];
+  const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * RED_CH + ck * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
+  if (c0 < C) {
+    float mean[8], rstd[8], g[8], bt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean[j] = 0.f; rstd[j] = 1.f; g[j] = 1.f; bt[j] = 0.f;
+      if (MODE == 1) { mean[j] = bn.mean[c0 + j]; rstd[j] = rsqrtf(bn.var[c0 + j] + bn.eps); g[j] = bn.gamma[c0 + j]; bt[j] = bn.beta[c0 + j]; }
+    }
+    for (int64_t r = r0 + rl; r < r1; r += 32) {
+      float v[8], d[8];
+      load8(x + r * C + c0, v);
+      if (MODE == 1) load8(dy + r * C + c0, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (MODE == 0) {
+          s0[j] += v[j];
+          s1[j] = fmaf(v[j], v[j], s1[j]);
+        } else {
+          const float xh = (v[j] - mean[j]) * rstd[j];
+          const float dz = d[j] * act_grad(fmaf(g[j], xh, bt[j]), bn.act);
+          s0[j] += dz;
+          s1[j] = fmaf(dz, xh, s1[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sm[0][rl][ck * 8 + j] = s0[j]; sm[1][rl][ck * 8 + j] = s1[j]; }
+  __syncthreads();
+  if (threadIdx.x < 2 * RED_CH) {
+    const int q = threadIdx.x / RED_CH, cl = threadIdx.x % RED_CH;
+    const int c = blockIdx.x * RED_CH + cl;
+    if (c < C) {
+      float a = 0.f;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) a += sm[q][l][cl];
+      part[((int64_t)q * gridDim.y + blockIdx.y) * C + c] = a;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int C, BnArgs bn,
+                                                         const T* __restrict__ residual) {
+  // thread = (chunk lane ck, row lane rl): a warp touches 4 rows x one 64-channel run (full 128-byte lines); grid.y walks the
+  // 64-channel slabs, so a thread's eight (scale, shift) pairs are loop invariants
+  const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * RED_CH + ck * 8;
+  if (c0 >= C) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float rs = rsqrtf(bn.var[c0 + j] + bn.eps);
+    sc[j] = bn.gamma[c0 + j] * rs;
+    sh[j] = bn.beta[c0 + j] - bn.mean[c0 + j] * sc[j];
+  }
+  for (int64_t r = (int64_t)blockIdx.x * 32 + rl; r < rows; r += (int64_t)gridDim.x * 32) {
+    float v[8], res[8];
+    load8(x + r * C + c0, v);
+    if (residual) load8(residual + r * C + c0, res);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = apply_act<true>(fmaf(v[j], sc[j], sh[j]), bn.act);      // gamma * xhat + beta with the mean folded into the shift
+      if (residual) v[j] += res[j];
+    }
+    store8(y + r * C + c0, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+                                                             int64_t rows, int C, float inv_rows, BnArgs bn,
+                                                             const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat) {
+  const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * RED_CH + ck * 8;
+  if (c0 >= C) return;
+  float mean[8], rstd[8], g[8], bt[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mean[j] = bn.mean[c0 + j]; rstd[j] = rsqrtf(bn.var[c0 + j] + bn.eps); g[j] = bn.gamma[c0 + j]; bt[j] = bn.beta[c0 + j];
+    m1[j] = sum_dz[c0 + j] * inv_rows; m2[j] = sum_dz_xhat[c0 + j] * inv_rows;
+  }
+  for (int64_t r = (int64_t)blockIdx.x * 32 + rl; r < rows; r += (int64_t)gridDim.x * 32) {
+    float v[8], d[8];
+    load8(x + r * C + c0, v);
+    load8(dy + r * C + c0, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (v[j] - mean[j]) * rstd[j];
+      const float dz = d[j] * act_grad(fmaf(g[j], xh, bt[j]), bn.act);
+      v[j] = g[j] * rstd[j] * (dz - m1[j] - xh * m2[j]);
+    }
+    store8(dx + r * C + c0, v);
+  }
+}
+
 int ew_grid(int64_t total) { return (int)std::min<int64_t>((total + 255) / 256, 148 * 16); }
 
 // ------------------------------------------------------------------------------------------------
@@ -1002,7 +1111,12 @@ int ftc_train_bn_stats(const void* x, int dtype, int64_t rows, int c, float* mea
   const int64_t rpc = (rows + nchunk - 1) / nchunk;
   dim3 grid(ceil_div(c, RED_CH), nchunk);
   BnArgs bn = {};
-  if (dtype == DT_F32)
+  const bool vec = c % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (vec && dtype == DT_F32)
+    col_reduce_vec_kernel<float, 0><<<grid, 256, 0, s>>>(cp<float>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
+  else if (vec)
+    col_reduce_vec_kernel<bf16, 0><<<grid, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
+  else if (dtype == DT_F32)
     col_reduce_kernel<float, 0><<<grid, RED_THREADS, 0, s>>>(cp<float>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
   else
     col_reduce_kernel<bf16, 0><<<grid, RED_THREADS, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
@@ -1019,7 +1133,13 @@ int ftc_train_bn_act(const void* x, void* y, int dtype, int64_t rows, int c, con
   cudaStream_t s = (cudaStream_t)stream;
   BnArgs bn = {mean, var, gamma, beta, eps, act};
   const int64_t total = rows * c;
-  if (dtype == DT_F32)
+  const bool vec = c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0;
+  const dim3 vgrid((unsigned)std::min<int64_t>((rows + 31) / 32, 148 * 8), ceil_div(c, RED_CH));
+  if (vec && dtype == DT_F32)
+    bn_act_vec_kernel<float><<<vgrid, 256, 0, s>>>(cp<float>(x), mp<float>(y), rows, c, bn, cp<float>(residual));
+  else if (vec)
+    bn_act_vec_kernel<bf16><<<vgrid, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, cp<bf16>(residual));
+  else if (dtype == DT_F32)
     bn_act_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x), mp<float>(y), total, c, bn, cp<float>(residual));
   else
     bn_act_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), total, c, bn, cp<bf16>(residual));
@@ -1038,7 +1158,12 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
   const int nchunk = red_chunks(rows);
   const int64_t rpc = (rows + nchunk - 1) / nchunk;
   dim3 grid(ceil_div(c, RED_CH), nchunk);
-  if (dtype == DT_F32)
+  const bool vec = c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  if (vec && dtype == DT_F32)
+    col_reduce_vec_kernel<float, 1><<<grid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), rows, c, rpc, (float*)scratch, bn);
+  else if (vec)
+    col_reduce_vec_kernel<bf16, 1><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
+  else if (dtype == DT_F32)
     col_reduce_kernel<float, 1><<<grid, RED_THREADS, 0, s>>>(cp<float>(x), cp<float>(dy), rows, c, rpc, (float*)scratch, bn);
   else
     col_reduce_kernel<bf16, 1><<<grid, RED_THREADS, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
@@ -1047,7 +1172,12 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
   FTC_POST_LAUNCH();
   const int64_t total = rows * c;
   const float inv_rows = (float)(1.0 / (double)rows);
-  if (dtype == DT_F32)
+  const dim3 vgrid((unsigned)std::min<int64_t>((rows + 31) / 32, 148 * 8), ceil_div(c, RED_CH));
+  if (vec && dtype == DT_F32)
+    bn_act_bwd_vec_kernel<float><<<vgrid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), mp<float>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
+  else if (vec)
+    bn_act_bwd_vec_kernel<bf16><<<vgrid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
+  else if (dtype == DT_F32)
     bn_act_bwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x), cp<float>(dy), mp<float>(dx), total, c, inv_rows, bn, dbeta,
                                                            dgamma);
   else

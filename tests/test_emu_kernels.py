@@ -46,7 +46,7 @@ def scratch(lib, rows, c):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("rows,c,act", [(37, 5, 1), (600, 70, 2), (9, 130, 0)])
+@pytest.mark.parametrize("rows,c,act", [(37, 5, 1), (600, 70, 2), (9, 130, 0), (50, 72, 1), (300, 200, 2), (5, 8, 0), (2, 64, 1)])
 def test_emu_batchnorm_kernels(emu, dt, rows, c, act):
     x = (rnd(rows, c, seed=1) * 1.7 + 0.3).to(dt)
     gamma, beta, res, dy = rnd(c, seed=2), rnd(c, seed=3), rnd(rows, c, seed=4, dt=dt), rnd(rows, c, seed=5, dt=dt)
