@@ -695,6 +695,65 @@ __global__ void __launch_bounds__(256) scale_bc_kernel(const T* __restrict__ x, 
   }
 }
 
+// 16-byte-vector versions (C % 8 == 0): thread = (chunk lane, row lane) as in the BatchNorm kernels; blockIdx.z = image, so the
+// per-(image, channel) factors are loop invariants
+template <typename T, int MUL>
+__global__ void __launch_bounds__(256) spatial_sum_vec_kernel(const T* __restrict__ x, const T* __restrict__ y, int HW, int C,
+                                                              float scale, float* __restrict__ out) {
+  __shared__ float sm[32][RED_CH + 1];
+  const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * RED_CH + ck * 8, b = blockIdx.y;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < C) {
+    const T* xb = x + (int64_t)b * HW * C + c0;
+    const T* yb = MUL ? y + (int64_t)b * HW * C + c0 : nullptr;
+    for (int p = rl; p < HW; p += 32) {
+      float v[8], w[8];
+      load8(xb + (int64_t)p * C, v);
+      if (MUL) load8(yb + (int64_t)p * C, w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += MUL ? v[j] * w[j] : v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[rl][ck * 8 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < RED_CH) {
+    const int c = blockIdx.x * RED_CH + threadIdx.x;
+    if (c < C) {
+      float a = 0.f;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) a += sm[l][threadIdx.x];
+      out[(int64_t)b * C + c] = a * scale;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_bc_vec_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ y, int HW,
+                                                           int C, const float* __restrict__ bias_bc, float bias_mul) {
+  const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * RED_CH + ck * 8, b = blockIdx.z;
+  if (c0 >= C) return;
+  float sc[8], bi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = s[(int64_t)b * C + c0 + j];
+    bi[j] = bias_bc ? bias_bc[(int64_t)b * C + c0 + j] * bias_mul : 0.f;
+  }
+  const T* xb = x + (int64_t)b * HW * C + c0;
+  T* yb = y + (int64_t)b * HW * C + c0;
+  for (int p = blockIdx.x * 32 + rl; p < HW; p += gridDim.x * 32) {
+    float v[8];
+    load8(xb + (int64_t)p * C, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], bi[j]);
+    store8(yb + (int64_t)p * C, v);
+  }
+}
+
 // SE excitation of one image per CTA: hid_pre = W1 mean + b1 ; hid = silu ; gate_pre = W2 hid + b2 ; gate = sigmoid
 // W1 [S][C], W2 [C][S] row-major (the squeezed conv weights of ops/misc.py:247-248)
 __global__ void __launch_bounds__(256) se_fc_fwd_kernel(const float* __restrict__ mean, int C, int S, const float* __restrict__ w1,
@@ -1306,6 +1365,17 @@ int ftc_train_spatial_sum(const void* x, const void* y, int dtype, int batch, in
   FTC_REQUIRE(x && out && dtype_ok(dtype) && batch > 0 && batch <= 65535 && hw > 0 && c > 0, "bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid(ceil_div(c, RED_CH), batch);
+  if (c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    if (dtype == DT_F32) {
+      if (y) spatial_sum_vec_kernel<float, 1><<<grid, 256, 0, s>>>(cp<float>(x), cp<float>(y), hw, c, scale, out);
+      else spatial_sum_vec_kernel<float, 0><<<grid, 256, 0, s>>>(cp<float>(x), nullptr, hw, c, scale, out);
+    } else {
+      if (y) spatial_sum_vec_kernel<bf16, 1><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(y), hw, c, scale, out);
+      else spatial_sum_vec_kernel<bf16, 0><<<grid, 256, 0, s>>>(cp<bf16>(x), nullptr, hw, c, scale, out);
+    }
+    FTC_POST_LAUNCH();
+    return 0;
+  }
   if (dtype == DT_F32) {
     if (y) spatial_sum_kernel<float, 1><<<grid, RED_THREADS, 0, s>>>(cp<float>(x), cp<float>(y), hw, c, scale, out);
     else spatial_sum_kernel<float, 0><<<grid, RED_THREADS, 0, s>>>(cp<float>(x), nullptr, hw, c, scale, out);
@@ -1322,6 +1392,13 @@ int ftc_train_scale_bc(const void* x, const float* scale_bc, const float* bias_b
   FTC_REQUIRE(x && scale_bc && y && dtype_ok(dtype) && batch > 0 && hw > 0 && c > 0, "bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t total = (int64_t)batch * hw * c;
+  if (c % 8 == 0 && batch <= 65535 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    dim3 vgrid((unsigned)std::min(ceil_div(hw, 32), 148 * 4), ceil_div(c, RED_CH), batch);
+    if (dtype == DT_F32) scale_bc_vec_kernel<float><<<vgrid, 256, 0, s>>>(cp<float>(x), scale_bc, mp<float>(y), hw, c, bias_bc, bias_mul);
+    else scale_bc_vec_kernel<bf16><<<vgrid, 256, 0, s>>>(cp<bf16>(x), scale_bc, mp<bf16>(y), hw, c, bias_bc, bias_mul);
+    FTC_POST_LAUNCH();
+    return 0;
+  }
   if (dtype == DT_F32)
     scale_bc_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x), scale_bc, mp<float>(y), hw, c, total, bias_bc, bias_mul);
   else
