@@ -1272,7 +1272,8 @@ int ftc_train_conv2d_wgrad(const void* x, const void* dy, int dtype, int batch, 
   mps = (mps + GK - 1) / GK * GK;
   splits = (M + mps - 1) / mps;
   static const bool use_mma = [] { const char* e = getenv("FTC_WGRAD_MMA"); return e && atoi(e) != 0; }();
-  if (use_mma && dtype == DT_BF16 && cin % 8 == 0 && cout % 8 == 0) {
+  if (use_mma && dtype == DT_BF16 && cin % 8 == 0 && cout % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0) {   // 16-byte cp.async pieces
     const int tiles2 = ceil_div(KK, WM_T) * ceil_div(cout, WM_T);
     int64_t sp = std::max<int64_t>(1, std::min<int64_t>((148 * 2 + tiles2 - 1) / tiles2, (M + 255) / 256));
     sp = std::min<int64_t>(sp, 65535);
