@@ -154,3 +154,60 @@ class TransformerPredictor(nn.Module, _EngineOwner):
             print(f"[{passes - 1} no remask stop]")
         self.last_passes, self.last_stop_reason = passes, reason
         return ids
+
+
+def _flat_mask(key_mask, batch: int):
+    """The reference passes the additive key mask as [B,1,1,Le] (models/transformer.py:250); the kernels take [B, Le] fp32."""
+    if key_mask is None:
+        return None
+    return key_mask.reshape(batch, -1).to(torch.float32).contiguous()
+
+
+class _PartPredictor(nn.Module):
+    """Export-side wrappers (convert3_onnx.py:27-28, convert3_coreml.py:28-29) run layer by layer on the per-layer kernels of
+    train_ops.py (no fused engine plan exists for half a model); precision as ``default_precision()`` or ``.precision``."""
+
+    precision: Optional[str] = None
+
+    def _dt(self):
+        prec = self.precision or default_precision()
+        return torch.float32 if prec == "fp32" else torch.bfloat16
+
+
+class TransformerEncoderPredictor(_PartPredictor):
+    """models/transformer.py:362-370: forward(enc_input [B,Le,106], key_mask [B,1,1,Le]) -> enc_output [B,Le,d]."""
+
+    def __init__(self, encoder):
+        super().__init__()
+        self.head_num = encoder.head_num
+        self.encoder = encoder
+
+    def forward(self, enc_input, key_mask):
+        from ..train_ops import _need_cuda, encoder_forward
+        _need_cuda(enc_input, "transformer")
+        with torch.no_grad():
+            return encoder_forward(self.encoder, enc_input, _flat_mask(key_mask, enc_input.shape[0]), self._dt()).float()
+
+
+class TransformerDecoderPredictor(_PartPredictor):
+    """models/transformer.py:385-393: forward(enc_output, decoder_input [B,Ld] int64, key_mask) -> 3 softmaxes [B,Ld,m_i]."""
+
+    def __init__(self, decoder):
+        super().__init__()
+        self.head_num = decoder.head_num
+        self.decoder = decoder
+
+    def forward(self, enc_output, decoder_input, key_mask):
+        from ..train_ops import _need_cuda, decoder_forward
+        _need_cuda(enc_output, "transformer")
+        with torch.no_grad():
+            outs = decoder_forward(self.decoder, decoder_input, enc_output.to(self._dt()).contiguous(),
+                                   _flat_mask(key_mask, enc_output.shape[0]), self._dt())
+        return [torch.softmax(o, dim=-1) for o in outs]
+
+
+class TransformerDecoderPredictorSplited(TransformerDecoderPredictor):
+    """models/transformer.py:395-404: the decoder input arrives as its three residues (x mod 1091, 1093, 1097)."""
+
+    def forward(self, enc_output, decoder_input1, decoder_input2, decoder_input3, key_mask):
+        return super().forward(enc_output, [decoder_input1, decoder_input2, decoder_input3], key_mask)

@@ -413,16 +413,15 @@ def _ln(x: Tensor, norm, r1=None, r2=None) -> Tensor:
     return _LayerNorm.apply(x.contiguous(), norm.weight, norm.bias, r1, r2, 1e-5)
 
 
-def transformer_train_forward(model, enc_input: Tensor, dec_input: Tensor) -> List[Tensor]:
-    """Transformer.forward (models/transformer.py:248-253) in train mode with a tape -> 3 x [B, Ld, m_i] fp32."""
-    _need_cuda(enc_input, "transformer")
-    if getattr(model, "dropout", 0.0):
-        raise NotImplementedError("findtextcenternet_b200: train-mode dropout > 0 is not built (ModelDimensions default is 0.0)")
-    dt = torch.float32 if model.precision == "fp32" else torch.bfloat16
-    enc, dec = model.encoder, model.decoder
-    heads = enc.head_num
+def key_pad_mask(enc_input: Tensor) -> Tensor:
+    """Transformer.forward (models/transformer.py:249-250): additive fp32 mask [B, Le], -inf on all-zero encoder rows."""
     key_pad = torch.all(enc_input == 0, dim=-1)
-    mask = torch.zeros(key_pad.shape, dtype=torch.float32, device=enc_input.device).masked_fill_(key_pad, float("-inf"))
+    return torch.zeros(key_pad.shape, dtype=torch.float32, device=enc_input.device).masked_fill_(key_pad, float("-inf"))
+
+
+def encoder_forward(enc, enc_input: Tensor, mask: Optional[Tensor], dt: torch.dtype) -> Tensor:
+    """Encoder.forward (models/transformer.py:173-180) layer by layer on the train kernels -> [B, Le, d] (dt)."""
+    heads = enc.head_num
     x = _pos(linear(enc_input.to(dt), enc.embed.weight), enc.pos_emb.encoding)
     x = _ln(x, enc.norm)
     for i in range(enc.block_num):
@@ -430,10 +429,23 @@ def transformer_train_forward(model, enc_input: Tensor, dec_input: Tensor) -> Li
         skip = x
         x = _ln(_mha(blk.mha, heads, x, None, mask), blk.norm1, skip)
         x = _ln(_ff(blk.ff, x), blk.norm2, x, skip)
-    y = x
+    return x
+
+
+def decoder_forward(dec, dec_input, y: Tensor, mask: Optional[Tensor], dt: torch.dtype) -> List[Tensor]:
+    """Decoder.forward (models/transformer.py:225-238) -> 3 x [B, Ld, m_i] fp32 logits.  dec_input: int64 tokens [B, Ld], or the
+    three residue tensors of DecoderSplited.forward (:371-383)."""
+    heads = dec.head_num
     emb = [_sub(dec.embed, i).weight for i in range(3)]
-    x = _pos(_Embed3.apply(dec_input.to(torch.int64), emb[0], emb[1], emb[2], dt), dec.pos_emb.encoding)
-    x = _ln(x, dec.norm)
+    if isinstance(dec_input, (list, tuple)):     # already reduced modulo m_i: one lookup per table (the other two tables zero)
+        x = None
+        for i, r in enumerate(dec_input):
+            tabs = [e if j == i else torch.zeros_like(e) for j, e in enumerate(emb)]
+            part = _Embed3.apply(r.to(torch.int64), tabs[0], tabs[1], tabs[2], dt)
+            x = part if x is None else x + part
+    else:
+        x = _Embed3.apply(dec_input.to(torch.int64), emb[0], emb[1], emb[2], dt)
+    x = _ln(_pos(x, dec.pos_emb.encoding), dec.norm)
     for i in range(dec.block_num):
         blk = _sub(dec.blocks, i)
         skip = x
@@ -441,3 +453,14 @@ def transformer_train_forward(model, enc_input: Tensor, dec_input: Tensor) -> Li
         x = _ln(_mha(blk.cross_attn, heads, x, y, mask), blk.norm2, x)
         x = _ln(_ff(blk.ff, x), blk.norm3, x, skip)
     return [linear(x, _sub(dec.out_layers, i).weight, _sub(dec.out_layers, i).bias).float() for i in range(3)]
+
+
+def transformer_train_forward(model, enc_input: Tensor, dec_input: Tensor) -> List[Tensor]:
+    """Transformer.forward (models/transformer.py:248-253) in train mode with a tape -> 3 x [B, Ld, m_i] fp32."""
+    _need_cuda(enc_input, "transformer")
+    if getattr(model, "dropout", 0.0):
+        raise NotImplementedError("findtextcenternet_b200: train-mode dropout > 0 is not built (ModelDimensions default is 0.0)")
+    dt = torch.float32 if model.precision == "fp32" else torch.bfloat16
+    mask = key_pad_mask(enc_input)
+    y = encoder_forward(model.encoder, enc_input, mask, dt)
+    return decoder_forward(model.decoder, dec_input, y, mask, dt)

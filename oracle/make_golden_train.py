@@ -154,6 +154,17 @@ def main_transformer():
     params = dict(model.named_parameters())
     for k in TF_FULL:
         out["full/" + k] = params[k].grad.float().numpy()
+    # the export-side wrappers (models/transformer.py:362-404) of the same fp32 model in eval mode
+    from models.transformer import TransformerEncoderPredictor, TransformerDecoderPredictor
+    m32 = model32.eval()
+    with torch.no_grad():
+        km = torch.where(torch.all(enc == 0, dim=-1)[:, None, None, :], float("-inf"), 0)
+        enc_out = TransformerEncoderPredictor(m32.encoder)(enc, km)
+        probs = TransformerDecoderPredictor(m32.decoder)(enc_out, dec, km)
+    out["pred_enc_out"] = enc_out.numpy()
+    for i in range(3):
+        out[f"pred_probs{i}_max"] = probs[i].max(-1).values.numpy()
+        out[f"pred_probs{i}_argmax"] = probs[i].argmax(-1).numpy()
     path = os.path.join(GOLD, "train_transformer_seed0.npz")
     np.savez_compressed(path, **out)
     rel = np.array(errs)[np.array(norms) > 0] / np.array(norms)[np.array(norms) > 0]

@@ -312,3 +312,30 @@ def test_transformer_train_graph_matches_reference_golden(oracle_kernels):
         assert rel_l2(outs[i].detach(), gold[f"out{i}"]) < 1e-5
     sum((o * torch.from_numpy(gold[f"w{i}"])).sum() for i, o in enumerate(outs)).backward()
     check_gradients_against_golden(gold, dict(model.named_parameters()), 1e-4)
+
+
+def test_part_predictors_match_reference(oracle_kernels):
+    """TransformerEncoderPredictor / TransformerDecoderPredictor(Splited) (export-side wrappers, models/transformer.py:362-404)
+    layer by layer on the train kernels (oracle-backed here) vs the reference's own wrappers on the same fp32 model."""
+    from findtextcenternet_b200 import synthetic
+    from findtextcenternet_b200.models.transformer import (Transformer, TransformerDecoderPredictor,
+                                                            TransformerDecoderPredictorSplited, TransformerEncoderPredictor)
+    gold = np.load(os.path.join(GOLDEN, "train_transformer_seed0.npz"))
+    model = Transformer(**TF_DIMS, dropout=0.0)
+    model.load_state_dict(synthetic.transformer_state_dict(0, **TF_DIMS))
+    model.eval()
+    enc, dec = torch.from_numpy(gold["enc"]), torch.from_numpy(gold["dec"])
+    km = torch.where(torch.all(enc == 0, dim=-1)[:, None, None, :], float("-inf"), 0)
+    ep, dp, ds = (TransformerEncoderPredictor(model.encoder), TransformerDecoderPredictor(model.decoder),
+                  TransformerDecoderPredictorSplited(model.decoder))
+    for m in (ep, dp, ds):
+        m.precision = "fp32"
+    enc_out = ep(enc, km)
+    assert rel_l2(enc_out, gold["pred_enc_out"]) < 1e-5
+    probs = dp(enc_out, dec, km)
+    split = ds(enc_out, dec % 1091, dec % 1093, dec % 1097, km)
+    for i in range(3):
+        assert rel_l2(probs[i].max(-1).values, gold[f"pred_probs{i}_max"]) < 1e-4
+        assert torch.equal(probs[i].argmax(-1), torch.from_numpy(gold[f"pred_probs{i}_argmax"]))
+        assert rel_l2(split[i], probs[i]) < 1e-6
+        assert torch.allclose(probs[i].sum(-1), torch.ones(probs[i].shape[:-1]), atol=1e-5)

@@ -420,3 +420,25 @@ def test_page_maps_on_device_match_reference_run_detector():
     assert np.abs(maps[1][::3, ::3] - gold["lines_all_s3"]).max() < 1e-5
     assert np.abs(maps[2][::3, ::3] - gold["seps_all_s3"]).max() < 1e-5
     assert np.abs(maps - DO.page_maps(heat9.numpy(), offsets, pw, ph)).max() < 1e-5
+
+
+def test_part_predictors_on_device():
+    """TransformerEncoderPredictor / TransformerDecoderPredictor(Splited) on the CUDA kernels vs the reference's wrappers (golden)."""
+    from findtextcenternet_b200.models.transformer import (TransformerDecoderPredictor, TransformerDecoderPredictorSplited,
+                                                            TransformerEncoderPredictor)
+    gold = np.load(os.path.join(GOLDEN, "train_transformer_seed0.npz"))
+    model = _transformer("fp32").eval()
+    enc, dec = torch.from_numpy(gold["enc"]).cuda(), torch.from_numpy(gold["dec"]).cuda()
+    km = torch.where(torch.all(enc == 0, dim=-1)[:, None, None, :], float("-inf"), 0)
+    ep, dp, ds = (TransformerEncoderPredictor(model.encoder), TransformerDecoderPredictor(model.decoder),
+                  TransformerDecoderPredictorSplited(model.decoder))
+    for m in (ep, dp, ds):
+        m.precision = "fp32"
+    enc_out = ep(enc, km)
+    assert rel_l2(enc_out.cpu(), gold["pred_enc_out"]) < 1e-4
+    probs = dp(enc_out, dec, km)
+    split = ds(enc_out, dec % 1091, dec % 1093, dec % 1097, km)
+    for i in range(3):
+        assert rel_l2(probs[i].max(-1).values.cpu(), gold[f"pred_probs{i}_max"]) < 1e-3
+        assert (probs[i].argmax(-1).cpu() == torch.from_numpy(gold[f"pred_probs{i}_argmax"])).float().mean() > 0.99
+        assert rel_l2(split[i].cpu(), probs[i].cpu()) < 1e-5
