@@ -391,3 +391,31 @@ def test_transformer_train_graph_through_product_wrappers_on_emu(ops_on_emu, mon
         assert rel_l2(outs[i].detach(), gold[f"out{i}"]) < 1e-4
     sum((o * torch.from_numpy(gold[f"w{i}"])).sum() for i, o in enumerate(outs)).backward()
     check_gradients_against_golden(gold, dict(model.named_parameters()), 1e-3)
+
+
+def test_emu_bf16_storage_of_the_bandwidth_kernels(emu):
+    """bf16 activations through the depthwise / squeeze-excitation / upsample-adjoint kernels (vector and scalar variants)."""
+    dt = torch.bfloat16
+    for c in (16, 12):          # 16: the 16-byte-vector kernels; 12: the scalar ones
+        b, h, w = 2, 6, 5
+        x, w9c, dy = rnd(b, h, w, c, seed=1, dt=dt), rnd(9, c, seed=2, scale=0.3), rnd(b, h, w, c, seed=3, dt=dt)
+        y, dx, dw = torch.empty_like(x), torch.empty_like(x), torch.empty(9, c)
+        ok(emu, emu.ftc_train_dwconv3x3(P(x), P(y), 1, b, h, w, c, 1, P(w9c), None))
+        ok(emu, emu.ftc_train_dwconv3x3_dgrad(P(dy), P(dx), 1, b, h, w, c, 1, P(w9c), None))
+        ok(emu, emu.ftc_train_dwconv3x3_wgrad(P(x), P(dy), 1, b, h, w, c, 1, P(dw), None))
+        assert rel_l2(y.float(), TO.dwconv3x3_raw(x.float(), w9c, 1)) < 1e-2
+        assert rel_l2(dx.float(), TO.dwconv3x3_dgrad(dy.float(), w9c, h, w, 1)) < 1e-2
+        assert rel_l2(dw, TO.dwconv3x3_wgrad(x.float(), dy.float(), 1)) < 1e-5
+        mean, dgate = torch.empty(b, c), torch.empty(b, c)
+        ok(emu, emu.ftc_train_spatial_sum(P(x), None, 1, b, h * w, c, C.c_float(1.0 / (h * w)), P(mean), None))
+        ok(emu, emu.ftc_train_spatial_sum(P(dy), P(x), 1, b, h * w, c, C.c_float(1.0), P(dgate), None))
+        assert rel_l2(mean, TO.spatial_sum(x.float(), None, 1.0 / (h * w))) < 1e-5
+        assert rel_l2(dgate, TO.spatial_sum(dy.float(), x.float(), 1.0)) < 1e-5
+        gate, bias = torch.rand(b, c, generator=torch.Generator().manual_seed(4)), rnd(b, c, seed=5)
+        out = torch.empty_like(x)
+        ok(emu, emu.ftc_train_scale_bc(P(x), P(gate), P(bias), C.c_float(0.25), P(out), 1, b, h * w, c, None))
+        assert rel_l2(out.float(), TO.scale_bc(x.float(), gate, bias, 0.25)) < 1e-2
+        du = rnd(b, 2 * h, 2 * w, c, seed=6, dt=dt)
+        dxu = torch.empty_like(x)
+        ok(emu, emu.ftc_train_upsample2x_bwd(P(du), P(dxu), 1, b, h, w, c, None))
+        assert rel_l2(dxu.float(), TO.upsample2x_bwd(du.float())) < 1e-2
