@@ -61,3 +61,79 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int 
             g.copy_(flat[off: off + g.numel()].view_as(g))
             off += g.numel()
     return len(pending)
+
+
+class GradientBuckets:
+    """Gradient all-reduce overlapped with backward (reverse-layer-order buckets launched as soon as their last
+    gradient is written).  Parameters are assigned to flat buckets in reverse registration order; a post-accumulate hook per
+    parameter counts arrivals, and the moment a bucket is complete its flat copy goes out as an ASYNCHRONOUS all-reduce (NCCL:
+    on its own stream, under the remaining backward kernels).  ``finish()`` - call it after ``backward()`` and before the
+    optimizer step - launches whatever is still pending (parameters that received no gradient this step are skipped, the same
+    on every rank), waits, divides by the world size and scatters the means back into ``.grad``.
+
+        buckets = GradientBuckets(model.parameters())      # once
+        loss.backward(); buckets.finish(); optimizer.step()
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20, group=None):
+        self.group = group
+        self.params = [p for p in reversed(list(params)) if p.requires_grad]
+        self.buckets: List[List[torch.nn.Parameter]] = []
+        cur, size = [], 0
+        for p in self.params:
+            nbytes = p.numel() * p.element_size()
+            if cur and (size + nbytes > bucket_bytes or p.dtype != cur[0].dtype):
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += nbytes
+        if cur:
+            self.buckets.append(cur)
+        self._bucket_of = {id(p): bi for bi, b in enumerate(self.buckets) for p in b}
+        self._arrived = [0] * len(self.buckets)
+        self._launched: List = [None] * len(self.buckets)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.launched_during_backward = 0
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        bi = self._bucket_of[id(p)]
+        self._arrived[bi] += 1
+        if self._arrived[bi] == len(self.buckets[bi]) and self._launched[bi] is None:
+            self._launch(bi)
+            self.launched_during_backward += 1
+
+    def _launch(self, bi: int) -> None:
+        members = [p for p in self.buckets[bi] if p.grad is not None]
+        if not members:
+            self._launched[bi] = ()
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in members])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._launched[bi] = (work, flat, members)
+
+    def finish(self) -> int:
+        """Complete the step's exchange; returns the number of all-reduce calls issued."""
+        world = dist.get_world_size(self.group)
+        calls = 0
+        for bi in range(len(self.buckets)):
+            if self._launched[bi] is None:
+                self._launch(bi)
+        for bi in range(len(self.buckets)):
+            item = self._launched[bi]
+            if item:
+                work, flat, members = item
+                work.wait()
+                flat.div_(world)
+                off = 0
+                for p in members:
+                    p.grad.copy_(flat[off: off + p.numel()].view_as(p.grad))
+                    off += p.numel()
+                calls += 1
+            self._launched[bi] = None
+            self._arrived[bi] = 0
+        return calls
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

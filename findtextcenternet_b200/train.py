@@ -23,10 +23,12 @@ TRAIN1_LOSSES = ["keymap_loss", "size_loss", "textline_loss", "separator_loss", 
 
 
 def train1_step(model, optimizer, cov, image, labelmap, idmap, fmask, iters_to_accumulate: int = 1, step_now: bool = True,
-                group=None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+                group=None, buckets: Optional["shard.GradientBuckets"] = None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
     """One iteration of the train1.py loop body (:183-191).  With torch.distributed initialised (world size > 1) the gradients
     are averaged over ranks in reverse-order flat buckets before the optimizer step, and the nine raw losses that drive the
-    CoV weights are averaged too, so every replica keeps bit-identical loss weights and parameters."""
+    CoV weights are averaged too, so every replica keeps bit-identical loss weights and parameters.  With ``buckets``
+    (``shard.GradientBuckets(model.parameters())``, built once; not with gradient accumulation) the bucket all-reduces are
+    launched from inside backward and overlap it."""
     heatmap, decoder_outputs = model(image, fmask)
     rawloss = loss_function(fmask, labelmap, idmap, heatmap, decoder_outputs)
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -35,7 +37,9 @@ def train1_step(model, optimizer, cov, image, labelmap, idmap, fmask, iters_to_a
     loss = cov(rawloss)
     (loss / iters_to_accumulate).backward()
     if step_now:
-        if distributed:
+        if distributed and buckets is not None:
+            buckets.finish()
+        elif distributed:
             shard.allreduce_gradients([p for p in model.parameters() if p.requires_grad], group=group)
         optimizer.step()
         optimizer.zero_grad()

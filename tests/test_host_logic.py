@@ -123,6 +123,28 @@ assert calls >= 2
 for i, p in enumerate(model.parameters()):
     mean = sum(grads_all[r][i] for r in range(world)) / world
     assert torch.allclose(p.grad, mean, atol=1e-6), i
+# overlapped exchange: buckets launched from inside backward by post-accumulate hooks give the same means
+from findtextcenternet_b200.shard import GradientBuckets
+torch.manual_seed(1)
+net = torch.nn.Sequential(torch.nn.Linear(19, 31), torch.nn.Tanh(), torch.nn.Linear(31, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+unused = torch.nn.Parameter(torch.zeros(5))            # never receives a gradient (like the self-attention pos_emb_k tables)
+params = list(net.parameters()) + [unused]
+gb = GradientBuckets(params, bucket_bytes=1024)
+assert len(gb.buckets) >= 3
+for step in range(2):
+    for p in params:
+        p.grad = None
+    gx = torch.Generator().manual_seed(500 + 10 * step + rank)
+    net(torch.randn(8, 19, generator=gx)).square().sum().backward()
+    local = [p.grad.clone() for p in net.parameters()]
+    calls = gb.finish()
+    assert calls >= 3 and gb.launched_during_backward >= 2 * (step + 1), (calls, gb.launched_during_backward)
+    gathered = [torch.zeros_like(torch.cat([g.reshape(-1) for g in local])) for _ in range(world)]
+    dist.all_gather(gathered, torch.cat([g.reshape(-1) for g in local]))
+    mean = sum(gathered) / world
+    assert torch.allclose(torch.cat([p.grad.reshape(-1) for p in net.parameters()]), mean, atol=1e-6)
+    assert unused.grad is None
+gb.remove()
 # train1_step: the nine raw losses that drive the CoV weights take their cross-rank mean VALUE but keep the local gradient path
 from findtextcenternet_b200.train import TRAIN1_LOSSES, _sync_loss_values
 leaf = torch.full((len(TRAIN1_LOSSES),), float(rank + 1), requires_grad=True)

@@ -43,6 +43,8 @@ def main():
     opt.train()
     cov = CoVWeightingLoss(device=dev, losses=train.TRAIN1_LOSSES)
     batch = synthetic.train1_batch(args.batch, seed=rank, size=args.size, device=dev)
+    from findtextcenternet_b200 import shard
+    buckets = shard.GradientBuckets([p for p in model.parameters() if p.requires_grad]) if world > 1 else None
     fmask = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     losses = []
@@ -55,7 +57,7 @@ def main():
             l0 = _lib.launch_count()
             e0.record()
         fmask = model.get_fmask(batch["labelmap"], fmask)
-        loss, raw = train.train1_step(model, opt, cov, batch["image"], batch["labelmap"], batch["idmap"], fmask)
+        loss, raw = train.train1_step(model, opt, cov, batch["image"], batch["labelmap"], batch["idmap"], fmask, buckets=buckets)
         losses.append(float(raw["loss"]))
     e1.record()
     torch.cuda.synchronize()
