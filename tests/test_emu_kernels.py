@@ -419,3 +419,61 @@ def test_emu_bf16_storage_of_the_bandwidth_kernels(emu):
         dxu = torch.empty_like(x)
         ok(emu, emu.ftc_train_upsample2x_bwd(P(du), P(dxu), 1, b, h, w, c, None))
         assert rel_l2(dxu.float(), TO.upsample2x_bwd(du.float())) < 1e-2
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_detector_blocks_through_product_wrappers_on_emu(ops_on_emu, monkeypatch, dt):
+    """A FusedMBConv block, an MBConv block (depthwise stride 2 + squeeze-excitation), a residual MBConv block with a pinned
+    StochasticDepth draw and a conv-BN-GELU-upsample head stage, forward + backward, through train_ops.py -> _ops.py -> the
+    emulated kernels (incl. the 16-byte-vector BatchNorm / SE kernels) against the same graph on the pure oracle."""
+    from findtextcenternet_b200 import arch, train_ops
+    from findtextcenternet_b200.models._tree import Node, populate
+
+    def build():
+        torch.manual_seed(0)
+        root = Node()
+        specs = list(arch._conv_bn("a.block.0", 16, 64, 3)) + list(arch._conv_bn("a.block.1", 64, 24, 1))           # fused, expand 4
+        for name, cin, cout in (("b", 24, 32), ("c", 32, 32)):
+            exp = cin * 2
+            specs += list(arch._conv_bn(f"{name}.block.0", cin, exp, 1)) + list(arch._conv_bn(f"{name}.block.1", exp, exp, 3, groups=exp))
+            specs += [arch.ParamSpec(f"{name}.block.2.fc1.weight", (8, exp, 1, 1), "conv", exp), arch.ParamSpec(f"{name}.block.2.fc1.bias", (8,), "bias"),
+                      arch.ParamSpec(f"{name}.block.2.fc2.weight", (exp, 8, 1, 1), "conv", 8), arch.ParamSpec(f"{name}.block.2.fc2.bias", (exp,), "bias")]
+            specs += list(arch._conv_bn(f"{name}.block.3", exp, cout, 1))
+        specs += list(arch._conv_bn("up", 32, 16, 3))
+        populate(root, specs, backbone_prefix="\0")
+        return root
+
+    def run(K, root, x, noise):
+        monkeypatch.setattr(train_ops, "K", K)
+        sa = arch.StageCfg(True, 4, 3, 1, 16, 24, 1)
+        sb = arch.StageCfg(False, 2, 3, 2, 24, 32, 1)
+        sc = arch.StageCfg(False, 2, 3, 1, 32, 32, 1)
+        y = train_ops._block(x, root.a, sa, 16, 1, 0.0, None)
+        y = train_ops._block(y, root.b, sb, 24, 2, 0.0, None)
+        y = train_ops._block(y, root.c, sc, 32, 1, 0.3, noise)          # residual + pinned StochasticDepth noise
+        y = train_ops._Upsample2x.apply(train_ops.conv_bn_act(y, root.up, arch.HEAD_BN_EPS, train_ops._lib.ACT_GELU))
+        w = torch.randn(y.shape, generator=torch.Generator().manual_seed(3))
+        (y.float() * w).sum().backward()
+        return y.detach().float(), {n: p.grad.clone() for n, p in root.named_parameters()}
+
+    class Hybrid:
+        def __getattr__(self, name):
+            return getattr(TO, name) if name in ("conv2d", "upsample2x") else getattr(ops_on_emu, name)
+
+    x = torch.randn(2, 8, 8, 16, generator=torch.Generator().manual_seed(1)).to(dt)
+    noise = torch.tensor([0.0, 1.0 / 0.7])
+    ref_root, emu_root = build(), build()
+    y_ref, g_ref = run(TO, ref_root, x.clone().requires_grad_(), noise)
+    y_emu, g_emu = run(Hybrid(), emu_root, x.clone().requires_grad_(), noise)
+    tol = 1e-4 if dt == torch.float32 else 6e-2
+    assert rel_l2(y_emu, y_ref) < tol
+    # BatchNorm shifts that feed a 1x1 conv + batch-statistics layer have exactly zero true gradient (both sides return rounding
+    # noise there): the error is measured against the largest gradient of the graph as well as against the tensor itself
+    scale = max(float(g.double().norm()) for g in g_ref.values())
+    gtol = tol + (0.0 if dt == torch.float32 else 0.1)
+    for n in g_ref:
+        err = float((g_emu[n].double() - g_ref[n].double()).norm())
+        assert err <= gtol * float(g_ref[n].double().norm()) + (1e-5 if dt == torch.float32 else 1e-3) * scale, (n, err)
+    for (n, b_ref), (_, b_emu) in zip(ref_root.named_buffers(), emu_root.named_buffers()):
+        btol = 1e-3 + (0 if dt == torch.float32 else 2e-2)      # + absolute floor: means of exactly centred inputs are pure noise
+        assert float((b_emu.double() - b_ref.double()).norm()) <= btol * float(b_ref.double().norm()) + (1e-5 if dt == torch.float32 else 1e-3), n
