@@ -602,6 +602,59 @@ __global__ void __launch_bounds__(256) dw_dgrad_kernel(const T* __restrict__ dy,
   }
 }
 
+// 16-byte-vector depthwise forward / data gradient (C % 8 == 0): thread = (chunk lane, pixel lane), blockIdx.y = 64-channel slab,
+// so the 9 x 8 tap weights are loop invariants in registers and every access is a full 16-byte piece of a 128-byte run.
+// DGRAD = false: y[b,oy,ox] = sum_t x[b, oy*s-1+ky, ox*s-1+kx] * w[t];  DGRAD = true: dx[b,iy,ix] = sum_t dy[b,(iy+1-ky)/s,(ix+1-kx)/s] * w[t]
+template <typename T, bool DGRAD>
+__global__ void __launch_bounds__(256) dw_vec_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int Hs, int Ws, int Hd, int Wd,
+                                                     int C, int stride, const float* __restrict__ w) {
+  const int ck = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * RED_CH + ck * 8;
+  if (c0 >= C) return;
+  float wk[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) load8(w + (int64_t)t * C + c0, wk[t]);
+  const int64_t P = (int64_t)B * Hd * Wd;
+  for (int64_t p = (int64_t)blockIdx.x * 32 + pl; p < P; p += (int64_t)gridDim.x * 32) {
+    int64_t q = p;
+    const int dx_ = (int)(q % Wd); q /= Wd;
+    const int dy_ = (int)(q % Hd);
+    const int b = (int)(q / Hd);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      int sy;
+      if (DGRAD) {
+        const int ny = dy_ + 1 - ky;
+        if (ny < 0 || ny % stride != 0) continue;
+        sy = ny / stride;
+      } else {
+        sy = dy_ * stride - 1 + ky;
+      }
+      if (sy < 0 || sy >= Hs) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        int sx;
+        if (DGRAD) {
+          const int nx = dx_ + 1 - kx;
+          if (nx < 0 || nx % stride != 0) continue;
+          sx = nx / stride;
+        } else {
+          sx = dx_ * stride - 1 + kx;
+        }
+        if (sx < 0 || sx >= Ws) continue;
+        float v[8];
+        load8(src + (((int64_t)b * Hs + sy) * Ws + sx) * C + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wk[ky * 3 + kx][j], acc[j]);
+      }
+    }
+    store8(dst + p * C + c0, acc);
+  }
+}
+
 // dw[t][c] += sum_{b,oy,ox} dy[b,oy,ox,c] * x[b, oy*s-1+ky, ox*s-1+kx, c]; CTA = 32 channels x 8 pixel lanes, pixel range
 // split over blockIdx.y, fp32 atomics into a zeroed buffer
 template <typename T>
@@ -855,7 +908,7 @@ __global__ void __launch_bounds__(256) se_fc_bwd_weight_kernel(const float* __re
 // footprint contains (iy, ix), with the forward's own weights.  Source coordinate of output o: f = o * (n-1)/(2n-1)
 // (computed as in upsample2x_kernel, detector_ops.cu), so the candidates of input index j are the outputs with floor(f) in
 // {j-1, j}: o in [2j-2, 2j+3] clipped.  CTA per input row, warps over pixels, lanes over channels.
-template <typename T>
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int H, int W, int C,
                                                              float sy, float sx) {
   const int Ho = 2 * H, Wo = 2 * W;
@@ -888,6 +941,25 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict
       if (wgt != 0.f) { wx[nx] = wgt; oxs[nx] = ox; ++nx; }
     }
     T* po = dx + (((int64_t)b * H + iy) * W + ix) * C;
+    if (VEC) {     // C % 8 == 0: a lane owns 8 consecutive channels, 16-byte loads / stores
+      for (int c = lane * 8; c < C; c += 256) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int a = 0; a < ny; ++a) {
+          const T* row = dy + (((int64_t)b * Ho + oys[a]) * Wo) * C + c;
+          for (int k = 0; k < nx; ++k) {
+            float v[8];
+            load8(row + (int64_t)oxs[k] * C, v);
+            const float wgt = wy[a] * wx[k];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, v[j], acc[j]);
+          }
+        }
+        store8(po + c, acc);
+      }
+      continue;
+    }
     for (int c = lane; c < C; c += 32) {
       float acc = 0.f;
       for (int a = 0; a < ny; ++a) {
@@ -1318,6 +1390,13 @@ int ftc_train_dwconv3x3(const void* x, void* y, int dtype, int batch, int h, int
   cudaStream_t s = (cudaStream_t)stream;
   const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
   const int64_t total = (int64_t)batch * ho * wo * c;
+  if (c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w9c)) & 15) == 0) {
+    const dim3 vgrid((unsigned)std::min<int64_t>(((int64_t)batch * ho * wo + 31) / 32, 148 * 8), ceil_div(c, RED_CH));
+    if (dtype == DT_F32) dw_vec_kernel<float, false><<<vgrid, 256, 0, s>>>(cp<float>(x), mp<float>(y), batch, h, w, ho, wo, c, stride, w9c);
+    else dw_vec_kernel<bf16, false><<<vgrid, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), batch, h, w, ho, wo, c, stride, w9c);
+    FTC_POST_LAUNCH();
+    return 0;
+  }
   if (dtype == DT_F32)
     dw_fwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x), mp<float>(y), batch, h, w, c, ho, wo, stride, w9c);
   else
@@ -1332,6 +1411,13 @@ int ftc_train_dwconv3x3_dgrad(const void* dy, void* dx, int dtype, int batch, in
   cudaStream_t s = (cudaStream_t)stream;
   const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
   const int64_t total = (int64_t)batch * h * w * c;
+  if (c % 8 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(w9c)) & 15) == 0) {
+    const dim3 vgrid((unsigned)std::min<int64_t>(((int64_t)batch * h * w + 31) / 32, 148 * 8), ceil_div(c, RED_CH));
+    if (dtype == DT_F32) dw_vec_kernel<float, true><<<vgrid, 256, 0, s>>>(cp<float>(dy), mp<float>(dx), batch, ho, wo, h, w, c, stride, w9c);
+    else dw_vec_kernel<bf16, true><<<vgrid, 256, 0, s>>>(cp<bf16>(dy), mp<bf16>(dx), batch, ho, wo, h, w, c, stride, w9c);
+    FTC_POST_LAUNCH();
+    return 0;
+  }
   if (dtype == DT_F32)
     dw_dgrad_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(dy), mp<float>(dx), batch, h, w, c, ho, wo, stride, w9c);
   else
@@ -1435,10 +1521,14 @@ int ftc_train_upsample2x_bwd(const void* dy, void* dx, int dtype, int batch, int
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid(h, batch);
   const float sy = (float)(h - 1) / (float)(2 * h - 1), sx = (float)(w - 1) / (float)(2 * w - 1);
-  if (dtype == DT_F32)
-    upsample2x_bwd_kernel<float><<<grid, 256, 0, s>>>(cp<float>(dy), mp<float>(dx), h, w, c, sy, sx);
-  else
-    upsample2x_bwd_kernel<bf16><<<grid, 256, 0, s>>>(cp<bf16>(dy), mp<bf16>(dx), h, w, c, sy, sx);
+  const bool vec = c % 8 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  if (dtype == DT_F32) {
+    if (vec) upsample2x_bwd_kernel<float, true><<<grid, 256, 0, s>>>(cp<float>(dy), mp<float>(dx), h, w, c, sy, sx);
+    else upsample2x_bwd_kernel<float, false><<<grid, 256, 0, s>>>(cp<float>(dy), mp<float>(dx), h, w, c, sy, sx);
+  } else {
+    if (vec) upsample2x_bwd_kernel<bf16, true><<<grid, 256, 0, s>>>(cp<bf16>(dy), mp<bf16>(dx), h, w, c, sy, sx);
+    else upsample2x_bwd_kernel<bf16, false><<<grid, 256, 0, s>>>(cp<bf16>(dy), mp<bf16>(dx), h, w, c, sy, sx);
+  }
   FTC_POST_LAUNCH();
   return 0;
 }
