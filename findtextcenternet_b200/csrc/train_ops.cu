@@ -1224,6 +1224,14 @@ template <typename T> T* mp(void* p) { return reinterpret_cast<T*>(p); }
 
 bool dtype_ok(int dt) { return dt == DT_F32 || dt == DT_BF16; }
 
+// staged mma.sync weight gradient: -1 = follow FTC_WGRAD_MMA (read once), 0 / 1 = set by ftc_debug_set_wgrad_mma
+int g_wgrad_mma = -1;
+bool wgrad_mma_enabled() {
+  if (g_wgrad_mma >= 0) return g_wgrad_mma != 0;
+  static const bool env = [] { const char* e = getenv("FTC_WGRAD_MMA"); return e && atoi(e) != 0; }();
+  return env;
+}
+
 }  // namespace
 }  // namespace ftc
 
@@ -1343,7 +1351,7 @@ int ftc_train_conv2d_wgrad(const void* x, const void* dy, int dtype, int batch, 
   int64_t mps = (M + splits - 1) / splits;
   mps = (mps + GK - 1) / GK * GK;
   splits = (M + mps - 1) / mps;
-  static const bool use_mma = [] { const char* e = getenv("FTC_WGRAD_MMA"); return e && atoi(e) != 0; }();
+  const bool use_mma = wgrad_mma_enabled();
   if (use_mma && dtype == DT_BF16 && cin % 8 == 0 && cout % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0) {   // 16-byte cp.async pieces
     const int tiles2 = ceil_div(KK, WM_T) * ceil_div(cout, WM_T);
@@ -1658,6 +1666,11 @@ int ftc_page_maps(const float* heat9, int batch, int h, int w, const int* tile_m
   page_maps_kernel<<<ew_grid((int64_t)batch * 7 * h * w), 256, 0, (cudaStream_t)stream>>>(heat9, batch, h, w, tile_meta, (int*)page, page_h4,
                                                                                          page_w4, scale);
   FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_debug_set_wgrad_mma(int on) {
+  g_wgrad_mma = on < 0 ? -1 : (on != 0);
   return 0;
 }
 

@@ -294,6 +294,10 @@ int ftc_train_attention_bwd(const void* q, const void* k, const void* v, const f
 int ftc_page_maps(const float* heat9, int batch, int h, int w, const int* tile_meta, float* page, int page_h4, int page_w4, int scale,
                   void* stream);
 
+/* debug / staging: route bf16 weight gradients (cin, cout multiples of 8) through the mma.sync kernel: 1 on, 0 off, -1 follow the
+ * FTC_WGRAD_MMA environment variable (default; off when unset) */
+int ftc_debug_set_wgrad_mma(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -390,20 +390,6 @@ def test_detect_page_equals_tile_by_tile_decode():
     assert ref.shape == loc.shape and np.allclose(ref, loc, rtol=1e-3, atol=1e-3)
 
 
-@pytest.mark.skipif(os.environ.get("FTC_WGRAD_MMA") != "1", reason="staged mma.sync weight-gradient kernel: run with FTC_WGRAD_MMA=1")
-@pytest.mark.parametrize("b,h,w,cin,cout,k,stride", [
-    (2, 6, 5, 8, 16, 3, 1), (2, 9, 7, 24, 40, 3, 2), (3, 8, 8, 16, 8, 1, 1), (2, 24, 24, 64, 136, 3, 1), (4, 48, 48, 192, 768, 1, 1),
-    (2, 13, 11, 264, 72, 3, 1)])
-def test_staged_mma_weight_gradient(b, h, w, cin, cout, k, stride):
-    """conv_wgrad_mma_kernel (ldmatrix.trans + mma.sync, FTC_WGRAD_MMA=1) against the oracle: bf16 operands, fp32 accumulation."""
-    from findtextcenternet_b200 import _ops
-    x = rnd(b, h, w, cin, seed=1).to(torch.bfloat16)
-    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
-    dy = rnd(b, ho, wo, cout, seed=3).to(torch.bfloat16)
-    dw = _ops.conv2d_wgrad(dev(x), dev(dy), k, stride)
-    assert rel_l2(dw.cpu(), TO.conv2d_wgrad(x.float(), dy.float(), k, stride)) < 2e-5
-
-
 def test_page_maps_on_device_match_reference_run_detector():
     """engine.page_maps (ftc_page_maps) == lines_all / seps_all of the unmodified reference run_detector (golden) and the
     oracle's seven maps."""
@@ -442,3 +428,27 @@ def test_part_predictors_on_device():
         assert rel_l2(probs[i].max(-1).values.cpu(), gold[f"pred_probs{i}_max"]) < 1e-3
         assert (probs[i].argmax(-1).cpu() == torch.from_numpy(gold[f"pred_probs{i}_argmax"])).float().mean() > 0.99
         assert rel_l2(split[i].cpu(), probs[i].cpu()) < 1e-5
+
+
+# keep this block LAST in the file (and the file last in the suite): if the staged kernel faulted, the CUDA context of the test
+# process would be unusable for whatever ran after it
+@pytest.mark.xfail(strict=False, reason="staged mma.sync weight-gradient kernel: written and emulated without GPU time, this is its "
+                                        "first hardware run (XPASS = it works and can become the default)")
+@pytest.mark.parametrize("b,h,w,cin,cout,k,stride", [
+    (2, 6, 5, 8, 16, 3, 1), (2, 9, 7, 24, 40, 3, 2), (3, 8, 8, 16, 8, 1, 1), (2, 24, 24, 64, 136, 3, 1), (4, 48, 48, 192, 768, 1, 1),
+    (2, 13, 11, 264, 72, 3, 1)])
+def test_staged_mma_weight_gradient(b, h, w, cin, cout, k, stride):
+    """conv_wgrad_mma_kernel (ldmatrix.trans + mma.sync, switched on through ftc_debug_set_wgrad_mma for this test only) against
+    the oracle: bf16 operands, fp32 accumulation."""
+    from findtextcenternet_b200 import _lib, _ops
+    x = rnd(b, h, w, cin, seed=1).to(torch.bfloat16)
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    dy = rnd(b, ho, wo, cout, seed=3).to(torch.bfloat16)
+    lib = _lib.load()
+    lib.ftc_debug_set_wgrad_mma(1)
+    try:
+        dw = _ops.conv2d_wgrad(dev(x), dev(dy), k, stride)
+        torch.cuda.synchronize()
+    finally:
+        lib.ftc_debug_set_wgrad_mma(-1)
+    assert rel_l2(dw.cpu(), TO.conv2d_wgrad(x.float(), dy.float(), k, stride)) < 2e-5

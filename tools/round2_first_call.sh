@@ -9,7 +9,7 @@ cd "${GRAFT_REPO_ROOT:-.}"
 timeout 200 python -m pytest tests/test_zz_gpu_train.py -q -m gpu --tb=short --durations=8 -p no:cacheprovider > gpurun_out/r2_train_tests.log 2>&1
 tail -15 gpurun_out/r2_train_tests.log
 # 2. the mma.sync weight-gradient kernel (off by default until this passes)
-FTC_WGRAD_MMA=1 timeout 120 python -m pytest tests/test_zz_gpu_train.py -q -m gpu -k "staged_mma or conv_wgrad or train_step_bf16" --tb=short -p no:cacheprovider \
+FTC_WGRAD_MMA=1 timeout 120 python -m pytest tests/test_zz_gpu_train.py -q -m gpu -k "staged_mma or conv_wgrad or train_step_bf16" -rxX --tb=short -p no:cacheprovider \
   > gpurun_out/r2_wgrad_mma_tests.log 2>&1
 tail -5 gpurun_out/r2_wgrad_mma_tests.log
 # 3. first train-step throughput numbers: CUDA-core wgrad vs mma.sync wgrad, small batch first (memory grows with batch)
