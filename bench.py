@@ -235,15 +235,18 @@ def run_ours(args):
                     if tj.get("batch") == B:
                         traffic, traffic_src = tj["dram_bytes_per_launch_avg"], "profiles/" + name
                     break
+            whole_tf = FLOP_PER_IMAGE * (value / world) / 1e12
             roofline = {
+                # lead figure: the WHOLE forward (865 GFLOP/image x images/s of one GPU) against both measured peaks
+                "whole_forward_tflops": whole_tf, "whole_forward_frac": whole_tf / peaks["bf16_sustained"],
+                "whole_forward_frac_burst": whole_tf / peaks["bf16_burst"],
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "frac": achieved / peaks["bf16_sustained"], "frac_burst": achieved / peaks["bf16_burst"],
+                "peak_burst": peaks["bf16_burst"], "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "conv_gemm_tma_kernel / conv_gemm_tc_kernel (tcgen05 implicit-GEMM conv, TMA or cp.async operand "
                           "staging), %d launches per forward" % n_gemm,
                 "flop_per_launch_avg": gemm_fl / max(n_gemm, 1), "ms_per_launch_avg": gemm_ms / max(n_gemm, 1),
                 "share_of_step": gemm_ms / all_ms, "peak_source": peaks["src"] + " bf16_tflops_sustained",
-                "whole_forward_tflops": FLOP_PER_IMAGE * (value / world) / 1e12,
-                "whole_forward_frac": FLOP_PER_IMAGE * (value / world) / 1e12 / peaks["bf16_sustained"],
                 "per_kind_ms": {names[k]: {"ms": round(v[0], 3), "tflops": (v[1] / (v[0] / 1e3) / 1e12 if v[0] > 0 else 0.0),
                                            "launches": v[2]} for k, v in sorted(by_kind.items())},
             }
@@ -271,6 +274,8 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
+    if world == 1 and not args.no_gpu_reference:
+        line["gpu_reference"] = gpu_reference_side_measurement(B, compile_too=args.gpu_reference_compile)
     if world == 1 and not args.no_train1:
         line["train1"] = train1_side_measurement()
         if "error" not in line["train1"]:
@@ -278,6 +283,28 @@ def run_ours(args):
             # loss trajectory next to the default path's is the first hardware evidence for or against it
             line["train1_wgrad_mma_staged"] = train1_side_measurement(env={"FTC_WGRAD_MMA": "1"})
     print(json.dumps(line), flush=True)
+
+
+def gpu_reference_side_measurement(batch: int, compile_too: bool = False, timeout_s: int = 420):
+    """The bar BASELINE.md section 3 names: the reference's math on THIS GPU through PyTorch's own kernels (cuDNN / cuBLAS, bf16
+    autocast, channels_last; eager, and torch.compile with --gpu-reference-compile), same batch, CUDA events, L2 flushed.  Child
+    process (tools/gpu_reference.py) with a hard timeout; a labelled side object, never the headline."""
+    try:
+        import torch
+        torch.cuda.empty_cache()
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "gpu_reference.py"), "detector", "--batch", str(batch), "--steps", "5", "--warmup", "3"]
+        if compile_too:
+            cmd.append("--compile")
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+        rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not rows:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        d = json.loads(rows[-1])
+        d["note"] = ("reference math (functional restatement pinned to the reference by tests/golden) executed by torch library kernels "
+                     "on the same GPU, bf16 autocast; the number the hand-written path has to beat")
+        return d
+    except Exception as e:
+        return {"error": repr(e)[:300]}
 
 
 def train1_side_measurement(batch: int = 4, timeout_s: int = 200, env=None):
@@ -312,6 +339,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16_simt", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train1", action="store_true", help="skip the auxiliary train1-step measurement (N = 1 only)")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the same-GPU torch (cuDNN eager) reference measurement")
+    ap.add_argument("--gpu-reference-compile", action="store_true", help="also time the torch.compile'd reference math (minutes)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

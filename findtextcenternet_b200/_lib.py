@@ -83,12 +83,14 @@ SYMBOLS = {
     "ftc_heatmap_loss_grad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ftc_ce_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "ftc_ce_rows_grad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
-    "ftc_peak_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ftc_peak_decode_scratch_bytes": (_sz, [_i, _i, _i]),
+    "ftc_peak_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ftc_peak_pick": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ftc_op_conv2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "ftc_op_conv2d_wpack_bytes": (_sz, [_i, _i, _i]),
     "ftc_op_dwconv3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "ftc_op_se_fc": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "ftc_op_dwconv3x3_tiles": (_i, [_i, _i, _i, _i]),
+    "ftc_op_se_fc": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "ftc_debug_set_trace": (_i, [_vp]),
     "ftc_debug_set_gemm_tuning": (_i, [_i, _i, _i, _i, _i]),
     "ftc_debug_bench_gemm": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float)]),

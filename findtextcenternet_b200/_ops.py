@@ -47,26 +47,36 @@ def conv2d(x: torch.Tensor, w_oihw: torch.Tensor, stride: int = 1, scale=None, b
 
 
 def dwconv3x3(x: torch.Tensor, w9c: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, stride: int = 1,
-              se_sum: Optional[torch.Tensor] = None) -> torch.Tensor:
+              want_se_sum: bool = False):
+    """Depthwise 3x3 + BN + SiLU.  With ``want_se_sum`` also the per-tile spatial sums [B, tiles, C] fp32 (the SE squeeze,
+    written without atomics; ``se_fc`` adds the tiles in order) -> (out, se_parts)."""
     lib = _lib.load()
     b, h, w, c = x.shape
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
     out = torch.empty(b, ho, wo, c, dtype=x.dtype, device=x.device)
+    parts = None
+    if want_se_sum:
+        nt = int(lib.ftc_op_dwconv3x3_tiles(h, w, stride, _dt(x)))
+        parts = torch.empty(b, nt, c, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(lib.ftc_op_dwconv3x3(x.data_ptr(), out.data_ptr(), _dt(x), b, h, w, c, stride, w9c.data_ptr(),
-                                        scale.data_ptr(), bias.data_ptr(), _p(se_sum), _s(x)), "ftc_op_dwconv3x3")
-    return out
+                                        scale.data_ptr(), bias.data_ptr(), _p(parts), _s(x)), "ftc_op_dwconv3x3")
+    return (out, parts) if want_se_sum else out
 
 
-def se_fc(se_sum: torch.Tensor, inv_hw: float, w1, b1, w2t, b2) -> torch.Tensor:
+def se_fc(se_parts: torch.Tensor, inv_hw: float, w1, b1, w2t, b2) -> torch.Tensor:
+    """se_parts fp32 [B, tiles, C] (or [B, C]) spatial sums -> SE gate [B, C]."""
     lib = _lib.load()
-    b, c = se_sum.shape
+    if se_parts.dim() == 2:
+        se_parts = se_parts[:, None]
+    se_parts = se_parts.contiguous()
+    b, nt, c = se_parts.shape
     s = w1.shape[0]
-    out = torch.empty(b, c, dtype=torch.float32, device=se_sum.device)
-    hid = torch.empty(b, s, dtype=torch.float32, device=se_sum.device)
-    with torch.cuda.device(se_sum.device):
-        _lib.check(lib.ftc_op_se_fc(se_sum.data_ptr(), out.data_ptr(), hid.data_ptr(), b, c, s, inv_hw, w1.data_ptr(), b1.data_ptr(),
-                                    w2t.data_ptr(), b2.data_ptr(), _s(se_sum)), "ftc_op_se_fc")
+    out = torch.empty(b, c, dtype=torch.float32, device=se_parts.device)
+    hid = torch.empty(b, s, dtype=torch.float32, device=se_parts.device)
+    with torch.cuda.device(se_parts.device):
+        _lib.check(lib.ftc_op_se_fc(se_parts.data_ptr(), nt, out.data_ptr(), hid.data_ptr(), b, c, s, inv_hw, w1.data_ptr(),
+                                    b1.data_ptr(), w2t.data_ptr(), b2.data_ptr(), _s(se_parts)), "ftc_op_se_fc")
     return out
 
 
@@ -94,7 +104,7 @@ def dwconv3x3_se(x: torch.Tensor, w9c, scale, bias, w1, b1, w2t, b2):
     b, h, w, c = x.shape
     s = w1.shape[0]
     out = torch.empty_like(x)
-    hid = torch.zeros(b, s, dtype=torch.float32, device=x.device)
+    hid = torch.empty(b, c // 32, s, dtype=torch.float32, device=x.device)    # one fc1 share per 32-channel CTA
     sc = torch.empty(b, c, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(lib.ftc_op_dwconv3x3_se(x.data_ptr(), out.data_ptr(), _dt(x), b, h, w, c, w9c.data_ptr(), scale.data_ptr(),

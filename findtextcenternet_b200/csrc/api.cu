@@ -52,11 +52,13 @@ int ftc_version(void) { return 100; }
 const char* ftc_last_error(void) { return g_err.c_str(); }
 int64_t ftc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+size_t ftc_peak_decode_scratch_bytes(int batch, int h, int w) { return peak_decode_scratch_bytes(batch, h, w); }
+
 int ftc_peak_decode(const float* heat9, const float* feat, int batch, int h, int w, int feat_ch, const int* tile_meta,
-                    float cut_off, float page_w, float page_h, int max_peaks, int* count, float* loc, float* gfeat,
+                    float cut_off, float page_w, float page_h, int max_peaks, int* count, int* total, float* loc, float* gfeat,
                     void* scratch, void* stream) {
-  FTC_REQUIRE(heat9 && feat && tile_meta && count && loc && gfeat && scratch && batch > 0, "bad argument");
-  return peak_decode(heat9, feat, batch, h, w, feat_ch, tile_meta, cut_off, page_w, page_h, max_peaks, count, loc, gfeat,
+  FTC_REQUIRE(heat9 && feat && tile_meta && count && total && loc && gfeat && scratch && batch > 0, "bad argument");
+  return peak_decode(heat9, feat, batch, h, w, feat_ch, tile_meta, cut_off, page_w, page_h, max_peaks, count, total, loc, gfeat,
                      scratch, (cudaStream_t)stream);
 }
 
@@ -132,10 +134,12 @@ int ftc_op_dwconv3x3(const void* x, void* out, int dtype, int batch, int h, int 
   return dwconv3x3(x, out, dtype, batch, h, w, c, stride, w9c, scale, bias, se_sum, (cudaStream_t)stream);
 }
 
-int ftc_op_se_fc(float* sum, float* scale_out, float* hid, int batch, int c, int s, float inv_hw, const float* w1,
+int ftc_op_dwconv3x3_tiles(int h, int w, int stride, int dtype) { return dwconv3x3_tiles(h, w, stride, dtype); }
+
+int ftc_op_se_fc(const float* sum, int tiles, float* scale_out, float* hid, int batch, int c, int s, float inv_hw, const float* w1,
                  const float* b1, const float* w2t, const float* b2, void* stream) {
-  FTC_REQUIRE(sum && scale_out && hid && w1 && b1 && w2t && b2, "null argument");
-  return se_fc(sum, scale_out, hid, batch, c, s, inv_hw, w1, b1, w2t, b2, (cudaStream_t)stream);
+  FTC_REQUIRE(sum && scale_out && hid && w1 && b1 && w2t && b2 && tiles >= 1, "null argument");
+  return se_fc(sum, tiles, scale_out, hid, batch, c, s, inv_hw, w1, b1, w2t, b2, (cudaStream_t)stream);
 }
 
 int ftc_mask_predict_step(const float* logits, int ld, int head_ld, const int64_t* dec_in, int64_t* ids, float* prob,
@@ -229,13 +233,12 @@ int ftc_debug_set_trace(void* dev_u64_4096) {
 
 int ftc_op_dwconv3x3_se(const void* x, void* out, int dtype, int batch, int h, int w, int c, const float* w9c,
                         const float* scale, const float* bias, const float* w1, const float* b1, const float* w2t,
-                        const float* b2, int s, float* hid_pre, float* scale_out, void* stream) {
-  FTC_REQUIRE(x && out && w9c && scale && bias && w1 && b1 && w2t && b2 && hid_pre && scale_out, "null argument");
+                        const float* b2, int s, float* hid_part, float* scale_out, void* stream) {
+  FTC_REQUIRE(x && out && w9c && scale && bias && w1 && b1 && w2t && b2 && hid_part && scale_out, "null argument");
   FTC_REQUIRE(dwconv3x3_se_supported(h, w, c, 1), "dwconv3x3_se: unsupported geometry");
-  int rc = dwconv3x3_se(x, out, dtype, batch, h, w, c, w9c, scale, bias, w1, s, hid_pre, (cudaStream_t)stream);
+  int rc = dwconv3x3_se(x, out, dtype, batch, h, w, c, w9c, scale, bias, w1, s, hid_part, (cudaStream_t)stream);
   if (rc) return rc;
-  // fc2 reads hid_pre; the "other parity" accumulator it clears is not used here: clear nothing (clear_n = 0)
-  return se_fc2_hid(hid_pre, hid_pre, 0, scale_out, batch, c, s, b1, w2t, b2, (cudaStream_t)stream);
+  return se_fc2_hid(hid_part, c / 32, scale_out, batch, c, s, b1, w2t, b2, (cudaStream_t)stream);
 }
 
 int ftc_op_head_top_conv(const void* y, int dtype, int pix_stride, int n_heads, const int* od, const float* w,

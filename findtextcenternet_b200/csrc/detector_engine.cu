@@ -59,7 +59,7 @@ struct Op {
   int bufIn = BUF_NONE, bufOut = BUF_NONE, C = 0, H = 0, W = 0, stride = 1, S = 0;
   size_t w_off = 0, scale_off = 0, bias_off = 0, w2_off = 0, b1_off = 0, b2_off = 0;
   bool fused_se = false;             // DW: squeeze + fc1 folded into the depthwise kernel (w1 at se_w1_off); SE: fc2 only
-  int parity = 0;                    // which of the two hid_pre accumulators this block uses
+  int parity = 0;                    // unfused SE: number of spatial tiles (partial sums) of the depthwise kernel
   size_t se_w1_off = 0;
 };
 
@@ -76,6 +76,7 @@ struct ftc_detector {
   std::vector<Op> ops;
   size_t buf_elems[BUF_COUNT] = {0};   // per image
   size_t se_c_max = 0;
+  size_t se_part_max = 1, se_hid_part_max = 1;   // floats per image: unfused tile partial sums / fused fc1 shares
   size_t weight_bytes = 0;
   size_t scratch_off = 0;              // packing scratch (floats) inside the packed buffer
   std::vector<std::function<int(const Lookup&, char*, cudaStream_t)>> pack_tasks;
@@ -213,7 +214,10 @@ int ftc_detector::build() {
         add_conv_bn(p + ".0", cur, BUF_E, cin, exp, H, W, 1, 1, ACT_SILU, BUF_NONE, false, EPS_BB);
         const bool fused_se = dwconv3x3_se_supported(H, W, exp, stride) && !getenv("FTC_NO_DW_STRIP");
         const size_t se_w1_off = walloc((size_t)sq * exp * 4);
-        const int parity = fused_se ? (n_fused_se++ & 1) : 0;
+        // unfused depthwise kernel: `parity` carries its spatial tile count (se_fc1 adds that many partial sums in order)
+        const int parity = fused_se ? 0 : dwconv3x3_tiles(H, W, stride, dtype);
+        if (fused_se) { if ((size_t)(exp / 32) * sq > se_hid_part_max) se_hid_part_max = (size_t)(exp / 32) * sq; }
+        else if ((size_t)parity * exp > se_part_max) se_part_max = (size_t)parity * exp;
         {
           Op op; op.type = Op::DW; op.bufIn = BUF_E; op.bufOut = BUF_D; op.C = exp; op.H = H; op.W = W; op.stride = stride;
           op.fused_se = fused_se; op.parity = parity; op.se_w1_off = se_w1_off; op.S = sq;
@@ -429,12 +433,12 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
   char* bufp[BUF_COUNT];
   size_t off = 0;
   for (int i = 0; i < BUF_COUNT; ++i) { bufp[i] = ws + off; off += align_up(d->buf_elems[i] * B * d->esize, 256); }
-  float* se_sum = (float*)(ws + off); off += align_up(d->se_c_max * B * 4, 256);
+  // SE scratch: every entry a kernel reads was written by the producing kernel of the same block (no accumulators to zero, no
+  // atomics: the squeeze is bit-reproducible and independent of the batch size)
+  float* se_sum = (float*)(ws + off); off += align_up(d->se_part_max * B * 4, 256);     // [B][tiles][C] partial sums (unfused path)
   float* se_scale = (float*)(ws + off); off += align_up(d->se_c_max * B * 4, 256);
   float* se_hid = (float*)(ws + off); off += align_up((size_t)256 * B * 4, 256);
-  float* se_hid2 = (float*)(ws + off); off += align_up((size_t)2 * 256 * B * 4, 256);   // two fc1 accumulators (block parity)
-  FTC_CHECK_CUDA(cudaMemsetAsync(se_sum, 0, d->se_c_max * B * 4, s));
-  FTC_CHECK_CUDA(cudaMemsetAsync(se_hid2, 0, (size_t)2 * 256 * B * 4, s));
+  float* se_hid2 = (float*)(ws + off); off += align_up(d->se_hid_part_max * B * 4, 256);  // [B][C/32][S] fc1 shares (fused path)
   auto bp = [&](int id) -> void* {
     if (id == BUF_NONE) return nullptr;
     if (id == BUF_EXT_HEAT9) return heat9;
@@ -456,17 +460,17 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
         if (op.fused_se)
           rc = dwconv3x3_se(bp(op.bufIn), bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, (const float*)(P + op.w_off),
                             (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), (const float*)(P + op.se_w1_off),
-                            op.S, se_hid2 + (size_t)op.parity * 256 * B, s);
+                            op.S, se_hid2, s);
         else
           rc = dwconv3x3(bp(op.bufIn), bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, op.stride, (const float*)(P + op.w_off),
                          (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), se_sum, s);
         break;
       case Op::SE:
         if (op.fused_se)
-          rc = se_fc2_hid(se_hid2 + (size_t)op.parity * 256 * B, se_hid2 + (size_t)(op.parity ^ 1) * 256 * B, 256, se_scale, B, op.C,
+          rc = se_fc2_hid(se_hid2, op.C / 32, se_scale, B, op.C,
                           op.S, (const float*)(P + op.b1_off), (const float*)(P + op.w2_off), (const float*)(P + op.b2_off), s);
         else
-          rc = se_fc(se_sum, se_scale, se_hid, B, op.C, op.S, 1.0f / (float)(op.H * op.W), (const float*)(P + op.w_off),
+          rc = se_fc(se_sum, op.parity /* = tile count of the depthwise kernel */, se_scale, se_hid, B, op.C, op.S, 1.0f / (float)(op.H * op.W), (const float*)(P + op.w_off),
                      (const float*)(P + op.b1_off), (const float*)(P + op.w2_off), (const float*)(P + op.b2_off), s);
         break;
       case Op::TOPS:
@@ -529,7 +533,8 @@ size_t ftc_detector_workspace_bytes(const ftc_detector* d, int batch) {
   if (!d) return 0;
   size_t off = 0;
   for (int i = 0; i < BUF_COUNT; ++i) off += align_up(d->buf_elems[i] * batch * d->esize, 256);
-  off += 2 * align_up(d->se_c_max * batch * 4, 256) + align_up((size_t)256 * batch * 4, 256) + align_up((size_t)2 * 256 * batch * 4, 256);
+  off += align_up(d->se_part_max * batch * 4, 256) + align_up(d->se_c_max * batch * 4, 256) + align_up((size_t)256 * batch * 4, 256) +
+         align_up(d->se_hid_part_max * batch * 4, 256);
   return off + 256;
 }
 

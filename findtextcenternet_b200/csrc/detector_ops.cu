@@ -212,8 +212,30 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T* __restrict__ in
     float t = 0.f;
     for (int q = 0; q < TW; ++q) t += red[q * 64 + tid];
     const int c = cb + tid;
-    if (c < C) atomicAdd(&se_sum[(int64_t)b * C + c], t);
+    // per-tile partial (no atomics: the squeeze must not depend on the CTA schedule); se_fc1 adds the tiles in order
+    if (c < C) se_sum[((int64_t)b * gridDim.x + blockIdx.x) * C + c] = t;
   }
+}
+
+static void dwconv3x3_tiling(int Ho, int Wo, int stride, size_t es, int* TWo, int* THo, size_t* smemo) {
+  // one thread per (output column, channel quad): TW columns x 16 quads = block size; tall tiles amortise the window
+  int TW = (Wo % 16 == 0) ? 16 : 8;
+  int TH = (Ho % 24 == 0) ? 24 : ((Ho % 16 == 0) ? 16 : 8);
+  size_t smem;
+  for (;;) {
+    const int IH = (TH - 1) * stride + 3, IW = (TW - 1) * stride + 3;
+    smem = align_up((size_t)IH * IW * 64 * es, 16) + (size_t)TW * 64 * sizeof(float);
+    if (smem <= 72 * 1024 || TH <= 4) break;                   // keep >= 3 CTAs per SM
+    TH /= 2;
+  }
+  *TWo = TW; *THo = TH; *smemo = smem;
+}
+
+int dwconv3x3_tiles(int H, int W, int stride, int dtype) {
+  int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1, TW, TH;
+  size_t smem;
+  dwconv3x3_tiling(Ho, Wo, stride, dtype == DT_F32 ? 4 : 2, &TW, &TH, &smem);
+  return ceil_div(Wo, TW) * ceil_div(Ho, TH);
 }
 
 int dwconv3x3(const void* in, void* out, int dtype, int B, int H, int W, int C, int stride, const float* w,
@@ -221,18 +243,10 @@ int dwconv3x3(const void* in, void* out, int dtype, int B, int H, int W, int C, 
   FTC_REQUIRE(C % 8 == 0, "depthwise channels must be a multiple of 8");
   FTC_REQUIRE(stride == 1 || stride == 2, "depthwise stride must be 1 or 2");
   int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;   // k=3, pad=1
-  // one thread per (output column, channel quad): TW columns x 16 quads = block size; tall tiles amortise the window
-  int TW = (Wo % 16 == 0) ? 16 : 8;
-  int TH = (Ho % 24 == 0) ? 24 : ((Ho % 16 == 0) ? 16 : 8);
   const size_t es = dtype == DT_F32 ? 4 : 2;
-  int IH, IW;
+  int TW, TH;
   size_t smem;
-  for (;;) {
-    IH = (TH - 1) * stride + 3; IW = (TW - 1) * stride + 3;
-    smem = align_up((size_t)IH * IW * 64 * es, 16) + (size_t)TW * 64 * sizeof(float);
-    if (smem <= 72 * 1024 || TH <= 4) break;                   // keep >= 3 CTAs per SM
-    TH /= 2;
-  }
+  dwconv3x3_tiling(Ho, Wo, stride, es, &TW, &TH, &smem);
   const int tiles_x = ceil_div(Wo, TW), tiles_y = ceil_div(Ho, TH);
   dim3 grid(tiles_x * tiles_y, ceil_div(C, 64), B);
   const int threads = TW * 16;
@@ -391,7 +405,7 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
       const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + c));
       t = fmaf(wv.x, mean[c], t); t = fmaf(wv.y, mean[c + 1], t); t = fmaf(wv.z, mean[c + 2], t); t = fmaf(wv.w, mean[c + 3], t);
     }
-    atomicAdd(&hid_pre[(int64_t)b * S + sidx], t);
+    hid_pre[((int64_t)b * gridDim.x + blockIdx.x) * S + sidx] = t;   // this CTA's 32-channel share (summed in order by se_fc2_hid)
   }
 }
 
@@ -563,7 +577,7 @@ __global__ void __launch_bounds__(512, 2) dwconv3x3_strip_mma_kernel(const bf16*
       const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + c));
       t = fmaf(wv.x, mean[c], t); t = fmaf(wv.y, mean[c + 1], t); t = fmaf(wv.z, mean[c + 2], t); t = fmaf(wv.w, mean[c + 3], t);
     }
-    atomicAdd(&hid_pre[(int64_t)b * S + sidx], t);
+    hid_pre[((int64_t)b * gridDim.x + blockIdx.x) * S + sidx] = t;   // this CTA's 32-channel share (summed in order by se_fc2_hid)
   }
 }
 
@@ -628,19 +642,36 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
   return 0;
 }
 
-// second half of SE for the folded path: scale[b,c] = sigmoid(b2[c] + w2t[:,c] . silu(hid_pre[b,:] + b1)); clears the
-// OTHER layer-parity accumulator (nobody reads it any more) so that the next block finds zeros
-__global__ void __launch_bounds__(256) se_fc2_hid_kernel(const float* __restrict__ hid_pre, float* __restrict__ hid_clear,
-                                                         float* __restrict__ scale_out, int C, int S, int clear_n,
+// second half of SE for the folded path: scale[b,c] = sigmoid(b2[c] + w2t[:,c] . silu(sum_g hid_part[b,g,:] + b1)).
+// hid_part [B][G][S] holds one fc1 share per depthwise CTA (G = C / 32 channel groups); the shares are added in a FIXED
+// order (P interleaved partial sums over g, combined in order), so the excitation is bit-reproducible run to run and
+// independent of the batch size -- near-tied peak scores downstream must not depend on the CTA schedule.
+__global__ void __launch_bounds__(256) se_fc2_hid_kernel(const float* __restrict__ hid_part, int G,
+                                                         float* __restrict__ scale_out, int C, int S,
                                                          const float* __restrict__ b1, const float* __restrict__ w2t,
                                                          const float* __restrict__ b2) {
   __shared__ float sh[256];
+  __shared__ float part[256];
   const int b = blockIdx.y;
   pdl_launch_dependents();
   pdl_wait();
-  for (int k = threadIdx.x; k < S; k += blockDim.x) sh[k] = silu_precise(hid_pre[(int64_t)b * S + k] + b1[k]);
-  if (blockIdx.x == 0)
-    for (int k = threadIdx.x; k < clear_n; k += blockDim.x) hid_clear[(int64_t)b * clear_n + k] = 0.f;
+  const int P = 256 / S > 0 ? 256 / S : 1;              // partial sums per squeeze unit (S <= 256)
+  {
+    const int k = threadIdx.x % S, pi = threadIdx.x / S;
+    if (pi < P) {
+      const float* hp = hid_part + (int64_t)b * G * S + k;
+      float t = 0.f;
+#pragma unroll 4
+      for (int g = pi; g < G; g += P) t += hp[(int64_t)g * S];
+      part[pi * S + k] = t;
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < S; k += blockDim.x) {
+    float t = part[k];
+    for (int pi = 1; pi < P; ++pi) t += part[pi * S + k];
+    sh[k] = silu_precise(t + b1[k]);
+  }
   __syncthreads();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -650,10 +681,10 @@ __global__ void __launch_bounds__(256) se_fc2_hid_kernel(const float* __restrict
   scale_out[(int64_t)b * C + c] = sigmoid_precise(t);
 }
 
-int se_fc2_hid(const float* hid_pre, float* hid_clear, int clear_n, float* scale_out, int B, int C, int S, const float* b1,
-               const float* w2t, const float* b2, cudaStream_t s) {
-  FTC_REQUIRE(S <= 256 && clear_n <= 256, "SE: squeeze <= 256");
-  FTC_CHECK_CUDA(launch_pdl(se_fc2_hid_kernel, dim3(ceil_div(C, 256), B), dim3(256), 0, s, hid_pre, hid_clear, scale_out, C, S, clear_n, b1, w2t, b2));
+int se_fc2_hid(const float* hid_part, int G, float* scale_out, int B, int C, int S, const float* b1, const float* w2t,
+               const float* b2, cudaStream_t s) {
+  FTC_REQUIRE(S <= 256 && S > 0 && G > 0, "SE: squeeze <= 256");
+  FTC_CHECK_CUDA(launch_pdl(se_fc2_hid_kernel, dim3(ceil_div(C, 256), B), dim3(256), 0, s, hid_part, G, scale_out, C, S, b1, w2t, b2));
   FTC_POST_LAUNCH();
   return 0;
 }
@@ -661,19 +692,24 @@ int se_fc2_hid(const float* hid_pre, float* hid_clear, int clear_n, float* scale
 // ------------------------------------------------------------------------------------------------
 // SE excitation in two small grid-filling kernels (one block per image was latency-bound: 0.22 ms per layer):
 //   fc1: one warp per (image, squeeze unit)   hid[b,s] = silu(b1[s] + w1[s,:] . mean[b,:])
-//   fc2: one thread per (image, channel)      scale[b,c] = sigmoid(b2[c] + w2t[:,c] . hid[b,:]); re-arms sum[b,c] = 0
-__global__ void __launch_bounds__(256) se_fc1_kernel(const float* __restrict__ sum, float* __restrict__ hid, int C, int S,
+//   fc2: one thread per (image, channel)      scale[b,c] = sigmoid(b2[c] + w2t[:,c] . hid[b,:])
+// sum: [B][nt][C] per-tile partial sums of the depthwise kernel, added tile by tile in order (deterministic)
+__global__ void __launch_bounds__(256) se_fc1_kernel(const float* __restrict__ sum, int nt, float* __restrict__ hid, int C, int S,
                                                      float inv_hw, const float* __restrict__ w1,
                                                      const float* __restrict__ b1) {
   const int b = blockIdx.y;
   const int sidx = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (sidx >= S) return;
   const float* wr = w1 + (int64_t)sidx * C;
-  const float* sp = sum + (int64_t)b * C;
+  const float* sp = sum + (int64_t)b * nt * C;
   float t = 0.f;
   for (int c = lane * 4; c < C; c += 128) {
     float4 w = *reinterpret_cast<const float4*>(wr + c);
     float4 m = *reinterpret_cast<const float4*>(sp + c);
+    for (int q = 1; q < nt; ++q) {
+      const float4 m2 = *reinterpret_cast<const float4*>(sp + (int64_t)q * C + c);
+      m.x += m2.x; m.y += m2.y; m.z += m2.z; m.w += m2.w;
+    }
     t = fmaf(w.x, m.x * inv_hw, t); t = fmaf(w.y, m.y * inv_hw, t);
     t = fmaf(w.z, m.z * inv_hw, t); t = fmaf(w.w, m.w * inv_hw, t);
   }
@@ -682,7 +718,7 @@ __global__ void __launch_bounds__(256) se_fc1_kernel(const float* __restrict__ s
   if (lane == 0) hid[(int64_t)b * S + sidx] = silu_precise(t + b1[sidx]);
 }
 
-__global__ void __launch_bounds__(256) se_fc2_kernel(float* __restrict__ sum, const float* __restrict__ hid,
+__global__ void __launch_bounds__(256) se_fc2_kernel(const float* __restrict__ hid,
                                                      float* __restrict__ scale_out, int C, int S,
                                                      const float* __restrict__ w2t, const float* __restrict__ b2) {
   __shared__ float sh[256];
@@ -694,15 +730,14 @@ __global__ void __launch_bounds__(256) se_fc2_kernel(float* __restrict__ sum, co
   float t = b2[c];
   for (int k = 0; k < S; ++k) t = fmaf(w2t[(int64_t)k * C + c], sh[k], t);
   scale_out[(int64_t)b * C + c] = sigmoid_precise(t);
-  sum[(int64_t)b * C + c] = 0.f;
 }
 
-int se_fc(float* sum, float* scale_out, float* hid, int B, int C, int S, float inv_hw, const float* w1, const float* b1,
+int se_fc(const float* sum, int nt, float* scale_out, float* hid, int B, int C, int S, float inv_hw, const float* w1, const float* b1,
           const float* w2t, const float* b2, cudaStream_t s) {
-  FTC_REQUIRE(S <= 256 && C % 4 == 0, "SE: squeeze <= 256 and channels % 4 == 0");
-  se_fc1_kernel<<<dim3(ceil_div(S, 8), B), 256, 0, s>>>(sum, hid, C, S, inv_hw, w1, b1);
+  FTC_REQUIRE(S <= 256 && C % 4 == 0 && nt >= 1, "SE: squeeze <= 256 and channels % 4 == 0");
+  se_fc1_kernel<<<dim3(ceil_div(S, 8), B), 256, 0, s>>>(sum, nt, hid, C, S, inv_hw, w1, b1);
   FTC_POST_LAUNCH();
-  se_fc2_kernel<<<dim3(ceil_div(C, 256), B), 256, 0, s>>>(sum, hid, scale_out, C, S, w2t, b2);
+  se_fc2_kernel<<<dim3(ceil_div(C, 256), B), 256, 0, s>>>(hid, scale_out, C, S, w2t, b2);
   FTC_POST_LAUNCH();
   return 0;
 }
@@ -1032,10 +1067,12 @@ int peak_pick(const float* heat9, float* heat10, int B, int H, int W, cudaStream
 // peak compaction + box decode
 __device__ __forceinline__ float np_sigmoid(float x) { return (tanhf(x * 0.5f) + 1.0f) * 0.5f; }   // util_func.py:14
 
+// candidates of tile b go to cand[b][0 .. total[b]) in arbitrary order (slot = atomic counter); the buffer holds one key per map
+// pixel, so nothing is ever dropped here, and peak_emit sorts by the key -- the RESULT does not depend on the slot order.
 __global__ void __launch_bounds__(256) peak_collect_kernel(const float* __restrict__ heat9, int H, int W,
                                                            const int* __restrict__ tile_meta, float cut_off,
-                                                           float page_w, float page_h, int max_peaks,
-                                                           int* __restrict__ count, unsigned long long* __restrict__ cand) {
+                                                           float page_w, float page_h,
+                                                           int* __restrict__ total, unsigned long long* __restrict__ cand) {
   const int b = blockIdx.y;
   const int hw = H * W;
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1052,23 +1089,51 @@ __global__ void __launch_bounds__(256) peak_collect_kernel(const float* __restri
   float h = expf(h9[2 * hw + r] - 3.f) * 1024.f;
   if (w <= 0.f || h <= 0.f) return;
   if (w > page_w || h > page_h) return;
-  int slot = atomicAdd(&count[b], 1);
-  if (slot < max_peaks)
-    cand[(int64_t)b * max_peaks + slot] =
-        ((unsigned long long)__float_as_uint(p) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+  int slot = atomicAdd(&total[b], 1);
+  cand[(int64_t)b * hw + slot] =
+      ((unsigned long long)__float_as_uint(p) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
 }
 
 template <int NMAX>
 __global__ void __launch_bounds__(1024) peak_emit_kernel(const float* __restrict__ heat9, const float* __restrict__ feat,
                                                          int H, int W, int FC, const int* __restrict__ tile_meta,
-                                                         int max_peaks, int* __restrict__ count,
+                                                         int max_peaks, int* __restrict__ count, const int* __restrict__ total,
                                                          const unsigned long long* __restrict__ cand,
                                                          float* __restrict__ loc, float* __restrict__ gfeat) {
   __shared__ unsigned long long keys[NMAX];
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_thr;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int hw = H * W;
-  int n = min(count[b], max_peaks);
-  for (int i = tid; i < NMAX; i += blockDim.x) keys[i] = (i < n) ? cand[(int64_t)b * max_peaks + i] : 0ull;
+  const int ntot = total[b];
+  const int n = min(ntot, max_peaks);
+  const unsigned long long* cb = cand + (int64_t)b * hw;
+  if (ntot <= NMAX) {
+    for (int i = tid; i < NMAX; i += blockDim.x) keys[i] = (i < ntot) ? cb[i] : 0ull;
+  } else {
+    // overflow: keep the NMAX largest keys.  Keys are distinct (the pixel index is part of the key), so the NMAX-th largest
+    // key T is found bit by bit from the top -- T = max { t : #(key >= t) >= NMAX } -- and exactly NMAX keys are >= T.
+    unsigned long long thr = 0ull;
+    for (int bit = 63; bit >= 0; --bit) {
+      const unsigned long long trial = thr | (1ull << bit);
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      int c = 0;
+      for (int i = tid; i < ntot; i += blockDim.x) c += (cb[i] >= trial) ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if ((tid & 31) == 0 && c) atomicAdd(&s_cnt, c);
+      __syncthreads();
+      if (s_cnt >= NMAX) thr = trial;
+      __syncthreads();
+    }
+    if (tid == 0) { s_cnt = 0; s_thr = thr; }
+    __syncthreads();
+    for (int i = tid; i < ntot; i += blockDim.x) {
+      const unsigned long long kk = cb[i];
+      if (kk >= s_thr) keys[atomicAdd(&s_cnt, 1)] = kk;      // slot order is irrelevant: sorted below
+    }
+  }
   __syncthreads();
   // bitonic sort, descending
   for (int k = 2; k <= NMAX; k <<= 1)
@@ -1108,21 +1173,23 @@ __global__ void __launch_bounds__(1024) peak_emit_kernel(const float* __restrict
   if (tid == 0) count[b] = n;
 }
 
+size_t peak_decode_scratch_bytes(int B, int H, int W) { return (size_t)B * H * W * sizeof(unsigned long long); }
+
 int peak_decode(const float* heat9, const float* feat, int B, int H, int W, int FC, const int* tile_meta, float cut_off,
-                float page_w, float page_h, int max_peaks, int* count, float* loc, float* gfeat, void* scratch,
+                float page_w, float page_h, int max_peaks, int* count, int* total, float* loc, float* gfeat, void* scratch,
                 cudaStream_t s) {
   FTC_REQUIRE(max_peaks == 1024 || max_peaks == 2048 || max_peaks == 4096, "max_peaks must be 1024/2048/4096");
-  FTC_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * B, s));
-  unsigned long long* cand = reinterpret_cast<unsigned long long*>(scratch);   // [B][max_peaks]
+  FTC_CHECK_CUDA(cudaMemsetAsync(total, 0, sizeof(int) * B, s));
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(scratch);   // [B][H*W]
   dim3 grid(ceil_div(H * W, 256), B);
-  peak_collect_kernel<<<grid, 256, 0, s>>>(heat9, H, W, tile_meta, cut_off, page_w, page_h, max_peaks, count, cand);
+  peak_collect_kernel<<<grid, 256, 0, s>>>(heat9, H, W, tile_meta, cut_off, page_w, page_h, total, cand);
   FTC_POST_LAUNCH();
   if (max_peaks == 1024)
-    peak_emit_kernel<1024><<<B, 1024, 0, s>>>(heat9, feat, H, W, FC, tile_meta, max_peaks, count, cand, loc, gfeat);
+    peak_emit_kernel<1024><<<B, 1024, 0, s>>>(heat9, feat, H, W, FC, tile_meta, max_peaks, count, total, cand, loc, gfeat);
   else if (max_peaks == 2048)
-    peak_emit_kernel<2048><<<B, 1024, 0, s>>>(heat9, feat, H, W, FC, tile_meta, max_peaks, count, cand, loc, gfeat);
+    peak_emit_kernel<2048><<<B, 1024, 0, s>>>(heat9, feat, H, W, FC, tile_meta, max_peaks, count, total, cand, loc, gfeat);
   else
-    peak_emit_kernel<4096><<<B, 1024, 0, s>>>(heat9, feat, H, W, FC, tile_meta, max_peaks, count, cand, loc, gfeat);
+    peak_emit_kernel<4096><<<B, 1024, 0, s>>>(heat9, feat, H, W, FC, tile_meta, max_peaks, count, total, cand, loc, gfeat);
   FTC_POST_LAUNCH();
   return 0;
 }

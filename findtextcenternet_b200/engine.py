@@ -150,8 +150,9 @@ def peak_decode(heat9: torch.Tensor, feat: torch.Tensor, tile_meta: torch.Tensor
     """Per-tile peak compaction + box decode on the device (process_ocr_base.py:498-538).
 
     heat9 [B,9,h,w] fp32, feat [B,F,h,w] fp32, tile_meta int32 [B,6] = (offset_x, offset_y, mask x_min, x_max, y_min,
-    y_max).  Returns (count int32 [B], loc fp32 [B,max_peaks,9], gfeat fp32 [B,max_peaks,F]); rows beyond count[b] are
-    unspecified.  Peaks are ordered by descending score, ties by ascending flat index."""
+    y_max).  Returns (count int32 [B], loc fp32 [B,max_peaks,9], gfeat fp32 [B,max_peaks,F], total int32 [B]); rows beyond
+    count[b] are unspecified.  Peaks are ordered by descending score, ties by ascending flat index.  total[b] is the number of
+    peaks the reference loop keeps (it has no cap); if total[b] > max_peaks the max_peaks highest-scoring ones are returned."""
     lib = _lib.load()
     if not (heat9.is_cuda and feat.is_cuda and tile_meta.is_cuda):
         raise RuntimeError("peak_decode needs CUDA tensors (no CPU path)")
@@ -164,12 +165,13 @@ def peak_decode(heat9: torch.Tensor, feat: torch.Tensor, tile_meta: torch.Tensor
     count = torch.empty(b, dtype=torch.int32, device=dev)
     loc = torch.empty(b, max_peaks, 9, dtype=torch.float32, device=dev)
     gfeat = torch.empty(b, max_peaks, fc, dtype=torch.float32, device=dev)
-    scratch = torch.empty(b * max_peaks, dtype=torch.int64, device=dev)
+    total = torch.empty(b, dtype=torch.int32, device=dev)
+    scratch = torch.empty(int(lib.ftc_peak_decode_scratch_bytes(b, h, w)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.ftc_peak_decode(heat9.data_ptr(), feat.data_ptr(), b, h, w, fc, tile_meta.data_ptr(), cut_off,
-                                       float(page_w), float(page_h), max_peaks, count.data_ptr(), loc.data_ptr(),
-                                       gfeat.data_ptr(), scratch.data_ptr(), _stream_ptr(dev)), "ftc_peak_decode")
-    return count, loc, gfeat
+                                       float(page_w), float(page_h), max_peaks, count.data_ptr(), total.data_ptr(),
+                                       loc.data_ptr(), gfeat.data_ptr(), scratch.data_ptr(), _stream_ptr(dev)), "ftc_peak_decode")
+    return count, loc, gfeat, total
 
 
 def page_maps(heat9: torch.Tensor, tile_meta: torch.Tensor, page_h: int, page_w: int, out: Optional[torch.Tensor] = None

@@ -21,10 +21,11 @@ from ._tree import Node, populate
 
 
 def _train_step(mod: nn.Module) -> bool:
-    """train1.py:128-170 calls the model in train mode with autograd on: that goes through the per-layer train kernels
-    (findtextcenternet_b200/train_ops.py: batch-statistics BatchNorm, StochasticDepth, a tape for backward); everything
-    else (eval(), no_grad) through the fused inference engine."""
-    return mod.training and torch.is_grad_enabled()
+    """Train mode (train1.py:128-170, and the 50 no-grad train-mode batches of train1.py:203-211 that re-estimate the BatchNorm
+    running statistics at the averaged weights before a checkpoint is saved) goes through the per-layer train kernels
+    (findtextcenternet_b200/train_ops.py: batch-statistics BatchNorm that updates running_mean / running_var /
+    num_batches_tracked, StochasticDepth; a tape only when autograd is on); eval() goes through the fused inference engine."""
+    return mod.training
 
 
 class BackboneModel(nn.Module):
@@ -122,6 +123,12 @@ class TextDetectorModel(nn.Module):
         super().__init__(**kwargs)
         self.detector = CenterNetDetection(pre_weights=pre_weights, model_size=model_size)
         self.decoder = SimpleDecoder()
+
+    def set_precision(self, precision: str) -> "TextDetectorModel":
+        """'fp32' | 'bf16' | 'bf16_simt' for BOTH halves (the detector maps and the SimpleDecoder MLPs / id_loss gradients)."""
+        self.detector.set_precision(precision)
+        self.decoder.precision = precision
+        return self
 
     def forward(self, x, fmask):
         heatmap, features = self.detector(x)

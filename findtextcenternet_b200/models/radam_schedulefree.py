@@ -71,5 +71,8 @@ class RAdamScheduleFree(AdamWScheduleFree):
                                                      tab["vs"].data_ptr(), tab["zs"].data_ptr(), tab["numels"].data_ptr(),
                                                      beta1, beta2, bias_correction2, eps, decay, lr, ckp1, int(rho_t > 4.0),
                                                      torch.cuda.current_stream(dev).cuda_stream), "ftc_radam_sf_step")
+                # the kernel wrote p / grad through raw pointers: tell autograd (and the engines' "did a weight change?" version keys)
+                torch.autograd.graph.increment_version(active)
+                torch.autograd.graph.increment_version([p.grad for p in active])
             group["k"] = k + 1
         return loss

@@ -69,11 +69,12 @@ class OCR_b200_Processer(_Base):
             data = torch.load("model.pt", map_location="cpu", weights_only=True)
             model.load_state_dict(data["model_state_dict"])
         if precision is not None:
-            model.detector.set_precision(precision)
+            model.set_precision(precision)
         detector = CenterNetDetector(model.detector)
         detector.to(device=self.device)
         detector.eval()
         self.detector = detector
+        self.precision = precision
         self.transformer = None
         self._transformer_args = (transformer_state_dict, transformer_config)
 
@@ -96,6 +97,8 @@ class OCR_b200_Processer(_Base):
         if sd is not None:
             model.load_state_dict(sd)
         pred = TransformerPredictor(model.encoder, model.decoder)
+        if self.precision is not None:
+            pred.set_precision(self.precision)
         pred.to(self.device)
         pred.eval()
         self.transformer = pred
@@ -108,34 +111,53 @@ class OCR_b200_Processer(_Base):
 
     # ---- batched device-side path --------------------------------------------------------------------
     def detect_tiles(self, tiles: torch.Tensor, offsets: Sequence[Tuple[int, int]], page_w: int, page_h: int,
-                     max_peaks: int = 1024, maps: Optional[torch.Tensor] = None):
+                     max_peaks: int = 4096, maps: Optional[torch.Tensor] = None, on_overflow: str = "raise"):
         """tiles: float32 [B,768,768,3] in 0..255 (host, ideally pinned, or device).  Runs detector + per-tile peak
         compaction/box decode (process_ocr_base.py:487-538) on the device and returns host arrays
-        (count int32 [B], locations float32 [B,max_peaks,9], glyphfeatures float32 [B,max_peaks,100]) in pinned buffers that
-        are reused by the call after the next one (copy them if they must live longer)."""
+        (count int32 [B], locations float32 [B,n,9], glyphfeatures float32 [B,n,100], n = max(count)) in pinned buffers that
+        are reused by the call after the next one (copy them if they must live longer).
+
+        The reference loop has no cap on the peaks of a tile; ``max_peaks`` (1024 | 2048 | 4096) bounds the device buffers.  A
+        tile with more peaks keeps its ``max_peaks`` highest-scoring ones (deterministic) and, with ``on_overflow="raise"``
+        (default), raises ``OverflowError`` so boxes are never lost silently; ``"truncate"`` accepts the top-``max_peaks``
+        result (``self.last_total`` holds the uncapped per-tile counts either way)."""
         x = tiles.to(self.device, non_blocking=True)
         eng = self.detector.detector.engine(self.device)
         meta = torch.tensor([tile_meta(ox, oy, page_w, page_h, self.step_ratio) for ox, oy in offsets], dtype=torch.int32)
         meta = meta.to(self.device, non_blocking=True)
         with torch.no_grad():
             heat9, feat, _ = eng.forward(x, False, nhwc255=True)
-            count, loc, gfeat = peak_decode(heat9, feat, meta, page_w, page_h, self.cut_off, max_peaks)
+            count, loc, gfeat, total = peak_decode(heat9, feat, meta, page_w, page_h, self.cut_off, max_peaks)
             if maps is not None:     # device tensor [7, page_h/4, page_w/4]: merge this batch's tiles into the page maps
                 page_maps(heat9, meta, page_h, page_w, out=maps)
-        # results leave through persistent PINNED host buffers (one async copy each, one sync): a pageable .cpu() of the
-        # [B, max_peaks, 109] arrays cost more than a millisecond per call
+        # results leave through persistent PINNED host buffers: first the per-tile counts (a few bytes, one sync), then only the
+        # rows that are in use -- [B, max(count), 109] floats instead of [B, max_peaks, 109] (57 MB per 32 tiles at 4096)
         key = (tuple(count.shape), tuple(loc.shape), tuple(gfeat.shape))
         if getattr(self, "_out_key", None) != key:
             self._out_key, self._out_turn = key, 0
-            self._out_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (count, loc, gfeat)] for _ in range(2)]
+            self._out_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (count, loc, gfeat, total)] for _ in range(2)]
         self._out_turn ^= 1
-        host = self._out_host[self._out_turn]          # two sets in rotation: a result stays valid across ONE further call
-        for h, d in zip(host, (count, loc, gfeat)):
-            h.copy_(d, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return tuple(host)
+        hc, hl, hg, ht = self._out_host[self._out_turn]   # two sets in rotation: a result stays valid across ONE further call
+        stream = torch.cuda.current_stream(self.device)
+        hc.copy_(count, non_blocking=True)
+        ht.copy_(total, non_blocking=True)
+        stream.synchronize()
+        b, n = loc.shape[0], max(int(hc.max()), 1)
+        hl = hl.view(-1)[: b * n * loc.shape[2]].view(b, n, loc.shape[2])
+        hg = hg.view(-1)[: b * n * gfeat.shape[2]].view(b, n, gfeat.shape[2])
+        hl.copy_(loc[:, :n].contiguous(), non_blocking=True)
+        hg.copy_(gfeat[:, :n].contiguous(), non_blocking=True)
+        stream.synchronize()
+        host = (hc, hl, hg, ht)
+        self.last_total = host[3]
+        if on_overflow == "raise" and bool((host[3] > max_peaks).any()):
+            raise OverflowError(f"detect_tiles: a tile has {int(host[3].max())} peaks >= cut_off, more than max_peaks={max_peaks}; "
+                                "the reference keeps all of them (process_ocr_base.py:519-538) - raise max_peaks or pass "
+                                "on_overflow='truncate' to keep the highest-scoring ones")
+        return tuple(host[:3])
 
-    def detect_page(self, im0: np.ndarray, max_peaks: int = 1024, tile_batch: int = 32, return_maps: bool = False):
+    def detect_page(self, im0: np.ndarray, max_peaks: int = 4096, tile_batch: int = 32, return_maps: bool = False,
+                    on_overflow: str = "raise"):
         """One page (uint8 RGB [H,W,3]) -> (locations float32 [n,9], glyphfeatures float32 [n,100]): every tile of the
         reference's tiling (``page_tiles``) through ``detect_tiles`` in batches of ``tile_batch``, peaks concatenated in the
         reference's order (tile by tile, descending score inside a tile; process_ocr_base.py:487-538).  With ``return_maps``
@@ -150,7 +172,7 @@ class OCR_b200_Processer(_Base):
             tiles = torch.empty(len(offs), arch.HEIGHT, arch.WIDTH, 3, dtype=torch.float32).pin_memory()
             for j, (x, y) in enumerate(offs):
                 tiles[j] = torch.from_numpy(page[y:y + arch.HEIGHT, x:x + arch.WIDTH].astype(np.float32))
-            count, loc, gfeat = self.detect_tiles(tiles, offs, page.shape[1], page.shape[0], max_peaks, maps)
+            count, loc, gfeat = self.detect_tiles(tiles, offs, page.shape[1], page.shape[0], max_peaks, maps, on_overflow)
             for j in range(len(offs)):
                 n = int(count[j])
                 locs.append(loc[j, :n].clone())

@@ -225,3 +225,47 @@ def page_maps_inputs(seed: int, n_tiles: int) -> torch.Tensor:
     hq = arch.HEIGHT // arch.SCALE
     tiles = [torch.randn(1, 10, hq, hq, generator=g).mul_(2.0) for _ in range(n_tiles)]
     return torch.cat([torch.cat([t[:, :1], t[:, 2:]], dim=1) for t in tiles])
+
+
+def page_image(seed: int, height: int, width: int) -> "np.ndarray":
+    """Seeded synthetic RGB page, uint8 [height, width, 3] (SURVEY.md 8d config 5 style): uniform noise (the domain the synthetic
+    detector weights were BN-calibrated on, so peaks exist) with blank white blocks and dark glyph-like rectangles pasted in,
+    so that the per-box histogram filter of run_detector (process_ocr_base.py:543-557, imageHist) sees both ink and blank."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    im = (rng.random((height, width, 3)) * 255).astype(np.uint8)
+    for _ in range(max(4, height * width // 60000)):
+        bh, bw = int(rng.integers(40, 160)), int(rng.integers(40, 160))
+        y, x = int(rng.integers(0, max(1, height - bh))), int(rng.integers(0, max(1, width - bw)))
+        im[y:y + bh, x:x + bw] = 255
+    for _ in range(max(40, height * width // 6000)):
+        bh, bw = int(rng.integers(4, 28)), int(rng.integers(4, 28))
+        y, x = int(rng.integers(0, max(1, height - bh))), int(rng.integers(0, max(1, width - bw)))
+        im[y:y + bh, x:x + bw] = rng.integers(0, 80, size=3).astype(np.uint8)
+    return im
+
+
+def dense_page_heatmaps(seed: int, n_tiles: int) -> torch.Tensor:
+    """Seeded 10-channel tile heatmaps [n,10,192,192] with MANY overlapping boxes (a stub backend feeds them to run_detector so
+    that every branch of the greedy selection fires: IoU > 0.5, intersection > 75 % of the box, fill map > 0.5, separator
+    veto, 3x3 code maximum).  Channel 1 (peak-or-minus-inf) is derived with the reference rule from channel 0."""
+    g = torch.Generator().manual_seed(seed)
+    hq = arch.HEIGHT // arch.SCALE
+    out = []
+    for _ in range(n_tiles):
+        t = torch.randn(1, 10, hq, hq, generator=g)
+        key = torch.full((hq, hq), -6.0)
+        n = 500
+        ys = torch.randint(0, hq, (n,), generator=g)
+        xs = torch.randint(0, hq, (n,), generator=g)
+        key[ys, xs] = torch.rand(n, generator=g) * 5.0 - 0.6          # sigmoid 0.35 .. 0.99: some below the cut-off
+        t[0, 0] = key
+        # box sizes 12 .. 90 px (log-normal), so neighbours overlap heavily
+        t[0, 2] = torch.log(torch.exp(torch.randn(hq, hq, generator=g) * 0.5) * 32.0 / 1024.0) + 3.0
+        t[0, 3] = torch.log(torch.exp(torch.randn(hq, hq, generator=g) * 0.5) * 32.0 / 1024.0) + 3.0
+        t[0, 5] = torch.randn(hq, hq, generator=g) * 2.0 - 1.5            # separator map: ~20 % above 0.5
+        pad = torch.nn.functional.pad(key[None, None], (1, 1, 1, 1), value=float("-inf"))
+        mx = torch.nn.functional.max_pool2d(pad, 3, 1)[0, 0]
+        t[0, 1] = torch.where(key < mx, torch.tensor(float("-inf")), key)
+        out.append(t)
+    return torch.cat(out)

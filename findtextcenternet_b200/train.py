@@ -29,6 +29,11 @@ def train1_step(model, optimizer, cov, image, labelmap, idmap, fmask, iters_to_a
     CoV weights are averaged too, so every replica keeps bit-identical loss weights and parameters.  With ``buckets``
     (``shard.GradientBuckets(model.parameters())``, built once; not with gradient accumulation) the bucket all-reduces are
     launched from inside backward and overlap it."""
+    if buckets is not None and (iters_to_accumulate != 1 or not step_now):
+        # the bucket hooks fire on every backward: with accumulation they would all-reduce partial gradients and finish()
+        # would overwrite the accumulated .grad with the first micro-step's mean
+        raise ValueError("train1_step: GradientBuckets cannot be combined with gradient accumulation "
+                         "(iters_to_accumulate != 1 or step_now=False); pass buckets=None")
     heatmap, decoder_outputs = model(image, fmask)
     rawloss = loss_function(fmask, labelmap, idmap, heatmap, decoder_outputs)
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1

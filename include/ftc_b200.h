@@ -83,9 +83,13 @@ int ftc_detector_tap(const ftc_detector* d, int tap, int batch, void* workspace,
 
 /* ---- per-tile peak compaction + box decode (process_ocr_base.py:498-538) ----
  * tile_meta: int32 [B][6] = {offset_x, offset_y, mask_xmin, mask_xmax, mask_ymin, mask_ymax} (device)
- * count: int32 [B]; loc: fp32 [B][max_peaks][9]; gfeat: fp32 [B][max_peaks][F]; scratch: 8*B*max_peaks bytes */
+ * count: int32 [B] rows written = min(total, max_peaks); total: int32 [B] = every peak the reference loop would keep (it has no
+ * cap); when total > max_peaks the max_peaks highest-scoring peaks are returned (deterministic) and the caller sees the overflow.
+ * Rows are ordered by descending score, ties by ascending flat pixel index.  loc: fp32 [B][max_peaks][9]; gfeat: fp32
+ * [B][max_peaks][F]; scratch: ftc_peak_decode_scratch_bytes(batch, h, w); max_peaks in {1024, 2048, 4096}. */
+size_t ftc_peak_decode_scratch_bytes(int batch, int h, int w);
 int ftc_peak_decode(const float* heat9, const float* feat, int batch, int h, int w, int feat_ch, const int* tile_meta,
-                    float cut_off, float page_w, float page_h, int max_peaks, int* count, float* loc, float* gfeat,
+                    float cut_off, float page_w, float page_h, int max_peaks, int* count, int* total, float* loc, float* gfeat,
                     void* scratch, void* stream);
 int ftc_peak_pick(const float* heat9, float* heat10, int batch, int h, int w, void* stream);
 
@@ -170,10 +174,14 @@ int ftc_op_conv2d(const void* x, int dtype, int batch, int h, int w, int cin, co
                   int stride, const float* scale, const float* bias, int act, const void* residual,
                   const float* a_scale, void* out, void* wpack, size_t wpack_bytes, int backend, void* stream);
 size_t ftc_op_conv2d_wpack_bytes(int cin, int cout, int ksize);
+/* depthwise 3x3 + BN + SiLU (torchvision efficientnet.py:137-149).  se_sum (optional): fp32 [batch][tiles][c] receives one partial
+ * spatial sum per CTA tile, tiles = ftc_op_dwconv3x3_tiles(h, w, stride, dtype); every entry is written, no atomics (the SE
+ * squeeze is bit-reproducible), ftc_op_se_fc adds the tiles in order. */
+int ftc_op_dwconv3x3_tiles(int h, int w, int stride, int dtype);
 int ftc_op_dwconv3x3(const void* x, void* out, int dtype, int batch, int h, int w, int c, int stride,
                      const float* w9c, const float* scale, const float* bias, float* se_sum, void* stream);
-/* hid: fp32 scratch [batch, s]; `sum` is zeroed (re-armed) on return */
-int ftc_op_se_fc(float* sum, float* scale_out, float* hid, int batch, int c, int s, float inv_hw, const float* w1,
+/* SqueezeExcitation gate (ops/misc.py:251-261) from the tile sums above; hid: fp32 scratch [batch, s] */
+int ftc_op_se_fc(const float* sum, int tiles, float* scale_out, float* hid, int batch, int c, int s, float inv_hw, const float* w1,
                  const float* b1, const float* w2t, const float* b2, void* stream);
 /* debug: device buffer of 4096 u64 receiving clock64 stamps of CTA 0 of every following tcgen05 conv launch
  * ([0,1024) MMA full-wait start, [1024,2048) end, [2048,3072) producer empty-wait start, [3072,4096) end); NULL = off */
@@ -188,12 +196,12 @@ int ftc_debug_bench_gemm(int batch, int hw, int k, int n, int act, int use_se, i
 int ftc_debug_bench_conv3x3(int batch, int h, int w, int cin, int cout, int act, int use_res, int iters, float* ms_out);
 int ftc_op_upsample2x(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream);
 /* MBConv middle (torchvision efficientnet.py:137-149 + ops/misc.py:251-261), stride 1: depthwise 3x3 + BN + SiLU with the SE
- * squeeze and fc1 folded into the same kernel, then fc2 + sigmoid.  hid_pre: fp32 [batch, s], zero on entry, holds the
- * fc1 pre-activations afterwards; scale_out: fp32 [batch, c].  Returns an error for unsupported geometry
+ * squeeze and fc1 folded into the same kernel, then fc2 + sigmoid.  hid_part: fp32 scratch [batch, c / 32, s] (one fc1 share per
+ * 32-channel CTA, added in a fixed order: no atomics, bit-reproducible); scale_out: fp32 [batch, c].  Returns an error for unsupported geometry
  * (needs w <= 48, w even, h % 8 == 0, c % 32 == 0). */
 int ftc_op_dwconv3x3_se(const void* x, void* out, int dtype, int batch, int h, int w, int c, const float* w9c,
                         const float* scale, const float* bias, const float* w1, const float* b1, const float* w2t,
-                        const float* b2, int s, float* hid_pre, float* scale_out, void* stream);
+                        const float* b2, int s, float* hid_part, float* scale_out, void* stream);
 /* Leafmap.top_conv of the 1-/2-channel heads (models/detector.py:188-190): y NHWC (dtype) with head i at channels
  * [i*192, i*192+192), w fp32 [sum(od)][9*192] tap-major, out NCHW fp32 [batch, sum(od), h, w] */
 int ftc_op_head_top_conv(const void* y, int dtype, int pix_stride, int n_heads, const int* od, const float* w,

@@ -11,6 +11,9 @@ a ``state_dict`` (no nn.Module, no torchvision):
   * ``simple_decoder``      <- models/detector.py:232-254
   * ``text_detector_forward`` / ``get_fmask`` <- models/detector.py:262-281
   * ``decode_tile``         <- process_ocr_base.py:498-538 (per-tile peak sort + box decode)
+  * ``page_maps``           <- process_ocr_base.py:480-520 (page maps merged over tiles)
+  * ``select_boxes`` / ``image_hist`` <- process_ocr_base.py:540-650, 652-693 (histogram filter, greedy box
+                               selection, separator veto, 3x3 code maximum)
 
 Pinned against the unmodified reference by tests/golden/*.npz (made by
 oracle/make_golden.py, which imports /root/reference in the build container).  The
@@ -20,6 +23,7 @@ reference owns no golden vectors of its own -> the pin is
 from __future__ import annotations
 
 import math
+import warnings
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -221,3 +225,131 @@ def page_maps(heat9, offsets, page_w, page_h, step_ratio=0.6):
             p = np_sigmoid(heat9[b, ch]) * mask
             out[m, y_is:y_is + y_s, x_is:x_is + x_s] = np.maximum(p, out[m, y_is:y_is + y_s, x_is:x_is + x_s])
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# page-level box selection of run_detector (process_ocr_base.py:540-650 + imageHist :652-693), restated with numpy.
+# Pinned by tests/golden/page4_seed0.npz (the unmodified reference run_detector on a 4-tile page, real detector on CPU) and
+# tests/golden/page_dense_seed0.npz (stub backend with dense overlapping boxes: every branch of the greedy loop fires).
+def two_means_gap(hist: np.ndarray) -> float:
+    """imageHist.cluster_dist (process_ocr_base.py:654-686): two-means clustering of a 256-bin histogram started at the
+    mean split; iterates until the centre distance repeats and returns the PREVIOUS distance (the reference returns
+    ``dist1``); 0 whenever a side is empty."""
+    hist = np.asarray(hist, dtype=np.int64)
+    total = int(hist.sum())
+    if total == 0:
+        return 0.0
+    bins = np.arange(hist.shape[0])
+    mass = hist * bins
+    split = int(mass.sum() / total + 0.5)
+    lo_n, hi_n = int(hist[:split].sum()), int(hist[split:].sum())
+    if lo_n == 0 or hi_n == 0:
+        return 0.0
+    c_lo, c_hi = mass[:split].sum() / lo_n, mass[split:].sum() / hi_n
+    prev, cur = 256.0, abs(c_lo - c_hi)
+    while prev != cur:
+        prev = cur
+        near_lo = np.abs(bins - c_lo) < np.abs(bins - c_hi)
+        lo_n, hi_n = int(hist[near_lo].sum()), int(hist[~near_lo].sum())
+        if lo_n == 0 or hi_n == 0:
+            return 0.0
+        c_lo, c_hi = mass[near_lo].sum() / lo_n, mass[~near_lo].sum() / hi_n
+        cur = abs(c_lo - c_hi)
+    return float(prev)
+
+
+def image_hist(crop: np.ndarray) -> float:
+    """OCR_Processer.imageHist (process_ocr_base.py:652-693): largest two-means gap over the three colour channels of a crop
+    (values 0..255); -1 floor as in the reference, 0 for an empty crop."""
+    best = -1.0
+    for c in range(3):
+        h = np.histogram(crop[:, :, c], bins=256, range=(0, 256))[0]
+        best = max(best, two_means_gap(h))
+    return best
+
+
+def _crop(img: np.ndarray, y0: int, y1: int, x0: int, x1: int) -> np.ndarray:
+    return img[y0:y1, x0:x1, :]        # python slice semantics on purpose: the reference lets negative bounds wrap around
+
+
+def box_hists(locations: np.ndarray, page: np.ndarray):
+    """Both imageHist passes of run_detector for every box (rows of ``locations``: p, cx, cy, w, h, ...):
+    ``loose`` = the threshold pass (:543-556, bounds int(c -+ s/2) -1 / +2, unclipped) and ``tight`` = the greedy loop's
+    test (:571-576, clipped to the page).  Returns (loose [n], tight [n]) float64."""
+    hgt, wid = page.shape[:2]
+    loose, tight = [], []
+    for p, cx, cy, w, h in locations[:, :5]:
+        loose.append(image_hist(_crop(page, int(cy - h / 2) - 1, int(cy + h / 2) + 2, int(cx - w / 2) - 1, int(cx + w / 2) + 2)))
+        tight.append(image_hist(_crop(page, max(0, int(cy - h / 2)), min(hgt - 1, int(cy + h / 2) + 1),
+                                      max(0, int(cx - w / 2)), min(wid - 1, int(cx + w / 2) + 1))))
+    return np.asarray(loose, dtype=np.float64), np.asarray(tight, dtype=np.float64)
+
+
+def select_boxes(locations: np.ndarray, glyphfeatures: np.ndarray, page: np.ndarray, seps_all: np.ndarray,
+                 code_all: np.ndarray, cut_off: float = 0.4, scale: int = arch.SCALE, return_index: bool = False):
+    """The second half of run_detector (process_ocr_base.py:540-650) on the concatenated per-tile peaks (all rows have
+    p >= cut_off; float64 ``locations`` [n,9] holding the fp32 values, as the reference builds them):
+
+      1. th = median(loose imageHist of every box) / 5                                    (:543-557)
+      2. greedy pass in descending score: drop a box if its tight imageHist < th, if IoU with an accepted box > 0.5, if its
+         intersection with an accepted box > 75 % of its own area, or if the accepted boxes it touches cover more than half of
+         its int(w) x int(h) pixel grid                                                   (:559-619)
+      3. drop boxes whose centre lies on the separator map (> 0.5)                        (:621-631)
+      4. code probabilities := max(own, 3x3 neighbourhood of the page code maps)          (:641-658)
+
+    -> (locations float32 [m,9], glyphfeatures [m,100]) in acceptance order (descending score)."""
+    loc = np.asarray(locations, dtype=np.float64)
+    n = loc.shape[0]
+    hgt, wid = page.shape[:2]
+    loose, tight = box_hists(loc, page)
+    with np.errstate(all="ignore"):
+        th = np.median(loose) / 5 if n else np.nan
+    order = np.argsort(-loc[:, 0], kind="stable")
+    kept: List[int] = []
+    acc = np.zeros([0, 4])
+    for i in order:
+        _, cx, cy, w, h = loc[i, :5]
+        if tight[i] < th:
+            continue
+        if acc.shape[0]:
+            lo_x = np.maximum(cx - w / 2, acc[:, 0] - acc[:, 2] / 2)
+            lo_y = np.maximum(cy - h / 2, acc[:, 1] - acc[:, 3] / 2)
+            hi_x = np.minimum(cx + w / 2, acc[:, 0] + acc[:, 2] / 2)
+            hi_y = np.minimum(cy + h / 2, acc[:, 1] + acc[:, 3] / 2)
+            inter = np.maximum(hi_x - lo_x, 0.) * np.maximum(hi_y - lo_y, 0.)
+            union = w * h + acc[:, 2] * acc[:, 3] - inter
+            with np.errstate(all="ignore"):
+                iou = np.where(union > 0., inter / union, 0.)
+            if iou.max() > 0.5 or inter.max() > w * h * 0.75:
+                continue
+            grid = np.zeros([int(w), int(h)], dtype=bool)
+            for j in np.nonzero(iou > 0)[0]:
+                a0 = int(lo_x[j] - (cx - w / 2)); a1 = int(hi_x[j] - (cx - w / 2)) + 1
+                b0 = int(lo_y[j] - (cy - h / 2)); b1 = int(hi_y[j] - (cy - h / 2)) + 1
+                grid[a0:a1, b0:b1] = True
+            with np.errstate(all="ignore"), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                if np.mean(grid) > 0.5:
+                    continue
+        acc = np.vstack([acc, [cx, cy, w, h]])
+        kept.append(int(i))
+    hq, wq = hgt // scale, wid // scale
+    final = []
+    for i in kept:
+        x, y = int(loc[i, 1] / scale), int(loc[i, 2] / scale)
+        if 0 <= x < wq and 0 <= y < hq and seps_all[y, x] > 0.5:
+            continue
+        final.append(i)
+    out = loc[final].copy() if final else np.zeros([0, 9])
+    for r, i in enumerate(final):
+        cx, cy = loc[i, 1], loc[i, 2]
+        x, y = int(cx / scale), int(cy / scale)
+        if 0 <= x < wq and 0 <= y < hq:
+            x0, y0 = max(0, int(cx / scale - 1)), max(0, int(cy / scale - 1))
+            x1, y1 = min(wq, int(cx / scale + 1) + 1), min(hq, int(cy / scale + 1) + 1)
+            for k in range(4):
+                out[r, 5 + k] = max(np.max(code_all[k][y0:y1, x0:x1]), out[r, 5 + k])
+    gf = np.asarray(glyphfeatures)[final] if final else np.zeros([0, arch.FEATURE_DIM], dtype=np.float32)
+    if return_index:
+        return out.astype(np.float32), gf, np.asarray(final, dtype=np.int64)
+    return out.astype(np.float32), gf

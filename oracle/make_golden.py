@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference)
 on the synthetic checkpoints.  Runs only in the build container (the GPU box has no
-/root/reference); the outputs are committed.  Usage:  python oracle/make_golden.py [detector|transformer|optimizer|loss|all]
+/root/reference); the outputs are committed.  Usage:  python oracle/make_golden.py [detector|page|transformer|optimizer|radam|loss|all]
 """
 import io
 import os
@@ -101,6 +101,94 @@ def golden_detector():
     with open(os.path.join(GOLD, "detector_state_keys.json"), "w") as f:
         json.dump(ref_keys, f)
     print("detector goldens written")
+
+
+PAGE4 = dict(seed=0, height=900, width=1000)
+DENSE = dict(seed=5, feat_seed=6, height=900, width=1000)
+
+
+def dense_features(n_tiles):
+    g = torch.Generator().manual_seed(DENSE["feat_seed"])
+    return torch.randn(n_tiles, 100, 192, 192, generator=g).numpy()
+
+
+def golden_page():
+    """tests/golden/page4_seed0.npz: the UNMODIFIED reference ``run_detector`` (process_ocr_base.py:474-650) over a 4-tile
+    synthetic page with the reference detector on CPU -> final boxes / glyph features / page maps, plus the per-tile peak decode
+    (oracle.decode_tile applied to the reference's own tile heatmaps) that the device-side ``detect_page`` must reproduce.
+    tests/golden/page_dense_seed0.npz: the same reference function over a stub backend whose seeded heatmaps carry ~2 000
+    heavily overlapping boxes, so every branch of the greedy selection is exercised."""
+    from models.detector import TextDetectorModel, CenterNetDetector
+    from process_ocr_base import OCR_Processer
+    from findtextcenternet_b200.process_ocr_b200 import page_tiles
+    from oracle import detector_oracle as DO
+
+    sd = synthetic.detector_state_dict(0)
+    model = TextDetectorModel(pre_weights=False)
+    model.load_state_dict(sd, strict=True)
+    det = CenterNetDetector(model.detector).eval()
+    captured = []
+
+    class RefProc(OCR_Processer):
+        def call_detector(self, image_input):
+            images = torch.from_numpy(image_input / 255.).permute(0, 3, 1, 2).float()
+            with torch.no_grad():
+                h, f = det(images)
+            captured.append((h.numpy(), f.numpy()))
+            return captured[-1]
+
+        def call_transformer(self, encoder_input):
+            raise NotImplementedError
+
+    def tiles_of(page):
+        im = page.astype(np.float32)
+        return im, [{"input": im[None, y:y + 768, x:x + 768, :], "offsetx": x, "offsety": y} for x, y in offsets]
+
+    page, offsets = page_tiles(synthetic.page_image(PAGE4["seed"], PAGE4["height"], PAGE4["width"]))
+    im, ds0 = tiles_of(page)
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        loc, gf, lines, seps = RefProc().run_detector(ds0, im)
+    pre_loc, pre_gf, counts = [], [], []
+    for (h10, feat), (x, y) in zip(captured, offsets):
+        l, f = DO.decode_tile(h10[0], feat[0], x, y, page.shape[1], page.shape[0])
+        pre_loc.append(l); pre_gf.append(f); counts.append(len(l))
+    pre_loc, pre_gf = np.concatenate(pre_loc), np.concatenate(pre_gf)
+    heat9 = np.concatenate([np.concatenate([h[:, :1], h[:, 2:]], 1) for h, _ in captured])
+    maps7 = DO.page_maps(heat9, offsets, page.shape[1], page.shape[0])
+    assert np.array_equal(maps7[1], lines) and np.array_equal(maps7[2], seps), "oracle page maps differ from the reference's"
+    print("page4: tiles", len(offsets), "peaks per tile", counts, "-> selected", loc.shape)
+    np.savez_compressed(os.path.join(GOLD, "page4_seed0.npz"), seed=np.array(PAGE4["seed"]), image_hw=np.array([PAGE4["height"], PAGE4["width"]]),
+                        offsets=np.array(offsets), page_hw=np.array(page.shape[:2]), pre_counts=np.array(counts),
+                        pre_locations=pre_loc.astype(np.float32), pre_glyphfeatures=pre_gf.astype(np.float32),
+                        locations=loc, glyphfeatures=gf, maps7=maps7)
+
+    # dense stub page
+    page, offsets = page_tiles(synthetic.page_image(DENSE["seed"], DENSE["height"], DENSE["width"]))
+    heat10 = synthetic.dense_page_heatmaps(DENSE["seed"], len(offsets)).numpy()
+    feats = dense_features(len(offsets))
+
+    class Stub(OCR_Processer):
+        def __init__(self):
+            super().__init__()
+            self.n = 0
+
+        def call_detector(self, image_input):
+            self.n += 1
+            return heat10[self.n - 1:self.n], feats[self.n - 1:self.n]
+
+        def call_transformer(self, encoder_input):
+            raise NotImplementedError
+
+    im, ds0 = tiles_of(page)
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        loc, gf, lines, seps = Stub().run_detector(ds0, im)
+    n_pre = sum(len(DO.decode_tile(heat10[i], feats[i], x, y, page.shape[1], page.shape[0])[0]) for i, (x, y) in enumerate(offsets))
+    print("dense: candidates", n_pre, "-> selected", loc.shape)
+    np.savez_compressed(os.path.join(GOLD, "page_dense_seed0.npz"), seed=np.array(DENSE["seed"]), feat_seed=np.array(DENSE["feat_seed"]),
+                        image_hw=np.array([DENSE["height"], DENSE["width"]]), offsets=np.array(offsets), page_hw=np.array(page.shape[:2]),
+                        n_candidates=np.array(n_pre), locations=loc, glyphfeatures_sum=gf.astype(np.float64).sum(1),
+                        lines_all_s3=lines[::3, ::3].copy(), seps_all_s3=seps[::3, ::3].copy())
+    print("page goldens written")
 
 
 TRANSFORMER_CFGS = {
@@ -267,6 +355,8 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     if what in ("detector", "all"):
         golden_detector()
+    if what in ("page", "all"):
+        golden_page()
     if what in ("transformer", "all"):
         golden_transformer()
     if what in ("optimizer", "all"):

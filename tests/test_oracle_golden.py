@@ -137,3 +137,47 @@ def test_page_maps_oracle_matches_reference_run_detector():
     assert np.abs(maps[1][::3, ::3] - gold["lines_all_s3"]).max() < 1e-6
     assert np.abs(maps[2][::3, ::3] - gold["seps_all_s3"]).max() < 1e-6
     assert maps[1].max() > 0.99 and (maps[1] == 0).sum() == 0          # every page pixel is covered by some tile window
+
+
+def _dense_page():
+    """Inputs of the dense stub page of oracle/make_golden.py::golden_page, regenerated from its seeds."""
+    from findtextcenternet_b200.process_ocr_b200 import page_tiles
+    gold = np.load(os.path.join(GOLDEN, "page_dense_seed0.npz"))
+    h, w = (int(v) for v in gold["image_hw"])
+    page, offsets = page_tiles(synthetic.page_image(int(gold["seed"]), h, w))
+    assert [tuple(int(v) for v in o) for o in gold["offsets"]] == offsets
+    heat10 = synthetic.dense_page_heatmaps(int(gold["seed"]), len(offsets)).numpy()
+    feats = torch.randn(len(offsets), 100, 192, 192, generator=torch.Generator().manual_seed(int(gold["feat_seed"]))).numpy()
+    return gold, page, offsets, heat10, feats
+
+
+def test_select_boxes_oracle_matches_reference_run_detector_real_page():
+    """oracle.select_boxes (process_ocr_base.py:540-650) on the per-tile peaks of the 4-tile synthetic page == the final boxes of
+    the unmodified reference run_detector (reference detector on CPU; golden page4_seed0.npz), bit for bit."""
+    gold = np.load(os.path.join(GOLDEN, "page4_seed0.npz"))
+    h, w = (int(v) for v in gold["image_hw"])
+    from findtextcenternet_b200.process_ocr_b200 import page_tiles
+    page, offsets = page_tiles(synthetic.page_image(int(gold["seed"]), h, w))
+    assert tuple(page.shape[:2]) == tuple(int(v) for v in gold["page_hw"])
+    maps7 = gold["maps7"]
+    loc, gf = DO.select_boxes(gold["pre_locations"].astype(np.float64), gold["pre_glyphfeatures"], page.astype(np.float32),
+                              maps7[2], maps7[3:7])
+    assert loc.shape == gold["locations"].shape and len(loc) > 50 and len(loc) < len(gold["pre_locations"])
+    assert np.array_equal(loc, gold["locations"]) and np.array_equal(gf, gold["glyphfeatures"])
+
+
+def test_select_boxes_oracle_matches_reference_run_detector_dense_page():
+    """Same on the dense stub page (1 150 candidates, 374 survivors): IoU, 75 %-intersection, fill-map, histogram, separator and
+    code-maximum branches all fire; decode_tile + page_maps + select_boxes chained == reference run_detector output."""
+    gold, page, offsets, heat10, feats = _dense_page()
+    ph, pw = page.shape[:2]
+    pre = [DO.decode_tile(heat10[i], feats[i], x, y, pw, ph) for i, (x, y) in enumerate(offsets)]
+    pre_loc, pre_gf = np.concatenate([p[0] for p in pre]), np.concatenate([p[1] for p in pre])
+    assert len(pre_loc) == int(gold["n_candidates"])
+    heat9 = np.concatenate([heat10[:, :1], heat10[:, 2:]], 1)
+    maps7 = DO.page_maps(heat9, offsets, pw, ph)
+    assert np.array_equal(maps7[1][::3, ::3], gold["lines_all_s3"]) and np.array_equal(maps7[2][::3, ::3], gold["seps_all_s3"])
+    loc, gf = DO.select_boxes(pre_loc, pre_gf, page.astype(np.float32), maps7[2], maps7[3:7])
+    assert loc.shape == gold["locations"].shape
+    assert np.array_equal(loc, gold["locations"])
+    assert np.allclose(gf.astype(np.float64).sum(1), gold["glyphfeatures_sum"], rtol=0, atol=1e-9)

@@ -368,26 +368,50 @@ def test_transformer_train3_step_bf16_and_optimizer():
     assert all(np.isfinite(losses)) and losses[-1] < losses[0] - 1e-4, losses
 
 
-def test_detect_page_equals_tile_by_tile_decode():
+def test_detect_page_matches_reference_golden_page():
     """OCR_b200_Processer.detect_page (BASELINE.json configs[4] host path: reference tiling -> batched detector + device peak
-    decode) returns exactly the concatenation of per-tile detect_tiles calls."""
+    decode + device page maps) on the 4-tile synthetic page against tests/golden/page4_seed0.npz: the per-tile peaks that
+    oracle.decode_tile extracts from the UNMODIFIED reference detector's own tile heatmaps (process_ocr_base.py:487-538) and the
+    reference run_detector's page maps.  Peaks are matched by their page coordinates (ix, iy), tile by tile; a peak whose score
+    is within 1e-4 of the 0.4 cut-off may fall either side (fp32 CPU vs fp32 GPU).  Also checks that the result does not depend
+    on how the tiles are batched (run-to-run and batch-size determinism of the fp32 path)."""
     from findtextcenternet_b200 import synthetic
     from findtextcenternet_b200.process_ocr_b200 import OCR_b200_Processer, page_tiles
-    # fp32 parity path: per-pixel arithmetic does not depend on the batch size, so the comparison is exact up to rounding
-    proc = OCR_b200_Processer(detector_state_dict=synthetic.detector_state_dict(0), precision="fp32")
-    rng = np.random.default_rng(0)
-    im = (rng.random((900, 1000, 3)) * 255).astype(np.uint8)
-    loc, feat, maps = proc.detect_page(im, tile_batch=3, return_maps=True)
+    gold = np.load(os.path.join(GOLDEN, "page4_seed0.npz"))
+    h, w = (int(v) for v in gold["image_hw"])
+    im = synthetic.page_image(int(gold["seed"]), h, w)
     page, offsets = page_tiles(im)
-    assert maps.shape == (7, page.shape[0] // 4, page.shape[1] // 4) and maps.min() >= 0.0 and maps.max() <= 1.0 and maps.max() > 0.0
-    assert len(offsets) == 4 and loc.shape[1] == 9 and feat.shape == (loc.shape[0], 100)
-    ref = []
-    for x, y in offsets:
-        tile = torch.from_numpy(page[y:y + 768, x:x + 768].astype(np.float32))[None]
-        c, l, _ = proc.detect_tiles(tile, [(x, y)], page.shape[1], page.shape[0])
-        ref.append(l[0, :int(c[0])].clone())
-    ref = torch.cat(ref).numpy()
-    assert ref.shape == loc.shape and np.allclose(ref, loc, rtol=1e-3, atol=1e-3)
+    assert [tuple(int(v) for v in o) for o in gold["offsets"]] == offsets and len(offsets) == 4
+    proc = OCR_b200_Processer(detector_state_dict=synthetic.detector_state_dict(0), precision="fp32")
+    loc, feat, maps = proc.detect_page(im, tile_batch=3, return_maps=True)
+    assert maps.shape == (7, page.shape[0] // 4, page.shape[1] // 4) and loc.shape[1] == 9 and feat.shape == (loc.shape[0], 100)
+    assert np.abs(maps - gold["maps7"]).max() < 2e-5
+    ref_loc, ref_gf = gold["pre_locations"], gold["pre_glyphfeatures"]
+    key = lambda l: (int(l[1]), int(l[2]))
+    # tiles overlap, so (ix, iy) is unique only inside a tile: walk the tile segments of both lists
+    ref_off = np.concatenate([[0], np.cumsum(gold["pre_counts"])])
+    pos = 0
+    for t in range(4):
+        r_loc, r_gf = ref_loc[ref_off[t]:ref_off[t + 1]], ref_gf[ref_off[t]:ref_off[t + 1]]
+        r_by = {key(l): i for i, l in enumerate(r_loc)}
+        sure = {k for k, i in r_by.items() if abs(r_loc[i, 0] - 0.4) > 1e-4}
+        # the device's segment for this tile: rows until the score sequence restarts (descending inside a tile)
+        end = pos + 1
+        while end < len(loc) and loc[end, 0] <= loc[end - 1, 0]:
+            end += 1
+        g_loc, g_gf = loc[pos:end], feat[pos:end]
+        pos = end
+        g_keys = [key(l) for l in g_loc]
+        assert sure <= set(g_keys) and all(k in r_by or abs(l[0] - 0.4) <= 1e-4 for k, l in zip(g_keys, g_loc)), t
+        sel = [i for i, k in enumerate(g_keys) if k in r_by]
+        perm = np.array([r_by[g_keys[i]] for i in sel])
+        np.testing.assert_allclose(g_loc[sel], r_loc[perm], rtol=1e-3, atol=1e-4)
+        assert rel_l2(g_gf[sel], r_gf[perm]) < 1e-3
+    assert pos == len(loc)
+    # batching must not change a single bit (fixed-order SE reduce, score-sorted decode)
+    loc1, feat1 = proc.detect_page(im, tile_batch=1)
+    loc4, feat4 = proc.detect_page(im, tile_batch=4)
+    assert np.array_equal(loc1, loc) and np.array_equal(loc4, loc) and np.array_equal(feat1, feat) and np.array_equal(feat4, feat)
 
 
 def test_page_maps_on_device_match_reference_run_detector():
@@ -428,27 +452,3 @@ def test_part_predictors_on_device():
         assert rel_l2(probs[i].max(-1).values.cpu(), gold[f"pred_probs{i}_max"]) < 1e-3
         assert (probs[i].argmax(-1).cpu() == torch.from_numpy(gold[f"pred_probs{i}_argmax"])).float().mean() > 0.99
         assert rel_l2(split[i].cpu(), probs[i].cpu()) < 1e-5
-
-
-# keep this block LAST in the file (and the file last in the suite): if the staged kernel faulted, the CUDA context of the test
-# process would be unusable for whatever ran after it
-@pytest.mark.xfail(strict=False, reason="staged mma.sync weight-gradient kernel: written and emulated without GPU time, this is its "
-                                        "first hardware run (XPASS = it works and can become the default)")
-@pytest.mark.parametrize("b,h,w,cin,cout,k,stride", [
-    (2, 6, 5, 8, 16, 3, 1), (2, 9, 7, 24, 40, 3, 2), (3, 8, 8, 16, 8, 1, 1), (2, 24, 24, 64, 136, 3, 1), (4, 48, 48, 192, 768, 1, 1),
-    (2, 13, 11, 264, 72, 3, 1)])
-def test_staged_mma_weight_gradient(b, h, w, cin, cout, k, stride):
-    """conv_wgrad_mma_kernel (ldmatrix.trans + mma.sync, switched on through ftc_debug_set_wgrad_mma for this test only) against
-    the oracle: bf16 operands, fp32 accumulation."""
-    from findtextcenternet_b200 import _lib, _ops
-    x = rnd(b, h, w, cin, seed=1).to(torch.bfloat16)
-    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
-    dy = rnd(b, ho, wo, cout, seed=3).to(torch.bfloat16)
-    lib = _lib.load()
-    lib.ftc_debug_set_wgrad_mma(1)
-    try:
-        dw = _ops.conv2d_wgrad(dev(x), dev(dy), k, stride)
-        torch.cuda.synchronize()
-    finally:
-        lib.ftc_debug_set_wgrad_mma(-1)
-    assert rel_l2(dw.cpu(), TO.conv2d_wgrad(x.float(), dy.float(), k, stride)) < 2e-5
