@@ -265,6 +265,29 @@ def test_train1_step_decreases_the_loss():
     assert all(not torch.equal(a, p.detach()) for a, p in zip(before, list(model.parameters())[:50]))
 
 
+def test_train_mode_forward_under_no_grad_updates_bn_running_stats():
+    """train1.py:203-211: before saving, the reference runs 50 train-mode batches under torch.no_grad() to re-estimate the
+    BatchNorm running statistics at the averaged weights.  A train-mode forward without autograd must therefore still use batch
+    statistics and update running_mean / running_var / num_batches_tracked (it must NOT be routed to the eval engine)."""
+    from findtextcenternet_b200 import synthetic
+    model = _model("fp32")
+    batch = synthetic.train1_batch(2, seed=0, size=64, device="cuda")
+    bn = getattr(getattr(model.detector.backbone.features, "0"), "1")
+    dbn = getattr(getattr(model.decoder.blocks, "0"), "1")
+    before = (bn.running_mean.clone(), bn.running_var.clone(), int(bn.num_batches_tracked), dbn.running_mean.clone())
+    fmask = model.get_fmask(batch["labelmap"], None)
+    with torch.no_grad():
+        heat, dec = model(batch["image"], fmask)
+    assert not heat.requires_grad and heat.shape == (2, 9, 16, 16)
+    assert int(bn.num_batches_tracked) == before[2] + 1
+    assert not torch.equal(bn.running_mean, before[0]) and not torch.equal(bn.running_var, before[1])
+    assert not torch.equal(dbn.running_mean, before[3])
+    # and it is the batch-statistics arithmetic: equal to the same forward with autograd on
+    model2 = _model("fp32")
+    heat2, _ = model2(batch["image"], fmask)
+    assert rel_l2(heat.cpu(), heat2.detach().cpu()) < 1e-6
+
+
 # ---- Transformer train step (train3.py) ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt,tol", DTYPES)
 @pytest.mark.parametrize("rows,d", [(7, 64), (300, 512), (1000, 768)])
@@ -366,6 +389,34 @@ def test_transformer_train3_step_bf16_and_optimizer():
     from findtextcenternet_b200 import train
     losses = [float(train.train3_step(model, opt, enc, dec, label)[0]) for _ in range(12)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0] - 1e-4, losses
+
+
+def test_optimizer_step_invalidates_the_packed_engine_weights():
+    """The fused optimizer kernels write the parameters through raw pointers; the version counters that key the engines' packed
+    weights must still move, or an eval forward between optimizer steps silently uses stale weights."""
+    from findtextcenternet_b200 import train
+    from findtextcenternet_b200.models.radam_schedulefree import RAdamScheduleFree
+    gold = np.load(os.path.join(GOLDEN, "train_transformer_seed0.npz"))
+    enc, dec = torch.from_numpy(gold["enc"]).cuda(), torch.from_numpy(gold["dec"]).cuda()
+    label = torch.randint(0, 0x3FFFF, dec.shape, generator=torch.Generator().manual_seed(5)).cuda()
+    model = _transformer("fp32")
+    opt = RAdamScheduleFree([p for p in model.parameters() if p.requires_grad], lr=1e-2, silent_sgd_phase=False)
+    opt.train()
+    model.eval()
+    with torch.no_grad():
+        out0 = [o.clone() for o in model(enc, dec)]
+    v0 = next(model.parameters())._version
+    model.train()
+    train.train3_step(model, opt, enc, dec, label)
+    assert next(model.parameters())._version > v0
+    model.eval()
+    with torch.no_grad():
+        out1 = [o.clone() for o in model(enc, dec)]
+        model._engine_key = None                  # force a repack: the cached engine must already have been equal to it
+        out2 = model(enc, dec)
+    assert not torch.equal(out0[0], out1[0])
+    for a, b in zip(out1, out2):
+        assert torch.equal(a, b)
 
 
 def test_detect_page_matches_reference_golden_page():
