@@ -1,7 +1,10 @@
 // C-ABI plumbing (error text, launch counter, version) and the single-op entry points of include/ftc_b200.h.
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/ftc_b200.h"
@@ -91,9 +94,27 @@ int ftc_op_conv2d(const void* x, int dtype, int batch, int h, int w, int cin, co
   const int npad = (cout + 15) / 16 * 16;
   char* wp = (char*)wpack;
   const int Kmax = std::max(K, ksize * ksize * 64 * ((cin + 63) / 64));
-  uint32_t* ktab_d = (uint32_t*)(wp + align_up((size_t)npad * Kmax * 4, 256));
+  // the im2col k-table depends on (cin, ksize) only: one device copy per (device, cin, ksize), made at first use and kept for
+  // the life of the library -- the call itself then neither copies from pageable host memory nor synchronises, so a whole train
+  // step of these calls can be captured into a CUDA graph (first uses must happen before the capture: warm-up step)
+  const uint32_t* ktab_d = nullptr;
+  {
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int>, uint32_t*> cache;
+    int devid = 0;
+    FTC_CHECK_CUDA(cudaGetDevice(&devid));
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_tuple(devid, cin, ksize);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      uint32_t* d = nullptr;
+      FTC_CHECK_CUDA(cudaMalloc((void**)&d, kt.size() * 4));
+      FTC_CHECK_CUDA(cudaMemcpy(d, kt.data(), kt.size() * 4, cudaMemcpyHostToDevice));
+      it = cache.emplace(key, d).first;
+    }
+    ktab_d = it->second;
+  }
   FTC_CHECK_CUDA(cudaMemsetAsync(wp, 0, (size_t)npad * Kmax * es, s));
-  FTC_CHECK_CUDA(cudaMemcpyAsync(ktab_d, kt.data(), kt.size() * 4, cudaMemcpyHostToDevice, s));
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   p.B = batch; p.H = h; p.W = w; p.stride = stride; p.pad = (ksize - 1) / 2;
@@ -123,9 +144,7 @@ int ftc_op_conv2d(const void* x, int dtype, int batch, int h, int w, int cin, co
     if (rc) return rc;
     rc = conv_gemm_simt(p, s);
   }
-  if (rc) return rc;
-  FTC_CHECK_CUDA(cudaStreamSynchronize(s));   // ktab upload source is a host temporary
-  return 0;
+  return rc;
 }
 
 int ftc_op_dwconv3x3(const void* x, void* out, int dtype, int batch, int h, int w, int c, int stride,

@@ -809,70 +809,76 @@ __global__ void __launch_bounds__(256) scale_bc_vec_kernel(const T* __restrict__
 
 // SE excitation of one image per CTA: hid_pre = W1 mean + b1 ; hid = silu ; gate_pre = W2 hid + b2 ; gate = sigmoid
 // W1 [S][C], W2 [C][S] row-major (the squeezed conv weights of ops/misc.py:247-248)
-__global__ void __launch_bounds__(256) se_fc_fwd_kernel(const float* __restrict__ mean, int C, int S, const float* __restrict__ w1,
-                                                        const float* __restrict__ b1, const float* __restrict__ w2,
-                                                        const float* __restrict__ b2, float* __restrict__ hid_pre,
-                                                        float* __restrict__ gate) {
-  extern __shared__ float se_sm[];   // [S] hidden activations
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// The two fully connected layers of SqueezeExcitation are tiny GEMVs per image (C <= 3840, S <= 160).  One CTA per image was
+// latency-bound (B = 2: two CTAs walking 2 x 2.4 MB of weights with strided accesses, 0.3 ms per launch, a quarter of the whole
+// train step under ncu); every phase is now a grid-filling kernel with coalesced weight rows:
+//   fwd 1  warp per (b, s)        hid_pre[b,s] = b1[s] + w1[s,:] . mean[b,:]
+//   fwd 2  warp per (b, c)        gate[b,c]    = sigmoid(b2[c] + w2[c,:] . silu(hid_pre[b,:]))
+//   bwd 1  CTA  per (b, 32 s)     dgp = dgate*g*(1-g);  dhp[b,s] = silu'(hid_pre) * sum_c w2[c,s] dgp[b,c]   (lanes over s: row-coalesced)
+//   bwd 2  thread per (b, c)      dmean[b,c]   = sum_s w1[s,c] dhp[b,s]
+// Summation orders are fixed (no atomics).
+__global__ void __launch_bounds__(256) se_fc_fwd1_kernel(const float* __restrict__ mean, int C, int S, const float* __restrict__ w1,
+                                                         const float* __restrict__ b1, float* __restrict__ hid_pre) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * 8 + warp;
+  if (s >= S) return;
   const float* mb = mean + (int64_t)b * C;
-  for (int s = warp; s < S; s += 8) {
+  float a = 0.f;
+  for (int c = lane; c < C; c += 32) a = fmaf(w1[(int64_t)s * C + c], mb[c], a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) hid_pre[(int64_t)b * S + s] = a + b1[s];
+}
+__global__ void __launch_bounds__(256) se_fc_fwd2_kernel(const float* __restrict__ hid_pre, int C, int S, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, float* __restrict__ gate) {
+  extern __shared__ float se_sm[];   // [S] silu(hid_pre[b,:])
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int s = threadIdx.x; s < S; s += 256) se_sm[s] = silu_precise(hid_pre[(int64_t)b * S + s]);
+  __syncthreads();
+  for (int c = blockIdx.x * 64 + warp; c < C && c < blockIdx.x * 64 + 64; c += 8) {
     float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(w1[(int64_t)s * C + c], mb[c], a);
+    for (int s = lane; s < S; s += 32) a = fmaf(w2[(int64_t)c * S + s], se_sm[s], a);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) {
-      a += b1[s];
-      hid_pre[(int64_t)b * S + s] = a;
-      se_sm[s] = silu_precise(a);
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float a = b2[c];
-    for (int s = 0; s < S; ++s) a = fmaf(w2[(int64_t)c * S + s], se_sm[s], a);
-    gate[(int64_t)b * C + c] = sigmoid_precise(a);
+    if (lane == 0) gate[(int64_t)b * C + c] = sigmoid_precise(a + b2[c]);
   }
 }
-
-// backward, data side, one image per CTA: dgp = dgate * gate (1 - gate) ; dhid = W2^T dgp ; dhp = dhid * silu'(hid_pre) ;
-// dmean = W1^T dhp
-__global__ void __launch_bounds__(256) se_fc_bwd_data_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
-                                                             const float* __restrict__ hid_pre, int C, int S,
-                                                             const float* __restrict__ w1, const float* __restrict__ w2,
-                                                             float* __restrict__ dgp, float* __restrict__ dhp,
-                                                             float* __restrict__ dmean) {
-  extern __shared__ float se_sm[];   // [C] dgp, then [S] dhp
-  float* s_dgp = se_sm;
-  float* s_dhp = se_sm + C;
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float gt = gate[(int64_t)b * C + c];
-    float v = dgate[(int64_t)b * C + c] * gt * (1.f - gt);
-    s_dgp[c] = v;
-    dgp[(int64_t)b * C + c] = v;
+__global__ void __launch_bounds__(256) se_fc_bwd1_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
+                                                         const float* __restrict__ hid_pre, int C, int S,
+                                                         const float* __restrict__ w2, float* __restrict__ dgp,
+                                                         float* __restrict__ dhp) {
+  __shared__ float red[8][32];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * 32 + lane;
+  const bool first = blockIdx.x == 0;              // the first s-chunk's CTA also publishes dgp (the weight kernel reads it)
+  float a = 0.f;
+  for (int c = warp; c < C; c += 8) {
+    const float gt = gate[(int64_t)b * C + c];
+    const float v = dgate[(int64_t)b * C + c] * gt * (1.f - gt);
+    if (first && lane == 0) dgp[(int64_t)b * C + c] = v;
+    if (s < S) a = fmaf(w2[(int64_t)c * S + s], v, a);
   }
+  red[warp][lane] = a;
   __syncthreads();
-  for (int s = warp; s < S; s += 8) {
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(w2[(int64_t)c * S + s], s_dgp[c], a);
+  if (warp == 0 && s < S) {
+    float t = red[0][lane];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) {
-      float v = a * act_grad(hid_pre[(int64_t)b * S + s], ACT_SILU);
-      s_dhp[s] = v;
-      dhp[(int64_t)b * S + s] = v;
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float a = 0.f;
-    for (int s = 0; s < S; ++s) a = fmaf(w1[(int64_t)s * C + c], s_dhp[s], a);
-    dmean[(int64_t)b * C + c] = a;
+    for (int w = 1; w < 8; ++w) t += red[w][lane];
+    dhp[(int64_t)b * S + s] = t * act_grad(hid_pre[(int64_t)b * S + s], ACT_SILU);
   }
 }
-
-// backward, weight side: dW2[c][s] = sum_b dgp[b][c] silu(hid_pre[b][s]) ; dW1[s][c] = sum_b dhp[b][s] mean[b][c] ; biases
+__global__ void __launch_bounds__(256) se_fc_bwd2_kernel(const float* __restrict__ dhp, int C, int S, const float* __restrict__ w1,
+                                                         float* __restrict__ dmean) {
+  extern __shared__ float se_sm[];   // [S] dhp[b,:]
+  const int b = blockIdx.y;
+  for (int s = threadIdx.x; s < S; s += 256) se_sm[s] = dhp[(int64_t)b * S + s];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int s = 0; s < S; ++s) a = fmaf(w1[(int64_t)s * C + c], se_sm[s], a);
+  dmean[(int64_t)b * C + c] = a;
+}
 __global__ void __launch_bounds__(256) se_fc_bwd_weight_kernel(const float* __restrict__ dgp, const float* __restrict__ dhp,
                                                                const float* __restrict__ hid_pre, const float* __restrict__ mean,
                                                                int B, int C, int S, float* __restrict__ dw1, float* __restrict__ db1,
@@ -1228,7 +1234,7 @@ bool dtype_ok(int dt) { return dt == DT_F32 || dt == DT_BF16; }
 int g_wgrad_mma = -1;
 bool wgrad_mma_enabled() {
   if (g_wgrad_mma >= 0) return g_wgrad_mma != 0;
-  static const bool env = [] { const char* e = getenv("FTC_WGRAD_MMA"); return e && atoi(e) != 0; }();
+  static const bool env = [] { const char* e = getenv("FTC_WGRAD_MMA"); return !e || atoi(e) != 0; }();   // default ON
   return env;
 }
 
@@ -1505,7 +1511,11 @@ int ftc_train_scale_bc(const void* x, const float* scale_bc, const float* bias_b
 int ftc_train_se_fc(const float* mean, int batch, int c, int sq, const float* w1, const float* b1, const float* w2,
                     const float* b2, float* hid_pre, float* gate, void* stream) {
   FTC_REQUIRE(mean && w1 && b1 && w2 && b2 && hid_pre && gate && batch > 0 && c > 0 && sq > 0 && sq <= 4096, "bad argument");
-  se_fc_fwd_kernel<<<batch, 256, (size_t)sq * sizeof(float), (cudaStream_t)stream>>>(mean, c, sq, w1, b1, w2, b2, hid_pre, gate);
+  FTC_REQUIRE(batch <= 65535, "batch");
+  cudaStream_t s = (cudaStream_t)stream;
+  se_fc_fwd1_kernel<<<dim3(ceil_div(sq, 8), batch), 256, 0, s>>>(mean, c, sq, w1, b1, hid_pre);
+  FTC_POST_LAUNCH();
+  se_fc_fwd2_kernel<<<dim3(ceil_div(c, 64), batch), 256, (size_t)sq * sizeof(float), s>>>(hid_pre, c, sq, w2, b2, gate);
   FTC_POST_LAUNCH();
   return 0;
 }
@@ -1514,9 +1524,11 @@ int ftc_train_se_fc_bwd(const float* dgate, const float* gate, const float* hid_
                         const float* w1, const float* w2, float* dgp, float* dhp, float* dmean, float* dw1, float* db1,
                         float* dw2, float* db2, void* stream) {
   FTC_REQUIRE(dgate && gate && hid_pre && mean && w1 && w2 && dgp && dhp && dmean && dw1 && db1 && dw2 && db2, "null argument");
-  FTC_REQUIRE(batch > 0 && c > 0 && sq > 0 && (size_t)(c + sq) * sizeof(float) <= 48 * 1024, "bad geometry");
+  FTC_REQUIRE(batch > 0 && batch <= 65535 && c > 0 && sq > 0 && sq <= 4096, "bad geometry");
   cudaStream_t s = (cudaStream_t)stream;
-  se_fc_bwd_data_kernel<<<batch, 256, (size_t)(c + sq) * sizeof(float), s>>>(dgate, gate, hid_pre, c, sq, w1, w2, dgp, dhp, dmean);
+  se_fc_bwd1_kernel<<<dim3(ceil_div(sq, 32), batch), 256, 0, s>>>(dgate, gate, hid_pre, c, sq, w2, dgp, dhp);
+  FTC_POST_LAUNCH();
+  se_fc_bwd2_kernel<<<dim3(ceil_div(c, 256), batch), 256, (size_t)sq * sizeof(float), s>>>(dhp, c, sq, w1, dmean);
   FTC_POST_LAUNCH();
   const int64_t n = (int64_t)c * sq;
   se_fc_bwd_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dgp, dhp, hid_pre, mean, batch, c, sq, dw1, db1, dw2, db2);

@@ -125,8 +125,10 @@ def loss_function(fmask, labelmap, idmap, heatmap, decoder_outputs):
     _need_cuda(fmask, labelmap, idmap, heatmap, *decoder_outputs)
     key_th3 = 0.99
     m9 = _HeatmapLosses.apply(heatmap, labelmap, idmap)      # differentiable w.r.t. heatmap (train1.py:151 loss.backward())
-    keyvals = labelmap[:, 0].flatten()[fmask].float()
-    target_id = idmap[:, 0].flatten()[fmask]
+    from .train_ops import select_rows
+    count = min(1024 * labelmap.shape[0], labelmap[:, 0].numel())      # population of get_fmask's mask (used under graph capture)
+    keyvals = select_rows(labelmap[:, 0].flatten(), fmask, count).float()
+    target_id = select_rows(idmap[:, 0].flatten(), fmask, count)
     pos = target_id > 0
     weight3 = torch.clamp_min(keyvals - key_th3, 0.) / (1 - key_th3)
     id_loss, o = _CEMean.apply(decoder_outputs[0], decoder_outputs[1], decoder_outputs[2], target_id, weight3,
@@ -149,36 +151,45 @@ def loss_function3(outputs, labelcode, mask):
 
 
 class CoVWeightingLoss(torch.nn.Module):
-    """loss_func.py:8-72 (Multi-Loss Weighting with Coefficient of Variations): Welford statistics of the loss ratios."""
+    """loss_func.py:8-72 (Multi-Loss Weighting with Coefficient of Variations): Welford statistics of the loss ratios.
+
+    Same arithmetic and attribute names as the reference, but the iteration-dependent pieces (first-iteration L0, the uniform
+    weights of iterations 0 and 1, ``mean_param``) are selected by a DEVICE-resident iteration counter and every statistic is
+    updated in place, so one call is a fixed sequence of kernels on fixed storage: a train step containing it can be captured
+    into a CUDA graph and replayed (findtextcenternet_b200/train.py::Train1Graph) and still advance the statistics."""
 
     def __init__(self, *args, **kwargs) -> None:
         self.device = kwargs.pop("device", "cpu")
         self.losses = kwargs.pop("losses", [])
         self.num_losses = len(self.losses)
         super().__init__(*args, **kwargs)
-        self.current_iter = -1
+        self.current_iter = -1           # host mirror of the device counter (the reference's attribute)
         z = lambda: torch.zeros((self.num_losses,), dtype=torch.float32, device=self.device)
         self.alphas, self.running_mean_L, self.running_mean_l, self.running_S_l = z(), z(), z(), z()
-        self.running_std_l = None
+        self.running_std_l = z()
+        self._it = torch.full((), -1.0, dtype=torch.float64, device=self.device)
 
     def forward(self, losses):
         L = torch.stack([losses[key].detach().to(torch.float32) for key in self.losses])
         if not self.train:          # (sic) the reference tests the bound method, which is always truthy (loss_func.py:30)
             return torch.sum(L)
         self.current_iter += 1
-        L0 = L.clone() if self.current_iter == 0 else self.running_mean_L
+        it = self._it.add_(1.0)                                   # device copy of current_iter
+        first = it == 0
+        L0 = torch.where(first, L, self.running_mean_L)
         l = L / L0
-        if self.current_iter <= 1:
-            self.alphas = torch.ones((self.num_losses,), dtype=torch.float32, device=self.device) / self.num_losses
-        else:
-            ls = self.running_std_l / self.running_mean_l
-            self.alphas = ls / torch.sum(ls)
-        mean_param = 0.0 if self.current_iter == 0 else (1. - 1 / (self.current_iter + 1))
-        x_l = l.clone()
-        new_mean_l = mean_param * self.running_mean_l + (1 - mean_param) * x_l
-        self.running_S_l = self.running_S_l + (x_l - self.running_mean_l) * (x_l - new_mean_l)
-        self.running_mean_l = new_mean_l
-        running_variance_l = self.running_S_l / (self.current_iter + 1)
-        self.running_std_l = torch.sqrt(running_variance_l.clamp_min(1e-16))
-        self.running_mean_L = mean_param * self.running_mean_L + (1 - mean_param) * L.clone()
-        return sum(self.alphas[i] * losses[key].to(torch.float32) for i, key in enumerate(self.losses))
+        ls = self.running_std_l / self.running_mean_l
+        uniform = torch.full_like(L, 1.0 / self.num_losses) if self.num_losses else L
+        self.alphas.copy_(torch.where(it <= 1, uniform, ls / torch.sum(ls)))
+        # Python-double arithmetic of the reference (1 - 1 / (n + 1), then 1 - that), rounded to fp32 once as torch does for
+        # scalar operands
+        mp64 = torch.where(first, torch.zeros_like(it), 1.0 - 1.0 / (it + 1.0))
+        mean_param, one_m = mp64.float(), (1.0 - mp64).float()
+        new_mean_l = mean_param * self.running_mean_l + one_m * l
+        self.running_S_l.add_((l - self.running_mean_l) * (l - new_mean_l))
+        self.running_mean_l.copy_(new_mean_l)
+        running_variance_l = self.running_S_l / (it + 1.0).float()
+        self.running_std_l.copy_(torch.sqrt(running_variance_l.clamp_min(1e-16)))
+        self.running_mean_L.copy_(mean_param * self.running_mean_L + one_m * L)
+        alphas = self.alphas.clone()         # the weights of THIS call (the statistics above already moved on)
+        return sum(alphas[i] * losses[key].to(torch.float32) for i, key in enumerate(self.losses))

@@ -75,8 +75,63 @@ class AdamWScheduleFree(torch.optim.Optimizer):
         self._tables[gi] = (key, tab)
         return tab
 
+    # ---- CUDA-graph support ------------------------------------------------------------------------------------------
+    def prepare_graph(self) -> None:
+        """Call once BEFORE capturing a CUDA graph that contains ``step()`` (after at least one eager step, so that the
+        per-parameter state and gradients exist at their final addresses).  Moves the step-dependent schedule state (k, lr_max,
+        weight_sum) of every param group to the device; from then on ``step()`` under capture records
+        ``ftc_adamw_sf_step_dev`` (schedule computed on the device), and every replay of the graph is one more optimizer step.
+        ``sync_from_graph()`` copies the device state back into ``param_groups`` (checkpointing, switching back to eager)."""
+        self._graph_state = {}
+        for gi, group in enumerate(self.param_groups):
+            active = [p for p in group["params"] if p.grad is not None]
+            if not active:
+                continue
+            for p in active:
+                if "z" not in self.state[p]:
+                    raise RuntimeError("prepare_graph(): run one eager step first (optimizer state not initialised)")
+            dev = active[0].device
+            beta1, beta2 = group["betas"]
+            consts = torch.tensor([float(group["lr"]), beta1, beta2, group["eps"], group["weight_decay"], float(group["warmup_steps"]),
+                                   group["r"], group["weight_lr_power"]], dtype=torch.float64, device=dev)
+            state = torch.tensor([float(group["k"]), float(group["lr_max"]), float(group["weight_sum"])], dtype=torch.float64, device=dev)
+            hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+            self._graph_state[gi] = dict(consts=consts, state=state, hyper=hyper, table=self._table(gi, active), active=active)
+
+    def sync_from_graph(self) -> None:
+        for gi, gs in getattr(self, "_graph_state", {}).items():
+            k, lr_max, weight_sum = (float(v) for v in gs["state"].cpu())
+            group = self.param_groups[gi]
+            group["k"], group["lr_max"], group["weight_sum"] = int(round(k)), lr_max, weight_sum
+
+    def _step_captured(self) -> None:
+        lib = _lib.load()
+        gstate = getattr(self, "_graph_state", None)
+        if not gstate:
+            raise RuntimeError("AdamWScheduleFree.step() inside a CUDA graph capture needs prepare_graph() before the capture")
+        for gi, gs in gstate.items():
+            active, tab = gs["active"], gs["table"]
+            key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg_sq"].data_ptr(), self.state[p]["z"].data_ptr(),
+                         p.numel()) for p in active)
+            if key != self._tables[gi][0]:
+                raise RuntimeError("a parameter / gradient buffer moved since prepare_graph(): gradients must live in static "
+                                   "storage (shard.FlatGradients) for a captured optimizer step")
+            dev = active[0].device
+            with torch.cuda.device(dev):
+                _lib.check(lib.ftc_adamw_sf_step_dev(tab["n"], tab["chunks"].data_ptr(), tab["ys"].data_ptr(), tab["gs"].data_ptr(),
+                                                     tab["vs"].data_ptr(), tab["zs"].data_ptr(), tab["numels"].data_ptr(),
+                                                     gs["consts"].data_ptr(), gs["state"].data_ptr(), gs["hyper"].data_ptr(),
+                                                     torch.cuda.current_stream(dev).cuda_stream), "ftc_adamw_sf_step_dev")
+            torch.autograd.graph.increment_version(active)
+            torch.autograd.graph.increment_version([p.grad for p in active])
+
     @torch.no_grad()
     def step(self, closure: Optional[Callable[[], float]] = None) -> Optional[float]:
+        if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            if closure is not None:
+                raise RuntimeError("closure is not supported inside a CUDA graph capture")
+            self._step_captured()
+            return None
         if not self.param_groups[0]["train_mode"]:
             raise Exception("Optimizer was not in train mode when step is called. Please insert .train() and .eval() calls "
                             "on the optimizer. See documentation for details.")

@@ -133,7 +133,8 @@ class TextDetectorModel(nn.Module):
     def forward(self, x, fmask):
         heatmap, features = self.detector(x)
         features = torch.permute(features, (0, 2, 3, 1)).flatten(0, -2)
-        decoder_outputs = self.decoder(features[fmask])
+        from ..train_ops import select_rows
+        decoder_outputs = self.decoder(select_rows(features, fmask, min(1024 * x.shape[0], features.shape[0])))
         return heatmap, decoder_outputs
 
     def get_fmask(self, heatmap, mask) -> Tensor:

@@ -23,12 +23,19 @@ TRAIN1_LOSSES = ["keymap_loss", "size_loss", "textline_loss", "separator_loss", 
 
 
 def train1_step(model, optimizer, cov, image, labelmap, idmap, fmask, iters_to_accumulate: int = 1, step_now: bool = True,
-                group=None, buckets: Optional["shard.GradientBuckets"] = None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+                group=None, buckets: Optional["shard.GradientBuckets"] = None, flat: Optional["shard.FlatGradients"] = None
+                ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
     """One iteration of the train1.py loop body (:183-191).  With torch.distributed initialised (world size > 1) the gradients
     are averaged over ranks in reverse-order flat buckets before the optimizer step, and the nine raw losses that drive the
     CoV weights are averaged too, so every replica keeps bit-identical loss weights and parameters.  With ``buckets``
     (``shard.GradientBuckets(model.parameters())``, built once; not with gradient accumulation) the bucket all-reduces are
-    launched from inside backward and overlap it."""
+    launched from inside backward and overlap it.  With ``flat`` (``shard.FlatGradients(model.parameters())``, built once) the
+    gradients live in flat bucket storage: buckets are all-reduced in place from inside backward, and ``flat.zero()`` replaces
+    ``optimizer.zero_grad()`` (the gradient views must stay attached)."""
+    if flat is not None:
+        if buckets is not None or iters_to_accumulate != 1 or not step_now:
+            raise ValueError("train1_step: flat=FlatGradients excludes buckets= and gradient accumulation")
+        flat.zero()
     if buckets is not None and (iters_to_accumulate != 1 or not step_now):
         # the bucket hooks fire on every backward: with accumulation they would all-reduce partial gradients and finish()
         # would overwrite the accumulated .grad with the first micro-step's mean
@@ -42,13 +49,77 @@ def train1_step(model, optimizer, cov, image, labelmap, idmap, fmask, iters_to_a
     loss = cov(rawloss)
     (loss / iters_to_accumulate).backward()
     if step_now:
-        if distributed and buckets is not None:
+        if flat is not None:
+            flat.finish()
+        elif distributed and buckets is not None:
             buckets.finish()
         elif distributed:
             shard.allreduce_gradients([p for p in model.parameters() if p.requires_grad], group=group)
         optimizer.step()
-        optimizer.zero_grad()
+        if flat is None:
+            optimizer.zero_grad()
     return loss.detach(), {k: v.detach() for k, v in rawloss.items()}
+
+
+class Train1Graph:
+    """The whole train1 step -- train-mode forward, losses, CoV weights, backward, in-place bucket all-reduce, fused optimizer
+    update: ~9 000 kernel launches issued from ~3 000 autograd nodes -- captured ONCE into a CUDA graph and replayed per
+    iteration, so the step is paced by the GPU and not by the Python interpreter (B200-first: streams and graphs instead of a
+    tracing compiler).  Everything step-dependent lives on the device: the CoV statistics (``CoVWeightingLoss`` updates fixed
+    storage from a device iteration counter), the optimizer schedule (``ftc_adamw_sf_step_dev``), the StochasticDepth draws
+    (torch's graph-safe Philox offsets), BatchNorm running statistics; gradients live in ``shard.FlatGradients`` storage.
+
+        graph = Train1Graph(model, optimizer, cov, batch_size, device)          # warm-up steps + capture
+        fmask = model.get_fmask(labelmap, fmask)
+        loss, rawloss = graph.step(image, labelmap, idmap, fmask)               # one replay = one train1.py loop body
+
+    The arguments of ``step`` are copied into the graph's static input buffers; the returned tensors are the graph's static
+    outputs (overwritten by the next replay).  ``eager_steps`` real optimizer steps are taken on the first batch while warming
+    up (lazy state, kernel attributes, k-tables must exist before the capture)."""
+
+    def __init__(self, model, optimizer, cov, batch, device, size: int = 768, group=None, flat: Optional["shard.FlatGradients"] = None,
+                 warmup_batch=None, eager_steps: int = 2):
+        dev = torch.device(device)
+        hq = size // 4
+        self.model, self.optimizer, self.cov, self.group = model, optimizer, cov, group
+        self.flat = flat if flat is not None else shard.FlatGradients([p for p in model.parameters() if p.requires_grad], group=group)
+        self.image = torch.zeros(batch, 3, size, size, dtype=torch.float32, device=dev)
+        self.labelmap = torch.zeros(batch, 5, hq, hq, dtype=torch.float32, device=dev)
+        self.idmap = torch.zeros(batch, 2, hq, hq, dtype=torch.int64, device=dev)
+        self.fmask = torch.zeros(batch * hq * hq, dtype=torch.bool, device=dev)
+        if warmup_batch is not None:
+            self._load(*warmup_batch)
+        else:       # a valid mask (exactly min(1024 * batch, all) pixels) and non-degenerate labels for the warm-up steps
+            self.image.uniform_()
+            self.labelmap.uniform_()
+            self.idmap[:, 0].random_(0, 0x3FFF)
+            self.fmask[: min(1024 * batch, self.fmask.numel())] = True
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(eager_steps, 1)):
+                train1_step(model, optimizer, cov, self.image, self.labelmap, self.idmap, self.fmask, group=group, flat=self.flat)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.flat.check_views()
+        optimizer.prepare_graph()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.rawloss = train1_step(model, optimizer, cov, self.image, self.labelmap, self.idmap, self.fmask,
+                                                  group=group, flat=self.flat)
+        self.replays = 0
+
+    def _load(self, image, labelmap, idmap, fmask):
+        self.image.copy_(image, non_blocking=True)
+        self.labelmap.copy_(labelmap, non_blocking=True)
+        self.idmap.copy_(idmap, non_blocking=True)
+        self.fmask.copy_(fmask.reshape(-1), non_blocking=True)
+
+    def step(self, image, labelmap, idmap, fmask):
+        self._load(image, labelmap, idmap, fmask)
+        self.graph.replay()
+        self.replays += 1
+        return self.loss, self.rawloss
 
 
 def _sync_loss_values(rawloss: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:

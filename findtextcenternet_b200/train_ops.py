@@ -65,7 +65,13 @@ class _Conv2d(Function):
             else:
                 dx = K.conv2d_dgrad(dy, w, x.shape[1], x.shape[2], ctx.stride)
         if ctx.needs_input_grad[1]:
-            dw = K.conv2d_wgrad(x, dy, k, ctx.stride).to(w.dtype)
+            if dy.dtype == torch.bfloat16 and cout % 8 and x.shape[-1] % 8 == 0:
+                # the tensor-core weight-gradient kernels stage 16-byte row pieces: pad the output channels of dy (the 1- / 2- /
+                # 100-channel top convs, the 1091 / 1093 / 1097-wide decoder heads) to a multiple of 8 and drop the zero rows
+                dyp = torch.nn.functional.pad(dy, (0, (-cout) % 8))
+                dw = K.conv2d_wgrad(x, dyp, k, ctx.stride)[:cout].to(w.dtype)
+            else:
+                dw = K.conv2d_wgrad(x, dy, k, ctx.stride).to(w.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             mean, _ = K.bn_stats(dy)
             db = mean * float(dy.numel() // cout)
@@ -163,6 +169,17 @@ class _RowScale(Function):
 # ---- layer helpers over the parameter containers of models/_tree.py ------------------------------------------------
 def _sub(node, name):
     return getattr(node, str(name))
+
+
+def select_rows(flat: Tensor, fmask: Tensor, count: int) -> Tensor:
+    """``flat[fmask]`` for the boolean pixel mask of ``TextDetectorModel.get_fmask`` (models/detector.py:270-281).  Boolean
+    indexing asks the device how many rows are selected (a host synchronisation, illegal while a CUDA graph is being captured);
+    under capture the mask's population is taken to be ``count`` (get_fmask sets exactly 1024 * batch pixels) and the rows are
+    gathered through ``nonzero_static`` - same rows, same order, static shapes."""
+    if fmask.dtype == torch.bool and fmask.is_cuda and torch.cuda.is_current_stream_capturing():
+        idx = torch.nonzero_static(fmask, size=count)[:, 0]
+        return flat.index_select(0, idx)
+    return flat[fmask]
 
 
 def conv2d(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, stride: int = 1) -> Tensor:
@@ -275,11 +292,14 @@ def leafmap_train_forward(leaf, taps: List[Tensor]) -> Tensor:
     return conv2d(y, top.weight, top.bias, 1)
 
 
-def detection_train_forward(det, x: Tensor, sd_prob: float = STOCHASTIC_DEPTH_PROB, sd_noise: Optional[dict] = None
+def detection_train_forward(det, x: Tensor, sd_prob: Optional[float] = None, sd_noise: Optional[dict] = None
                             ) -> Tuple[Tensor, Tensor]:
     """CenterNetDetection.forward (models/detector.py:217-230) in train mode: x NCHW in [0,1] -> (heatmap [B,9,H/4,W/4],
-    feature [B,100,H/4,W/4]) fp32 NCHW with autograd history."""
+    feature [B,100,H/4,W/4]) fp32 NCHW with autograd history.  StochasticDepth probability: ``sd_prob``, else the module's
+    ``stochastic_depth_prob`` attribute, else torchvision's 0.2."""
     _need_cuda(x, "detector")
+    if sd_prob is None:
+        sd_prob = getattr(det, "stochastic_depth_prob", STOCHASTIC_DEPTH_PROB)
     dt = torch.float32 if det.precision == "fp32" else torch.bfloat16
     xh = (x.float() * 2 - 1).permute(0, 2, 3, 1).to(dt).contiguous()
     taps = backbone_train_forward(det.backbone.features, xh, det.model_size, sd_prob, sd_noise)

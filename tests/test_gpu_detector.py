@@ -71,6 +71,11 @@ def test_detector_fp32_batch_invariance(model):
 @pytest.mark.parametrize("precision", ["bf16_simt", "bf16"])
 @pytest.mark.parametrize("name", ["rand0", "test1"])
 def test_detector_bf16_close_to_reference(name, precision, model, golden_detector, test1_tile):
+    """The benchmarked precision (bf16 storage, fp32 accumulation, tcgen05) against the reference golden.  Bounds calibrated on
+    B200 in round 2 (tools/measure_bf16_gate.py, profiles/r02a_bf16_gate.jsonl): rand0 heat 0.61 %, features 0.73 % -> asserted
+    at 2e-2; peak sets (3x3 local maxima, +-1 map pixel) Jaccard 0.988 at the 0.4 cut-off (161 peaks) and 0.982 over the 1 970
+    peaks above sigmoid 0.27 -> asserted at 0.95.  The near-constant white test1 tile lies outside the noise domain the synthetic
+    weights were BN-calibrated on (activations cancel; 3 peaks above the cut-off): 9.4 % measured -> 0.15, no peak statistics."""
     m, det = model
     m.detector.set_precision(precision)
     g = golden_detector
@@ -79,20 +84,21 @@ def test_detector_bf16_close_to_reference(name, precision, model, golden_detecto
     h10, feat = h10.cpu().numpy()[0], feat.cpu().numpy()[0]
     ref = g[name + "_heatmap10"]
     other = [0] + list(range(2, 10))
-    assert rel_l2(h10[other], ref[other]) < 1e-1
-    assert rel_l2(feat[:, ::8, ::8], g[name + "_feat_s8"]) < 1e-1
-    # peaks above cut_off 0.4 (logit -0.405): every reference peak has a device peak within one map pixel and vice
-    # versa for >= 85 % of them (bf16 noise moves plateau maxima by a pixel; exact equality is the fp32 gate)
-    a, b = np.isfinite(h10[1]) & (h10[1] > -0.405), np.isfinite(ref[1]) & (ref[1] > -0.405)
+    bound = 2e-2 if name == "rand0" else 0.15
+    assert rel_l2(h10[other], ref[other]) < bound
+    assert rel_l2(feat[:, ::8, ::8], g[name + "_feat_s8"]) < bound
+    if name != "rand0":
+        return
 
     def dilate(m):
         p = np.pad(m, 1)
         return np.max([p[dy:dy + m.shape[0], dx:dx + m.shape[1]] for dy in range(3) for dx in range(3)], axis=0)
 
-    recall = (b & dilate(a)).sum() / max(1, b.sum())
-    precision_ = (a & dilate(b)).sum() / max(1, a.sum())
-    if b.sum() >= 50:   # the white test1 tile has 3 peaks above cut-off with these synthetic weights: no statistics
-        assert recall >= 0.85 and precision_ >= 0.85, (recall, precision_, int(a.sum()), int(b.sum()))
+    for thr, min_peaks in ((-0.405, 100), (-1.0, 200)):       # the cut-off (sigmoid 0.4) and a lower level with ~2 000 peaks
+        a, b = np.isfinite(h10[1]) & (h10[1] > thr), np.isfinite(ref[1]) & (ref[1] > thr)
+        matched = ((a & dilate(b)).sum() + (b & dilate(a)).sum()) / 2.0
+        jaccard = matched / max(a.sum() + b.sum() - matched, 1)
+        assert b.sum() >= min_peaks and jaccard >= 0.95, (thr, jaccard, int(a.sum()), int(b.sum()))
 
 
 def test_tc_and_simt_bf16_agree(model):

@@ -276,6 +276,7 @@ def test_train_mode_forward_under_no_grad_updates_bn_running_stats():
     dbn = getattr(getattr(model.decoder.blocks, "0"), "1")
     before = (bn.running_mean.clone(), bn.running_var.clone(), int(bn.num_batches_tracked), dbn.running_mean.clone())
     fmask = model.get_fmask(batch["labelmap"], None)
+    model.detector.stochastic_depth_prob = 0.0       # StochasticDepth draws would differ between the two forwards below
     with torch.no_grad():
         heat, dec = model(batch["image"], fmask)
     assert not heat.requires_grad and heat.shape == (2, 9, 16, 16)
@@ -284,8 +285,45 @@ def test_train_mode_forward_under_no_grad_updates_bn_running_stats():
     assert not torch.equal(dbn.running_mean, before[3])
     # and it is the batch-statistics arithmetic: equal to the same forward with autograd on
     model2 = _model("fp32")
+    model2.detector.stochastic_depth_prob = 0.0
     heat2, _ = model2(batch["image"], fmask)
     assert rel_l2(heat.cpu(), heat2.detach().cpu()) < 1e-6
+
+
+def test_train1_graph_replay_equals_eager_steps():
+    """train.Train1Graph (the whole train1 step captured into a CUDA graph: device-resident CoV statistics, device-scheduled
+    AdamWScheduleFree, gradients in FlatGradients storage) must walk the same trajectory as the eager train1_step: same losses,
+    same parameters after 2 eager + 3 replayed steps vs 5 eager steps (fp32, StochasticDepth off so both draw nothing)."""
+    from findtextcenternet_b200 import shard, synthetic, train
+    from findtextcenternet_b200.loss_func import CoVWeightingLoss
+    from findtextcenternet_b200.models.adamw_schedulefree import AdamWScheduleFree
+    batch = synthetic.train1_batch(2, seed=0, size=64, device="cuda")
+
+    def make():
+        model = _model("fp32")
+        model.detector.stochastic_depth_prob = 0.0
+        opt = AdamWScheduleFree([p for p in model.parameters() if p.requires_grad], lr=1e-4, warmup_steps=3, weight_decay=1e-2)
+        opt.train()
+        return model, opt, CoVWeightingLoss(device="cuda", losses=train.TRAIN1_LOSSES)
+
+    fmask = _model("fp32").get_fmask(batch["labelmap"], None)
+    args = (batch["image"], batch["labelmap"], batch["idmap"], fmask)
+    model_e, opt_e, cov_e = make()
+    flat_e = shard.FlatGradients([p for p in model_e.parameters() if p.requires_grad])
+    losses_e = [float(train.train1_step(model_e, opt_e, cov_e, *args, flat=flat_e)[0]) for _ in range(5)]
+    model_g, opt_g, cov_g = make()
+    graph = train.Train1Graph(model_g, opt_g, cov_g, 2, "cuda", size=64, warmup_batch=args, eager_steps=2)
+    losses_g = [float(graph.step(*args)[0]) for _ in range(3)]
+    assert np.allclose(losses_g, losses_e[2:], rtol=2e-4), (losses_e, losses_g)
+    worst = max(rel_l2(pg.detach().cpu(), pe.detach().cpu()) for pe, pg in zip(model_e.parameters(), model_g.parameters()))
+    assert worst < 1e-3, worst
+    opt_g.sync_from_graph()
+    assert opt_g.param_groups[0]["k"] == opt_e.param_groups[0]["k"] == 5
+    assert abs(opt_g.param_groups[0]["weight_sum"] - opt_e.param_groups[0]["weight_sum"]) < 1e-12 * max(1.0, opt_e.param_groups[0]["weight_sum"])
+    bn_e = getattr(getattr(model_e.detector.backbone.features, "0"), "1")
+    bn_g = getattr(getattr(model_g.detector.backbone.features, "0"), "1")
+    assert int(bn_g.num_batches_tracked) == int(bn_e.num_batches_tracked) == 5
+    assert rel_l2(bn_g.running_var.cpu(), bn_e.running_var.cpu()) < 1e-4
 
 
 # ---- Transformer train step (train3.py) ---------------------------------------------------------------------------------

@@ -21,6 +21,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--mode", default="graph", choices=["graph", "flat", "buckets"],
+                    help="graph: whole step replayed as one CUDA graph (Train1Graph); flat: eager step, gradients in FlatGradients "
+                         "storage; buckets: eager step with GradientBuckets (round-1 path)")
+    ap.add_argument("--no-exchange", action="store_true", help="multi-GPU: skip the gradient all-reduce (to time its exposed cost)")
     args = ap.parse_args()
     from findtextcenternet_b200 import _lib, synthetic, train
     from findtextcenternet_b200.loss_func import CoVWeightingLoss
@@ -36,16 +40,29 @@ def main():
     dev = torch.device("cuda", local)
     model = TextDetectorModel(pre_weights=False)
     model.load_state_dict(synthetic.detector_state_dict(0))
-    model.detector.set_precision(args.precision)
-    model.decoder.precision = args.precision
+    model.set_precision(args.precision)
     model = model.to(dev).train()
     opt = AdamWScheduleFree([p for p in model.parameters() if p.requires_grad], lr=1e-4)
     opt.train()
     cov = CoVWeightingLoss(device=dev, losses=train.TRAIN1_LOSSES)
     batch = synthetic.train1_batch(args.batch, seed=rank, size=args.size, device=dev)
     from findtextcenternet_b200 import shard
-    buckets = shard.GradientBuckets([p for p in model.parameters() if p.requires_grad]) if world > 1 else None
-    fmask = None
+    params = [p for p in model.parameters() if p.requires_grad]
+    group = None
+    if args.no_exchange and world > 1:
+        group = dist.new_group([rank])           # a one-rank group: every collective of the step degenerates, nothing is exchanged
+    buckets = flat = graph = None
+    fmask = model.get_fmask(batch["labelmap"], None)
+    capture_launches = 0
+    if args.mode == "buckets":
+        buckets = shard.GradientBuckets(params, group=group) if world > 1 else None
+    else:
+        flat = shard.FlatGradients(params, group=group)
+    if args.mode == "graph":
+        l00 = _lib.launch_count()
+        graph = train.Train1Graph(model, opt, cov, args.batch, dev, size=args.size, group=group, flat=flat,
+                                  warmup_batch=(batch["image"], batch["labelmap"], batch["idmap"], fmask), eager_steps=2)
+        capture_launches = int(_lib.launch_count() - l00) // 3        # 2 eager steps + the captured one
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     losses = []
     l0 = 0
@@ -57,10 +74,15 @@ def main():
             l0 = _lib.launch_count()
             e0.record()
         fmask = model.get_fmask(batch["labelmap"], fmask)
-        loss, raw = train.train1_step(model, opt, cov, batch["image"], batch["labelmap"], batch["idmap"], fmask, buckets=buckets)
-        losses.append(float(raw["loss"]))
+        if graph is not None:
+            loss, raw = graph.step(batch["image"], batch["labelmap"], batch["idmap"], fmask)
+        else:
+            loss, raw = train.train1_step(model, opt, cov, batch["image"], batch["labelmap"], batch["idmap"], fmask, group=group,
+                                          buckets=buckets, flat=flat)
+        losses.append(raw["loss"].detach().clone())
     e1.record()
     torch.cuda.synchronize()
+    losses = [float(l) for l in losses]
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -69,8 +91,11 @@ def main():
             "metric": "768x768 images/sec train1 step (fwd + loss_func + bwd + AdamWScheduleFree)", "value": world * args.batch / (float(ms) / 1e3),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms),
             "dtype": args.precision, "data": "synthetic", "scaling": "weak",
-            "config": {"workload": f"train1 step, batch {args.batch}/GPU, {args.size}x{args.size}", "kernels": "first correct path (CUDA-core wgrad)"},
-            "gpu_launches": int(_lib.launch_count() - l0), "losses": losses,
+            "config": {"workload": f"train1 step, batch {args.batch}/GPU, {args.size}x{args.size}", "mode": args.mode,
+                       "exchange": "none" if (args.no_exchange or world == 1) else "bucketed all-reduce inside backward"},
+            "gpu_launches": (capture_launches * args.steps) if graph is not None else int(_lib.launch_count() - l0),
+            "launches_per_step": capture_launches if graph is not None else int(_lib.launch_count() - l0) // max(args.steps, 1),
+            "losses": losses,
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
     if world > 1:
         dist.destroy_process_group()
