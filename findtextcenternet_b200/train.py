@@ -102,6 +102,7 @@ class Train1Graph:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.flat.check_views()
+        torch.cuda.empty_cache()        # hand the warm-up steps' activation blocks back before the graph's private pool grows
         optimizer.prepare_graph()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
