@@ -104,6 +104,8 @@ SYMBOLS = {
     "ftc_train_bn_act": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
     "ftc_train_bn_act_bwd": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp]),
     "ftc_train_conv2d_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ftc_train_conv2d_wgrad_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "ftc_train_conv2d_wgrad_ws": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "ftc_train_conv2d_dgrad": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ftc_train_dwconv3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ftc_train_dwconv3x3_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -122,6 +124,7 @@ SYMBOLS = {
     "ftc_train_attention_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "ftc_train_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ftc_debug_set_wgrad_mma": (_i, [_i]),
+    "ftc_debug_set_wgrad_tc": (_i, [_i]),
     "ftc_page_maps": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "ftc_op_attention": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }

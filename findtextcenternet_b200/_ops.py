@@ -205,9 +205,11 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, stride: int = 1)
     cout = dy.shape[-1]
     assert dy.shape == (b, (h - 1) // stride + 1, (w - 1) // stride + 1, cout), (x.shape, dy.shape)
     dw = torch.empty(cout, cin, ksize, ksize, dtype=torch.float32, device=x.device)
+    nbytes = int(lib.ftc_train_conv2d_wgrad_scratch_bytes(b, h, w, cin, cout, ksize, stride)) if x.dtype == torch.bfloat16 else 0
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
     with torch.cuda.device(x.device):
-        _lib.check(lib.ftc_train_conv2d_wgrad(x.data_ptr(), dy.data_ptr(), _dt(x), b, h, w, cin, cout, ksize, stride,
-                                              dw.data_ptr(), _s(x)), "ftc_train_conv2d_wgrad")
+        _lib.check(lib.ftc_train_conv2d_wgrad_ws(x.data_ptr(), dy.data_ptr(), _dt(x), b, h, w, cin, cout, ksize, stride,
+                                                 dw.data_ptr(), _p(scratch), nbytes, _s(x)), "ftc_train_conv2d_wgrad_ws")
     return dw
 
 

@@ -244,6 +244,13 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
  * splits); dgrad writes dx = conv_transpose(dy, w) (+ add, e.g. the gradient arriving over a residual connection). */
 int ftc_train_conv2d_wgrad(const void* x, const void* dy, int dtype, int batch, int h, int w, int cin, int cout, int ksize,
                            int stride, float* dw_oihw, void* stream);
+/* The same weight gradient with caller-provided scratch: bf16 stride-1 convolutions / linears (cin, cout multiples of 8) run on the
+ * tcgen05 tensor cores -- dy and the input as MN-major UMMA operands straight from TMA tensor boxes, split over pixel tiles, fp32
+ * partial tiles in `scratch` added in a fixed order (deterministic, no atomics); other shapes fall back to ftc_train_conv2d_wgrad.
+ * scratch_bytes >= ftc_train_conv2d_wgrad_scratch_bytes(...) (0 = the tcgen05 kernel does not take the shape). */
+size_t ftc_train_conv2d_wgrad_scratch_bytes(int batch, int h, int w, int cin, int cout, int ksize, int stride);
+int ftc_train_conv2d_wgrad_ws(const void* x, const void* dy, int dtype, int batch, int h, int w, int cin, int cout, int ksize,
+                              int stride, float* dw_oihw, void* scratch, size_t scratch_bytes, void* stream);
 int ftc_train_conv2d_dgrad(const void* dy, int dtype, int batch, int h, int w, int cin, int cout, int ksize, int stride,
                            const float* w_oihw, const void* add, void* dx, void* stream);
 /* depthwise 3x3 (pad 1, stride 1 | 2) of MBConv (efficientnet.py:136-147): raw forward, data gradient, weight gradient;
@@ -313,6 +320,9 @@ int ftc_page_maps(const float* heat9, int batch, int h, int w, const int* tile_m
 /* debug / staging: route bf16 weight gradients (cin, cout multiples of 8) through the mma.sync kernel: 1 on, 0 off, -1 follow the
  * FTC_WGRAD_MMA environment variable (default; off when unset) */
 int ftc_debug_set_wgrad_mma(int on);
+/* debug / staging: the tcgen05 weight gradient: 0 off, 1 on (three N = 64 row-tap instructions per column shift), 2 on with the
+ * three row taps fused into one N = 192 instruction, -1 follow the FTC_WGRAD_TC environment variable (default 1) */
+int ftc_debug_set_wgrad_tc(int mode);
 
 #ifdef __cplusplus
 }
