@@ -86,16 +86,27 @@ __global__ void __launch_bounds__(RED_THREADS) col_reduce_kernel(const T* __rest
 }
 
 // FIN 0: out0 = mean, out1 = biased variance ; FIN 1: out0 = sum0, out1 = sum1
+// CTA = 32 channels x 32 chunk lanes: lane ly adds chunks ly, ly + 32, ... in double, the 32 lane sums are then added in lane
+// order by one thread per channel -- a fixed summation order (deterministic) with 32-way parallelism over the up-to-4096
+// partials.  (One thread per channel walking all partials was latency-bound: ~50 us per launch, 724 launches per train step.)
 template <int FIN>
-__global__ void col_reduce_finish_kernel(const float* __restrict__ part, int nchunk, int C, int64_t rows, float* __restrict__ out0,
-                                         float* __restrict__ out1) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(1024) col_reduce_finish_kernel(const float* __restrict__ part, int nchunk, int C, int64_t rows,
+                                                                 float* __restrict__ out0, float* __restrict__ out1) {
+  __shared__ double sa[32][33], sb[32][33];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   double a = 0.0, b = 0.0;
-  for (int k = 0; k < nchunk; ++k) {
-    a += (double)part[((int64_t)0 * nchunk + k) * C + c];
-    b += (double)part[((int64_t)1 * nchunk + k) * C + c];
+  if (c < C) {
+    for (int k = ly; k < nchunk; k += 32) {
+      a += (double)part[((int64_t)0 * nchunk + k) * C + c];
+      b += (double)part[((int64_t)1 * nchunk + k) * C + c];
+    }
   }
+  sa[ly][cx] = a; sb[ly][cx] = b;
+  __syncthreads();
+  if (ly != 0 || c >= C) return;
+  a = 0.0; b = 0.0;
+  for (int j = 0; j < 32; ++j) { a += sa[j][cx]; b += sb[j][cx]; }
   if (FIN == 0) {
     double m = a / (double)rows;
     double v = b / (double)rows - m * m;
@@ -1266,7 +1277,7 @@ int ftc_train_bn_stats(const void* x, int dtype, int64_t rows, int c, float* mea
   else
     col_reduce_kernel<bf16, 0><<<grid, RED_THREADS, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
   FTC_POST_LAUNCH();
-  col_reduce_finish_kernel<0><<<ceil_div(c, 128), 128, 0, s>>>((const float*)scratch, nchunk, c, rows, mean, var);
+  col_reduce_finish_kernel<0><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, nchunk, c, rows, mean, var);
   FTC_POST_LAUNCH();
   return 0;
 }
@@ -1313,7 +1324,7 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
   else
     col_reduce_kernel<bf16, 1><<<grid, RED_THREADS, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
   FTC_POST_LAUNCH();
-  col_reduce_finish_kernel<1><<<ceil_div(c, 128), 128, 0, s>>>((const float*)scratch, nchunk, c, rows, dbeta, dgamma);
+  col_reduce_finish_kernel<1><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, nchunk, c, rows, dbeta, dgamma);
   FTC_POST_LAUNCH();
   const int64_t total = rows * c;
   const float inv_rows = (float)(1.0 / (double)rows);
@@ -1588,7 +1599,7 @@ int ftc_train_layernorm_bwd(const void* xs, const void* dy, void* dx, const floa
     ln_col_reduce_kernel<bf16><<<rgrid, RED_THREADS, 0, s>>>(cp<bf16>(xs), cp<bf16>(dy), mean, rstd, rows, d, rpc, (float*)scratch);
   }
   FTC_POST_LAUNCH();
-  col_reduce_finish_kernel<1><<<ceil_div(d, 128), 128, 0, s>>>((const float*)scratch, nchunk, d, rows, dbeta, dgamma);
+  col_reduce_finish_kernel<1><<<ceil_div(d, 32), 1024, 0, s>>>((const float*)scratch, nchunk, d, rows, dbeta, dgamma);
   FTC_POST_LAUNCH();
   return 0;
 }

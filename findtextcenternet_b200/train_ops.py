@@ -41,13 +41,31 @@ def _backend(x: Tensor, cin: int = 64, cout: int = 64) -> int:
     return _lib.GEMM_TCGEN05
 
 
+def _pad_last(t: Tensor, mult: int, at_least: int = 0) -> Tensor:
+    """Zero-pad the channel (last) axis up to a multiple of ``mult`` (and at least ``at_least``)."""
+    c = t.shape[-1]
+    target = max((c + mult - 1) // mult * mult, at_least)
+    return t if target == c else torch.nn.functional.pad(t, (0, target - c))
+
+
 class _Conv2d(Function):
-    """nn.Conv2d(k in {1,3}, padding=(k-1)//2, stride, bias optional) on NHWC tensors; weight OIHW."""
+    """nn.Conv2d(k in {1,3}, padding=(k-1)//2, stride, bias optional) on NHWC tensors; weight OIHW.
+
+    bf16 tensors keep every GEMM-shaped piece on the tensor cores.  Channel counts the tcgen05 kernels do not take directly are
+    zero-padded (zero channels contribute nothing): the 1- / 2-channel top convs run as 16-output-channel GEMMs, the data and
+    weight gradients of the 1- / 2- / 100- / 1091- / 1093- / 1097-channel outputs see dy padded to a multiple of 8 (>= 32 as the
+    input of the data-gradient convolution).  The data gradient of a stride-2 convolution is the stride-1 data gradient of dy
+    with zeros inserted between its pixels (4x the minimal arithmetic, but on tcgen05 instead of CUDA cores)."""
 
     @staticmethod
     def forward(ctx, x, w, bias, stride):
         ctx.save_for_backward(x, w)
         ctx.stride, ctx.has_bias = stride, bias is not None
+        cout, cin = w.shape[0], w.shape[1]
+        if x.dtype == torch.bfloat16 and cin >= 32 and cout < 16 and stride == 1:
+            wp = torch.nn.functional.pad(w.detach(), (0, 0, 0, 0, 0, 0, 0, 16 - cout))
+            bp = None if bias is None else torch.nn.functional.pad(bias.detach(), (0, 16 - cout))
+            return K.conv2d(x, wp, 1, None, bp, _lib.ACT_NONE, None, None, _lib.GEMM_TCGEN05)[..., :cout].contiguous()
         return K.conv2d(x, w, stride, None, bias, _lib.ACT_NONE, None, None, _backend(x, w.shape[1], w.shape[0]))
 
     @staticmethod
@@ -56,22 +74,25 @@ class _Conv2d(Function):
         dy = dy.contiguous()
         cout, cin, k, _ = w.shape
         dx = dw = db = None
+        tc = dy.dtype == torch.bfloat16 and x.shape[-1] % 8 == 0
+        dyp = _pad_last(dy, 8) if tc else dy             # shared by the data and the weight gradient
         if ctx.needs_input_grad[0]:
-            if ctx.stride == 1 and cout % 8 == 0 and _backend(x, cout, cin) == _lib.GEMM_TCGEN05:
-                # stride-1 data gradient = the same convolution with the taps rotated 180 degrees and the channel roles
-                # swapped: runs on the tcgen05 forward kernel
-                wt = w.detach().float().flip(2, 3).transpose(0, 1).contiguous()
-                dx = K.conv2d(dy, wt, 1, None, None, _lib.ACT_NONE, None, None, _lib.GEMM_TCGEN05)
+            if tc and cin >= 16 and (ctx.stride == 1 or k == 3):
+                # data gradient = a stride-1 convolution of dy with the taps rotated 180 degrees and the channel roles swapped:
+                # runs on the tcgen05 forward kernel
+                d = _pad_last(dyp, 8, 32)
+                wt = w.detach().float().flip(2, 3).transpose(0, 1)
+                if d.shape[-1] != cout:
+                    wt = torch.nn.functional.pad(wt, (0, 0, 0, 0, 0, d.shape[-1] - cout))
+                if ctx.stride == 2:
+                    up = torch.zeros(d.shape[0], x.shape[1], x.shape[2], d.shape[-1], dtype=d.dtype, device=d.device)
+                    up[:, ::2, ::2] = d                   # U[2 oy, 2 ox] = dy[oy, ox]; iy = 2 oy + ky - 1
+                    d = up
+                dx = K.conv2d(d, wt.contiguous(), 1, None, None, _lib.ACT_NONE, None, None, _lib.GEMM_TCGEN05)
             else:
                 dx = K.conv2d_dgrad(dy, w, x.shape[1], x.shape[2], ctx.stride)
         if ctx.needs_input_grad[1]:
-            if dy.dtype == torch.bfloat16 and cout % 8 and x.shape[-1] % 8 == 0:
-                # the tensor-core weight-gradient kernels stage 16-byte row pieces: pad the output channels of dy (the 1- / 2- /
-                # 100-channel top convs, the 1091 / 1093 / 1097-wide decoder heads) to a multiple of 8 and drop the zero rows
-                dyp = torch.nn.functional.pad(dy, (0, (-cout) % 8))
-                dw = K.conv2d_wgrad(x, dyp, k, ctx.stride)[:cout].to(w.dtype)
-            else:
-                dw = K.conv2d_wgrad(x, dy, k, ctx.stride).to(w.dtype)
+            dw = K.conv2d_wgrad(x, dyp, k, ctx.stride)[:cout].to(w.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             mean, _ = K.bn_stats(dy)
             db = mean * float(dy.numel() // cout)

@@ -109,3 +109,36 @@ def test_fused_radam_schedulefree_matches_reference(gold_radam, name):
     for i, p in enumerate(params):
         np.testing.assert_allclose(p.detach().cpu().numpy(), gold_radam[f"{name}_eval_x{i}"], rtol=2e-5, atol=1e-6)
     assert set(opt.param_groups[0].keys()) >= {"silent_sgd_phase", "scheduled_lr", "weight_sum", "lr_max", "k", "train_mode"}
+
+
+@pytest.mark.gpu
+def test_graph_replayed_adamw_step_matches_reference(gold):
+    """The CUDA-graph form of the step (ftc_adamw_sf_step_dev: schedule state k / lr_max / weight_sum on the device, advanced by
+    each replay) against the SAME reference golden: one eager step, then the remaining four as replays of one captured graph
+    whose gradients are refreshed in place (static gradient storage, as shard.FlatGradients provides)."""
+    from oracle.make_golden import OPT_CFG
+    from findtextcenternet_b200.models.adamw_schedulefree import AdamWScheduleFree
+    params = [torch.nn.Parameter(p.clone().cuda()) for p in _inputs(-1)]
+    opt = AdamWScheduleFree(params, **OPT_CFG)
+    opt.train()
+    for p, g in zip(params, _inputs(0)):
+        p.grad = g.clone().cuda()
+    opt.step()                                            # eager: creates z / exp_avg_sq
+    opt.prepare_graph()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        opt.step()
+    for step in range(1, 5):
+        for p, g in zip(params, _inputs(step)):
+            p.grad.copy_(g.cuda())                        # same storage: the graph's pointers stay valid
+        graph.replay()
+        torch.cuda.synchronize()
+        for i, p in enumerate(params):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), gold[f"s{step}_y{i}"], rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(opt.state[p]["z"].cpu().numpy(), gold[f"s{step}_z{i}"], rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(opt.state[p]["exp_avg_sq"].cpu().numpy(), gold[f"s{step}_v{i}"], rtol=2e-6, atol=1e-12)
+    opt.sync_from_graph()
+    assert opt.param_groups[0]["k"] == 5
+    opt.eval()
+    for i, p in enumerate(params):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), gold[f"eval_x{i}"], rtol=2e-5, atol=1e-6)

@@ -292,8 +292,11 @@ def test_train_mode_forward_under_no_grad_updates_bn_running_stats():
 
 def test_train1_graph_replay_equals_eager_steps():
     """train.Train1Graph (the whole train1 step captured into a CUDA graph: device-resident CoV statistics, device-scheduled
-    AdamWScheduleFree, gradients in FlatGradients storage) must walk the same trajectory as the eager train1_step: same losses,
-    same parameters after 2 eager + 3 replayed steps vs 5 eager steps (fp32, StochasticDepth off so both draw nothing)."""
+    AdamWScheduleFree, gradients in FlatGradients storage) must walk the same trajectory as the eager train1_step: 2 eager + 3
+    replayed steps vs 5 eager steps (fp32, StochasticDepth off so neither draws anything).  The 64x64 fixture normalises over 8
+    samples in its last stages and amplifies rounding noise from step to step (the weight-gradient kernels add their pixel splits
+    with fp32 atomics), so the allowed deviation is measured: a SECOND eager run gives the run-to-run spread, and the graph must
+    stay within 5x of it (and the step the graph takes first, from identical parameters, must agree to 1e-4)."""
     from findtextcenternet_b200 import shard, synthetic, train
     from findtextcenternet_b200.loss_func import CoVWeightingLoss
     from findtextcenternet_b200.models.adamw_schedulefree import AdamWScheduleFree
@@ -308,22 +311,39 @@ def test_train1_graph_replay_equals_eager_steps():
 
     fmask = _model("fp32").get_fmask(batch["labelmap"], None)
     args = (batch["image"], batch["labelmap"], batch["idmap"], fmask)
-    model_e, opt_e, cov_e = make()
-    flat_e = shard.FlatGradients([p for p in model_e.parameters() if p.requires_grad])
-    losses_e = [float(train.train1_step(model_e, opt_e, cov_e, *args, flat=flat_e)[0]) for _ in range(5)]
+
+    def eager_run():
+        model, opt, cov = make()
+        flat = shard.FlatGradients([p for p in model.parameters() if p.requires_grad])
+        losses = [float(train.train1_step(model, opt, cov, *args, flat=flat)[0]) for _ in range(5)]
+        return model, opt, cov, losses
+
+    model_e, opt_e, cov_e, losses_e = eager_run()
+    model_e2, _, _, losses_e2 = eager_run()
     model_g, opt_g, cov_g = make()
     graph = train.Train1Graph(model_g, opt_g, cov_g, 2, "cuda", size=64, warmup_batch=args, eager_steps=2)
     losses_g = [float(graph.step(*args)[0]) for _ in range(3)]
-    assert np.allclose(losses_g, losses_e[2:], rtol=2e-4), (losses_e, losses_g)
-    worst = max(rel_l2(pg.detach().cpu(), pe.detach().cpu()) for pe, pg in zip(model_e.parameters(), model_g.parameters()))
-    assert worst < 1e-3, worst
+    # schedule state and iteration counters are exact
     opt_g.sync_from_graph()
-    assert opt_g.param_groups[0]["k"] == opt_e.param_groups[0]["k"] == 5
-    assert abs(opt_g.param_groups[0]["weight_sum"] - opt_e.param_groups[0]["weight_sum"]) < 1e-12 * max(1.0, opt_e.param_groups[0]["weight_sum"])
+    ge, gg = opt_e.param_groups[0], opt_g.param_groups[0]
+    assert gg["k"] == ge["k"] == 5 and abs(gg["weight_sum"] - ge["weight_sum"]) <= 1e-12 * ge["weight_sum"] and gg["lr_max"] == ge["lr_max"]
+    assert float(cov_g._it) == float(cov_e._it) == 4.0
     bn_e = getattr(getattr(model_e.detector.backbone.features, "0"), "1")
     bn_g = getattr(getattr(model_g.detector.backbone.features, "0"), "1")
     assert int(bn_g.num_batches_tracked) == int(bn_e.num_batches_tracked) == 5
-    assert rel_l2(bn_g.running_var.cpu(), bn_e.running_var.cpu()) < 1e-4
+    # first replayed step starts from (almost) identical parameters
+    assert abs(losses_g[0] - losses_e[2]) <= 1e-4 * abs(losses_e[2]), (losses_e, losses_g)
+    noise_l = max(abs(a - b) / abs(a) for a, b in zip(losses_e, losses_e2))
+    dev_l = max(abs(a - b) / abs(a) for a, b in zip(losses_e[2:], losses_g))
+
+    def spread(ma, mb):
+        return max(rel_l2(pb.detach().cpu(), pa.detach().cpu()) for pa, pb in zip(ma.parameters(), mb.parameters()))
+
+    noise_p, dev_p = spread(model_e, model_e2), spread(model_e, model_g)
+    print(f"eager-vs-eager: loss {noise_l:.3e} params {noise_p:.3e}; graph-vs-eager: loss {dev_l:.3e} params {dev_p:.3e}")
+    assert dev_l <= max(5 * noise_l, 2e-4), (noise_l, dev_l, losses_e, losses_e2, losses_g)
+    assert dev_p <= max(5 * noise_p, 1e-5), (noise_p, dev_p)
+    assert rel_l2(bn_g.running_var.cpu(), bn_e.running_var.cpu()) <= max(5 * noise_l, 1e-4)
 
 
 # ---- Transformer train step (train3.py) ---------------------------------------------------------------------------------
