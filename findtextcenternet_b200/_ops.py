@@ -205,11 +205,19 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, stride: int = 1)
     cout = dy.shape[-1]
     assert dy.shape == (b, (h - 1) // stride + 1, (w - 1) // stride + 1, cout), (x.shape, dy.shape)
     dw = torch.empty(cout, cin, ksize, ksize, dtype=torch.float32, device=x.device)
-    nbytes = int(lib.ftc_train_conv2d_wgrad_scratch_bytes(b, h, w, cin, cout, ksize, stride)) if x.dtype == torch.bfloat16 else 0
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
+    # bf16 shapes the tcgen05 kernel takes need scratch for its per-split partial tiles (0 bytes = not taken: CUDA-core / mma.sync
+    # kernels of the plain entry point; the CPU kernel-emulation library has only that one)
+    nbytes = 0
+    if x.dtype == torch.bfloat16 and hasattr(lib, "ftc_train_conv2d_wgrad_scratch_bytes"):
+        nbytes = int(lib.ftc_train_conv2d_wgrad_scratch_bytes(b, h, w, cin, cout, ksize, stride))
     with torch.cuda.device(x.device):
-        _lib.check(lib.ftc_train_conv2d_wgrad_ws(x.data_ptr(), dy.data_ptr(), _dt(x), b, h, w, cin, cout, ksize, stride,
-                                                 dw.data_ptr(), _p(scratch), nbytes, _s(x)), "ftc_train_conv2d_wgrad_ws")
+        if nbytes:
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            _lib.check(lib.ftc_train_conv2d_wgrad_ws(x.data_ptr(), dy.data_ptr(), _dt(x), b, h, w, cin, cout, ksize, stride,
+                                                     dw.data_ptr(), scratch.data_ptr(), nbytes, _s(x)), "ftc_train_conv2d_wgrad_ws")
+        else:
+            _lib.check(lib.ftc_train_conv2d_wgrad(x.data_ptr(), dy.data_ptr(), _dt(x), b, h, w, cin, cout, ksize, stride,
+                                                  dw.data_ptr(), _s(x)), "ftc_train_conv2d_wgrad")
     return dw
 
 
