@@ -13,6 +13,11 @@ seeded synthetic weights (BN-calibrated; findtextcenternet_b200/synthetic.py).  
 `roofline`: tensor-pipe bound.  achieved = algorithmic FLOPs of the dominant kernel family (the tcgen05 implicit-GEMM
             convolution, every dense conv launch of one forward) / the summed CUDA-event durations of those launches,
             measured live by ftc_detector_forward_timed; peak = MEASURED_PEAKS.json bf16_tflops_sustained.
+`train1`  : BASELINE.json configs[2] measured in the same run on every rank (tools/bench_train.py::run): the whole step as one
+            CUDA graph, batch 16 per GPU, gradients all-reduced in place over NCCL from inside backward; whole-job images/s, its
+            own roofline (2 717 GFLOP/image) and, for N > 1, the step time with the exchange removed (exposed all-reduce).
+`gpu_reference`: the reference's math on the SAME GPU through torch's library kernels (cuDNN eager, bf16 autocast): the bar.
+`transformer_cfg4`, `page_2048`: BASELINE.json configs[3] / configs[4] as labelled side objects (child processes, N = 1).
 `cpu_baseline`: the oracle port (oracle/detector_oracle.py, fp32 torch CPU ops restating the reference) on the host cores.
 --impl reference: the same CPU port timed as the reference arm (the reference is Python+torchvision and cannot travel
             to the GPU box; oracle/ restates it and is pinned to it by tests/golden).
@@ -254,6 +259,17 @@ def run_ours(args):
                 ips, threads, times = cpu_port_images_per_sec(1, 3, 1)
                 cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                        "sample": "1 image per pass x 3 passes (+1 warm-up) of the same forward, fp32 oracle port on the host cores"}
+    # ---- configs[2]: the train1 step (fwd + losses + bwd + in-place bucket all-reduce + optimizer) at batch 16 per GPU, on every
+    # rank (NCCL): whole-job images/s, and the step time without the exchange to show what the all-reduce costs when overlapped
+    train1 = None
+    if not args.no_train1:
+        del x_dev, flush, tiles
+        proc.detector = None
+        det = proc = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        train1 = train1_measurement(world, dev, args.train_batch)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -276,12 +292,11 @@ def run_ours(args):
     }
     if world == 1 and not args.no_gpu_reference:
         line["gpu_reference"] = gpu_reference_side_measurement(B, compile_too=args.gpu_reference_compile)
-    if world == 1 and not args.no_train1:
-        line["train1"] = train1_side_measurement()
-        if "error" not in line["train1"]:
-            # same step with the staged mma.sync weight-gradient kernel (off by default until it has run on hardware): its
-            # loss trajectory next to the default path's is the first hardware evidence for or against it
-            line["train1_wgrad_mma_staged"] = train1_side_measurement(env={"FTC_WGRAD_MMA": "1"})
+    if train1 is not None:
+        line["train1"] = train1
+    if world == 1 and not args.no_side:
+        line["transformer_cfg4"] = side_measurement("bench_transformer.py", ["cfg4", "bf16"], 240)
+        line["page_2048"] = side_measurement("bench_page.py", ["--pages", "3", "--chunks", "32"], 240)
     print(json.dumps(line), flush=True)
 
 
@@ -307,25 +322,64 @@ def gpu_reference_side_measurement(batch: int, compile_too: bool = False, timeou
         return {"error": repr(e)[:300]}
 
 
-def train1_side_measurement(batch: int = 4, timeout_s: int = 200, env=None):
-    """Auxiliary, clearly labelled: the train1 step (BASELINE.json configs[2]: fwd + loss_func + bwd + AdamWScheduleFree) timed by
-    tools/bench_train.py in a CHILD process (its own CUDA context, hard timeout), so that nothing it does can disturb the
-    headline forward numbers above.  First-correct-path kernels (CUDA-core weight gradients) at a small per-GPU batch: a
-    progress marker, not the configs[2] headline (batch 16 per GPU)."""
+def _tool(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ftc_tool_" + name[:-3], os.path.join(ROOT, "tools", name))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def train1_measurement(world: int, dev, batch: int = 16, steps: int = 3):
+    """BASELINE.json configs[2] on all ranks of this job (tools/bench_train.py::run): the step replayed as one CUDA graph
+    (train.Train1Graph); if the capture fails on any rank every rank falls back to the eager step with FlatGradients.  N > 1:
+    a second run with the gradient exchange removed gives the exposed all-reduce time (step with - step without)."""
+    import torch
+    import torch.distributed as dist
+    bt = _tool("bench_train.py")
+
+    def agreed_run(mode, no_exchange):
+        out, err = None, 0
+        try:
+            out = bt.run(batch=batch, steps=steps, warmup=1, mode=mode, no_exchange=no_exchange, device=dev)
+        except Exception as e:          # report, and let the other ranks know
+            out, err = {"error": repr(e)[:400], "mode": mode}, 1
+        flag = torch.tensor([err], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        return out, int(flag.item()) != 0
+
     try:
-        import torch
-        torch.cuda.empty_cache()
-        cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_train.py"), "--batch", str(batch), "--steps", "2", "--warmup", "1"]
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=dict(os.environ, **(env or {})))
+        res, failed = agreed_run("graph", False)
+        if failed:
+            first_error = res.get("error") if isinstance(res, dict) else None
+            torch.cuda.empty_cache()
+            res, failed2 = agreed_run("flat", False)
+            if isinstance(res, dict):
+                res["graph_capture_error"] = first_error or "capture failed on another rank"
+            if failed2:
+                return res
+        if world > 1 and "error" not in res:
+            base, failed3 = agreed_run(res["config"]["mode"], True)
+            if not failed3:
+                res["no_exchange_ms_per_step"] = base["ms_per_step"]
+                res["exposed_allreduce_ms"] = res["ms_per_step"] - base["ms_per_step"]
+                res["allreduce_bytes_per_step"] = 262350422 * 4
+        return res
+    except Exception as e:
+        return {"error": repr(e)[:400]}
+
+
+def side_measurement(tool: str, tool_args, timeout_s: int):
+    """A labelled side object measured by a tools/ script in a CHILD process (own CUDA context, hard timeout): never the headline,
+    and nothing it does can disturb the numbers above."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), *tool_args], capture_output=True, text=True, timeout=timeout_s)
         rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if r.returncode != 0 or not rows:
             return {"error": (r.stderr or r.stdout)[-300:]}
-        d = json.loads(rows[-1])
-        return {"metric": d["metric"], "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "batch_per_gpu": batch,
-                "steps": d["steps"], "warmup": d["warmup"], "dtype": d["dtype"], "gpu_launches": d["gpu_launches"],
-                "losses": d["losses"], "peak_mem_gb": d["peak_mem_gb"],
-                "note": "first correct path (CUDA-core weight gradients, per-call weight packing); child process, CUDA events"}
-    except Exception as e:      # the side measurement must never cost the headline line
+        return json.loads(rows[-1])
+    except Exception as e:
         return {"error": repr(e)[:300]}
 
 
@@ -338,7 +392,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16_simt", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train1", action="store_true", help="skip the auxiliary train1-step measurement (N = 1 only)")
+    ap.add_argument("--no-train1", action="store_true", help="skip the train1-step measurement (BASELINE.json configs[2])")
+    ap.add_argument("--train-batch", type=int, default=16, help="train1 batch per GPU (configs[2]: 16)")
+    ap.add_argument("--no-side", action="store_true", help="skip the transformer (configs[3]) and page (configs[4]) side objects")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the same-GPU torch (cuDNN eager) reference measurement")
     ap.add_argument("--gpu-reference-compile", action="store_true", help="also time the torch.compile'd reference math (minutes)")
     args = ap.parse_args()
