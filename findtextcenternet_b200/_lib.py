@@ -123,6 +123,9 @@ SYMBOLS = {
     "ftc_train_embed3_bwd": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ftc_train_attention_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "ftc_train_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ftc_box_hists": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
+    "ftc_select_boxes_scratch_bytes": (_sz, [_i]),
+    "ftc_select_boxes": (_i, [_vp, _vp, _i, _vp, _i, _vp, _d, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ftc_debug_set_wgrad_mma": (_i, [_i]),
     "ftc_debug_set_wgrad_tc": (_i, [_i]),
     "ftc_page_maps": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp]),

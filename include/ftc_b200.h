@@ -317,11 +317,26 @@ int ftc_train_attention_bwd(const void* q, const void* k, const void* v, const f
 int ftc_page_maps(const float* heat9, int batch, int h, int w, const int* tile_meta, float* page, int page_h4, int page_w4, int scale,
                   void* stream);
 
+/* ---- page-level box selection of run_detector (process_ocr_base.py:540-650, imageHist :652-693), on the device ----
+ * ftc_box_hists: for each of the n candidate boxes (loc fp32 [n][9] = p, cx, cy, w, h, c1, c2, c4, c8 as ftc_peak_decode writes
+ * them) the reference's two histogram scores on the padded page (uint8 [page_h][page_w][3]): hists[0][i] = "loose" crop of the
+ * threshold pass (:543-556, Python wrap-around slice semantics included), hists[1][i] = "tight" crop of the greedy pass (:571-576);
+ * device double [2][n], bit-identical to numpy.  The threshold is median(hists[0]) / 5 (caller).
+ * ftc_select_boxes: the greedy pass over `order` (candidate indices by descending score), the separator veto and the 3x3 code-map
+ * maximum.  seps_all fp32 [h4][w4], code_all fp32 [4][h4][w4] (rows 2 and 3..6 of ftc_page_maps).  Outputs: *n_out accepted boxes,
+ * sel_idx int32 [n] their candidate indices in acceptance order, out_loc fp32 [n][9], out_gf fp32 [n][feat_ch] (first *n_out rows).
+ * One CTA (the greedy loop is sequential); scratch: ftc_select_boxes_scratch_bytes(n). */
+int ftc_box_hists(const unsigned char* page, int page_h, int page_w, const float* loc, int n, double* hists, void* stream);
+size_t ftc_select_boxes_scratch_bytes(int n);
+int ftc_select_boxes(const float* loc, const float* gfeat, int feat_ch, const int* order, int n, const double* tight, double th,
+                     const float* seps_all, const float* code_all, int h4, int w4, int scale, int* n_out, int* sel_idx, float* out_loc,
+                     float* out_gf, void* scratch, size_t scratch_bytes, void* stream);
+
 /* debug / staging: route bf16 weight gradients (cin, cout multiples of 8) through the mma.sync kernel: 1 on, 0 off, -1 follow the
  * FTC_WGRAD_MMA environment variable (default; off when unset) */
 int ftc_debug_set_wgrad_mma(int on);
 /* debug / staging: the tcgen05 weight gradient: 0 off, 1 on (three N = 64 row-tap instructions per column shift), 2 on with the
- * three row taps fused into one N = 192 instruction, -1 follow the FTC_WGRAD_TC environment variable (default 1) */
+ * three row taps fused into one N = 192 instruction, -1 follow the FTC_WGRAD_TC environment variable (default 2) */
 int ftc_debug_set_wgrad_tc(int mode);
 
 #ifdef __cplusplus

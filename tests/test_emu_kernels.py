@@ -477,3 +477,75 @@ def test_detector_blocks_through_product_wrappers_on_emu(ops_on_emu, monkeypatch
     for (n, b_ref), (_, b_emu) in zip(ref_root.named_buffers(), emu_root.named_buffers()):
         btol = 1e-3 + (0 if dt == torch.float32 else 2e-2)      # + absolute floor: means of exactly centred inputs are pure noise
         assert float((b_emu.double() - b_ref.double()).norm()) <= btol * float(b_ref.double().norm()) + (1e-5 if dt == torch.float32 else 1e-3), n
+
+
+# ---- page-level box selection (csrc/page_ops.cu) on host threads vs the reference-pinned oracle --------------------------------
+def _select_on_emu(emu, loc32, gf, tight, th, seps, code):
+    import numpy as np
+    n = loc32.shape[0]
+    order = torch.from_numpy(np.argsort(-loc32[:, 0].astype(np.float64), kind="stable").astype(np.int32))
+    loc_t, gf_t, tight_t = torch.from_numpy(loc32.copy()), torch.from_numpy(gf.copy()), torch.from_numpy(tight.copy())
+    seps_t, code_t = torch.from_numpy(seps.copy()), torch.from_numpy(np.ascontiguousarray(code))
+    emu.ftc_select_boxes_scratch_bytes.restype = C.c_size_t
+    nb = emu.ftc_select_boxes_scratch_bytes(n)
+    scr = torch.empty(nb, dtype=torch.uint8)
+    n_out, sel = torch.zeros(1, dtype=torch.int32), torch.zeros(n, dtype=torch.int32)
+    out_loc, out_gf = torch.zeros(n, 9), torch.zeros(n, gf.shape[1])
+    ok(emu, emu.ftc_select_boxes(P(loc_t), P(gf_t), gf.shape[1], P(order), n, P(tight_t), C.c_double(th), P(seps_t), P(code_t),
+                                 seps.shape[0], seps.shape[1], 4, P(n_out), P(sel), P(out_loc), P(out_gf), P(scr), C.c_size_t(nb), None))
+    m = int(n_out[0])
+    return out_loc[:m].numpy(), out_gf[:m].numpy(), sel[:m].numpy()
+
+
+def test_emu_box_hists_and_select_boxes_real_page():
+    """ftc_box_hists + ftc_select_boxes (kernel source on host threads) on the 402 per-tile peaks of the 4-tile golden page: the
+    histogram scores are bit-identical to the oracle's numpy imageHist, and the selected boxes equal the UNMODIFIED reference
+    run_detector's final output (tests/golden/page4_seed0.npz), bit for bit."""
+    import numpy as np
+    from conftest import GOLDEN
+    from findtextcenternet_b200 import synthetic
+    from findtextcenternet_b200.process_ocr_b200 import page_tiles
+    from oracle import detector_oracle as DO
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "emu"))
+    import build_emu
+    emu = C.CDLL(build_emu.build())
+    emu.ftc_last_error.restype = C.c_char_p
+    gold = np.load(os.path.join(GOLDEN, "page4_seed0.npz"))
+    h, w = (int(v) for v in gold["image_hw"])
+    page, _ = page_tiles(synthetic.page_image(int(gold["seed"]), h, w))
+    loc32, gf = gold["pre_locations"], gold["pre_glyphfeatures"]
+    n = loc32.shape[0]
+    page_t = torch.from_numpy(np.ascontiguousarray(page))
+    hists = torch.zeros(2, n, dtype=torch.float64)
+    loc_t = torch.from_numpy(loc32.copy())
+    ok(emu, emu.ftc_box_hists(P(page_t), page.shape[0], page.shape[1], P(loc_t), n, P(hists), None))
+    loose, tight = DO.box_hists(loc32.astype(np.float64), page.astype(np.float32))
+    assert np.array_equal(hists[0].numpy(), loose) and np.array_equal(hists[1].numpy(), tight)
+    assert len(set(np.round(loose, 3))) > 20                     # the fixture has ink, blank and noise boxes
+    th = float(np.median(loose) / 5)
+    maps7 = gold["maps7"]
+    out_loc, out_gf, sel = _select_on_emu(emu, loc32, gf, tight, th, maps7[2], maps7[3:7])
+    assert out_loc.shape == gold["locations"].shape
+    assert np.array_equal(out_loc, gold["locations"]) and np.array_equal(out_gf, gold["glyphfeatures"])
+
+
+def test_emu_select_boxes_dense_page():
+    """The greedy kernel on the dense stub page (1 150 candidates, 374 survivors in the reference): IoU / 75 % / fill-map /
+    histogram / separator / code-maximum branches all fire; output == reference run_detector golden."""
+    import numpy as np
+    from test_oracle_golden import _dense_page
+    from oracle import detector_oracle as DO
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "emu"))
+    import build_emu
+    emu = C.CDLL(build_emu.build())
+    emu.ftc_last_error.restype = C.c_char_p
+    gold, page, offsets, heat10, feats = _dense_page()
+    ph, pw = page.shape[:2]
+    pre = [DO.decode_tile(heat10[i], feats[i], x, y, pw, ph) for i, (x, y) in enumerate(offsets)]
+    loc = np.concatenate([p[0] for p in pre]).astype(np.float32)
+    gf = np.concatenate([p[1] for p in pre]).astype(np.float32)
+    maps7 = DO.page_maps(np.concatenate([heat10[:, :1], heat10[:, 2:]], 1), offsets, pw, ph)
+    loose, tight = DO.box_hists(loc.astype(np.float64), page.astype(np.float32))
+    out_loc, out_gf, sel = _select_on_emu(emu, loc, gf, tight, float(np.median(loose) / 5), maps7[2], maps7[3:7])
+    assert out_loc.shape == gold["locations"].shape and np.array_equal(out_loc, gold["locations"])
+    assert np.allclose(out_gf.astype(np.float64).sum(1), gold["glyphfeatures_sum"], rtol=0, atol=1e-9)
