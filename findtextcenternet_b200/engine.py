@@ -195,6 +195,53 @@ def page_maps(heat9: torch.Tensor, tile_meta: torch.Tensor, page_h: int, page_w:
     return page
 
 
+def box_hists(page_u8: torch.Tensor, loc: torch.Tensor) -> torch.Tensor:
+    """The two imageHist scores of run_detector per candidate box (process_ocr_base.py:543-557, 571-576, 652-693) on the device:
+    page_u8 uint8 [H, W, 3] (the padded page), loc fp32 [n, 9] -> float64 [2, n] = (loose, tight), bit-identical to numpy."""
+    lib = _lib.load()
+    if not (page_u8.is_cuda and loc.is_cuda):
+        raise RuntimeError("box_hists needs CUDA tensors (no CPU path)")
+    assert page_u8.dtype == torch.uint8 and page_u8.dim() == 3 and page_u8.shape[2] == 3 and loc.dim() == 2 and loc.shape[1] == 9
+    page_u8, loc = page_u8.contiguous(), loc.float().contiguous()
+    n = loc.shape[0]
+    out = torch.zeros(2, n, dtype=torch.float64, device=loc.device)
+    if n:
+        with torch.cuda.device(loc.device):
+            _lib.check(lib.ftc_box_hists(page_u8.data_ptr(), page_u8.shape[0], page_u8.shape[1], loc.data_ptr(), n, out.data_ptr(),
+                                         _stream_ptr(loc.device)), "ftc_box_hists")
+    return out
+
+
+def select_boxes(loc: torch.Tensor, gfeat: torch.Tensor, tight: torch.Tensor, th: float, maps7: torch.Tensor):
+    """The greedy box selection, separator veto and 3x3 code-map maximum of run_detector (process_ocr_base.py:559-658) on the
+    device.  loc fp32 [n, 9], gfeat fp32 [n, F] (all tiles' peaks concatenated), tight float64 [n] (``box_hists``), th =
+    median(loose) / 5, maps7 fp32 [7, H/4, W/4] (``page_maps``).  Returns (locations fp32 [m, 9], glyphfeatures fp32 [m, F],
+    indices int32 [m] into the candidate list) in the reference's order (descending score)."""
+    lib = _lib.load()
+    if not (loc.is_cuda and gfeat.is_cuda and tight.is_cuda and maps7.is_cuda):
+        raise RuntimeError("select_boxes needs CUDA tensors (no CPU path)")
+    loc, gfeat, tight, maps7 = loc.float().contiguous(), gfeat.float().contiguous(), tight.double().contiguous(), maps7.float().contiguous()
+    n, fc = loc.shape[0], gfeat.shape[1]
+    dev = loc.device
+    # descending score, ties by ascending candidate index (np.argsort(-p) of the reference is unstable: ties are unspecified there)
+    order = torch.argsort(loc[:, 0], descending=True, stable=True).to(torch.int32) if n else torch.zeros(0, dtype=torch.int32, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    sel = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    out_loc = torch.empty(max(n, 1), 9, dtype=torch.float32, device=dev)
+    out_gf = torch.empty(max(n, 1), fc, dtype=torch.float32, device=dev)
+    nb = int(lib.ftc_select_boxes_scratch_bytes(n))
+    scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+    seps, code = maps7[2], maps7[3:7].contiguous()
+    if n:
+        with torch.cuda.device(dev):
+            _lib.check(lib.ftc_select_boxes(loc.data_ptr(), gfeat.data_ptr(), fc, order.data_ptr(), n, tight.data_ptr(), float(th),
+                                            seps.data_ptr(), code.data_ptr(), maps7.shape[1], maps7.shape[2], arch.SCALE,
+                                            n_out.data_ptr(), sel.data_ptr(), out_loc.data_ptr(), out_gf.data_ptr(), scratch.data_ptr(),
+                                            nb, _stream_ptr(dev)), "ftc_select_boxes")
+    m = int(n_out.item())
+    return out_loc[:m], out_gf[:m], sel[:m]
+
+
 class TransformerEngine:
     """One ``ftc_transformer`` plan + packed weights (models/transformer.py Encoder + Decoder)."""
 

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import arch
-from .engine import page_maps, peak_decode
+from .engine import box_hists, page_maps, peak_decode, select_boxes
 
 try:  # running inside a reference checkout
     from process_ocr_base import OCR_Processer as _Base  # type: ignore
@@ -180,6 +180,47 @@ class OCR_b200_Processer(_Base):
         if return_maps:
             return torch.cat(locs).numpy(), torch.cat(feats).numpy(), maps.cpu().numpy()
         return torch.cat(locs).numpy(), torch.cat(feats).numpy()
+
+    # ---- run_detector of the reference pipeline, on the device ---------------------------------------------------------------------
+    def run_detector(self, ds, org_img, max_peaks: int = 4096, tile_batch: int = 32):
+        """Drop-in for ``OCR_Processer.run_detector`` (process_ocr_base.py:474-650), which ``call_OCR`` (:78) calls with the tile
+        list ``ds`` ([{'input': float32 [1,768,768,3], 'offsetx', 'offsety'}, ...]) and the padded float32 page ``org_img``: returns
+        the same ``(locations float32 [m,9], glyphfeatures float32 [m,100], lines_all, seps_all)``.  The reference walks the tiles one
+        by one through call_detector (16 MB of maps to the host per tile) and runs the peak loop, imageHist and the greedy selection
+        in numpy; here the page goes to the device ONCE as uint8, tiles are cut there and run in batches, and peak decode, page
+        maps, histogram scores, greedy selection, separator veto and code maximum are kernels (ftc_peak_decode, ftc_page_maps,
+        ftc_box_hists, ftc_select_boxes).  Host work left: the median of the histogram scores (np.median, a few KB)."""
+        page_h, page_w = int(org_img.shape[0]), int(org_img.shape[1])
+        page_u8 = torch.from_numpy(np.ascontiguousarray(org_img).astype(np.uint8)).to(self.device, non_blocking=True)
+        offsets = [(int(d["offsetx"]), int(d["offsety"])) for d in ds]
+        eng = self.detector.detector.engine(self.device)
+        maps = torch.zeros(7, page_h // arch.SCALE, page_w // arch.SCALE, dtype=torch.float32, device=self.device)
+        locs, feats = [], []
+        with torch.no_grad():
+            for i in range(0, len(offsets), tile_batch):
+                offs = offsets[i:i + tile_batch]
+                tiles = torch.stack([page_u8[y:y + arch.HEIGHT, x:x + arch.WIDTH] for x, y in offs]).float()
+                meta = torch.tensor([tile_meta(x, y, page_w, page_h, self.step_ratio) for x, y in offs], dtype=torch.int32).to(self.device)
+                heat9, feat, _ = eng.forward(tiles, False, nhwc255=True)
+                count, loc, gfeat, total = peak_decode(heat9, feat, meta, page_w, page_h, self.cut_off, max_peaks)
+                page_maps(heat9, meta, page_h, page_w, out=maps)
+                if bool((total > max_peaks).any()):
+                    raise OverflowError(f"run_detector: a tile has {int(total.max())} peaks, more than max_peaks={max_peaks}")
+                valid = torch.arange(max_peaks, device=self.device)[None, :] < count[:, None]      # tile-major, score order inside
+                locs.append(loc[valid])
+                feats.append(gfeat[valid])
+            cand_loc = torch.cat(locs) if locs else torch.zeros(0, 9, device=self.device)
+            cand_gf = torch.cat(feats) if feats else torch.zeros(0, arch.FEATURE_DIM, device=self.device)
+            hists = box_hists(page_u8, cand_loc)
+            loose = hists[0].cpu().numpy()
+            with np.errstate(all="ignore"):
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    th = float(np.median(loose) / 5) if loose.size else float("nan")      # process_ocr_base.py:557
+            out_loc, out_gf, _ = select_boxes(cand_loc, cand_gf, hists[1], th, maps)
+        self.last_candidates = int(cand_loc.shape[0])
+        return out_loc.cpu().numpy(), out_gf.cpu().numpy(), maps[1].cpu().numpy(), maps[2].cpu().numpy()
 
     def call_transformer_batch(self, encoder_inputs):
         """All feature chunks of a page (or of many pages) in ONE predictor call: float32 [N, max_encoderlen, 106] ->
