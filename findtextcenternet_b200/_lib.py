@@ -101,6 +101,7 @@ SYMBOLS = {
     "ftc_op_head_top_conv": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ftc_train_reduce_scratch_bytes": (_sz, [_i64, _i]),
     "ftc_train_bn_stats": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp]),
+    "ftc_train_bn_stats_running": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
     "ftc_train_bn_act": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
     "ftc_train_bn_act_bwd": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp]),
     "ftc_train_conv2d_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -9,6 +9,9 @@ import torch
 from . import _lib
 
 
+FUSED_RUNNING_STATS = True      # train_ops.batchnorm_act: BatchNorm running statistics updated inside ftc_train_bn_stats_running
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return _lib.DT_F32
@@ -148,8 +151,9 @@ def _reduce_scratch(rows: int, c: int, dev) -> torch.Tensor:
     return torch.empty(n // 4, dtype=torch.float32, device=dev)
 
 
-def bn_stats(x: torch.Tensor):
-    """x [..., C] contiguous -> (batch mean, biased batch variance) fp32 [C]."""
+def bn_stats(x: torch.Tensor, running=None, momentum: float = 0.1):
+    """x [..., C] contiguous -> (batch mean, biased batch variance) fp32 [C].  ``running`` = (running_mean, running_var,
+    num_batches_tracked) fp32 / fp32 / int64 device tensors: updated in place by the same kernel (nn.BatchNorm train mode)."""
     lib = _lib.load()
     assert x.is_cuda and x.is_contiguous()
     c = x.shape[-1]
@@ -158,8 +162,16 @@ def bn_stats(x: torch.Tensor):
     var = torch.empty(c, dtype=torch.float32, device=x.device)
     scratch = _reduce_scratch(rows, c, x.device)
     with torch.cuda.device(x.device):
-        _lib.check(lib.ftc_train_bn_stats(x.data_ptr(), _dt(x), rows, c, mean.data_ptr(), var.data_ptr(), scratch.data_ptr(),
-                                          _s(x)), "ftc_train_bn_stats")
+        if running is None:
+            _lib.check(lib.ftc_train_bn_stats(x.data_ptr(), _dt(x), rows, c, mean.data_ptr(), var.data_ptr(), scratch.data_ptr(),
+                                              _s(x)), "ftc_train_bn_stats")
+        else:
+            rm, rv, nbt = running
+            assert rm.dtype == torch.float32 and rv.dtype == torch.float32 and rm.is_contiguous() and rv.is_contiguous()
+            assert nbt is None or nbt.dtype == torch.int64
+            _lib.check(lib.ftc_train_bn_stats_running(x.data_ptr(), _dt(x), rows, c, mean.data_ptr(), var.data_ptr(), scratch.data_ptr(),
+                                                      rm.data_ptr(), rv.data_ptr(), _p(nbt), momentum, _s(x)), "ftc_train_bn_stats_running")
+            torch.autograd.graph.increment_version([t for t in (rm, rv, nbt) if t is not None])
     return mean, var
 
 

@@ -285,7 +285,7 @@ template <typename T, int TH>
 __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmIn, T* __restrict__ out, int H, int W, int C,
                                                               const float* __restrict__ w, const float* __restrict__ scale,
                                                               const float* __restrict__ bias, const float* __restrict__ w1,
-                                                              int S, float inv_hw, float* __restrict__ hid_pre) {
+                                                              int S, float inv_hw, float* __restrict__ hid_pre, int flip) {
   extern __shared__ __align__(16) unsigned char dw_smem_raw[];
   // TMA destinations need 128-byte alignment; the dynamic shared window only guarantees 16
   unsigned char* dw_smem = dw_smem_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(dw_smem_raw) & 127u)) & 127u);
@@ -334,10 +334,14 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
   prefetch(0);
   const int quad = tid & 7, col = tid >> 3;            // 4 channels, one output column
   const int c0 = cb + quad * 4;
+  // raw = plain depthwise convolution (train step: BatchNorm needs the batch statistics of the raw output first; the data
+  // gradient of a stride-1 depthwise conv is the same kernel with the taps reversed): no BN / SiLU / SE
+  const bool raw = scale == nullptr;
   f32x2 wk[9][2], sc[2], bi[2], ssum[2];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) load4p(w + t * C + c0, wk[t]);
-  load4p(scale + c0, sc); load4p(bias + c0, bi);
+  for (int t = 0; t < 9; ++t) load4p(w + (flip ? 8 - t : t) * C + c0, wk[t]);      // flip: taps rotated 180 degrees (data gradient)
+  if (!raw) { load4p(scale + c0, sc); load4p(bias + c0, bi); }
+  else { sc[0] = sc[1] = pk2(1.f, 1.f); bi[0] = bi[1] = pk2(0.f, 0.f); }
   ssum[0] = ssum[1] = pk2(0.f, 0.f);
   const f32x2 half2 = pk2(0.5f, 0.5f);
   for (int s = 0; s < nstrips; ++s) {
@@ -364,7 +368,9 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
         for (int t = 1; t < 9; ++t) acc = ffma2(r[(py + t / 3) % 3][t % 3][h], wk[t][h], acc);
         const f32x2 t2 = ffma2(acc, sc[h], bi[h]);
         float x0, x1;
-        if (sizeof(T) == 4) {
+        if (raw) {
+          upk2(acc, x0, x1);
+        } else if (sizeof(T) == 4) {
           upk2(t2, x0, x1);
           x0 = silu_precise(x0); x1 = silu_precise(x1);
         } else {
@@ -382,6 +388,7 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
     }
     __syncthreads();                                    // the strip buffer is refilled two iterations later
   }
+  if (raw) return;
   // ---- squeeze (complete for these 32 channels) + this CTA's share of fc1 ----
   {
     float s0, s1, s2, s3;
@@ -586,7 +593,7 @@ bool dwconv3x3_se_supported(int H, int W, int C, int stride) {
 }
 
 int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int C, const float* w, const float* scale,
-                 const float* bias, const float* w1, int S, float* hid_pre, cudaStream_t s) {
+                 const float* bias, const float* w1, int S, float* hid_pre, cudaStream_t s, int flip) {
   FTC_REQUIRE(dwconv3x3_se_supported(H, W, C, 1), "dwconv3x3_se: unsupported geometry");
   FTC_REQUIRE(B <= 65535, "batch");
   constexpr int TH = 8;
@@ -605,7 +612,7 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
   do {                                                                                                                 \
     static bool done = false;                                                                                          \
     if (!done) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<TT, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; } \
-    FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre)); \
+    FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip)); \
   } while (0)
   // the mma.sync variant is correct but measured SLOWER on B200 (0.26 vs 0.17 ms at 48x48x1536, B=32: its BN/SiLU/SE
   // epilogue and fragment exchange cost as many issue slots as the FMAs they replace); kept behind FTC_DW_MMA=1
@@ -622,7 +629,7 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
     if (rc) return rc;
     static bool done12 = false;
     if (!done12) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<bf16, TH12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done12 = true; }
-    FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<bf16, TH12>, grid, dim3(threads), smem12, s, tm12, (bf16*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre));
+    FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<bf16, TH12>, grid, dim3(threads), smem12, s, tm12, (bf16*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip));
   }
   else if (dtype == DT_F32) DWS_LAUNCH(float);
   else if (!env_mma) DWS_LAUNCH(bf16);
@@ -640,6 +647,12 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
 #undef DWS_LAUNCH
   FTC_POST_LAUNCH();
   return 0;
+}
+
+// plain stride-1 depthwise 3x3 through the strip kernel (train step forward / data gradient)
+int dwconv3x3_raw_strip(const void* in, void* out, int dtype, int B, int H, int W, int C, const float* w, int flip, cudaStream_t s) {
+  FTC_REQUIRE(dwconv3x3_se_supported(H, W, C, 1), "dwconv3x3_raw_strip: unsupported geometry");
+  return dwconv3x3_se(in, out, dtype, B, H, W, C, w, nullptr, nullptr, nullptr, 0, nullptr, s, flip);
 }
 
 // second half of SE for the folded path: scale[b,c] = sigmoid(b2[c] + w2t[:,c] . silu(sum_g hid_part[b,g,:] + b1)).

@@ -27,7 +27,10 @@ int se_fc(const float* sum, int nt, float* scale_out, float* hid, int B, int C, 
 //   hid_part[b, g, s] = sum_{c in group g} w1[s, c] * mean_hw(out[b, :, :, c])   (hid_part [B][C/32][S] fp32, every entry written)
 bool dwconv3x3_se_supported(int H, int W, int C, int stride);
 int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int C, const float* w /*[9][C]*/, const float* scale,
-                 const float* bias, const float* w1 /*[S][C]*/, int S, float* hid_part, cudaStream_t s);
+                 const float* bias, const float* w1 /*[S][C]*/, int S, float* hid_part, cudaStream_t s, int flip = 0);
+// the same strip kernel as a PLAIN stride-1 depthwise 3x3 (scale == nullptr: no BN / SiLU / SE); flip = 1 rotates the taps by 180
+// degrees, which makes it the data gradient (train step: ftc_train_dwconv3x3 / ftc_train_dwconv3x3_dgrad)
+int dwconv3x3_raw_strip(const void* in, void* out, int dtype, int B, int H, int W, int C, const float* w /*[9][C]*/, int flip, cudaStream_t s);
 // scale[b,c] = sigmoid(b2[c] + w2t[:,c] . silu(sum_g hid_part[b,g,:] + b1)), groups added in a fixed order (G = C / 32)
 int se_fc2_hid(const float* hid_part, int G, float* scale_out, int B, int C, int S, const float* b1,
                const float* w2t, const float* b2, cudaStream_t s);

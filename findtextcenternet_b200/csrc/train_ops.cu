@@ -14,6 +14,9 @@
 
 #include "../../include/ftc_b200.h"
 #include "common.cuh"
+#ifndef FTC_EMU
+#include "detector_ops.cuh"
+#endif
 
 namespace ftc {
 
@@ -89,9 +92,16 @@ __global__ void __launch_bounds__(RED_THREADS) col_reduce_kernel(const T* __rest
 // CTA = 32 channels x 32 chunk lanes: lane ly adds chunks ly, ly + 32, ... in double, the 32 lane sums are then added in lane
 // order by one thread per channel -- a fixed summation order (deterministic) with 32-way parallelism over the up-to-4096
 // partials.  (One thread per channel walking all partials was latency-bound: ~50 us per launch, 724 launches per train step.)
+struct RunningStats {           // nn.BatchNorm train-mode side effects (torch batch_norm: momentum update, UNBIASED variance)
+  float* mean;                  // running_mean [C] or nullptr
+  float* var;                   // running_var [C]
+  long long* count;             // num_batches_tracked (scalar) or nullptr
+  float momentum;
+};
+
 template <int FIN>
 __global__ void __launch_bounds__(1024) col_reduce_finish_kernel(const float* __restrict__ part, int nchunk, int C, int64_t rows,
-                                                                 float* __restrict__ out0, float* __restrict__ out1) {
+                                                                 float* __restrict__ out0, float* __restrict__ out1, RunningStats rs) {
   __shared__ double sa[32][33], sb[32][33];
   const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -110,8 +120,15 @@ __global__ void __launch_bounds__(1024) col_reduce_finish_kernel(const float* __
   if (FIN == 0) {
     double m = a / (double)rows;
     double v = b / (double)rows - m * m;
-    out0[c] = (float)m;
-    out1[c] = (float)(v > 0.0 ? v : 0.0);
+    const float mf = (float)m, vf = (float)(v > 0.0 ? v : 0.0);
+    out0[c] = mf;
+    out1[c] = vf;
+    if (rs.mean != nullptr) {     // running = running * (1 - momentum) + momentum * batch statistic (variance: n / (n - 1) corrected)
+      const float unbiased = vf * ((float)rows / (float)(rows > 1 ? rows - 1 : 1));
+      rs.mean[c] = fmaf(rs.momentum, mf, rs.mean[c] * (1.0f - rs.momentum));
+      rs.var[c] = fmaf(rs.momentum, unbiased, rs.var[c] * (1.0f - rs.momentum));
+      if (c == 0 && rs.count != nullptr) *rs.count += 1;
+    }
   } else {
     out0[c] = (float)a;
     out1[c] = (float)b;
@@ -663,6 +680,68 @@ __global__ void __launch_bounds__(256) dw_vec_kernel(const T* __restrict__ src, 
       }
     }
     store8(dst + p * C + c0, acc);
+  }
+}
+
+// 16-byte-vector depthwise weight gradient (C % 8 == 0): thread = (8-channel chunk lane, pixel lane) as in dw_vec_kernel, CTA = 64
+// channels x 32 pixel lanes walking a contiguous pixel range in raster order (neighbouring lanes touch neighbouring pixels: the
+// nine shifted reads of x hit L1); 72 fp32 accumulators per thread, reduced over the pixel lanes by warp shuffles + shared
+// memory, then one fp32 atomic per (tap, channel) per CTA into the zeroed gradient.
+template <typename T>
+__global__ void __launch_bounds__(256) dw_wgrad_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, int B, int H, int W, int C,
+                                                           int Ho, int Wo, int stride, int pix_per_split, float* __restrict__ dw) {
+  __shared__ float sm[8][9][RED_CH];
+  const int ck = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * RED_CH + ck * 8;
+  const int P = B * Ho * Wo;
+  const int p0 = blockIdx.y * pix_per_split, p1 = min(P, p0 + pix_per_split);
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  if (c0 < C) {
+    for (int p = p0 + pl; p < p1; p += 32) {
+      const int ox = p % Wo, q = p / Wo;
+      const int oy = q % Ho, b = q / Ho;
+      float g[8];
+      load8(dy + (int64_t)p * C + c0, g);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * stride - 1 + ky;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * stride - 1 + kx;
+          if (ix < 0 || ix >= W) continue;
+          float v[8];
+          load8(x + (((int64_t)b * H + iy) * W + ix) * C + c0, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(g[j], v[j], acc[ky * 3 + kx][j]);
+        }
+      }
+    }
+  }
+  // lanes of a warp: ck = lane & 7, four pixel lanes (lane >> 3): fold them, then the eight warps through shared memory
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[t][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 8) sm[warp][t][ck * 8 + j] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * RED_CH; i += 256) {
+    const int t = i / RED_CH, cc = i - t * RED_CH;
+    const int c = blockIdx.x * RED_CH + cc;
+    if (c >= C) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) s += sm[l][t][cc];
+    atomicAdd(dw + (int64_t)t * C + c, s);
   }
 }
 
@@ -1260,7 +1339,22 @@ size_t ftc_train_reduce_scratch_bytes(int64_t rows, int c) {
   return (size_t)2 * red_chunks(rows) * (size_t)c * sizeof(float);
 }
 
+static int bn_stats_impl(const void* x, int dtype, int64_t rows, int c, float* mean, float* var, void* scratch, RunningStats rs,
+                         void* stream);
+
 int ftc_train_bn_stats(const void* x, int dtype, int64_t rows, int c, float* mean, float* var, void* scratch, void* stream) {
+  return bn_stats_impl(x, dtype, rows, c, mean, var, scratch, RunningStats{nullptr, nullptr, nullptr, 0.f}, stream);
+}
+
+int ftc_train_bn_stats_running(const void* x, int dtype, int64_t rows, int c, float* mean, float* var, void* scratch,
+                               float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum, void* stream) {
+  FTC_REQUIRE(running_mean && running_var, "null running statistics");
+  return bn_stats_impl(x, dtype, rows, c, mean, var, scratch,
+                       RunningStats{running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked), momentum}, stream);
+}
+
+static int bn_stats_impl(const void* x, int dtype, int64_t rows, int c, float* mean, float* var, void* scratch, RunningStats rs,
+                         void* stream) {
   FTC_REQUIRE(x && mean && var && scratch && rows > 0 && c > 0 && dtype_ok(dtype), "bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int nchunk = red_chunks(rows);
@@ -1277,7 +1371,7 @@ int ftc_train_bn_stats(const void* x, int dtype, int64_t rows, int c, float* mea
   else
     col_reduce_kernel<bf16, 0><<<grid, RED_THREADS, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
   FTC_POST_LAUNCH();
-  col_reduce_finish_kernel<0><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, nchunk, c, rows, mean, var);
+  col_reduce_finish_kernel<0><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, nchunk, c, rows, mean, var, rs);
   FTC_POST_LAUNCH();
   return 0;
 }
@@ -1324,7 +1418,7 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
   else
     col_reduce_kernel<bf16, 1><<<grid, RED_THREADS, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
   FTC_POST_LAUNCH();
-  col_reduce_finish_kernel<1><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, nchunk, c, rows, dbeta, dgamma);
+  col_reduce_finish_kernel<1><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, nchunk, c, rows, dbeta, dgamma, RunningStats{nullptr, nullptr, nullptr, 0.f});
   FTC_POST_LAUNCH();
   const int64_t total = rows * c;
   const float inv_rows = (float)(1.0 / (double)rows);
@@ -1415,6 +1509,12 @@ int ftc_train_dwconv3x3(const void* x, void* y, int dtype, int batch, int h, int
   cudaStream_t s = (cudaStream_t)stream;
   const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
   const int64_t total = (int64_t)batch * ho * wo * c;
+#ifndef FTC_EMU
+  // stride-1 maps up to 48 px wide (78 of the 80 depthwise convs of EfficientNetV2-XL at 768 px): the TMA strip kernel of the
+  // inference engine in its plain mode -- each input element crosses L2 -> SM once instead of nine times
+  if (stride == 1 && batch <= 65535 && dwconv3x3_se_supported(h, w, c, 1) && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+    return dwconv3x3_raw_strip(x, y, dtype, batch, h, w, c, w9c, 0, s);
+#endif
   if (c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w9c)) & 15) == 0) {
     const dim3 vgrid((unsigned)std::min<int64_t>(((int64_t)batch * ho * wo + 31) / 32, 148 * 8), ceil_div(c, RED_CH));
     if (dtype == DT_F32) dw_vec_kernel<float, false><<<vgrid, 256, 0, s>>>(cp<float>(x), mp<float>(y), batch, h, w, ho, wo, c, stride, w9c);
@@ -1436,6 +1536,11 @@ int ftc_train_dwconv3x3_dgrad(const void* dy, void* dx, int dtype, int batch, in
   cudaStream_t s = (cudaStream_t)stream;
   const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
   const int64_t total = (int64_t)batch * h * w * c;
+#ifndef FTC_EMU
+  // stride 1: the data gradient is the same depthwise convolution with the taps rotated by 180 degrees
+  if (stride == 1 && batch <= 65535 && dwconv3x3_se_supported(h, w, c, 1) && (reinterpret_cast<uintptr_t>(dy) & 15) == 0)
+    return dwconv3x3_raw_strip(dy, dx, dtype, batch, h, w, c, w9c, 1, s);
+#endif
   if (c % 8 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(w9c)) & 15) == 0) {
     const dim3 vgrid((unsigned)std::min<int64_t>(((int64_t)batch * h * w + 31) / 32, 148 * 8), ceil_div(c, RED_CH));
     if (dtype == DT_F32) dw_vec_kernel<float, true><<<vgrid, 256, 0, s>>>(cp<float>(dy), mp<float>(dx), batch, ho, wo, h, w, c, stride, w9c);
@@ -1458,6 +1563,21 @@ int ftc_train_dwconv3x3_wgrad(const void* x, const void* dy, int dtype, int batc
   const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
   FTC_CHECK_CUDA(cudaMemsetAsync(dw9c, 0, (size_t)9 * c * sizeof(float), s));
   const int64_t P = (int64_t)batch * ho * wo;
+  if (c % 8 == 0 && P < 0x7fffffff && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0) {
+    const int cb = ceil_div(c, RED_CH);
+    int64_t sp = std::max<int64_t>(1, std::min<int64_t>((148 * 6 + cb - 1) / cb, (P + 255) / 256));
+    sp = std::min<int64_t>(sp, 65535);
+    int64_t per = (P + sp - 1) / sp;
+    per = (per + 31) / 32 * 32;
+    sp = (P + per - 1) / per;
+    dim3 vgrid(cb, (unsigned)sp);
+    if (dtype == DT_F32)
+      dw_wgrad_vec_kernel<float><<<vgrid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), batch, h, w, c, ho, wo, stride, (int)per, dw9c);
+    else
+      dw_wgrad_vec_kernel<bf16><<<vgrid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), batch, h, w, c, ho, wo, stride, (int)per, dw9c);
+    FTC_POST_LAUNCH();
+    return 0;
+  }
   const int cblocks = ceil_div(c, 32);
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>((148 * 8 + cblocks - 1) / cblocks, (P + 63) / 64));
   splits = std::min<int64_t>(splits, 65535);
@@ -1599,7 +1719,7 @@ int ftc_train_layernorm_bwd(const void* xs, const void* dy, void* dx, const floa
     ln_col_reduce_kernel<bf16><<<rgrid, RED_THREADS, 0, s>>>(cp<bf16>(xs), cp<bf16>(dy), mean, rstd, rows, d, rpc, (float*)scratch);
   }
   FTC_POST_LAUNCH();
-  col_reduce_finish_kernel<1><<<ceil_div(d, 32), 1024, 0, s>>>((const float*)scratch, nchunk, d, rows, dbeta, dgamma);
+  col_reduce_finish_kernel<1><<<ceil_div(d, 32), 1024, 0, s>>>((const float*)scratch, nchunk, d, rows, dbeta, dgamma, RunningStats{nullptr, nullptr, nullptr, 0.f});
   FTC_POST_LAUNCH();
   return 0;
 }

@@ -211,12 +211,16 @@ def batchnorm_act(x: Tensor, bn, eps: float, act: int, residual: Optional[Tensor
     """Train-mode BatchNorm (+ activation, + residual after it); updates running_mean / running_var /
     num_batches_tracked like torch (momentum 0.1, unbiased variance into running_var)."""
     with torch.no_grad():
-        mean, var = K.bn_stats(x)
-        n = x.numel() // x.shape[-1]
-        bn.running_mean.mul_(1 - BN_MOMENTUM).add_(mean.to(bn.running_mean.dtype), alpha=BN_MOMENTUM)
-        unbiased = var * (float(n) / max(n - 1, 1))
-        bn.running_var.mul_(1 - BN_MOMENTUM).add_(unbiased.to(bn.running_var.dtype), alpha=BN_MOMENTUM)
-        bn.num_batches_tracked += 1
+        rm, rv, nbt = bn.running_mean, bn.running_var, bn.num_batches_tracked
+        if getattr(K, "FUSED_RUNNING_STATS", False) and rm.dtype == torch.float32 and rv.dtype == torch.float32 and nbt.is_cuda:
+            mean, var = K.bn_stats(x, (rm, rv, nbt), BN_MOMENTUM)       # running statistics updated by the finishing kernel
+        else:
+            mean, var = K.bn_stats(x)
+            n = x.numel() // x.shape[-1]
+            rm.mul_(1 - BN_MOMENTUM).add_(mean.to(rm.dtype), alpha=BN_MOMENTUM)
+            unbiased = var * (float(n) / max(n - 1, 1))
+            rv.mul_(1 - BN_MOMENTUM).add_(unbiased.to(rv.dtype), alpha=BN_MOMENTUM)
+            bn.num_batches_tracked += 1
     return _BNAct.apply(x, bn.weight, bn.bias, mean, var, eps, act, residual)
 
 

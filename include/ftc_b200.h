@@ -234,6 +234,11 @@ int ftc_op_attention(const void* q, int q_stride, int q_off, const void* k, cons
  *                        with dz = dy * act'(gamma * xhat + beta) recomputed from x (the residual's gradient is dy itself) */
 size_t ftc_train_reduce_scratch_bytes(int64_t rows, int c);
 int ftc_train_bn_stats(const void* x, int dtype, int64_t rows, int c, float* mean, float* var, void* scratch, void* stream);
+/* the same with nn.BatchNorm's train-mode side effects folded into the finishing kernel (six tiny launches per layer otherwise):
+ * running_mean = (1 - momentum) * running_mean + momentum * mean, running_var likewise with the UNBIASED batch variance,
+ * *num_batches_tracked += 1 (may be NULL) */
+int ftc_train_bn_stats_running(const void* x, int dtype, int64_t rows, int c, float* mean, float* var, void* scratch,
+                               float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum, void* stream);
 int ftc_train_bn_act(const void* x, void* y, int dtype, int64_t rows, int c, const float* mean, const float* var,
                      const float* gamma, const float* beta, float eps, int act, const void* residual, void* stream);
 int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t rows, int c, const float* mean,

@@ -549,3 +549,20 @@ def test_emu_select_boxes_dense_page():
     out_loc, out_gf, sel = _select_on_emu(emu, loc, gf, tight, float(np.median(loose) / 5), maps7[2], maps7[3:7])
     assert out_loc.shape == gold["locations"].shape and np.array_equal(out_loc, gold["locations"])
     assert np.allclose(out_gf.astype(np.float64).sum(1), gold["glyphfeatures_sum"], rtol=0, atol=1e-9)
+
+
+def test_emu_bn_stats_running_update(emu):
+    """ftc_train_bn_stats_running: batch statistics AND nn.BatchNorm's train-mode side effects (momentum update with the unbiased
+    variance, num_batches_tracked) in one call == torch.nn.functional.batch_norm(training=True)."""
+    import torch.nn.functional as F
+    rows, c = 300, 72
+    x = rnd(rows, c, seed=1) * 1.7 + 0.3
+    rm, rv = rnd(c, seed=2), rnd(c, seed=3).abs() + 0.5
+    nbt = torch.tensor(7, dtype=torch.int64)
+    rm0, rv0 = rm.clone(), rv.clone()
+    F.batch_norm(x, rm0, rv0, None, None, True, 0.1, 1e-3)
+    mean, var, sc = torch.empty(c), torch.empty(c), scratch(emu, rows, c)
+    ok(emu, emu.ftc_train_bn_stats_running(P(x), 0, C.c_int64(rows), c, P(mean), P(var), P(sc), P(rm), P(rv), P(nbt), C.c_float(0.1), None))
+    m0, v0 = TO.bn_stats(x)
+    assert rel_l2(mean, m0) < 1e-5 and rel_l2(var, v0) < 1e-4
+    assert rel_l2(rm, rm0) < 1e-6 and rel_l2(rv, rv0) < 1e-6 and int(nbt) == 8
