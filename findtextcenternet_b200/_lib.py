@@ -74,6 +74,7 @@ SYMBOLS = {
     "ftc_transformer_head_stride": (_i, []),
     "ftc_transformer_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "ftc_transformer_predict": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, C.POINTER(_i), C.POINTER(_i), _vp, _sz, _vp]),
+    "ftc_transformer_predict_each": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "ftc_mask_predict_step": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "ftc_adamw_sf_chunk_elems": (_i, []),
     "ftc_adamw_sf_step": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _d, _d, _d, _vp]),

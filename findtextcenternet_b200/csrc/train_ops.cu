@@ -37,6 +37,32 @@ __device__ __forceinline__ float act_grad(float z, int act) {
   return 1.f;
 }
 
+// bf16-storage variant: the derivative only has to be good to bf16 rounding (2^-9).  SiLU': one ex2 + one rcp; GELU': the cdf
+// through the same 3-term tanh fit as the forward epilogue (abs. error 2.5e-5), one ex2 for the pdf.  (The precise version costs
+// ~40 instructions per element and made the BatchNorm backward kernels issue-bound: 4x off the HBM roofline.)
+__device__ __forceinline__ float act_grad_fast(float z, int act) {
+#ifdef FTC_EMU
+  return act_grad(z, act);
+#else
+  if (act == ACT_SILU) {
+    const float s = __fdividef(1.f, 1.f + __expf(-z));
+    return s * fmaf(z, 1.f - s, 1.f);
+  }
+  if (act == ACT_GELU) {
+    const float z2 = fminf(z * z, 64.f);
+    const float u = z * fmaf(z2, fmaf(z2, -3.51516792e-04f, 3.70056461e-02f), 7.97507884e-01f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    const float cdf = fmaf(0.5f, t, 0.5f);
+    return fmaf(z, 0.39894228040143267794f * __expf(-0.5f * z2), cdf);
+  }
+  return 1.f;
+#endif
+}
+template <typename T> __device__ __forceinline__ float act_grad_t(float z, int act) {
+  return sizeof(T) == 2 ? act_grad_fast(z, act) : act_grad(z, act);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Column reductions over a row-major [rows, C] matrix (NHWC activations: rows = B*H*W).
 // Stage 1: CTA = (64 channels) x (4 row lanes); each CTA owns a contiguous chunk of rows and writes fp32 partials
@@ -174,7 +200,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ x
 // above remain for odd channel counts.  Reduction CTA = 8 chunk lanes (64 channels, one 128-byte line of bf16 per row) x 32
 // row lanes.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256) col_reduce_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t rows, int C,
+__global__ void __launch_bounds__(256, 2) col_reduce_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t rows, int C,
                                                              int64_t rows_per_chunk, float* __restrict__ part, BnArgs bn) {
   __shared__ float sm[2][32][RED_CH + 1];
   const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
@@ -190,20 +216,33 @@ __global__ void __launch_bounds__(256) col_reduce_vec_kernel(const T* __restrict
       mean[j] = 0.f; rstd[j] = 1.f; g[j] = 1.f; bt[j] = 0.f;
       if (MODE == 1) { mean[j] = bn.mean[c0 + j]; rstd[j] = rsqrtf(bn.var[c0 + j] + bn.eps); g[j] = bn.gamma[c0 + j]; bt[j] = bn.beta[c0 + j]; }
     }
-    for (int64_t r = r0 + rl; r < r1; r += 32) {
-      float v[8], d[8];
-      load8(x + r * C + c0, v);
-      if (MODE == 1) load8(dy + r * C + c0, d);
+    // U rows per trip, all loads issued before the arithmetic: 4 x 2 x 16 B in flight per thread (the one-row loop kept one
+    // or two loads in flight and ran at ~25 % of the HBM roofline)
+    constexpr int U = sizeof(T) == 2 ? 4 : 2;
+    for (int64_t r = r0 + rl; r < r1; r += 32 * U) {
+      float v[U][8], d[U][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (MODE == 0) {
-          s0[j] += v[j];
-          s1[j] = fmaf(v[j], v[j], s1[j]);
-        } else {
-          const float xh = (v[j] - mean[j]) * rstd[j];
-          const float dz = d[j] * act_grad(fmaf(g[j], xh, bt[j]), bn.act);
-          s0[j] += dz;
-          s1[j] = fmaf(dz, xh, s1[j]);
+      for (int u = 0; u < U; ++u) {
+        const int64_t rr = r + 32 * u;
+        if (rr < r1) {
+          load8(x + rr * C + c0, v[u]);
+          if (MODE == 1) load8(dy + rr * C + c0, d[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r + 32 * u >= r1) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (MODE == 0) {
+            s0[j] += v[u][j];
+            s1[j] = fmaf(v[u][j], v[u][j], s1[j]);
+          } else {
+            const float xh = (v[u][j] - mean[j]) * rstd[j];
+            const float dz = d[u][j] * act_grad_t<T>(fmaf(g[j], xh, bt[j]), bn.act);
+            s0[j] += dz;
+            s1[j] = fmaf(dz, xh, s1[j]);
+          }
         }
       }
     }
@@ -224,7 +263,7 @@ __global__ void __launch_bounds__(256) col_reduce_vec_kernel(const T* __restrict
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_act_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int C, BnArgs bn,
+__global__ void __launch_bounds__(256, 2) bn_act_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int C, BnArgs bn,
                                                          const T* __restrict__ residual) {
   // thread = (chunk lane ck, row lane rl): a warp touches 4 rows x one 64-channel run (full 128-byte lines); grid.y walks the
   // 64-channel slabs, so a thread's eight (scale, shift) pairs are loop invariants
@@ -238,21 +277,36 @@ __global__ void __launch_bounds__(256) bn_act_vec_kernel(const T* __restrict__ x
     sc[j] = bn.gamma[c0 + j] * rs;
     sh[j] = bn.beta[c0 + j] - bn.mean[c0 + j] * sc[j];
   }
-  for (int64_t r = (int64_t)blockIdx.x * 32 + rl; r < rows; r += (int64_t)gridDim.x * 32) {
-    float v[8], res[8];
-    load8(x + r * C + c0, v);
-    if (residual) load8(residual + r * C + c0, res);
+  constexpr int U = sizeof(T) == 2 ? 4 : 2;
+  const int64_t stride = (int64_t)gridDim.x * 32;
+  for (int64_t r = (int64_t)blockIdx.x * 32 + rl; r < rows; r += stride * U) {
+    float v[U][8], res[U][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] = apply_act<true>(fmaf(v[j], sc[j], sh[j]), bn.act);      // gamma * xhat + beta with the mean folded into the shift
-      if (residual) v[j] += res[j];
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + stride * u;
+      if (rr < rows) {
+        load8(x + rr * C + c0, v[u]);
+        if (residual) load8(residual + rr * C + c0, res[u]);
+      }
     }
-    store8(y + r * C + c0, v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + stride * u;
+      if (rr >= rows) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // gamma * xhat + beta with the mean folded into the shift; bf16 storage: the 1-SFU activations of the inference epilogues
+        const float z = fmaf(v[u][j], sc[j], sh[j]);
+        v[u][j] = sizeof(T) == 2 ? apply_act<false>(z, bn.act) : apply_act<true>(z, bn.act);
+        if (residual) v[u][j] += res[u][j];
+      }
+      store8(y + rr * C + c0, v[u]);
+    }
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_act_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+__global__ void __launch_bounds__(256, 2) bn_act_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
                                                              int64_t rows, int C, float inv_rows, BnArgs bn,
                                                              const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat) {
   const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
@@ -264,17 +318,27 @@ __global__ void __launch_bounds__(256) bn_act_bwd_vec_kernel(const T* __restrict
     mean[j] = bn.mean[c0 + j]; rstd[j] = rsqrtf(bn.var[c0 + j] + bn.eps); g[j] = bn.gamma[c0 + j]; bt[j] = bn.beta[c0 + j];
     m1[j] = sum_dz[c0 + j] * inv_rows; m2[j] = sum_dz_xhat[c0 + j] * inv_rows;
   }
-  for (int64_t r = (int64_t)blockIdx.x * 32 + rl; r < rows; r += (int64_t)gridDim.x * 32) {
-    float v[8], d[8];
-    load8(x + r * C + c0, v);
-    load8(dy + r * C + c0, d);
+  constexpr int U = sizeof(T) == 2 ? 4 : 2;
+  const int64_t stride = (int64_t)gridDim.x * 32;
+  for (int64_t r = (int64_t)blockIdx.x * 32 + rl; r < rows; r += stride * U) {
+    float v[U][8], d[U][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (v[j] - mean[j]) * rstd[j];
-      const float dz = d[j] * act_grad(fmaf(g[j], xh, bt[j]), bn.act);
-      v[j] = g[j] * rstd[j] * (dz - m1[j] - xh * m2[j]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + stride * u;
+      if (rr < rows) { load8(x + rr * C + c0, v[u]); load8(dy + rr * C + c0, d[u]); }
     }
-    store8(dx + r * C + c0, v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + stride * u;
+      if (rr >= rows) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (v[u][j] - mean[j]) * rstd[j];
+        const float dz = d[u][j] * act_grad_t<T>(fmaf(g[j], xh, bt[j]), bn.act);
+        v[u][j] = g[j] * rstd[j] * (dz - m1[j] - xh * m2[j]);
+      }
+      store8(dx + rr * C + c0, v[u]);
+    }
   }
 }
 

@@ -536,4 +536,45 @@ int ftc_transformer_predict(ftc_transformer* t, const float* enc_input, int batc
   return 0;
 }
 
+// TransformerPredictor.forward for a batch of INDEPENDENT sequences: every sequence follows the stop rules the reference applies
+// to a batch of one (models/transformer.py:326, :356 test torch.all / torch.any over whatever batch they are given, so a batched
+// reference call couples its sequences; process_ocr_base.py:235 always calls it with one chunk).  The chunks of a page decoded
+// here in one call therefore give exactly the code points of the reference's chunk-by-chunk loop.  seq_state: device int32
+// [3 * batch] = {done, passes, stop reason} per sequence on return; scratch_i32: device int32 [2 * batch + 4].
+int ftc_transformer_predict_each(ftc_transformer* t, const float* enc_input, int batch, int enc_len, int dec_len, int64_t* out_ids,
+                                 int max_passes, int* seq_state, int* scratch_i32, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  FTC_REQUIRE(t && enc_input && out_ids && seq_state && scratch_i32 && workspace && batch > 0 && max_passes > 0, "bad argument");
+  FTC_REQUIRE(t->packed, "ftc_transformer_pack_weights must be called first");
+  FTC_REQUIRE(enc_len <= t->cfg.max_enc_len && dec_len <= t->cfg.max_dec_len && enc_len <= t->cfg.max_dec_len,
+              "sequence longer than the positional tables");
+  FTC_REQUIRE(workspace_bytes >= ftc_transformer_workspace_bytes(t, batch, enc_len, dec_len), "workspace too small");
+  size_t used;
+  Bufs b = carve(t, batch, enc_len, dec_len, workspace, workspace_bytes, &used);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int M = batch * dec_len;
+  RUN(encode_impl(t, enc_input, batch, enc_len, b, s));
+  {
+    std::vector<int64_t> init((size_t)M, 3);
+    FTC_CHECK_CUDA(cudaMemcpyAsync(b.dec_in, init.data(), (size_t)M * 8, cudaMemcpyHostToDevice, s));
+    FTC_CHECK_CUDA(cudaStreamSynchronize(s));
+  }
+  int* seq_flags = scratch_i32;
+  int* n_running = scratch_i32 + 2 * batch;
+  FTC_CHECK_CUDA(cudaMemsetAsync(scratch_i32, 0, sizeof(int) * (2 * (size_t)batch + 4), s));
+  FTC_CHECK_CUDA(cudaMemsetAsync(seq_state, 0, sizeof(int) * 3 * (size_t)batch, s));
+  for (int k = 0; k < max_passes; ++k) {
+    FTC_CHECK_CUDA(cudaMemsetAsync(b.flags, 0, 8, s));
+    FTC_CHECK_CUDA(cudaMemsetAsync(n_running, 0, sizeof(int), s));
+    RUN(decode_impl(t, b.dec_in, batch, dec_len, enc_len, b, b.logits, s));
+    RUN(mask_predict_step(b.logits, 3 * HEAD_LD, HEAD_LD, b.dec_in, b.ids, b.prob, b.next_in, b.flags, M, s, dec_len, seq_flags));
+    RUN(mask_predict_advance(seq_flags, seq_state, b.dec_in, b.next_in, b.ids, out_ids, batch, dec_len, k, max_passes - 1, n_running, s));
+    int running = 0;
+    FTC_CHECK_CUDA(cudaMemcpyAsync(&running, n_running, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FTC_CHECK_CUDA(cudaStreamSynchronize(s));
+    if (running == 0) break;
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) mask_predict_step_kernel(const float* __r
                                                                 const int64_t* __restrict__ dec_in, int64_t* __restrict__ ids,
                                                                 float* __restrict__ prob, int64_t* __restrict__ next_in,
                                                                 int* __restrict__ flags, int M, int64_t inv12, int64_t inv13,
-                                                                int64_t inv23) {
+                                                                int64_t inv23, int seq_len, int* __restrict__ seq_flags) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= M) return;
   const int mods[3] = {(int)CRT_M1, (int)CRT_M2, (int)CRT_M3};
@@ -294,9 +294,38 @@ __global__ void __launch_bounds__(256) mask_predict_step_kernel(const float* __r
     prob[warp] = bp;
     const int64_t din = dec_in[warp];
     const bool remask = (bp < 0.9f) || (bid > 0x3FFFF);
-    if (din == 3 && bid > 0 && !(bp > 0.99f)) atomicOr(&flags[0], 1);
-    if (remask) atomicOr(&flags[1], 1);
+    if (din == 3 && bid > 0 && !(bp > 0.99f)) { atomicOr(&flags[0], 1); if (seq_flags) atomicOr(&seq_flags[2 * (warp / seq_len)], 1); }
+    if (remask) { atomicOr(&flags[1], 1); if (seq_flags) atomicOr(&seq_flags[2 * (warp / seq_len) + 1], 1); }
     next_in[warp] = remask ? (int64_t)3 : bid;
+  }
+}
+
+// Per-sequence bookkeeping of the mask-predict loop (TransformerPredictor.forward, models/transformer.py:326-358, evaluated for
+// EACH sequence as the reference evaluates it for its batch of one): a sequence stops at pass k if none of its masked, non-PAD
+// positions is below 0.99 ("early stop"), or if nothing of it would be re-masked ("no remask stop", not on the last pass), or
+// after the last pass; its code points are frozen then.  One CTA per sequence.  state[b] = {done, passes, reason}.
+__global__ void __launch_bounds__(128) mask_predict_advance_kernel(int* __restrict__ seq_flags, int* __restrict__ state,
+                                                                   int64_t* __restrict__ dec_in, const int64_t* __restrict__ next_in,
+                                                                   const int64_t* __restrict__ ids, int64_t* __restrict__ out_ids,
+                                                                   int seq_len, int k, int last, int* __restrict__ n_running) {
+  const int b = blockIdx.x;
+  int* st = state + 3 * b;
+  const int f0 = seq_flags[2 * b], f1 = seq_flags[2 * b + 1];
+  __syncthreads();
+  if (threadIdx.x == 0) { seq_flags[2 * b] = 0; seq_flags[2 * b + 1] = 0; }       // re-arm for the next pass
+  if (st[0]) return;
+  int reason = 0;
+  bool stop = false;
+  if (f0 == 0) { stop = true; reason = 1; }
+  else if (k < last && f1 == 0) { stop = true; reason = 2; }
+  else if (k == last) stop = true;
+  if (stop) {
+    for (int i = threadIdx.x; i < seq_len; i += blockDim.x) out_ids[(int64_t)b * seq_len + i] = ids[(int64_t)b * seq_len + i];
+    __syncthreads();
+    if (threadIdx.x == 0) { st[0] = 1; st[1] = k + 1; st[2] = reason; }
+  } else {
+    for (int i = threadIdx.x; i < seq_len; i += blockDim.x) dec_in[(int64_t)b * seq_len + i] = next_in[(int64_t)b * seq_len + i];
+    if (threadIdx.x == 0) atomicAdd(n_running, 1);
   }
 }
 
@@ -579,12 +608,19 @@ int attention(const void* q, int q_stride, int q_off, const void* k, const void*
   FTC_REQUIRE(false, "attention: head_dim must be 16, 32 or 64");
 }
 
+int mask_predict_advance(int* seq_flags, int* state, int64_t* dec_in, const int64_t* next_in, const int64_t* ids, int64_t* out_ids,
+                         int batch, int seq_len, int k, int last, int* n_running, cudaStream_t s) {
+  mask_predict_advance_kernel<<<batch, 128, 0, s>>>(seq_flags, state, dec_in, next_in, ids, out_ids, seq_len, k, last, n_running);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
 int mask_predict_step(const float* logits, int ld, int head_ld, const int64_t* dec_in, int64_t* ids, float* prob,
-                      int64_t* next_in, int* flags, int M, cudaStream_t s) {
+                      int64_t* next_in, int* flags, int M, cudaStream_t s, int seq_len, int* seq_flags) {
   const int64_t inv12 = powmod(CRT_M1, CRT_M2 - 2, CRT_M2), inv13 = powmod(CRT_M1, CRT_M3 - 2, CRT_M3),
                 inv23 = powmod(CRT_M2, CRT_M3 - 2, CRT_M3);
   mask_predict_step_kernel<<<ceil_div(M, 8), 256, 0, s>>>(logits, ld, head_ld, dec_in, ids, prob, next_in, flags, M, inv12,
-                                                         inv13, inv23);
+                                                         inv13, inv23, seq_len > 0 ? seq_len : 1, seq_flags);
   FTC_POST_LAUNCH();
   return 0;
 }

@@ -30,7 +30,10 @@ int attention(const void* q, int q_stride, int q_off, const void* k, const void*
 //   -> ids int64 [M], prob fp32 [M]; flags[0] |= any(dec_in==MSK && id>0 && !(p>0.99)); flags[1] |= any(remask);
 //   next_in[m] = remask ? MSK : id   (remask = p < 0.9 || id > 0x3FFFF)
 int mask_predict_step(const float* logits, int ld, int head_ld, const int64_t* dec_in, int64_t* ids, float* prob,
-                      int64_t* next_in, int* flags, int M, cudaStream_t s);
+                      int64_t* next_in, int* flags, int M, cudaStream_t s, int seq_len = 0, int* seq_flags = nullptr);
+// per-sequence stop rules of the mask-predict loop (see transformer_ops.cu); seq_flags int [2 * batch], state int [3 * batch]
+int mask_predict_advance(int* seq_flags, int* state, int64_t* dec_in, const int64_t* next_in, const int64_t* ids, int64_t* out_ids,
+                         int batch, int seq_len, int k, int last, int* n_running, cudaStream_t s);
 
 int interleave_rows_f32(float* dst, const float* a, const float* b, int rows, int cols, cudaStream_t s);
 int cast_f32(void* dst, int dtype, const float* src, int64_t n, cudaStream_t s);

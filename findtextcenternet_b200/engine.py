@@ -332,3 +332,18 @@ class TransformerEngine:
                                                         C.byref(passes), C.byref(reason), ws.data_ptr(), ws.numel(),
                                                         _stream_ptr(self.device)), "ftc_transformer_predict")
         return ids, passes.value, reason.value
+
+    def predict_each(self, enc_input: torch.Tensor, dec_len: int, max_passes: int = 8):
+        """Independent sequences (every chunk stops by its own rule, as the reference's chunk-by-chunk loop does) ->
+        (ids int64 [B, dec_len], state int32 [B, 3] = (1, passes, stop reason))"""
+        x = self._check(enc_input)
+        b, le, _ = x.shape
+        ids = torch.empty(b, dec_len, dtype=torch.int64, device=self.device)
+        state = torch.empty(b, 3, dtype=torch.int32, device=self.device)
+        scratch = torch.empty(2 * b + 4, dtype=torch.int32, device=self.device)
+        ws = self._workspace(b, le, dec_len)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ftc_transformer_predict_each(self.handle, x.data_ptr(), b, le, dec_len, ids.data_ptr(), max_passes,
+                                                             state.data_ptr(), scratch.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                             _stream_ptr(self.device)), "ftc_transformer_predict_each")
+        return ids, state

@@ -155,6 +155,24 @@ class TransformerPredictor(nn.Module, _EngineOwner):
         self.last_passes, self.last_stop_reason = passes, reason
         return ids
 
+    def forward_each(self, enc_input):
+        """A batch of INDEPENDENT sequences: each one stops by the rules the reference applies to a batch of one, so row i equals
+        ``forward(enc_input[i:i+1])`` -- what ``call_OCR`` gets from its chunk-by-chunk ``call_transformer`` loop
+        (process_ocr_base.py:235).  Prints the reference's stop line per sequence when ``verbose``."""
+        _no_train(self)
+        if not enc_input.is_cuda:
+            raise RuntimeError("findtextcenternet_b200 transformer: input must be a CUDA tensor (no CPU path)")
+        with torch.no_grad():
+            ids, state = self.engine(enc_input.device).predict_each(enc_input, max_decoderlen, 8)
+        self.last_state = state.cpu()
+        if self.verbose:
+            for _, passes, reason in self.last_state.tolist():
+                if reason == 1:
+                    print(f"[{passes - 1} early stop]")
+                elif reason == 2:
+                    print(f"[{passes - 1} no remask stop]")
+        return ids
+
 
 def _flat_mask(key_mask, batch: int):
     """The reference passes the additive key mask as [B,1,1,Le] (models/transformer.py:250); the kernels take [B, Le] fp32."""

@@ -228,4 +228,4 @@ class OCR_b200_Processer(_Base):
         if self.transformer is None:
             self._load_transformer()
         x = torch.from_numpy(np.ascontiguousarray(encoder_inputs, dtype=np.float32)).to(self.device)
-        return self.transformer(x).cpu().numpy()
+        return self.transformer.forward_each(x).cpu().numpy()      # every chunk stops by its own rule: == chunk-by-chunk calls

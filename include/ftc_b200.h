@@ -124,6 +124,13 @@ int ftc_transformer_forward(ftc_transformer* t, const float* enc_input, const in
 int ftc_transformer_predict(ftc_transformer* t, const float* enc_input, int batch, int enc_len, int dec_len, int64_t* out_ids,
                             int max_passes, int* passes_run, int* stop_reason, void* workspace, size_t workspace_bytes,
                             void* stream);
+/* The same loop for a batch of INDEPENDENT sequences (all feature chunks of a page in one call, process_ocr_base.py:187-283): each
+ * sequence stops by the rules the reference applies to its batch of one (it always decodes chunk by chunk, :235), so the result
+ * equals the chunk-by-chunk loop.  seq_state: device int32 [3 * batch] = {1, passes run, stop reason} per sequence on return;
+ * scratch_i32: device int32 [2 * batch + 4].  Synchronises once per pass. */
+int ftc_transformer_predict_each(ftc_transformer* t, const float* enc_input, int batch, int enc_len, int dec_len, int64_t* out_ids,
+                                 int max_passes, int* seq_state, int* scratch_i32, void* workspace, size_t workspace_bytes,
+                                 void* stream);
 /* one mask-predict decision per position on fp32 logits (models/transformer.py:311-324 + util_func.py:92-126) */
 int ftc_mask_predict_step(const float* logits, int ld, int head_ld, const int64_t* dec_in, int64_t* ids, float* prob,
                           int64_t* next_in, int* flags, int rows, void* stream);

@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference)
 on the synthetic checkpoints.  Runs only in the build container (the GPU box has no
-/root/reference); the outputs are committed.  Usage:  python oracle/make_golden.py [detector|page|transformer|optimizer|radam|loss|all]
+/root/reference); the outputs are committed.  Usage:  python oracle/make_golden.py [detector|page|chunks|transformer|optimizer|radam|loss|all]
 """
 import io
 import os
@@ -191,6 +191,92 @@ def golden_page():
     print("page goldens written")
 
 
+def chunk_features(seed: int, n: int) -> np.ndarray:
+    """Synthetic ``features`` [n, 106] of call_OCR (process_ocr_base.py:114-171): 100 glyph features + 5 x (vertical, rubybase,
+    ruby, space, emphasis, newline) flags, with runs of ruby / ruby base, spaces, single and double newlines and a
+    horizontal / vertical change, so that every split rule of the chunk loop (:187-283) fires."""
+    rng = np.random.default_rng(seed)
+    f = np.zeros((n, 106), dtype=np.float32)
+    f[:, :100] = rng.standard_normal((n, 100)).astype(np.float32)
+    vertical, i = 0, 0
+    while i < n:
+        run = int(rng.integers(5, 60))
+        kind = rng.random()
+        for k in range(i, min(n, i + run)):
+            f[k, 100] = 5 * vertical
+            if kind < 0.15:
+                f[k, 101] = 5                       # ruby base run ...
+            elif kind < 0.3:
+                f[k, 102] = 5                       # ... ruby text run
+            if rng.random() < 0.08:
+                f[k, 103] = 5                       # space
+        i += run
+        if i < n:                                    # newline row(s) between runs
+            f[i, :100] = 0
+            f[i, 100] = 5 * vertical
+            f[i, 105] = 5
+            i += 1
+            if rng.random() < 0.3 and i < n:
+                f[i, :100] = 0
+                f[i, 100] = 5 * vertical
+                f[i, 105] = 5
+                i += 1
+            if rng.random() < 0.2:
+                vertical ^= 1
+    return f
+
+
+def stub_codes(encoder_input: np.ndarray) -> np.ndarray:
+    """Deterministic stand-in for call_transformer in the chunk goldens: one code point per feature row between the SP tokens
+    (a function of the row's first feature), SOT first, EOT after the last."""
+    x = encoder_input[0]
+    sp = np.zeros(106, dtype=np.float32); sp[0:100:2] = 5; sp[1:100:2] = -5
+    end = next(k for k in range(1, x.shape[0]) if np.array_equal(x[k], -sp))
+    out = np.zeros(x.shape[0], dtype=np.int64)
+    out[0] = 1
+    for k in range(1, end):
+        out[k] = 0x3042 + int(abs(float(x[k, 0])) * 7) % 80 if x[k, 105] == 0 else 0x0A
+    out[end] = 2
+    return out
+
+
+def golden_chunks():
+    """tests/golden/chunks_seed0.json: the chunk windows, overlaps and assembled text of the UNMODIFIED reference loop
+    (process_ocr_base.py:187-283, executed from the reference's own source text with a stub call_transformer)."""
+    import json, textwrap
+    from const import max_encoderlen, decoder_SOT, decoder_EOT, decoder_PAD
+    encoder_dim = 106
+    src = open(os.path.join(REF, "process_ocr_base.py")).read().split("\n")
+    body = textwrap.dedent("\n".join(src[181:283]))           # cur_i = 0 ... end of the while loop (:182-283)
+    assert body.startswith("cur_i = 0") and "linebuf += " in body, body[:80]
+    out = {}
+    for seed, n in ((0, 37), (1, 420), (2, 1300), (3, 800), (4, 396), (5, 397), (6, 398)):
+        features = chunk_features(seed, n)
+        calls = []
+
+        class Self:
+            def call_transformer(self, encoder_input):
+                calls.append(encoder_input.copy())
+                return stub_codes(encoder_input)
+
+        SP_token = np.zeros([encoder_dim], dtype=np.float32)
+        SP_token[0:100:2] = 5
+        SP_token[1:100:2] = -5
+        ns = dict(np=np, features=features, self=Self(), max_encoderlen=max_encoderlen, encoder_dim=encoder_dim, SP_token=SP_token,
+                  decoder_SOT=decoder_SOT, decoder_EOT=decoder_EOT, decoder_PAD=decoder_PAD)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            exec(compile(body, "process_ocr_base.py:182-283", "exec"), ns)
+        windows = [[int(v) for v in ln.split("/")[0].split()] for ln in buf.getvalue().strip().split("\n") if ln.strip()]
+        out[f"s{seed}_n{n}"] = dict(seed=seed, n=n, windows=windows, result_txt=ns["result_txt"],
+                                    linebuf=[[int(a), int(b), c] for a, b, c in ns["linebuf"]],
+                                    input_sums=[float(np.abs(c).sum()) for c in calls])
+        print(seed, n, "chunks", len(windows), "text", len(ns["result_txt"]))
+    with open(os.path.join(GOLD, "chunks_seed0.json"), "w") as f:
+        json.dump(out, f)
+    print("chunk goldens written")
+
+
 TRANSFORMER_CFGS = {
     # name: (dims, batch, predictor max_decoderlen)
     "tiny": (dict(embed_dim=64, head_num=4, enc_block_num=2, dec_block_num=2, max_enc_seq_len=24, max_dec_seq_len=24), 3),
@@ -357,6 +443,8 @@ if __name__ == "__main__":
         golden_detector()
     if what in ("page", "all"):
         golden_page()
+    if what in ("chunks", "all"):
+        golden_chunks()
     if what in ("transformer", "all"):
         golden_transformer()
     if what in ("optimizer", "all"):

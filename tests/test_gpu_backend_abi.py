@@ -76,14 +76,47 @@ def test_call_transformer_matches_reference_default_predictor(proc32, golden_tra
 
 
 def test_call_transformer_batch_equals_single_calls(proc32):
-    """call_transformer_batch (all chunks of a page in one predictor call) == chunk-by-chunk call_transformer when no early exit
-    couples the sequences (the reference's batch-global stop tests, models/transformer.py:326,356, see every sequence)."""
+    """call_transformer_batch (all chunks of a page in ONE predictor call, ftc_transformer_predict_each) == the reference's
+    chunk-by-chunk call_transformer loop (process_ocr_base.py:235): every sequence stops by the rule the reference applies to its
+    batch of one, so the code points are identical row by row."""
     from findtextcenternet_b200 import synthetic
     enc, _, _ = synthetic.transformer_inputs(3, 400, 400, seed=1)
     with contextlib.redirect_stdout(io.StringIO()):
         batch = proc32.call_transformer_batch(enc.numpy())
-        passes = proc32.transformer.last_passes
         single = np.stack([proc32.call_transformer(enc[i:i + 1].numpy()) for i in range(3)])
     assert batch.shape == (3, 400) and batch.dtype == np.int64
-    # nobody stopped early (8 passes): per-sequence results do not depend on the batch up to argmax near-ties
-    assert (batch == single).mean() > (0.99 if passes == 8 else 0.9)
+    assert np.array_equal(batch, single)
+
+
+def test_predict_each_follows_per_sequence_stop_rules():
+    """Sequences with DIFFERENT stop behaviour in one batch (tiny model; the output-head bias of U+3042 boosted so that the
+    mask-predict loop exits early, as in the reference golden's 'peaked' / 'medium' variants): forward_each row i == forward on
+    sequence i alone, including the number of passes and the stop reason."""
+    import findtextcenternet_b200.models.transformer as T
+    from findtextcenternet_b200 import arch, synthetic
+    from oracle.make_golden import TRANSFORMER_CFGS
+    dims, _ = TRANSFORMER_CFGS["tiny"]
+    old = T.max_decoderlen
+    T.max_decoderlen = 24
+    try:
+        for boost in (20.0, 10.5, 6.0, 0.0):
+            sd = synthetic.transformer_state_dict(0, **dims)
+            for i, m in enumerate(arch.MODULO_LIST):
+                bias = sd[f"decoder.out_layers.{i}.bias"].clone()
+                bias[0x3042 % m] += boost
+                sd[f"decoder.out_layers.{i}.bias"] = bias
+            model = T.Transformer(**T.ModelDimensions(**dims).__dict__)
+            model.load_state_dict(sd)
+            pred = T.TransformerPredictor(model.encoder, model.decoder).set_precision("fp32").cuda().eval()
+            pred.verbose = False
+            enc, _, _ = synthetic.transformer_inputs(5, 24, 24, seed=3)
+            enc[1] *= 0.05            # a very different sequence: other confidence profile, other stop pass
+            enc = enc.cuda()
+            ids = pred.forward_each(enc).cpu().numpy()
+            state = pred.last_state.numpy()
+            for i in range(enc.shape[0]):
+                one = pred(enc[i:i + 1]).cpu().numpy()[0]
+                assert np.array_equal(ids[i], one), (boost, i)
+                assert state[i, 1] == pred.last_passes and state[i, 2] == pred.last_stop_reason, (boost, i, state[i])
+    finally:
+        T.max_decoderlen = old

@@ -193,3 +193,28 @@ def test_page_tiles_match_the_reference_tiling(h, w):
     assert offsets == ref_offsets
     if (h, w) == (2048, 2048):
         assert page.shape[:2] == (2148, 2148) and len(offsets) == 16
+
+
+def test_chunk_planner_matches_the_reference_loop():
+    """ocr_text.plan_chunks / chunk_inputs / assemble_text == the window loop of call_OCR (process_ocr_base.py:182-283), executed
+    from the UNMODIFIED reference source with a stub transformer (tests/golden/chunks_seed0.json, oracle/make_golden.py::
+    golden_chunks): same windows, same encoder inputs, same overlaps, same assembled text -- for pages that need 1 ... 13 windows
+    and lengths right at the 397-row window limit."""
+    import json
+    from conftest import GOLDEN
+    from findtextcenternet_b200 import ocr_text
+    from oracle.make_golden import chunk_features, stub_codes
+    with open(os.path.join(GOLDEN, "chunks_seed0.json")) as f:
+        gold = json.load(f)
+    assert len(gold) == 7
+    for name, g in gold.items():
+        feats = chunk_features(g["seed"], g["n"])
+        chunks = ocr_text.plan_chunks(feats)
+        assert [[c.prev_j, c.cur_i, c.cur_j] for c in chunks] == g["windows"], name
+        x = ocr_text.chunk_inputs(feats, chunks)
+        assert x.shape == (len(chunks), 400, 106)
+        assert [float(np.abs(x[i]).sum()) for i in range(len(chunks))] == g["input_sums"], name
+        preds = np.stack([stub_codes(x[i:i + 1]) for i in range(len(chunks))])
+        txt, linebuf = ocr_text.assemble_text(chunks, preds)
+        assert txt == g["result_txt"], name
+        assert [[a, b, c] for a, b, c in linebuf] == g["linebuf"], name

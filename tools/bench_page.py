@@ -39,32 +39,51 @@ def main():
     proc = OCR_b200_Processer(detector_state_dict=synthetic.detector_state_dict(0),
                               transformer_state_dict=synthetic.transformer_state_dict(0, **dims), transformer_config=dims)
     proc.detector.detector.weights_frozen = True
+    from findtextcenternet_b200.process_ocr_b200 import page_tiles
     enc, _, _ = synthetic.transformer_inputs(args.chunks, arch.MAX_ENCODERLEN, arch.MAX_DECODERLEN, 0)
     enc = enc.numpy()
-    pages = [synthetic_page(i) for i in range(args.pages + 1)]
-    proc.detect_page(pages[-1]); proc.call_transformer_batch(enc)          # warm-up (weight packing, workspaces)
+    # white page with dark glyph-like rectangles has almost no peaks with the synthetic weights (they were calibrated on noise
+    # images): the noise-based synthetic page keeps a realistic few hundred candidate boxes per page in the selection stage
+    pages = [synthetic.page_image(100 + i, 2048, 2048) for i in range(args.pages + 1)]
+
+    def tiles_of(im0):
+        page, offsets = page_tiles(im0)
+        im = page.astype(np.float32)
+        return im, [{"input": None, "offsetx": x, "offsety": y} for x, y in offsets]
+
+    im, ds = tiles_of(pages[-1])
+    proc.run_detector(ds, im); proc.call_transformer_batch(enc)          # warm-up (weight packing, workspaces)
     torch.cuda.synchronize()
     l0 = _lib.launch_count()
-    t_det = t_tf = 0.0
-    n_peaks = 0
-    for im in pages[:args.pages]:
+    t_prep = t_det = t_tf = 0.0
+    n_boxes = n_cand = 0
+    for im0 in pages[:args.pages]:
         t0 = time.perf_counter()
-        loc, _ = proc.detect_page(im)
-        torch.cuda.synchronize()
+        im, ds = tiles_of(im0)                        # the reference's white padding + float32 page (call_OCR :58-76)
         t1 = time.perf_counter()
-        proc.call_transformer_batch(enc)
+        loc, gf, lines, seps = proc.run_detector(ds, im)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
-        t_det += t1 - t0
-        t_tf += t2 - t1
-        n_peaks += loc.shape[0]
-    total = t_det + t_tf
-    print(json.dumps({"metric": "2048x2048 pages/sec end to end (16 tiles detector + peak decode + batched transformer decode)",
+        proc.call_transformer_batch(enc)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        t_prep += t1 - t0
+        t_det += t2 - t1
+        t_tf += t3 - t2
+        n_boxes += loc.shape[0]
+        n_cand += proc.last_candidates
+    total = t_prep + t_det + t_tf
+    print(json.dumps({"metric": "2048x2048 pages/sec end to end (16 tiles: detector + peak decode + page maps + histogram scores + greedy "
+                                "box selection on the device, then batched transformer decode)",
                       "value": args.pages / total, "unit": "pages/s", "n_gpus": 1, "pages": args.pages,
-                      "ms_per_page": 1e3 * total / args.pages, "detector_ms": 1e3 * t_det / args.pages,
-                      "transformer_ms": 1e3 * t_tf / args.pages, "chunks_per_page": args.chunks, "peaks_per_page": n_peaks / args.pages,
+                      "ms_per_page": 1e3 * total / args.pages, "host_page_prep_ms": 1e3 * t_prep / args.pages,
+                      "run_detector_ms": 1e3 * t_det / args.pages, "transformer_ms": 1e3 * t_tf / args.pages,
+                      "chunks_per_page": args.chunks, "candidates_per_page": n_cand / args.pages, "boxes_per_page": n_boxes / args.pages,
                       "gpu_launches": int(_lib.launch_count() - l0), "data": "synthetic",
-                      "note": "host wall clock around synchronised calls; linedetect / NMS post-processing (reference host code) not included"}))
+                      "h2d_bytes_per_page": int(pages[0].shape[0] + 100) ** 2 * 3,
+                      "note": "run_detector = OCR_b200_Processer.run_detector (drop-in for process_ocr_base.py:474-650): uint8 page H2D, tiles "
+                              "cut on the device, imageHist + greedy selection included; linedetect (reference C++ host tool) and the "
+                              "chunk assembly are not part of this number; host wall clock around synchronised calls"}))
 
 
 if __name__ == "__main__":
