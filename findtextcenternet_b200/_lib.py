@@ -129,6 +129,7 @@ SYMBOLS = {
     "ftc_select_boxes_scratch_bytes": (_sz, [_i]),
     "ftc_select_boxes": (_i, [_vp, _vp, _i, _vp, _i, _vp, _d, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ftc_debug_set_wgrad_mma": (_i, [_i]),
+    "ftc_debug_set_bn_unroll": (_i, [_i]),
     "ftc_debug_set_wgrad_tc": (_i, [_i]),
     "ftc_page_maps": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "ftc_op_attention": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ x
 // channels, so its per-channel constants live in registers and every load / store is a full 16-byte piece; the scalar kernels
 // above remain for odd channel counts.  Reduction CTA = 8 chunk lanes (64 channels, one 128-byte line of bf16 per row) x 32
 // row lanes.
-template <typename T, int MODE>
-__global__ void __launch_bounds__(256, 2) col_reduce_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t rows, int C,
+template <typename T, int MODE, int U>
+__global__ void __launch_bounds__(256, U >= 4 ? 2 : (U == 2 ? 3 : 3)) col_reduce_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t rows, int C,
                                                              int64_t rows_per_chunk, float* __restrict__ part, BnArgs bn) {
   __shared__ float sm[2][32][RED_CH + 1];
   const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
@@ -218,7 +218,6 @@ __global__ void __launch_bounds__(256, 2) col_reduce_vec_kernel(const T* __restr
     }
     // U rows per trip, all loads issued before the arithmetic: 4 x 2 x 16 B in flight per thread (the one-row loop kept one
     // or two loads in flight and ran at ~25 % of the HBM roofline)
-    constexpr int U = sizeof(T) == 2 ? 4 : 2;
     for (int64_t r = r0 + rl; r < r1; r += 32 * U) {
       float v[U][8], d[U][8];
 #pragma unroll
@@ -262,8 +261,8 @@ __global__ void __launch_bounds__(256, 2) col_reduce_vec_kernel(const T* __restr
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256, 2) bn_act_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int C, BnArgs bn,
+template <typename T, int U>
+__global__ void __launch_bounds__(256, U >= 4 ? 2 : (U == 2 ? 3 : 3)) bn_act_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int C, BnArgs bn,
                                                          const T* __restrict__ residual) {
   // thread = (chunk lane ck, row lane rl): a warp touches 4 rows x one 64-channel run (full 128-byte lines); grid.y walks the
   // 64-channel slabs, so a thread's eight (scale, shift) pairs are loop invariants
@@ -277,7 +276,6 @@ __global__ void __launch_bounds__(256, 2) bn_act_vec_kernel(const T* __restrict_
     sc[j] = bn.gamma[c0 + j] * rs;
     sh[j] = bn.beta[c0 + j] - bn.mean[c0 + j] * sc[j];
   }
-  constexpr int U = sizeof(T) == 2 ? 4 : 2;
   const int64_t stride = (int64_t)gridDim.x * 32;
   for (int64_t r = (int64_t)blockIdx.x * 32 + rl; r < rows; r += stride * U) {
     float v[U][8], res[U][8];
@@ -305,8 +303,8 @@ __global__ void __launch_bounds__(256, 2) bn_act_vec_kernel(const T* __restrict_
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256, 2) bn_act_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+template <typename T, int U>
+__global__ void __launch_bounds__(256, U >= 4 ? 2 : (U == 2 ? 3 : 3)) bn_act_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
                                                              int64_t rows, int C, float inv_rows, BnArgs bn,
                                                              const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat) {
   const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
@@ -318,7 +316,6 @@ __global__ void __launch_bounds__(256, 2) bn_act_bwd_vec_kernel(const T* __restr
     mean[j] = bn.mean[c0 + j]; rstd[j] = rsqrtf(bn.var[c0 + j] + bn.eps); g[j] = bn.gamma[c0 + j]; bt[j] = bn.beta[c0 + j];
     m1[j] = sum_dz[c0 + j] * inv_rows; m2[j] = sum_dz_xhat[c0 + j] * inv_rows;
   }
-  constexpr int U = sizeof(T) == 2 ? 4 : 2;
   const int64_t stride = (int64_t)gridDim.x * 32;
   for (int64_t r = (int64_t)blockIdx.x * 32 + rl; r < rows; r += stride * U) {
     float v[U][8], d[U][8];
@@ -1384,6 +1381,14 @@ template <typename T> T* mp(void* p) { return reinterpret_cast<T*>(p); }
 
 bool dtype_ok(int dt) { return dt == DT_F32 || dt == DT_BF16; }
 
+// rows per loop trip of the bf16 BatchNorm kernels (FTC_BN_UNROLL = 1 | 2 | 4; measured by tools/bench_bn.py)
+int g_bn_unroll = -1;
+int bn_unroll() {
+  if (g_bn_unroll >= 0) return g_bn_unroll;
+  static const int env = [] { const char* e = getenv("FTC_BN_UNROLL"); return e ? atoi(e) : 1; }();
+  return env;
+}
+
 // staged mma.sync weight gradient: -1 = follow FTC_WGRAD_MMA (read once), 0 / 1 = set by ftc_debug_set_wgrad_mma
 int g_wgrad_mma = -1;
 bool wgrad_mma_enabled() {
@@ -1427,9 +1432,13 @@ static int bn_stats_impl(const void* x, int dtype, int64_t rows, int c, float* m
   BnArgs bn = {};
   const bool vec = c % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   if (vec && dtype == DT_F32)
-    col_reduce_vec_kernel<float, 0><<<grid, 256, 0, s>>>(cp<float>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
+    col_reduce_vec_kernel<float, 0, 1><<<grid, 256, 0, s>>>(cp<float>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
+  else if (vec && bn_unroll() >= 4)
+    col_reduce_vec_kernel<bf16, 0, 4><<<grid, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
+  else if (vec && bn_unroll() == 2)
+    col_reduce_vec_kernel<bf16, 0, 2><<<grid, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
   else if (vec)
-    col_reduce_vec_kernel<bf16, 0><<<grid, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
+    col_reduce_vec_kernel<bf16, 0, 1><<<grid, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
   else if (dtype == DT_F32)
     col_reduce_kernel<float, 0><<<grid, RED_THREADS, 0, s>>>(cp<float>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
   else
@@ -1450,9 +1459,13 @@ int ftc_train_bn_act(const void* x, void* y, int dtype, int64_t rows, int c, con
   const bool vec = c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0;
   const dim3 vgrid((unsigned)std::min<int64_t>((rows + 31) / 32, 148 * 8), ceil_div(c, RED_CH));
   if (vec && dtype == DT_F32)
-    bn_act_vec_kernel<float><<<vgrid, 256, 0, s>>>(cp<float>(x), mp<float>(y), rows, c, bn, cp<float>(residual));
+    bn_act_vec_kernel<float, 1><<<vgrid, 256, 0, s>>>(cp<float>(x), mp<float>(y), rows, c, bn, cp<float>(residual));
+  else if (vec && bn_unroll() >= 4)
+    bn_act_vec_kernel<bf16, 4><<<vgrid, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, cp<bf16>(residual));
+  else if (vec && bn_unroll() == 2)
+    bn_act_vec_kernel<bf16, 2><<<vgrid, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, cp<bf16>(residual));
   else if (vec)
-    bn_act_vec_kernel<bf16><<<vgrid, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, cp<bf16>(residual));
+    bn_act_vec_kernel<bf16, 1><<<vgrid, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, cp<bf16>(residual));
   else if (dtype == DT_F32)
     bn_act_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x), mp<float>(y), total, c, bn, cp<float>(residual));
   else
@@ -1474,9 +1487,13 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
   dim3 grid(ceil_div(c, RED_CH), nchunk);
   const bool vec = c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
   if (vec && dtype == DT_F32)
-    col_reduce_vec_kernel<float, 1><<<grid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), rows, c, rpc, (float*)scratch, bn);
+    col_reduce_vec_kernel<float, 1, 1><<<grid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), rows, c, rpc, (float*)scratch, bn);
+  else if (vec && bn_unroll() >= 4)
+    col_reduce_vec_kernel<bf16, 1, 4><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
+  else if (vec && bn_unroll() == 2)
+    col_reduce_vec_kernel<bf16, 1, 2><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
   else if (vec)
-    col_reduce_vec_kernel<bf16, 1><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
+    col_reduce_vec_kernel<bf16, 1, 1><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
   else if (dtype == DT_F32)
     col_reduce_kernel<float, 1><<<grid, RED_THREADS, 0, s>>>(cp<float>(x), cp<float>(dy), rows, c, rpc, (float*)scratch, bn);
   else
@@ -1488,9 +1505,13 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
   const float inv_rows = (float)(1.0 / (double)rows);
   const dim3 vgrid((unsigned)std::min<int64_t>((rows + 31) / 32, 148 * 8), ceil_div(c, RED_CH));
   if (vec && dtype == DT_F32)
-    bn_act_bwd_vec_kernel<float><<<vgrid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), mp<float>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
+    bn_act_bwd_vec_kernel<float, 1><<<vgrid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), mp<float>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
+  else if (vec && bn_unroll() >= 4)
+    bn_act_bwd_vec_kernel<bf16, 4><<<vgrid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
+  else if (vec && bn_unroll() == 2)
+    bn_act_bwd_vec_kernel<bf16, 2><<<vgrid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
   else if (vec)
-    bn_act_bwd_vec_kernel<bf16><<<vgrid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
+    bn_act_bwd_vec_kernel<bf16, 1><<<vgrid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
   else if (dtype == DT_F32)
     bn_act_bwd_kernel<float><<<ew_grid(total), 256, 0, s>>>(cp<float>(x), cp<float>(dy), mp<float>(dx), total, c, inv_rows, bn, dbeta,
                                                            dgamma);
@@ -1873,6 +1894,11 @@ int ftc_page_maps(const float* heat9, int batch, int h, int w, const int* tile_m
   page_maps_kernel<<<ew_grid((int64_t)batch * 7 * h * w), 256, 0, (cudaStream_t)stream>>>(heat9, batch, h, w, tile_meta, (int*)page, page_h4,
                                                                                          page_w4, scale);
   FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_debug_set_bn_unroll(int u) {
+  g_bn_unroll = u;
   return 0;
 }
 

@@ -150,3 +150,47 @@ def train3_step(model, optimizer, encoder_input, decoder_input, label_code, msk_
         shard.allreduce_gradients([p for p in model.parameters() if p.requires_grad], group=group)
     optimizer.step()
     return rawloss["loss"].detach(), {k: v.detach() for k, v in rawloss.items()}
+
+
+# ---- checkpoints (reference: train1.py:203-216, 93-95) --------------------------------------------------------
+def save_checkpoint(path, model, optimizer=None, cov=None, epoch: int = 0, extra: Optional[dict] = None) -> None:
+    """``torch.save`` of the reference's checkpoint dict -- ``{'epoch', 'model_state_dict'}`` (train1.py:213-216; what
+    ``process_ocr_torch.py:13-15`` and every converter load) -- plus what the reference never saves and a true resume needs: the
+    schedule-free optimizer state (``z``, ``exp_avg_sq``, ``k``, ``lr_max``, ``weight_sum``) and the CoV loss-weighting statistics.
+    Readers that only know the reference's two keys are unaffected.  Call it with the optimizer in the mode you want stored: the
+    reference switches to ``optimizer.eval()`` (parameters = averaged iterate x) and re-estimates the BatchNorm statistics with
+    train-mode no-grad forwards before saving (train1.py:203-211)."""
+    data = {"epoch": epoch, "model_state_dict": model.state_dict()}
+    if optimizer is not None:
+        if getattr(optimizer, "_graph_state", None):
+            optimizer.sync_from_graph()              # a CUDA-graph-replayed optimizer keeps k / lr_max / weight_sum on the device
+        data["optimizer_state_dict"] = optimizer.state_dict()
+    if cov is not None:
+        data["cov_state"] = {"current_iter": int(round(float(cov._it))), "alphas": cov.alphas, "running_mean_L": cov.running_mean_L,
+                             "running_mean_l": cov.running_mean_l, "running_S_l": cov.running_S_l, "running_std_l": cov.running_std_l,
+                             "losses": list(cov.losses)}
+    if extra:
+        data.update(extra)
+    torch.save(data, path)
+
+
+def load_checkpoint(path, model, optimizer=None, cov=None, map_location="cpu") -> int:
+    """Inverse of ``save_checkpoint``; a reference checkpoint (weights only) restores the weights and leaves optimizer / CoV state
+    untouched, as train1.py:93-95 does.  Returns the stored epoch."""
+    data = torch.load(path, map_location=map_location, weights_only=True)
+    model.load_state_dict(data["model_state_dict"])
+    if optimizer is not None and "optimizer_state_dict" in data:
+        optimizer.load_state_dict(data["optimizer_state_dict"])
+        if hasattr(optimizer, "_tables"):
+            optimizer._tables = {}                   # the fused step caches device pointers of the state tensors
+        if hasattr(optimizer, "_graph_state"):
+            optimizer._graph_state = {}
+    if cov is not None and "cov_state" in data:
+        st = data["cov_state"]
+        if list(st["losses"]) != list(cov.losses):
+            raise ValueError("checkpoint CoV statistics belong to a different loss list")
+        cov.current_iter = int(st["current_iter"])
+        cov._it.fill_(float(st["current_iter"]))
+        for name in ("alphas", "running_mean_L", "running_mean_l", "running_S_l", "running_std_l"):
+            getattr(cov, name).copy_(st[name].to(getattr(cov, name).device))
+    return int(data.get("epoch", 0))

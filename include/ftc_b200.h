@@ -347,6 +347,8 @@ int ftc_select_boxes(const float* loc, const float* gfeat, int feat_ch, const in
 /* debug / staging: route bf16 weight gradients (cin, cout multiples of 8) through the mma.sync kernel: 1 on, 0 off, -1 follow the
  * FTC_WGRAD_MMA environment variable (default; off when unset) */
 int ftc_debug_set_wgrad_mma(int on);
+/* debug / tuning: rows per loop trip of the bf16 BatchNorm train kernels (1 | 2 | 4; -1 = FTC_BN_UNROLL, default 1) */
+int ftc_debug_set_bn_unroll(int u);
 /* debug / staging: the tcgen05 weight gradient: 0 off, 1 on (three N = 64 row-tap instructions per column shift), 2 on with the
  * three row taps fused into one N = 192 instruction, -1 follow the FTC_WGRAD_TC environment variable (default 2) */
 int ftc_debug_set_wgrad_tc(int mode);
