@@ -1381,6 +1381,20 @@ template <typename T> T* mp(void* p) { return reinterpret_cast<T*>(p); }
 
 bool dtype_ok(int dt) { return dt == DT_F32 || dt == DT_BF16; }
 
+// grid.x of the row-walking element kernels (CTA = 32 row lanes x one 64-channel slab, `slabs` slabs in grid.y).  Every thread
+// pays a prologue of ~100 instructions for its eight channels' parameters (loads, rsqrt, folding), so it must own several rows:
+// ncu (round 2) showed one row per thread on the 48x48 / 24x24 layers -- 36 us for a 28 MB tensor, 1.5 TB/s.  Target eight rows per
+// thread, but never fewer than ~2 CTAs per SM in total.
+unsigned ew_rows_grid(int64_t rows, int slabs) {
+  const int64_t max_x = (rows + 31) / 32;
+  int64_t x = (rows + 32 * 8 - 1) / (32 * 8);
+  const int64_t want = (148 * 2 + slabs - 1) / slabs;
+  if (x < want) x = want;
+  if (x > max_x) x = max_x;
+  if (x > 148 * 8) x = 148 * 8;
+  return (unsigned)(x > 0 ? x : 1);
+}
+
 // rows per loop trip of the bf16 BatchNorm kernels (FTC_BN_UNROLL = 1 | 2 | 4; measured by tools/bench_bn.py)
 int g_bn_unroll = -1;
 int bn_unroll() {
@@ -1457,7 +1471,7 @@ int ftc_train_bn_act(const void* x, void* y, int dtype, int64_t rows, int c, con
   BnArgs bn = {mean, var, gamma, beta, eps, act};
   const int64_t total = rows * c;
   const bool vec = c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0;
-  const dim3 vgrid((unsigned)std::min<int64_t>((rows + 31) / 32, 148 * 8), ceil_div(c, RED_CH));
+  const dim3 vgrid(ew_rows_grid(rows, ceil_div(c, RED_CH)), ceil_div(c, RED_CH));
   if (vec && dtype == DT_F32)
     bn_act_vec_kernel<float, 1><<<vgrid, 256, 0, s>>>(cp<float>(x), mp<float>(y), rows, c, bn, cp<float>(residual));
   else if (vec && bn_unroll() >= 4)
@@ -1503,7 +1517,7 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
   FTC_POST_LAUNCH();
   const int64_t total = rows * c;
   const float inv_rows = (float)(1.0 / (double)rows);
-  const dim3 vgrid((unsigned)std::min<int64_t>((rows + 31) / 32, 148 * 8), ceil_div(c, RED_CH));
+  const dim3 vgrid(ew_rows_grid(rows, ceil_div(c, RED_CH)), ceil_div(c, RED_CH));
   if (vec && dtype == DT_F32)
     bn_act_bwd_vec_kernel<float, 1><<<vgrid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), mp<float>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
   else if (vec && bn_unroll() >= 4)
