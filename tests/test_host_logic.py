@@ -145,6 +145,41 @@ for step in range(2):
     assert torch.allclose(torch.cat([p.grad.reshape(-1) for p in net.parameters()]), mean, atol=1e-6)
     assert unused.grad is None
 gb.remove()
+# gradients that LIVE in flat bucket storage (shard.FlatGradients): in-place bucket all-reduce launched from inside backward,
+# views stay attached across steps, zero() replaces zero_grad(), a parameter without a gradient contributes zeros
+from findtextcenternet_b200.shard import FlatGradients
+torch.manual_seed(2)
+net2 = torch.nn.Sequential(torch.nn.Linear(19, 31), torch.nn.Tanh(), torch.nn.Linear(31, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+unused2 = torch.nn.Parameter(torch.zeros(5))
+params2 = list(net2.parameters()) + [unused2]
+fg = FlatGradients(params2, bucket_bytes=1024)
+assert len(fg.buckets) >= 3 and all(p.grad is not None for p in params2)
+ptrs = [p.grad.data_ptr() for p in params2]
+for step in range(3):
+    fg.zero()
+    gx = torch.Generator().manual_seed(700 + 10 * step + rank)
+    # the same un-averaged local gradients, computed on a detached copy
+    ref_net = torch.nn.Sequential(torch.nn.Linear(19, 31), torch.nn.Tanh(), torch.nn.Linear(31, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+    ref_net.load_state_dict(net2.state_dict())
+    xin = torch.randn(8, 19, generator=gx)
+    ref_net(xin).square().sum().backward()
+    local = torch.cat([p.grad.reshape(-1) for p in ref_net.parameters()])
+    net2(xin).square().sum().backward()
+    assert fg.finish() == len(fg.buckets) and fg.launched_during_backward >= 2 * (step + 1)
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    mean = sum(gathered) / world
+    assert torch.allclose(torch.cat([p.grad.reshape(-1) for p in net2.parameters()]), mean, atol=1e-6), step
+    assert float(unused2.grad.abs().max()) == 0.0
+    assert [p.grad.data_ptr() for p in params2] == ptrs           # static addresses (CUDA-graph / fused-optimizer tables)
+    fg.check_views()
+net2[0].weight.grad = None
+try:
+    fg.check_views()
+    raise SystemExit("check_views did not notice the detached gradient view")
+except RuntimeError:
+    pass
+fg.remove()
 # train1_step: the nine raw losses that drive the CoV weights take their cross-rank mean VALUE but keep the local gradient path
 from findtextcenternet_b200.train import TRAIN1_LOSSES, _sync_loss_values
 leaf = torch.full((len(TRAIN1_LOSSES),), float(rank + 1), requires_grad=True)
