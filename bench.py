@@ -226,6 +226,7 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(e2e_u8_t, op=dist.ReduceOp.MAX)
         e2e_u8_value = world * B * e2e_steps / float(e2e_u8_t.item())
+        h2d_u8 = tiles_u8.numel() + B * 6 * 4
 
         # ---- per-op CUDA-event profile of one forward -> roofline of the tcgen05 conv kernel family ----
         roofline = cpu = None
@@ -298,7 +299,7 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "OCR_b200_Processer.detect_tiles(pinned float32 NHWC 0..255 tiles)", "steps": e2e_steps,
-                "uint8_tiles": {"value": e2e_u8_value, "unit": "images/s", "h2d_bytes_per_step": tiles_u8.numel() + B * 6 * 4,
+                "uint8_tiles": {"value": e2e_u8_value, "unit": "images/s", "h2d_bytes_per_step": h2d_u8,
                                 "note": "same call, host tiles as uint8 (the page's own type): cast to float on the device"}},
         "gpu_launches": launches,
         "roofline": roofline,
