@@ -281,7 +281,7 @@ __device__ __forceinline__ void load4p(const bf16* p, f32x2 (&v)[2]) {
   v[1] = pk2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
 }
 
-template <typename T, int TH>
+template <typename T, int TH, bool RAW>
 __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmIn, T* __restrict__ out, int H, int W, int C,
                                                               const float* __restrict__ w, const float* __restrict__ scale,
                                                               const float* __restrict__ bias, const float* __restrict__ w1,
@@ -336,10 +336,12 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
   const int c0 = cb + quad * 4;
   // raw = plain depthwise convolution (train step: BatchNorm needs the batch statistics of the raw output first; the data
   // gradient of a stride-1 depthwise conv is the same kernel with the taps reversed): no BN / SiLU / SE
-  const bool raw = scale == nullptr;
+  // RAW is a template parameter: as a run-time flag it cost the inference instantiation 300-450 bytes of register spills
+  // (7.4 -> 14.4 ms per B = 32 forward, measured)
+  constexpr bool raw = RAW;
   f32x2 wk[9][2], sc[2], bi[2], ssum[2];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) load4p(w + (flip ? 8 - t : t) * C + c0, wk[t]);      // flip: taps rotated 180 degrees (data gradient)
+  for (int t = 0; t < 9; ++t) load4p(w + ((RAW && flip) ? 8 - t : t) * C + c0, wk[t]);      // flip: taps rotated 180 degrees (data gradient)
   if (!raw) { load4p(scale + c0, sc); load4p(bias + c0, bi); }
   else { sc[0] = sc[1] = pk2(1.f, 1.f); bi[0] = bi[1] = pk2(0.f, 0.f); }
   ssum[0] = ssum[1] = pk2(0.f, 0.f);
@@ -603,6 +605,7 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
   dim3 grid(C / 32, B);
   const int threads = W * 8;
   const float inv_hw = 1.0f / (float)(H * W);
+  const bool raw_mode = scale == nullptr;
   alignas(64) CUtensorMap tmIn;
   {
     int rc = tma_encode_nhwc(&tmIn, in, dtype, C, C, W, H, B, 32, W + 2, TH + 2, CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -611,8 +614,13 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
 #define DWS_LAUNCH(TT)                                                                                                 \
   do {                                                                                                                 \
     static bool done = false;                                                                                          \
-    if (!done) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<TT, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; } \
-    FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip)); \
+    if (!done) {                                                                                                       \
+      FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<TT, TH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<TT, TH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      done = true;                                                                                                     \
+    }                                                                                                                  \
+    if (raw_mode) FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH, true>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip)); \
+    else FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH, false>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip)); \
   } while (0)
   // the mma.sync variant is correct but measured SLOWER on B200 (0.26 vs 0.17 ms at 48x48x1536, B=32: its BN/SiLU/SE
   // epilogue and fragment exchange cost as many issue slots as the FMAs they replace); kept behind FTC_DW_MMA=1
@@ -628,8 +636,13 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
     int rc = tma_encode_nhwc(&tm12, in, dtype, C, C, W, H, B, 32, W + 2, TH12 + 2, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
     static bool done12 = false;
-    if (!done12) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<bf16, TH12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done12 = true; }
-    FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<bf16, TH12>, grid, dim3(threads), smem12, s, tm12, (bf16*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip));
+    if (!done12) {
+      FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<bf16, TH12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<bf16, TH12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      done12 = true;
+    }
+    if (raw_mode) FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<bf16, TH12, true>, grid, dim3(threads), smem12, s, tm12, (bf16*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip));
+    else FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<bf16, TH12, false>, grid, dim3(threads), smem12, s, tm12, (bf16*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip));
   }
   else if (dtype == DT_F32) DWS_LAUNCH(float);
   else if (!env_mma) DWS_LAUNCH(bf16);
