@@ -128,6 +128,9 @@ SYMBOLS = {
     "ftc_box_hists": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
     "ftc_select_boxes_scratch_bytes": (_sz, [_i]),
     "ftc_select_boxes": (_i, [_vp, _vp, _i, _vp, _i, _vp, _d, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ftc_crop_sample_bytes": (_i, []),
+    "ftc_crop_scratch_bytes": (_sz, [_i, _i]),
+    "ftc_crop_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ftc_debug_set_wgrad_mma": (_i, [_i]),
     "ftc_debug_set_bn_unroll": (_i, [_i]),
     "ftc_debug_set_wgrad_tc": (_i, [_i]),

@@ -1,0 +1,366 @@
+// train1 input pipeline on the device: the reference's per-sample Cython routine
+// dataset/processer.pyx::transform_crop (:260-454) + process() (:655-673) + the colour compositing functions (:675-887) +
+// random_salt (dataset/data_detector.py:17-26), for a whole batch in four launches.
+//
+//   crop_init_kernel     centre map = 0, log-size maps = +inf, id maps = 0
+//   crop_prepare_kernel  one CTA per sample: box corners through the page's affine matrix (:345-355), the crop origin from the
+//                        anchor box (:358-366), per-box crop coordinates + in-crop flag, minsize in the reference's sequential
+//                        order (:371-385)
+//   crop_label_kernel    one CTA per box: separable Gaussian (center_map :137-163) merged with atomicMax on the float bit patterns
+//                        (values in (0, 1]), ellipse footprint (box_map :165-186, id_map :188-206) merged with atomicMin / atomicMax:
+//                        maximum and minimum are order-independent, so the result is deterministic
+//   crop_image_kernel    thread per output pixel: inverse affine, inverse_partial folded into the pixel fetch, nearest or bilinear
+//                        gather from the uint8 page (L2-resident), salt cells, colour compositing; coalesced plane writes
+//   crop_maps_kernel     thread per map pixel: bilinear textline / separator crop, +inf -> 0 on the log-size maps
+//
+// Bound: HBM writes (7.1 MB of fp32 image + 1.0 MB of maps per sample; the page bytes a crop touches are ~0.6 MB).
+// Arithmetic follows the generated C of the Cython source operation by operation: float32 with round-to-nearest intrinsics (no
+// FMA contraction), and double where the source promotes ("1 - dx" is emitted as 1.0 - dx, "rx + 0.5", the colour blend).
+// expf / logf are evaluated in double and rounded (<= 1 ulp from any libm).
+// Plain SIMT on purpose: oracle/emu compiles this file for host threads (tests/test_emu_kernels.py).
+#include "../../include/ftc_b200.h"
+#include "common.cuh"
+
+#ifdef FTC_EMU
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline unsigned atomicMax(unsigned* p, unsigned v) {
+  std::lock_guard<std::mutex> g(emu::atomic_lock);
+  unsigned old = *p; if (v > old) *p = v; return old;
+}
+static inline int atomicMin(int* p, int v) {
+  std::lock_guard<std::mutex> g(emu::atomic_lock);
+  int old = *p; if (v < old) *p = v; return old;
+}
+#endif
+
+namespace ftc {
+namespace {
+
+constexpr int CW = 768, CH = 768, CS = 4, MW = CW / CS, MH = CH / CS;     // util_func.py:6-8
+
+struct BoxRec { float cx, cy, w, h; int flag, sample, code1, code2; };
+
+// vector_dot (:75-86): v = 0; v += a[k] * b[k] for b = (x, y, 1), float32, one rounding per operation
+__device__ __forceinline__ void vdot(const float* a, float x, float y, float* rx, float* ry) {
+  *rx = __fadd_rn(__fadd_rn(__fmul_rn(a[0], x), __fmul_rn(a[1], y)), a[2]);
+  *ry = __fadd_rn(__fadd_rn(__fmul_rn(a[3], x), __fmul_rn(a[4], y)), a[5]);
+}
+
+__global__ void crop_init_kernel(float* __restrict__ out_map, int* __restrict__ out_idmap, int batch) {
+  const long long per = (long long)MH * MW;
+  const long long total = (long long)batch * 5 * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)((i / per) % 5);
+    if (ch == 0) out_map[i] = 0.f;
+    else if (ch <= 2) out_map[i] = INFINITY;
+    else {                                   // reuse the index space of channels 3, 4 for the two id-map planes
+      const long long b = i / (5 * per), r = i % per;
+      out_idmap[(b * 2 + (ch - 3)) * per + r] = 0;
+    }
+  }
+}
+
+__global__ void crop_prepare_kernel(const ftc_crop_sample* __restrict__ samples, const float* __restrict__ position,
+                                    const int* __restrict__ codelist, BoxRec* __restrict__ rec, float* __restrict__ start,
+                                    float* __restrict__ out_minsize) {
+  const int b = blockIdx.x;
+  const ftc_crop_sample& s = samples[b];
+  __shared__ float sh_start[2];
+  const int n = s.blank ? 0 : s.box_count;
+  // rotated boxes (cx, cy, w, h) in page coordinates
+  for (int i = threadIdx.x; i < s.box_count; i += blockDim.x) {
+    const float* p = position + (size_t)(s.box_begin + i) * 4;
+    const float hw = __fdiv_rn(p[2], 2.f), hh = __fdiv_rn(p[3], 2.f);
+    float xr1, yr1, xr2, yr2;
+    vdot(s.rot, __fsub_rn(p[0], hw), __fsub_rn(p[1], hh), &xr1, &yr1);
+    vdot(s.rot, __fadd_rn(p[0], hw), __fadd_rn(p[1], hh), &xr2, &yr2);
+    BoxRec r;
+    r.cx = __fdiv_rn(__fadd_rn(xr1, xr2), 2.f);
+    r.cy = __fdiv_rn(__fadd_rn(yr1, yr2), 2.f);
+    r.w = __fsub_rn(xr2, xr1);
+    r.h = __fsub_rn(yr2, yr1);
+    r.flag = 0; r.sample = b;
+    r.code1 = codelist[(size_t)(s.box_begin + i) * 2];
+    r.code2 = codelist[(size_t)(s.box_begin + i) * 2 + 1];
+    rec[s.box_begin + i] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sx = s.startx0, sy = s.starty0;
+    if (s.box_count > 0) {
+      const BoxRec& a = rec[s.box_begin + s.cidx];
+      sx = __fsub_rn(a.cx, s.woffset);
+      sy = __fsub_rn(a.cy, s.hoffset);
+    }
+    sh_start[0] = sx; sh_start[1] = sy;
+    start[b * 2] = sx; start[b * 2 + 1] = sy;
+  }
+  __syncthreads();
+  const float sx = sh_start[0], sy = sh_start[1];
+  for (int i = threadIdx.x; i < s.box_count; i += blockDim.x) {
+    BoxRec& r = rec[s.box_begin + i];
+    r.cx = __fsub_rn(r.cx, sx);
+    r.cy = __fsub_rn(r.cy, sy);
+    r.flag = (i < n && r.cx > 0.f && r.cx < (float)CW && r.cy > 0.f && r.cy < (float)CH) ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {            // the reference's running minimum restarts whenever it is <= 0 (:382-385)
+    float m = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const BoxRec& r = rec[s.box_begin + i];
+      if (!r.flag) continue;
+      const float v = r.h > r.w ? r.h : r.w;
+      if (m <= 0.f) m = v; else m = v < m ? v : m;
+    }
+    out_minsize[b] = m;
+  }
+}
+
+// gkern (:40-47): ax = i - (l - 1) / 2.0 (double, stored float); exp argument ((-0.5 * ax) * ax) / (double)(sig * sig) -> float
+__device__ __forceinline__ float gauss_tap(int i, int l, float sig) {
+  const float ax = (float)__dsub_rn((double)(float)i, __ddiv_rn((double)(float)(l - 1), 2.0));
+  const double arg = __ddiv_rn(__dmul_rn(__dmul_rn(-0.5, (double)ax), (double)ax), (double)__fmul_rn(sig, sig));
+  return (float)exp((double)(float)arg);
+}
+
+__global__ void crop_label_kernel(const BoxRec* __restrict__ rec, float* __restrict__ out_map, int* __restrict__ out_idmap) {
+  const BoxRec r = rec[blockIdx.x];
+  if (!r.flag) return;
+  __shared__ float gx[MW], gy[MH];
+  const long long per = (long long)MH * MW;
+  float* center = out_map + (size_t)r.sample * 5 * per;
+  float* box0 = center + per;
+  float* box1 = center + 2 * per;
+  int* id0 = out_idmap + (size_t)r.sample * 2 * per;
+  int* id1 = id0 + per;
+  // ---- center_map (:137-163) ----
+  {
+    const float cx = __fdiv_rn(r.cx, (float)CS), cy = __fdiv_rn(r.cy, (float)CS);
+    const float w = __fdiv_rn(r.w, (float)CS), h = __fdiv_rn(r.h, (float)CS);
+    const float w2 = __fdiv_rn(w, 2.f), h2 = __fdiv_rn(h, 2.f);
+    const float fix_w = 1.f > w2 ? 1.f : w2, fix_h = 1.f > h2 ? 1.f : h2;
+    const double kw = __dmul_rn((double)fix_w, 1.5), kh = __dmul_rn((double)fix_h, 1.5);
+    const int ks = (int)(kh > kw ? kh : kw);
+    const float std_x = __fdiv_rn(fix_w, 4.f), std_y = __fdiv_rn(fix_h, 4.f);
+    const int L = ks * 2 + 1;
+    const int xi = (int)roundf(cx), yi = (int)roundf(cy);
+    const int x0 = xi - ks, y0 = yi - ks;
+    const int xa = x0 > 0 ? x0 : 0, xb = (x0 + L) < MW ? (x0 + L) : MW;
+    const int ya = y0 > 0 ? y0 : 0, yb = (y0 + L) < MH ? (y0 + L) : MH;
+    for (int x = xa + (int)threadIdx.x; x < xb; x += blockDim.x) gx[x] = gauss_tap(x - x0, L, std_x);
+    for (int y = ya + (int)threadIdx.x; y < yb; y += blockDim.x) gy[y] = gauss_tap(y - y0, L, std_y);
+    __syncthreads();
+    const int ww = xb - xa, wh = yb - ya;
+    if (ww > 0 && wh > 0)
+      for (int i = threadIdx.x; i < ww * wh; i += blockDim.x) {
+        const int x = xa + i % ww, y = ya + i / ww;
+        const float v = __fmul_rn(gy[y], gx[x]);
+        atomicMax(reinterpret_cast<unsigned*>(center + (size_t)y * MW + x), __float_as_uint(v));   // v >= 0
+      }
+  }
+  // ---- box_map / id_map footprint (:165-206) ----
+  {
+    const float w10 = __fdiv_rn(r.w, 10.f), h10 = __fdiv_rn(r.h, 10.f);
+    const float fix_w = (float)CS > w10 ? (float)CS : w10, fix_h = (float)CS > h10 ? (float)CS : h10;
+    const float sizex = (float)__dadd_rn((double)(float)log((double)__fdiv_rn(r.w, 1024.f)), 3.0);
+    const float sizey = (float)__dadd_rn((double)(float)log((double)__fdiv_rn(r.h, 1024.f)), 3.0);
+    int xmin = (int)__fdiv_rn(__fsub_rn(r.cx, fix_w), (float)CS) - 2; xmin = xmin > 0 ? xmin : 0;
+    int xmax = (int)__fdiv_rn(__fadd_rn(r.cx, fix_w), (float)CS) + 2; xmax = xmax < MW ? xmax : MW;
+    int ymin = (int)__fdiv_rn(__fsub_rn(r.cy, fix_h), (float)CS) - 2; ymin = ymin > 0 ? ymin : 0;
+    int ymax = (int)__fdiv_rn(__fadd_rn(r.cy, fix_h), (float)CS) + 2; ymax = ymax < MH ? ymax : MH;
+    const int ww = xmax - xmin, wh = ymax - ymin;
+    if (ww > 0 && wh > 0)
+      for (int i = threadIdx.x; i < ww * wh; i += blockDim.x) {
+        const int xi = xmin + i % ww, yi = ymin + i / ww;
+        const float x = __fsub_rn((float)(xi * CS), r.cx), y = __fsub_rn((float)(yi * CS), r.cy);
+        const float qx = __fdiv_rn(x, fix_w), qy = __fdiv_rn(y, fix_h);
+        if (__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)) < 1.f) {
+          const size_t idx = (size_t)yi * MW + xi;
+          // float minimum through integer atomics: non-negative floats order like signed ints, negative ones like reversed unsigned
+          if (sizex == sizex) {
+            if (sizex >= 0.f) atomicMin(reinterpret_cast<int*>(box0 + idx), __float_as_int(sizex));
+            else atomicMax(reinterpret_cast<unsigned*>(box0 + idx), __float_as_uint(sizex));
+          }
+          if (sizey == sizey) {
+            if (sizey >= 0.f) atomicMin(reinterpret_cast<int*>(box1 + idx), __float_as_int(sizey));
+            else atomicMax(reinterpret_cast<unsigned*>(box1 + idx), __float_as_uint(sizey));
+          }
+          atomicMax(id0 + idx, r.code1);
+          atomicMax(id1 + idx, r.code2);
+        }
+      }
+  }
+}
+
+// getpixel (:208-211) with inverse_partial (:124-135) folded in
+__device__ __forceinline__ float page_pixel(const ftc_crop_sample& s, int x, int y) {
+  if (x < 0 || x >= s.im_w || y < 0 || y >= s.im_h) return 0.f;
+  int v = s.image[(size_t)y * s.im_w + x];
+  if (y >= s.inv_i && y < s.inv_i + s.inv_h && x >= s.inv_j && x < s.inv_j + s.inv_w) v = 255 - v;
+  return __fdiv_rn((float)v, 255.f);
+}
+__device__ __forceinline__ float mask_pixel(const unsigned char* img, int im_h, int im_w, int x, int y) {
+  if (x < 0 || x >= im_w || y < 0 || y >= im_h) return 0.f;
+  return __fdiv_rn((float)img[(size_t)y * im_w + x], 255.f);
+}
+
+// bilinear weights (:396-401): w11 = (1.0 - dx) * (1.0 - dy), w21 = dx * (1.0 - dy), w12 = (1.0 - dx) * dy in double, w22 = dx * dy in float
+__device__ __forceinline__ void bilinear_weights(float rx, float ry, float* w11, float* w21, float* w12, float* w22) {
+  const float dx = __fsub_rn(rx, floorf(rx)), dy = __fsub_rn(ry, floorf(ry));
+  const double ex = __dsub_rn(1.0, (double)dx), ey = __dsub_rn(1.0, (double)dy);
+  *w11 = (float)__dmul_rn(ex, ey);
+  *w21 = (float)__dmul_rn((double)dx, ey);
+  *w12 = (float)__dmul_rn(ex, (double)dy);
+  *w22 = __fmul_rn(dx, dy);
+}
+
+__global__ void crop_image_kernel(const ftc_crop_sample* __restrict__ samples, const float* __restrict__ start,
+                                  float* __restrict__ out_image, int out_channels, int batch) {
+  const long long per = (long long)CH * CW;
+  const long long total = (long long)batch * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per);
+    const int rem = (int)(i % per);
+    const int y = rem / CW, x = rem % CW;
+    const ftc_crop_sample& s = samples[b];
+    float a = 0.f;
+    if (!s.blank) {
+      float rx, ry;
+      vdot(s.inv, __fadd_rn((float)x, start[b * 2]), __fadd_rn((float)y, start[b * 2 + 1]), &rx, &ry);
+      if (s.nearest) {
+        a = page_pixel(s, (int)__dadd_rn((double)rx, 0.5), (int)__dadd_rn((double)ry, 0.5));
+      } else {
+        float w11, w21, w12, w22;
+        bilinear_weights(rx, ry, &w11, &w21, &w12, &w22);
+        const int ix = (int)rx, iy = (int)ry;
+        a = __fmul_rn(w11, page_pixel(s, ix, iy));
+        a = __fadd_rn(a, __fmul_rn(w21, page_pixel(s, ix + 1, iy)));
+        a = __fadd_rn(a, __fmul_rn(w12, page_pixel(s, ix, iy + 1)));
+        a = __fadd_rn(a, __fmul_rn(w22, page_pixel(s, ix + 1, iy + 1)));
+      }
+    }
+    if (s.salt != nullptr) {           // random_salt (data_detector.py:17-26): x * noise, NaN cells -> 1
+      const int c = s.salt[(size_t)(y / s.salt_s) * s.salt_w + x / s.salt_s];
+      a = c == 0 ? 0.f : (c == 2 ? 1.f : a);
+    }
+    if (out_channels == 1) { out_image[i] = a; continue; }
+    float* o = out_image + (size_t)b * 3 * per + rem;
+    const double na = __dsub_rn(1.0, (double)a);
+    if (s.color_mode == 2) {           // random_background (:690-741)
+      const int yi = y + s.bg_starty, xi = x + s.bg_startx;
+      const bool in = yi >= 0 && yi < s.bg_h && xi >= 0 && xi < s.bg_w;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float bgv = in ? __fdiv_rn((float)s.bgimg[((size_t)yi * s.bg_w + xi) * 3 + c], 255.f) : 0.f;
+        double v = __dadd_rn((double)__fmul_rn(a, s.fg1[c]), __dmul_rn(na, (double)bgv));
+        v = v < 1.0 ? v : 1.0;         // max(0, min(1, v)) as the generated comparisons evaluate it
+        v = v > 0.0 ? v : 0.0;
+        o[(size_t)c * per] = (float)v;
+      }
+    } else {                           // random_mono / random_single / random_double (:745-887)
+      const bool inner = x > s.rect_left && x < s.rect_right && y > s.rect_top && y < s.rect_bottom;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float fg = inner ? s.fg2[c] : s.fg1[c];
+        o[(size_t)c * per] = (float)__dadd_rn((double)__fmul_rn(a, fg), __dmul_rn(na, (double)s.bg[c]));
+      }
+    }
+  }
+}
+
+__global__ void crop_maps_kernel(const ftc_crop_sample* __restrict__ samples, const float* __restrict__ start,
+                                 float* __restrict__ out_map, int batch) {
+  const long long per = (long long)MH * MW;
+  const long long total = (long long)batch * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per);
+    const int rem = (int)(i % per);
+    const int y = rem / MW, x = rem % MW;
+    const ftc_crop_sample& s = samples[b];
+    float* m = out_map + (size_t)b * 5 * per + rem;
+    if (s.blank) {
+      m[0] = 0.f; m[per] = 0.f; m[2 * per] = 0.f; m[3 * per] = 0.f; m[4 * per] = 0.f;
+      continue;
+    }
+    // +inf (no box) -> 0 (:441-442)
+    const float b0 = m[per], b1 = m[2 * per];
+    m[per] = (b0 - b0 == 0.f) ? b0 : 0.f;
+    m[2 * per] = (b1 - b1 == 0.f) ? b1 : 0.f;
+    float rx, ry;
+    const float px = __fadd_rn(__fmul_rn((float)x, (float)(CS / 2)), __fdiv_rn(start[b * 2], 2.f));
+    const float py = __fadd_rn(__fmul_rn((float)y, (float)(CS / 2)), __fdiv_rn(start[b * 2 + 1], 2.f));
+    vdot(s.inv2, px, py, &rx, &ry);
+    float w11, w21, w12, w22;
+    bilinear_weights(rx, ry, &w11, &w21, &w12, &w22);
+    const int ix = (int)rx, iy = (int)ry;
+    float t = __fmul_rn(w11, mask_pixel(s.textline, s.im_h2, s.im_w2, ix, iy));
+    t = __fadd_rn(t, __fmul_rn(w21, mask_pixel(s.textline, s.im_h2, s.im_w2, ix + 1, iy)));
+    t = __fadd_rn(t, __fmul_rn(w12, mask_pixel(s.textline, s.im_h2, s.im_w2, ix, iy + 1)));
+    t = __fadd_rn(t, __fmul_rn(w22, mask_pixel(s.textline, s.im_h2, s.im_w2, ix + 1, iy + 1)));
+    float p = __fmul_rn(w11, mask_pixel(s.sepline, s.im_h2, s.im_w2, ix, iy));
+    p = __fadd_rn(p, __fmul_rn(w21, mask_pixel(s.sepline, s.im_h2, s.im_w2, ix + 1, iy)));
+    p = __fadd_rn(p, __fmul_rn(w12, mask_pixel(s.sepline, s.im_h2, s.im_w2, ix, iy + 1)));
+    p = __fadd_rn(p, __fmul_rn(w22, mask_pixel(s.sepline, s.im_h2, s.im_w2, ix + 1, iy + 1)));
+    m[3 * per] = t;
+    m[4 * per] = p;
+  }
+}
+
+#ifdef FTC_EMU
+constexpr int kThreads = 32, kMaxBlocks = 4, kBoxThreads = 32;     // one OS thread per CUDA thread on the host
+#else
+constexpr int kThreads = 256, kMaxBlocks = 148 * 16, kBoxThreads = 128;
+#endif
+
+inline int grid_for(long long n) {
+  long long g = (n + kThreads - 1) / kThreads;
+  return (int)(g < 1 ? 1 : (g > kMaxBlocks ? kMaxBlocks : g));
+}
+
+}  // namespace
+}  // namespace ftc
+
+using namespace ftc;
+
+extern "C" int ftc_crop_sample_bytes(void) { return (int)sizeof(ftc_crop_sample); }
+
+extern "C" size_t ftc_crop_scratch_bytes(int batch, int total_boxes) {
+  return (size_t)(total_boxes > 0 ? total_boxes : 1) * sizeof(BoxRec) + (size_t)(batch > 0 ? batch : 1) * 2 * sizeof(float) + 256;
+}
+
+extern "C" int ftc_crop_batch(const ftc_crop_sample* samples, int batch, const float* position, const int* codelist, int total_boxes,
+                              float* out_image, int out_channels, float* out_map, int* out_idmap, float* out_minsize, void* scratch,
+                              size_t scratch_bytes, void* stream) {
+  FTC_REQUIRE(batch > 0 && total_boxes >= 0, "ftc_crop_batch: batch / boxes");
+  FTC_REQUIRE(out_channels == 1 || out_channels == 3, "ftc_crop_batch: out_channels is 1 (gray) or 3 (composited)");
+  FTC_REQUIRE(samples && out_image && out_map && out_idmap && out_minsize && scratch, "ftc_crop_batch: null pointer");
+  FTC_REQUIRE(total_boxes == 0 || (position && codelist), "ftc_crop_batch: boxes without position / codelist");
+  FTC_REQUIRE(scratch_bytes >= ftc_crop_scratch_bytes(batch, total_boxes), "ftc_crop_batch: scratch too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  uintptr_t p = ((uintptr_t)scratch + 127) & ~(uintptr_t)127;
+  BoxRec* rec = reinterpret_cast<BoxRec*>(p);
+  float* start = reinterpret_cast<float*>(p + (size_t)(total_boxes > 0 ? total_boxes : 1) * sizeof(BoxRec));
+  FTC_CHECK_CUDA(cudaMemsetAsync(rec, 0, (size_t)(total_boxes > 0 ? total_boxes : 1) * sizeof(BoxRec), s));   // boxes no sample owns: flag 0
+  crop_init_kernel<<<grid_for((long long)batch * 5 * MH * MW), kThreads, 0, s>>>(out_map, out_idmap, batch);
+  FTC_POST_LAUNCH();
+  crop_prepare_kernel<<<batch, kBoxThreads, 0, s>>>(samples, position, codelist, rec, start, out_minsize);
+  FTC_POST_LAUNCH();
+  if (total_boxes > 0) {
+    crop_label_kernel<<<total_boxes, kBoxThreads, 0, s>>>(rec, out_map, out_idmap);
+    FTC_POST_LAUNCH();
+  }
+  crop_image_kernel<<<grid_for((long long)batch * CH * CW), kThreads, 0, s>>>(samples, start, out_image, out_channels, batch);
+  FTC_POST_LAUNCH();
+  crop_maps_kernel<<<grid_for((long long)batch * MH * MW), kThreads, 0, s>>>(samples, start, out_map, batch);
+  FTC_POST_LAUNCH();
+  return 0;
+}

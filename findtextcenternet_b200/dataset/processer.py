@@ -1,0 +1,393 @@
+"""Device version of the reference's train1 input pipeline.
+
+Reference: ``dataset/processer.pyx`` (``process`` :655-673 -> ``transform_crop`` :260-454; ``random_background`` / ``random_mono`` /
+``random_single`` / ``random_double`` :675-887) and ``dataset/data_detector.py`` (``random_salt`` :17-26, ``transforms3`` :44-59).
+There every sample goes through one Python / Cython call on a DataLoader worker; here a whole batch is four kernel launches
+(``ftc_crop_batch``, csrc/data_ops.cu) and the result is born in HBM in the layout the train step reads:
+image float32 [B,3,768,768] in [0,1], labelmap float32 [B,5,192,192], idmap [B,2,192,192].
+
+Split of the work: every RANDOM DECISION stays on the host, drawn in the reference's order from the same generator the
+reference uses (libc ``rand()``; ``srand(seed)`` therefore reproduces the reference's augmentation stream draw for draw), a few
+dozen scalars per sample; every PIXEL is computed on the device.  The same parameters give the reference's arrays bit for bit
+(tests/test_gpu_dataset.py, tests/test_emu_kernels.py).  ``random_distortion`` (data_detector.py:28-42: additive noise, Gaussian
+blur / unsharp mask from numpy's generator) is not part of this module.
+
+No CPU fallback: without the CUDA library / a CUDA device the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import ctypes.util
+import math
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+F = np.float32
+WIDTH, HEIGHT, SCALE = 768, 768, 4
+RAND_MAX = 2147483647
+
+
+# cosf / sinf / logf of the C library, the calls the reference's parameter stage makes (float results are not correctly rounded:
+# going through float64 would differ by an ulp now and then, and an ulp in the affine matrix moves every pixel)
+_libm = C.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+for _n in ("cosf", "sinf", "logf"):
+    getattr(_libm, _n).restype = C.c_float
+    getattr(_libm, _n).argtypes = [C.c_float]
+
+
+class CropSample(C.Structure):
+    """ftc_crop_sample of include/ftc_b200.h"""
+    _fields_ = [
+        ("image", C.c_void_p), ("textline", C.c_void_p), ("sepline", C.c_void_p), ("bgimg", C.c_void_p), ("salt", C.c_void_p),
+        ("im_h", C.c_int), ("im_w", C.c_int), ("im_h2", C.c_int), ("im_w2", C.c_int),
+        ("box_begin", C.c_int), ("box_count", C.c_int),
+        ("rot", C.c_float * 9), ("inv", C.c_float * 9), ("inv2", C.c_float * 9),
+        ("inv_i", C.c_int), ("inv_j", C.c_int), ("inv_h", C.c_int), ("inv_w", C.c_int),
+        ("cidx", C.c_int),
+        ("woffset", C.c_float), ("hoffset", C.c_float), ("startx0", C.c_float), ("starty0", C.c_float),
+        ("nearest", C.c_int), ("blank", C.c_int), ("color_mode", C.c_int),
+        ("fg1", C.c_float * 3), ("fg2", C.c_float * 3), ("bg", C.c_float * 3),
+        ("rect_top", C.c_int), ("rect_bottom", C.c_int), ("rect_left", C.c_int), ("rect_right", C.c_int),
+        ("bg_h", C.c_int), ("bg_w", C.c_int), ("bg_startx", C.c_int), ("bg_starty", C.c_int),
+        ("salt_s", C.c_int), ("salt_h", C.c_int), ("salt_w", C.c_int),
+    ]
+
+
+class LibcRand:
+    """``rand()`` of the C library -- the generator dataset/processer.pyx draws from (:22-25, seeded at import :887)."""
+
+    def __init__(self, seed: Optional[int] = None):
+        self._libc = C.CDLL(None)
+        self._libc.rand.restype = C.c_int
+        if seed is not None:
+            self._libc.srand(C.c_uint(seed))
+
+    def __call__(self) -> int:
+        return int(self._libc.rand())
+
+
+def _uniform(rand) -> np.float32:
+    return F(F(rand()) / F(RAND_MAX))
+
+
+def _gaussian(rand) -> np.float32:
+    # polar method, first variate (processer.pyx:27-38); the square root is taken in double
+    while True:
+        x1 = F(2.0 * float(_uniform(rand)) - 1.0)
+        x2 = F(2.0 * float(_uniform(rand)) - 1.0)
+        w = F(F(x1 * x1) + F(x2 * x2))
+        if w < F(1.0):
+            break
+    lw = float(F(_libm.logf(float(w))))
+    return F(x1 * F(math.pow((-2.0 * lw) / float(w), 0.5)))
+
+
+def _mat3(a, b):
+    out = np.zeros(9, F)
+    for j in range(3):
+        for i in range(3):
+            v = F(0)
+            for k in range(3):
+                v = F(v + F(a[j * 3 + k] * b[k * 3 + i]))
+            out[j * 3 + i] = v
+    return out
+
+
+def _affine(cx, cy, angle, size_x, size_y, sh_x, sh_y):
+    """GetMatrix (processer.pyx:88-122): shear . resize . move . rotate . move-back in float32"""
+    cx, cy = F(cx), F(cy)
+    c, s = F(_libm.cosf(float(angle))), F(_libm.sinf(float(angle)))
+    m = _mat3(np.array([1, sh_y, 0, sh_x, 1, 0, 0, 0, 1], F), np.array([size_x, 0, 0, 0, size_y, 0, 0, 0, 1], F))
+    m = _mat3(m, np.array([1, 0, cx, 0, 1, cy, 0, 0, 1], F))
+    m = _mat3(m, np.array([c, -s, 0, s, c, 0, 0, 0, 1], F))
+    return _mat3(m, np.array([1, 0, -cx, 0, 1, -cy, 0, 0, 1], F))
+
+
+def draw_crop_params(rand: Callable[[], int], im_h: int, im_w: int, im_h2: int, im_w2: int, position) -> dict:
+    """The random decisions of one transform_crop call, in the reference's order (processer.pyx:283-366, :389)."""
+    position = np.asarray(position, F).reshape(-1, 4)
+    n = position.shape[0]
+    mean_size = F(0)
+    for i in range(n):
+        mean_size = F(mean_size + max(position[i, 2], position[i, 3]))
+    mean_size = F(10) if mean_size <= 0 else F(mean_size / F(n))
+    angle = F(np.deg2rad(float(_gaussian(rand)) * 5.0))
+    size_x = F(float(_gaussian(rand)) + 1.0)
+    aspect = F(float(abs(_gaussian(rand))) + 1.0)
+    sh_x = F(float(_gaussian(rand)) * 0.01)
+    sh_y = F(float(_gaussian(rand)) * 0.01)
+    if float(size_x) < 0.8:
+        size_x = F(0.8 - float(size_x) + 0.8)
+    if float(size_x) < 1.0 and F(size_x * mean_size) < 10:
+        size_x, aspect = F(10.0 / float(mean_size)), F(1)
+    size_y = F(size_x * aspect) if float(_uniform(rand)) < 0.5 else F(size_x / aspect)
+    rot = _affine(im_w // 2, im_h // 2, angle, size_x, size_y, sh_x, sh_y)
+    rot2 = _affine(im_w2 // 2, im_h2 // 2, angle, size_x, size_y, sh_x, sh_y)
+    inv = np.linalg.inv(rot.reshape(3, 3)).astype(F).reshape(9)
+    inv2 = np.linalg.inv(rot2.reshape(3, 3)).astype(F).reshape(9)
+    h = int(F(_uniform(rand) * F(im_h - 1)))                  # inverse_partial :124-128
+    w = int(F(_uniform(rand) * F(im_w - 1)))
+    i = int(F(_uniform(rand) * F(im_h - h + 1)))
+    j = int(F(_uniform(rand) * F(im_w - w + 1)))
+    p = dict(rot=rot, inv=inv, inv2=inv2, inv_rect=(i, j, h, w), cidx=-1, woffset=F(0), hoffset=F(0), startx0=F(0), starty0=F(0))
+    if n > 0:
+        p["cidx"] = int(F(_uniform(rand) * F(n)))
+        p["woffset"] = F(float(F(_uniform(rand) * F(WIDTH))) * 0.75 + WIDTH / 8.0)
+        p["hoffset"] = F(float(F(_uniform(rand) * F(HEIGHT))) * 0.75 + HEIGHT / 8.0)
+    else:
+        p["startx0"] = F(_uniform(rand) * F(WIDTH))
+        p["starty0"] = F(_uniform(rand) * F(HEIGHT))
+    p["nearest"] = bool(float(_uniform(rand)) < 0.05)
+    return p
+
+
+def draw_process_params(rand, im_h, im_w, im_h2, im_w2, position) -> dict:
+    """process() (:655-673): 1 % of the samples are blank, the others get transform_crop parameters"""
+    if float(_uniform(rand)) < 0.01:
+        return dict(blank=True)
+    return draw_crop_params(rand, im_h, im_w, im_h2, im_w2, position)
+
+
+def _contrast(v, u):
+    """the partner colour at least 0.5 away from v (:752-757 and its per-channel copies); double expression rounded once"""
+    v, u = F(v), F(u)
+    if float(v) > 0.5:
+        return F(u * F(float(v) - 0.5))
+    return F(1.0 - float(u) * (1.0 - float(F(float(v) + 0.5))))
+
+
+def draw_mono(rand) -> dict:
+    fg = _uniform(rand)
+    bg = _contrast(fg, _uniform(rand))
+    return dict(mode=1, fg1=[fg] * 3, fg2=[fg] * 3, bg=[bg] * 3, rect=(0, 0, 0, 0))
+
+
+def draw_single(rand) -> dict:
+    fg = [_uniform(rand) for _ in range(3)]
+    bg = [_contrast(fg[c], _uniform(rand)) for c in range(3)]
+    return dict(mode=1, fg1=fg, fg2=list(fg), bg=bg, rect=(0, 0, 0, 0))
+
+
+def draw_double(rand) -> dict:
+    fg1 = [_uniform(rand) for _ in range(3)]
+    fg2 = [_uniform(rand) for _ in range(3)]
+    fg2 = [F(float(fg2[c]) * 0.5 + 0.5) if float(fg1[c]) > 0.5 else F(float(fg2[c]) * 0.5) for c in range(3)]
+    hi = [F(float(max(fg1[c], fg2[c])) + 0.5) for c in range(3)]
+    lo = [F(float(min(fg1[c], fg2[c])) - 0.5) for c in range(3)]
+    u = [_uniform(rand) for _ in range(3)]
+    bg = [F(u[c] * lo[c]) if float(fg1[c]) > 0.5 else F(1.0 - float(u[c]) * (1.0 - float(hi[c]))) for c in range(3)]
+    top = int(F(_uniform(rand) * F(HEIGHT - 1)))
+    bottom = int(F(_uniform(rand) * F(HEIGHT - top))) + top
+    left = int(F(_uniform(rand) * F(WIDTH - 1)))
+    right = int(F(_uniform(rand) * F(WIDTH - left))) + left
+    return dict(mode=1, fg1=fg1, fg2=fg2, bg=bg, rect=(top, bottom, left, right))
+
+
+def draw_background(rand, bgimg: np.ndarray) -> dict:
+    """random_background (:675-731): crop origin, then one foreground colour per channel contrasting with the crop's mean"""
+    bh, bw = bgimg.shape[:2]
+    sx = int(F(_uniform(rand) * F(bw - WIDTH))) if bw > WIDTH else 0
+    sy = int(F(_uniform(rand) * F(bh - HEIGHT))) if bh > HEIGHT else 0
+    crop = np.zeros((3, HEIGHT, WIDTH), F)
+    ye, xe = min(HEIGHT, bh - sy), min(WIDTH, bw - sx)
+    crop[:, :ye, :xe] = (bgimg[sy:sy + ye, sx:sx + xe, :3].astype(F) / F(255)).transpose(2, 0, 1)
+    fg = []
+    for c in range(3):
+        m = F(np.mean(crop[c]))
+        u = _uniform(rand)
+        fg.append(F(u * F(float(m) - 0.5)) if float(m) > 0.5 else F(1.0 - float(u) * (1.0 - float(F(float(m) + 0.5)))))
+    return dict(mode=2, fg1=fg, fg2=list(fg), bg=[F(0)] * 3, rect=(0, 0, 0, 0), bg_start=(sx, sy))
+
+
+def draw_salt(rng: np.random.Generator, minsize: float, prob: float):
+    """random_salt (data_detector.py:17-26) as a cell grid: (cell size, uint8 cells with 0 -> ink 0, 1 -> keep, 2 -> ink 1)"""
+    s = min(max(1, int(minsize / 4)), int(rng.integers(1, 16)))
+    shape = ((HEIGHT + s) // s, (WIDTH + s) // s)
+    cells = rng.choice(np.array([0, 1, 2], np.uint8), p=[prob / 2, 1 - prob, prob / 2], size=shape).astype(np.uint8)
+    return s, cells
+
+
+def fill_descriptor(d: CropSample, ptrs: dict, shapes: dict, box_begin: int, box_count: int, p: dict, color: Optional[dict] = None,
+                    salt: Optional[tuple] = None) -> None:
+    """ptrs: addresses of image / textline / sepline (/ bgimg / salt cells); shapes: their (h, w)"""
+    d.image, d.textline, d.sepline = ptrs["image"], ptrs["textline"], ptrs["sepline"]
+    d.im_h, d.im_w = shapes["image"]
+    d.im_h2, d.im_w2 = shapes["textline"]
+    d.box_begin, d.box_count = box_begin, box_count
+    d.blank = 1 if p.get("blank") else 0
+    if not d.blank:
+        for k in ("rot", "inv", "inv2"):
+            getattr(d, k)[:] = [float(v) for v in p[k]]
+        d.inv_i, d.inv_j, d.inv_h, d.inv_w = p["inv_rect"]
+        d.cidx = max(int(p["cidx"]), 0)
+        d.woffset, d.hoffset, d.startx0, d.starty0 = float(p["woffset"]), float(p["hoffset"]), float(p["startx0"]), float(p["starty0"])
+        d.nearest = 1 if p["nearest"] else 0
+    d.color_mode = 0
+    d.bgimg = None
+    if color is not None:
+        d.color_mode = color["mode"]
+        d.fg1[:] = [float(v) for v in color["fg1"]]
+        d.fg2[:] = [float(v) for v in color["fg2"]]
+        d.bg[:] = [float(v) for v in color["bg"]]
+        d.rect_top, d.rect_bottom, d.rect_left, d.rect_right = color["rect"]
+        if color["mode"] == 2:
+            d.bgimg = ptrs["bgimg"]
+            d.bg_h, d.bg_w = shapes["bgimg"]
+            d.bg_startx, d.bg_starty = color["bg_start"]
+    d.salt = None
+    if salt is not None:
+        d.salt = ptrs["salt"]
+        d.salt_s = int(salt[0])
+        d.salt_h, d.salt_w = shapes["salt"]
+
+
+class GpuProcesser:
+    """Batch version of ``dataset.map(process).map(transforms3)`` (dataset/data_detector.py:96-97).
+
+    samples: sequence of (image uint8 [H,W], textline uint8 [H/2,W/2], sepline uint8 [H/2,W/2], position float32 [n,4],
+    codelist int32 [n,2]) exactly as the reference's WebDataset decoder yields them (numpy, host).  ``__call__`` returns device
+    tensors (image [B,3,768,768] float32, labelmap [B,5,192,192] float32, idmap [B,2,192,192] int64, minsize [B] float32)."""
+
+    def __init__(self, device="cuda", rand: Optional[Callable[[], int]] = None, rng: Optional[np.random.Generator] = None,
+                 backgrounds: Sequence[np.ndarray] = ()):
+        import torch
+        from .. import _lib
+        self.torch, self.lib = torch, _lib.load()
+        self._check = _lib.check
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GpuProcesser runs on a CUDA device only (no CPU fallback)")
+        self.rand = rand if rand is not None else LibcRand()
+        self.rng = rng if rng is not None else np.random.default_rng()
+        self.backgrounds = list(backgrounds)
+
+    # -- parameter drawing: the reference's control flow (process :655-673, transforms3 :44-59) --
+    def draw(self, sample) -> tuple:
+        image, textline, sepline, position, codelist = sample
+        p = draw_process_params(self.rand, image.shape[0], image.shape[1], textline.shape[0], textline.shape[1], position)
+        return p
+
+    def draw_color(self, minsize: float):
+        """transforms3 (:44-59): optional salt, then background photograph / mono / single / double colouring"""
+        rng = self.rng
+        salt = None
+        if rng.random() < 0.2:
+            salt = draw_salt(rng, minsize, 0.2 * rng.random())
+        bgimg = None
+        if rng.random() < 0.3 and self.backgrounds:
+            bgimg = self.backgrounds[int(rng.integers(len(self.backgrounds)))]
+            color = draw_background(self.rand, bgimg)
+        elif rng.random() < 0.5:
+            color = draw_mono(self.rand)
+        elif rng.random() < 0.5:
+            color = draw_single(self.rand)
+        else:
+            color = draw_double(self.rand)
+        return color, salt, bgimg
+
+    def stage(self, samples, params, colors=None, salts=None, bgimgs=None) -> dict:
+        """Host -> device: pages, masks, boxes and the descriptor table of one batch (pinned staging, asynchronous copies)."""
+        torch = self.torch
+        B = len(samples)
+        dev = self.device
+
+        def up(a, dtype):
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype))
+            return t.pin_memory().to(dev, non_blocking=True) if t.numel() else torch.empty(0, dtype=t.dtype, device=dev)
+
+        keep, desc = [], (CropSample * B)()
+        counts = [int(np.asarray(s[3]).reshape(-1, 4).shape[0]) for s in samples]
+        total = int(sum(counts))
+        pos = up(np.concatenate([np.asarray(s[3], F).reshape(-1, 4) for s in samples]) if total else np.zeros((0, 4), F), F)
+        code = up(np.concatenate([np.asarray(s[4], np.int32).reshape(-1, 2) for s in samples]) if total else np.zeros((0, 2), np.int32), np.int32)
+        begin, h2d = 0, 0
+        for b, s in enumerate(samples):
+            t = {"image": up(s[0], np.uint8), "textline": up(s[1], np.uint8), "sepline": up(s[2], np.uint8)}
+            shapes = {"image": s[0].shape[:2], "textline": s[1].shape[:2]}
+            color = colors[b] if colors is not None else None
+            salt = salts[b] if salts is not None else None
+            if color is not None and color["mode"] == 2:
+                t["bgimg"] = up(bgimgs[b][:, :, :3], np.uint8)
+                shapes["bgimg"] = bgimgs[b].shape[:2]
+            if salt is not None:
+                t["salt"] = up(salt[1], np.uint8)
+                shapes["salt"] = salt[1].shape
+            keep.append(t)
+            h2d += sum(v.numel() for v in t.values())
+            fill_descriptor(desc[b], {k: v.data_ptr() for k, v in t.items()}, shapes, begin, counts[b], params[b], color, salt)
+            begin += counts[b]
+        desc_dev = up(np.frombuffer(bytes(desc), np.uint8), np.uint8)
+        nbytes = int(self.lib.ftc_crop_scratch_bytes(B, total))
+        return dict(batch=B, total=total, desc=desc_dev, pos=pos, code=code, keep=keep, channels=1 if colors is None else 3,
+                    scratch=torch.empty(nbytes, dtype=torch.uint8, device=dev), scratch_bytes=nbytes,
+                    h2d_bytes=h2d + pos.numel() * 4 + code.numel() * 4 + desc_dev.numel())
+
+    def launch(self, st: dict, stream=None, out=None):
+        """ftc_crop_batch on a staged batch: four kernel launches, outputs born on the device."""
+        torch, dev, B = self.torch, self.device, st["batch"]
+        if out is None:
+            out = (torch.empty(B, st["channels"], HEIGHT, WIDTH, dtype=torch.float32, device=dev),
+                   torch.empty(B, 5, HEIGHT // SCALE, WIDTH // SCALE, dtype=torch.float32, device=dev),
+                   torch.empty(B, 2, HEIGHT // SCALE, WIDTH // SCALE, dtype=torch.int32, device=dev),
+                   torch.empty(B, dtype=torch.float32, device=dev))
+        image, labelmap, idmap, minsize = out
+        cs = stream if stream is not None else torch.cuda.current_stream(dev)
+        total = st["total"]
+        self._check(self.lib.ftc_crop_batch(st["desc"].data_ptr(), B, st["pos"].data_ptr() if total else None,
+                                            st["code"].data_ptr() if total else None, total, image.data_ptr(), st["channels"],
+                                            labelmap.data_ptr(), idmap.data_ptr(), minsize.data_ptr(), st["scratch"].data_ptr(),
+                                            st["scratch_bytes"], cs.cuda_stream), "ftc_crop_batch")
+        return image, labelmap, idmap, minsize
+
+    def run(self, samples, params, colors=None, salts=None, bgimgs=None, stream=None):
+        """stage + launch with explicit parameters (what the parity tests drive).  colors None -> gray [B,1,768,768]."""
+        st = self.stage(samples, params, colors, salts, bgimgs)
+        out = self.launch(st, stream)
+        cs = stream if stream is not None else self.torch.cuda.current_stream(self.device)
+        for t in st["keep"]:                # the launches read these buffers on `cs`
+            for v in t.values():
+                v.record_stream(cs)
+        for v in (st["pos"], st["code"], st["desc"], st["scratch"]):
+            v.record_stream(cs)
+        return out
+
+    def __call__(self, samples):
+        """process + transforms3 for a batch: parameters drawn per sample in order, pixels on the device.  The colour stage needs
+        minsize (salt cell size) only when salt is drawn; it is recomputed on the host from the rotated boxes in that case."""
+        params = [self.draw(s) for s in samples]
+        colors, salts, bgs = [], [], []
+        for s, p in zip(samples, params):
+            c, salt, bg = self.draw_color(host_minsize(s[3], p))
+            colors.append(c); salts.append(salt); bgs.append(bg)
+        image, labelmap, idmap, minsize = self.run(samples, params, colors, salts, bgs)
+        return image, labelmap, idmap.long(), minsize
+
+
+def host_minsize(position, p) -> float:
+    """minsize of transform_crop (:371-385) from the parameters alone (a few hundred boxes: host arithmetic)"""
+    if p.get("blank"):
+        return 0.0
+    pos = np.asarray(position, F).reshape(-1, 4)
+    if pos.shape[0] == 0:
+        return 0.0
+    a = p["rot"]
+
+    def vd(x, y):
+        rx = ((a[0] * x).astype(F) + (a[1] * y).astype(F)).astype(F) + a[2]
+        ry = ((a[3] * x).astype(F) + (a[4] * y).astype(F)).astype(F) + a[5]
+        return rx.astype(F), ry.astype(F)
+
+    hw, hh = (pos[:, 2] / F(2)).astype(F), (pos[:, 3] / F(2)).astype(F)
+    x1, y1 = vd((pos[:, 0] - hw).astype(F), (pos[:, 1] - hh).astype(F))
+    x2, y2 = vd((pos[:, 0] + hw).astype(F), (pos[:, 1] + hh).astype(F))
+    cx, cy = ((x1 + x2).astype(F) / F(2)).astype(F), ((y1 + y2).astype(F) / F(2)).astype(F)
+    w, h = (x2 - x1).astype(F), (y2 - y1).astype(F)
+    sx, sy = F(cx[p["cidx"]] - p["woffset"]), F(cy[p["cidx"]] - p["hoffset"])
+    rx, ry = (cx - sx).astype(F), (cy - sy).astype(F)
+    m = 0.0
+    for k in range(pos.shape[0]):
+        if 0 < rx[k] < WIDTH and 0 < ry[k] < HEIGHT:
+            v = float(max(w[k], h[k]))
+            m = v if m <= 0 else min(m, v)
+    return m

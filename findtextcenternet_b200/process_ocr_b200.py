@@ -190,8 +190,21 @@ class OCR_b200_Processer(_Base):
         in numpy; here the page goes to the device ONCE as uint8, tiles are cut there and run in batches, and peak decode, page
         maps, histogram scores, greedy selection, separator veto and code maximum are kernels (ftc_peak_decode, ftc_page_maps,
         ftc_box_hists, ftc_select_boxes).  Host work left: the median of the histogram scores (np.median, a few KB)."""
+        import time
+        prof = getattr(self, "profile", False)      # profile=True: synchronised wall-clock split in self.last_split (tools/bench_page.py)
+        split, t_last = {}, time.perf_counter()
+
+        def mark(name):
+            nonlocal t_last
+            if prof:
+                torch.cuda.synchronize(self.device)
+                now = time.perf_counter()
+                split[name] = split.get(name, 0.0) + 1e3 * (now - t_last)
+                t_last = now
+
         page_h, page_w = int(org_img.shape[0]), int(org_img.shape[1])
         page_u8 = torch.from_numpy(np.ascontiguousarray(org_img).astype(np.uint8)).to(self.device, non_blocking=True)
+        mark("page_to_uint8_h2d")
         offsets = [(int(d["offsetx"]), int(d["offsety"])) for d in ds]
         eng = self.detector.detector.engine(self.device)
         maps = torch.zeros(7, page_h // arch.SCALE, page_w // arch.SCALE, dtype=torch.float32, device=self.device)
@@ -201,26 +214,36 @@ class OCR_b200_Processer(_Base):
                 offs = offsets[i:i + tile_batch]
                 tiles = torch.stack([page_u8[y:y + arch.HEIGHT, x:x + arch.WIDTH] for x, y in offs]).float()
                 meta = torch.tensor([tile_meta(x, y, page_w, page_h, self.step_ratio) for x, y in offs], dtype=torch.int32).to(self.device)
+                mark("cut_tiles")
                 heat9, feat, _ = eng.forward(tiles, False, nhwc255=True)
+                mark("detector")
                 count, loc, gfeat, total = peak_decode(heat9, feat, meta, page_w, page_h, self.cut_off, max_peaks)
                 page_maps(heat9, meta, page_h, page_w, out=maps)
+                mark("peak_decode_page_maps")
                 if bool((total > max_peaks).any()):
                     raise OverflowError(f"run_detector: a tile has {int(total.max())} peaks, more than max_peaks={max_peaks}")
                 valid = torch.arange(max_peaks, device=self.device)[None, :] < count[:, None]      # tile-major, score order inside
                 locs.append(loc[valid])
                 feats.append(gfeat[valid])
+                mark("compact")
             cand_loc = torch.cat(locs) if locs else torch.zeros(0, 9, device=self.device)
             cand_gf = torch.cat(feats) if feats else torch.zeros(0, arch.FEATURE_DIM, device=self.device)
             hists = box_hists(page_u8, cand_loc)
+            mark("box_hists")
             loose = hists[0].cpu().numpy()
             with np.errstate(all="ignore"):
                 import warnings
                 with warnings.catch_warnings():
                     warnings.simplefilter("ignore")
                     th = float(np.median(loose) / 5) if loose.size else float("nan")      # process_ocr_base.py:557
+            mark("median")
             out_loc, out_gf, _ = select_boxes(cand_loc, cand_gf, hists[1], th, maps)
+            mark("select_boxes")
         self.last_candidates = int(cand_loc.shape[0])
-        return out_loc.cpu().numpy(), out_gf.cpu().numpy(), maps[1].cpu().numpy(), maps[2].cpu().numpy()
+        res = out_loc.cpu().numpy(), out_gf.cpu().numpy(), maps[1].cpu().numpy(), maps[2].cpu().numpy()
+        mark("d2h")
+        self.last_split = split
+        return res
 
     def call_transformer_batch(self, encoder_inputs):
         """All feature chunks of a page (or of many pages) in ONE predictor call: float32 [N, max_encoderlen, 106] ->

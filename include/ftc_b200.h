@@ -344,6 +344,47 @@ int ftc_select_boxes(const float* loc, const float* gfeat, int feat_ch, const in
                      const float* seps_all, const float* code_all, int h4, int w4, int scale, int* n_out, int* sel_idx, float* out_loc,
                      float* out_gf, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- train1 input pipeline on the device: the reference's per-sample Cython routine
+ * dataset/processer.pyx::transform_crop (:260-454: inverse_partial :124-135, position rotation :345-355, center_map :137-163,
+ * box_map :165-186, id_map :188-206, nearest / bilinear affine crop :387-409, textline / separator map crop :411-425), the blank
+ * sample of process() (:662-666), random_salt of dataset/data_detector.py:17-26 and the colour compositing of
+ * random_mono / random_single / random_double / random_background (:675-887), for a whole batch in four launches.
+ * Every random decision is an INPUT (the host draws them in the reference's order, findtextcenternet_b200/dataset/processer.py),
+ * so the same parameters give the reference's arrays: images, textline / separator maps, id maps and minsize bit for bit
+ * (float32 operations rounded one by one, the double-promoted sub-expressions of the generated C evaluated in double),
+ * the Gaussian centre map and the log-size maps to 1 ulp of libm's expf / logf.
+ * ftc_crop_sample lives in DEVICE memory (array of `batch`); its pointers are device pointers. */
+typedef struct {
+  const unsigned char* image;     /* uint8 [im_h][im_w] page (ink high) */
+  const unsigned char* textline;  /* uint8 [im_h2][im_w2] half-resolution text-line mask */
+  const unsigned char* sepline;   /* uint8 [im_h2][im_w2] half-resolution separator mask */
+  const unsigned char* bgimg;     /* color_mode 2: uint8 [bg_h][bg_w][3] background photograph */
+  const unsigned char* salt;      /* optional uint8 [salt_h][salt_w] noise cells: 0 -> ink 0, 1 -> keep, 2 -> ink 1 (NaN cell) */
+  int im_h, im_w, im_h2, im_w2;
+  int box_begin, box_count;       /* this sample's rows of position / codelist */
+  float rot[9];                   /* GetMatrix of the page (:308): rotates the box corners */
+  float inv[9], inv2[9];          /* inverse affine of the page / of the half-resolution masks (:314-326) */
+  int inv_i, inv_j, inv_h, inv_w; /* inverse_partial rectangle: rows [i, i + h), columns [j, j + w) are inverted */
+  int cidx;                       /* box whose rotated centre anchors the crop (:359-364); box_count == 0: startx0 / starty0 */
+  float woffset, hoffset, startx0, starty0;
+  int nearest;                    /* 1: nearest-neighbour crop (:390-394) */
+  int blank;                      /* 1: process()'s all-zero sample */
+  int color_mode;                 /* 0: gray output [768][768]; 1: fg1 / fg2 (inside rect) over bg; 2: fg1 over the bgimg crop, clamped */
+  float fg1[3], fg2[3], bg[3];
+  int rect_top, rect_bottom, rect_left, rect_right;   /* random_double's inner rectangle (exclusive bounds); empty otherwise */
+  int bg_h, bg_w, bg_startx, bg_starty;
+  int salt_s, salt_h, salt_w;     /* cell size in pixels and grid shape */
+} ftc_crop_sample;
+
+int ftc_crop_sample_bytes(void);   /* sizeof(ftc_crop_sample): binding check */
+size_t ftc_crop_scratch_bytes(int batch, int total_boxes);
+/* position fp32 [total_boxes][4] (cx, cy, w, h in page pixels), codelist int32 [total_boxes][2]; out_image fp32
+ * [batch][out_channels][768][768] (out_channels 1: every sample color_mode 0; 3: every sample color_mode 1 / 2), out_map fp32
+ * [batch][5][192][192] (centre, log w, log h, textline, separator), out_idmap int32 [batch][2][192][192], out_minsize fp32 [batch]. */
+int ftc_crop_batch(const ftc_crop_sample* samples, int batch, const float* position, const int* codelist, int total_boxes,
+                   float* out_image, int out_channels, float* out_map, int* out_idmap, float* out_minsize, void* scratch,
+                   size_t scratch_bytes, void* stream);
+
 /* debug / staging: route bf16 weight gradients (cin, cout multiples of 8) through the mma.sync kernel: 1 on, 0 off, -1 follow the
  * FTC_WGRAD_MMA environment variable (default; off when unset) */
 int ftc_debug_set_wgrad_mma(int on);

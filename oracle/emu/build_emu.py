@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "findtextcenternet_b200", "csrc")
 OUT = os.path.join(ROOT, "oracle", "_ref")
-SOURCES = ["train_ops.cu", "loss_ops.cu", "page_ops.cu"]
+SOURCES = ["train_ops.cu", "loss_ops.cu", "page_ops.cu", "data_ops.cu"]
 
 
 def _split_top(s):

@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE: golden vectors of the train1 input pipeline from the UNMODIFIED reference (dataset/processer.pyx compiled
+by oracle/ref_processer/build_ref.py from /root/reference).  Run in the build container:
+
+    python oracle/make_golden_processer.py        ->  tests/golden/processer_golden.npz
+
+Per case: the inputs (small synthetic page, masks, boxes, codes), the libc rand() values the reference consumed (recorded by
+replaying the same srand seed through oracle.processer_oracle, whose draw order is pinned to the reference by the equality of the
+outputs), the parameters drawn from them, and the reference's outputs: SHA-256 of the bit-exact arrays (768x768 image, textline / separator maps, id maps,
+colour images), the centre / log-size maps in full (compared to 1 ulp), minsize.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_processer"))
+import build_ref  # noqa: E402
+from oracle import processer_oracle as PO  # noqa: E402
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def make_sample(seed, n, shape=(560, 420)):
+    rng = np.random.default_rng(seed)
+    h, w = shape
+    img = np.zeros(shape, np.uint8)
+    pos = np.stack([rng.uniform(0, w, n), rng.uniform(0, h, n), rng.uniform(6, 90, n), rng.uniform(6, 90, n)], 1).astype(np.float32)
+    for cx, cy, bw, bh in pos:                                   # glyph-like dark-on-light ink blobs (ink = high values)
+        x0, x1 = int(max(cx - bw / 2, 0)), int(min(cx + bw / 2, w))
+        y0, y1 = int(max(cy - bh / 2, 0)), int(min(cy + bh / 2, h))
+        img[y0:y1, x0:x1] = rng.integers(60, 256, (max(y1 - y0, 0), max(x1 - x0, 0)), dtype=np.uint8)
+    img = np.maximum(img, (rng.random(shape) < 0.02).astype(np.uint8) * 200)
+    tl = (rng.random((h // 2, w // 2)) * 255).astype(np.uint8)
+    sp = ((rng.random((h // 2, w // 2)) < 0.1) * 255).astype(np.uint8)
+    code = np.stack([rng.integers(0x3000, 0x9FFF, n), rng.integers(0, 16, n)], 1).astype(np.int32)
+    return img, tl, sp, pos, code
+
+
+def find_seed(pred, start=0):
+    s = start
+    while True:
+        if pred(s):
+            return s
+        s += 1
+
+
+def main():
+    ref = build_ref.load()
+    out = {}
+    cases = []
+
+    def nearest_of(seed, sample):
+        p = PO.draw_crop_params(PO.LibcRand(seed), sample[0].shape[0], sample[0].shape[1], sample[1].shape[0], sample[1].shape[1], sample[3])
+        return p["nearest"]
+
+    plan = [(0, 0), (1, 4), (2, 120), (3, 400)]
+    big = make_sample(100, 60)
+    plan_seeds = [s for s, _ in plan]
+    near_seed = find_seed(lambda s: nearest_of(s, big), 10)
+    for ci, (seed, n) in enumerate(plan + [(near_seed, 60)]):
+        sample = big if n == 60 else make_sample(seed, n)
+        PO.LibcRand(seed)
+        r_img, r_map, r_idx, r_min = ref.transform_crop(*sample)
+        rec = PO.RecordingRand(PO.LibcRand(seed))
+        p = PO.draw_crop_params(rec, sample[0].shape[0], sample[0].shape[1], sample[1].shape[0], sample[1].shape[1], sample[3])
+        o = PO.transform_crop(*sample, p)
+        assert np.array_equal(o[0], r_img) and np.array_equal(o[2], r_idx) and np.array_equal(o[1][3:], r_map[3:]), seed
+        k = f"crop{ci}_"
+        for name, a in zip(("image", "textline", "sepline", "position", "codelist"), sample):
+            out[k + name] = a
+        out[k + "rand"] = np.array(rec.values, np.int64)
+        # the drawn parameters themselves (cosf / sinf / logf of another C library may differ by an ulp: the pixel tests take these)
+        for name in ("rot", "inv", "inv2"):
+            out[k + "p_" + name] = p[name]
+        out[k + "p_ints"] = np.array([*p["inv_rect"], p["cidx"], int(p["nearest"])], np.int64)
+        out[k + "p_floats"] = np.array([p["woffset"], p["hoffset"], p["startx0"], p["starty0"]], np.float32)
+        out[k + "sha_image"] = sha(r_img)
+        out[k + "sha_lines"] = sha(r_map[3:])
+        out[k + "sha_idmap"] = sha(r_idx)
+        out[k + "maps012"] = r_map[:3]
+        out[k + "minsize"] = np.float32(r_min)
+        out[k + "nearest"] = bool(p["nearest"])
+        cases.append(k)
+        print(k, "seed", seed, "boxes", n, "nearest", p["nearest"], "draws", len(rec.values), "minsize", float(r_min))
+    # process(): a seed whose first uniform is below 0.01 -> blank sample
+    blank_seed = find_seed(lambda s: float(PO.random_uniform(PO.LibcRand(s))) < 0.01, 0)
+    PO.LibcRand(blank_seed)
+    b = ref.process(make_sample(1, 4))
+    assert not b[0].any() and not b[1].any() and not b[2].any()
+    out["blank_rand"] = np.array([PO.LibcRand(blank_seed)()], np.int64)
+    # colour compositing on the alpha image of case 2
+    PO.LibcRand(2)
+    alpha = ref.transform_crop(*make_sample(2, 120))[0]
+    bgimg = (np.random.default_rng(7).random((900, 1000, 3)) * 255).astype(np.uint8)
+    small_bg = (np.random.default_rng(8).random((300, 500, 3)) * 255).astype(np.uint8)
+    out["color_bgimg_seed"] = np.array([7, 900, 1000, 8, 300, 500])
+    for name in ("mono", "single", "double"):
+        PO.LibcRand(11)
+        r = getattr(ref, "random_" + name)(alpha)
+        rec = PO.RecordingRand(PO.LibcRand(11))
+        cp = getattr(PO, "draw_" + name)(rec)
+        assert np.array_equal(PO.composite(alpha, cp), r), name
+        out[f"color_{name}_rand"] = np.array(rec.values, np.int64)
+        out[f"color_{name}_sha"] = sha(r)
+    for tag, bg in (("bg_large", bgimg), ("bg_small", small_bg)):
+        PO.LibcRand(12)
+        r = ref.random_background(alpha, bg)
+        rec = PO.RecordingRand(PO.LibcRand(12))
+        cp = PO.draw_background(rec, bg)
+        assert np.array_equal(PO.composite(alpha, cp, bg), r), tag
+        out[f"color_{tag}_rand"] = np.array(rec.values, np.int64)
+        out[f"color_{tag}_sha"] = sha(r)
+    out["cases"] = np.array(cases)
+    path = os.path.join(ROOT, "tests", "golden", "processer_golden.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path) // 1024, "KB")
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pages", type=int, default=5)
     ap.add_argument("--chunks", type=int, default=32, help="transformer feature chunks decoded per page")
+    ap.add_argument("--split", action="store_true", help="also report the synchronised per-stage split of run_detector (one extra page)")
     args = ap.parse_args()
     from findtextcenternet_b200 import _lib, arch, synthetic
     from findtextcenternet_b200.process_ocr_b200 import OCR_b200_Processer
@@ -73,13 +74,20 @@ def main():
         n_boxes += loc.shape[0]
         n_cand += proc.last_candidates
     total = t_prep + t_det + t_tf
+    split = None
+    if args.split:
+        proc.profile = True
+        im, ds = tiles_of(pages[0])
+        proc.run_detector(ds, im)
+        split = {k: round(v, 3) for k, v in proc.last_split.items()}
+        proc.profile = False
     print(json.dumps({"metric": "2048x2048 pages/sec end to end (16 tiles: detector + peak decode + page maps + histogram scores + greedy "
                                 "box selection on the device, then batched transformer decode)",
                       "value": args.pages / total, "unit": "pages/s", "n_gpus": 1, "pages": args.pages,
                       "ms_per_page": 1e3 * total / args.pages, "host_page_prep_ms": 1e3 * t_prep / args.pages,
                       "run_detector_ms": 1e3 * t_det / args.pages, "transformer_ms": 1e3 * t_tf / args.pages,
                       "chunks_per_page": args.chunks, "candidates_per_page": n_cand / args.pages, "boxes_per_page": n_boxes / args.pages,
-                      "gpu_launches": int(_lib.launch_count() - l0), "data": "synthetic",
+                      "gpu_launches": int(_lib.launch_count() - l0), "data": "synthetic", "run_detector_split_ms": split,
                       "h2d_bytes_per_page": int(pages[0].shape[0] + 100) ** 2 * 3,
                       "note": "run_detector = OCR_b200_Processer.run_detector (drop-in for process_ocr_base.py:474-650): uint8 page H2D, tiles "
                               "cut on the device, imageHist + greedy selection included; linedetect (reference C++ host tool) and the "
