@@ -339,6 +339,241 @@ __global__ void __launch_bounds__(256, U >= 4 ? 2 : (U == 2 ? 3 : 3)) bn_act_bwd
   }
 }
 
+// ---- stream versions of the three BatchNorm kernels for bf16 storage (the train step's configuration) -------------------------
+// What the one-row-at-a-time kernels above lost, measured (tools/bench_bn.py, ncu r2g): (1) one or two 16-byte loads in flight per
+// thread = ~10 KB per SM, against the ~40 KB Little's law asks of a 6.5 TB/s memory system; (2) the activation selected at run time
+// and written with IEEE divisions / erff: ~5 000 SASS lines of slow paths, issue slots 45 % busy; (3) a 32-load + 8-rsqrt prologue
+// per thread for eight rows of work; (4) row-major grids whose resident CTAs all read the same 128-byte column stripe (one 128 B
+// burst per DRAM page).  Here: activation and residual are template parameters with the 1-SFU forms of the inference epilogues
+// (tanh.approx), four row groups (4 x 16 B, twice that with dy / residual) in flight per thread, the channel slab is the FASTEST grid
+// dimension (resident CTAs sweep whole rows), each CTA walks many row tiles, vector-loaded constants.  CK = 16-byte chunk lanes per
+// row: 8 (64-channel slabs) or 4 (C = 32, 96: no idle lanes).
+__device__ __forceinline__ float tanh_fast(float x) {
+#ifdef FTC_EMU
+  return tanhf(x);
+#else
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+#endif
+}
+template <int ACT> __device__ __forceinline__ float act_fwd_fast(float z) {
+  if (ACT == ACT_SILU) { const float h = 0.5f * z; return fmaf(h, tanh_fast(h), h); }                // z * sigmoid(z)
+  if (ACT == ACT_GELU) {                                                                             // erf form to 2.5e-5
+    const float z2 = fminf(z * z, 64.f);
+    const float u = z * fmaf(z2, fmaf(z2, -3.51516792e-04f, 3.70056461e-02f), 7.97507884e-01f);
+    const float h = 0.5f * z;
+    return fmaf(h, tanh_fast(u), h);
+  }
+  return z;
+}
+template <int ACT> __device__ __forceinline__ float act_grad_fast_t(float z) {
+  if (ACT == ACT_SILU) {
+    const float s = fmaf(0.5f, tanh_fast(0.5f * z), 0.5f);
+    return s * fmaf(z, 1.f - s, 1.f);
+  }
+  if (ACT == ACT_GELU) {
+    const float z2 = fminf(z * z, 64.f);
+    const float u = z * fmaf(z2, fmaf(z2, -3.51516792e-04f, 3.70056461e-02f), 7.97507884e-01f);
+    const float cdf = fmaf(0.5f, tanh_fast(u), 0.5f);
+#ifdef FTC_EMU
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * z2);
+#else
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * z2);
+#endif
+    return fmaf(z, pdf, cdf);
+  }
+  return 1.f;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+  v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xFFFF0000u);
+  v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xFFFF0000u);
+}
+__device__ __forceinline__ void ldf8(const float* __restrict__ p, float (&v)[8]) { load8(p, v); }
+
+constexpr int BS_U = 4;      // row groups in flight per thread
+
+template <int ACT, bool RES, int CK>
+__global__ void __launch_bounds__(256) bn_apply_stream_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t rows, int C, BnArgs bn,
+                                                              const bf16* __restrict__ residual) {
+  constexpr int RL = 256 / CK;
+  const int ck = threadIdx.x % CK, rl = threadIdx.x / CK;
+  const int c0 = (blockIdx.x * CK + ck) * 8;
+  if (c0 >= C) return;
+  float sc[8], sh[8];
+  {
+    float m[8], v[8], g[8], b[8];
+    ldf8(bn.mean + c0, m); ldf8(bn.var + c0, v); ldf8(bn.gamma + c0, g); ldf8(bn.beta + c0, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = g[j] * rsqrtf(v[j] + bn.eps); sh[j] = fmaf(-m[j], sc[j], b[j]); }
+  }
+  const int64_t tile = (int64_t)RL * BS_U;
+  for (int64_t t0 = (int64_t)blockIdx.y * tile; t0 < rows; t0 += (int64_t)gridDim.y * tile) {
+    uint4 xv[BS_U], rv[BS_U];
+#pragma unroll
+    for (int u = 0; u < BS_U; ++u) {
+      const int64_t rr = t0 + u * RL + rl;
+      if (rr < rows) {
+        xv[u] = *reinterpret_cast<const uint4*>(x + rr * C + c0);
+        if (RES) rv[u] = *reinterpret_cast<const uint4*>(residual + rr * C + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BS_U; ++u) {
+      const int64_t rr = t0 + u * RL + rl;
+      if (rr < rows) {
+        float v[8], r[8];
+        unpack8(xv[u], v);
+        if (RES) unpack8(rv[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = act_fwd_fast<ACT>(fmaf(v[j], sc[j], sh[j]));
+          if (RES) v[j] += r[j];
+        }
+        store8(y + rr * C + c0, v);
+      }
+    }
+  }
+}
+
+// MODE 0: sum x, sum x^2;  MODE 1: sum dz, sum dz * xhat with dz = dy * act'(gamma * xhat + beta).  part[q][blockIdx.y][C]
+template <int MODE, int ACT, int CK>
+__global__ void __launch_bounds__(256) bn_reduce_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, int64_t rows, int C,
+                                                               float* __restrict__ part, BnArgs bn) {
+  constexpr int RL = 256 / CK;
+  __shared__ float sm[2][RL][CK * 8 + 1];
+  const int ck = threadIdx.x % CK, rl = threadIdx.x / CK;
+  const int c0 = (blockIdx.x * CK + ck) * 8;
+  const bool live = c0 < C;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
+  if (live) {
+    float a[8], b[8], g[8], bt[8];
+    if (MODE == 1) {
+      float m[8], v[8];
+      ldf8(bn.mean + c0, m); ldf8(bn.var + c0, v); ldf8(bn.gamma + c0, g); ldf8(bn.beta + c0, bt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] = rsqrtf(v[j] + bn.eps); b[j] = -m[j] * a[j]; }
+    }
+    const int64_t tile = (int64_t)RL * BS_U;
+    for (int64_t t0 = (int64_t)blockIdx.y * tile; t0 < rows; t0 += (int64_t)gridDim.y * tile) {
+      uint4 xv[BS_U], dv[BS_U];
+#pragma unroll
+      for (int u = 0; u < BS_U; ++u) {
+        const int64_t rr = t0 + u * RL + rl;
+        if (rr < rows) {
+          xv[u] = *reinterpret_cast<const uint4*>(x + rr * C + c0);
+          if (MODE == 1) dv[u] = *reinterpret_cast<const uint4*>(dy + rr * C + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BS_U; ++u) {
+        const int64_t rr = t0 + u * RL + rl;
+        if (rr < rows) {
+          float v[8], d[8];
+          unpack8(xv[u], v);
+          if (MODE == 1) unpack8(dv[u], d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (MODE == 0) {
+              s0[j] += v[j];
+              s1[j] = fmaf(v[j], v[j], s1[j]);
+            } else {
+              const float xh = fmaf(v[j], a[j], b[j]);
+              const float dz = d[j] * act_grad_fast_t<ACT>(fmaf(g[j], xh, bt[j]));
+              s0[j] += dz;
+              s1[j] = fmaf(dz, xh, s1[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sm[0][rl][ck * 8 + j] = s0[j]; sm[1][rl][ck * 8 + j] = s1[j]; }
+  __syncthreads();
+  if (threadIdx.x < 2 * CK * 8) {
+    const int q = threadIdx.x / (CK * 8), cl = threadIdx.x % (CK * 8);
+    const int c = blockIdx.x * CK * 8 + cl;
+    if (c < C) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int l = 0; l < RL; ++l) acc += sm[q][l][cl];
+      part[((int64_t)q * gridDim.y + blockIdx.y) * C + c] = acc;
+    }
+  }
+}
+
+template <int ACT, int CK>
+__global__ void __launch_bounds__(256) bn_bwd_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                                                            int64_t rows, int C, float inv_rows, BnArgs bn,
+                                                            const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat) {
+  constexpr int RL = 256 / CK;
+  const int ck = threadIdx.x % CK, rl = threadIdx.x / CK;
+  const int c0 = (blockIdx.x * CK + ck) * 8;
+  if (c0 >= C) return;
+  float a[8], b[8], g[8], bt[8], k[8], m1[8], m2[8];
+  {
+    float m[8], v[8];
+    ldf8(bn.mean + c0, m); ldf8(bn.var + c0, v); ldf8(bn.gamma + c0, g); ldf8(bn.beta + c0, bt);
+    ldf8(sum_dz + c0, m1); ldf8(sum_dz_xhat + c0, m2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = rsqrtf(v[j] + bn.eps); b[j] = -m[j] * a[j]; k[j] = g[j] * a[j];
+      m1[j] *= inv_rows; m2[j] *= inv_rows;
+    }
+  }
+  const int64_t tile = (int64_t)RL * BS_U;
+  for (int64_t t0 = (int64_t)blockIdx.y * tile; t0 < rows; t0 += (int64_t)gridDim.y * tile) {
+    uint4 xv[BS_U], dv[BS_U];
+#pragma unroll
+    for (int u = 0; u < BS_U; ++u) {
+      const int64_t rr = t0 + u * RL + rl;
+      if (rr < rows) {
+        xv[u] = *reinterpret_cast<const uint4*>(x + rr * C + c0);
+        dv[u] = *reinterpret_cast<const uint4*>(dy + rr * C + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BS_U; ++u) {
+      const int64_t rr = t0 + u * RL + rl;
+      if (rr < rows) {
+        float v[8], d[8];
+        unpack8(xv[u], v);
+        unpack8(dv[u], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(v[j], a[j], b[j]);
+          const float dz = d[j] * act_grad_fast_t<ACT>(fmaf(g[j], xh, bt[j]));
+          v[j] = k[j] * (dz - m1[j] - xh * m2[j]);
+        }
+        store8(dx + rr * C + c0, v);
+      }
+    }
+  }
+}
+
+// grid of the stream kernels: x = channel slabs (fastest: resident CTAs sweep whole rows), y = row walkers (each strides over row tiles)
+inline dim3 stream_grid(int64_t rows, int c, int ck, int64_t max_y) {
+  const int slabs = (c + ck * 8 - 1) / (ck * 8);
+  const int64_t tile = (int64_t)(256 / ck) * BS_U;
+  int64_t y = (rows + tile - 1) / tile;
+  const int64_t cap = std::max<int64_t>(1, (148 * 6 + slabs - 1) / slabs);
+  y = std::min<int64_t>(std::min<int64_t>(y, cap), std::max<int64_t>(1, max_y));
+  return dim3((unsigned)slabs, (unsigned)y);
+}
+inline int stream_ck(int c) { return (c % 64 == 0) ? 8 : 4; }
+
+#define FTC_BN_ACT_SWITCH(act, CALL)            \
+  do {                                          \
+    if ((act) == ACT_SILU) { CALL(ACT_SILU); }  \
+    else if ((act) == ACT_GELU) { CALL(ACT_GELU); } \
+    else { CALL(ACT_NONE); }                    \
+  } while (0)
+
 int ew_grid(int64_t total) { return (int)std::min<int64_t>((total + 255) / 256, 148 * 16); }
 
 // ------------------------------------------------------------------------------------------------
@@ -1395,11 +1630,12 @@ unsigned ew_rows_grid(int64_t rows, int slabs) {
   return (unsigned)(x > 0 ? x : 1);
 }
 
-// rows per loop trip of the bf16 BatchNorm kernels (FTC_BN_UNROLL = 1 | 2 | 4; measured by tools/bench_bn.py)
+// bf16 BatchNorm kernels: FTC_BN_UNROLL = 0 stream kernels (default) | 1 | 2 | 4 rows per loop trip of the earlier vector kernels
+// (kept for the A/B in tools/bench_bn.py)
 int g_bn_unroll = -1;
 int bn_unroll() {
   if (g_bn_unroll >= 0) return g_bn_unroll;
-  static const int env = [] { const char* e = getenv("FTC_BN_UNROLL"); return e ? atoi(e) : 1; }();
+  static const int env = [] { const char* e = getenv("FTC_BN_UNROLL"); return e ? atoi(e) : 0; }();   // 0 = stream kernels (default)
   return env;
 }
 
@@ -1445,6 +1681,16 @@ static int bn_stats_impl(const void* x, int dtype, int64_t rows, int c, float* m
   dim3 grid(ceil_div(c, RED_CH), nchunk);
   BnArgs bn = {};
   const bool vec = c % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (vec && dtype == DT_BF16 && c % 32 == 0 && bn_unroll() == 0) {
+    const int ck = stream_ck(c);
+    const dim3 sg = stream_grid(rows, c, ck, nchunk);
+    if (ck == 8) bn_reduce_stream_kernel<0, ACT_NONE, 8><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn);
+    else bn_reduce_stream_kernel<0, ACT_NONE, 4><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn);
+    FTC_POST_LAUNCH();
+    col_reduce_finish_kernel<0><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, (int)sg.y, c, rows, mean, var, rs);
+    FTC_POST_LAUNCH();
+    return 0;
+  }
   if (vec && dtype == DT_F32)
     col_reduce_vec_kernel<float, 0, 1><<<grid, 256, 0, s>>>(cp<float>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
   else if (vec && bn_unroll() >= 4)
@@ -1472,6 +1718,24 @@ int ftc_train_bn_act(const void* x, void* y, int dtype, int64_t rows, int c, con
   const int64_t total = rows * c;
   const bool vec = c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0;
   const dim3 vgrid(ew_rows_grid(rows, ceil_div(c, RED_CH)), ceil_div(c, RED_CH));
+  const bool par16 = ((reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var) | reinterpret_cast<uintptr_t>(gamma) |
+                       reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+  if (vec && par16 && dtype == DT_BF16 && c % 32 == 0 && bn_unroll() == 0) {
+    const int ck = stream_ck(c);
+    const dim3 sg = stream_grid(rows, c, ck, 1 << 30);
+#define BN_APPLY(A)                                                                                                                      \
+    if (ck == 8) {                                                                                                                       \
+      if (residual) bn_apply_stream_kernel<A, true, 8><<<sg, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, cp<bf16>(residual));      \
+      else bn_apply_stream_kernel<A, false, 8><<<sg, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, nullptr);                        \
+    } else {                                                                                                                             \
+      if (residual) bn_apply_stream_kernel<A, true, 4><<<sg, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, cp<bf16>(residual));      \
+      else bn_apply_stream_kernel<A, false, 4><<<sg, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, nullptr);                        \
+    }
+    FTC_BN_ACT_SWITCH(act, BN_APPLY);
+#undef BN_APPLY
+    FTC_POST_LAUNCH();
+    return 0;
+  }
   if (vec && dtype == DT_F32)
     bn_act_vec_kernel<float, 1><<<vgrid, 256, 0, s>>>(cp<float>(x), mp<float>(y), rows, c, bn, cp<float>(residual));
   else if (vec && bn_unroll() >= 4)
@@ -1500,6 +1764,29 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
   const int64_t rpc = (rows + nchunk - 1) / nchunk;
   dim3 grid(ceil_div(c, RED_CH), nchunk);
   const bool vec = c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  const bool par16 = ((reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var) | reinterpret_cast<uintptr_t>(gamma) |
+                       reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(dbeta) | reinterpret_cast<uintptr_t>(dgamma)) & 15) == 0;
+  if (vec && par16 && dtype == DT_BF16 && c % 32 == 0 && bn_unroll() == 0) {
+    const int ck = stream_ck(c);
+    const dim3 rg = stream_grid(rows, c, ck, nchunk);
+#define BN_RED(A)                                                                                                                  \
+    if (ck == 8) bn_reduce_stream_kernel<1, A, 8><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn);        \
+    else bn_reduce_stream_kernel<1, A, 4><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn);
+    FTC_BN_ACT_SWITCH(act, BN_RED);
+#undef BN_RED
+    FTC_POST_LAUNCH();
+    col_reduce_finish_kernel<1><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, (int)rg.y, c, rows, dbeta, dgamma, RunningStats{nullptr, nullptr, nullptr, 0.f});
+    FTC_POST_LAUNCH();
+    const float inv_rows_s = (float)(1.0 / (double)rows);
+    const dim3 ag = stream_grid(rows, c, ck, 1 << 30);
+#define BN_BWD(A)                                                                                                                              \
+    if (ck == 8) bn_bwd_stream_kernel<A, 8><<<ag, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows_s, bn, dbeta, dgamma);   \
+    else bn_bwd_stream_kernel<A, 4><<<ag, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows_s, bn, dbeta, dgamma);
+    FTC_BN_ACT_SWITCH(act, BN_BWD);
+#undef BN_BWD
+    FTC_POST_LAUNCH();
+    return 0;
+  }
   if (vec && dtype == DT_F32)
     col_reduce_vec_kernel<float, 1, 1><<<grid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), rows, c, rpc, (float*)scratch, bn);
   else if (vec && bn_unroll() >= 4)

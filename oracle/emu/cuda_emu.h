@@ -108,6 +108,7 @@ inline int atomicMax(int* p, int v) {
   int old = *p; if (v > old) *p = v; return old;
 }
 inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 template <typename T> inline T atomicAdd(T* p, T v) {
   std::lock_guard<std::mutex> g(emu::atomic_lock);
   T old = *p; *p = old + v; return old;

@@ -46,7 +46,9 @@ def scratch(lib, rows, c):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("rows,c,act", [(37, 5, 1), (600, 70, 2), (9, 130, 0), (50, 72, 1), (300, 200, 2), (5, 8, 0), (2, 64, 1)])
+@pytest.mark.parametrize("rows,c,act", [(37, 5, 1), (600, 70, 2), (9, 130, 0), (50, 72, 1), (300, 200, 2), (5, 8, 0), (2, 64, 1),
+                                        # bf16 with C % 32 == 0 takes the stream kernels (4 row groups in flight, 4 / 8 chunk lanes)
+                                        (300, 96, 1), (700, 128, 2), (1100, 32, 0), (513, 64, 1)])
 def test_emu_batchnorm_kernels(emu, dt, rows, c, act):
     x = (rnd(rows, c, seed=1) * 1.7 + 0.3).to(dt)
     gamma, beta, res, dy = rnd(c, seed=2), rnd(c, seed=3), rnd(rows, c, seed=4, dt=dt), rnd(rows, c, seed=5, dt=dt)
@@ -62,7 +64,11 @@ def test_emu_batchnorm_kernels(emu, dt, rows, c, act):
     ok(emu, emu.ftc_train_bn_act_bwd(P(x), P(dy), P(dx), DT[dt], C.c_int64(rows), c, P(m0), P(v0), P(gamma), P(beta), C.c_float(1e-3), act,
                                      P(dbeta), P(dgamma), P(sc), None))
     dx0, dg0, db0 = TO.bn_act_bwd(x.float(), dy.float(), m0, v0, gamma, beta, 1e-3, act)
-    assert rel_l2(dgamma, dg0) < 1e-4 and rel_l2(dbeta, db0) < 1e-4 and rel_l2(dx.float(), dx0) < max(tol, 1e-4)
+    gtol = 1e-4 if (dt == torch.float32 or c % 32) else 5e-4     # stream kernels: 1-SFU activation forms (tanh fit of erf: 2.5e-5 abs)
+    assert rel_l2(dgamma, dg0) < gtol and rel_l2(dbeta, db0) < gtol and rel_l2(dx.float(), dx0) < max(tol, 1e-4)
+    if c % 32 == 0:                                               # no-residual instantiation
+        ok(emu, emu.ftc_train_bn_act(P(x), P(y), DT[dt], C.c_int64(rows), c, P(m0), P(v0), P(gamma), P(beta), C.c_float(1e-3), act, None, None))
+        assert rel_l2(y.float(), TO.bn_act(x.float(), m0, v0, gamma, beta, 1e-3, act, None)) < tol
 
 
 @pytest.mark.parametrize("b,h,w,cin,cout,k,stride", [(2, 6, 5, 8, 16, 3, 1), (1, 7, 6, 3, 70, 3, 2), (2, 4, 4, 72, 5, 1, 1)])

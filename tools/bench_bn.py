@@ -34,7 +34,7 @@ def timed(fn, iters=5):
 
 
 rows_out = []
-for unroll in (1, 2, 4):
+for unroll in (0, 1):      # 0 = stream kernels (default), 1 = the earlier one-row-per-trip vector kernels
     os.environ["FTC_BN_UNROLL"] = str(unroll)
     lib.ftc_debug_set_bn_unroll(unroll)
     tot = {"stats": 0.0, "apply": 0.0, "bwd": 0.0}
