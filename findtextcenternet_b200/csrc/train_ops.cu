@@ -557,11 +557,11 @@ __global__ void __launch_bounds__(256) bn_bwd_stream_kernel(const bf16* __restri
 }
 
 // grid of the stream kernels: x = channel slabs (fastest: resident CTAs sweep whole rows), y = row walkers (each strides over row tiles)
-inline dim3 stream_grid(int64_t rows, int c, int ck, int64_t max_y) {
+inline dim3 stream_grid(int64_t rows, int c, int ck, int64_t max_y, int ctas_per_sm = 6) {
   const int slabs = (c + ck * 8 - 1) / (ck * 8);
   const int64_t tile = (int64_t)(256 / ck) * BS_U;
   int64_t y = (rows + tile - 1) / tile;
-  const int64_t cap = std::max<int64_t>(1, (148 * 6 + slabs - 1) / slabs);
+  const int64_t cap = std::max<int64_t>(1, (148 * ctas_per_sm + slabs - 1) / slabs);
   y = std::min<int64_t>(std::min<int64_t>(y, cap), std::max<int64_t>(1, max_y));
   return dim3((unsigned)slabs, (unsigned)y);
 }
@@ -997,6 +997,40 @@ __global__ void __launch_bounds__(256) dw_wgrad_vec_kernel(const T* __restrict__
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   if (c0 < C) {
+    if constexpr (sizeof(T) == 2) {
+      // bf16: the ten 16-byte loads of a pixel are issued together from clamped addresses (taps outside the image are masked
+      // afterwards): with the boundary tests as branches around each load the compiler kept ONE load in flight per thread and
+      // the kernel ran at 1.4 TB/s (12.9 ms of a B = 16 step, ncu r02l)
+      for (int p = p0 + pl; p < p1; p += 32) {
+        const int ox = p % Wo, q = p / Wo;
+        const int oy = q % Ho, b = q / Ho;
+        const uint4 gv = *reinterpret_cast<const uint4*>(dy + (int64_t)p * C + c0);
+        uint4 xv[9];
+        unsigned okm = 0;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int iy = oy * stride - 1 + ky;
+          const int iyc = min(max(iy, 0), H - 1);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * stride - 1 + kx;
+            const int ixc = min(max(ix, 0), W - 1);
+            xv[ky * 3 + kx] = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + iyc) * W + ixc) * C + c0);
+            okm |= (iy == iyc && ix == ixc) ? (1u << (ky * 3 + kx)) : 0u;
+          }
+        }
+        float g[8];
+        unpack8(gv, g);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          float v[8];
+          unpack8(xv[t], v);
+          const float m = (okm >> t) & 1u ? 1.f : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(g[j] * m, v[j], acc[t][j]);
+        }
+      }
+    } else {
     for (int p = p0 + pl; p < p1; p += 32) {
       const int ox = p % Wo, q = p / Wo;
       const int oy = q % Ho, b = q / Ho;
@@ -1016,6 +1050,7 @@ __global__ void __launch_bounds__(256) dw_wgrad_vec_kernel(const T* __restrict__
           for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(g[j], v[j], acc[ky * 3 + kx][j]);
         }
       }
+    }
     }
   }
   // lanes of a warp: ck = lane & 7, four pixel lanes (lane >> 3): fold them, then the eight warps through shared memory
@@ -1148,12 +1183,24 @@ __global__ void __launch_bounds__(256) spatial_sum_vec_kernel(const T* __restric
   if (c0 < C) {
     const T* xb = x + (int64_t)b * HW * C + c0;
     const T* yb = MUL ? y + (int64_t)b * HW * C + c0 : nullptr;
-    for (int p = rl; p < HW; p += 32) {
-      float v[8], w[8];
-      load8(xb + (int64_t)p * C, v);
-      if (MUL) load8(yb + (int64_t)p * C, w);
+    // four pixel groups per trip, loads first (one load in flight per thread ran at ~1.5 TB/s); summation order per lane unchanged
+    for (int p = rl; p < HW; p += 128) {
+      float v[4][8], w[4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += MUL ? v[j] * w[j] : v[j];
+      for (int u = 0; u < 4; ++u) {
+        const int pp = p + 32 * u;
+        if (pp < HW) {
+          load8(xb + (int64_t)pp * C, v[u]);
+          if (MUL) load8(yb + (int64_t)pp * C, w[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p + 32 * u < HW) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += MUL ? v[u][j] * w[u][j] : v[u][j];
+        }
+      }
     }
   }
 #pragma unroll
@@ -1173,23 +1220,35 @@ __global__ void __launch_bounds__(256) spatial_sum_vec_kernel(const T* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) scale_bc_vec_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ y, int HW,
                                                            int C, const float* __restrict__ bias_bc, float bias_mul) {
+  // grid: x = channel slab (fastest: resident CTAs sweep whole rows), y = pixel walkers, z = image; four pixel groups per trip
   const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
-  const int c0 = blockIdx.y * RED_CH + ck * 8, b = blockIdx.z;
+  const int c0 = blockIdx.x * RED_CH + ck * 8, b = blockIdx.z;
   if (c0 >= C) return;
   float sc[8], bi[8];
+  load8(s + (int64_t)b * C + c0, sc);
+  if (bias_bc) {
+    load8(bias_bc + (int64_t)b * C + c0, bi);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = s[(int64_t)b * C + c0 + j];
-    bi[j] = bias_bc ? bias_bc[(int64_t)b * C + c0 + j] * bias_mul : 0.f;
+    for (int j = 0; j < 8; ++j) bi[j] *= bias_mul;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bi[j] = 0.f;
   }
   const T* xb = x + (int64_t)b * HW * C + c0;
   T* yb = y + (int64_t)b * HW * C + c0;
-  for (int p = blockIdx.x * 32 + rl; p < HW; p += gridDim.x * 32) {
-    float v[8];
-    load8(xb + (int64_t)p * C, v);
+  for (int p = blockIdx.y * 128 + rl; p < HW; p += gridDim.y * 128) {
+    float v[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], bi[j]);
-    store8(yb + (int64_t)p * C, v);
+    for (int u = 0; u < 4; ++u)
+      if (p + 32 * u < HW) load8(xb + (int64_t)(p + 32 * u) * C, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p + 32 * u < HW) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u][j] = fmaf(v[u][j], sc[j], bi[j]);
+        store8(yb + (int64_t)(p + 32 * u) * C, v[u]);
+      }
+    }
   }
 }
 
@@ -1238,11 +1297,27 @@ __global__ void __launch_bounds__(256) se_fc_bwd1_kernel(const float* __restrict
   const int s = blockIdx.x * 32 + lane;
   const bool first = blockIdx.x == 0;              // the first s-chunk's CTA also publishes dgp (the weight kernel reads it)
   float a = 0.f;
-  for (int c = warp; c < C; c += 8) {
-    const float gt = gate[(int64_t)b * C + c];
-    const float v = dgate[(int64_t)b * C + c] * gt * (1.f - gt);
-    if (first && lane == 0) dgp[(int64_t)b * C + c] = v;
-    if (s < S) a = fmaf(w2[(int64_t)c * S + s], v, a);
+  // eight channels per trip with all loads issued first (the one-channel loop was a chain of dependent L2 round trips: 53 us per
+  // launch for a few hundred KB); the summation order per (warp, lane) is unchanged: c = warp, warp + 8, ...
+  for (int cb = warp; cb < C; cb += 64) {
+    float gt[8], dg[8], wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = cb + 8 * u;
+      const bool in = c < C;
+      gt[u] = in ? gate[(int64_t)b * C + c] : 0.f;
+      dg[u] = in ? dgate[(int64_t)b * C + c] : 0.f;
+      wv[u] = (in && s < S) ? w2[(int64_t)c * S + s] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = cb + 8 * u;
+      if (c < C) {
+        const float v = dg[u] * gt[u] * (1.f - gt[u]);
+        if (first && lane == 0) dgp[(int64_t)b * C + c] = v;
+        if (s < S) a = fmaf(wv[u], v, a);
+      }
+    }
   }
   red[warp][lane] = a;
   __syncthreads();
@@ -1683,7 +1758,7 @@ static int bn_stats_impl(const void* x, int dtype, int64_t rows, int c, float* m
   const bool vec = c % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   if (vec && dtype == DT_BF16 && c % 32 == 0 && bn_unroll() == 0) {
     const int ck = stream_ck(c);
-    const dim3 sg = stream_grid(rows, c, ck, nchunk);
+    const dim3 sg = stream_grid(rows, c, ck, nchunk, 3);   // all CTAs resident; few partial rows for the finish
     if (ck == 8) bn_reduce_stream_kernel<0, ACT_NONE, 8><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn);
     else bn_reduce_stream_kernel<0, ACT_NONE, 4><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn);
     FTC_POST_LAUNCH();
@@ -1768,7 +1843,7 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
                        reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(dbeta) | reinterpret_cast<uintptr_t>(dgamma)) & 15) == 0;
   if (vec && par16 && dtype == DT_BF16 && c % 32 == 0 && bn_unroll() == 0) {
     const int ck = stream_ck(c);
-    const dim3 rg = stream_grid(rows, c, ck, nchunk);
+    const dim3 rg = stream_grid(rows, c, ck, nchunk, 2);   // 128 registers: 2 CTAs per SM
 #define BN_RED(A)                                                                                                                  \
     if (ck == 8) bn_reduce_stream_kernel<1, A, 8><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn);        \
     else bn_reduce_stream_kernel<1, A, 4><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn);
@@ -2011,7 +2086,10 @@ int ftc_train_scale_bc(const void* x, const float* scale_bc, const float* bias_b
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t total = (int64_t)batch * hw * c;
   if (c % 8 == 0 && batch <= 65535 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
-    dim3 vgrid((unsigned)std::min(ceil_div(hw, 32), 148 * 4), ceil_div(c, RED_CH), batch);
+    // pixel walkers per (slab, image): enough CTAs to fill the machine (~6 per SM), each thread >= 4 pixels when the map allows
+    const int slabs = ceil_div(c, RED_CH);
+    const int want = std::max(1, (148 * 6 + slabs * batch - 1) / (slabs * batch));
+    dim3 vgrid(slabs, (unsigned)std::min(ceil_div(hw, 128), want), batch);
     if (dtype == DT_F32) scale_bc_vec_kernel<float><<<vgrid, 256, 0, s>>>(cp<float>(x), scale_bc, mp<float>(y), hw, c, bias_bc, bias_mul);
     else scale_bc_vec_kernel<bf16><<<vgrid, 256, 0, s>>>(cp<bf16>(x), scale_bc, mp<bf16>(y), hw, c, bias_bc, bias_mul);
     FTC_POST_LAUNCH();
