@@ -223,20 +223,37 @@ __device__ __forceinline__ void bilinear_weights(float rx, float ry, float* w11,
   *w22 = __fmul_rn(dx, dy);
 }
 
-__global__ void crop_image_kernel(const ftc_crop_sample* __restrict__ samples, const float* __restrict__ start,
-                                  float* __restrict__ out_image, int out_channels, int batch) {
+// CTA = 256 consecutive pixels of IMG_ROWS consecutive rows of one sample: the sample's parameters are read once per thread
+// (registers) and amortised over the rows; every store is a fully coalesced 1 KB run of one output plane.
+constexpr int IMG_ROWS = 8;
+__global__ void __launch_bounds__(256) crop_image_kernel(const ftc_crop_sample* __restrict__ samples, const float* __restrict__ start,
+                                                         float* __restrict__ out_image, int out_channels, int rows_per_cta) {
   const long long per = (long long)CH * CW;
-  const long long total = (long long)batch * per;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / per);
-    const int rem = (int)(i % per);
-    const int y = rem / CW, x = rem % CW;
-    const ftc_crop_sample& s = samples[b];
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= CW) return;
+  const ftc_crop_sample& s = samples[b];
+  const int blank = s.blank, nearest = s.nearest, mode = s.color_mode;
+  float inv[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) inv[i] = s.inv[i];
+  const float sx = start[b * 2], sy = start[b * 2 + 1];
+  const unsigned char* salt = s.salt;
+  const int salt_s = salt ? s.salt_s : 1, salt_w = s.salt_w;
+  float fg1[3], fg2[3], bg[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { fg1[c] = s.fg1[c]; fg2[c] = s.fg2[c]; bg[c] = s.bg[c]; }
+  const int rt = s.rect_top, rb = s.rect_bottom, rl = s.rect_left, rr = s.rect_right;
+  const unsigned char* bgimg = s.bgimg;
+  const int bg_h = s.bg_h, bg_w = s.bg_w, bg_sx = s.bg_startx, bg_sy = s.bg_starty;
+  const float fx = __fadd_rn((float)x, sx);
+  const int y0 = blockIdx.y * rows_per_cta;
+  for (int y = y0; y < y0 + rows_per_cta && y < CH; ++y) {
     float a = 0.f;
-    if (!s.blank) {
+    if (!blank) {
       float rx, ry;
-      vdot(s.inv, __fadd_rn((float)x, start[b * 2]), __fadd_rn((float)y, start[b * 2 + 1]), &rx, &ry);
-      if (s.nearest) {
+      vdot(inv, fx, __fadd_rn((float)y, sy), &rx, &ry);
+      if (nearest) {
         a = page_pixel(s, (int)__dadd_rn((double)rx, 0.5), (int)__dadd_rn((double)ry, 0.5));
       } else {
         float w11, w21, w12, w22;
@@ -248,30 +265,31 @@ __global__ void crop_image_kernel(const ftc_crop_sample* __restrict__ samples, c
         a = __fadd_rn(a, __fmul_rn(w22, page_pixel(s, ix + 1, iy + 1)));
       }
     }
-    if (s.salt != nullptr) {           // random_salt (data_detector.py:17-26): x * noise, NaN cells -> 1
-      const int c = s.salt[(size_t)(y / s.salt_s) * s.salt_w + x / s.salt_s];
+    if (salt != nullptr) {             // random_salt (data_detector.py:17-26): x * noise, NaN cells -> 1
+      const int c = salt[(size_t)(y / salt_s) * salt_w + x / salt_s];
       a = c == 0 ? 0.f : (c == 2 ? 1.f : a);
     }
-    if (out_channels == 1) { out_image[i] = a; continue; }
+    const long long rem = (long long)y * CW + x;
+    if (out_channels == 1) { out_image[(size_t)b * per + rem] = a; continue; }
     float* o = out_image + (size_t)b * 3 * per + rem;
     const double na = __dsub_rn(1.0, (double)a);
-    if (s.color_mode == 2) {           // random_background (:690-741)
-      const int yi = y + s.bg_starty, xi = x + s.bg_startx;
-      const bool in = yi >= 0 && yi < s.bg_h && xi >= 0 && xi < s.bg_w;
+    if (mode == 2) {                   // random_background (:690-741)
+      const int yi = y + bg_sy, xi = x + bg_sx;
+      const bool in = yi >= 0 && yi < bg_h && xi >= 0 && xi < bg_w;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float bgv = in ? __fdiv_rn((float)s.bgimg[((size_t)yi * s.bg_w + xi) * 3 + c], 255.f) : 0.f;
-        double v = __dadd_rn((double)__fmul_rn(a, s.fg1[c]), __dmul_rn(na, (double)bgv));
+        const float bgv = in ? __fdiv_rn((float)bgimg[((size_t)yi * bg_w + xi) * 3 + c], 255.f) : 0.f;
+        double v = __dadd_rn((double)__fmul_rn(a, fg1[c]), __dmul_rn(na, (double)bgv));
         v = v < 1.0 ? v : 1.0;         // max(0, min(1, v)) as the generated comparisons evaluate it
         v = v > 0.0 ? v : 0.0;
         o[(size_t)c * per] = (float)v;
       }
     } else {                           // random_mono / random_single / random_double (:745-887)
-      const bool inner = x > s.rect_left && x < s.rect_right && y > s.rect_top && y < s.rect_bottom;
+      const bool inner = x > rl && x < rr && y > rt && y < rb;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float fg = inner ? s.fg2[c] : s.fg1[c];
-        o[(size_t)c * per] = (float)__dadd_rn((double)__fmul_rn(a, fg), __dmul_rn(na, (double)s.bg[c]));
+        const float fg = inner ? fg2[c] : fg1[c];
+        o[(size_t)c * per] = (float)__dadd_rn((double)__fmul_rn(a, fg), __dmul_rn(na, (double)bg[c]));
       }
     }
   }
@@ -358,7 +376,15 @@ extern "C" int ftc_crop_batch(const ftc_crop_sample* samples, int batch, const f
     crop_label_kernel<<<total_boxes, kBoxThreads, 0, s>>>(rec, out_map, out_idmap);
     FTC_POST_LAUNCH();
   }
-  crop_image_kernel<<<grid_for((long long)batch * CH * CW), kThreads, 0, s>>>(samples, start, out_image, out_channels, batch);
+  {
+#ifdef FTC_EMU
+    const int tx = 32, rows = 96;      // few, fat CTAs on host threads
+#else
+    const int tx = 256, rows = IMG_ROWS;
+#endif
+    FTC_REQUIRE(batch <= 65535, "ftc_crop_batch: batch");
+    crop_image_kernel<<<dim3((CW + tx - 1) / tx, (CH + rows - 1) / rows, batch), tx, 0, s>>>(samples, start, out_image, out_channels, rows);
+  }
   FTC_POST_LAUNCH();
   crop_maps_kernel<<<grid_for((long long)batch * MH * MW), kThreads, 0, s>>>(samples, start, out_map, batch);
   FTC_POST_LAUNCH();

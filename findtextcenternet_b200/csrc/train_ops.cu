@@ -1843,7 +1843,7 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
                        reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(dbeta) | reinterpret_cast<uintptr_t>(dgamma)) & 15) == 0;
   if (vec && par16 && dtype == DT_BF16 && c % 32 == 0 && bn_unroll() == 0) {
     const int ck = stream_ck(c);
-    const dim3 rg = stream_grid(rows, c, ck, nchunk, 2);   // 128 registers: 2 CTAs per SM
+    const dim3 rg = stream_grid(rows, c, ck, nchunk, 6);   // (2 per SM measured slower: 27.5 vs 24.5 ms per step, tools/bench_bn.py)
 #define BN_RED(A)                                                                                                                  \
     if (ck == 8) bn_reduce_stream_kernel<1, A, 8><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn);        \
     else bn_reduce_stream_kernel<1, A, 4><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn);

@@ -108,9 +108,8 @@ def draw_crop_params(rand: Callable[[], int], im_h: int, im_w: int, im_h2: int, 
     """The random decisions of one transform_crop call, in the reference's order (processer.pyx:283-366, :389)."""
     position = np.asarray(position, F).reshape(-1, 4)
     n = position.shape[0]
-    mean_size = F(0)
-    for i in range(n):
-        mean_size = F(mean_size + max(position[i, 2], position[i, 3]))
+    # running float32 sum in box order (:283-289); ufunc.accumulate is strictly sequential, so the rounding sequence is the loop's
+    mean_size = F(np.add.accumulate(np.maximum(position[:, 2], position[:, 3]), dtype=F)[-1]) if n else F(0)
     mean_size = F(10) if mean_size <= 0 else F(mean_size / F(n))
     angle = F(np.deg2rad(float(_gaussian(rand)) * 5.0))
     size_x = F(float(_gaussian(rand)) + 1.0)
@@ -286,42 +285,83 @@ class GpuProcesser:
             color = draw_double(self.rand)
         return color, salt, bgimg
 
+    def _arena(self, nbytes: int):
+        """Two rotating (pinned host, device) byte arenas: one memcpy per array into pinned memory, ONE H2D copy per batch.  A set is
+        reused only after the copy that read its host half has completed (event), and device-side reuse is ordered by the stream."""
+        torch = self.torch
+        if not hasattr(self, "_arenas"):
+            self._arenas, self._turn = [None, None], 0
+        self._turn ^= 1
+        a = self._arenas[self._turn]
+        if a is None or a["host"].numel() < nbytes:
+            cap = max(nbytes, 1 << 20) * 5 // 4
+            a = {"host": torch.empty(cap, dtype=torch.uint8).pin_memory(), "dev": torch.empty(cap, dtype=torch.uint8, device=self.device),
+                 "event": None}
+            self._arenas[self._turn] = a
+        if a["event"] is not None:
+            a["event"].synchronize()
+        return a
+
     def stage(self, samples, params, colors=None, salts=None, bgimgs=None) -> dict:
-        """Host -> device: pages, masks, boxes and the descriptor table of one batch (pinned staging, asynchronous copies)."""
+        """Host -> device: pages, masks, boxes and the descriptor table of one batch through one pinned arena and ONE asynchronous
+        H2D copy (the per-array pin_memory() + copy of the first version cost more than the kernels)."""
         torch = self.torch
         B = len(samples)
-        dev = self.device
-
-        def up(a, dtype):
-            t = torch.from_numpy(np.ascontiguousarray(a, dtype))
-            return t.pin_memory().to(dev, non_blocking=True) if t.numel() else torch.empty(0, dtype=t.dtype, device=dev)
-
-        keep, desc = [], (CropSample * B)()
         counts = [int(np.asarray(s[3]).reshape(-1, 4).shape[0]) for s in samples]
         total = int(sum(counts))
-        pos = up(np.concatenate([np.asarray(s[3], F).reshape(-1, 4) for s in samples]) if total else np.zeros((0, 4), F), F)
-        code = up(np.concatenate([np.asarray(s[4], np.int32).reshape(-1, 2) for s in samples]) if total else np.zeros((0, 2), np.int32), np.int32)
-        begin, h2d = 0, 0
+        items = []                      # (key, sample index or -1, contiguous numpy array)
+
+        def add(key, b, a, dtype):
+            items.append((key, b, np.ascontiguousarray(a, dtype)))
+
+        add("pos", -1, np.concatenate([np.asarray(s[3], F).reshape(-1, 4) for s in samples]) if total else np.zeros((1, 4), F), F)
+        add("code", -1, np.concatenate([np.asarray(s[4], np.int32).reshape(-1, 2) for s in samples]) if total else np.zeros((1, 2), np.int32), np.int32)
+        shapes = []
         for b, s in enumerate(samples):
-            t = {"image": up(s[0], np.uint8), "textline": up(s[1], np.uint8), "sepline": up(s[2], np.uint8)}
-            shapes = {"image": s[0].shape[:2], "textline": s[1].shape[:2]}
+            add("image", b, s[0], np.uint8); add("textline", b, s[1], np.uint8); add("sepline", b, s[2], np.uint8)
+            sh = {"image": s[0].shape[:2], "textline": s[1].shape[:2]}
             color = colors[b] if colors is not None else None
             salt = salts[b] if salts is not None else None
             if color is not None and color["mode"] == 2:
-                t["bgimg"] = up(bgimgs[b][:, :, :3], np.uint8)
-                shapes["bgimg"] = bgimgs[b].shape[:2]
+                add("bgimg", b, bgimgs[b][:, :, :3], np.uint8)
+                sh["bgimg"] = bgimgs[b].shape[:2]
             if salt is not None:
-                t["salt"] = up(salt[1], np.uint8)
-                shapes["salt"] = salt[1].shape
-            keep.append(t)
-            h2d += sum(v.numel() for v in t.values())
-            fill_descriptor(desc[b], {k: v.data_ptr() for k, v in t.items()}, shapes, begin, counts[b], params[b], color, salt)
+                add("salt", b, salt[1], np.uint8)
+                sh["salt"] = salt[1].shape
+            shapes.append(sh)
+        offs, n = [], 0
+        for _, _, a in items:
+            offs.append(n)
+            n += (a.nbytes + 255) // 256 * 256
+        desc_off = n
+        n += (C.sizeof(CropSample) * B + 255) // 256 * 256
+        arena = self._arena(n)
+        host = arena["host"].numpy()
+        base = arena["dev"].data_ptr()
+        ptrs = [dict() for _ in range(B)]
+        glob = {}
+        for (key, b, a), o in zip(items, offs):
+            host[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+            if b < 0:
+                glob[key] = base + o
+            else:
+                ptrs[b][key] = base + o
+        desc = (CropSample * B)()
+        begin = 0
+        for b in range(B):
+            fill_descriptor(desc[b], ptrs[b], shapes[b], begin, counts[b], params[b], colors[b] if colors is not None else None,
+                            salts[b] if salts is not None else None)
             begin += counts[b]
-        desc_dev = up(np.frombuffer(bytes(desc), np.uint8), np.uint8)
+        raw = np.frombuffer(bytes(desc), np.uint8)
+        host[desc_off:desc_off + raw.size] = raw
+        cs = torch.cuda.current_stream(self.device)
+        arena["dev"][:n].copy_(arena["host"][:n], non_blocking=True)
+        arena["event"] = torch.cuda.Event()
+        arena["event"].record(cs)
         nbytes = int(self.lib.ftc_crop_scratch_bytes(B, total))
-        return dict(batch=B, total=total, desc=desc_dev, pos=pos, code=code, keep=keep, channels=1 if colors is None else 3,
-                    scratch=torch.empty(nbytes, dtype=torch.uint8, device=dev), scratch_bytes=nbytes,
-                    h2d_bytes=h2d + pos.numel() * 4 + code.numel() * 4 + desc_dev.numel())
+        return dict(batch=B, total=total, desc_ptr=base + desc_off, pos_ptr=glob["pos"], code_ptr=glob["code"], arena=arena,
+                    channels=1 if colors is None else 3, scratch=torch.empty(nbytes, dtype=torch.uint8, device=self.device),
+                    scratch_bytes=nbytes, h2d_bytes=n)
 
     def launch(self, st: dict, stream=None, out=None):
         """ftc_crop_batch on a staged batch: four kernel launches, outputs born on the device."""
@@ -334,8 +374,8 @@ class GpuProcesser:
         image, labelmap, idmap, minsize = out
         cs = stream if stream is not None else torch.cuda.current_stream(dev)
         total = st["total"]
-        self._check(self.lib.ftc_crop_batch(st["desc"].data_ptr(), B, st["pos"].data_ptr() if total else None,
-                                            st["code"].data_ptr() if total else None, total, image.data_ptr(), st["channels"],
+        self._check(self.lib.ftc_crop_batch(st["desc_ptr"], B, st["pos_ptr"] if total else None,
+                                            st["code_ptr"] if total else None, total, image.data_ptr(), st["channels"],
                                             labelmap.data_ptr(), idmap.data_ptr(), minsize.data_ptr(), st["scratch"].data_ptr(),
                                             st["scratch_bytes"], cs.cuda_stream), "ftc_crop_batch")
         return image, labelmap, idmap, minsize
@@ -343,13 +383,12 @@ class GpuProcesser:
     def run(self, samples, params, colors=None, salts=None, bgimgs=None, stream=None):
         """stage + launch with explicit parameters (what the parity tests drive).  colors None -> gray [B,1,768,768]."""
         st = self.stage(samples, params, colors, salts, bgimgs)
+        if stream is not None:              # the arena copy was enqueued on the current stream
+            stream.wait_stream(self.torch.cuda.current_stream(self.device))
         out = self.launch(st, stream)
-        cs = stream if stream is not None else self.torch.cuda.current_stream(self.device)
-        for t in st["keep"]:                # the launches read these buffers on `cs`
-            for v in t.values():
-                v.record_stream(cs)
-        for v in (st["pos"], st["code"], st["desc"], st["scratch"]):
-            v.record_stream(cs)
+        if stream is not None:
+            st["scratch"].record_stream(stream)
+            self.torch.cuda.current_stream(self.device).wait_stream(stream)   # the arena is reused in stream order
         return out
 
     def __call__(self, samples):

@@ -55,8 +55,8 @@ def main():
     for ev in prof.events():
         if ev.device_type != torch.autograd.DeviceType.CUDA:
             continue
-        name = re.sub(r"\(.*", "", ev.name).replace("void ", "")
-        name = re.sub(r"ftc::|\(anonymous namespace\)::|_GLOBAL__N__[0-9a-f_]+_cu_[0-9a-f]+::|at::native::|<unnamed>::", "", name)[:78]
+        name = re.sub(r"ftc::|\(anonymous namespace\)::|_GLOBAL__N__[0-9a-f_]+_cu_[0-9a-f]+::|at::native::|<unnamed>::", "", ev.name)
+        name = re.sub(r"\(.*", "", name).replace("void ", "")[:78]
         d = agg.setdefault(name, [0, 0.0])
         d[0] += 1
         d[1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
