@@ -131,6 +131,8 @@ SYMBOLS = {
     "ftc_crop_sample_bytes": (_i, []),
     "ftc_crop_scratch_bytes": (_sz, [_i, _i]),
     "ftc_crop_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ftc_distort_scratch_bytes": (_sz, [_i]),
+    "ftc_distort_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ftc_debug_set_wgrad_mma": (_i, [_i]),
     "ftc_debug_set_bn_unroll": (_i, [_i]),
     "ftc_debug_set_wgrad_tc": (_i, [_i]),

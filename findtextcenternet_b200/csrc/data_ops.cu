@@ -333,6 +333,95 @@ __global__ void crop_maps_kernel(const ftc_crop_sample* __restrict__ samples, co
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// random_distortion (dataset/data_detector.py:28-42)
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+constexpr long long IMG3 = 3LL * CH * CW;
+
+// im = float(double(im) + alpha * z), clipped to [0, 1]; z: given table or Philox + Box-Muller (two normals per counter pair)
+__global__ void distort_noise_kernel(float* __restrict__ image, const ftc_distort_sample* __restrict__ samples,
+                                     const double* __restrict__ noise, int batch) {
+  const long long total = (long long)batch * IMG3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / IMG3);
+    const ftc_distort_sample& s = samples[b];
+    if (!s.noise_on) continue;
+    double z;
+    if (noise != nullptr) {
+      z = noise[i];
+    } else {
+      const long long e = i - (long long)b * IMG3;
+      unsigned r[4];
+      philox4x32_10((unsigned)(e >> 1), (unsigned)((e >> 1) >> 32), (unsigned)b, 0u, (unsigned)s.noise_seed, (unsigned)(s.noise_seed >> 32), r);
+      const float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincosf(6.283185307179586f * u2, &sn, &cs);
+      z = (double)(rad * ((e & 1) ? sn : cs));
+    }
+    float v = (float)__dadd_rn((double)image[i], __dmul_rn(s.alpha, z));
+    v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+    image[i] = v;
+  }
+}
+
+// one axis of scipy.ndimage.gaussian_filter (correlate1d, symmetric kernel, mode 'reflect'): in -> out, fp32 storage, double sum
+// tmp = in[0] * w[0]; for j = R .. 1: tmp += (in[-j] + in[+j]) * w[j]
+__global__ void distort_gauss_axis_kernel(const float* __restrict__ in, float* __restrict__ out, const ftc_distort_sample* __restrict__ samples,
+                                          const double* __restrict__ weights, int axis, int batch) {
+  const long long total = (long long)batch * IMG3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / IMG3);
+    const ftc_distort_sample& s = samples[b];
+    if (s.mode == 0) continue;
+    const int e = (int)(i - (long long)b * IMG3);
+    const int c = e / (CH * CW), y = (e / CW) % CH, x = e % CW;
+    const int n = axis == 0 ? 3 : (axis == 1 ? CH : CW);
+    const int pos = axis == 0 ? c : (axis == 1 ? y : x);
+    const long long stride = axis == 0 ? (long long)CH * CW : (axis == 1 ? CW : 1);
+    const float* line = in + (i - (long long)pos * stride);
+    const double* w = weights + (size_t)b * 64;
+    double tmp = __dmul_rn((double)line[(long long)pos * stride], w[0]);
+    for (int j = s.radius; j >= 1; --j) {
+      int lo = pos - j, hi = pos + j;
+      // half-sample symmetric reflection with period 2n (lines shorter than the radius reflect repeatedly)
+      lo %= 2 * n; if (lo < 0) lo += 2 * n; if (lo >= n) lo = 2 * n - 1 - lo;
+      hi %= 2 * n; if (hi >= n) hi = 2 * n - 1 - hi;
+      tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn((double)line[(long long)lo * stride], (double)line[(long long)hi * stride]), w[j]));
+    }
+    out[i] = (float)tmp;
+  }
+}
+
+// mode 1: im = clip(blur); mode 2: im = clip(im + k * (im - blur)) in float32 (numpy: weak Python scalar, float32 arrays)
+__global__ void distort_combine_kernel(float* __restrict__ image, const float* __restrict__ blur, const ftc_distort_sample* __restrict__ samples,
+                                       int batch) {
+  const long long total = (long long)batch * IMG3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const ftc_distort_sample& s = samples[(int)(i / IMG3)];
+    if (s.mode == 0) continue;
+    float v = blur[i];
+    if (s.mode == 2) {
+      const float im = image[i];
+      v = __fadd_rn(im, __fmul_rn(s.unsharp_k, __fsub_rn(im, v)));
+    }
+    v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+    image[i] = v;
+  }
+}
+
 #ifdef FTC_EMU
 constexpr int kThreads = 32, kMaxBlocks = 4, kBoxThreads = 32;     // one OS thread per CUDA thread on the host
 #else
@@ -387,6 +476,29 @@ extern "C" int ftc_crop_batch(const ftc_crop_sample* samples, int batch, const f
   }
   FTC_POST_LAUNCH();
   crop_maps_kernel<<<grid_for((long long)batch * MH * MW), kThreads, 0, s>>>(samples, start, out_map, batch);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+extern "C" size_t ftc_distort_scratch_bytes(int batch) { return (size_t)2 * (size_t)(batch > 0 ? batch : 1) * 3 * CH * CW * sizeof(float) + 256; }
+
+extern "C" int ftc_distort_batch(float* image, int batch, const ftc_distort_sample* samples, const double* weights, const double* noise,
+                                 void* scratch, size_t scratch_bytes, void* stream) {
+  FTC_REQUIRE(image && samples && weights && scratch && batch > 0, "ftc_distort_batch: bad argument");
+  FTC_REQUIRE(scratch_bytes >= ftc_distort_scratch_bytes(batch), "ftc_distort_batch: scratch too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* t1 = reinterpret_cast<float*>(((uintptr_t)scratch + 127) & ~(uintptr_t)127);
+  float* t2 = t1 + (size_t)batch * 3 * CH * CW;
+  const int grid = grid_for((long long)batch * IMG3 / 4);
+  distort_noise_kernel<<<grid, kThreads, 0, s>>>(image, samples, noise, batch);
+  FTC_POST_LAUNCH();
+  distort_gauss_axis_kernel<<<grid, kThreads, 0, s>>>(image, t1, samples, weights, 0, batch);
+  FTC_POST_LAUNCH();
+  distort_gauss_axis_kernel<<<grid, kThreads, 0, s>>>(t1, t2, samples, weights, 1, batch);
+  FTC_POST_LAUNCH();
+  distort_gauss_axis_kernel<<<grid, kThreads, 0, s>>>(t2, t1, samples, weights, 2, batch);
+  FTC_POST_LAUNCH();
+  distort_combine_kernel<<<grid, kThreads, 0, s>>>(image, t1, samples, batch);
   FTC_POST_LAUNCH();
   return 0;
 }

@@ -9,8 +9,10 @@ image float32 [B,3,768,768] in [0,1], labelmap float32 [B,5,192,192], idmap [B,2
 Split of the work: every RANDOM DECISION stays on the host, drawn in the reference's order from the same generator the
 reference uses (libc ``rand()``; ``srand(seed)`` therefore reproduces the reference's augmentation stream draw for draw), a few
 dozen scalars per sample; every PIXEL is computed on the device.  The same parameters give the reference's arrays bit for bit
-(tests/test_gpu_dataset.py, tests/test_emu_kernels.py).  ``random_distortion`` (data_detector.py:28-42: additive noise, Gaussian
-blur / unsharp mask from numpy's generator) is not part of this module.
+(tests/test_processer.py).  ``random_distortion`` (data_detector.py:28-42) is ``ftc_distort_batch``: its decisions are drawn from the
+numpy Generator in the reference's order, blur / unsharp mask reproduce scipy's gaussian_filter (all three axes, reflect, double
+accumulation in correlate1d's order); only the NOISE FIELD differs in kind: 1.8 M normals per image come from a counter-based
+generator on the device instead of numpy's stream (same distribution, not the same numbers).
 
 No CPU fallback: without the CUDA library / a CUDA device the calls raise.
 """
@@ -52,6 +54,12 @@ class CropSample(C.Structure):
         ("bg_h", C.c_int), ("bg_w", C.c_int), ("bg_startx", C.c_int), ("bg_starty", C.c_int),
         ("salt_s", C.c_int), ("salt_h", C.c_int), ("salt_w", C.c_int),
     ]
+
+
+class DistortSample(C.Structure):
+    """ftc_distort_sample of include/ftc_b200.h"""
+    _fields_ = [("noise_on", C.c_int), ("mode", C.c_int), ("radius", C.c_int), ("pad_", C.c_int), ("alpha", C.c_double),
+                ("noise_seed", C.c_ulonglong), ("unsharp_k", C.c_float), ("pad2_", C.c_float)]
 
 
 class LibcRand:
@@ -207,6 +215,44 @@ def draw_salt(rng: np.random.Generator, minsize: float, prob: float):
     return s, cells
 
 
+def draw_distortion(rng: np.random.Generator, minsize: float) -> dict:
+    """random_distortion's decisions (data_detector.py:28-42) in its draw order; the noise field itself is generated on the device"""
+    d = dict(noise_on=False, alpha=0.0, mode=0, sigma=0.0, unsharp_k=0.0, noise_seed=0)
+    if rng.random() < 0.3:
+        d["noise_on"], d["alpha"] = True, min(0.4 * rng.random(), 20 / max(1, minsize))
+        d["noise_seed"] = int(rng.integers(0, 2 ** 63 - 1))
+    if rng.random() < 0.3:
+        d["mode"], d["sigma"] = 1, min(minsize / 8, 1.5 * rng.random())
+    elif rng.random() < 0.3:
+        d["mode"], d["sigma"], d["unsharp_k"] = 2, 5.0, 10. * rng.random()
+    return d
+
+
+def gauss_taps(sigma: float, truncate: float = 4.0):
+    """(radius, taps w[0..radius]) of scipy.ndimage.gaussian_filter1d: radius int(truncate sigma + 0.5), exp(-x^2 / 2 sigma^2) normalised
+    over the full kernel in float64 (scipy's _gaussian_kernel1d); sigma <= 1e-15 is scipy's "skip this axis" = identity."""
+    if not sigma > 1e-15:
+        return 0, np.ones(1)
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    phi = phi / phi.sum()
+    return radius, phi[radius::-1].copy()          # w[j] = tap at distance j (left half, as correlate1d indexes it)
+
+
+def fill_distort(d: DistortSample, p: dict) -> np.ndarray:
+    d.noise_on, d.mode = int(bool(p["noise_on"])), int(p["mode"])
+    d.alpha, d.noise_seed = float(p["alpha"]), int(p.get("noise_seed", 0))
+    d.unsharp_k = float(np.float32(p["unsharp_k"]))
+    radius, taps = gauss_taps(p["sigma"]) if p["mode"] else (0, np.ones(1))
+    if radius > 63:
+        raise ValueError("random_distortion: blur radius above 63 taps")
+    d.radius = radius
+    w = np.zeros(64)
+    w[:radius + 1] = taps
+    return w
+
+
 def fill_descriptor(d: CropSample, ptrs: dict, shapes: dict, box_begin: int, box_count: int, p: dict, color: Optional[dict] = None,
                     salt: Optional[tuple] = None) -> None:
     """ptrs: addresses of image / textline / sepline (/ bgimg / salt cells); shapes: their (h, w)"""
@@ -249,7 +295,7 @@ class GpuProcesser:
     tensors (image [B,3,768,768] float32, labelmap [B,5,192,192] float32, idmap [B,2,192,192] int64, minsize [B] float32)."""
 
     def __init__(self, device="cuda", rand: Optional[Callable[[], int]] = None, rng: Optional[np.random.Generator] = None,
-                 backgrounds: Sequence[np.ndarray] = ()):
+                 backgrounds: Sequence[np.ndarray] = (), distortion: bool = True):
         import torch
         from .. import _lib
         self.torch, self.lib = torch, _lib.load()
@@ -260,6 +306,7 @@ class GpuProcesser:
         self.rand = rand if rand is not None else LibcRand()
         self.rng = rng if rng is not None else np.random.default_rng()
         self.backgrounds = list(backgrounds)
+        self.distortion = distortion
 
     # -- parameter drawing: the reference's control flow (process :655-673, transforms3 :44-59) --
     def draw(self, sample) -> tuple:
@@ -391,15 +438,39 @@ class GpuProcesser:
             self.torch.cuda.current_stream(self.device).wait_stream(stream)   # the arena is reused in stream order
         return out
 
+    def distort(self, image, dparams, noise=None, stream=None):
+        """random_distortion (data_detector.py:28-42) in place on a device batch [B,3,768,768] float32 (ftc_distort_batch)."""
+        torch = self.torch
+        B = image.shape[0]
+        assert image.is_cuda and image.dtype == torch.float32 and image.is_contiguous() and tuple(image.shape[1:]) == (3, HEIGHT, WIDTH)
+        desc = (DistortSample * B)()
+        w = np.stack([fill_distort(desc[b], dparams[b]) for b in range(B)])
+        if not any(d.noise_on or d.mode for d in desc):
+            return image
+        desc_dev = torch.from_numpy(np.frombuffer(bytes(desc), np.uint8).copy()).to(self.device)
+        w_dev = torch.from_numpy(np.ascontiguousarray(w)).to(self.device)
+        nz = None if noise is None else noise.to(self.device, torch.float64).contiguous()
+        nbytes = int(self.lib.ftc_distort_scratch_bytes(B))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        cs = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self._check(self.lib.ftc_distort_batch(image.data_ptr(), B, desc_dev.data_ptr(), w_dev.data_ptr(), None if nz is None else nz.data_ptr(),
+                                               scratch.data_ptr(), nbytes, cs.cuda_stream), "ftc_distort_batch")
+        for t in (desc_dev, w_dev, scratch) + (() if nz is None else (nz,)):
+            t.record_stream(cs)
+        return image
+
     def __call__(self, samples):
         """process + transforms3 for a batch: parameters drawn per sample in order, pixels on the device.  The colour stage needs
         minsize (salt cell size) only when salt is drawn; it is recomputed on the host from the rotated boxes in that case."""
         params = [self.draw(s) for s in samples]
         colors, salts, bgs = [], [], []
-        for s, p in zip(samples, params):
-            c, salt, bg = self.draw_color(host_minsize(s[3], p))
+        host_ms = [host_minsize(s[3], p) for s, p in zip(samples, params)]
+        for m in host_ms:
+            c, salt, bg = self.draw_color(m)
             colors.append(c); salts.append(salt); bgs.append(bg)
         image, labelmap, idmap, minsize = self.run(samples, params, colors, salts, bgs)
+        if self.distortion:
+            self.distort(image, [draw_distortion(self.rng, m) for m in host_ms])
         return image, labelmap, idmap.long(), minsize
 
 

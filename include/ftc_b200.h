@@ -385,6 +385,30 @@ int ftc_crop_batch(const ftc_crop_sample* samples, int batch, const float* posit
                    float* out_image, int out_channels, float* out_map, int* out_idmap, float* out_minsize, void* scratch,
                    size_t scratch_bytes, void* stream);
 
+/* ---- random_distortion of the train1 input pipeline (dataset/data_detector.py:28-42) on the device, in place on the batch
+ * image fp32 [batch][3][768][768]: (1) additive Gaussian noise im = float(double(im) + alpha * N(0,1)), clipped to [0,1]; (2) either a
+ * Gaussian blur (scipy.ndimage.gaussian_filter semantics: the scalar sigma filters ALL THREE axes, the colour axis included, mode
+ * 'reflect', radius int(4 sigma + 0.5), each axis pass accumulated in double in correlate1d's order -- centre tap, then symmetric pairs
+ * from the outermost inwards -- and rounded to fp32 before the next axis), clipped, or (3) an unsharp mask im + k * (im - blur_5), clipped.
+ * The random decisions are inputs (ftc_distort_sample, DEVICE array of `batch`); `weights` is a device double [batch][64] table, row b
+ * = the normalised Gaussian taps w[0..radius] (w[0] = centre) the host computed as scipy does.  Noise comes from a counter-based
+ * generator (Philox4x32-10, Box-Muller) keyed by noise_seed, or -- for parity tests -- from `noise` (device double
+ * [batch][3][768][768] standard normals, may be NULL).  scratch: 2 * batch * 3 * 768 * 768 floats. */
+typedef struct {
+  int noise_on;                 /* 1: add noise */
+  int mode;                     /* 0 none, 1 blur, 2 unsharp */
+  int radius;                   /* taps each side (<= 63) */
+  int pad_;
+  double alpha;                 /* noise amplitude */
+  unsigned long long noise_seed;
+  float unsharp_k;              /* 10 * rng.random() as float32 */
+  float pad2_;
+} ftc_distort_sample;
+
+size_t ftc_distort_scratch_bytes(int batch);
+int ftc_distort_batch(float* image, int batch, const ftc_distort_sample* samples, const double* weights, const double* noise,
+                      void* scratch, size_t scratch_bytes, void* stream);
+
 /* debug / staging: route bf16 weight gradients (cin, cout multiples of 8) through the mma.sync kernel: 1 on, 0 off, -1 follow the
  * FTC_WGRAD_MMA environment variable (default; off when unset) */
 int ftc_debug_set_wgrad_mma(int on);

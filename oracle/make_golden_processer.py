@@ -49,6 +49,17 @@ def find_seed(pred, start=0):
         s += 1
 
 
+def reference_random_distortion():
+    """random_distortion of /root/reference/dataset/data_detector.py, compiled from ITS source text (the module imports webdataset)"""
+    import ast
+    from scipy.ndimage import gaussian_filter
+    src = open("/root/reference/dataset/data_detector.py").read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "random_distortion")
+    g = {"np": np, "gaussian_filter": gaussian_filter, "rng": None}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "data_detector.py", "exec"), g)
+    return g["random_distortion"]
+
+
 def main():
     ref = build_ref.load()
     out = {}
@@ -115,6 +126,27 @@ def main():
         assert np.array_equal(PO.composite(alpha, cp, bg), r), tag
         out[f"color_{tag}_rand"] = np.array(rec.values, np.int64)
         out[f"color_{tag}_sha"] = sha(r)
+    # random_distortion: the reference's own function (source extracted from dataset/data_detector.py, which cannot be imported here:
+    # webdataset is absent) executed with seeded numpy Generators; seeds chosen to cover noise / blur / unsharp
+    ref_distort = reference_random_distortion()
+    PO.LibcRand(11)
+    base = ref.random_single(alpha)
+    picked = {}
+    for seed in range(200):
+        d = PO.draw_distortion(np.random.default_rng(seed), 40.0, base.shape)
+        key = (d["noise_on"], d["mode"])
+        if key not in picked and (d["noise_on"] or d["mode"]):
+            picked[key] = seed
+        if len(picked) == 5:
+            break
+    seeds = sorted(picked.values())
+    for seed in seeds:
+        ref_distort.__globals__["rng"] = np.random.default_rng(seed)
+        r = ref_distort(base.copy(), 40.0)
+        d = PO.draw_distortion(np.random.default_rng(seed), 40.0, base.shape)
+        assert np.array_equal(PO.random_distortion(base, d), r), seed
+        out[f"distort{seed}_sha"] = sha(r)
+    out["distort_seeds"] = np.array(seeds)
     out["cases"] = np.array(cases)
     path = os.path.join(ROOT, "tests", "golden", "processer_golden.npz")
     np.savez_compressed(path, **out)

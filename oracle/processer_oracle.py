@@ -484,3 +484,40 @@ def composite(a, cp, bgimg=None):
         v2 = blend(cp["fg2"][c], cp["bg"][c]).astype(F)
         out[c] = np.where(inner, v2, v1)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# random_distortion (dataset/data_detector.py:28-42): numpy Generator decisions, scipy.ndimage.gaussian_filter pixels
+# ---------------------------------------------------------------------------------------------------------------------
+def draw_distortion(rng, s, shape=None):
+    """The decisions of random_distortion in its draw order.  With ``shape`` the noise field is drawn from ``rng`` exactly where the
+    reference draws it (pin test: the generator streams stay aligned); without it the noise is left to the caller."""
+    d = {"noise_on": False, "alpha": 0.0, "mode": 0, "sigma": 0.0, "unsharp_k": F(0), "noise": None}
+    if rng.random() < 0.3:
+        d["noise_on"] = True
+        d["alpha"] = min(0.4 * rng.random(), 20 / max(1, s))
+        if shape is not None:
+            d["noise"] = rng.normal(size=shape)
+    if rng.random() < 0.3:
+        d["mode"], d["sigma"] = 1, min(s / 8, 1.5 * rng.random())
+    elif rng.random() < 0.3:
+        d["mode"], d["sigma"], d["unsharp_k"] = 2, 5.0, 10. * rng.random()
+    return d
+
+
+def random_distortion(im, d, noise=None):
+    """im float32 [3,768,768] -> float32 [3,768,768]; d from draw_distortion; noise: float64 standard normals (else d['noise'])"""
+    from scipy.ndimage import gaussian_filter
+    im = np.array(im, F, copy=True)
+    if d["noise_on"]:
+        z = noise if noise is not None else d["noise"]
+        im += d["alpha"] * z
+        im = np.clip(im, 0, 1)
+    if d["mode"] == 1:
+        im = gaussian_filter(im, sigma=d["sigma"])
+        im = np.clip(im, 0, 1)
+    elif d["mode"] == 2:
+        blurred = gaussian_filter(im, sigma=5.)
+        im = im + float(d["unsharp_k"]) * (im - blurred)
+        im = np.clip(im, 0, 1)
+    return im

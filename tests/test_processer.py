@@ -231,6 +231,68 @@ def test_emu_colour_salt_blank(emu):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# random_distortion (dataset/data_detector.py:28-42)
+# ---------------------------------------------------------------------------------------------------------------------
+DSEEDS = [int(v) for v in G["distort_seeds"]]
+
+
+def _distort_base():
+    return PO.composite(_alpha(), color_params("single", PO)[0])       # the image the goldens were made from (random_single, seed 11)
+
+
+@pytest.mark.parametrize("seed", DSEEDS)
+def test_oracle_distortion_matches_reference_golden(seed):
+    base = _distort_base()
+    d = PO.draw_distortion(np.random.default_rng(seed), 40.0, base.shape)
+    assert sha(PO.random_distortion(base, d)) == str(G[f"distort{seed}_sha"])
+
+
+def test_host_distortion_decisions_follow_the_reference_order():
+    for seed in range(60):          # same branch decisions / amplitudes as the oracle when no noise field is drawn in between
+        a = PO.draw_distortion(np.random.default_rng(seed), 33.0, None)
+        rng = np.random.default_rng(seed)
+        b = P.draw_distortion(rng, 33.0)
+        if a["noise_on"]:           # the product draws one integer (the device generator's seed) where the reference draws the field
+            assert b["noise_on"] and b["alpha"] == a["alpha"]
+            continue
+        assert (b["noise_on"], b["mode"], b["sigma"], float(b["unsharp_k"])) == (a["noise_on"], a["mode"], a["sigma"], float(a["unsharp_k"]))
+    from scipy.ndimage import _filters
+    for sigma in (0.3, 1.0, 1.49, 5.0):
+        r, w = P.gauss_taps(sigma)
+        full = _filters._gaussian_kernel1d(sigma, 0, r)
+        assert r == int(4.0 * sigma + 0.5) and np.array_equal(w, full[r::-1])
+
+
+def run_distort_host(lib, image, dparams, noise):
+    B = image.shape[0]
+    desc = (P.DistortSample * B)()
+    w = np.ascontiguousarray(np.stack([P.fill_distort(desc[b], dparams[b]) for b in range(B)]))
+    lib.ftc_distort_scratch_bytes.restype = C.c_size_t
+    n = lib.ftc_distort_scratch_bytes(B)
+    scratch = np.empty(n, np.uint8)
+    img = np.ascontiguousarray(image, np.float32).copy()
+    nz = None if noise is None else np.ascontiguousarray(noise, np.float64)
+    rc = lib.ftc_distort_batch(C.c_void_p(img.ctypes.data), B, C.byref(desc), C.c_void_p(w.ctypes.data),
+                               None if nz is None else C.c_void_p(nz.ctypes.data), C.c_void_p(scratch.ctypes.data), C.c_size_t(n), None)
+    assert rc == 0, lib.ftc_last_error()
+    return img
+
+
+def _distort_cases():
+    base = _distort_base()
+    ds = [PO.draw_distortion(np.random.default_rng(seed), 40.0, base.shape) for seed in DSEEDS]
+    noise = np.stack([d["noise"] if d["noise"] is not None else np.zeros(base.shape) for d in ds])
+    return base, ds, noise
+
+
+def test_emu_distortion_kernels_equal_reference_golden(emu):
+    base, ds, noise = _distort_cases()
+    out = run_distort_host(emu, np.stack([base] * len(ds)), ds, noise)
+    for b, seed in enumerate(DSEEDS):
+        assert sha(out[b]) == str(G[f"distort{seed}_sha"]), (seed, ds[b]["noise_on"], ds[b]["mode"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # GPU: the product path through the C-ABI
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
@@ -274,3 +336,23 @@ def test_gpu_processer_call_feeds_the_train_step_layout():
     assert labelmap.shape == (len(CASES), 5, 192, 192) and idmap.shape == (len(CASES), 2, 192, 192) and idmap.dtype == torch.int64
     assert float(image.min()) >= 0.0 and float(image.max()) <= 1.0 and torch.isfinite(labelmap).all()
     assert float(labelmap[:, 0].max()) <= 1.0
+
+
+@pytest.mark.gpu
+def test_gpu_distortion_equals_reference_golden_and_device_noise_is_standard_normal():
+    import torch
+    proc = P.GpuProcesser("cuda:0")
+    base, ds, noise = _distort_cases()
+    img = torch.from_numpy(np.stack([base] * len(ds))).cuda()
+    out = proc.distort(img, ds, noise=torch.from_numpy(noise)).cpu().numpy()
+    for b, seed in enumerate(DSEEDS):
+        assert sha(out[b]) == str(G[f"distort{seed}_sha"]), (seed, ds[b]["noise_on"], ds[b]["mode"])
+    # device generator: (out - in) / alpha on unclipped pixels of a mid-grey image is N(0, 1)
+    grey = torch.full((2, 3, 768, 768), 0.5, device="cuda")
+    dp = [dict(noise_on=True, alpha=0.05, mode=0, sigma=0.0, unsharp_k=0.0, noise_seed=s) for s in (123, 456)]
+    z = ((proc.distort(grey.clone(), dp) - grey) / 0.05).double()
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3
+    assert abs(float((z ** 3).mean())) < 2e-2 and abs(float((z ** 4).mean()) - 3.0) < 5e-2
+    assert float((z[0] - z[1]).abs().mean()) > 0.5                    # different seeds: different fields
+    zz = z[0].flatten()
+    assert abs(float((zz[:-1] * zz[1:]).mean())) < 5e-3               # neighbouring samples uncorrelated
