@@ -394,14 +394,55 @@ __global__ void distort_gauss_axis_kernel(const float* __restrict__ in, float* _
     const float* line = in + (i - (long long)pos * stride);
     const double* w = weights + (size_t)b * 64;
     double tmp = __dmul_rn((double)line[(long long)pos * stride], w[0]);
-    for (int j = s.radius; j >= 1; --j) {
-      int lo = pos - j, hi = pos + j;
-      // half-sample symmetric reflection with period 2n (lines shorter than the radius reflect repeatedly)
-      lo %= 2 * n; if (lo < 0) lo += 2 * n; if (lo >= n) lo = 2 * n - 1 - lo;
-      hi %= 2 * n; if (hi >= n) hi = 2 * n - 1 - hi;
-      tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn((double)line[(long long)lo * stride], (double)line[(long long)hi * stride]), w[j]));
+    const int R = s.radius;
+    if (pos - R >= 0 && pos + R < n) {             // interior: no reflection arithmetic (all but a 2R-wide frame of the image axes)
+      const float* lp = line + (long long)pos * stride;
+      for (int j = R; j >= 1; --j)
+        tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn((double)lp[-(long long)j * stride], (double)lp[(long long)j * stride]), w[j]));
+    } else {
+      for (int j = R; j >= 1; --j) {
+        int lo = pos - j, hi = pos + j;
+        // half-sample symmetric reflection with period 2n (lines shorter than the radius reflect repeatedly: the 3-element colour axis)
+        lo %= 2 * n; if (lo < 0) lo += 2 * n; if (lo >= n) lo = 2 * n - 1 - lo;
+        hi %= 2 * n; if (hi >= n) hi = 2 * n - 1 - hi;
+        tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn((double)line[(long long)lo * stride], (double)line[(long long)hi * stride]), w[j]));
+      }
     }
     out[i] = (float)tmp;
+  }
+}
+
+// axis 0 (the 3-element colour axis): thread per pixel, the three channels in registers; the reflected index of c +- j follows the
+// period-6 pattern 0 1 2 2 1 0, looked up from j mod 6 (one small modulo per tap instead of two 64-bit divisions per tap and channel)
+__global__ void distort_gauss_color_kernel(const float* __restrict__ in, float* __restrict__ out, const ftc_distort_sample* __restrict__ samples,
+                                           const double* __restrict__ weights, int batch) {
+  const long long per = (long long)CH * CW;
+  const long long total = (long long)batch * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per);
+    const ftc_distort_sample& s = samples[b];
+    if (s.mode == 0) continue;
+    const long long base = (long long)b * IMG3 + (i - (long long)b * per);
+    double v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (double)in[base + c * per];
+    const double* w = weights + (size_t)b * 64;
+    double t[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) t[c] = __dmul_rn(v[c], w[0]);
+    for (int j = s.radius; j >= 1; --j) {
+      const int m = j % 6;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        int lo = (c - m + 6) % 6, hi = (c + m) % 6;          // compile-time c: small constant arithmetic
+        lo = lo >= 3 ? 5 - lo : lo; hi = hi >= 3 ? 5 - hi : hi;
+        const double a = lo == 0 ? v[0] : (lo == 1 ? v[1] : v[2]);
+        const double d = hi == 0 ? v[0] : (hi == 1 ? v[1] : v[2]);
+        t[c] = __dadd_rn(t[c], __dmul_rn(__dadd_rn(a, d), w[j]));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[base + c * per] = (float)t[c];
   }
 }
 
@@ -492,7 +533,7 @@ extern "C" int ftc_distort_batch(float* image, int batch, const ftc_distort_samp
   const int grid = grid_for((long long)batch * IMG3 / 4);
   distort_noise_kernel<<<grid, kThreads, 0, s>>>(image, samples, noise, batch);
   FTC_POST_LAUNCH();
-  distort_gauss_axis_kernel<<<grid, kThreads, 0, s>>>(image, t1, samples, weights, 0, batch);
+  distort_gauss_color_kernel<<<grid_for((long long)batch * CH * CW / 2), kThreads, 0, s>>>(image, t1, samples, weights, batch);
   FTC_POST_LAUNCH();
   distort_gauss_axis_kernel<<<grid, kThreads, 0, s>>>(t1, t2, samples, weights, 1, batch);
   FTC_POST_LAUNCH();

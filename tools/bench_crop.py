@@ -126,7 +126,7 @@ def main():
             torch.cuda.synchronize()
         for ev in prof.events():
             if ev.device_type == torch.autograd.DeviceType.CUDA:
-                name = ev.name.split("(")[0].split("::")[-1]
+                name = ev.name.replace("(anonymous namespace)::", "").split("(")[0].split("::")[-1]
                 split[name] = round(split.get(name, 0.0) + ev.device_time_total, 1)
     except Exception as e:      # noqa: BLE001
         split = {"error": repr(e)[:100]}
@@ -140,13 +140,23 @@ def main():
         minsize.cpu()
     torch.cuda.synchronize()
     e2e = a.batch * e2e_steps / (time.perf_counter() - t0)
+    proc.distortion = False
+    proc(samples)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        image, labelmap, idmap, minsize = proc(samples)
+        minsize.cpu()
+    torch.cuda.synchronize()
+    e2e_nodist = a.batch * e2e_steps / (time.perf_counter() - t0)
     line = {"metric": "train1 input pipeline samples/sec (transform_crop + colour compositing, 768x768)", "value": value, "unit": "samples/s",
             "ms_per_batch": ms, "batch": a.batch, "boxes_per_sample": a.boxes, "steps": a.steps, "dtype": "f32", "data": "synthetic",
             "gpu_launches": launches, "kernel_split_us": split, "distort_worst_case_ms_per_batch": distort_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "bytes_per_sample": bytes_per_sample, "traffic": None},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": a.batch * 4,
-                    "api": "GpuProcesser.__call__(host numpy samples)"}}
+                    "api": "GpuProcesser.__call__(host numpy samples): process + transforms3 incl. random_distortion",
+                    "without_random_distortion": e2e_nodist}}
     if not a.no_cpu:
         line["cpu_baseline"] = cpu_reference(samples[:8])
     print(json.dumps(line), flush=True)
