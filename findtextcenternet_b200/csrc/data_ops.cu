@@ -201,12 +201,14 @@ __global__ void crop_label_kernel(const BoxRec* __restrict__ rec, float* __restr
   }
 }
 
-// getpixel (:208-211) with inverse_partial (:124-135) folded in
-__device__ __forceinline__ float page_pixel(const ftc_crop_sample& s, int x, int y) {
-  if (x < 0 || x >= s.im_w || y < 0 || y >= s.im_h) return 0.f;
+// getpixel (:208-211) with inverse_partial (:124-135) folded in.  lut[v] = v / 255 rounded to nearest (the IEEE division the
+// reference performs per fetch; as an instruction sequence it was ~60 of the kernel's ~290 instructions per pixel)
+struct PageView { const unsigned char* image; int im_h, im_w, inv_i0, inv_i1, inv_j0, inv_j1; };
+__device__ __forceinline__ float page_pixel(const PageView& s, const float* __restrict__ lut, int x, int y) {
+  if ((unsigned)x >= (unsigned)s.im_w || (unsigned)y >= (unsigned)s.im_h) return 0.f;
   int v = s.image[(size_t)y * s.im_w + x];
-  if (y >= s.inv_i && y < s.inv_i + s.inv_h && x >= s.inv_j && x < s.inv_j + s.inv_w) v = 255 - v;
-  return __fdiv_rn((float)v, 255.f);
+  if (y >= s.inv_i0 && y < s.inv_i1 && x >= s.inv_j0 && x < s.inv_j1) v = 255 - v;
+  return lut[v];
 }
 __device__ __forceinline__ float mask_pixel(const unsigned char* img, int im_h, int im_w, int x, int y) {
   if (x < 0 || x >= im_w || y < 0 || y >= im_h) return 0.f;
@@ -228,12 +230,18 @@ __device__ __forceinline__ void bilinear_weights(float rx, float ry, float* w11,
 constexpr int IMG_ROWS = 8;
 __global__ void __launch_bounds__(256) crop_image_kernel(const ftc_crop_sample* __restrict__ samples, const float* __restrict__ start,
                                                          float* __restrict__ out_image, int out_channels, int rows_per_cta) {
+  __shared__ float lut[256];
+  for (int v = threadIdx.x; v < 256; v += blockDim.x) lut[v] = __fdiv_rn((float)v, 255.f);
+  __syncthreads();
   const long long per = (long long)CH * CW;
   const int b = blockIdx.z;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= CW) return;
   const ftc_crop_sample& s = samples[b];
   const int blank = s.blank, nearest = s.nearest, mode = s.color_mode;
+  PageView pv;
+  pv.image = s.image; pv.im_h = s.im_h; pv.im_w = s.im_w;
+  pv.inv_i0 = s.inv_i; pv.inv_i1 = s.inv_i + s.inv_h; pv.inv_j0 = s.inv_j; pv.inv_j1 = s.inv_j + s.inv_w;
   float inv[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) inv[i] = s.inv[i];
@@ -254,15 +262,15 @@ __global__ void __launch_bounds__(256) crop_image_kernel(const ftc_crop_sample* 
       float rx, ry;
       vdot(inv, fx, __fadd_rn((float)y, sy), &rx, &ry);
       if (nearest) {
-        a = page_pixel(s, (int)__dadd_rn((double)rx, 0.5), (int)__dadd_rn((double)ry, 0.5));
+        a = page_pixel(pv, lut, (int)__dadd_rn((double)rx, 0.5), (int)__dadd_rn((double)ry, 0.5));
       } else {
         float w11, w21, w12, w22;
         bilinear_weights(rx, ry, &w11, &w21, &w12, &w22);
         const int ix = (int)rx, iy = (int)ry;
-        a = __fmul_rn(w11, page_pixel(s, ix, iy));
-        a = __fadd_rn(a, __fmul_rn(w21, page_pixel(s, ix + 1, iy)));
-        a = __fadd_rn(a, __fmul_rn(w12, page_pixel(s, ix, iy + 1)));
-        a = __fadd_rn(a, __fmul_rn(w22, page_pixel(s, ix + 1, iy + 1)));
+        a = __fmul_rn(w11, page_pixel(pv, lut, ix, iy));
+        a = __fadd_rn(a, __fmul_rn(w21, page_pixel(pv, lut, ix + 1, iy)));
+        a = __fadd_rn(a, __fmul_rn(w12, page_pixel(pv, lut, ix, iy + 1)));
+        a = __fadd_rn(a, __fmul_rn(w22, page_pixel(pv, lut, ix + 1, iy + 1)));
       }
     }
     if (salt != nullptr) {             // random_salt (data_detector.py:17-26): x * noise, NaN cells -> 1
@@ -278,7 +286,7 @@ __global__ void __launch_bounds__(256) crop_image_kernel(const ftc_crop_sample* 
       const bool in = yi >= 0 && yi < bg_h && xi >= 0 && xi < bg_w;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float bgv = in ? __fdiv_rn((float)bgimg[((size_t)yi * bg_w + xi) * 3 + c], 255.f) : 0.f;
+        const float bgv = in ? lut[bgimg[((size_t)yi * bg_w + xi) * 3 + c]] : 0.f;
         double v = __dadd_rn((double)__fmul_rn(a, fg1[c]), __dmul_rn(na, (double)bgv));
         v = v < 1.0 ? v : 1.0;         // max(0, min(1, v)) as the generated comparisons evaluate it
         v = v > 0.0 ? v : 0.0;

@@ -384,11 +384,16 @@ class GpuProcesser:
         n += (C.sizeof(CropSample) * B + 255) // 256 * 256
         arena = self._arena(n)
         host = arena["host"].numpy()
+        host_t = arena["host"]
         base = arena["dev"].data_ptr()
         ptrs = [dict() for _ in range(B)]
         glob = {}
         for (key, b, a), o in zip(items, offs):
-            host[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+            flat = a.reshape(-1).view(np.uint8)
+            if flat.size >= (1 << 20) and flat.flags.writeable:        # page-sized arrays: torch's threaded copy
+                host_t[o:o + flat.size].copy_(torch.from_numpy(flat))
+            else:
+                host[o:o + flat.size] = flat
             if b < 0:
                 glob[key] = base + o
             else:
