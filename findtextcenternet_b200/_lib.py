@@ -90,6 +90,7 @@ SYMBOLS = {
     "ftc_peak_pick": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ftc_op_conv2d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "ftc_op_conv2d_wpack_bytes": (_sz, [_i, _i, _i]),
+    "ftc_op_conv2d_dgrad": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "ftc_op_dwconv3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "ftc_op_dwconv3x3_tiles": (_i, [_i, _i, _i, _i]),
     "ftc_op_se_fc": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),

@@ -49,6 +49,23 @@ def conv2d(x: torch.Tensor, w_oihw: torch.Tensor, stride: int = 1, scale=None, b
     return out
 
 
+def conv2d_dgrad_tc(dy: torch.Tensor, w_fwd_oihw: torch.Tensor) -> torch.Tensor:
+    """Stride-1 data gradient on the tcgen05 kernel: dy bf16 [B,H,W,C] (C >= Cout, extra channels zero) and the FORWARD weight fp32
+    [Cout,Cin,k,k] -> dx [B,H,W,Cin]; the transposed / rotated operand is formed by the weight-pack kernel."""
+    lib = _lib.load()
+    assert dy.is_cuda and dy.is_contiguous() and dy.dtype == torch.bfloat16
+    b, h, w, c = dy.shape
+    cout, cin, k, _ = w_fwd_oihw.shape
+    w32 = w_fwd_oihw.detach().to(device=dy.device, dtype=torch.float32).contiguous()
+    dx = torch.empty(b, h, w, cin, dtype=dy.dtype, device=dy.device)
+    nbytes = int(lib.ftc_op_conv2d_wpack_bytes(c, cin, k))
+    wpack = torch.empty(nbytes, dtype=torch.uint8, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _lib.check(lib.ftc_op_conv2d_dgrad(dy.data_ptr(), b, h, w, c, w32.data_ptr(), cout, cin, k, dx.data_ptr(), wpack.data_ptr(),
+                                           nbytes, _s(dy)), "ftc_op_conv2d_dgrad")
+    return dx
+
+
 def dwconv3x3(x: torch.Tensor, w9c: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, stride: int = 1,
               want_se_sum: bool = False):
     """Depthwise 3x3 + BN + SiLU.  With ``want_se_sum`` also the per-tile spatial sums [B, tiles, C] fp32 (the SE squeeze,

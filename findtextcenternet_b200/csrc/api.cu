@@ -79,10 +79,29 @@ size_t ftc_op_conv2d_wpack_bytes(int cin, int cout, int ksize) {
   return align_up((size_t)npad * K * 4, 256) + align_up(kt.size() * 4, 256) + 256;
 }
 
+static int op_conv2d_impl(const void* x, int dtype, int batch, int h, int w, int cin, const float* w_oihw, int cout, int ksize,
+                          int stride, const float* scale, const float* bias, int act, const void* residual,
+                          const float* a_scale, void* out, void* wpack, size_t wpack_bytes, int backend, void* stream, int dgrad_rows);
+
 int ftc_op_conv2d(const void* x, int dtype, int batch, int h, int w, int cin, const float* w_oihw, int cout, int ksize,
                   int stride, const float* scale, const float* bias, int act, const void* residual,
                   const float* a_scale, void* out, void* wpack, size_t wpack_bytes, int backend, void* stream) {
+  return op_conv2d_impl(x, dtype, batch, h, w, cin, w_oihw, cout, ksize, stride, scale, bias, act, residual, a_scale, out, wpack,
+                        wpack_bytes, backend, stream, 0);
+}
+
+int ftc_op_conv2d_dgrad(const void* dy, int batch, int h, int w, int dy_ch, const float* w_fwd_oihw, int fwd_cout, int fwd_cin,
+                        int ksize, void* dx, void* wpack, size_t wpack_bytes, void* stream) {
+  FTC_REQUIRE(fwd_cout > 0 && fwd_cout <= dy_ch, "ftc_op_conv2d_dgrad: dy has fewer channels than the forward convolution's outputs");
+  return op_conv2d_impl(dy, DT_BF16, batch, h, w, dy_ch, w_fwd_oihw, fwd_cin, ksize, 1, nullptr, nullptr, ACT_NONE, nullptr, nullptr, dx,
+                        wpack, wpack_bytes, FTC_GEMM_TCGEN05, stream, fwd_cout);
+}
+
+static int op_conv2d_impl(const void* x, int dtype, int batch, int h, int w, int cin, const float* w_oihw, int cout, int ksize,
+                          int stride, const float* scale, const float* bias, int act, const void* residual,
+                          const float* a_scale, void* out, void* wpack, size_t wpack_bytes, int backend, void* stream, int dgrad_rows) {
   FTC_REQUIRE(x && w_oihw && out && wpack, "null argument");
+  FTC_REQUIRE(dgrad_rows == 0 || backend == FTC_GEMM_TCGEN05, "data-gradient weight form is packed by the tcgen05 path only");
   FTC_REQUIRE(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
   FTC_REQUIRE(cin % 8 == 0, "cin must be a multiple of 8");
   FTC_REQUIRE(wpack_bytes >= ftc_op_conv2d_wpack_bytes(cin, cout, ksize), "wpack too small");
@@ -135,7 +154,7 @@ int ftc_op_conv2d(const void* x, int dtype, int batch, int h, int w, int cin, co
     if (rc) return rc;
     p.K = plan.NKB * KBLOCK;
     rc = pack_conv_weight_tc(wp, w_oihw, cout, cin, ksize, ksize, 0, cin, 0, p.K, 0, plan.BN, nullptr, s,
-                             plan.tma == TMA_HALO ? (plan.kb32 ? 2 : 1) : 0);
+                             plan.tma == TMA_HALO ? (plan.kb32 ? 2 : 1) : 0, dgrad_rows);
     if (rc) return rc;
     p.tc = plan;
     rc = conv_gemm_tc(p, s);

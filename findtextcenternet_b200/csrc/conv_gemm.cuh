@@ -98,7 +98,7 @@ int conv_gemm_tma(const ConvGemmParams& p, cudaStream_t stream);   // called by 
 //   halo_order = 1: k = k_off + ((c/64)*9 + kx*3 + ky)*64 + c%64      (TMA_HALO: per 64-channel chunk and column
 //                   shift kx one halo tile serves the three row taps ky; k_off of source B = 9*64*nGA)
 int pack_conv_weight_tc(void* dst, const float* src, int O, int Itot, int kh, int kw, int c_off, int C, int k_off,
-                        int Kpad, int o_off, int BN, const float* cscale, cudaStream_t s, int halo_order = 0);
+                        int Kpad, int o_off, int BN, const float* cscale, cudaStream_t s, int halo_order = 0, int dgrad_rows = 0);
 size_t conv_tc_weight_bytes(const ConvTcPlan& plan, int G);
 void conv_gemm_tc_set_trace(unsigned long long* dev_ptr);
 unsigned long long* conv_gemm_trace_ptr();   // current trace buffer (null = off)   // 4 x 1024 u64: MMA wait start/end, producer wait start/end

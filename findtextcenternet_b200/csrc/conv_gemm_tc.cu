@@ -339,9 +339,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
   }
 }
 
+// dgrad_rows > 0: src is the FORWARD convolution's OIHW weight [dgrad_rows][O][kh][kw]; the packed operand is the data gradient's
+// (channel roles swapped, taps rotated 180 degrees): element (o, c, ky, kx) = src[c][o][kh-1-ky][kw-1-kx], zero for c >= dgrad_rows
+// (dy channels padded up to the kernel's granularity).  Saves the flip / transpose / contiguous copies per convolution and step.
 __global__ void pack_conv_weight_tc_kernel(bf16* __restrict__ dst, const float* __restrict__ src, int O, int Itot, int kh,
                                            int kw, int c_off, int C, int k_off, int NKB, int o_off, int BN,
-                                           const float* __restrict__ cscale, int halo_order) {
+                                           const float* __restrict__ cscale, int halo_order, int dgrad_rows) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t per_o = (int64_t)kh * kw * C;
   if (idx >= (int64_t)O * per_o) return;
@@ -349,7 +352,9 @@ __global__ void pack_conv_weight_tc_kernel(bf16* __restrict__ dst, const float* 
   int r = idx - (int64_t)o * per_o;
   int t = r / C, c = r - t * C;
   int ky = t / kw, kx = t - ky * kw;
-  float v = src[(((int64_t)o * Itot + c_off + c) * kh + ky) * kw + kx];
+  float v;
+  if (dgrad_rows > 0) v = c < dgrad_rows ? src[(((int64_t)c * O + o) * kh + (kh - 1 - ky)) * kw + (kw - 1 - kx)] : 0.f;
+  else v = src[(((int64_t)o * Itot + c_off + c) * kh + ky) * kw + kx];
   if (cscale) v *= cscale[c];
   int R = o_off + o;
   int tile = R / BN, rr = R - tile * BN;
@@ -448,12 +453,12 @@ size_t conv_tc_weight_bytes(const ConvTcPlan& plan, int G) {
 }
 
 int pack_conv_weight_tc(void* dst, const float* src, int O, int Itot, int kh, int kw, int c_off, int C, int k_off, int Kpad,
-                        int o_off, int BN, const float* cscale, cudaStream_t s, int halo_order) {
+                        int o_off, int BN, const float* cscale, cudaStream_t s, int halo_order, int dgrad_rows) {
   int64_t total = (int64_t)O * kh * kw * C;
   int grid = (int)((total + 255) / 256);
   FTC_REQUIRE(!halo_order || (kh == 3 && kw == 3), "halo order is for 3x3 kernels");
   pack_conv_weight_tc_kernel<<<grid, 256, 0, s>>>((bf16*)dst, src, O, Itot, kh, kw, c_off, C, k_off, Kpad / KBLOCK, o_off, BN,
-                                                  cscale, halo_order);
+                                                  cscale, halo_order, dgrad_rows);
   FTC_POST_LAUNCH();
   return 0;
 }

@@ -81,14 +81,17 @@ class _Conv2d(Function):
                 # data gradient = a stride-1 convolution of dy with the taps rotated 180 degrees and the channel roles swapped:
                 # runs on the tcgen05 forward kernel
                 d = _pad_last(dyp, 8, 32)
-                wt = w.detach().float().flip(2, 3).transpose(0, 1)
-                if d.shape[-1] != cout:
-                    wt = torch.nn.functional.pad(wt, (0, 0, 0, 0, 0, d.shape[-1] - cout))
                 if ctx.stride == 2:
                     up = torch.zeros(d.shape[0], x.shape[1], x.shape[2], d.shape[-1], dtype=d.dtype, device=d.device)
                     up[:, ::2, ::2] = d                   # U[2 oy, 2 ox] = dy[oy, ox]; iy = 2 oy + ky - 1
                     d = up
-                dx = K.conv2d(d, wt.contiguous(), 1, None, None, _lib.ACT_NONE, None, None, _lib.GEMM_TCGEN05)
+                if hasattr(K, "conv2d_dgrad_tc"):         # the weight-pack kernel reads the forward weight transposed + rotated
+                    dx = K.conv2d_dgrad_tc(d.contiguous(), w)
+                else:                                     # kernel namespaces without it (CPU graph tests): explicit operand
+                    wt = w.detach().float().flip(2, 3).transpose(0, 1)
+                    if d.shape[-1] != cout:
+                        wt = torch.nn.functional.pad(wt, (0, 0, 0, 0, 0, d.shape[-1] - cout))
+                    dx = K.conv2d(d, wt.contiguous(), 1, None, None, _lib.ACT_NONE, None, None, _lib.GEMM_TCGEN05)
             else:
                 dx = K.conv2d_dgrad(dy, w, x.shape[1], x.shape[2], ctx.stride)
         if ctx.needs_input_grad[1]:

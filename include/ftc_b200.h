@@ -188,6 +188,13 @@ int ftc_ce_rows_grad(const float* logits0, const float* logits1, const float* lo
 int ftc_op_conv2d(const void* x, int dtype, int batch, int h, int w, int cin, const float* w_oihw, int cout, int ksize,
                   int stride, const float* scale, const float* bias, int act, const void* residual,
                   const float* a_scale, void* out, void* wpack, size_t wpack_bytes, int backend, void* stream);
+/* data gradient of a stride-1 bf16 convolution on the tcgen05 kernel: dx [B,h,w,fwd_cin] = conv(dy [B,h,w,dy_ch], W') with W' =
+ * the forward weight (fp32 OIHW [fwd_cout][fwd_cin][k][k], as nn.Conv2d stores it) read with the channel roles swapped and the taps
+ * rotated 180 degrees INSIDE the weight-pack kernel (no flip / transpose / contiguous copies); dy_ch >= fwd_cout: extra (zero-padded)
+ * dy channels meet zero weights.  wpack: ftc_op_conv2d_wpack_bytes(dy_ch, fwd_cin, ksize).  (torch autograd's conv backward-input of
+ * train1.py:170 loss.backward().) */
+int ftc_op_conv2d_dgrad(const void* dy, int batch, int h, int w, int dy_ch, const float* w_fwd_oihw, int fwd_cout, int fwd_cin,
+                        int ksize, void* dx, void* wpack, size_t wpack_bytes, void* stream);
 size_t ftc_op_conv2d_wpack_bytes(int cin, int cout, int ksize);
 /* depthwise 3x3 + BN + SiLU (torchvision efficientnet.py:137-149).  se_sum (optional): fp32 [batch][tiles][c] receives one partial
  * spatial sum per CTA tile, tiles = ftc_op_dwconv3x3_tiles(h, w, stride, dtype); every entry is written, no atomics (the SE

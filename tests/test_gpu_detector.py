@@ -181,3 +181,28 @@ def test_detect_tiles_end_to_end_matches_reference_decode(detector_sd, golden_de
     # (the SE squeeze accumulates fc1 shares with fp32 atomics: run-to-run differences of a few ulp are expected)
     assert int(count2[0]) == n and torch.allclose(loc2[0, :n], loc[0, :n], rtol=1e-5, atol=1e-5)
     assert int(count[1]) > 0 and not torch.equal(loc[1, :8], loc[0, :8])
+
+
+def test_full_size_properties_at_the_benchmarked_configuration(model):
+    """BASELINE.json configs[1] at its full size (batch 32, bf16, tcgen05 path), through properties that need no 32-image reference
+    run: (1) every image's maps are BIT-identical to its own batch-1 forward (no cross-image coupling, no dependence on how the
+    M tiles of a batch are scheduled: the forward is deterministic since round 2); (2) permuting the batch permutes the outputs;
+    (3) the peak channel is exactly the 3x3 local-maximum rule of CenterNetDetector.forward (models/detector.py:289-296)
+    applied to channel 0, checked against torch's max_pool2d over all 32 x 192 x 192 positions."""
+    m, det = model
+    m.detector.set_precision("bf16")
+    g = torch.Generator().manual_seed(32)
+    x = torch.rand(32, 3, 768, 768, generator=g).cuda()
+    with torch.no_grad():
+        h10, feat = det(x)
+        perm = torch.randperm(32, generator=g).cuda()
+        h10p, featp = det(x[perm].contiguous())
+        for i in (0, 13, 31):
+            h1, f1 = det(x[i:i + 1].contiguous())
+            assert torch.equal(h1[0], h10[i]) and torch.equal(f1[0], feat[i]), f"image {i}: batch-32 row differs from its batch-1 forward"
+    assert torch.equal(h10p, h10[perm]) and torch.equal(featp, feat[perm])
+    key = h10[:, 0:1]
+    pooled = torch.nn.functional.max_pool2d(torch.nn.functional.pad(key, (1, 1, 1, 1), value=float("-inf")), 3, 1)
+    expect = torch.where(key < pooled, torch.full_like(key, float("-inf")), key)
+    assert torch.equal(h10[:, 1:2], expect)
+    assert torch.isfinite(h10[:, [0] + list(range(2, 10))]).all() and torch.isfinite(feat).all()

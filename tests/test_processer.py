@@ -356,3 +356,34 @@ def test_gpu_distortion_equals_reference_golden_and_device_noise_is_standard_nor
     assert float((z[0] - z[1]).abs().mean()) > 0.5                    # different seeds: different fields
     zz = z[0].flatten()
     assert abs(float((zz[:-1] * zz[1:]).mean())) < 5e-3               # neighbouring samples uncorrelated
+
+
+@pytest.mark.gpu
+def test_gpu_full_batch_properties():
+    """Batch 64 (the bench's size) through size-independent properties: the batch equals its two halves run separately (bitwise: no
+    cross-sample coupling through the atomics / scratch), a blank sample composited with any colour is the background colour, and the
+    id map only holds codes of in-crop boxes (or 0)."""
+    import torch
+    proc = P.GpuProcesser("cuda:0")
+    base = [case_params(k) for k in CASES]
+    sp = [base[i % len(base)] for i in range(64)]
+    samples, params = [s for s, _ in sp], [dict(p) for _, p in sp]
+    for i, p in enumerate(params):                 # vary the crop anchor per copy so the 64 samples differ
+        if p["cidx"] >= 0:
+            p["woffset"] = np.float32(float(p["woffset"]) + 3.0 * (i // len(base)))
+        else:
+            p["startx0"] = np.float32(float(p["startx0"]) + 3.0 * (i // len(base)))
+    params[5] = {"blank": True}
+    colors = [color_params(COLOR[i % 3], P)[0] for i in range(64)]
+    full = [t.cpu() for t in proc.run(samples, params, colors)]
+    lo = [t.cpu() for t in proc.run(samples[:32], params[:32], colors[:32])]
+    hi = [t.cpu() for t in proc.run(samples[32:], params[32:], colors[32:])]
+    for f, a, b in zip(full, lo, hi):
+        assert torch.equal(f, torch.cat([a, b]))
+    image, maps, idmap, minsize = full
+    bgc = torch.tensor(np.asarray(colors[5]["bg"], np.float32)).view(3, 1, 1)
+    assert torch.equal(image[5], bgc.expand(3, 768, 768)) and not maps[5].any() and not idmap[5].any() and minsize[5] == 0
+    for b in (0, 2, 40):
+        codes = set(np.unique(idmap[b, 0].numpy()).tolist()) - {0}
+        assert codes <= set(samples[b][4][:, 0].tolist())
+        assert float(maps[b, 0].max()) <= 1.0 and float(maps[b, 0].min()) >= 0.0
