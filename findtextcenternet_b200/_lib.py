@@ -106,6 +106,8 @@ SYMBOLS = {
     "ftc_train_bn_stats_running": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
     "ftc_train_bn_act": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
     "ftc_train_bn_act_bwd": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp]),
+    "ftc_train_bn_act_bwd_ld": (_i, [_vp, _vp, _i64, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp]),
+    "ftc_train_upsample2x_bwd_ld": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp]),
     "ftc_train_conv2d_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ftc_train_conv2d_wgrad_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "ftc_train_conv2d_wgrad_ws": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),

@@ -206,12 +206,33 @@ def bn_act(x, mean, var, gamma, beta, eps: float, act: int, residual=None) -> to
     return y
 
 
+def _channel_slice_ld(t: torch.Tensor, c: int) -> int:
+    """Row stride of ``t`` when it is a channel slice ``wide[..., a:a+c]`` of a contiguous tensor (16-byte aligned), else 0."""
+    st, sh = t.stride(), t.shape
+    if t.dim() < 2 or st[-1] != 1 or sh[-1] != c:
+        return 0
+    ld = st[-2]
+    if ld <= c or ld % 8 or t.data_ptr() % 16:
+        return 0
+    for i in range(t.dim() - 2):
+        if st[i] != st[i + 1] * sh[i + 1]:
+            return 0
+    return int(ld)
+
+
 def bn_act_bwd(x, dy, mean, var, gamma, beta, eps: float, act: int):
-    """-> (dx, dgamma, dbeta)"""
+    """-> (dx, dgamma, dbeta).  A dy that is a channel slice of a wider map (torch.cat's backward) is read in place by the bf16
+    stream kernels."""
     lib = _lib.load()
     assert x.is_cuda and x.is_contiguous()
-    dy = dy.contiguous()
     c = x.shape[-1]
+    ld = c
+    if not dy.is_contiguous():
+        sl = _channel_slice_ld(dy, c) if (x.dtype == torch.bfloat16 and c % 32 == 0 and hasattr(lib, "ftc_train_bn_act_bwd_ld")) else 0
+        if sl:
+            ld = sl
+        else:
+            dy = dy.contiguous()
     rows = x.numel() // c
     dx = torch.empty_like(x)
     dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
@@ -219,9 +240,14 @@ def bn_act_bwd(x, dy, mean, var, gamma, beta, eps: float, act: int):
     scratch = _reduce_scratch(rows, c, x.device)
     g, b = _f32(gamma, x.device), _f32(beta, x.device)
     with torch.cuda.device(x.device):
-        _lib.check(lib.ftc_train_bn_act_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), _dt(x), rows, c, mean.data_ptr(),
-                                            var.data_ptr(), g.data_ptr(), b.data_ptr(), eps, act, dbeta.data_ptr(),
-                                            dgamma.data_ptr(), scratch.data_ptr(), _s(x)), "ftc_train_bn_act_bwd")
+        if ld != c:
+            _lib.check(lib.ftc_train_bn_act_bwd_ld(x.data_ptr(), dy.data_ptr(), ld, dx.data_ptr(), _dt(x), rows, c, mean.data_ptr(),
+                                                   var.data_ptr(), g.data_ptr(), b.data_ptr(), eps, act, dbeta.data_ptr(),
+                                                   dgamma.data_ptr(), scratch.data_ptr(), _s(x)), "ftc_train_bn_act_bwd_ld")
+        else:
+            _lib.check(lib.ftc_train_bn_act_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), _dt(x), rows, c, mean.data_ptr(),
+                                                var.data_ptr(), g.data_ptr(), b.data_ptr(), eps, act, dbeta.data_ptr(),
+                                                dgamma.data_ptr(), scratch.data_ptr(), _s(x)), "ftc_train_bn_act_bwd")
     return dx, dgamma, dbeta
 
 
@@ -362,12 +388,22 @@ def se_fc_train_bwd(dgate, gate, hid_pre, mean, w1, w2):
 
 def upsample2x_bwd(dy: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
-    dy = dy.contiguous()
     b, ho, wo, c = dy.shape
+    ld = c
+    if not dy.is_contiguous():
+        sl = _channel_slice_ld(dy, c) if hasattr(lib, "ftc_train_upsample2x_bwd_ld") else 0
+        if sl:
+            ld = sl             # channel slice of a wider map (torch.cat's backward): read in place
+        else:
+            dy = dy.contiguous()
     dx = torch.empty(b, ho // 2, wo // 2, c, dtype=dy.dtype, device=dy.device)
     with torch.cuda.device(dy.device):
-        _lib.check(lib.ftc_train_upsample2x_bwd(dy.data_ptr(), dx.data_ptr(), _dt(dy), b, ho // 2, wo // 2, c, _s(dy)),
-                   "ftc_train_upsample2x_bwd")
+        if ld != c:
+            _lib.check(lib.ftc_train_upsample2x_bwd_ld(dy.data_ptr(), ld, dx.data_ptr(), _dt(dy), b, ho // 2, wo // 2, c, _s(dy)),
+                       "ftc_train_upsample2x_bwd_ld")
+        else:
+            _lib.check(lib.ftc_train_upsample2x_bwd(dy.data_ptr(), dx.data_ptr(), _dt(dy), b, ho // 2, wo // 2, c, _s(dy)),
+                       "ftc_train_upsample2x_bwd")
     return dx
 
 

@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256) bn_apply_stream_kernel(const bf16* __rest
 // MODE 0: sum x, sum x^2;  MODE 1: sum dz, sum dz * xhat with dz = dy * act'(gamma * xhat + beta).  part[q][blockIdx.y][C]
 template <int MODE, int ACT, int CK>
 __global__ void __launch_bounds__(256) bn_reduce_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, int64_t rows, int C,
-                                                               float* __restrict__ part, BnArgs bn) {
+                                                               float* __restrict__ part, BnArgs bn, int64_t ldy) {   // ldy: dy row stride
   constexpr int RL = 256 / CK;
   __shared__ float sm[2][RL][CK * 8 + 1];
   const int ck = threadIdx.x % CK, rl = threadIdx.x / CK;
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(256) bn_reduce_stream_kernel(const bf16* __res
         const int64_t rr = t0 + u * RL + rl;
         if (rr < rows) {
           xv[u] = *reinterpret_cast<const uint4*>(x + rr * C + c0);
-          if (MODE == 1) dv[u] = *reinterpret_cast<const uint4*>(dy + rr * C + c0);
+          if (MODE == 1) dv[u] = *reinterpret_cast<const uint4*>(dy + rr * ldy + c0);
         }
       }
 #pragma unroll
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(256) bn_reduce_stream_kernel(const bf16* __res
 template <int ACT, int CK>
 __global__ void __launch_bounds__(256) bn_bwd_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
                                                             int64_t rows, int C, float inv_rows, BnArgs bn,
-                                                            const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat) {
+                                                            const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat, int64_t ldy) {
   constexpr int RL = 256 / CK;
   const int ck = threadIdx.x % CK, rl = threadIdx.x / CK;
   const int c0 = (blockIdx.x * CK + ck) * 8;
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(256) bn_bwd_stream_kernel(const bf16* __restri
       const int64_t rr = t0 + u * RL + rl;
       if (rr < rows) {
         xv[u] = *reinterpret_cast<const uint4*>(x + rr * C + c0);
-        dv[u] = *reinterpret_cast<const uint4*>(dy + rr * C + c0);
+        dv[u] = *reinterpret_cast<const uint4*>(dy + rr * ldy + c0);
       }
     }
 #pragma unroll
@@ -1377,7 +1377,7 @@ __global__ void __launch_bounds__(256) se_fc_bwd_weight_kernel(const float* __re
 // {j-1, j}: o in [2j-2, 2j+3] clipped.  CTA per input row, warps over pixels, lanes over channels.
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int H, int W, int C,
-                                                             float sy, float sx) {
+                                                             float sy, float sx, int64_t ldy) {   // ldy: dy pixel stride (>= C: a channel slice of a wider map)
   const int Ho = 2 * H, Wo = 2 * W;
   const int b = blockIdx.y, iy = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1414,10 +1414,10 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
         for (int a = 0; a < ny; ++a) {
-          const T* row = dy + (((int64_t)b * Ho + oys[a]) * Wo) * C + c;
+          const T* row = dy + (((int64_t)b * Ho + oys[a]) * Wo) * ldy + c;
           for (int k = 0; k < nx; ++k) {
             float v[8];
-            load8(row + (int64_t)oxs[k] * C, v);
+            load8(row + (int64_t)oxs[k] * ldy, v);
             const float wgt = wy[a] * wx[k];
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, v[j], acc[j]);
@@ -1430,9 +1430,9 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict
     for (int c = lane; c < C; c += 32) {
       float acc = 0.f;
       for (int a = 0; a < ny; ++a) {
-        const T* row = dy + (((int64_t)b * Ho + oys[a]) * Wo) * C + c;
+        const T* row = dy + (((int64_t)b * Ho + oys[a]) * Wo) * ldy + c;
         float r = 0.f;
-        for (int k = 0; k < nx; ++k) r = fmaf(wx[k], to_f(row[(int64_t)oxs[k] * C]), r);
+        for (int k = 0; k < nx; ++k) r = fmaf(wx[k], to_f(row[(int64_t)oxs[k] * ldy]), r);
         acc = fmaf(wy[a], r, acc);
       }
       po[c] = from_f<T>(acc);
@@ -1759,8 +1759,8 @@ static int bn_stats_impl(const void* x, int dtype, int64_t rows, int c, float* m
   if (vec && dtype == DT_BF16 && c % 32 == 0 && bn_unroll() == 0) {
     const int ck = stream_ck(c);
     const dim3 sg = stream_grid(rows, c, ck, nchunk, 3);   // all CTAs resident; few partial rows for the finish
-    if (ck == 8) bn_reduce_stream_kernel<0, ACT_NONE, 8><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn);
-    else bn_reduce_stream_kernel<0, ACT_NONE, 4><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn);
+    if (ck == 8) bn_reduce_stream_kernel<0, ACT_NONE, 8><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn, c);
+    else bn_reduce_stream_kernel<0, ACT_NONE, 4><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn, c);
     FTC_POST_LAUNCH();
     col_reduce_finish_kernel<0><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, (int)sg.y, c, rows, mean, var, rs);
     FTC_POST_LAUNCH();
@@ -1830,8 +1830,15 @@ int ftc_train_bn_act(const void* x, void* y, int dtype, int64_t rows, int c, con
 int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t rows, int c, const float* mean,
                          const float* var, const float* gamma, const float* beta, float eps, int act, float* dbeta,
                          float* dgamma, void* scratch, void* stream) {
+  return ftc_train_bn_act_bwd_ld(x, dy, c, dx, dtype, rows, c, mean, var, gamma, beta, eps, act, dbeta, dgamma, scratch, stream);
+}
+
+int ftc_train_bn_act_bwd_ld(const void* x, const void* dy, int64_t dy_ld, void* dx, int dtype, int64_t rows, int c, const float* mean,
+                            const float* var, const float* gamma, const float* beta, float eps, int act, float* dbeta,
+                            float* dgamma, void* scratch, void* stream) {
   FTC_REQUIRE(x && dy && dx && mean && var && gamma && beta && dbeta && dgamma && scratch && rows > 0 && c > 0 && dtype_ok(dtype),
               "bad argument");
+  FTC_REQUIRE(dy_ld >= c, "dy row stride below the channel count");
   FTC_REQUIRE(act == ACT_NONE || act == ACT_SILU || act == ACT_GELU, "activation");
   cudaStream_t s = (cudaStream_t)stream;
   BnArgs bn = {mean, var, gamma, beta, eps, act};
@@ -1841,12 +1848,14 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
   const bool vec = c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
   const bool par16 = ((reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var) | reinterpret_cast<uintptr_t>(gamma) |
                        reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(dbeta) | reinterpret_cast<uintptr_t>(dgamma)) & 15) == 0;
-  if (vec && par16 && dtype == DT_BF16 && c % 32 == 0 && bn_unroll() == 0) {
+  const bool stream_path = vec && par16 && dtype == DT_BF16 && c % 32 == 0 && dy_ld % 8 == 0 && bn_unroll() == 0;
+  FTC_REQUIRE(stream_path || dy_ld == c, "a row-strided dy is taken by the bf16 stream kernels only (C % 32 == 0): pass a contiguous dy");
+  if (stream_path) {
     const int ck = stream_ck(c);
     const dim3 rg = stream_grid(rows, c, ck, nchunk, 6);   // (2 per SM measured slower: 27.5 vs 24.5 ms per step, tools/bench_bn.py)
 #define BN_RED(A)                                                                                                                  \
-    if (ck == 8) bn_reduce_stream_kernel<1, A, 8><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn);        \
-    else bn_reduce_stream_kernel<1, A, 4><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn);
+    if (ck == 8) bn_reduce_stream_kernel<1, A, 8><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn, dy_ld);        \
+    else bn_reduce_stream_kernel<1, A, 4><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn, dy_ld);
     FTC_BN_ACT_SWITCH(act, BN_RED);
 #undef BN_RED
     FTC_POST_LAUNCH();
@@ -1855,8 +1864,8 @@ int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int
     const float inv_rows_s = (float)(1.0 / (double)rows);
     const dim3 ag = stream_grid(rows, c, ck, 1 << 30);
 #define BN_BWD(A)                                                                                                                              \
-    if (ck == 8) bn_bwd_stream_kernel<A, 8><<<ag, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows_s, bn, dbeta, dgamma);   \
-    else bn_bwd_stream_kernel<A, 4><<<ag, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows_s, bn, dbeta, dgamma);
+    if (ck == 8) bn_bwd_stream_kernel<A, 8><<<ag, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows_s, bn, dbeta, dgamma, dy_ld);   \
+    else bn_bwd_stream_kernel<A, 4><<<ag, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows_s, bn, dbeta, dgamma, dy_ld);
     FTC_BN_ACT_SWITCH(act, BN_BWD);
 #undef BN_BWD
     FTC_POST_LAUNCH();
@@ -2132,17 +2141,23 @@ int ftc_train_se_fc_bwd(const float* dgate, const float* gate, const float* hid_
 }
 
 int ftc_train_upsample2x_bwd(const void* dy, void* dx, int dtype, int batch, int h, int w, int c, void* stream) {
+  return ftc_train_upsample2x_bwd_ld(dy, c, dx, dtype, batch, h, w, c, stream);
+}
+
+int ftc_train_upsample2x_bwd_ld(const void* dy, int64_t dy_ld, void* dx, int dtype, int batch, int h, int w, int c, void* stream) {
   FTC_REQUIRE(dy && dx && dtype_ok(dtype) && batch > 0 && batch <= 65535 && h > 0 && w > 0 && c > 0, "bad argument");
+  FTC_REQUIRE(dy_ld >= c, "dy pixel stride below the channel count");
+  const int64_t ldy = dy_ld;
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid(h, batch);
   const float sy = (float)(h - 1) / (float)(2 * h - 1), sx = (float)(w - 1) / (float)(2 * w - 1);
-  const bool vec = c % 8 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  const bool vec = c % 8 == 0 && ldy % 8 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
   if (dtype == DT_F32) {
-    if (vec) upsample2x_bwd_kernel<float, true><<<grid, 256, 0, s>>>(cp<float>(dy), mp<float>(dx), h, w, c, sy, sx);
-    else upsample2x_bwd_kernel<float, false><<<grid, 256, 0, s>>>(cp<float>(dy), mp<float>(dx), h, w, c, sy, sx);
+    if (vec) upsample2x_bwd_kernel<float, true><<<grid, 256, 0, s>>>(cp<float>(dy), mp<float>(dx), h, w, c, sy, sx, ldy);
+    else upsample2x_bwd_kernel<float, false><<<grid, 256, 0, s>>>(cp<float>(dy), mp<float>(dx), h, w, c, sy, sx, ldy);
   } else {
-    if (vec) upsample2x_bwd_kernel<bf16, true><<<grid, 256, 0, s>>>(cp<bf16>(dy), mp<bf16>(dx), h, w, c, sy, sx);
-    else upsample2x_bwd_kernel<bf16, false><<<grid, 256, 0, s>>>(cp<bf16>(dy), mp<bf16>(dx), h, w, c, sy, sx);
+    if (vec) upsample2x_bwd_kernel<bf16, true><<<grid, 256, 0, s>>>(cp<bf16>(dy), mp<bf16>(dx), h, w, c, sy, sx, ldy);
+    else upsample2x_bwd_kernel<bf16, false><<<grid, 256, 0, s>>>(cp<bf16>(dy), mp<bf16>(dx), h, w, c, sy, sx, ldy);
   }
   FTC_POST_LAUNCH();
   return 0;

@@ -115,8 +115,7 @@ class _BNAct(Function):
     @staticmethod
     def backward(ctx, dy):
         x, gamma, beta, mean, var = ctx.saved_tensors
-        dy = dy.contiguous()
-        dx, dgamma, dbeta = K.bn_act_bwd(x, dy, mean, var, gamma, beta, ctx.eps, ctx.act)
+        dx, dgamma, dbeta = K.bn_act_bwd(x, dy, mean, var, gamma, beta, ctx.eps, ctx.act)     # dy may be a channel slice (cat backward)
         return dx, dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None, None, None, None, (dy if ctx.has_res else None)
 
 
@@ -172,7 +171,7 @@ class _Upsample2x(Function):
 
     @staticmethod
     def backward(ctx, dy):
-        return K.upsample2x_bwd(dy.contiguous())
+        return K.upsample2x_bwd(dy)          # dy may be a channel slice of a wider map (cat backward): read in place
 
 
 class _RowScale(Function):

@@ -258,6 +258,12 @@ int ftc_train_bn_act(const void* x, void* y, int dtype, int64_t rows, int c, con
 int ftc_train_bn_act_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t rows, int c, const float* mean,
                          const float* var, const float* gamma, const float* beta, float eps, int act, float* dbeta,
                          float* dgamma, void* scratch, void* stream);
+/* the same with a ROW-STRIDED dy (dy_ld elements between rows, >= c): the gradient of a channel slice of a wider map -- what
+ * torch.cat's backward hands to each of its inputs (Leafmap: cat([y, bn(x)]), models/detector.py:199) -- is consumed in place instead
+ * of being copied into a contiguous tensor first.  bf16 with c % 32 == 0 (the stream kernels); otherwise dy_ld must equal c. */
+int ftc_train_bn_act_bwd_ld(const void* x, const void* dy, int64_t dy_ld, void* dx, int dtype, int64_t rows, int c, const float* mean,
+                            const float* var, const float* gamma, const float* beta, float eps, int act, float* dbeta,
+                            float* dgamma, void* scratch, void* stream);
 /* gradients of nn.Conv2d(k = 1 | 3, padding = (k-1)/2, stride = 1 | 2, bias-free): x [batch,h,w,cin], dy [batch,ho,wo,cout] NHWC;
  * weights and their gradient fp32 OIHW (the parameter's own layout).  wgrad OVERWRITES dw_oihw (fp32 atomics over pixel
  * splits); dgrad writes dx = conv_transpose(dy, w) (+ add, e.g. the gradient arriving over a residual connection). */
@@ -299,6 +305,8 @@ int ftc_train_se_fc_bwd(const float* dgate, const float* gate, const float* hid_
 /* adjoint of nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True, models/detector.py:167-186): dy [batch,2h,2w,c] ->
  * dx [batch,h,w,c] */
 int ftc_train_upsample2x_bwd(const void* dy, void* dx, int dtype, int batch, int h, int w, int c, void* stream);
+/* the same with a pixel-strided dy (dy_ld elements between pixels, >= c) */
+int ftc_train_upsample2x_bwd_ld(const void* dy, int64_t dy_ld, void* dx, int dtype, int batch, int h, int w, int c, void* stream);
 
 /* ---- train step of the Transformer (train3.py:132-137 differentiates models/transformer.py:58-253; dropout = 0 as in
  * ModelDimensions :257-264).  Linear layers are ftc_op_conv2d / ftc_train_conv2d_{wgrad,dgrad} on [rows,1,1,C] tensors.

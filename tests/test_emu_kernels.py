@@ -574,3 +574,35 @@ def test_emu_bn_stats_running_update(emu):
     m0, v0 = TO.bn_stats(x)
     assert rel_l2(mean, m0) < 1e-5 and rel_l2(var, v0) < 1e-4
     assert rel_l2(rm, rm0) < 1e-6 and rel_l2(rv, rv0) < 1e-6 and int(nbt) == 8
+
+
+def test_emu_row_strided_dy_is_read_in_place(emu):
+    """The gradient of a channel slice of a wider map (torch.cat's backward) goes to the BatchNorm / upsample backward kernels with its
+    row stride instead of a contiguous copy: same numbers as the contiguous call."""
+    rows, c, wide = 300, 64, 160
+    x = (rnd(rows, c, seed=1) * 1.3).to(torch.bfloat16)
+    dwide = rnd(rows, wide, seed=2, dt=torch.bfloat16)
+    dy = dwide[:, 96:160]                                   # channel slice: row stride 160, 16-byte aligned offset
+    gamma, beta = rnd(c, seed=3), rnd(c, seed=4)
+    m0, v0 = TO.bn_stats(x.float())
+    sc = scratch(emu, rows, c)
+    outs = []
+    for d, ld in ((dy.contiguous(), c), (dy, wide)):
+        dx, dbeta, dgamma = torch.empty_like(x), torch.empty(c), torch.empty(c)
+        ok(emu, emu.ftc_train_bn_act_bwd_ld(P(x), C.c_void_p(d.data_ptr()), C.c_int64(ld), P(dx), 1, C.c_int64(rows), c, P(m0), P(v0), P(gamma),
+                                            P(beta), C.c_float(1e-3), 1, P(dbeta), P(dgamma), P(sc), None))
+        outs.append((dx.clone(), dbeta.clone(), dgamma.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    b_, h, w, cc = 2, 3, 4, 16
+    duw = rnd(b_, 2 * h, 2 * w, 40, seed=5, dt=torch.bfloat16)
+    du = duw[..., 8:24]
+    res = []
+    for d, ld in ((du.contiguous(), cc), (du, 40)):
+        dxu = torch.empty(b_, h, w, cc, dtype=torch.bfloat16)
+        ok(emu, emu.ftc_train_upsample2x_bwd_ld(C.c_void_p(d.data_ptr()), C.c_int64(ld), P(dxu), 1, b_, h, w, cc, None))
+        res.append(dxu.clone())
+    assert torch.equal(res[0], res[1])
+    from findtextcenternet_b200 import _ops
+    assert _ops._channel_slice_ld(dy, c) == wide and _ops._channel_slice_ld(dy.contiguous(), c) == 0
+    assert _ops._channel_slice_ld(du, cc) == 40 and _ops._channel_slice_ld(duw[:, ::2, :, 8:24], cc) == 0
