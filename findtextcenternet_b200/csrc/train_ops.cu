@@ -986,60 +986,64 @@ __global__ void __launch_bounds__(256) dw_vec_kernel(const T* __restrict__ src, 
 template <typename T>
 __global__ void __launch_bounds__(256) dw_wgrad_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, int B, int H, int W, int C,
                                                            int Ho, int Wo, int stride, int pix_per_split, float* __restrict__ dw) {
-  __shared__ float sm[8][9][RED_CH];
+  // blockIdx.z = kernel row ky: a CTA accumulates the three taps of one row (24 accumulators per thread instead of 72: three CTAs
+  // per SM instead of one; the all-taps version was latency-bound at one CTA per SM: 8.8 ms of a B = 16 step for 1.8 ms of traffic)
+  __shared__ float sm[8][3][RED_CH];
   const int ck = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int c0 = blockIdx.x * RED_CH + ck * 8;
+  const int ky = blockIdx.z;
   const int P = B * Ho * Wo;
   const int p0 = blockIdx.y * pix_per_split, p1 = min(P, p0 + pix_per_split);
-  float acc[9][8];
+  float acc[3][8];
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < 3; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   if (c0 < C) {
     if constexpr (sizeof(T) == 2) {
-      // bf16: the ten 16-byte loads of a pixel are issued together from clamped addresses (taps outside the image are masked
-      // afterwards): with the boundary tests as branches around each load the compiler kept ONE load in flight per thread and
-      // the kernel ran at 1.4 TB/s (12.9 ms of a B = 16 step, ncu r02l)
-      for (int p = p0 + pl; p < p1; p += 32) {
-        const int ox = p % Wo, q = p / Wo;
-        const int oy = q % Ho, b = q / Ho;
-        const uint4 gv = *reinterpret_cast<const uint4*>(dy + (int64_t)p * C + c0);
-        uint4 xv[9];
+      // bf16: two pixels per trip, their eight 16-byte loads issued together from clamped addresses (taps outside the image are
+      // masked afterwards; boundary tests as branches around each load keep one load in flight per thread)
+      for (int p = p0 + pl; p < p1; p += 64) {
+        uint4 gv[2], xv[2][3];
         unsigned okm = 0;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+        for (int u = 0; u < 2; ++u) {
+          const int pp = min(p + 32 * u, p1 - 1);
+          const int ox = pp % Wo, q = pp / Wo;
+          const int oy = q % Ho, b = q / Ho;
+          gv[u] = *reinterpret_cast<const uint4*>(dy + (int64_t)pp * C + c0);
           const int iy = oy * stride - 1 + ky;
           const int iyc = min(max(iy, 0), H - 1);
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             const int ix = ox * stride - 1 + kx;
             const int ixc = min(max(ix, 0), W - 1);
-            xv[ky * 3 + kx] = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + iyc) * W + ixc) * C + c0);
-            okm |= (iy == iyc && ix == ixc) ? (1u << (ky * 3 + kx)) : 0u;
+            xv[u][kx] = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + iyc) * W + ixc) * C + c0);
+            okm |= (p + 32 * u < p1 && iy == iyc && ix == ixc) ? (1u << (u * 3 + kx)) : 0u;
           }
         }
-        float g[8];
-        unpack8(gv, g);
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          float v[8];
-          unpack8(xv[t], v);
-          const float m = (okm >> t) & 1u ? 1.f : 0.f;
+        for (int u = 0; u < 2; ++u) {
+          float g[8];
+          unpack8(gv[u], g);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(g[j] * m, v[j], acc[t][j]);
+          for (int kx = 0; kx < 3; ++kx) {
+            float v[8];
+            unpack8(xv[u][kx], v);
+            const float m = (okm >> (u * 3 + kx)) & 1u ? 1.f : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[kx][j] = fmaf(g[j] * m, v[j], acc[kx][j]);
+          }
         }
       }
     } else {
-    for (int p = p0 + pl; p < p1; p += 32) {
-      const int ox = p % Wo, q = p / Wo;
-      const int oy = q % Ho, b = q / Ho;
-      float g[8];
-      load8(dy + (int64_t)p * C + c0, g);
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
+      for (int p = p0 + pl; p < p1; p += 32) {
+        const int ox = p % Wo, q = p / Wo;
+        const int oy = q % Ho, b = q / Ho;
         const int iy = oy * stride - 1 + ky;
         if (iy < 0 || iy >= H) continue;
+        float g[8];
+        load8(dy + (int64_t)p * C + c0, g);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int ix = ox * stride - 1 + kx;
@@ -1047,16 +1051,15 @@ __global__ void __launch_bounds__(256) dw_wgrad_vec_kernel(const T* __restrict__
           float v[8];
           load8(x + (((int64_t)b * H + iy) * W + ix) * C + c0, v);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(g[j], v[j], acc[ky * 3 + kx][j]);
+          for (int j = 0; j < 8; ++j) acc[kx][j] = fmaf(g[j], v[j], acc[kx][j]);
         }
       }
-    }
     }
   }
   // lanes of a warp: ck = lane & 7, four pixel lanes (lane >> 3): fold them, then the eight warps through shared memory
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < 3; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = acc[t][j];
@@ -1065,14 +1068,14 @@ __global__ void __launch_bounds__(256) dw_wgrad_vec_kernel(const T* __restrict__
       if (lane < 8) sm[warp][t][ck * 8 + j] = v;
     }
   __syncthreads();
-  for (int i = threadIdx.x; i < 9 * RED_CH; i += 256) {
+  for (int i = threadIdx.x; i < 3 * RED_CH; i += 256) {
     const int t = i / RED_CH, cc = i - t * RED_CH;
     const int c = blockIdx.x * RED_CH + cc;
     if (c >= C) continue;
     float s = 0.f;
 #pragma unroll
     for (int l = 0; l < 8; ++l) s += sm[l][t][cc];
-    atomicAdd(dw + (int64_t)t * C + c, s);
+    atomicAdd(dw + (int64_t)(ky * 3 + t) * C + c, s);
   }
 }
 
@@ -1171,11 +1174,16 @@ __global__ void __launch_bounds__(256) scale_bc_kernel(const T* __restrict__ x, 
 
 // 16-byte-vector versions (C % 8 == 0): thread = (chunk lane, row lane) as in the BatchNorm kernels; blockIdx.z = image, so the
 // per-(image, channel) factors are loop invariants
+#ifdef FTC_EMU
+constexpr int SSUM_THREADS = 256;
+#else
+constexpr int SSUM_THREADS = 1024;    // 128 pixel lanes: (C / 64) x B CTAs are few (384 at 48 x 48 x 1536, B = 16): fill the SMs with threads
+#endif
 template <typename T, int MUL>
-__global__ void __launch_bounds__(256) spatial_sum_vec_kernel(const T* __restrict__ x, const T* __restrict__ y, int HW, int C,
-                                                              float scale, float* __restrict__ out) {
-  __shared__ float sm[32][RED_CH + 1];
-  const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
+__global__ void __launch_bounds__(1024) spatial_sum_vec_kernel(const T* __restrict__ x, const T* __restrict__ y, int HW, int C,
+                                                               float scale, float* __restrict__ out) {
+  __shared__ float sm[128][RED_CH + 1];
+  const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3, nrl = blockDim.x >> 3;
   const int c0 = blockIdx.x * RED_CH + ck * 8, b = blockIdx.y;
   float acc[8];
 #pragma unroll
@@ -1183,20 +1191,22 @@ __global__ void __launch_bounds__(256) spatial_sum_vec_kernel(const T* __restric
   if (c0 < C) {
     const T* xb = x + (int64_t)b * HW * C + c0;
     const T* yb = MUL ? y + (int64_t)b * HW * C + c0 : nullptr;
-    // four pixel groups per trip, loads first (one load in flight per thread ran at ~1.5 TB/s); summation order per lane unchanged
-    for (int p = rl; p < HW; p += 128) {
-      float v[4][8], w[4][8];
+    // U pixel groups per trip, loads first (one load in flight per thread ran at ~1.5 TB/s); fixed summation order.  U = 2 with the
+    // second operand: 1024-thread CTAs leave 64 registers per thread
+    constexpr int U = MUL ? 2 : 4;
+    for (int p = rl; p < HW; p += U * nrl) {
+      float v[U][8], w[U][8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int pp = p + 32 * u;
+      for (int u = 0; u < U; ++u) {
+        const int pp = p + nrl * u;
         if (pp < HW) {
           load8(xb + (int64_t)pp * C, v[u]);
           if (MUL) load8(yb + (int64_t)pp * C, w[u]);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (p + 32 * u < HW) {
+      for (int u = 0; u < U; ++u) {
+        if (p + nrl * u < HW) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] += MUL ? v[u][j] * w[u][j] : v[u][j];
         }
@@ -1210,13 +1220,11 @@ __global__ void __launch_bounds__(256) spatial_sum_vec_kernel(const T* __restric
     const int c = blockIdx.x * RED_CH + threadIdx.x;
     if (c < C) {
       float a = 0.f;
-#pragma unroll 8
-      for (int l = 0; l < 32; ++l) a += sm[l][threadIdx.x];
+      for (int l = 0; l < nrl; ++l) a += sm[l][threadIdx.x];
       out[(int64_t)b * C + c] = a * scale;
     }
   }
 }
-
 template <typename T>
 __global__ void __launch_bounds__(256) scale_bc_vec_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ y, int HW,
                                                            int C, const float* __restrict__ bias_bc, float bias_mul) {
@@ -1288,22 +1296,27 @@ __global__ void __launch_bounds__(256) se_fc_fwd2_kernel(const float* __restrict
     if (lane == 0) gate[(int64_t)b * C + c] = sigmoid_precise(a + b2[c]);
   }
 }
-__global__ void __launch_bounds__(256) se_fc_bwd1_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
-                                                         const float* __restrict__ hid_pre, int C, int S,
-                                                         const float* __restrict__ w2, float* __restrict__ dgp,
-                                                         float* __restrict__ dhp) {
-  __shared__ float red[8][32];
-  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef FTC_EMU
+constexpr int SE_BWD1_THREADS = 256;
+#else
+constexpr int SE_BWD1_THREADS = 1024;
+#endif
+__global__ void __launch_bounds__(1024) se_fc_bwd1_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
+                                                          const float* __restrict__ hid_pre, int C, int S,
+                                                          const float* __restrict__ w2, float* __restrict__ dgp,
+                                                          float* __restrict__ dhp) {
+  // 32 warps walk the channels (warp w: c = w, w + 32, ...), eight channels per trip with all loads issued first: C = 3 072 is 12
+  // dependent trips instead of the 384 of the first version (one channel per trip, 8 warps: 53 us per launch for a few hundred KB)
+  __shared__ float red[32][32];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int s = blockIdx.x * 32 + lane;
   const bool first = blockIdx.x == 0;              // the first s-chunk's CTA also publishes dgp (the weight kernel reads it)
   float a = 0.f;
-  // eight channels per trip with all loads issued first (the one-channel loop was a chain of dependent L2 round trips: 53 us per
-  // launch for a few hundred KB); the summation order per (warp, lane) is unchanged: c = warp, warp + 8, ...
-  for (int cb = warp; cb < C; cb += 64) {
+  for (int cb = warp; cb < C; cb += nw * 8) {
     float gt[8], dg[8], wv[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int c = cb + 8 * u;
+      const int c = cb + nw * u;
       const bool in = c < C;
       gt[u] = in ? gate[(int64_t)b * C + c] : 0.f;
       dg[u] = in ? dgate[(int64_t)b * C + c] : 0.f;
@@ -1311,7 +1324,7 @@ __global__ void __launch_bounds__(256) se_fc_bwd1_kernel(const float* __restrict
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int c = cb + 8 * u;
+      const int c = cb + nw * u;
       if (c < C) {
         const float v = dg[u] * gt[u] * (1.f - gt[u]);
         if (first && lane == 0) dgp[(int64_t)b * C + c] = v;
@@ -1323,8 +1336,7 @@ __global__ void __launch_bounds__(256) se_fc_bwd1_kernel(const float* __restrict
   __syncthreads();
   if (warp == 0 && s < S) {
     float t = red[0][lane];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) t += red[w][lane];
+    for (int w = 1; w < nw; ++w) t += red[w][lane];
     dhp[(int64_t)b * S + s] = t * act_grad(hid_pre[(int64_t)b * S + s], ACT_SILU);
   }
 }
@@ -2035,12 +2047,12 @@ int ftc_train_dwconv3x3_wgrad(const void* x, const void* dy, int dtype, int batc
   const int64_t P = (int64_t)batch * ho * wo;
   if (c % 8 == 0 && P < 0x7fffffff && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0) {
     const int cb = ceil_div(c, RED_CH);
-    int64_t sp = std::max<int64_t>(1, std::min<int64_t>((148 * 6 + cb - 1) / cb, (P + 255) / 256));
+    int64_t sp = std::max<int64_t>(1, std::min<int64_t>((148 * 6 + 3 * cb - 1) / (3 * cb), (P + 255) / 256));   // x 3 kernel rows (grid z)
     sp = std::min<int64_t>(sp, 65535);
     int64_t per = (P + sp - 1) / sp;
     per = (per + 31) / 32 * 32;
     sp = (P + per - 1) / per;
-    dim3 vgrid(cb, (unsigned)sp);
+    dim3 vgrid(cb, (unsigned)sp, 3);
     if (dtype == DT_F32)
       dw_wgrad_vec_kernel<float><<<vgrid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), batch, h, w, c, ho, wo, stride, (int)per, dw9c);
     else
@@ -2069,11 +2081,11 @@ int ftc_train_spatial_sum(const void* x, const void* y, int dtype, int batch, in
   dim3 grid(ceil_div(c, RED_CH), batch);
   if (c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
     if (dtype == DT_F32) {
-      if (y) spatial_sum_vec_kernel<float, 1><<<grid, 256, 0, s>>>(cp<float>(x), cp<float>(y), hw, c, scale, out);
-      else spatial_sum_vec_kernel<float, 0><<<grid, 256, 0, s>>>(cp<float>(x), nullptr, hw, c, scale, out);
+      if (y) spatial_sum_vec_kernel<float, 1><<<grid, SSUM_THREADS, 0, s>>>(cp<float>(x), cp<float>(y), hw, c, scale, out);
+      else spatial_sum_vec_kernel<float, 0><<<grid, SSUM_THREADS, 0, s>>>(cp<float>(x), nullptr, hw, c, scale, out);
     } else {
-      if (y) spatial_sum_vec_kernel<bf16, 1><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(y), hw, c, scale, out);
-      else spatial_sum_vec_kernel<bf16, 0><<<grid, 256, 0, s>>>(cp<bf16>(x), nullptr, hw, c, scale, out);
+      if (y) spatial_sum_vec_kernel<bf16, 1><<<grid, SSUM_THREADS, 0, s>>>(cp<bf16>(x), cp<bf16>(y), hw, c, scale, out);
+      else spatial_sum_vec_kernel<bf16, 0><<<grid, SSUM_THREADS, 0, s>>>(cp<bf16>(x), nullptr, hw, c, scale, out);
     }
     FTC_POST_LAUNCH();
     return 0;
@@ -2130,7 +2142,7 @@ int ftc_train_se_fc_bwd(const float* dgate, const float* gate, const float* hid_
   FTC_REQUIRE(dgate && gate && hid_pre && mean && w1 && w2 && dgp && dhp && dmean && dw1 && db1 && dw2 && db2, "null argument");
   FTC_REQUIRE(batch > 0 && batch <= 65535 && c > 0 && sq > 0 && sq <= 4096, "bad geometry");
   cudaStream_t s = (cudaStream_t)stream;
-  se_fc_bwd1_kernel<<<dim3(ceil_div(sq, 32), batch), 256, 0, s>>>(dgate, gate, hid_pre, c, sq, w2, dgp, dhp);
+  se_fc_bwd1_kernel<<<dim3(ceil_div(sq, 32), batch), SE_BWD1_THREADS, 0, s>>>(dgate, gate, hid_pre, c, sq, w2, dgp, dhp);
   FTC_POST_LAUNCH();
   se_fc_bwd2_kernel<<<dim3(ceil_div(c, 256), batch), 256, (size_t)sq * sizeof(float), s>>>(dhp, c, sq, w1, dmean);
   FTC_POST_LAUNCH();

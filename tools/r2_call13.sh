@@ -1,8 +1,8 @@
 #!/bin/bash
-# Round 2, GPU call 19: batched loads in dw_wgrad / spatial_sum / scale_bc / se_fc_bwd1, fewer reduce chunks: tests + train step.
+# Round 2, GPU call 21: batched loads in dw_wgrad / spatial_sum / scale_bc / se_fc_bwd1, fewer reduce chunks: tests + train step.
 set -u
 mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-.}"
-timeout 900 python -m pytest tests/test_zz_gpu_train.py -x -q > gpurun_out/r2s_pytest_train.log 2>&1; tail -4 gpurun_out/r2s_pytest_train.log
-timeout 400 python tools/bench_train.py --batch 16 --mode graph --steps 3 --warmup 1 > gpurun_out/r2s_train_b16.json 2> gpurun_out/r2s_train_b16.err
-cut -c1-400 gpurun_out/r2s_train_b16.json; tail -2 gpurun_out/r2s_train_b16.err
+timeout 900 python -m pytest tests/test_zz_gpu_train.py -x -q > gpurun_out/r2t_pytest_train.log 2>&1; tail -4 gpurun_out/r2t_pytest_train.log
+timeout 400 python tools/bench_train.py --batch 16 --mode graph --steps 3 --warmup 1 > gpurun_out/r2t_train_b16.json 2> gpurun_out/r2t_train_b16.err
+cut -c1-400 gpurun_out/r2t_train_b16.json; tail -2 gpurun_out/r2t_train_b16.err
