@@ -986,64 +986,61 @@ __global__ void __launch_bounds__(256) dw_vec_kernel(const T* __restrict__ src, 
 template <typename T>
 __global__ void __launch_bounds__(256) dw_wgrad_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, int B, int H, int W, int C,
                                                            int Ho, int Wo, int stride, int pix_per_split, float* __restrict__ dw) {
-  // blockIdx.z = kernel row ky: a CTA accumulates the three taps of one row (24 accumulators per thread instead of 72: three CTAs
-  // per SM instead of one; the all-taps version was latency-bound at one CTA per SM: 8.8 ms of a B = 16 step for 1.8 ms of traffic)
-  __shared__ float sm[8][3][RED_CH];
+  __shared__ float sm[8][9][RED_CH];
   const int ck = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int c0 = blockIdx.x * RED_CH + ck * 8;
-  const int ky = blockIdx.z;
   const int P = B * Ho * Wo;
   const int p0 = blockIdx.y * pix_per_split, p1 = min(P, p0 + pix_per_split);
-  float acc[3][8];
+  float acc[9][8];
 #pragma unroll
-  for (int t = 0; t < 3; ++t)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   if (c0 < C) {
     if constexpr (sizeof(T) == 2) {
-      // bf16: two pixels per trip, their eight 16-byte loads issued together from clamped addresses (taps outside the image are
-      // masked afterwards; boundary tests as branches around each load keep one load in flight per thread)
-      for (int p = p0 + pl; p < p1; p += 64) {
-        uint4 gv[2], xv[2][3];
+      // bf16: the ten 16-byte loads of a pixel are issued together from clamped addresses (taps outside the image are masked
+      // afterwards): with the boundary tests as branches around each load the compiler kept ONE load in flight per thread and
+      // the kernel ran at 1.4 TB/s (12.9 ms of a B = 16 step, ncu r02l).  Tried and measured slower: one kernel row per CTA (24
+      // accumulators, 4 CTAs per SM, grid z = 3): 11.2 vs 8.8 ms per step -- dy is read three times and the index arithmetic triples
+      for (int p = p0 + pl; p < p1; p += 32) {
+        const int ox = p % Wo, q = p / Wo;
+        const int oy = q % Ho, b = q / Ho;
+        const uint4 gv = *reinterpret_cast<const uint4*>(dy + (int64_t)p * C + c0);
+        uint4 xv[9];
         unsigned okm = 0;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int pp = min(p + 32 * u, p1 - 1);
-          const int ox = pp % Wo, q = pp / Wo;
-          const int oy = q % Ho, b = q / Ho;
-          gv[u] = *reinterpret_cast<const uint4*>(dy + (int64_t)pp * C + c0);
+        for (int ky = 0; ky < 3; ++ky) {
           const int iy = oy * stride - 1 + ky;
           const int iyc = min(max(iy, 0), H - 1);
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             const int ix = ox * stride - 1 + kx;
             const int ixc = min(max(ix, 0), W - 1);
-            xv[u][kx] = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + iyc) * W + ixc) * C + c0);
-            okm |= (p + 32 * u < p1 && iy == iyc && ix == ixc) ? (1u << (u * 3 + kx)) : 0u;
+            xv[ky * 3 + kx] = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + iyc) * W + ixc) * C + c0);
+            okm |= (iy == iyc && ix == ixc) ? (1u << (ky * 3 + kx)) : 0u;
           }
         }
+        float g[8];
+        unpack8(gv, g);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          float g[8];
-          unpack8(gv[u], g);
+        for (int t = 0; t < 9; ++t) {
+          float v[8];
+          unpack8(xv[t], v);
+          const float m = (okm >> t) & 1u ? 1.f : 0.f;
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            float v[8];
-            unpack8(xv[u][kx], v);
-            const float m = (okm >> (u * 3 + kx)) & 1u ? 1.f : 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[kx][j] = fmaf(g[j] * m, v[j], acc[kx][j]);
-          }
+          for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(g[j] * m, v[j], acc[t][j]);
         }
       }
     } else {
-      for (int p = p0 + pl; p < p1; p += 32) {
-        const int ox = p % Wo, q = p / Wo;
-        const int oy = q % Ho, b = q / Ho;
+    for (int p = p0 + pl; p < p1; p += 32) {
+      const int ox = p % Wo, q = p / Wo;
+      const int oy = q % Ho, b = q / Ho;
+      float g[8];
+      load8(dy + (int64_t)p * C + c0, g);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
         const int iy = oy * stride - 1 + ky;
         if (iy < 0 || iy >= H) continue;
-        float g[8];
-        load8(dy + (int64_t)p * C + c0, g);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int ix = ox * stride - 1 + kx;
@@ -1051,15 +1048,16 @@ __global__ void __launch_bounds__(256) dw_wgrad_vec_kernel(const T* __restrict__
           float v[8];
           load8(x + (((int64_t)b * H + iy) * W + ix) * C + c0, v);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[kx][j] = fmaf(g[j], v[j], acc[kx][j]);
+          for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(g[j], v[j], acc[ky * 3 + kx][j]);
         }
       }
+    }
     }
   }
   // lanes of a warp: ck = lane & 7, four pixel lanes (lane >> 3): fold them, then the eight warps through shared memory
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int t = 0; t < 3; ++t)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = acc[t][j];
@@ -1068,14 +1066,97 @@ __global__ void __launch_bounds__(256) dw_wgrad_vec_kernel(const T* __restrict__
       if (lane < 8) sm[warp][t][ck * 8 + j] = v;
     }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * RED_CH; i += 256) {
+  for (int i = threadIdx.x; i < 9 * RED_CH; i += 256) {
     const int t = i / RED_CH, cc = i - t * RED_CH;
     const int c = blockIdx.x * RED_CH + cc;
     if (c >= C) continue;
     float s = 0.f;
 #pragma unroll
     for (int l = 0; l < 8; ++l) s += sm[l][t][cc];
-    atomicAdd(dw + (int64_t)(ky * 3 + t) * C + c, s);
+    atomicAdd(dw + (int64_t)t * C + c, s);
+  }
+}
+
+// Shared-memory strip version of the depthwise weight gradient (bf16, stride 1, H % 4 == 0): CTA = 64 channels x a run of 4-row
+// strips.  Per strip the 6 input rows (zero halo columns / rows included) and the 4 dy rows arrive through cp.async (the loads in
+// flight no longer depend on registers: the register-resident version above runs at one or two CTAs per SM and is latency-bound,
+// 8.8 ms of a B = 16 step for 1.8 ms of traffic); every thread then takes pixels of the strip from shared memory: 10 conflict-free
+// 16-byte reads and 72 FMAs per (pixel, 8 channels).  The 72 accumulators live across all strips of the CTA; the final fold over
+// pixel lanes / warps and the one atomic per (tap, channel) per CTA are those of the kernel above.
+constexpr int DWS_R = 4;
+__global__ void __launch_bounds__(256) dw_wgrad_strip_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, int B, int H, int W, int C,
+                                                             int strips_per_cta, float* __restrict__ dw) {
+  extern __shared__ __align__(16) uint8_t dws_raw[];
+  const int IW = W + 2;
+  bf16* xs = reinterpret_cast<bf16*>(dws_raw);                          // [DWS_R + 2][IW][64]
+  bf16* ds = xs + (size_t)(DWS_R + 2) * IW * RED_CH;                      // [DWS_R][W][64]
+  const int tid = threadIdx.x, ck = tid & 7, pl = tid >> 3;
+  const int cb = blockIdx.x * RED_CH;
+  const int spi = H / DWS_R, n_strips = B * spi;
+  const int s0 = blockIdx.y * strips_per_cta, s1 = min(n_strips, s0 + strips_per_cta);
+  const bool live = cb + ck * 8 < C;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  for (int st = s0; st < s1; ++st) {
+    const int b = st / spi, y0 = (st - b * spi) * DWS_R;
+    for (int i = tid; i < (DWS_R + 2) * IW * 8; i += 256) {
+      const int pc = i & 7, q = i >> 3;
+      const int row = q / IW, col = q - row * IW;
+      const int iy = y0 - 1 + row, ix = col - 1;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W && cb + pc * 8 < C;
+      const bf16* src = ok ? x + (((int64_t)b * H + iy) * W + ix) * C + cb + pc * 8 : x;
+      cp_async16(xs + (size_t)q * RED_CH + pc * 8, src, ok);
+    }
+    for (int i = tid; i < DWS_R * W * 8; i += 256) {
+      const int pc = i & 7, q = i >> 3;
+      const bool ok = cb + pc * 8 < C;
+      const bf16* src = ok ? dy + (((int64_t)b * H + y0) * W + q) * C + cb + pc * 8 : dy;
+      cp_async16(ds + (size_t)q * RED_CH + pc * 8, src, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (live) {
+      for (int p = pl; p < DWS_R * W; p += 32) {
+        const int oy = p / W, ox = p - oy * W;
+        float g[8];
+        load8(ds + (size_t)p * RED_CH + ck * 8, g);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            float v[8];
+            load8(xs + ((size_t)(oy + ky) * IW + ox + kx) * RED_CH + ck * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(g[j], v[j], acc[ky * 3 + kx][j]);
+          }
+      }
+    }
+    __syncthreads();                                                      // the strip buffers are refilled next
+  }
+  float (*sm)[9][RED_CH] = reinterpret_cast<float (*)[9][RED_CH]>(dws_raw);   // 18 KB, the strip buffers are free now
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[t][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 8) sm[warp][t][ck * 8 + j] = v;
+    }
+  __syncthreads();
+  for (int i = tid; i < 9 * RED_CH; i += 256) {
+    const int t = i / RED_CH, cc = i - t * RED_CH;
+    const int c = cb + cc;
+    if (c >= C) continue;
+    float a = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) a += sm[l][t][cc];
+    atomicAdd(dw + (int64_t)t * C + c, a);
   }
 }
 
@@ -1177,7 +1258,8 @@ __global__ void __launch_bounds__(256) scale_bc_kernel(const T* __restrict__ x, 
 #ifdef FTC_EMU
 constexpr int SSUM_THREADS = 256;
 #else
-constexpr int SSUM_THREADS = 1024;    // 128 pixel lanes: (C / 64) x B CTAs are few (384 at 48 x 48 x 1536, B = 16): fill the SMs with threads
+constexpr int SSUM_THREADS = 1024;    // product sums (SE backward): 128 pixel lanes, (C / 64) x B CTAs are few (384 at 48 x 48 x 1536, B = 16):
+                                      // 5.4 -> 3.5 ms per step; the plain sums stay at 256 threads (1024: 1.8 -> 2.4 ms, the serial lane fold)
 #endif
 template <typename T, int MUL>
 __global__ void __launch_bounds__(1024) spatial_sum_vec_kernel(const T* __restrict__ x, const T* __restrict__ y, int HW, int C,
@@ -2045,14 +2127,32 @@ int ftc_train_dwconv3x3_wgrad(const void* x, const void* dy, int dtype, int batc
   const int ho = (h - 1) / stride + 1, wo = (w - 1) / stride + 1;
   FTC_CHECK_CUDA(cudaMemsetAsync(dw9c, 0, (size_t)9 * c * sizeof(float), s));
   const int64_t P = (int64_t)batch * ho * wo;
+  static const int env_strip = [] { const char* e = getenv("FTC_DW_WGRAD_STRIP"); return e ? atoi(e) : 1; }();
+  if (env_strip && dtype == DT_BF16 && stride == 1 && c % 8 == 0 && h % DWS_R == 0 && w >= 2 && w <= 128 && P < 0x7fffffff &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0) {
+    const int slabs = ceil_div(c, RED_CH);
+    const int n_strips = batch * (h / DWS_R);
+    const size_t smem = ((size_t)(DWS_R + 2) * (w + 2) + (size_t)DWS_R * w) * RED_CH * sizeof(bf16);
+    int groups = std::max(1, std::min(n_strips, (148 * 3 + slabs - 1) / slabs));
+    const int per_cta = (n_strips + groups - 1) / groups;
+    groups = (n_strips + per_cta - 1) / per_cta;
+    static bool attr_done = false;
+    if (!attr_done) {
+      FTC_CHECK_CUDA(cudaFuncSetAttribute(dw_wgrad_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+    dw_wgrad_strip_kernel<<<dim3(slabs, groups), 256, std::max<size_t>(smem, 9 * 8 * RED_CH * sizeof(float)), s>>>(cp<bf16>(x), cp<bf16>(dy), batch, h, w, c, per_cta, dw9c);
+    FTC_POST_LAUNCH();
+    return 0;
+  }
   if (c % 8 == 0 && P < 0x7fffffff && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0) {
     const int cb = ceil_div(c, RED_CH);
-    int64_t sp = std::max<int64_t>(1, std::min<int64_t>((148 * 6 + 3 * cb - 1) / (3 * cb), (P + 255) / 256));   // x 3 kernel rows (grid z)
+    int64_t sp = std::max<int64_t>(1, std::min<int64_t>((148 * 6 + cb - 1) / cb, (P + 255) / 256));
     sp = std::min<int64_t>(sp, 65535);
     int64_t per = (P + sp - 1) / sp;
     per = (per + 31) / 32 * 32;
     sp = (P + per - 1) / per;
-    dim3 vgrid(cb, (unsigned)sp, 3);
+    dim3 vgrid(cb, (unsigned)sp);
     if (dtype == DT_F32)
       dw_wgrad_vec_kernel<float><<<vgrid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), batch, h, w, c, ho, wo, stride, (int)per, dw9c);
     else
@@ -2082,10 +2182,10 @@ int ftc_train_spatial_sum(const void* x, const void* y, int dtype, int batch, in
   if (c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
     if (dtype == DT_F32) {
       if (y) spatial_sum_vec_kernel<float, 1><<<grid, SSUM_THREADS, 0, s>>>(cp<float>(x), cp<float>(y), hw, c, scale, out);
-      else spatial_sum_vec_kernel<float, 0><<<grid, SSUM_THREADS, 0, s>>>(cp<float>(x), nullptr, hw, c, scale, out);
+      else spatial_sum_vec_kernel<float, 0><<<grid, 256, 0, s>>>(cp<float>(x), nullptr, hw, c, scale, out);
     } else {
       if (y) spatial_sum_vec_kernel<bf16, 1><<<grid, SSUM_THREADS, 0, s>>>(cp<bf16>(x), cp<bf16>(y), hw, c, scale, out);
-      else spatial_sum_vec_kernel<bf16, 0><<<grid, SSUM_THREADS, 0, s>>>(cp<bf16>(x), nullptr, hw, c, scale, out);
+      else spatial_sum_vec_kernel<bf16, 0><<<grid, 256, 0, s>>>(cp<bf16>(x), nullptr, hw, c, scale, out);
     }
     FTC_POST_LAUNCH();
     return 0;

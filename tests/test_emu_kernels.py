@@ -606,3 +606,13 @@ def test_emu_row_strided_dy_is_read_in_place(emu):
     from findtextcenternet_b200 import _ops
     assert _ops._channel_slice_ld(dy, c) == wide and _ops._channel_slice_ld(dy.contiguous(), c) == 0
     assert _ops._channel_slice_ld(du, cc) == 40 and _ops._channel_slice_ld(duw[:, ::2, :, 8:24], cc) == 0
+
+
+@pytest.mark.parametrize("b,h,w,c", [(2, 8, 6, 72), (1, 4, 10, 64), (3, 12, 5, 8)])
+def test_emu_depthwise_weight_gradient_strip_kernel(emu, b, h, w, c):
+    """bf16, stride 1, H % 4 == 0: the shared-memory strip kernel (cp.async staging, zero halo) against the oracle"""
+    x = rnd(b, h, w, c, seed=1, dt=torch.bfloat16)
+    dy = rnd(b, h, w, c, seed=2, dt=torch.bfloat16)
+    dw = torch.empty(9, c)
+    ok(emu, emu.ftc_train_dwconv3x3_wgrad(P(x), P(dy), 1, b, h, w, c, 1, P(dw), None))
+    assert rel_l2(dw, TO.dwconv3x3_wgrad(x.float(), dy.float(), 1)) < 1e-5
