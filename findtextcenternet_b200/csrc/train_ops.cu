@@ -395,28 +395,6 @@ __device__ __forceinline__ void ldf8(const float* __restrict__ p, float (&v)[8])
 
 constexpr int BS_U = 4;      // row groups in flight per thread
 
-// The finishing step of a column reduction inside the reduction kernel: every CTA publishes its partial sums, takes a ticket for its
-// channel slab, and the LAST CTA of the slab adds the slab's partials in a fixed order (double) and writes the results -- the
-// separate finishing launch per BatchNorm call (724 per train step, ~3 ms of launch-bound kernels) disappears.  Tickets live in a
-// static zero-initialised device array and are reset by the CTA that finishes; consecutive launches rotate over 16 regions, so
-// launches that overlap (other streams, parallel graph branches) do not share tickets.
-constexpr int BN_TICKET_SLABS = 1024, BN_TICKET_REGIONS = 16;
-__device__ unsigned g_bn_tickets[BN_TICKET_REGIONS * BN_TICKET_SLABS];
-struct BnFinish {
-  float* out0; float* out1;   // MODE 0: mean, var;  MODE 1: sum dz, sum dz * xhat
-  RunningStats rs;            // MODE 0 only (may be all null)
-  int64_t rows;
-  unsigned* tickets;          // null: no fused finish (the caller launches col_reduce_finish_kernel)
-};
-__device__ __forceinline__ float ld_l2(const float* p) {
-#ifdef FTC_EMU
-  return *p;
-#else
-  return __ldcg(p);           // partials of other CTAs: read at L2
-#endif
-}
-
-
 template <int ACT, bool RES, int CK>
 __global__ void __launch_bounds__(256) bn_apply_stream_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t rows, int C, BnArgs bn,
                                                               const bf16* __restrict__ residual) {
@@ -463,7 +441,7 @@ __global__ void __launch_bounds__(256) bn_apply_stream_kernel(const bf16* __rest
 // MODE 0: sum x, sum x^2;  MODE 1: sum dz, sum dz * xhat with dz = dy * act'(gamma * xhat + beta).  part[q][blockIdx.y][C]
 template <int MODE, int ACT, int CK>
 __global__ void __launch_bounds__(256) bn_reduce_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, int64_t rows, int C,
-                                                               float* __restrict__ part, BnArgs bn, int64_t ldy, BnFinish fin) {   // ldy: dy row stride
+                                                               float* __restrict__ part, BnArgs bn, int64_t ldy) {   // ldy: dy row stride
   constexpr int RL = 256 / CK;
   __shared__ float sm[2][RL][CK * 8 + 1];
   const int ck = threadIdx.x % CK, rl = threadIdx.x / CK;
@@ -527,52 +505,6 @@ __global__ void __launch_bounds__(256) bn_reduce_stream_kernel(const bf16* __res
       part[((int64_t)q * gridDim.y + blockIdx.y) * C + c] = acc;
     }
   }
-  if (fin.tickets == nullptr) return;
-  // ---- fused finish: the last CTA of this channel slab folds the slab's partials ----
-  __shared__ int s_last;
-  __shared__ double tot[2][CK * 8];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(fin.tickets + blockIdx.x, 1u) == gridDim.y - 1 ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  {
-    constexpr int NPAIR = 2 * CK * 8, G = 256 / NPAIR;       // G adjacent threads share one (quantity, channel) pair
-    const int pair = threadIdx.x / G, sub = threadIdx.x % G;
-    const int q = pair / (CK * 8), cl = pair % (CK * 8);
-    const int c = blockIdx.x * CK * 8 + cl;
-    double a = 0.0;
-    if (c < C)
-      for (int k = sub; k < (int)gridDim.y; k += G) a += (double)ld_l2(part + ((int64_t)q * gridDim.y + k) * C + c);
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (sub == 0) tot[q][cl] = a;
-  }
-  __syncthreads();
-  if (threadIdx.x < CK * 8) {
-    const int c = blockIdx.x * CK * 8 + threadIdx.x;
-    if (c < C) {
-      const double a = tot[0][threadIdx.x], b = tot[1][threadIdx.x];
-      if (MODE == 0) {
-        const double m = a / (double)fin.rows;
-        const double v = b / (double)fin.rows - m * m;
-        const float mf = (float)m, vf = (float)(v > 0.0 ? v : 0.0);
-        fin.out0[c] = mf;
-        fin.out1[c] = vf;
-        if (fin.rs.mean != nullptr) {   // running statistics as col_reduce_finish_kernel<0> updates them
-          const float unbiased = vf * ((float)fin.rows / (float)(fin.rows > 1 ? fin.rows - 1 : 1));
-          fin.rs.mean[c] = fmaf(fin.rs.momentum, mf, fin.rs.mean[c] * (1.0f - fin.rs.momentum));
-          fin.rs.var[c] = fmaf(fin.rs.momentum, unbiased, fin.rs.var[c] * (1.0f - fin.rs.momentum));
-          if (c == 0 && fin.rs.count != nullptr) *fin.rs.count += 1;
-        }
-      } else {
-        fin.out0[c] = (float)a;
-        fin.out1[c] = (float)b;
-      }
-    }
-  }
-  if (threadIdx.x == 0) fin.tickets[blockIdx.x] = 0;          // ready for the next launch that rotates onto this region
 }
 
 template <int ACT, int CK>
@@ -634,23 +566,6 @@ inline dim3 stream_grid(int64_t rows, int c, int ck, int64_t max_y, int ctas_per
   return dim3((unsigned)slabs, (unsigned)y);
 }
 inline int stream_ck(int c) { return (c % 64 == 0) ? 8 : 4; }
-// ticket region of the next reduction launch (null when the slab count exceeds a region or the fused finish is switched off)
-inline unsigned* bn_ticket_region(int slabs) {
-  static const int on = [] { const char* e = getenv("FTC_BN_FUSED_FINISH"); return e ? atoi(e) : 1; }();
-  if (!on || slabs > BN_TICKET_SLABS) return nullptr;
-  static unsigned* base = nullptr;
-  static unsigned turn = 0;
-  if (base == nullptr) {
-#ifdef FTC_EMU
-    base = g_bn_tickets;
-#else
-    void* p = nullptr;
-    if (cudaGetSymbolAddress(&p, g_bn_tickets) != cudaSuccess) return nullptr;
-    base = static_cast<unsigned*>(p);
-#endif
-  }
-  return base + (size_t)(turn++ % BN_TICKET_REGIONS) * BN_TICKET_SLABS;
-}
 
 #define FTC_BN_ACT_SWITCH(act, CALL)            \
   do {                                          \
@@ -1938,14 +1853,11 @@ static int bn_stats_impl(const void* x, int dtype, int64_t rows, int c, float* m
   if (vec && dtype == DT_BF16 && c % 32 == 0 && bn_unroll() == 0) {
     const int ck = stream_ck(c);
     const dim3 sg = stream_grid(rows, c, ck, nchunk, 3);   // all CTAs resident; few partial rows for the finish
-    const BnFinish fin = {mean, var, rs, rows, bn_ticket_region((int)sg.x)};
-    if (ck == 8) bn_reduce_stream_kernel<0, ACT_NONE, 8><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn, c, fin);
-    else bn_reduce_stream_kernel<0, ACT_NONE, 4><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn, c, fin);
+    if (ck == 8) bn_reduce_stream_kernel<0, ACT_NONE, 8><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn, c);
+    else bn_reduce_stream_kernel<0, ACT_NONE, 4><<<sg, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, (float*)scratch, bn, c);
     FTC_POST_LAUNCH();
-    if (fin.tickets == nullptr) {
-      col_reduce_finish_kernel<0><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, (int)sg.y, c, rows, mean, var, rs);
-      FTC_POST_LAUNCH();
-    }
+    col_reduce_finish_kernel<0><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, (int)sg.y, c, rows, mean, var, rs);
+    FTC_POST_LAUNCH();
     return 0;
   }
   if (vec && dtype == DT_F32)
@@ -2036,16 +1948,13 @@ int ftc_train_bn_act_bwd_ld(const void* x, const void* dy, int64_t dy_ld, void* 
     const int ck = stream_ck(c);
     const dim3 rg = stream_grid(rows, c, ck, nchunk, 6);   // (2 per SM measured slower: 27.5 vs 24.5 ms per step, tools/bench_bn.py)
 #define BN_RED(A)                                                                                                                  \
-    if (ck == 8) bn_reduce_stream_kernel<1, A, 8><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn, dy_ld, fin);   \
-    else bn_reduce_stream_kernel<1, A, 4><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn, dy_ld, fin);
-    const BnFinish fin = {dbeta, dgamma, RunningStats{nullptr, nullptr, nullptr, 0.f}, rows, bn_ticket_region((int)rg.x)};
+    if (ck == 8) bn_reduce_stream_kernel<1, A, 8><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn, dy_ld);        \
+    else bn_reduce_stream_kernel<1, A, 4><<<rg, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, (float*)scratch, bn, dy_ld);
     FTC_BN_ACT_SWITCH(act, BN_RED);
 #undef BN_RED
     FTC_POST_LAUNCH();
-    if (fin.tickets == nullptr) {
-      col_reduce_finish_kernel<1><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, (int)rg.y, c, rows, dbeta, dgamma, RunningStats{nullptr, nullptr, nullptr, 0.f});
-      FTC_POST_LAUNCH();
-    }
+    col_reduce_finish_kernel<1><<<ceil_div(c, 32), 1024, 0, s>>>((const float*)scratch, (int)rg.y, c, rows, dbeta, dgamma, RunningStats{nullptr, nullptr, nullptr, 0.f});
+    FTC_POST_LAUNCH();
     const float inv_rows_s = (float)(1.0 / (double)rows);
     const dim3 ag = stream_grid(rows, c, ck, 1 << 30);
 #define BN_BWD(A)                                                                                                                              \

@@ -91,7 +91,6 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 #define blockDim (emu::b_dim)
 #define gridDim (emu::g_dim)
 
-inline void __threadfence() {}
 inline void __syncthreads() { emu::blk->bar->arrive_and_wait(); }
 inline void __syncwarp() { emu::blk->wbar[emu::t_lin >> 5]->arrive_and_wait(); }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o) {
