@@ -418,11 +418,8 @@ int conv_gemm_tc_plan(const ConvGemmParams& p, ConvTcPlan* plan, bool allow_tma)
       // K <= 256 with many n-tiles (MBConv expand 192->768, 256->1536): 192-wide n-tiles keep the resident weight tile at
       // <= 96 KB under the weight-stationary schedule, which leaves room for a deeper activation ring (measured 89 vs 103 us)
       if (nGA <= 4 && p.N % 192 == 0 && p.N >= 768 && plan->BN > 192 && gemm_tuning().plan_bn == 0) { plan->BN = 192; plan->NT = p.N / 192; }
-      // K in (256, 512]: a 128-wide n-tile lets the weight-stationary schedule keep [128 x K] resident (conv_gemm_tma.cu)
-      // (measured slower on B200 for K = 512, N = 3072, M = 18432: 0.127 vs 0.078 ms -- off unless FTC_BSTAT_BN=1)
-      if (nGA > 4 && nGA <= 8 && plan->BN > 128 && p.N % 128 == 0 && p.N >= 1024 && getenv("FTC_BSTAT_BN")) {
-        plan->BN = 128; plan->NT = p.N / 128;
-      }
+      // (K in (256, 512] with 128-wide n-tiles so that [128 x K] stays resident was measured slower: 0.127 vs 0.078 ms at
+      // K = 512, N = 3072, M = 18432; removed)
     } else if (p.pad == 1 && strides_ok && chunks_ok && p.H % 8 == 0 && !(env_no_tma & 4)) {
       plan->tma = TMA_HALO; plan->nGA = nGA; plan->nGB = nGB; plan->NKB = 9 * (nGA + nGB);
       // <= 32 input channels (stage 1): 32-wide k-blocks; padding to 64 doubled the MMA count and every tcgen05.mma streams

@@ -371,12 +371,9 @@ int ftc_detector::build() {
   };
   int heat_ch = 0;
   for (int h = 0; h < NH - 1; ++h) { heat_ch += c.head_out[h]; FTC_REQUIRE(c.head_out[h] <= 2, "small head out_dim <= 2"); }
-  const char* tops_env = getenv("FTC_TOPS_GEMM");
-  const bool tops_gemm = use_tc && allow_tma && tops_env && atoi(tops_env) != 0;
-  if (tops_gemm) {
-    add_top(0, NH - 1, 16, BUF_EXT_HEAT9, heat_ch);
-  } else {
-    // the eight small heads: dedicated bandwidth kernel (head_top_conv), fp32 tap-major weights
+  {
+    // the eight small heads: dedicated bandwidth kernel (head_top_conv), fp32 tap-major weights (as one grouped N = 16 tcgen05
+    // GEMM they took 3.1 instead of 1.5 ms; that route was removed)
     Op op; op.type = Op::TOPS; op.bufIn = ybuf; op.H = Hq; op.W = Wq; op.n_heads = NH - 1; op.head0 = 0; op.pix_stride = NT;
     op.out_ch = heat_ch;
     for (int h = 0; h < NH - 1; ++h) op.od[h] = c.head_out[h];

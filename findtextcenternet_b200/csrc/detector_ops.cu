@@ -418,178 +418,6 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
   }
 }
 
-// ---- bf16 product version of the strip kernel: the 3x3 taps run on the warp-level tensor cores -------------------------
-// The CUDA-core strip kernel above is instruction-issue bound (ncu: 70 % issue-active, 28 % DRAM).  Here a depthwise conv
-// becomes a block-diagonal GEMM per 8-channel group:  D[16 px, 8 ch] += A[16 px, (2 taps x 8 ch)] * B[(2 taps x 8 ch), 8 ch]
-// with B[(t, c), c'] = w[t][c] * (c == c').  Seven eighths of the MMA is multiplication by zero, but the tensor pipe is idle
-// anyway and one ldmatrix.x4 + one mma.sync replace ~60 unpack/FMA instructions: 0.3 instead of 0.6 warp-instructions per
-// output.  Pixels are the strip's FLATTENED (row, column-with-halo) index, so every tap is a constant address offset and
-// an M tile is any 16 consecutive flat pixels (halo columns produce garbage that is masked at the store).
-// Shared-memory pixels are padded to 40 channels (80 B) so that the 8 row addresses of an ldmatrix hit distinct banks.
-template <int TH>
-__global__ void __launch_bounds__(512, 2) dwconv3x3_strip_mma_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int H, int W, int C,
-                                                                     const float* __restrict__ w, const float* __restrict__ scale,
-                                                                     const float* __restrict__ bias, const float* __restrict__ w1,
-                                                                     int S, float inv_hw, float* __restrict__ hid_pre, int wpg) {
-  extern __shared__ __align__(16) unsigned char dw_smem[];
-  constexpr int CB = 32, PS = 40;                       // channels per CTA, padded pixel stride (elements)
-  const int IW = W + 2;
-  const int strip_px = (TH + 2) * IW + 2;               // one pad pixel in front and behind (tap offsets of the halo columns)
-  bf16* ring = reinterpret_cast<bf16*>(dw_smem);        // [2][strip_px][PS]
-  float* red = reinterpret_cast<float*>(dw_smem + (size_t)2 * strip_px * PS * sizeof(bf16));   // [nwarps][CB] then mean[CB]
-  const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, cb = blockIdx.x * CB;
-  const bf16* img = in + (int64_t)b * H * W * C + cb;
-  bf16* oimg = out + (int64_t)b * H * W * C + cb;
-  const int nstrips = H / TH;
-  const int row_items = IW * 4;                         // 16-byte pieces per tile row (4 per pixel)
-  const uint32_t row_inv = (1u << 20) / (uint32_t)row_items + 1u;
-  const uint32_t iw_inv = (1u << 20) / (uint32_t)IW + 1u;
-  auto prefetch = [&](int s) {
-    bf16* dst = ring + (size_t)(s & 1) * strip_px * PS + PS;      // skip the front pad pixel
-    const int iy0 = s * TH - 1;
-    for (int i = tid; i < (TH + 2) * row_items; i += nthr) {
-      const int py = (int)(((uint32_t)i * row_inv) >> 20);
-      const int j = i - py * row_items;
-      const int px = j >> 2, piece = j & 3;
-      const int iy = iy0 + py, ix = px - 1;
-      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-      const bf16* src = ok ? img + ((int64_t)iy * W + ix) * C + piece * 8 : img;
-      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + (size_t)(py * IW + px) * PS + piece * 8);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16u : 0u) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  prefetch(0);
-  // this warp's 16-channel half and its B fragments: two 8-channel groups x 5 k-steps (taps 2j, 2j+1; tap 9 = zero)
-  const int grp = warp / wpg, wig = warp - grp * wpg;   // channel half (0/1), warp index inside the half
-  const int c16 = grp * 16;
-  uint32_t bf[2][5][2];
-  {
-    const int n = lane >> 2, kq = (lane & 3) * 2;
-#pragma unroll
-    for (int g8 = 0; g8 < 2; ++g8)
-#pragma unroll
-      for (int j = 0; j < 5; ++j)
-#pragma unroll
-        for (int hi = 0; hi < 2; ++hi) {
-          const int tap = 2 * j + hi;
-          float w0 = 0.f, w1v = 0.f;
-          if (tap < 9 && (n >> 1) == (lane & 3)) {
-            const float wv = __ldg(w + tap * C + cb + c16 + g8 * 8 + n);
-            if (n == kq) w0 = wv; else w1v = wv;
-          }
-          __nv_bfloat162 pk = __floats2bfloat162_rn(w0, w1v);
-          bf[g8][j][hi] = *reinterpret_cast<uint32_t*>(&pk);
-        }
-  }
-  // ldmatrix row address of this lane: matrix (lane>>3): pixels (lane&7) + 8*((lane>>3)&1), tap 2j + (lane>>4)
-  int toff[5];
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    int tap = 2 * j + (lane >> 4);
-    if (tap > 8) tap = 8;
-    toff[j] = ((tap / 3) * IW + (tap % 3) + (lane & 7) + 8 * ((lane >> 3) & 1)) * (PS * 2);   // bytes; "- 1 + pad pixel" cancel
-  }
-  // epilogue constants: after the pair exchange this lane owns 4 consecutive channels
-  const int q = lane & 3;
-  const int ch4 = c16 + ((q & 1) ? 8 : 0) + (q >> 1) * 4;       // lanes q = 0,1,2,3 -> channels 0-3, 8-11, 4-7, 12-15
-  float sc[4], bi[4], ssum[4] = {0.f, 0.f, 0.f, 0.f};
-  load4(scale + cb + ch4, sc); load4(bias + cb + ch4, bi);
-  const int ntiles = (TH * IW + 15) / 16;
-  for (int s = 0; s < nstrips; ++s) {
-    if (s + 1 < nstrips) {
-      prefetch(s + 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ring + (size_t)(s & 1) * strip_px * PS) + (uint32_t)(c16 * 2);
-    for (int t = wig; t < ntiles; t += wpg) {
-      const int q0 = t * 16;
-      float acc[2][4];
-#pragma unroll
-      for (int g8 = 0; g8 < 2; ++g8)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[g8][e] = 0.f;
-      const uint32_t tb = sbase + (uint32_t)(q0 * PS * 2);
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-#pragma unroll
-        for (int g8 = 0; g8 < 2; ++g8) {
-          uint32_t a0, a1, a2, a3;
-          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(tb + (uint32_t)toff[j] + (uint32_t)(g8 * 16)) : "memory");
-          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                       : "+f"(acc[g8][0]), "+f"(acc[g8][1]), "+f"(acc[g8][2]), "+f"(acc[g8][3])
-                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf[g8][j][0]), "r"(bf[g8][j][1]));
-        }
-      }
-      // pair exchange: lane (q even) keeps group-0 pairs and takes its right neighbour's; odd lanes the group-1 pairs.
-      // acc[g][0..1] = pixel (lane>>2), channels g*8 + 2q, +1 ; acc[g][2..3] = pixel (lane>>2) + 8
-      float v[2][4];                                     // [pixel half][4 consecutive channels]
-      {
-        const bool odd = q & 1;
-#pragma unroll
-        for (int hp = 0; hp < 2; ++hp) {
-          const float s0 = odd ? acc[0][2 * hp] : acc[1][2 * hp], s1 = odd ? acc[0][2 * hp + 1] : acc[1][2 * hp + 1];
-          const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-          if (odd) { v[hp][0] = r0; v[hp][1] = r1; v[hp][2] = acc[1][2 * hp]; v[hp][3] = acc[1][2 * hp + 1]; }
-          else { v[hp][0] = acc[0][2 * hp]; v[hp][1] = acc[0][2 * hp + 1]; v[hp][2] = r0; v[hp][3] = r1; }
-        }
-      }
-#pragma unroll
-      for (int hp = 0; hp < 2; ++hp) {
-        const int qq = q0 + (lane >> 2) + 8 * hp;        // flat output pixel: row y, halo column x'
-        const int y = (int)(((uint32_t)qq * iw_inv) >> 20);
-        const int xp = qq - y * IW;
-        const bool valid = y < TH && xp >= 1 && xp <= W;
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          o[e] = silu_tanh_f(fmaf(v[hp][e], sc[e], bi[e]));
-          ssum[e] += valid ? o[e] : 0.f;
-        }
-        if (valid) store4(oimg + ((int64_t)(s * TH + y) * W + (xp - 1)) * C + ch4, o);
-      }
-    }
-    __syncthreads();                                    // the strip buffer is refilled two iterations later
-  }
-  // ---- squeeze: reduce over the 8 pixel rows of the fragment (lanes with equal q), then over warps ----
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float t = ssum[e];
-    t += __shfl_xor_sync(0xffffffffu, t, 4); t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
-    ssum[e] = t;
-  }
-  const int nwarps = nthr >> 5;
-  if (lane < 4) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) red[warp * CB + ch4 + e] = ssum[e];
-  }
-  // a warp only touched its own 16-channel half: zero the other half of its row
-  if (lane >= 4 && lane < 20) red[warp * CB + (grp ? 0 : 16) + (lane - 4)] = 0.f;
-  __syncthreads();
-  float* mean = red + (size_t)nwarps * CB;
-  if (tid < CB) {
-    float t = 0.f;
-    for (int wq = 0; wq < nwarps; ++wq) t += red[wq * CB + tid];
-    mean[tid] = t * inv_hw;
-  }
-  __syncthreads();
-  for (int sidx = tid; sidx < S; sidx += nthr) {
-    const float* wr = w1 + (int64_t)sidx * C + cb;
-    float t = 0.f;
-#pragma unroll
-    for (int c = 0; c < CB; c += 4) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + c));
-      t = fmaf(wv.x, mean[c], t); t = fmaf(wv.y, mean[c + 1], t); t = fmaf(wv.z, mean[c + 2], t); t = fmaf(wv.w, mean[c + 3], t);
-    }
-    hid_pre[((int64_t)b * gridDim.x + blockIdx.x) * S + sidx] = t;   // this CTA's 32-channel share (summed in order by se_fc2_hid)
-  }
-}
-
 bool dwconv3x3_se_supported(int H, int W, int C, int stride) {
   return stride == 1 && W * 8 <= 384 && W >= 4 && W % 2 == 0 && H % 8 == 0 && C % 32 == 0;
 }
@@ -622,13 +450,11 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
     if (raw_mode) FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH, true>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip)); \
     else FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH, false>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip)); \
   } while (0)
-  // the mma.sync variant is correct but measured SLOWER on B200 (0.26 vs 0.17 ms at 48x48x1536, B=32: its BN/SiLU/SE
-  // epilogue and fragment exchange cost as many issue slots as the FMAs they replace); kept behind FTC_DW_MMA=1
-  static int env_mma = -1;
-  if (env_mma < 0) { const char* e = getenv("FTC_DW_MMA"); env_mma = e ? atoi(e) : 0; }
+  // (an mma.sync variant of this kernel was measured slower on B200 -- 0.26 vs 0.17 ms at 48x48x1536, B = 32: its BN / SiLU / SE
+  // epilogue and fragment exchange cost as many issue slots as the FMAs they replace -- and was removed)
   static int env_th12 = -1;
   if (env_th12 < 0) { const char* e = getenv("FTC_DW_TH12"); env_th12 = e ? atoi(e) : 1; }   // default on (measured 6.6 vs 7.1 ms)
-  if (dtype == DT_BF16 && !env_mma && env_th12 && H % 12 == 0) {
+  if (dtype == DT_BF16 && env_th12 && H % 12 == 0) {
     // 12-row strips: 14/12 instead of 10/8 rows loaded per output row, fewer strip turn-arounds; 90 KB of shared memory
     constexpr int TH12 = 12;
     const size_t smem12 = 2 * (size_t)(TH12 + 2) * (W + 2) * 32 * es + (size_t)(W + 1) * 32 * sizeof(float) + 16 + 128;
@@ -645,18 +471,7 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
     else FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<bf16, TH12, false>, grid, dim3(threads), smem12, s, tm12, (bf16*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip));
   }
   else if (dtype == DT_F32) DWS_LAUNCH(float);
-  else if (!env_mma) DWS_LAUNCH(bf16);
-  else {
-    // tensor-core variant: warps-per-channel-half so that the M tiles of a strip split into equal rounds of <= 6
-    const int ntiles = (TH * (W + 2) + 15) / 16;
-    const int rounds = (ntiles + 5) / 6;
-    const int wpg = (ntiles + rounds - 1) / rounds;
-    const int thr = 2 * wpg * 32;
-    const size_t smem2 = 2 * (size_t)((TH + 2) * (W + 2) + 2) * 40 * 2 + (size_t)(2 * wpg + 1) * 32 * sizeof(float) + 16 * 80;   // + M-tile round-up overrun of the last taps (garbage rows)
-    static bool done2 = false;
-    if (!done2) { FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_mma_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done2 = true; }
-    dwconv3x3_strip_mma_kernel<TH><<<grid, thr, smem2, s>>>((const bf16*)in, (bf16*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, wpg);
-  }
+  else DWS_LAUNCH(bf16);
 #undef DWS_LAUNCH
   FTC_POST_LAUNCH();
   return 0;

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const T* __restrict__ x
 // above remain for odd channel counts.  Reduction CTA = 8 chunk lanes (64 channels, one 128-byte line of bf16 per row) x 32
 // row lanes.
 template <typename T, int MODE, int U>
-__global__ void __launch_bounds__(256, U >= 4 ? 2 : (U == 2 ? 3 : 3)) col_reduce_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t rows, int C,
+__global__ void __launch_bounds__(256, 3) col_reduce_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t rows, int C,
                                                              int64_t rows_per_chunk, float* __restrict__ part, BnArgs bn) {
   __shared__ float sm[2][32][RED_CH + 1];
   const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256, U >= 4 ? 2 : (U == 2 ? 3 : 3)) col_reduce
 }
 
 template <typename T, int U>
-__global__ void __launch_bounds__(256, U >= 4 ? 2 : (U == 2 ? 3 : 3)) bn_act_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int C, BnArgs bn,
+__global__ void __launch_bounds__(256, 3) bn_act_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int C, BnArgs bn,
                                                          const T* __restrict__ residual) {
   // thread = (chunk lane ck, row lane rl): a warp touches 4 rows x one 64-channel run (full 128-byte lines); grid.y walks the
   // 64-channel slabs, so a thread's eight (scale, shift) pairs are loop invariants
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256, U >= 4 ? 2 : (U == 2 ? 3 : 3)) bn_act_vec
 }
 
 template <typename T, int U>
-__global__ void __launch_bounds__(256, U >= 4 ? 2 : (U == 2 ? 3 : 3)) bn_act_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
                                                              int64_t rows, int C, float inv_rows, BnArgs bn,
                                                              const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat) {
   const int ck = threadIdx.x & 7, rl = threadIdx.x >> 3;
@@ -1799,8 +1799,8 @@ unsigned ew_rows_grid(int64_t rows, int slabs) {
   return (unsigned)(x > 0 ? x : 1);
 }
 
-// bf16 BatchNorm kernels: FTC_BN_UNROLL = 0 stream kernels (default) | 1 | 2 | 4 rows per loop trip of the earlier vector kernels
-// (kept for the A/B in tools/bench_bn.py)
+// bf16 BatchNorm kernels: FTC_BN_UNROLL = 0 stream kernels (default) | 1 the earlier one-row-per-trip vector kernels (A/B in
+// tools/bench_bn.py; they also serve fp32 and channel counts that are not multiples of 32)
 int g_bn_unroll = -1;
 int bn_unroll() {
   if (g_bn_unroll >= 0) return g_bn_unroll;
@@ -1862,10 +1862,6 @@ static int bn_stats_impl(const void* x, int dtype, int64_t rows, int c, float* m
   }
   if (vec && dtype == DT_F32)
     col_reduce_vec_kernel<float, 0, 1><<<grid, 256, 0, s>>>(cp<float>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
-  else if (vec && bn_unroll() >= 4)
-    col_reduce_vec_kernel<bf16, 0, 4><<<grid, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
-  else if (vec && bn_unroll() == 2)
-    col_reduce_vec_kernel<bf16, 0, 2><<<grid, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
   else if (vec)
     col_reduce_vec_kernel<bf16, 0, 1><<<grid, 256, 0, s>>>(cp<bf16>(x), nullptr, rows, c, rpc, (float*)scratch, bn);
   else if (dtype == DT_F32)
@@ -1907,10 +1903,6 @@ int ftc_train_bn_act(const void* x, void* y, int dtype, int64_t rows, int c, con
   }
   if (vec && dtype == DT_F32)
     bn_act_vec_kernel<float, 1><<<vgrid, 256, 0, s>>>(cp<float>(x), mp<float>(y), rows, c, bn, cp<float>(residual));
-  else if (vec && bn_unroll() >= 4)
-    bn_act_vec_kernel<bf16, 4><<<vgrid, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, cp<bf16>(residual));
-  else if (vec && bn_unroll() == 2)
-    bn_act_vec_kernel<bf16, 2><<<vgrid, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, cp<bf16>(residual));
   else if (vec)
     bn_act_vec_kernel<bf16, 1><<<vgrid, 256, 0, s>>>(cp<bf16>(x), mp<bf16>(y), rows, c, bn, cp<bf16>(residual));
   else if (dtype == DT_F32)
@@ -1967,10 +1959,6 @@ int ftc_train_bn_act_bwd_ld(const void* x, const void* dy, int64_t dy_ld, void* 
   }
   if (vec && dtype == DT_F32)
     col_reduce_vec_kernel<float, 1, 1><<<grid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), rows, c, rpc, (float*)scratch, bn);
-  else if (vec && bn_unroll() >= 4)
-    col_reduce_vec_kernel<bf16, 1, 4><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
-  else if (vec && bn_unroll() == 2)
-    col_reduce_vec_kernel<bf16, 1, 2><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
   else if (vec)
     col_reduce_vec_kernel<bf16, 1, 1><<<grid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), rows, c, rpc, (float*)scratch, bn);
   else if (dtype == DT_F32)
@@ -1985,10 +1973,6 @@ int ftc_train_bn_act_bwd_ld(const void* x, const void* dy, int64_t dy_ld, void* 
   const dim3 vgrid(ew_rows_grid(rows, ceil_div(c, RED_CH)), ceil_div(c, RED_CH));
   if (vec && dtype == DT_F32)
     bn_act_bwd_vec_kernel<float, 1><<<vgrid, 256, 0, s>>>(cp<float>(x), cp<float>(dy), mp<float>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
-  else if (vec && bn_unroll() >= 4)
-    bn_act_bwd_vec_kernel<bf16, 4><<<vgrid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
-  else if (vec && bn_unroll() == 2)
-    bn_act_bwd_vec_kernel<bf16, 2><<<vgrid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
   else if (vec)
     bn_act_bwd_vec_kernel<bf16, 1><<<vgrid, 256, 0, s>>>(cp<bf16>(x), cp<bf16>(dy), mp<bf16>(dx), rows, c, inv_rows, bn, dbeta, dgamma);
   else if (dtype == DT_F32)

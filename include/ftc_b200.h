@@ -427,7 +427,8 @@ int ftc_distort_batch(float* image, int batch, const ftc_distort_sample* samples
 /* debug / staging: route bf16 weight gradients (cin, cout multiples of 8) through the mma.sync kernel: 1 on, 0 off, -1 follow the
  * FTC_WGRAD_MMA environment variable (default; off when unset) */
 int ftc_debug_set_wgrad_mma(int on);
-/* debug / tuning: rows per loop trip of the bf16 BatchNorm train kernels (1 | 2 | 4; -1 = FTC_BN_UNROLL, default 1) */
+/* debug / tuning: bf16 BatchNorm train kernels: 0 = stream kernels (default), 1 = the earlier one-row-per-trip vector kernels;
+ * -1 = follow FTC_BN_UNROLL */
 int ftc_debug_set_bn_unroll(int u);
 /* debug / staging: the tcgen05 weight gradient: 0 off, 1 on (three N = 64 row-tap instructions per column shift), 2 on with the
  * three row taps fused into one N = 192 instruction, -1 follow the FTC_WGRAD_TC environment variable (default 2) */
