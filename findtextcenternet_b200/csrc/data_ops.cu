@@ -17,7 +17,7 @@
 // Arithmetic follows the generated C of the Cython source operation by operation: float32 with round-to-nearest intrinsics (no
 // FMA contraction), and double where the source promotes ("1 - dx" is emitted as 1.0 - dx, "rx + 0.5", the colour blend).
 // expf / logf are evaluated in double and rounded (<= 1 ulp from any libm).
-// Plain SIMT on purpose: oracle/emu compiles this file for host threads (tests/test_emu_kernels.py).
+// Plain SIMT on purpose: the CPU kernel-emulation build compiles this file for host threads (tests/test_processer.py).
 #include "../../include/ftc_b200.h"
 #include "common.cuh"
 
