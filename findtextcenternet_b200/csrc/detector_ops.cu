@@ -285,10 +285,7 @@ template <typename T, int TH, bool RAW>
 __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmIn, T* __restrict__ out, int H, int W, int C,
                                                               const float* __restrict__ w, const float* __restrict__ scale,
                                                               const float* __restrict__ bias, const float* __restrict__ w1,
-                                                              int S, float inv_hw, float* __restrict__ hid_pre, int flip, int B, int ipc) {
-  // ipc = images per CTA: the CTA keeps its 32 channels (weights, BN constants in registers) and walks `ipc` consecutive images
-  // with ONE strip ring running across them -- the first strip of the next image is in flight while the squeeze / fc1 share of the
-  // current one is computed.  At 24 x 24 a CTA's streaming time (74 KB in + out) was about the size of its start-up and epilogue.
+                                                              int S, float inv_hw, float* __restrict__ hid_pre, int flip) {
   extern __shared__ __align__(16) unsigned char dw_smem_raw[];
   // TMA destinations need 128-byte alignment; the dynamic shared window only guarantees 16
   unsigned char* dw_smem = dw_smem_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(dw_smem_raw) & 127u)) & 127u);
@@ -300,10 +297,9 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
   T* ring = reinterpret_cast<T*>(dw_smem);              // [2][(TH+2)][IW][CB]
   float* red = reinterpret_cast<float*>(dw_smem + (size_t)2 * strip_elems * sizeof(T));   // [W][CB] then mean[CB]
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int b0 = blockIdx.y * ipc, cb = blockIdx.x * CB;
-  const int nimg = min(ipc, B - b0);
+  const int b = blockIdx.y, cb = blockIdx.x * CB;
+  T* oimg = out + (int64_t)b * H * W * C + cb;
   const int nstrips = H / TH;
-  const int total = nimg * nstrips;                     // strips of this CTA, numbered across its images
   // strip loader: ONE TMA tensor box per strip -- (TH+2) rows x (W+2) pixels x 32 channels of image b, issued by one thread;
   // out-of-bounds zero fill is the conv padding.  (The cp.async version spent ~20 % of the kernel's issue slots on its
   // address arithmetic.)
@@ -318,14 +314,13 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
   pdl_launch_dependents();
   pdl_wait();
   const uint32_t strip_bytes = (uint32_t)(strip_elems * sizeof(T));
-  auto prefetch = [&](int g) {                          // g: CTA-wide strip number = image * nstrips + strip
+  auto prefetch = [&](int s) {
     if (tid == 0) {
-      const int gi = g / nstrips, gs = g - gi * nstrips;
-      const uint32_t bar = bar0 + 8u * (uint32_t)(g & 1);
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (size_t)(g & 1) * strip_elems);
+      const uint32_t bar = bar0 + 8u * (uint32_t)(s & 1);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (size_t)(s & 1) * strip_elems);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(strip_bytes) : "memory");
       asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                   ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmIn)), "r"(cb), "r"(-1), "r"(gs * TH - 1), "r"(b0 + gi), "r"(bar) : "memory");
+                   ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmIn)), "r"(cb), "r"(-1), "r"(s * TH - 1), "r"(b), "r"(bar) : "memory");
     }
   };
   auto wait_strip = [&](int s) {
@@ -349,16 +344,12 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
   for (int t = 0; t < 9; ++t) load4p(w + ((RAW && flip) ? 8 - t : t) * C + c0, wk[t]);      // flip: taps rotated 180 degrees (data gradient)
   if (!raw) { load4p(scale + c0, sc); load4p(bias + c0, bi); }
   else { sc[0] = sc[1] = pk2(1.f, 1.f); bi[0] = bi[1] = pk2(0.f, 0.f); }
-  const f32x2 half2 = pk2(0.5f, 0.5f);
-  for (int img = 0; img < nimg; ++img) {
-  const int b = b0 + img;
-  T* oimg = out + (int64_t)b * H * W * C + cb;
   ssum[0] = ssum[1] = pk2(0.f, 0.f);
+  const f32x2 half2 = pk2(0.5f, 0.5f);
   for (int s = 0; s < nstrips; ++s) {
-    const int g = img * nstrips + s;
-    if (g + 1 < total) prefetch(g + 1);
-    wait_strip(g);
-    const T* tcol = ring + (size_t)(g & 1) * strip_elems + (size_t)col * CB + quad * 4;
+    if (s + 1 < nstrips) prefetch(s + 1);
+    wait_strip(s);
+    const T* tcol = ring + (size_t)(s & 1) * strip_elems + (size_t)col * CB + quad * 4;
     f32x2 r[3][3][2];
     auto load_row = [&](int slot, int trow) {
       const T* rp = tcol + (size_t)trow * IW * CB;
@@ -399,7 +390,7 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
     }
     __syncthreads();                                    // the strip buffer is refilled two iterations later
   }
-  if (raw) continue;
+  if (raw) return;
   // ---- squeeze (complete for these 32 channels) + this CTA's share of fc1 ----
   {
     float s0, s1, s2, s3;
@@ -425,7 +416,6 @@ __global__ void __launch_bounds__(384, 2) dwconv3x3_strip_kernel(const __grid_co
     }
     hid_pre[((int64_t)b * gridDim.x + blockIdx.x) * S + sidx] = t;   // this CTA's 32-channel share (summed in order by se_fc2_hid)
   }
-  }   // images of this CTA (red / mean are rewritten only after the next image's strip barriers)
 }
 
 bool dwconv3x3_se_supported(int H, int W, int C, int stride) {
@@ -440,12 +430,7 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
   const size_t es = dtype == DT_F32 ? 4 : 2;
   const size_t smem = 2 * (size_t)(TH + 2) * (W + 2) * 32 * es + (size_t)(W + 1) * 32 * sizeof(float) + 16 + 128;   // + mbarriers + alignment slack
   FTC_REQUIRE(smem <= 200 * 1024, "dwconv3x3_se: strip does not fit shared memory");
-  // images per CTA: keep >= ~2.5 waves of CTAs (2 per SM), at most 4 images
-  int ipc = 1;
-  while (ipc < 4 && (int64_t)(C / 32) * ((B + 2 * ipc - 1) / (2 * ipc)) >= 740) ipc *= 2;
-  static const int env_ipc = [] { const char* e = getenv("FTC_DW_IPC"); return e ? atoi(e) : 0; }();
-  if (env_ipc > 0) ipc = env_ipc;
-  dim3 grid(C / 32, (B + ipc - 1) / ipc);
+  dim3 grid(C / 32, B);
   const int threads = W * 8;
   const float inv_hw = 1.0f / (float)(H * W);
   const bool raw_mode = scale == nullptr;
@@ -462,8 +447,8 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
       FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<TT, TH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
       done = true;                                                                                                     \
     }                                                                                                                  \
-    if (raw_mode) FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH, true>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip, B, ipc)); \
-    else FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH, false>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip, B, ipc)); \
+    if (raw_mode) FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH, true>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip)); \
+    else FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<TT, TH, false>, grid, dim3(threads), smem, s, tmIn, (TT*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip)); \
   } while (0)
   // (an mma.sync variant of this kernel was measured slower on B200 -- 0.26 vs 0.17 ms at 48x48x1536, B = 32: its BN / SiLU / SE
   // epilogue and fragment exchange cost as many issue slots as the FMAs they replace -- and was removed)
@@ -482,8 +467,8 @@ int dwconv3x3_se(const void* in, void* out, int dtype, int B, int H, int W, int 
       FTC_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<bf16, TH12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       done12 = true;
     }
-    if (raw_mode) FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<bf16, TH12, true>, grid, dim3(threads), smem12, s, tm12, (bf16*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip, B, ipc));
-    else FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<bf16, TH12, false>, grid, dim3(threads), smem12, s, tm12, (bf16*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip, B, ipc));
+    if (raw_mode) FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<bf16, TH12, true>, grid, dim3(threads), smem12, s, tm12, (bf16*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip));
+    else FTC_CHECK_CUDA(launch_pdl(dwconv3x3_strip_kernel<bf16, TH12, false>, grid, dim3(threads), smem12, s, tm12, (bf16*)out, H, W, C, w, scale, bias, w1, S, inv_hw, hid_pre, flip));
   }
   else if (dtype == DT_F32) DWS_LAUNCH(float);
   else DWS_LAUNCH(bf16);
