@@ -230,6 +230,33 @@ def test_emu_colour_salt_blank(emu):
     check_crop("crop2_", a, maps[0], idmap[0], minsize[0])
 
 
+def test_emu_edge_cases_empty_boxes_tiny_page_and_negative_coordinates(emu):
+    """Edge cases the reference handles implicitly: a batch without a single box (crop origin drawn directly, :367-369), a page much
+    smaller than the 768 x 768 crop (everything outside reads as 0), boxes far outside the crop (flag 0), a one-pixel page."""
+    rng = np.random.default_rng(5)
+    tiny = (rng.random((90, 70)) * 255).astype(np.uint8)
+    tl, sp = (rng.random((45, 35)) * 255).astype(np.uint8), (rng.random((45, 35)) * 255).astype(np.uint8)
+    none4, none2 = np.zeros((0, 4), np.float32), np.zeros((0, 2), np.int32)
+    far = np.array([[5000., 5000., 30., 30.], [35., 45., 20., 25.]], np.float32)
+    far_code = np.array([[0x3042, 1], [0x3044, 3]], np.int32)
+    one = np.array([[200]], np.uint8)
+    samples = [(tiny, tl, sp, none4, none2), (tiny, tl, sp, far, far_code), (one, one, one, none4, none2)]
+    params = []
+    for i, smp in enumerate(samples):
+        params.append(PO.draw_crop_params(PO.LibcRand(100 + i), smp[0].shape[0], smp[0].shape[1], smp[1].shape[0], smp[1].shape[1], smp[3]))
+    params[1]["cidx"] = 1                        # anchor on the in-page box so that the other one lies far outside the crop
+    image, maps, idmap, minsize = run_host(emu, samples, params)
+    for b, (smp, p) in enumerate(zip(samples, params)):
+        o = PO.transform_crop(*smp, p)
+        assert np.array_equal(image[b, 0], o[0]) and np.array_equal(maps[b, 3:], o[1][3:]) and np.array_equal(idmap[b], o[2])
+        assert maps_close(maps[b, :3], o[1][:3]) and np.float32(minsize[b]) == o[3]
+    assert not idmap[0].any() and not maps[0, :3].any() and minsize[0] == 0
+    assert set(np.unique(idmap[1, 0]).tolist()) <= {0, 0x3044}
+    # a batch in which NO sample has a box (total_boxes = 0: the label kernel is not launched)
+    image2, maps2, idmap2, _ = run_host(emu, [samples[0], samples[2]], [params[0], params[2]])
+    assert np.array_equal(image2[0], image[0]) and np.array_equal(image2[1], image[2]) and not idmap2.any()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # random_distortion (dataset/data_detector.py:28-42)
 # ---------------------------------------------------------------------------------------------------------------------
@@ -387,3 +414,27 @@ def test_gpu_full_batch_properties():
         codes = set(np.unique(idmap[b, 0].numpy()).tolist()) - {0}
         assert codes <= set(samples[b][4][:, 0].tolist())
         assert float(maps[b, 0].max()) <= 1.0 and float(maps[b, 0].min()) >= 0.0
+
+
+@pytest.mark.gpu
+def test_gpu_processer_batch_drives_a_train1_step():
+    """The batch GpuProcesser produces is what the train step consumes: one eager train1 step (fwd + losses + bwd + optimizer) on it."""
+    import torch
+    from findtextcenternet_b200 import synthetic, train
+    from findtextcenternet_b200.loss_func import CoVWeightingLoss
+    from findtextcenternet_b200.models.adamw_schedulefree import AdamWScheduleFree
+    from findtextcenternet_b200.models.detector import TextDetectorModel
+    proc = P.GpuProcesser("cuda:0", rand=PO.ListRand(np.random.default_rng(3).integers(0, 2**31 - 1, 4000)), rng=np.random.default_rng(4))
+    samples = [case_sample("crop2_"), case_sample("crop3_")]
+    image, labelmap, idmap, _ = proc(samples)
+    model = TextDetectorModel(pre_weights=False)
+    model.load_state_dict(synthetic.detector_state_dict(0))
+    model.set_precision("bf16")
+    model = model.cuda().train()
+    opt = AdamWScheduleFree([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+    opt.train()
+    cov = CoVWeightingLoss(device=image.device, losses=train.TRAIN1_LOSSES)
+    fmask = model.get_fmask(labelmap, None)
+    loss, raw = train.train1_step(model, opt, cov, image, labelmap, idmap, fmask)
+    assert torch.isfinite(loss) and all(torch.isfinite(v).all() for v in raw.values())
+    assert int(fmask.sum()) == 1024 * len(samples)
