@@ -487,26 +487,22 @@ int dwconv3x3_raw_strip(const void* in, void* out, int dtype, int B, int H, int 
 // hid_part [B][G][S] holds one fc1 share per depthwise CTA (G = C / 32 channel groups); the shares are added in a FIXED
 // order (P interleaved partial sums over g, combined in order), so the excitation is bit-reproducible run to run and
 // independent of the batch size -- near-tied peak scores downstream must not depend on the CTA schedule.
-__global__ void __launch_bounds__(512) se_fc2_hid_kernel(const float* __restrict__ hid_part, int G,
+__global__ void __launch_bounds__(256) se_fc2_hid_kernel(const float* __restrict__ hid_part, int G,
                                                          float* __restrict__ scale_out, int C, int S,
                                                          const float* __restrict__ b1, const float* __restrict__ w2t,
                                                          const float* __restrict__ b2) {
-  // 512 threads: the kernel is a chain of dependent L2 round trips on the critical path between the depthwise and the project
-  // convolution (18.5 us per launch with 256 threads, P = 2: 48 serial loads per thread in the first phase, 128 in the last);
-  // P = 512 / S interleaved partial sums and 16 loads in flight in the fc2 loop cut the trips to a quarter.  The summation order is
-  // fixed by (S, G) alone: bit-reproducible and independent of the batch.
   __shared__ float sh[256];
-  __shared__ float part[512];
+  __shared__ float part[256];
   const int b = blockIdx.y;
   pdl_launch_dependents();
   pdl_wait();
-  const int P = (int)blockDim.x / S > 0 ? (int)blockDim.x / S : 1;   // partial sums per squeeze unit (S <= 256)
+  const int P = 256 / S > 0 ? 256 / S : 1;              // partial sums per squeeze unit (S <= 256)
   {
     const int k = threadIdx.x % S, pi = threadIdx.x / S;
     if (pi < P) {
       const float* hp = hid_part + (int64_t)b * G * S + k;
       float t = 0.f;
-#pragma unroll 8
+#pragma unroll 4
       for (int g = pi; g < G; g += P) t += hp[(int64_t)g * S];
       part[pi * S + k] = t;
     }
@@ -521,15 +517,15 @@ __global__ void __launch_bounds__(512) se_fc2_hid_kernel(const float* __restrict
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float t = b2[c];
-#pragma unroll 16
-  for (int k = 0; k < S; ++k) t = fmaf(__ldg(w2t + (int64_t)k * C + c), sh[k], t);   // 16 loads in flight (same summation order)
+#pragma unroll 8
+  for (int k = 0; k < S; ++k) t = fmaf(__ldg(w2t + (int64_t)k * C + c), sh[k], t);   // 8 loads in flight (same summation order)
   scale_out[(int64_t)b * C + c] = sigmoid_precise(t);
 }
 
 int se_fc2_hid(const float* hid_part, int G, float* scale_out, int B, int C, int S, const float* b1, const float* w2t,
                const float* b2, cudaStream_t s) {
   FTC_REQUIRE(S <= 256 && S > 0 && G > 0, "SE: squeeze <= 256");
-  FTC_CHECK_CUDA(launch_pdl(se_fc2_hid_kernel, dim3(ceil_div(C, 512), B), dim3(512), 0, s, hid_part, G, scale_out, C, S, b1, w2t, b2));
+  FTC_CHECK_CUDA(launch_pdl(se_fc2_hid_kernel, dim3(ceil_div(C, 256), B), dim3(256), 0, s, hid_part, G, scale_out, C, S, b1, w2t, b2));
   FTC_POST_LAUNCH();
   return 0;
 }
