@@ -147,6 +147,15 @@ def test_host_parameters_equal_the_oracles():
     assert np.float32(P.host_minsize(s[3], p)) == G["crop2_minsize"]
 
 
+def test_product_input_pipeline_has_no_cpu_route():
+    """GpuProcesser is the CUDA path or nothing: a CPU device raises (the oracle is never a fallback)."""
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        P.GpuProcesser("cpu")
+    import inspect
+    src = inspect.getsource(P)
+    assert "import oracle" not in src and "from oracle" not in src and "/root/reference" not in src
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # the kernel source on host threads (oracle/emu)
 # ---------------------------------------------------------------------------------------------------------------------
