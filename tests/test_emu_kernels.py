@@ -167,7 +167,9 @@ def test_emu_layernorm_swiglu_embed(emu, dt):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("b,heads,hd,lt,ls,masked", [(1, 2, 16, 5, 5, False), (2, 2, 32, 6, 37, True)])
+@pytest.mark.parametrize("b,heads,hd,lt,ls,masked", [(1, 2, 16, 5, 5, False), (2, 2, 32, 6, 37, True),
+                                                     (2, 3, 32, 50, 43, True), (1, 1, 64, 9, 128, False),    # fused kernel (<= 128), ragged 4 x 4 tiles
+                                                     (1, 2, 16, 7, 150, False)])                             # > 128 keys: row / column kernels
 def test_emu_attention_backward(emu, dt, b, heads, hd, lt, ls, masked):
     d = heads * hd
     q, do = rnd(b, lt, d, seed=1, dt=dt), rnd(b, lt, d, seed=4, dt=dt)
