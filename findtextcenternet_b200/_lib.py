@@ -79,6 +79,7 @@ SYMBOLS = {
     "ftc_adamw_sf_chunk_elems": (_i, []),
     "ftc_adamw_sf_step": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _d, _d, _d, _vp]),
     "ftc_adamw_sf_step_dev": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ftc_radam_sf_step_dev": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ftc_radam_sf_step": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _d, _d, _d, _i, _vp]),
     "ftc_heatmap_loss_scratch_bytes": (_sz, []),
     "ftc_heatmap_loss": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

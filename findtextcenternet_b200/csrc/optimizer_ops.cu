@@ -62,6 +62,33 @@ __global__ void adamw_sf_schedule_kernel(const double* __restrict__ consts, doub
   state[0] = k + 1.0; state[1] = lr_max; state[2] = weight_sum;
   hyper[0] = (float)beta2; hyper[1] = (float)(1.0 - beta2); hyper[2] = (float)bc2; hyper[3] = (float)eps;
   hyper[4] = (float)decay; hyper[5] = (float)lr; hyper[6] = (float)ckp1; hyper[7] = (float)(lr * (beta1 * (1.0 - ckp1) - 1.0));
+  hyper[8] = 1.0f;       // Adam normalisation on
+}
+
+// Schedule-Free RAdam (models/radam_schedulefree.py:138-152): the rectification term of the variance, evaluated on the device in double
+// as the reference evaluates it in Python floats.  consts: lr, beta1, beta2, eps, weight_decay, silent_sgd_phase (0 / 1), r,
+// weight_lr_power; state: k, lr_max, weight_sum
+__global__ void radam_sf_schedule_kernel(const double* __restrict__ consts, double* __restrict__ state, float* __restrict__ hyper) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double lr0 = consts[0], beta1 = consts[1], beta2 = consts[2], eps = consts[3], decay = consts[4], silent = consts[5],
+               r = consts[6], wlp = consts[7];
+  const double k = state[0], step = k + 1.0;
+  const double beta2_t = pow(beta2, step);
+  const double bc2 = 1.0 - beta2_t;
+  const double rho_inf = 2.0 / (1.0 - beta2) - 1.0;
+  const double rho_t = rho_inf - 2.0 * step * beta2_t / bc2;
+  const bool adam = rho_t > 4.0;
+  const double rect = adam ? sqrt((rho_t - 4.0) * (rho_t - 2.0) * rho_inf / ((rho_inf - 4.0) * (rho_inf - 2.0) * rho_t))
+                           : (silent != 0.0 ? 0.0 : 1.0);
+  const double lr = lr0 * rect;
+  const double lr_max = fmax(lr, state[1]);
+  const double weight = pow(step, r) * pow(lr_max, wlp);
+  const double weight_sum = state[2] + weight;
+  const double ckp1 = weight_sum != 0.0 ? weight / weight_sum : 0.0;
+  state[0] = step; state[1] = lr_max; state[2] = weight_sum;
+  hyper[0] = (float)beta2; hyper[1] = (float)(1.0 - beta2); hyper[2] = (float)bc2; hyper[3] = (float)eps;
+  hyper[4] = (float)decay; hyper[5] = (float)lr; hyper[6] = (float)ckp1; hyper[7] = (float)(lr * (beta1 * (1.0 - ckp1) - 1.0));
+  hyper[8] = adam ? 1.0f : 0.0f;
 }
 
 __global__ void __launch_bounds__(256) adamw_sf_step_dev_kernel(const SfChunk* __restrict__ chunks, float* const* __restrict__ ys,
@@ -70,6 +97,7 @@ __global__ void __launch_bounds__(256) adamw_sf_step_dev_kernel(const SfChunk* _
                                                                 const float* __restrict__ hyper) {
   const float beta2 = hyper[0], one_m_beta2 = hyper[1], bias_correction2 = hyper[2], eps = hyper[3], decay = hyper[4], lr = hyper[5],
               ckp1 = hyper[6], y_alpha = hyper[7];
+  const bool normalize = hyper[8] != 0.0f;
   const SfChunk c = chunks[blockIdx.x];
   float* y = ys[c.tensor] + c.offset;
   float* g = grads[c.tensor] + c.offset;
@@ -82,7 +110,8 @@ __global__ void __launch_bounds__(256) adamw_sf_step_dev_kernel(const SfChunk* _
     float vi = v[i] * beta2;
     vi = vi + one_m_beta2 * (gi * gi);
     v[i] = vi;
-    float gn = gi / (sqrtf(vi / bias_correction2) + eps);
+    float gn = gi;
+    if (normalize) gn = gi / (sqrtf(vi / bias_correction2) + eps);
     float yi = y[i];
     if (decay != 0.0f) gn = gn + decay * yi;
     g[i] = gn;
@@ -127,6 +156,19 @@ int ftc_adamw_sf_step_dev(int n_chunks, const void* chunks, const void* const* y
   if (n_chunks == 0) return 0;
   adamw_sf_step_dev_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(
       (const SfChunk*)chunks, (float* const*)ys, (float* const*)grads, (float* const*)exp_avg_sqs, (float* const*)zs, numels, hyper8);
+  FTC_POST_LAUNCH();
+  return 0;
+}
+
+int ftc_radam_sf_step_dev(int n_chunks, const void* chunks, const void* const* ys, const void* const* grads,
+                          const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, const double* consts8,
+                          double* state3, float* hyper9, void* stream) {
+  FTC_REQUIRE(n_chunks >= 0 && chunks && ys && grads && exp_avg_sqs && zs && numels && consts8 && state3 && hyper9, "bad argument");
+  radam_sf_schedule_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(consts8, state3, hyper9);
+  FTC_POST_LAUNCH();
+  if (n_chunks == 0) return 0;
+  adamw_sf_step_dev_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(
+      (const SfChunk*)chunks, (float* const*)ys, (float* const*)grads, (float* const*)exp_avg_sqs, (float* const*)zs, numels, hyper9);
   FTC_POST_LAUNCH();
   return 0;
 }

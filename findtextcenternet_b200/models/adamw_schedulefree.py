@@ -92,11 +92,18 @@ class AdamWScheduleFree(torch.optim.Optimizer):
                     raise RuntimeError("prepare_graph(): run one eager step first (optimizer state not initialised)")
             dev = active[0].device
             beta1, beta2 = group["betas"]
-            consts = torch.tensor([float(group["lr"]), beta1, beta2, group["eps"], group["weight_decay"], float(group["warmup_steps"]),
-                                   group["r"], group["weight_lr_power"]], dtype=torch.float64, device=dev)
+            consts = torch.tensor(self._graph_consts(group), dtype=torch.float64, device=dev)
             state = torch.tensor([float(group["k"]), float(group["lr_max"]), float(group["weight_sum"])], dtype=torch.float64, device=dev)
-            hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+            hyper = torch.zeros(9, dtype=torch.float32, device=dev)
             self._graph_state[gi] = dict(consts=consts, state=state, hyper=hyper, table=self._table(gi, active), active=active)
+
+    _DEV_STEP = "ftc_adamw_sf_step_dev"
+
+    def _graph_consts(self, group) -> list:
+        """the eight schedule constants the device schedule kernel reads (ftc_adamw_sf_step_dev)"""
+        beta1, beta2 = group["betas"]
+        return [float(group["lr"]), beta1, beta2, group["eps"], group["weight_decay"], float(group["warmup_steps"]), group["r"],
+                group["weight_lr_power"]]
 
     def sync_from_graph(self) -> None:
         for gi, gs in getattr(self, "_graph_state", {}).items():
@@ -118,10 +125,10 @@ class AdamWScheduleFree(torch.optim.Optimizer):
                                    "storage (shard.FlatGradients) for a captured optimizer step")
             dev = active[0].device
             with torch.cuda.device(dev):
-                _lib.check(lib.ftc_adamw_sf_step_dev(tab["n"], tab["chunks"].data_ptr(), tab["ys"].data_ptr(), tab["gs"].data_ptr(),
-                                                     tab["vs"].data_ptr(), tab["zs"].data_ptr(), tab["numels"].data_ptr(),
-                                                     gs["consts"].data_ptr(), gs["state"].data_ptr(), gs["hyper"].data_ptr(),
-                                                     torch.cuda.current_stream(dev).cuda_stream), "ftc_adamw_sf_step_dev")
+                _lib.check(getattr(lib, self._DEV_STEP)(tab["n"], tab["chunks"].data_ptr(), tab["ys"].data_ptr(), tab["gs"].data_ptr(),
+                                                        tab["vs"].data_ptr(), tab["zs"].data_ptr(), tab["numels"].data_ptr(),
+                                                        gs["consts"].data_ptr(), gs["state"].data_ptr(), gs["hyper"].data_ptr(),
+                                                        torch.cuda.current_stream(dev).cuda_stream), self._DEV_STEP)
             torch.autograd.graph.increment_version(active)
             torch.autograd.graph.increment_version([p.grad for p in active])
 

@@ -22,8 +22,20 @@ class RAdamScheduleFree(AdamWScheduleFree):
         torch.optim.Optimizer.__init__(self, params, defaults)
         self._tables = {}
 
+    _DEV_STEP = "ftc_radam_sf_step_dev"
+
+    def _graph_consts(self, group) -> list:
+        beta1, beta2 = group["betas"]
+        return [float(group["lr"]), beta1, beta2, group["eps"], group["weight_decay"], 1.0 if group["silent_sgd_phase"] else 0.0,
+                group["r"], group["weight_lr_power"]]
+
     @torch.no_grad()
     def step(self, closure: Optional[Callable[[], float]] = None) -> Optional[float]:
+        if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            if closure is not None:
+                raise RuntimeError("closure is not supported inside a CUDA graph capture")
+            self._step_captured()          # device-side rectification schedule (ftc_radam_sf_step_dev)
+            return None
         if not self.param_groups[0]["train_mode"]:
             raise Exception("Optimizer was not in train mode when step is called. Please insert .train() and .eval() calls "
                             "on the optimizer. See documentation for details.")

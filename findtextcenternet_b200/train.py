@@ -135,21 +135,74 @@ def _sync_loss_values(rawloss: Dict[str, torch.Tensor], group=None) -> Dict[str,
     return out
 
 
-def train3_step(model, optimizer, encoder_input, decoder_input, label_code, msk_token: int = 3, group=None
-                ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+def train3_step(model, optimizer, encoder_input, decoder_input, label_code, msk_token: int = 3, group=None,
+                flat: Optional["shard.FlatGradients"] = None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
     """One iteration of the train3.py loop body (:132-150): ``outputs = model(encoder_input, decoder_input)`` in train mode,
     ``loss_function3(outputs, label_code, decoder_input == decoder_MSK)``, backward, (gradient all-reduce,) optimizer step.
     The reference wraps the step in fp16 autocast + GradScaler; here precision is the model's ``set_precision`` (bf16 storage
-    with fp32 accumulation needs no loss scaling)."""
+    with fp32 accumulation needs no loss scaling).  With ``flat`` (``shard.FlatGradients``) the gradients live in static flat
+    buckets that are all-reduced in place from inside backward -- what a CUDA-graph capture of the step needs (``Train3Graph``)."""
     from .loss_func import loss_function3
-    optimizer.zero_grad()
+    if flat is not None:
+        flat.zero()
+    else:
+        optimizer.zero_grad()
     outputs = model(encoder_input, decoder_input)
     rawloss = loss_function3(outputs, label_code, decoder_input == msk_token)
     rawloss["loss"].backward()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if flat is not None:
+        flat.finish()
+    elif dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         shard.allreduce_gradients([p for p in model.parameters() if p.requires_grad], group=group)
     optimizer.step()
     return rawloss["loss"].detach(), {k: v.detach() for k, v in rawloss.items()}
+
+
+class Train3Graph:
+    """The train3 step (Transformer forward, ``loss_function3``, backward, in-place bucket all-reduce, fused schedule-free RAdam with
+    its rectification schedule on the device: ``ftc_radam_sf_step_dev``) captured once into a CUDA graph and replayed per iteration
+    -- the eager step issues ~4 400 launches from Python and is paced by the interpreter (81 ms wall for 48 ms of kernels at batch
+    64).  Same contract as ``Train1Graph``: ``step`` copies its arguments into static buffers and returns the graph's static outputs;
+    ``optimizer.sync_from_graph()`` brings k / lr_max / weight_sum back to the host (checkpoints)."""
+
+    def __init__(self, model, optimizer, batch, device, enc_len: int, dec_len: int, enc_dim: int = 106, msk_token: int = 3, group=None,
+                 flat: Optional["shard.FlatGradients"] = None, warmup_batch=None, eager_steps: int = 2):
+        dev = torch.device(device)
+        self.model, self.optimizer, self.group, self.msk_token = model, optimizer, group, msk_token
+        self.flat = flat if flat is not None else shard.FlatGradients([p for p in model.parameters() if p.requires_grad], group=group)
+        self.enc = torch.zeros(batch, enc_len, enc_dim, dtype=torch.float32, device=dev)
+        self.dec = torch.full((batch, dec_len), msk_token, dtype=torch.int64, device=dev)
+        self.label = torch.zeros(batch, dec_len, dtype=torch.int64, device=dev)
+        if warmup_batch is not None:
+            self._load(*warmup_batch)
+        else:
+            self.enc.normal_()
+            self.label.random_(0, 0x3FFFF)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(eager_steps, 1)):
+                train3_step(model, optimizer, self.enc, self.dec, self.label, msk_token, group=group, flat=self.flat)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.flat.check_views()
+        torch.cuda.empty_cache()
+        optimizer.prepare_graph()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.rawloss = train3_step(model, optimizer, self.enc, self.dec, self.label, msk_token, group=group, flat=self.flat)
+        self.replays = 0
+
+    def _load(self, enc, dec, label):
+        self.enc.copy_(enc, non_blocking=True)
+        self.dec.copy_(dec, non_blocking=True)
+        self.label.copy_(label, non_blocking=True)
+
+    def step(self, encoder_input, decoder_input, label_code):
+        self._load(encoder_input, decoder_input, label_code)
+        self.graph.replay()
+        self.replays += 1
+        return self.loss, self.rawloss
 
 
 # ---- checkpoints (SURVEY.md 8 row f4; reference: train1.py:203-216, 93-95) --------------------------------------------------------

@@ -145,7 +145,7 @@ int ftc_adamw_sf_step(int n_chunks, const void* chunks, const void* const* ys, c
                       double bias_correction2, double eps, double weight_decay, double lr, double ckp1, void* stream);
 /* Graph-replayable form of ftc_adamw_sf_step: nothing step-dependent is passed by value.  consts8 (device double[8]) = lr, beta1,
  * beta2, eps, weight_decay, warmup_steps, r, weight_lr_power; state3 (device double[3]) = k, lr_max, weight_sum (the param-group
- * entries of models/adamw_schedulefree.py:121-140), advanced by the call; hyper8: device fp32[8] scratch.  Two launches: a
+ * entries of models/adamw_schedulefree.py:121-140), advanced by the call; hyper8: device fp32[9] scratch (9 since round 2: [8] = Adam normalisation flag).  Two launches: a
  * one-thread schedule kernel, then the same element update as ftc_adamw_sf_step.  A CUDA graph that contains this call performs
  * one further optimizer step per replay. */
 int ftc_adamw_sf_step_dev(int n_chunks, const void* chunks, const void* const* ys, const void* const* grads,
@@ -153,6 +153,12 @@ int ftc_adamw_sf_step_dev(int n_chunks, const void* chunks, const void* const* y
                           double* state3, float* hyper8, void* stream);
 /* Schedule-Free RAdam (models/radam_schedulefree.py:109-236, train3.py:121): same update with the rectified lr computed by
  * the caller; adam_step = 0 during the early phase (rho_t <= 4), where the gradient is NOT normalised (:182-190) */
+/* graph-replayable Schedule-Free RAdam: consts8 (device double[8]) = lr, beta1, beta2, eps, weight_decay, silent_sgd_phase (0 / 1), r,
+ * weight_lr_power; state3 (device double[3]) = k, lr_max, weight_sum, advanced by the call; hyper9: device fp32[9] scratch.  The
+ * rectification schedule (:138-152) runs on the device in double. */
+int ftc_radam_sf_step_dev(int n_chunks, const void* chunks, const void* const* ys, const void* const* grads,
+                          const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, const double* consts8,
+                          double* state3, float* hyper9, void* stream);
 int ftc_radam_sf_step(int n_chunks, const void* chunks, const void* const* ys, const void* const* grads,
                       const void* const* exp_avg_sqs, const void* const* zs, const int64_t* numels, double beta1, double beta2,
                       double bias_correction2, double eps, double weight_decay, double lr, double ckp1, int adam_step,

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"], help="graph: the step replayed as one CUDA graph (train.Train3Graph)")
     args = ap.parse_args()
     from findtextcenternet_b200 import _lib, synthetic, train
     from findtextcenternet_b200.models.radam_schedulefree import RAdamScheduleFree
@@ -35,20 +36,28 @@ def main():
     label = torch.randint(0, 0x3FFFF, dec.shape, generator=torch.Generator().manual_seed(1)).cuda()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     losses, l0 = [], 0
+    graph = None
+    if args.mode == "graph":
+        graph = train.Train3Graph(model, opt, args.batch, "cuda", 100, 100, warmup_batch=(enc, dec, label))
     for it in range(args.warmup + args.steps):
         if it == args.warmup:
             torch.cuda.synchronize()
             l0 = _lib.launch_count()
             e0.record()
-        loss, _ = train.train3_step(model, opt, enc, dec, label)
-        losses.append(float(loss))
+        if graph is not None:
+            loss, _ = graph.step(enc, dec, label)
+            losses.append(loss.detach().clone())
+        else:
+            loss, _ = train.train3_step(model, opt, enc, dec, label)
+            losses.append(loss.detach().clone())
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    losses = [float(v) for v in losses]
     print(json.dumps({"metric": "sequences/sec train3 step (Transformer fwd + loss_function3 + bwd + RAdamScheduleFree)",
                       "value": args.batch / (ms / 1e3), "unit": "sequences/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": ms, "dtype": args.precision, "data": "synthetic",
-                      "config": {"workload": f"train3 step, batch {args.batch}, enc100/dec100 d=512 16+16 blocks"},
+                      "config": {"workload": f"train3 step, batch {args.batch}, enc100/dec100 d=512 16+16 blocks", "mode": args.mode},
                       "gpu_launches": int(_lib.launch_count() - l0), "losses": losses,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
 
