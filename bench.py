@@ -17,7 +17,8 @@ seeded synthetic weights (BN-calibrated; findtextcenternet_b200/synthetic.py).  
             CUDA graph, batch 16 per GPU, gradients all-reduced in place over NCCL from inside backward; whole-job images/s, its
             own roofline (2 717 GFLOP/image) and, for N > 1, the step time with the exchange removed (exposed all-reduce).
 `gpu_reference`: the reference's math on the SAME GPU through torch's library kernels (cuDNN eager, bf16 autocast): the bar.
-`transformer_cfg4`, `page_2048`: BASELINE.json configs[3] / configs[4] as labelled side objects (child processes, N = 1).
+`transformer_cfg4`, `page_2048`, `train3`: BASELINE.json configs[3] / configs[4] and the train3 step (configs[3]'s shape, batch 64, one
+            CUDA graph) as labelled side objects (child processes, N = 1).
 `cpu_baseline`: the oracle port (oracle/detector_oracle.py, fp32 torch CPU ops restating the reference) on the host cores.
 --impl reference: the same CPU port timed as the reference arm (the reference is Python+torchvision and cannot travel
             to the GPU box; oracle/ restates it and is pinned to it by tests/golden).
@@ -312,6 +313,7 @@ def run_ours(args):
     if world == 1 and not args.no_side:
         line["transformer_cfg4"] = side_measurement("bench_transformer.py", ["cfg4", "bf16"], 240)
         line["page_2048"] = side_measurement("bench_page.py", ["--pages", "3", "--chunks", "32"], 240)
+        line["train3"] = side_measurement("bench_train3.py", ["--batch", "64", "--steps", "5", "--warmup", "2", "--mode", "graph"], 240)
     print(json.dumps(line), flush=True)
 
 
