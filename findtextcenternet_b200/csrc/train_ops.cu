@@ -1822,13 +1822,20 @@ bool wgrad_mma_enabled() {
 // staged once (storage type), S = scale QK^T + mask and dP = dO V^T are formed as 4 x 4 register tiles into two fp32 matrices, a warp
 // per row turns them into P and dS = P (dP - sum_j P dP), and dQ = scale dS K, dK = scale dS^T Q, dV = P^T dO are read off the
 // shared matrices.  No atomics, fixed summation order.
+// two consecutive operand elements as floats (one 32-bit / 64-bit shared-memory load; operand rows are 4-byte aligned: RS is even)
+__device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld_pair(const bf16* p) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) attn_bwd_fused_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                                                              const float* __restrict__ mask, const T* __restrict__ dout,
                                                              float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
                                                              int hd, int Lt, int Ls, int D, float scale) {
   extern __shared__ __align__(16) uint8_t afb_raw[];
-  const int RS = hd + 2;                                   // operand row stride (elements): odd word stride for both storage types
+  const int RS = hd + 2;                                   // operand row stride (elements, even): 4 rows apart = 4 (bf16) / 8 (fp32) banks
   const int PS = Ls + 1;                                   // matrix row stride (floats)
   float* Pm = reinterpret_cast<float*>(afb_raw);           // [Lt][PS]  S, then P
   float* Dm = Pm + (size_t)Lt * PS;                        // [Lt][PS]  dP, then dS
@@ -1836,7 +1843,7 @@ __global__ void __launch_bounds__(256) attn_bwd_fused_kernel(const T* __restrict
   T* Os = Qs + (size_t)Lt * RS;                            // [Lt][RS]  dO
   T* Ks = Os + (size_t)Lt * RS;                            // [Ls][RS]
   T* Vs = Ks + (size_t)Ls * RS;                            // [Ls][RS]
-  const int tid = threadIdx.x, h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, h = blockIdx.x, b = blockIdx.y;
   const int64_t qbase = (int64_t)b * Lt * D + (int64_t)h * hd, kbase = (int64_t)b * Ls * D + (int64_t)h * hd;
   for (int i = tid; i < Lt * hd; i += 256) {
     const int r = i / hd, e = i - r * hd;
@@ -1849,27 +1856,36 @@ __global__ void __launch_bounds__(256) attn_bwd_fused_kernel(const T* __restrict
     Vs[r * RS + e] = v[kbase + (int64_t)r * D + e];
   }
   __syncthreads();
-  // ---- S and dP as 4 x 4 register tiles ----
+  // ---- S = scale Q K^T + mask and dP = dO V^T as 4 x 4 register tiles.  A warp takes a patch of 4 (query) x 8 (key) tiles: the
+  // eight key-tile lanes read eight different banks, lanes that share a tile row / column read the same word (broadcast). ----
   const int tq = (Lt + 3) / 4, tk = (Ls + 3) / 4;
-  for (int t = tid; t < tq * tk; t += 256) {
-    const int i0 = (t / tk) * 4, j0 = (t % tk) * 4;
+  const int pq = (tq + 3) / 4, pk = (tk + 7) / 8;
+  for (int pidx = warp; pidx < pq * pk; pidx += 8) {
+    const int it = (pidx / pk) * 4 + (lane >> 3), jt = (pidx % pk) * 8 + (lane & 7);
+    if (it >= tq || jt >= tk) continue;
+    const int i0 = it * 4, j0 = jt * 4;
+    int ri[4], rj[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { ri[a] = min(i0 + a, Lt - 1) * RS; rj[a] = min(j0 + a, Ls - 1) * RS; }
     float sacc[4][4], pacc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int c = 0; c < 4; ++c) { sacc[a][c] = 0.f; pacc[a][c] = 0.f; }
-    for (int e = 0; e < hd; ++e) {
-      float qa[4], oa[4], ka[4], va[4];
+    for (int e = 0; e < hd; e += 2) {
+      float2 qa[4], oa[4], ka[4], va[4];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        const int i = min(i0 + a, Lt - 1), j = min(j0 + a, Ls - 1);
-        qa[a] = to_f(Qs[i * RS + e]); oa[a] = to_f(Os[i * RS + e]);
-        ka[a] = to_f(Ks[j * RS + e]); va[a] = to_f(Vs[j * RS + e]);
+        qa[a] = ld_pair(Qs + ri[a] + e); oa[a] = ld_pair(Os + ri[a] + e);
+        ka[a] = ld_pair(Ks + rj[a] + e); va[a] = ld_pair(Vs + rj[a] + e);
       }
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { sacc[a][c] = fmaf(qa[a], ka[c], sacc[a][c]); pacc[a][c] = fmaf(oa[a], va[c], pacc[a][c]); }
+        for (int c = 0; c < 4; ++c) {
+          sacc[a][c] = fmaf(qa[a].y, ka[c].y, fmaf(qa[a].x, ka[c].x, sacc[a][c]));
+          pacc[a][c] = fmaf(oa[a].y, va[c].y, fmaf(oa[a].x, va[c].x, pacc[a][c]));
+        }
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -1884,7 +1900,6 @@ __global__ void __launch_bounds__(256) attn_bwd_fused_kernel(const T* __restrict
   }
   __syncthreads();
   // ---- rows: P = softmax(S), dS = P (dP - sum_j P dP); one warp per row ----
-  const int warp = tid >> 5, lane = tid & 31;
   for (int i = warp; i < Lt; i += 8) {
     float* pr = Pm + i * PS;
     float* dr = Dm + i * PS;
@@ -1904,24 +1919,55 @@ __global__ void __launch_bounds__(256) attn_bwd_fused_kernel(const T* __restrict
     for (int j = lane; j < Ls; j += 32) dr[j] = pr[j] * (dr[j] - delta);
   }
   __syncthreads();
-  // ---- dQ[i][e] = scale sum_j dS[i][j] K[j][e] ----
-  for (int t = tid; t < Lt * hd; t += 256) {
-    const int i = t / hd, e = t - i * hd;
-    const float* dr = Dm + i * PS;
-    float a = 0.f;
-    for (int j = 0; j < Ls; ++j) a = fmaf(dr[j], to_f(Ks[j * RS + e]), a);
-    dq[qbase + (int64_t)i * D + e] = a * scale;
-  }
-  // ---- dV[j][e] = sum_i P[i][j] dO[i][e];  dK[j][e] = scale sum_i dS[i][j] Q[i][e] ----
-  for (int t = tid; t < Ls * hd; t += 256) {
-    const int j = t / hd, e = t - j * hd;
-    float av = 0.f, ak = 0.f;
-    for (int i = 0; i < Lt; ++i) {
-      av = fmaf(Pm[i * PS + j], to_f(Os[i * RS + e]), av);
-      ak = fmaf(Dm[i * PS + j], to_f(Qs[i * RS + e]), ak);
+  // ---- dQ = scale dS K: thread = 4 query rows x 2 head-dim columns (8 FMAs per 5 shared-memory loads) ----
+  const int he = hd / 2;
+  for (int t = tid; t < tq * he; t += 256) {
+    const int i0 = (t / he) * 4, e = (t % he) * 2;
+    const float* dr[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) dr[a] = Dm + min(i0 + a, Lt - 1) * PS;
+    float acc[4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { acc[a][0] = 0.f; acc[a][1] = 0.f; }
+    for (int j = 0; j < Ls; ++j) {
+      const float2 kv = ld_pair(Ks + j * RS + e);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { const float d = dr[a][j]; acc[a][0] = fmaf(d, kv.x, acc[a][0]); acc[a][1] = fmaf(d, kv.y, acc[a][1]); }
     }
-    dv[kbase + (int64_t)j * D + e] = av;
-    dk[kbase + (int64_t)j * D + e] = ak * scale;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if (i0 + a < Lt) {
+        dq[qbase + (int64_t)(i0 + a) * D + e] = acc[a][0] * scale;
+        dq[qbase + (int64_t)(i0 + a) * D + e + 1] = acc[a][1] * scale;
+      }
+  }
+  // ---- dV = P^T dO, dK = scale dS^T Q: thread = 4 keys x 2 head-dim columns (16 FMAs per 10 loads) ----
+  for (int t = tid; t < tk * he; t += 256) {
+    const int j0 = (t / he) * 4, e = (t % he) * 2;
+    int cj[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cj[c] = min(j0 + c, Ls - 1);
+    float av[4][2], ak[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { av[c][0] = av[c][1] = 0.f; ak[c][0] = ak[c][1] = 0.f; }
+    for (int i = 0; i < Lt; ++i) {
+      const float2 ov = ld_pair(Os + i * RS + e), qv = ld_pair(Qs + i * RS + e);
+      const float* pr = Pm + i * PS;
+      const float* dr = Dm + i * PS;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float pv = pr[cj[c]], dsv = dr[cj[c]];
+        av[c][0] = fmaf(pv, ov.x, av[c][0]); av[c][1] = fmaf(pv, ov.y, av[c][1]);
+        ak[c][0] = fmaf(dsv, qv.x, ak[c][0]); ak[c][1] = fmaf(dsv, qv.y, ak[c][1]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (j0 + c < Ls) {
+        const int64_t o = kbase + (int64_t)(j0 + c) * D + e;
+        dv[o] = av[c][0]; dv[o + 1] = av[c][1];
+        dk[o] = ak[c][0] * scale; dk[o + 1] = ak[c][1] * scale;
+      }
   }
 }
 
@@ -2470,7 +2516,7 @@ int ftc_train_attention_bwd(const void* q, const void* k, const void* v, const f
   {   // short sequences: one CTA per (batch, head) with everything in shared memory
     const size_t es = dtype == DT_F32 ? 4 : 2;
     const size_t fused = (size_t)2 * lt * (ls + 1) * sizeof(float) + (size_t)2 * (lt + ls) * (hd + 2) * es;
-    if (lt <= 128 && ls <= 128 && fused <= 200 * 1024) {
+    if (lt <= 128 && ls <= 128 && hd % 2 == 0 && fused <= 200 * 1024) {
       dim3 gf(heads, batch);
       if (dtype == DT_F32) {
         static bool done = false;
