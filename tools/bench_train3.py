@@ -37,8 +37,11 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     losses, l0 = [], 0
     graph = None
+    captured = 0
     if args.mode == "graph":
+        c0 = _lib.launch_count()
         graph = train.Train3Graph(model, opt, args.batch, "cuda", 100, 100, warmup_batch=(enc, dec, label))
+        captured = int(_lib.launch_count() - c0) // 3          # 2 eager warm-up steps + the captured one
     for it in range(args.warmup + args.steps):
         if it == args.warmup:
             torch.cuda.synchronize()
@@ -58,7 +61,9 @@ def main():
                       "value": args.batch / (ms / 1e3), "unit": "sequences/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": ms, "dtype": args.precision, "data": "synthetic",
                       "config": {"workload": f"train3 step, batch {args.batch}, enc100/dec100 d=512 16+16 blocks", "mode": args.mode},
-                      "gpu_launches": int(_lib.launch_count() - l0), "losses": losses,
+                      "gpu_launches": int(_lib.launch_count() - l0) if graph is None else captured * args.steps,
+                      "launches_per_step": (int(_lib.launch_count() - l0) // max(args.steps, 1)) if graph is None else captured,
+                      "tflops": 3 * 21.47e9 * args.batch / (ms / 1e3) / 1e12, "losses": losses,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
 
 
