@@ -598,6 +598,11 @@ int attention(const void* q, int q_stride, int q_off, const void* k, const void*
                         v_off % 8 == 0 && B <= 65535 && heads <= 65535 && !getenv("FTC_ATT_NO_MMA") &&
                         (reinterpret_cast<uintptr_t>(k) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(q) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+    // sequences of up to 128 tokens: tcgen05 kernel (attention_tc.cu); it declines (1) shapes it does not take
+    if (mma_ok) {
+      const int rc = attention_tc(q, q_stride, q_off, k, v, kv_stride, k_off, v_off, mask, out, out_stride, B, heads, hd, Lt, Ls, s);
+      if (rc <= 0) return rc;
+    }
     if (mma_ok && hd == 32) return launch_attention_mma<32>(q, q_stride, q_off, k, v, kv_stride, k_off, v_off, mask, out, out_stride, B, heads, Lt, Ls, s);
     if (mma_ok && hd == 64) return launch_attention_mma<64>(q, q_stride, q_off, k, v, kv_stride, k_off, v_off, mask, out, out_stride, B, heads, Lt, Ls, s);
     if (hd == 16) ATT(bf16, 16);

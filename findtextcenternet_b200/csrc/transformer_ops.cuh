@@ -25,6 +25,10 @@ int attention(const void* q, int q_stride, int q_off, const void* k, const void*
               const float* mask, void* out, int out_stride, int dtype, int B, int heads, int hd, int Lt, int Ls,
               cudaStream_t s);
 
+// the same product on tcgen05 / TMEM for bf16 sequences of up to 128 tokens (attention_tc.cu); returns 1 when it declines the shape
+int attention_tc(const void* q, int q_stride, int q_off, const void* k, const void* v, int kv_stride, int k_off, int v_off,
+                 const float* mask, void* out, int out_stride, int B, int heads, int hd, int Lt, int Ls, cudaStream_t s);
+
 // one mask-predict decision per position (models/transformer.py:311-324 + util_func.py:92-126 CRT):
 //   logits fp32 [M, ld] with the three heads at columns g*head_ld (m_g valid each)
 //   -> ids int64 [M], prob fp32 [M]; flags[0] |= any(dec_in==MSK && id>0 && !(p>0.99)); flags[1] |= any(remask);
