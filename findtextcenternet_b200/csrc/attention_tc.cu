@@ -207,22 +207,29 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
       const bool more = n + 1 < n_tasks;
       if (more && mask_col) mnext = __ldg(mask_col + (int64_t)((item + item_inc) / p.n_slabs) * p.Ls);   // in flight under the softmax
       const float* ms = ms_g + par * 128 + c_begin * 16;
-      mbar_wait(bar(AB_SREADY, g), (uint32_t)par);
+      mbar_wait(bar(AB_SREADY, g), (uint32_t)par, 0, 4000);   // suspend-time hint: a waiting group leaves the issue slots to the other one
       tc_fence_after();
       uint32_t sv[64];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         if (c < my_n) tmem_ld16(t_s + (uint32_t)(c * 16), *reinterpret_cast<uint32_t(*)[16]>(&sv[c * 16]));
       tmem_ld_wait();
+      // scale + key mask as packed fp32 pairs (FFMA2), row maximum of this thread's half
       float mx = -INFINITY;
+      const f32x2 scale2 = pk2(p.scale_log2, p.scale_log2);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         if (c < my_n) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float v = fmaf(__uint_as_float(sv[c * 16 + j]), p.scale_log2, ms[c * 16 + j]);
-            sv[c * 16 + j] = __float_as_uint(v);
-            mx = fmaxf(mx, v);
+          for (int j = 0; j < 16; j += 4) {
+            const float4 mk = *reinterpret_cast<const float4*>(ms + c * 16 + j);
+            const f32x2 a = ffma2(pk2(__uint_as_float(sv[c * 16 + j]), __uint_as_float(sv[c * 16 + j + 1])), scale2, pk2(mk.x, mk.y));
+            const f32x2 bq = ffma2(pk2(__uint_as_float(sv[c * 16 + j + 2]), __uint_as_float(sv[c * 16 + j + 3])), scale2, pk2(mk.z, mk.w));
+            float a0, a1, b0, b1;
+            upk2(a, a0, a1); upk2(bq, b0, b1);
+            sv[c * 16 + j] = __float_as_uint(a0); sv[c * 16 + j + 1] = __float_as_uint(a1);
+            sv[c * 16 + j + 2] = __float_as_uint(b0); sv[c * 16 + j + 3] = __float_as_uint(b1);
+            mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(b0, b1)));
           }
         }
       float* xm = xm_g + par * 256;
@@ -231,17 +238,19 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
       asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
       mx = fmaxf(mx, xm[(hf ^ 1) * 128 + r]);
       const float msafe = mx == -INFINITY ? 0.f : mx;       // fully masked row: every p is 0, the row sum 0 (NaN output, as SDPA)
-      float l = 0.f;
+      const f32x2 negm2 = pk2(-msafe, -msafe);
+      f32x2 l2 = pk2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         if (c < my_n) {
           uint32_t w[8];
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float p0 = ex2_approx(__uint_as_float(sv[c * 16 + j]) - msafe);
-            const float p1 = ex2_approx(__uint_as_float(sv[c * 16 + j + 1]) - msafe);
-            l += p0 + p1;
-            w[j >> 1] = pack_bf16x2(p0, p1);
+          for (int j = 0; j < 8; ++j) {
+            float d0, d1;
+            upk2(fadd2(pk2(__uint_as_float(sv[c * 16 + 2 * j]), __uint_as_float(sv[c * 16 + 2 * j + 1])), negm2), d0, d1);
+            const float p0 = ex2_approx(d0), p1 = ex2_approx(d1);
+            l2 = fadd2(l2, pk2(p0, p1));
+            w[j] = pack_bf16x2(p0, p1);
           }
           // keys cg*16 .. cg*16+15 = two 16-byte chunks of row r in the K-major 128B-swizzled P tile (64 keys per 128-byte row)
           const int cg = c_begin + c;
@@ -250,13 +259,15 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
           *reinterpret_cast<uint4*>(pc + (uint32_t)((c16 ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
           *reinterpret_cast<uint4*>(pc + (uint32_t)(((c16 + 1) ^ (r & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
         }
+      float l;
+      { float la, lb; upk2(l2, la, lb); l = la + lb; }
       float* xl = xl_g + par * 256;
       xl[hf * 128 + r] = l;
       tc_fence_before();
       fence_proxy_async();                                   // P (generic-proxy stores) -> visible to the tensor core's reads
       mbar_arrive(bar(AB_PREADY, g));
       // ---- O row (this thread's half of the head's channels): divide by the row sum, store
-      mbar_wait(bar(AB_OREADY, g), (uint32_t)par);
+      mbar_wait(bar(AB_OREADY, g), (uint32_t)par, 0, 4000);
       tc_fence_after();
       uint32_t ov[OC];
 #pragma unroll
