@@ -16,10 +16,13 @@
 //     divide by the row sum and store bf16.  For hd = 32 the N = 64 product also forms P_h V_{other head}: those columns are
 //     not read.
 // Two softmax groups run independent pipelines (hd 32: group g = head g of every item; hd 64: items alternate), each with its
-// own S / O columns in TMEM, its own P tile and its own MMA-issuing thread, so one group's exponentials run under the other
-// group's P.V product and epilogue.  (First version, measured: ONE thread driving TMA and both groups' MMAs was the bottleneck --
-// ~4 k cycles of dependent single-thread issue per task, ncu samples spread evenly over its code, 63 us per call against 56 for
-// the mma.sync kernel.)  Warps 0..15 softmax / epilogue (TMEM lane quarter = warp % 4), warps 16 / 17 MMA issuers, warp 18 TMA.
+// own TMEM columns, its own P tile and its own MMA-issuing thread, so one group's exponentials run under the other group's
+// products.  Inside a group the tasks are software-pipelined: TMEM holds TWO score buffers per group (the 64 output columns
+// of a task overwrite the head of its own, already consumed, score buffer), the score product of task n + 1 is issued before
+// P.V of task n, and the group reads / scales / maximises the scores of task n + 1 while the tensor core runs P.V of task n.
+// (Measured steps, cfg4 batch 256, per call under ncu: one thread driving TMA and both groups' MMAs 63 us -- ~4 k cycles of
+// dependent single-thread issue per task, samples spread evenly over its code; one issuer per group + a TMA warp 57 us; the
+// mma.sync kernel 56 us.)  Warps 0..15 softmax / epilogue (TMEM lane quarter = warp % 4), warps 16 / 17 MMA issuers, warp 18 TMA.
 #include "../../include/ftc_b200.h"
 #include "tc_common.cuh"
 #include "tma_util.cuh"
@@ -34,7 +37,7 @@ constexpr uint32_t AT_STAGE = 3u * AT_TILE;  // Q, K, V
 constexpr int AT_NSTAGE = 3;
 constexpr int AT_THREADS = 19 * 32;            // 16 softmax warps, 2 MMA issuers, 1 TMA producer
 // barrier slots
-constexpr int AB_FULL = 0, AB_EMPTY = 3, AB_SREADY = 6, AB_PREADY = 8, AB_OREADY = 10, AB_OCONS = 12, AB_COUNT = 14;
+constexpr int AB_FULL = 0, AB_EMPTY = 3, AB_SREADY = 6 /* [group][S buffer] */, AB_PREADY = 10, AB_OREADY = 12, AB_OCONS = 14, AB_COUNT = 16;
 // shared memory behind the operand tiles (floats): key mask [2 groups][2][128], row-max halves and row-sum halves [2][2][2][128]
 constexpr uint32_t AT_MS_FLOATS = 2 * 2 * 128, AT_X_FLOATS = 2 * 2 * 2 * 128;
 constexpr uint32_t AT_TAIL_OFF = AT_NSTAGE * AT_STAGE + 2u * 2u * AT_TILE;
@@ -91,10 +94,8 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
   if (warp == W_TMA) {
     if (lane == 0) {
       for (int i = 0; i < AT_NSTAGE; ++i) { mbar_init(bar(AB_FULL, i), 1); mbar_init(bar(AB_EMPTY, i), NH); }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(bar(AB_SREADY, i), 1); mbar_init(bar(AB_PREADY, i), 256);
-        mbar_init(bar(AB_OREADY, i), 1); mbar_init(bar(AB_OCONS, i), 256);
-      }
+      for (int i = 0; i < 4; ++i) mbar_init(bar(AB_SREADY, i), 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(bar(AB_PREADY, i), 256); mbar_init(bar(AB_OREADY, i), 1); mbar_init(bar(AB_OCONS, i), 256); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
@@ -114,7 +115,6 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
   const int first = blockIdx.x, step = gridDim.x;
   const int n_my = first < p.n_items ? (p.n_items - first + step - 1) / step : 0;   // items of this CTA (local index it)
   // group g runs head g of every item (hd 32) or the items it = 2 n + g (hd 64): its n-th task is item IT0 + n * ITS
-  // TMEM columns: S_g at g * 192 (128 wide), O_g at g * 192 + 128 (64 wide)
   if (warp == W_TMA) {
     // ---------------------------------------------------------------- TMA producer: three boxes per item, three stages ahead
     if (lane == 0) {
@@ -142,7 +142,9 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const int ksteps_o = p.Np >> 4;
-      const uint32_t t_s = tmem_base + (uint32_t)(g * 192), t_o = t_s + 128u;
+      // TMEM columns of group g: two score buffers S[k] at g * 256 + k * 128; the output of task n overwrites the first 64
+      // columns of ITS score buffer S[n & 1] (read out by the group before it announced P)
+      const uint32_t t_g = tmem_base + (uint32_t)(g * 256);
       // descriptors advance in 16-byte units in their low word (shared-memory addresses stay below 2^18)
       const uint64_t dq0 = umma_desc_sw128(sbase + (uint32_t)(hh * HD) * 2u);
       const uint64_t dk0 = umma_desc_sw128(sbase + AT_TILE + (uint32_t)(hh * HD) * 2u);
@@ -150,31 +152,38 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
       const uint64_t dp0 = umma_desc_sw128(p_base + (uint32_t)g * 2u * AT_TILE);
       int stage = it0 % AT_NSTAGE;                 // stage / parity of the item of the NEXT score product
       uint32_t ph = 0;
-      auto issue_s = [&]() {
+      int pv_stage = stage;                        // stage of the item of the next P.V product
+      auto issue_s = [&](int k) {                  // score product of task k into S[k & 1]
         mbar_wait(bar(AB_FULL, stage), ph);
         tc_fence_after();
         const uint64_t so = (uint64_t)((uint32_t)stage * (AT_STAGE >> 4));
 #pragma unroll
-        for (int k = 0; k < KS; ++k) umma_f16(t_s, dq0 + so + (uint64_t)(k * 2), dk0 + so + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
-        umma_commit(bar(AB_SREADY, g));
-      };
-      issue_s();
-      for (int n = 0; n < n_tasks; ++n) {
-        const int cur_stage = stage;
+        for (int q = 0; q < KS; ++q)
+          umma_f16(t_g + (uint32_t)((k & 1) * 128), dq0 + so + (uint64_t)(q * 2), dk0 + so + (uint64_t)(q * 2), idesc_s, q ? 1u : 0u);
+        umma_commit(bar(AB_SREADY, g * 2 + (k & 1)));
         stage += its;
         if (stage >= AT_NSTAGE) { stage -= AT_NSTAGE; ph ^= 1u; }
+      };
+      issue_s(0);
+      if (n_tasks > 1) issue_s(1);
+      for (int n = 0; n < n_tasks; ++n) {
         mbar_wait(bar(AB_PREADY, g), (uint32_t)(n & 1));
-        if (n > 0) mbar_wait(bar(AB_OCONS, g), (uint32_t)((n - 1) & 1));
         tc_fence_after();
-        const uint64_t vo = dv0 + (uint64_t)((uint32_t)cur_stage * (AT_STAGE >> 4));
+        const uint64_t vo = dv0 + (uint64_t)((uint32_t)pv_stage * (AT_STAGE >> 4));
+        const uint32_t t_o = t_g + (uint32_t)((n & 1) * 128);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           if (k < ksteps_o)
             umma_f16(t_o, dp0 + (uint64_t)((k >> 2) * (AT_TILE >> 4) + (k & 3) * 2), vo + (uint64_t)(k * (2048 >> 4)), idesc_o, k ? 1u : 0u);
         umma_commit(bar(AB_OREADY, g));
-        umma_commit(bar(AB_EMPTY, cur_stage));     // this head's reads of the stage are done when these MMAs complete
-        // the next score product: S_g is free (the group announced P after reading S), its operands were prefetched
-        if (n + 1 < n_tasks) issue_s();
+        umma_commit(bar(AB_EMPTY, pv_stage));      // this head's reads of the stage are done when these MMAs complete
+        pv_stage += its;
+        if (pv_stage >= AT_NSTAGE) pv_stage -= AT_NSTAGE;
+        // score product n + 2 reuses S[n & 1]: the group must have read O(n) out of it
+        if (n + 2 < n_tasks) {
+          mbar_wait(bar(AB_OCONS, g), (uint32_t)(n & 1));
+          issue_s(n + 2);
+        }
       }
     }
     __syncwarp();
@@ -187,8 +196,7 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
     const int n_tasks = NH == 2 ? n_my : (n_my - g + 1) / 2;
     const int nch = p.Np >> 4, n0 = (nch + 1) >> 1;
     const int c_begin = hf ? n0 : 0, my_n = hf ? nch - n0 : n0;   // this thread's 16-key chunks
-    const uint32_t t_s = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 192) + (uint32_t)(c_begin * 16);
-    const uint32_t t_o = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 192 + 128 + hh * HD + hf * OC);
+    const uint32_t t_g = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 256);
     uint8_t* prow = smem + AT_NSTAGE * AT_STAGE + (uint32_t)g * 2u * AT_TILE + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
     float* ms_g = Ms + g * 256;                    // [2][128]
     float* xm_g = Xm + g * 512;                    // [2][2 halves][128]
@@ -196,27 +204,28 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
     const bool key_thread = gt < 128;
     const float* mask_col = (p.mask && gt < p.Ls) ? p.mask + gt : nullptr;
     const float mask_pad = gt < p.Ls ? 0.f : -INFINITY;
-    int item = first + it0 * step;                 // global item of the current task
-    const int item_inc = its * step;
-    if (n_tasks > 0 && key_thread) ms_g[gt] = mask_col ? __ldg(mask_col + (int64_t)(item / p.n_slabs) * p.Ls) : mask_pad;
+    const int item0 = first + it0 * step, item_inc = its * step;
+    auto mask_of = [&](int k) -> float {           // key mask value of task k for key gt
+      return mask_col ? __ldg(mask_col + (int64_t)((item0 + k * item_inc) / p.n_slabs) * p.Ls) : mask_pad;
+    };
+    if (n_tasks > 0 && key_thread) ms_g[gt] = mask_of(0);
+    float mreg = (n_tasks > 1 && key_thread) ? mask_of(1) : mask_pad;
     asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-    for (int n = 0; n < n_tasks; ++n, item += item_inc) {
-      const int par = n & 1;
-      const int b = item / p.n_slabs, slab = item - b * p.n_slabs;
-      float mnext = mask_pad;
-      const bool more = n + 1 < n_tasks;
-      if (more && mask_col) mnext = __ldg(mask_col + (int64_t)((item + item_inc) / p.n_slabs) * p.Ls);   // in flight under the softmax
-      const float* ms = ms_g + par * 128 + c_begin * 16;
-      mbar_wait(bar(AB_SREADY, g), (uint32_t)par, 0, 4000);   // suspend-time hint: a waiting group leaves the issue slots to the other one
+    uint32_t sv[64];
+    float mx = -INFINITY;
+    const f32x2 scale2 = pk2(p.scale_log2, p.scale_log2);
+    // phase A of task k: scores out of TMEM, scale + key mask, this thread's half of the row maximum; also publishes the key mask
+    // of task k + 1 (loaded one task ahead)
+    auto phase_a = [&](int k) {
+      const float* ms = ms_g + (k & 1) * 128 + c_begin * 16;
+      mbar_wait(bar(AB_SREADY, g * 2 + (k & 1)), (uint32_t)((k >> 1) & 1), 0, 4000);
       tc_fence_after();
-      uint32_t sv[64];
+      const uint32_t t_s = t_g + (uint32_t)((k & 1) * 128 + c_begin * 16);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         if (c < my_n) tmem_ld16(t_s + (uint32_t)(c * 16), *reinterpret_cast<uint32_t(*)[16]>(&sv[c * 16]));
       tmem_ld_wait();
-      // scale + key mask as packed fp32 pairs (FFMA2), row maximum of this thread's half
-      float mx = -INFINITY;
-      const f32x2 scale2 = pk2(p.scale_log2, p.scale_log2);
+      mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         if (c < my_n) {
@@ -232,11 +241,16 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
             mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(b0, b1)));
           }
         }
-      float* xm = xm_g + par * 256;
-      xm[hf * 128 + r] = mx;
-      if (more && key_thread) ms_g[(par ^ 1) * 128 + gt] = mnext;
+      xm_g[(k & 1) * 256 + hf * 128 + r] = mx;
+      if (k + 1 < n_tasks && key_thread) ms_g[((k + 1) & 1) * 128 + gt] = mreg;
       asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-      mx = fmaxf(mx, xm[(hf ^ 1) * 128 + r]);
+      mx = fmaxf(mx, xm_g[(k & 1) * 256 + (hf ^ 1) * 128 + r]);
+    };
+    if (n_tasks > 0) phase_a(0);
+    for (int n = 0; n < n_tasks; ++n) {
+      const int par = n & 1;
+      if (n + 2 < n_tasks && key_thread) mreg = mask_of(n + 2);   // in flight under the exponentials; published by phase A of n + 1
+      // ---- phase B: exponentials, row-sum half, P tile
       const float msafe = mx == -INFINITY ? 0.f : mx;       // fully masked row: every p is 0, the row sum 0 (NaN output, as SDPA)
       const f32x2 negm2 = pk2(-msafe, -msafe);
       f32x2 l2 = pk2(0.f, 0.f);
@@ -266,10 +280,13 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
       tc_fence_before();
       fence_proxy_async();                                   // P (generic-proxy stores) -> visible to the tensor core's reads
       mbar_arrive(bar(AB_PREADY, g));
-      // ---- O row (this thread's half of the head's channels): divide by the row sum, store
+      // ---- phase A of the NEXT task runs under this task's P.V product (its scores are in the other S buffer)
+      if (n + 1 < n_tasks) phase_a(n + 1);
+      // ---- phase C: O row (this thread's half of the head's channels), divide by the row sum, store
       mbar_wait(bar(AB_OREADY, g), (uint32_t)par, 0, 4000);
       tc_fence_after();
       uint32_t ov[OC];
+      const uint32_t t_o = t_g + (uint32_t)(par * 128 + hh * HD + hf * OC);
 #pragma unroll
       for (int c = 0; c < OC / 16; ++c) tmem_ld16(t_o + (uint32_t)(c * 16), *reinterpret_cast<uint32_t(*)[16]>(&ov[c * 16]));
       tmem_ld_wait();
@@ -278,6 +295,8 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
       asm volatile("bar.sync %0, 256;" ::"r"(3 + g) : "memory");   // both halves of every row sum are in shared memory
       l += xl[(hf ^ 1) * 128 + r];
       if (r < p.Lt) {
+        const int item = item0 + n * item_inc;
+        const int b = item / p.n_slabs, slab = item - b * p.n_slabs;
         const float inv = 1.f / l;
         bf16* op = p.out + ((int64_t)b * p.Lt + r) * p.out_stride + (slab * NH + hh) * HD + hf * OC;
 #pragma unroll
