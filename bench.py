@@ -9,7 +9,9 @@ seeded synthetic weights (BN-calibrated; findtextcenternet_b200/synthetic.py).  
 
 `value`   : images/s with the batch already resident in HBM (CUDA events, max over ranks, L2 flushed between steps).
 `e2e`     : images/s through OCR_b200_Processer.detect_tiles: pinned HOST float32 NHWC 0..255 tiles -> H2D -> detector
-            -> on-device peak compaction/box decode -> D2H of (count, locations, glyphfeatures), all inside the timed region.
+            -> on-device peak compaction/box decode -> D2H of (count, locations, glyphfeatures), all inside the timed region,
+            every step (one synchronous call per step; inside the call the upload is cut in pieces and the first layers of a
+            piece run while the next one crosses PCIe: engine.forward_from_host, bit-identical to the one-copy forward).
 `roofline`: tensor-pipe bound.  achieved = algorithmic FLOPs of the dominant kernel family (the tcgen05 implicit-GEMM
             convolution, every dense conv launch of one forward) / the summed CUDA-event durations of those launches,
             measured live by ftc_detector_forward_timed; peak = MEASURED_PEAKS.json bf16_tflops_sustained.
@@ -299,7 +301,7 @@ def run_ours(args):
                    "l2": "256 MiB flush buffer written between timed steps", "wall_s_timed_region": t_wall},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "OCR_b200_Processer.detect_tiles(pinned float32 NHWC 0..255 tiles)", "steps": e2e_steps,
+                "api": "OCR_b200_Processer.detect_tiles(pinned float32 NHWC 0..255 tiles); the upload crosses PCIe in 8 pieces, stem + features[1..3] of a piece run while the next is in flight (ftc_detector_forward_part)", "steps": e2e_steps,
                 "uint8_tiles": {"value": e2e_u8_value, "unit": "images/s", "h2d_bytes_per_step": h2d_u8,
                                 "note": "same call, host tiles as uint8 (the page's own type): cast to float on the device"}},
         "gpu_launches": launches,

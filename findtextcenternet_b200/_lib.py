@@ -21,6 +21,7 @@ GEMM_SIMT, GEMM_TCGEN05, GEMM_TCGEN05_IM2COL = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_SWIGLU = 0, 1, 2, 3
 DT_F32, DT_BF16 = 0, 1
 INPUT_NCHW_UNIT, INPUT_NHWC_255 = 0, 1
+PART_EARLY, PART_REST = 1, 2
 
 
 class StageCfg(C.Structure):
@@ -60,6 +61,7 @@ SYMBOLS = {
     "ftc_detector_workspace_bytes": (_sz, [_vp, _i]),
     "ftc_detector_pack_weights": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(_i64), _vp, _sz, _vp]),
     "ftc_detector_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ftc_detector_forward_part": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ftc_detector_set_input_format": (_i, [_vp, _i]),
     "ftc_detector_num_ops": (_i, [_vp]),
     "ftc_detector_forward_timed": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _i, C.POINTER(C.c_float),

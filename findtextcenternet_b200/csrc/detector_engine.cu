@@ -83,6 +83,7 @@ struct ftc_detector {
   char* packed = nullptr;              // bound at pack time
   int input_format = 0;                // FTC_INPUT_*
   int Hq = 0, Wq = 0;                  // output resolution (H/4)
+  int early_end = 0;                   // ops [0, early_end) = stem + features[1..3]: their surviving outputs (taps x1, x2) live in buffers of their own
   int tapC[4] = {0, 0, 0, 0}, tapH[4] = {0, 0, 0, 0}, tapW[4] = {0, 0, 0, 0};
 
   size_t walloc(size_t bytes) { size_t o = weight_bytes; weight_bytes = align_up(weight_bytes + bytes, 256); return o; }
@@ -258,6 +259,7 @@ int ftc_detector::build() {
       cur = out; H = Ho; W = Wo;
     }
     if (is_tap_stage) { tap_C[ntap] = st.cout; tap_H[ntap] = H; ++ntap; }
+    if (si + 1 == 3) early_end = (int)ops.size();
   }
   FTC_REQUIRE(ntap == 3, "expected three intermediate taps");
   add_conv_bn("backbone.features." + std::to_string(c.n_stages + 1), cur, BUF_T4, c.stages[c.n_stages - 1].cout,
@@ -422,10 +424,21 @@ static double op_flops(const Op& op, int B) {
   return 0.0;
 }
 
+// Runs ops [op_lo, op_hi) on images [i0, i0 + nb) of a batch of B (every activation tensor is [B][pixels][channels]: a range of
+// images is a pointer offset per tensor).  i0 > 0 / nb < B only for the early ops (op_hi <= early_end): their intermediate
+// tensors share the ping-pong buffers with different per-image sizes, so image ranges of DIFFERENT ops may overlap there; the
+// early ops of one range run to completion before the next range starts, and what survives them (taps x1, x2) sits in buffers
+// that hold one tensor only.
 static int detector_forward_impl(ftc_detector* d, const float* images, int B, float* heat9, float* feat, float* heat10,
-                                 void* workspace, size_t ws_bytes, cudaStream_t s, cudaEvent_t* ev = nullptr) {
+                                 void* workspace, size_t ws_bytes, cudaStream_t s, cudaEvent_t* ev = nullptr, int op_lo = 0,
+                                 int op_hi = -1, int i0 = 0, int nb = -1) {
   FTC_REQUIRE(d->packed != nullptr, "ftc_detector_pack_weights must be called before forward");
   FTC_REQUIRE(ws_bytes >= ftc_detector_workspace_bytes(d, B), "workspace too small");
+  const int n_ops = (int)d->ops.size();
+  if (op_hi < 0) op_hi = n_ops;
+  if (nb < 0) nb = B;
+  FTC_REQUIRE(op_lo >= 0 && op_lo <= op_hi && op_hi <= n_ops && i0 >= 0 && nb > 0 && i0 + nb <= B, "bad op / image range");
+  FTC_REQUIRE((i0 == 0 && nb == B) || op_hi <= d->early_end, "image ranges are for the early ops only");
   char* ws = (char*)workspace;
   char* bufp[BUF_COUNT];
   size_t off = 0;
@@ -436,55 +449,59 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
   float* se_scale = (float*)(ws + off); off += align_up(d->se_c_max * B * 4, 256);
   float* se_hid = (float*)(ws + off); off += align_up((size_t)256 * B * 4, 256);
   float* se_hid2 = (float*)(ws + off); off += align_up(d->se_hid_part_max * B * 4, 256);  // [B][C/32][S] fc1 shares (fused path)
-  auto bp = [&](int id) -> void* {
+  const size_t es = d->esize;
+  auto bp = [&](int id, size_t pix = 0, size_t stride = 0) -> void* {      // image i0 of the [B][pix][stride] tensor in buffer id
     if (id == BUF_NONE) return nullptr;
     if (id == BUF_EXT_HEAT9) return heat9;
     if (id == BUF_EXT_FEAT) return feat;
-    return bufp[id];
+    return bufp[id] + (size_t)i0 * pix * stride * es;
   };
   char* P = d->packed;
-  int op_index = 0;
-  for (const Op& op : d->ops) {
+  for (int oi = op_lo; oi < op_hi; ++oi) {
+    const Op& op = d->ops[oi];
     int rc = 0;
-    if (ev) FTC_CHECK_CUDA(cudaEventRecord(ev[op_index], s));
-    ++op_index;
+    if (ev) FTC_CHECK_CUDA(cudaEventRecord(ev[oi], s));
     switch (op.type) {
       case Op::STEM:
-        rc = stem_conv(images, d->input_format, bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, (const float*)(P + op.w_off),
-                       (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), s);
+        rc = stem_conv(images + (size_t)i0 * 3 * op.H * op.W, d->input_format, bp(op.bufOut, (size_t)(op.H / 2) * (op.W / 2), op.C), d->dtype, nb,
+                       op.H, op.W, op.C, (const float*)(P + op.w_off), (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), s);
         break;
-      case Op::DW:
+      case Op::DW: {
+        const int Ho = (op.H - 1) / op.stride + 1, Wo = (op.W - 1) / op.stride + 1;
+        void* in = bp(op.bufIn, (size_t)op.H * op.W, op.C);
+        void* out = bp(op.bufOut, (size_t)Ho * Wo, op.C);
         if (op.fused_se)
-          rc = dwconv3x3_se(bp(op.bufIn), bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, (const float*)(P + op.w_off),
+          rc = dwconv3x3_se(in, out, d->dtype, nb, op.H, op.W, op.C, (const float*)(P + op.w_off),
                             (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), (const float*)(P + op.se_w1_off),
                             op.S, se_hid2, s);
         else
-          rc = dwconv3x3(bp(op.bufIn), bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, op.stride, (const float*)(P + op.w_off),
+          rc = dwconv3x3(in, out, d->dtype, nb, op.H, op.W, op.C, op.stride, (const float*)(P + op.w_off),
                          (const float*)(P + op.scale_off), (const float*)(P + op.bias_off), se_sum, s);
         break;
+      }
       case Op::SE:
         if (op.fused_se)
-          rc = se_fc2_hid(se_hid2, op.C / 32, se_scale, B, op.C,
+          rc = se_fc2_hid(se_hid2, op.C / 32, se_scale, nb, op.C,
                           op.S, (const float*)(P + op.b1_off), (const float*)(P + op.w2_off), (const float*)(P + op.b2_off), s);
         else
-          rc = se_fc(se_sum, op.parity /* = tile count of the depthwise kernel */, se_scale, se_hid, B, op.C, op.S, 1.0f / (float)(op.H * op.W), (const float*)(P + op.w_off),
+          rc = se_fc(se_sum, op.parity /* = tile count of the depthwise kernel */, se_scale, se_hid, nb, op.C, op.S, 1.0f / (float)(op.H * op.W), (const float*)(P + op.w_off),
                      (const float*)(P + op.b1_off), (const float*)(P + op.w2_off), (const float*)(P + op.b2_off), s);
         break;
       case Op::TOPS:
         rc = head_top_conv(bp(op.bufIn), d->dtype, op.pix_stride, op.head0, op.n_heads, op.od, (const float*)(P + op.w_off),
-                           (const float*)(P + op.bias_off), heat9, op.out_ch, B, op.H, op.W, s);
+                           (const float*)(P + op.bias_off), heat9, op.out_ch, nb, op.H, op.W, s);
         break;
       case Op::UP:
-        rc = upsample2x(bp(op.bufIn), bp(op.bufOut), d->dtype, B, op.H, op.W, op.C, s);
+        rc = upsample2x(bp(op.bufIn), bp(op.bufOut), d->dtype, nb, op.H, op.W, op.C, s);
         break;
       case Op::GEMM: {
         const GemmOp& g = op.g;
         ConvGemmParams p;
         memset(&p, 0, sizeof(p));
-        p.B = B; p.H = g.H; p.W = g.W; p.Ho = g.Ho; p.Wo = g.Wo; p.stride = g.stride; p.pad = (g.ksize - 1) / 2;
-        p.M = B * g.Ho * g.Wo; p.N = g.N; p.G = g.G; p.K = g.K;
-        p.srcA = bp(g.bufA); p.a_pix_stride = g.a_pix_stride; p.a_ch_off = 0;
-        p.srcB = bp(g.bufB); p.b_pix_stride = g.b_pix_stride; p.b_ch_off = g.b_ch_off; p.b_group_stride = g.b_group_stride;
+        p.B = nb; p.H = g.H; p.W = g.W; p.Ho = g.Ho; p.Wo = g.Wo; p.stride = g.stride; p.pad = (g.ksize - 1) / 2;
+        p.M = nb * g.Ho * g.Wo; p.N = g.N; p.G = g.G; p.K = g.K;
+        p.srcA = bp(g.bufA, (size_t)g.H * g.W, g.a_pix_stride); p.a_pix_stride = g.a_pix_stride; p.a_ch_off = 0;
+        p.srcB = bp(g.bufB, (size_t)g.H * g.W, g.b_pix_stride); p.b_pix_stride = g.b_pix_stride; p.b_ch_off = g.b_ch_off; p.b_group_stride = g.b_group_stride;
         p.CA = g.CA; p.CB = g.CB;
         p.ktab = (const uint32_t*)(P + g.ktab_off);
         p.a_scale = g.se ? se_scale : nullptr; p.a_scale_stride = g.CA;
@@ -492,9 +509,10 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
         p.scale = g.has_scale ? (const float*)(P + g.scale_off) : nullptr;
         p.bias_tab = (const float*)(P + g.bias_off); p.ncase = g.ncase;
         p.act = g.act;
-        p.res1 = bp(g.bufRes); p.res1_stride = g.res_stride; p.res1_row_mod = 0;
+        p.res1 = bp(g.bufRes, (size_t)g.Ho * g.Wo, g.res_stride); p.res1_stride = g.res_stride; p.res1_row_mod = 0;
         p.res2 = nullptr; p.res2_stride = 0;
-        p.out = bp(g.bufOut); p.out_layout = g.out_layout; p.out_stride = g.out_stride;
+        p.out = g.out_layout == OUT_NHWC ? bp(g.bufOut, (size_t)g.Ho * g.Wo, g.out_stride) : bp(g.bufOut);
+        p.out_layout = g.out_layout; p.out_stride = g.out_stride;
         for (int i = 0; i < MAX_GROUPS; ++i) { p.out_ch_base[i] = g.out_ch_base[i]; p.n_valid[i] = g.n_valid[i]; }
         p.dtype = d->dtype;
         p.tc = g.tc;
@@ -505,8 +523,8 @@ static int detector_forward_impl(ftc_detector* d, const float* images, int B, fl
     }
     if (rc) return rc;
   }
-  if (ev) FTC_CHECK_CUDA(cudaEventRecord(ev[op_index], s));
-  if (heat10) return peak_pick(heat9, heat10, B, d->Hq, d->Wq, s);
+  if (ev && op_hi == n_ops) FTC_CHECK_CUDA(cudaEventRecord(ev[n_ops], s));
+  if (heat10 && op_hi == n_ops) return peak_pick(heat9, heat10, B, d->Hq, d->Wq, s);
   return 0;
 }
 
@@ -596,6 +614,17 @@ int ftc_detector_pack_weights(ftc_detector* d, int n, const char* const* names, 
   FTC_CHECK_CUDA(cudaStreamSynchronize(s));
   d->packed = (char*)packed;
   return 0;
+}
+
+int ftc_detector_forward_part(ftc_detector* d, const float* images, int batch, int part, int image0, int n_images, float* heat9,
+                              float* feat, float* heat10, void* workspace, size_t workspace_bytes, void* stream) {
+  FTC_REQUIRE(d && images && workspace && batch > 0 && (part == FTC_PART_EARLY || part == FTC_PART_REST), "bad argument");
+  if (part == FTC_PART_EARLY)
+    return detector_forward_impl(d, images, batch, nullptr, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream, nullptr,
+                                 0, d->early_end, image0, n_images);
+  FTC_REQUIRE(heat9 && feat, "bad argument");
+  return detector_forward_impl(d, images, batch, heat9, feat, heat10, workspace, workspace_bytes, (cudaStream_t)stream, nullptr,
+                               d->early_end, -1, 0, batch);
 }
 
 int ftc_detector_forward(ftc_detector* d, const float* images, int batch, float* heat9, float* feat, float* heat10,

@@ -115,6 +115,63 @@ class DetectorEngine:
                                                      _stream_ptr(self.device)), "ftc_detector_forward")
         return heat9, feat, heat10
 
+    def forward_from_host(self, tiles: torch.Tensor, want_heat10: bool = False, chunks: Optional[int] = None
+                          ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+        """``forward(nhwc255=True)`` for HOST tiles [B,768,768,3] (float32 0..255 or uint8; pinned for a truly asynchronous copy)
+        with the upload hidden behind the first layers: the batch crosses PCIe in ``chunks`` pieces on a copy stream, and the
+        stem + features[1..3] of a piece (``ftc_detector_forward_part(FTC_PART_EARLY)``) run as soon as it has landed, i.e. while
+        the next piece is still in flight; the rest of the network then runs on the whole batch.  Results are bit-identical to
+        ``forward`` (the same kernels on the same images; every layer is per-image)."""
+        if tiles.device.type != "cpu":
+            raise RuntimeError("forward_from_host takes host tiles; use forward() for device tensors")
+        if self.packed is None:
+            raise RuntimeError("weights not packed")
+        b = tiles.shape[0]
+        want = (self.height, self.width, 3)
+        if tiles.dim() != 4 or tuple(tiles.shape[1:]) != want or tiles.dtype not in (torch.float32, torch.uint8):
+            raise ValueError(f"expected float32 / uint8 [B,{want[0]},{want[1]},{want[2]}], got {tiles.dtype} {tuple(tiles.shape)}")
+        tiles = tiles.contiguous()
+        _lib.check(self.lib.ftc_detector_set_input_format(self.handle, _lib.INPUT_NHWC_255), "ftc_detector_set_input_format")
+        if getattr(self, "_in_dev", None) is None or self._in_dev.shape[0] < b:
+            self._in_dev = torch.empty(b, *want, dtype=torch.float32, device=self.device)
+            self._in_u8 = None
+            self._copy_stream = torch.cuda.Stream(self.device)
+        x = self._in_dev[:b]
+        stage = None
+        if tiles.dtype == torch.uint8:      # a quarter of the bytes cross the bus; cast to float on the device, piece by piece
+            if self._in_u8 is None or self._in_u8.shape[0] < b:
+                self._in_u8 = torch.empty(b, *want, dtype=torch.uint8, device=self.device)
+            stage = self._in_u8[:b]
+        heat9, feat, heat10 = self._outputs(b, want_heat10)
+        ws = self._workspace(b)
+        main = torch.cuda.current_stream(self.device)
+        cs = self._copy_stream
+        if chunks is None:   # measured at batch 32 (tools/ab_upload_chunks.sh): float32 tiles 2 / 4 / 8 / 16 pieces -> 96.4 / 95.5 / 98.5 / 95.9 % of the
+            # kernel-only rate (93 % with one copy first); uint8 tiles have a quarter of the bytes to hide: 2 pieces
+            chunks = int(os.environ.get("FTC_UPLOAD_CHUNKS", "8" if tiles.dtype == torch.float32 else "2"))
+        n = max(1, min(chunks, b))
+        bounds = [(i * b) // n for i in range(n + 1)]
+        cs.wait_stream(main)                 # the previous call's kernels may still be reading the input buffer
+        with torch.cuda.device(self.device):
+            for i in range(n):
+                lo, hi = bounds[i], bounds[i + 1]
+                if hi == lo:
+                    continue
+                with torch.cuda.stream(cs):
+                    (stage if stage is not None else x)[lo:hi].copy_(tiles[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                main.wait_event(ev)
+                if stage is not None:
+                    x[lo:hi].copy_(stage[lo:hi])
+                _lib.check(self.lib.ftc_detector_forward_part(self.handle, x.data_ptr(), b, _lib.PART_EARLY, lo, hi - lo, None, None, None,
+                                                              ws.data_ptr(), ws.numel(), _stream_ptr(self.device)),
+                           "ftc_detector_forward_part(early)")
+            _lib.check(self.lib.ftc_detector_forward_part(self.handle, x.data_ptr(), b, _lib.PART_REST, 0, b, heat9.data_ptr(), feat.data_ptr(),
+                                                          heat10.data_ptr() if want_heat10 else None, ws.data_ptr(), ws.numel(),
+                                                          _stream_ptr(self.device)), "ftc_detector_forward_part(rest)")
+        return heat9, feat, heat10
+
     def forward_timed(self, images: torch.Tensor):
         """One forward with CUDA events around every op: list of (kind, ms, flops).  Measurement only."""
         x = self._check_input(images, False)

@@ -75,6 +75,7 @@ class OCR_b200_Processer(_Base):
         detector.eval()
         self.detector = detector
         self.precision = precision
+        self.overlap_upload = True     # detect_tiles: host tiles are uploaded in pieces under the first layers (False: one copy first)
         self.transformer = None
         self._transformer_args = (transformer_state_dict, transformer_config)
 
@@ -121,12 +122,15 @@ class OCR_b200_Processer(_Base):
         tile with more peaks keeps its ``max_peaks`` highest-scoring ones (deterministic) and, with ``on_overflow="raise"``
         (default), raises ``OverflowError`` so boxes are never lost silently; ``"truncate"`` accepts the top-``max_peaks``
         result (``self.last_total`` holds the uncapped per-tile counts either way)."""
-        x = tiles.to(self.device, non_blocking=True)
         eng = self.detector.detector.engine(self.device)
         meta = torch.tensor([tile_meta(ox, oy, page_w, page_h, self.step_ratio) for ox, oy in offsets], dtype=torch.int32)
         meta = meta.to(self.device, non_blocking=True)
         with torch.no_grad():
-            heat9, feat, _ = eng.forward(x, False, nhwc255=True)
+            if tiles.device.type == "cpu" and self.overlap_upload:
+                # host tiles: the upload is cut in pieces and hidden behind the first layers (engine.forward_from_host)
+                heat9, feat, _ = eng.forward_from_host(tiles, False)
+            else:
+                heat9, feat, _ = eng.forward(tiles.to(self.device, non_blocking=True), False, nhwc255=True)
             count, loc, gfeat, total = peak_decode(heat9, feat, meta, page_w, page_h, self.cut_off, max_peaks)
             if maps is not None:     # device tensor [7, page_h/4, page_w/4]: merge this batch's tiles into the page maps
                 page_maps(heat9, meta, page_h, page_w, out=maps)

@@ -69,6 +69,16 @@ int ftc_detector_pack_weights(ftc_detector* d, int n, const char* const* names, 
  * heat10 (optional, may be NULL): [B,10,H/4,W/4] = CenterNetDetector output with the peak channel. */
 int ftc_detector_forward(ftc_detector* d, const float* images, int batch, float* heat9, float* feat, float* heat10,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* The same forward in two parts, so that the host -> device copy of a batch of tiles (process_ocr_base.py:487-497 hands
+ * run_detector host float32 tiles; 226 MB for 32 of them) overlaps the first layers:
+ *   FTC_PART_EARLY: stem + backbone.features[1..3] (models/detector.py:139-146) for images [image0, image0 + n_images) of the
+ *                   batch -- call it per chunk of images as soon as that chunk has arrived in `images` (device, full-batch base
+ *                   pointer); heat9 / feat / heat10 are not touched (may be NULL);
+ *   FTC_PART_REST : everything after features[3] for the whole batch (image0 = 0, n_images = batch), outputs as ftc_detector_forward.
+ * EARLY over every image followed by REST is bit-identical to ftc_detector_forward. */
+enum { FTC_PART_EARLY = 1, FTC_PART_REST = 2 };
+int ftc_detector_forward_part(ftc_detector* d, const float* images, int batch, int part, int image0, int n_images, float* heat9,
+                              float* feat, float* heat10, void* workspace, size_t workspace_bytes, void* stream);
 
 int ftc_detector_set_input_format(ftc_detector* d, int fmt);
 /* measurement: same forward with a CUDA-event pair around every op of the plan (synchronises the stream).

@@ -206,3 +206,26 @@ def test_full_size_properties_at_the_benchmarked_configuration(model):
     expect = torch.where(key < pooled, torch.full_like(key, float("-inf")), key)
     assert torch.equal(h10[:, 1:2], expect)
     assert torch.isfinite(h10[:, [0] + list(range(2, 10))]).all() and torch.isfinite(feat).all()
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_upload_overlapped_forward_is_bit_identical(model, prec):
+    """engine.forward_from_host (the path of detect_tiles for host tiles: the batch crosses PCIe in pieces and
+    ftc_detector_forward_part(FTC_PART_EARLY) runs stem + features[1..3] per piece, FTC_PART_REST the rest on the whole batch)
+    against the one-piece forward on the same tiles: bit-identical maps for float32 and uint8 host tiles, a ragged split
+    (9 images in 4 pieces), more pieces than images, and one piece."""
+    m, det = model
+    m.detector.set_precision(prec)
+    eng = m.detector.engine(torch.device("cuda", torch.cuda.current_device()))
+    g = torch.Generator().manual_seed(5)
+    b = 9 if prec == "bf16" else 3
+    tiles_u8 = torch.randint(0, 256, (b, 768, 768, 3), generator=g, dtype=torch.uint8)
+    tiles_f = tiles_u8.float().pin_memory()
+    with torch.no_grad():
+        ref9, reff, _ = eng.forward(tiles_f.cuda(), False, nhwc255=True)
+        ref9, reff = ref9.clone(), reff.clone()
+        for tiles, chunks in ((tiles_f, 4), (tiles_u8.pin_memory(), 4), (tiles_f, 16), (tiles_f, 1)):
+            h9, ft, _ = eng.forward_from_host(tiles, False, chunks=chunks)
+            torch.cuda.synchronize()
+            assert torch.equal(h9, ref9) and torch.equal(ft, reff), f"{tiles.dtype} tiles in {chunks} pieces differ from the one-piece forward"
+    m.detector.set_precision("bf16")
