@@ -122,7 +122,7 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
       uint32_t ph = 1;                             // parity that passes on a fresh barrier
       int item = first;
       for (int j = 0; j < n_my; ++j, item += step) {
-        mbar_wait(bar(AB_EMPTY, stage), ph);
+        mbar_wait(bar(AB_EMPTY, stage), ph, 0, 2000);   // hinted waits: a spinning control warp takes issue slots from the softmax warps of its scheduler
         const int b = item / p.n_slabs, slab = item - b * p.n_slabs;
         const uint32_t st = sbase + (uint32_t)stage * AT_STAGE, fb = bar(AB_FULL, stage);
         mbar_arrive_expect_tx(fb, AT_STAGE);
@@ -154,7 +154,7 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
       uint32_t ph = 0;
       int pv_stage = stage;                        // stage of the item of the next P.V product
       auto issue_s = [&](int k) {                  // score product of task k into S[k & 1]
-        mbar_wait(bar(AB_FULL, stage), ph);
+        mbar_wait(bar(AB_FULL, stage), ph, 0, 1000);
         tc_fence_after();
         const uint64_t so = (uint64_t)((uint32_t)stage * (AT_STAGE >> 4));
 #pragma unroll
@@ -167,7 +167,7 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
       issue_s(0);
       if (n_tasks > 1) issue_s(1);
       for (int n = 0; n < n_tasks; ++n) {
-        mbar_wait(bar(AB_PREADY, g), (uint32_t)(n & 1));
+        mbar_wait(bar(AB_PREADY, g), (uint32_t)(n & 1), 0, 1000);
         tc_fence_after();
         const uint64_t vo = dv0 + (uint64_t)((uint32_t)pv_stage * (AT_STAGE >> 4));
         const uint32_t t_o = t_g + (uint32_t)((n & 1) * 128);
@@ -181,7 +181,7 @@ attention_tc_kernel(const __grid_constant__ AttTcParams p, const __grid_constant
         if (pv_stage >= AT_NSTAGE) pv_stage -= AT_NSTAGE;
         // score product n + 2 reuses S[n & 1]: the group must have read O(n) out of it
         if (n + 2 < n_tasks) {
-          mbar_wait(bar(AB_OCONS, g), (uint32_t)(n & 1));
+          mbar_wait(bar(AB_OCONS, g), (uint32_t)(n & 1), 0, 1000);
           issue_s(n + 2);
         }
       }
