@@ -253,3 +253,29 @@ def test_chunk_planner_matches_the_reference_loop():
         txt, linebuf = ocr_text.assemble_text(chunks, preds)
         assert txt == g["result_txt"], name
         assert [[a, b, c] for a, b, c in linebuf] == g["linebuf"], name
+
+
+def test_forward_part_argument_checks_need_no_gpu():
+    """ftc_detector_forward_part (include/ftc_b200.h: the forward in two parts so that the upload of host tiles overlaps the
+    first layers) rejects bad parts / unpacked plans with an error code and a message before any CUDA call."""
+    import ctypes as C
+    from findtextcenternet_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.make_detector_config("xl", 1, 1, 768, 768)      # bf16, tcgen05: the plan is host arithmetic only
+    h = C.c_void_p()
+    assert lib.ftc_detector_create(C.byref(cfg), C.byref(h)) == 0
+    try:
+        fake = C.c_void_p(256)
+        ws = lib.ftc_detector_workspace_bytes(h, 4)
+        assert ws > 0
+        # unknown part
+        assert lib.ftc_detector_forward_part(h, fake, 4, 7, 0, 4, fake, fake, None, fake, ws, None) != 0
+        # null images
+        assert lib.ftc_detector_forward_part(h, None, 4, _lib.PART_EARLY, 0, 4, None, None, None, fake, ws, None) != 0
+        # weights not packed: refused before anything is launched
+        assert lib.ftc_detector_forward_part(h, fake, 4, _lib.PART_EARLY, 0, 2, None, None, None, fake, ws, None) != 0
+        assert b"pack_weights" in lib.ftc_last_error()
+        # the second part needs the output maps
+        assert lib.ftc_detector_forward_part(h, fake, 4, _lib.PART_REST, 0, 4, None, None, None, fake, ws, None) != 0
+    finally:
+        lib.ftc_detector_destroy(h)
